@@ -1,0 +1,156 @@
+/*
+ * map2d_b200.h — C-ABI of the B200-native Map2DFusion feed() hot path.
+ *
+ * This is the drop-in boundary: every entry point below replaces one member of the reference's
+ * `Map2D` plugin interface (reference paths are relative to the pi-slam-fusion tree) and is what a
+ * `class Map2DB200 : public Map2D` adapter (see include/Map2DB200.h) binds to.
+ *
+ *   reference (C++, Map2DFusion/)                         this library (extern "C")
+ *   ----------------------------------------------------  ------------------------------------------
+ *   Map2D::create(type,thread)          Map2D.cpp:51-66   m2d_create
+ *   Map2D::prepare(plane,camera,frames) Map2D.h:88-89     m2d_prepare
+ *     Map2DPrepare::prepare             Map2D.cpp:32-49
+ *     Map2DCPUData::prepare             Map2DCPU.cpp:44-92 / MultiBandMap2DCPU.cpp:199-255
+ *   Map2D::feed(img,pose)               Map2D.h:91        m2d_feed / m2d_feed_device / m2d_feed_batch
+ *     Map2DCPU::renderFrame             Map2DCPU.cpp:150-336
+ *     MultiBandMap2DCPU::renderFrame    MultiBandMap2DCPU.cpp:311-558
+ *   Map2D::save(filename)               Map2D.h:95        m2d_save, m2d_get_image (in-memory variant)
+ *     Map2DCPU::save                    Map2DCPU.cpp:523-564
+ *     MultiBandMap2DCPU::save           MultiBandMap2DCPU.cpp:779-847
+ *   Map2D::queueSize()                  Map2D.h:97        m2d_queue_size
+ *   (raw tile state; the reference has no getter)         m2d_get_tile  (for bit-exact parity tests)
+ *   legacy seam renderFramesCaller      UtilGPU.cuh:114-124  (shape of the old C++->CUDA call; NOT ported)
+ *
+ * Conventions: plain pointers and sizes only; no exceptions cross the ABI; every call returns an int
+ * status (M2D_OK == the reference returning true, M2D_REJECTED == the reference returning false, <0 ==
+ * an error the reference could not have produced, e.g. a CUDA failure). The library never calls exit().
+ * Poses are 7 doubles in the reference's stream order `x y z qx qy qz qw` (GSLAM/core/SE3.h:105-117),
+ * camera-to-world for frames, plane-to-world for the plane. Cameras are the 6 doubles of
+ * PinHoleParameters `w h fx fy cx cy` (Map2D.h:37-43). Images are 8-bit BGR, row-major.
+ */
+#ifndef MAP2D_B200_H
+#define MAP2D_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define M2D_ELE_PIXELS 256 /* Map2D.h:35  ELE_PIXELS */
+#define M2D_MAX_LEVELS 9   /* BandNumber is clamped to ceil(log2(256)) = 8 -> 9 stored levels */
+
+/* Map2D::Map2DType, Map2D.h:83. TypeGPU(2) behaves like TypeCPU(1): the reference build has no CUDA and
+ * create(TypeGPU) hands back a Map2DCPU (Map2D.cpp:57-65). TypeRender(4) is out of scope. */
+enum { M2D_TYPE_NONE = 0, M2D_TYPE_CPU = 1, M2D_TYPE_GPU = 2, M2D_TYPE_MULTIBAND = 3, M2D_TYPE_RENDER = 4 };
+
+#define M2D_OK 0
+#define M2D_REJECTED 1         /* the reference's `return false` from prepare()/feed()/save() */
+#define M2D_ERR_ARG (-1)
+#define M2D_ERR_STATE (-2)
+#define M2D_ERR_CUDA (-3)
+#define M2D_ERR_NOMEM (-4)
+#define M2D_ERR_UNSUPPORTED (-5)
+#define M2D_ERR_IO (-6)
+
+/* The svar keys the hot path reads, as one plain struct. */
+typedef struct m2d_config {
+    double scale;        /* Map2D.Scale       (Map2DCPU.cpp:75)                      default 1   */
+    double resolution;   /* Map2D.Resolution  (MultiBandMap2DCPU.cpp:228), 0 = auto  default 0   */
+    int weight_type;     /* Map2D.WeightType  (Map2DCPU.cpp:246)                     default 0   */
+    int band_number;     /* MultiBandMap2DCPU.BandNumber (MultiBandMap2DCPU.cpp:260) default 5   */
+    int force_float;     /* MultiBandMap2DCPU.ForceFloat (:444) — must be 0 (int16 path only)    */
+    int background;      /* Result.BackGroundColor (:840)                            default 0   */
+    int thread;          /* Map2D.Thread: 0 = feed() returns after the work is enqueued AND bounds are
+                            decided (reference thread=false semantics, result-equivalent); non-zero is
+                            accepted and treated the same: there is no drop-oldest queue on the GPU. */
+    int device;          /* CUDA device ordinal                                       default 0   */
+    /* Spatial tile ownership for multi-GPU runs. Tiles are keyed on ABSOLUTE tile
+     * coordinates (anchored at prepare(), stable under spreadMap). owner = floor(abs / shard_span) mod
+     * shard_count along shard_axis (0 = x, 1 = y). shard_count <= 1 owns everything. */
+    int shard_rank, shard_count, shard_axis, shard_span;
+    int collect_stats;   /* non-zero: kernels also count winners (for algorithmic-byte accounting) */
+    int batch_frames;    /* frames fused per launch group in m2d_feed_batch (0 = library default) */
+} m2d_config;
+
+/* Algorithmic-traffic counters, SURVEY.md §8(d). Filled by the oracle always and by the CUDA library when
+ * collect_stats != 0. Index = pyramid level (weighted mode uses level 0 only). */
+typedef struct m2d_stats {
+    uint64_t frames_fed, frames_fused;
+    uint64_t input_px;                     /* sum of W*H over fused frames                        */
+    uint64_t region_px[M2D_MAX_LEVELS];    /* D_l summed over fused frames (owned tiles only)     */
+    uint64_t fresh_px[M2D_MAX_LEVELS];     /* px of D_l that fell in first-touch tiles            */
+    uint64_t win_px[M2D_MAX_LEVELS];       /* px of non-fresh tiles where the frame replaced state */
+    uint64_t footprint_px;                 /* weighted: region px with warped alpha > 0            */
+} m2d_stats;
+
+typedef struct m2d_map* m2d_handle;
+
+void m2d_config_default(m2d_config* cfg);
+
+/* Map2D::create — Map2D.cpp:51-66. type NONE/RENDER -> M2D_ERR_UNSUPPORTED and *out = NULL. */
+int m2d_create(int type, const m2d_config* cfg, m2d_handle* out);
+void m2d_destroy(m2d_handle h);
+
+/* Map2D::prepare — only the poses of the prepare-frames are used to lay out the tile grid
+ * (Map2DCPU.cpp:50-61). M2D_REJECTED when the reference returns false (no frames, bad camera,
+ * camera heights straddling the plane). */
+int m2d_prepare(m2d_handle h, const double plane[7], const double camera[6], int n_frames,
+                const double* poses /* n_frames x 7 */);
+
+/* Map2D::feed — host image (pageable or pinned). stride in bytes. Returns after the frame's work is
+ * enqueued on the handle's stream; the host buffer may be reused immediately (it is staged). */
+int m2d_feed(m2d_handle h, const uint8_t* bgr, int w, int h_px, size_t stride, const double pose_c2w[7]);
+/* Same, the image already lives in device memory (must stay valid until m2d_sync). */
+int m2d_feed_device(m2d_handle h, const uint8_t* d_bgr, int w, int h_px, size_t stride,
+                    const double pose_c2w[7]);
+/* n frames, frame i at base + i*frame_stride; result[i] receives the per-frame status (may be NULL).
+ * Semantics are exactly n sequential feed() calls; internally frames are grouped so that each map tile is
+ * read and written once per group. */
+int m2d_feed_batch(m2d_handle h, int n, const uint8_t* base, size_t frame_stride, int w, int h_px,
+                   size_t stride, const double* poses /* n x 7 */, int on_device, int* result);
+
+int m2d_sync(m2d_handle h);
+int m2d_queue_size(m2d_handle h);                 /* frames enqueued and not yet finished on the GPU */
+int m2d_set_stream(m2d_handle h, void* cuda_stream /* cudaStream_t, NULL = library-owned */);
+int m2d_reset(m2d_handle h);                      /* drop all tiles, keep the prepared grid */
+
+/* Grid as laid out by prepare()/spreadMap (Map2DCPUData: _w,_h,_min,_max,_lengthPixel). */
+int m2d_get_grid(m2d_handle h, int* w, int* h_tiles, double min_xyz[3], double max_xyz[3],
+                 double* length_pixel);
+/* Tile rectangle (xminInt,yminInt,xmaxInt,ymaxInt) of the most recent accepted feed (Map2DCPU.cpp:219-222),
+ * in the CURRENT grid indexing. */
+int m2d_last_rect(m2d_handle h, int rect[4]);
+/* Raw tile state. Weighted: level must be 0, `data` receives 256*256*4 u8 BGRA, `weight` unused.
+ * Multi-band: `data` receives n*n*3 int16 (interleaved BGR Laplacian, n = 256>>level), `weight` n*n f32.
+ * M2D_REJECTED if the tile was never touched (or is not owned by this shard). */
+int m2d_get_tile(m2d_handle h, int tx, int ty, int level, void* data, float* weight);
+/* In-memory save(): bbox of touched tiles. Call with out == NULL to get the geometry, then with a buffer of
+ * w*h*channels bytes. Weighted -> 4 channels BGRA (untouched tiles zero); multi-band -> 3 channels BGR,
+ * collapsed, background where weight[0]==0. */
+int m2d_get_image(m2d_handle h, uint8_t* out, int* w, int* h_px, int* channels, int* tile_min_x,
+                  int* tile_min_y);
+/* Map2D::save — writes the same image as a PNG (8-bit BGRA/BGR stored as RGBA/RGB). */
+int m2d_save(m2d_handle h, const char* filename);
+
+int m2d_get_stats(m2d_handle h, m2d_stats* out);
+const char* m2d_last_error(m2d_handle h);
+/* Number of CUDA kernels this handle has launched so far (bench.py's gpu_launches). */
+uint64_t m2d_launch_count(m2d_handle h);
+
+/* Pinned host staging helpers for callers that want truly asynchronous m2d_feed(). */
+void* m2d_alloc_host(size_t bytes);
+void m2d_free_host(void* p);
+
+/* The tile-overlap/bounds kernel on its own (SURVEY.md §8a A4+A7): for n poses against the CURRENT grid,
+ * rect[i] = {xminInt,yminInt,xmaxInt,ymaxInt} (or all -1 when the frame is rejected) and hinv[i] = the
+ * inverse homography (region px -> source px, row-major 3x3). No spreadMap is applied: out-of-grid frames
+ * report indices outside [0,w]x[0,h]. Used by m2d_feed_batch and exposed for parity tests. */
+int m2d_compute_bounds(m2d_handle h, int n, const double* poses, int* rects /* n x 4 */,
+                       double* hinv /* n x 9 */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAP2D_B200_H */
