@@ -605,7 +605,7 @@ bool Map::render_weighted(const uint8_t* bgr, size_t stride, const double* Minv,
             }
             stats.region_px[0] += (uint64_t)M2D_ELE_PIXELS * M2D_ELE_PIXELS;
             if (fresh) stats.fresh_px[0] += (uint64_t)M2D_ELE_PIXELS * M2D_ELE_PIXELS;
-            stats.win_px[0] += wins;
+            if (!fresh) stats.win_px[0] += wins;  // wins on first-touch tiles are accounted as fresh_px
             stats.footprint_px += foot;
         }
     return true;

@@ -1,0 +1,761 @@
+// map2d.cu — host side of libmap2d_b200.so: the Map2D object behind the C-ABI of include/map2d_b200.h.
+//
+// Mirrors the reference classes Map2DCPU / MultiBandMap2DCPU (Map2DFusion/Map2DCPU.cpp, MultiBandMap2DCPU.cpp):
+// prepare() lays out the tile grid, feed() decides the frame's tile rectangle on the host in FP64 (geom.h, the
+// same code the bounds kernel runs), allocates first-touch tiles from a slab pool in HBM, and enqueues the fusion
+// kernels on the handle's stream.  There is no CPU fallback: without a CUDA device every call fails loudly.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <string>
+#include <vector>
+
+#include "../../include/map2d_b200.h"
+#include "geom.h"
+#include "kernels.cuh"
+
+int m2d_write_png(const char* path, const uint8_t* bgr_or_bgra, int w, int h, int channels);  // png.cpp
+
+using namespace m2d;
+
+#define CU(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            char buf_[512];                                                                           \
+            snprintf(buf_, sizeof buf_, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            err = buf_;                                                                               \
+            return M2D_ERR_CUDA;                                                                      \
+        }                                                                                             \
+    } while (0)
+#define LAUNCH(call)  \
+    do {              \
+        CU(call);     \
+        launches++;   \
+    } while (0)
+
+struct m2d_map {
+    int type = 0;
+    m2d_config cfg{};
+    int band_num = 5, levels = 6;
+    bool valid = false;
+    std::string err;
+    uint64_t launches = 0;
+
+    // Map2DPrepare + Map2DCPUData
+    GridGeom g{};
+    double min_z = 0, max_z = 0, length_pixel = 0;
+    int org_x = 0, org_y = 0;  // absolute tile coordinate of grid slot (0,0); moves under spreadMap
+    std::vector<uint8_t*> table;  // host mirror of the device tile table (w*h), NULL = untouched / not owned
+    uint8_t** d_table = nullptr;
+    size_t d_table_cap = 0;
+    int last_rect[4] = {-1, -1, -1, -1};
+
+    // tile pool
+    TileLayout lay{};
+    size_t tile_bytes = 0;
+    std::vector<void*> chunks;
+    std::vector<uint8_t*> free_tiles;
+    size_t tiles_in_use = 0;
+
+    // per-size weight images
+    int wimg_w = 0, wimg_h = 0;
+    uint8_t* d_alpha = nullptr;
+    float* d_wimg = nullptr;
+
+    // frame staging ring (host images -> HBM)
+    static constexpr int kRing = 4;
+    uint8_t* d_ring[kRing] = {nullptr, nullptr, nullptr, nullptr};
+    size_t ring_bytes = 0;
+    int ring_next = 0;
+
+    // multi-band scratch pyramid
+    uint8_t* d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::deque<cudaEvent_t> inflight;
+    std::vector<cudaEvent_t> event_pool;
+
+    unsigned long long* d_stats = nullptr;  // [0..8] level wins, [16] footprint, [17] weighted wins
+    m2d_stats stats{};
+
+    int init();
+    void release();
+    int prepare(const double* plane, const double* cam, int n, const double* poses);
+    int spread(double xmin, double ymin, double xmax, double ymax);
+    int feed(const uint8_t* img, int w, int h, size_t stride, const double* pose, bool on_device);
+    int ensure_weight_images(int w, int h);
+    int stage_frame(const uint8_t* img, int w, int h, size_t stride, const uint8_t** d_img, int* d_stride);
+    int alloc_tile(uint8_t** out);
+    int upload_table_rows(int x0, int y0, int x1, int y1);
+    int ensure_scratch(size_t bytes);
+    int run_weighted(const FrameBounds& fb, const FrameRect& r, const uint32_t* fresh, const uint8_t* d_img, int d_stride);
+    int run_multiband(const FrameBounds& fb, const FrameRect& r, const uint32_t* fresh, const uint8_t* d_img, int d_stride);
+    bool owns(int tx, int ty) const;
+    bool tile_bbox(int& x0, int& y0, int& x1, int& y1) const;
+    int get_image(uint8_t* out, int* w, int* h, int* channels, int* tmx, int* tmy);
+    int mark_frame_done();
+    int queue_size();
+    int sync();
+    int reset();
+};
+
+static inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
+bool m2d_map::owns(int tx, int ty) const {
+    if (cfg.shard_count <= 1) return true;
+    int a = (cfg.shard_axis == 0) ? tx + org_x : ty + org_y;
+    int span = cfg.shard_span > 0 ? cfg.shard_span : 1;
+    int s = floordiv(a, span) % cfg.shard_count;
+    if (s < 0) s += cfg.shard_count;
+    return s == cfg.shard_rank;
+}
+
+int m2d_map::init() {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        err = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU path)";
+        return M2D_ERR_CUDA;
+    }
+    CU(cudaSetDevice(cfg.device));
+    CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    own_stream = true;
+    CU(cudaMalloc(&d_stats, 32 * sizeof(unsigned long long)));
+    CU(cudaMemsetAsync(d_stats, 0, 32 * sizeof(unsigned long long), stream));
+    levels = (type == M2D_TYPE_MULTIBAND) ? band_num + 1 : 1;
+    if (type == M2D_TYPE_MULTIBAND) {
+        lay = make_tile_layout(levels);
+        tile_bytes = lay.bytes;
+    } else {
+        tile_bytes = (size_t)kEle * kEle * 4;
+    }
+    return M2D_OK;
+}
+
+void m2d_map::release() {
+    cudaSetDevice(cfg.device);
+    if (stream) cudaStreamSynchronize(stream);
+    for (void* c : chunks) cudaFree(c);
+    chunks.clear();
+    free_tiles.clear();
+    if (d_table) cudaFree(d_table);
+    if (d_alpha) cudaFree(d_alpha);
+    if (d_wimg) cudaFree(d_wimg);
+    for (int i = 0; i < kRing; i++)
+        if (d_ring[i]) cudaFree(d_ring[i]);
+    if (d_scratch) cudaFree(d_scratch);
+    if (d_stats) cudaFree(d_stats);
+    for (cudaEvent_t ev : inflight) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : event_pool) cudaEventDestroy(ev);
+    if (own_stream && stream) cudaStreamDestroy(stream);
+}
+
+// Map2DPrepare::prepare (Map2D.cpp:32-49) + Map2DCPUData::prepare (Map2DCPU.cpp:44-92 / MultiBandMap2DCPU.cpp:199-255)
+int m2d_map::prepare(const double* plane7, const double* cam, int n, const double* poses) {
+    if (n <= 0 || !poses || cam[0] <= 0 || cam[1] <= 0 || cam[2] == 0 || cam[3] == 0) return M2D_REJECTED;
+    GridGeom ng{};
+    ng.cam_w = cam[0]; ng.cam_h = cam[1]; ng.cx = cam[4]; ng.cy = cam[5];
+    ng.fxinv = 1. / cam[2]; ng.fyinv = 1. / cam[3];
+    ng.plane_inv = pose_inverse(pose_from7(plane7));
+    Vec3 mx{-1e10, -1e10, -1e10}, mn{1e10, 1e10, 1e10};
+    for (int i = 0; i < n; i++) {
+        Pose p = pose_mul(ng.plane_inv, pose_from7(poses + 7 * i));
+        const Vec3& t = p.t;
+        mx.x = t.x > mx.x ? t.x : mx.x; mx.y = t.y > mx.y ? t.y : mx.y; mx.z = t.z > mx.z ? t.z : mx.z;
+        mn.x = t.x < mn.x ? t.x : mn.x; mn.y = t.y < mn.y ? t.y : mn.y; mn.z = t.z < mn.z ? t.z : mn.z;
+    }
+    if (mn.z * mx.z <= 0) return M2D_REJECTED;
+    double hgt;
+    if (type == M2D_TYPE_MULTIBAND) hgt = (mx.z > 0) ? mx.z : -mn.z;
+    else hgt = (mn.z > 0) ? mn.z : -mx.z;
+    double lx = (ng.cam_w - ng.cx) * ng.fxinv - (0 - ng.cx) * ng.fxinv;
+    double ly = (ng.cam_h - ng.cy) * ng.fyinv - (0 - ng.cy) * ng.fyinv;
+    double radius = 0.5 * hgt * sqrt((lx * lx + ly * ly));
+    double lp = 0;
+    if (type == M2D_TYPE_MULTIBAND) lp = cfg.resolution;
+    if (!lp) {
+        lp = 2 * radius / sqrt(ng.cam_w * ng.cam_w + ng.cam_h * ng.cam_h);
+        lp /= cfg.scale;
+    }
+    mn.x = mn.x - radius; mn.y = mn.y - radius;
+    mx.x = mx.x + radius; mx.y = mx.y + radius;
+    Vec3 c{0.5 * (mn.x + mx.x), 0.5 * (mn.y + mx.y), 0.5 * (mn.z + mx.z)};
+    mn = Vec3{2 * mn.x - c.x, 2 * mn.y - c.y, 2 * mn.z - c.z};
+    mx = Vec3{2 * mx.x - c.x, 2 * mx.y - c.y, 2 * mx.z - c.z};
+    double ele = kEle * lp;
+    int w = (int)ceil((mx.x - mn.x) / ele), h = (int)ceil((mx.y - mn.y) / ele);
+    if (w <= 0 || h <= 0 || (long long)w * h > (1ll << 26)) return M2D_REJECTED;
+    mx.x = mn.x + ele * w;
+    mx.y = mn.y + ele * h;
+    ng.min_x = mn.x; ng.min_y = mn.y; ng.max_x = mx.x; ng.max_y = mx.y;
+    ng.ele_size = ele; ng.ele_size_inv = 1. / ele; ng.length_pixel_inv = 1. / lp;
+    ng.w = w; ng.h = h;
+
+    CU(cudaSetDevice(cfg.device));
+    if (valid) {  // a second prepare() starts a fresh map, like the reference swapping in new Prepare/Data objects
+        int rc = reset();
+        if (rc != M2D_OK) return rc;
+    }
+    g = ng;
+    min_z = mn.z; max_z = mx.z; length_pixel = lp;
+    org_x = org_y = 0;
+    table.assign((size_t)w * h, nullptr);
+    if ((size_t)w * h > d_table_cap) {
+        if (d_table) { CU(cudaStreamSynchronize(stream)); CU(cudaFree(d_table)); d_table = nullptr; }
+        d_table_cap = (size_t)w * h * 2;
+        CU(cudaMalloc(&d_table, d_table_cap * sizeof(uint8_t*)));
+    }
+    CU(cudaMemsetAsync(d_table, 0, (size_t)w * h * sizeof(uint8_t*), stream));
+    last_rect[0] = last_rect[1] = last_rect[2] = last_rect[3] = -1;
+    valid = true;
+    return M2D_OK;
+}
+
+// spreadMap — Map2DCPU.cpp:339-382: grow the grid (never shrinks) and re-index the tile table; no pixel moves.
+int m2d_map::spread(double xmin, double ymin, double xmax, double ymax) {
+    int xminInt = (int)floor((xmin - g.min_x) * g.ele_size_inv), yminInt = (int)floor((ymin - g.min_y) * g.ele_size_inv);
+    int xmaxInt = (int)ceil((xmax - g.min_x) * g.ele_size_inv), ymaxInt = (int)ceil((ymax - g.min_y) * g.ele_size_inv);
+    xminInt = std::min(xminInt, 0); yminInt = std::min(yminInt, 0);
+    xmaxInt = std::max(xmaxInt, g.w); ymaxInt = std::max(ymaxInt, g.h);
+    int nw = xmaxInt - xminInt, nh = ymaxInt - yminInt;
+    if (nw <= 0 || nh <= 0 || (long long)nw * nh > (1ll << 26)) return M2D_REJECTED;
+    double nminx = g.min_x + g.ele_size * xminInt, nminy = g.min_y + g.ele_size * yminInt;
+    double nmaxx = nminx + nw * g.ele_size, nmaxy = nminy + nh * g.ele_size;
+    std::vector<uint8_t*> nt((size_t)nw * nh, nullptr);
+    for (int x = 0; x < g.w; x++)
+        for (int y = 0; y < g.h; y++) nt[(size_t)(x - xminInt) + (size_t)(y - yminInt) * nw] = table[(size_t)y * g.w + x];
+    table.swap(nt);
+    g.min_x = nminx; g.min_y = nminy; g.max_x = nmaxx; g.max_y = nmaxy;
+    g.w = nw; g.h = nh;
+    org_x += xminInt; org_y += yminInt;
+    if ((size_t)nw * nh > d_table_cap) {
+        CU(cudaStreamSynchronize(stream));
+        CU(cudaFree(d_table));
+        d_table = nullptr;
+        d_table_cap = (size_t)nw * nh * 2;
+        CU(cudaMalloc(&d_table, d_table_cap * sizeof(uint8_t*)));
+    }
+    // the whole index changed: re-upload it (stream-ordered after the kernels that used the old one)
+    CU(cudaStreamSynchronize(stream));
+    CU(cudaMemcpyAsync(d_table, table.data(), table.size() * sizeof(uint8_t*), cudaMemcpyHostToDevice, stream));
+    CU(cudaStreamSynchronize(stream));
+    return M2D_OK;
+}
+
+int m2d_map::ensure_weight_images(int w, int h) {
+    if (wimg_w == w && wimg_h == h) return M2D_OK;
+    CU(cudaStreamSynchronize(stream));
+    if (d_alpha) { CU(cudaFree(d_alpha)); d_alpha = nullptr; }
+    if (d_wimg) { CU(cudaFree(d_wimg)); d_wimg = nullptr; }
+    if (type == M2D_TYPE_MULTIBAND) CU(cudaMalloc(&d_wimg, (size_t)w * h * sizeof(float)));
+    else CU(cudaMalloc(&d_alpha, (size_t)w * h));
+    LAUNCH(launch_weight_images(w, h, cfg.weight_type, d_alpha, d_wimg, stream));
+    wimg_w = w; wimg_h = h;
+    return M2D_OK;
+}
+
+int m2d_map::stage_frame(const uint8_t* img, int w, int h, size_t stride, const uint8_t** d_img, int* d_stride) {
+    size_t need = (size_t)w * h * 3;
+    if (need > ring_bytes) {
+        CU(cudaStreamSynchronize(stream));
+        for (int i = 0; i < kRing; i++) {
+            if (d_ring[i]) { CU(cudaFree(d_ring[i])); d_ring[i] = nullptr; }
+            CU(cudaMalloc(&d_ring[i], need + 256));
+        }
+        ring_bytes = need;
+    }
+    uint8_t* dst = d_ring[ring_next];
+    ring_next = (ring_next + 1) % kRing;
+    // Stream-ordered: the slot's previous consumer kernels precede this copy on the same stream.  Pageable
+    // sources are staged by the runtime before the call returns; pinned sources are DMA'd asynchronously.
+    if (stride == (size_t)w * 3) CU(cudaMemcpyAsync(dst, img, need, cudaMemcpyHostToDevice, stream));
+    else CU(cudaMemcpy2DAsync(dst, (size_t)w * 3, img, stride, (size_t)w * 3, h, cudaMemcpyHostToDevice, stream));
+    *d_img = dst;
+    *d_stride = w * 3;
+    return M2D_OK;
+}
+
+int m2d_map::alloc_tile(uint8_t** out) {
+    if (free_tiles.empty()) {
+        size_t per_chunk = std::max<size_t>(16, ((size_t)128 << 20) / tile_bytes);
+        void* c = nullptr;
+        cudaError_t e = cudaMalloc(&c, per_chunk * tile_bytes);
+        if (e != cudaSuccess) {
+            err = std::string("tile pool cudaMalloc failed: ") + cudaGetErrorString(e);
+            cudaGetLastError();
+            return M2D_ERR_NOMEM;
+        }
+        chunks.push_back(c);
+        for (size_t i = per_chunk; i-- > 0;) free_tiles.push_back((uint8_t*)c + i * tile_bytes);
+    }
+    *out = free_tiles.back();
+    free_tiles.pop_back();
+    tiles_in_use++;
+    return M2D_OK;
+}
+
+int m2d_map::upload_table_rows(int x0, int y0, int x1, int y1) {
+    for (int y = y0; y < y1; y++)
+        CU(cudaMemcpyAsync(d_table + (size_t)y * g.w + x0, table.data() + (size_t)y * g.w + x0,
+                           (size_t)(x1 - x0) * sizeof(uint8_t*), cudaMemcpyHostToDevice, stream));
+    return M2D_OK;
+}
+
+int m2d_map::ensure_scratch(size_t bytes) {
+    if (bytes <= scratch_bytes) return M2D_OK;
+    CU(cudaStreamSynchronize(stream));
+    if (d_scratch) { CU(cudaFree(d_scratch)); d_scratch = nullptr; }
+    scratch_bytes = bytes + bytes / 4;
+    CU(cudaMalloc(&d_scratch, scratch_bytes));
+    return M2D_OK;
+}
+
+int m2d_map::mark_frame_done() {
+    while (!inflight.empty() && cudaEventQuery(inflight.front()) == cudaSuccess) {
+        event_pool.push_back(inflight.front());
+        inflight.pop_front();
+    }
+    cudaEvent_t ev;
+    if (!event_pool.empty()) { ev = event_pool.back(); event_pool.pop_back(); }
+    else CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CU(cudaEventRecord(ev, stream));
+    inflight.push_back(ev);
+    return M2D_OK;
+}
+
+int m2d_map::queue_size() {
+    while (!inflight.empty() && cudaEventQuery(inflight.front()) == cudaSuccess) {
+        event_pool.push_back(inflight.front());
+        inflight.pop_front();
+    }
+    cudaGetLastError();
+    return (int)inflight.size();
+}
+
+int m2d_map::sync() {
+    CU(cudaSetDevice(cfg.device));
+    CU(cudaStreamSynchronize(stream));
+    queue_size();
+    return M2D_OK;
+}
+
+int m2d_map::reset() {
+    CU(cudaSetDevice(cfg.device));
+    CU(cudaStreamSynchronize(stream));
+    for (uint8_t*& t : table)
+        if (t) { free_tiles.push_back(t); t = nullptr; tiles_in_use--; }
+    if (d_table && !table.empty()) CU(cudaMemsetAsync(d_table, 0, table.size() * sizeof(uint8_t*), stream));
+    CU(cudaMemsetAsync(d_stats, 0, 32 * sizeof(unsigned long long), stream));
+    memset(&stats, 0, sizeof stats);
+    last_rect[0] = last_rect[1] = last_rect[2] = last_rect[3] = -1;
+    return M2D_OK;
+}
+
+// feed() + renderFrame() — Map2DCPU.cpp:127-336 / MultiBandMap2DCPU.cpp:288-558
+int m2d_map::feed(const uint8_t* img, int w, int h, size_t stride, const double* pose, bool on_device) {
+    stats.frames_fed++;
+    if (!valid) return M2D_REJECTED;                       // Map2DCPU.cpp:129
+    if (!img || !pose) return M2D_ERR_ARG;
+    if (w != g.cam_w || h != g.cam_h) {                    // Map2DCPU.cpp:158-162
+        fprintf(stderr, "Map2DB200::renderFrame: frame size != camera size\n");
+        return M2D_REJECTED;
+    }
+    if (stride < (size_t)w * 3) return M2D_ERR_ARG;
+    CU(cudaSetDevice(cfg.device));
+    FrameBounds fb;
+    frame_bounds(g, pose, &fb);
+    if (!fb.ok) return M2D_REJECTED;                       // oblique view (Map2DCPU.cpp:179-182)
+    if (fb.gx0 < g.min_x || fb.gx1 > g.max_x || fb.gy0 < g.min_y || fb.gy1 > g.max_y) {
+        int rc = spread(fb.gx0, fb.gy0, fb.gx1, fb.gy1);   // Map2DCPU.cpp:199-218
+        if (rc != M2D_OK) return rc;
+        frame_bounds(g, pose, &fb);
+        if (!fb.ok) return M2D_REJECTED;
+    }
+    if (fb.x0 < 0 || fb.y0 < 0 || fb.x1 > g.w || fb.y1 > g.h || fb.x0 >= fb.x1 || fb.y0 >= fb.y1) {
+        fprintf(stderr, "Map2DB200::renderFrame:should never happen!\n");  // Map2DCPU.cpp:223-227
+        return M2D_REJECTED;
+    }
+    FrameRect r{};
+    r.rx0 = fb.x0; r.ry0 = fb.y0; r.nx = fb.x1 - fb.x0; r.ny = fb.y1 - fb.y0;
+    if ((long long)r.nx * r.ny > kMaxRectTiles) {
+        err = "frame covers more than 1024 tiles";
+        return M2D_ERR_UNSUPPORTED;
+    }
+    memcpy(last_rect, &fb.x0, sizeof(int) * 4);
+    stats.frames_fused++;
+    stats.input_px += (uint64_t)w * h;
+
+    // owned tiles inside the rect; first-touch allocation (Map2DCPU.cpp:311-319)
+    uint32_t fresh[kMaxRectTiles / 32];
+    memset(fresh, 0, sizeof fresh);
+    int ox0 = INT32_MAX, oy0 = INT32_MAX, ox1 = INT32_MIN, oy1 = INT32_MIN;
+    bool dirty = false;
+    for (int ty = fb.y0; ty < fb.y1; ty++)
+        for (int tx = fb.x0; tx < fb.x1; tx++) {
+            if (!owns(tx, ty)) continue;
+            ox0 = std::min(ox0, tx); oy0 = std::min(oy0, ty); ox1 = std::max(ox1, tx + 1); oy1 = std::max(oy1, ty + 1);
+            uint8_t*& slot = table[(size_t)ty * g.w + tx];
+            bool is_fresh = false;
+            if (!slot) {
+                int rc = alloc_tile(&slot);
+                if (rc != M2D_OK) return rc;
+                int bit = (ty - fb.y0) * r.nx + (tx - fb.x0);
+                fresh[bit >> 5] |= 1u << (bit & 31);
+                dirty = true;
+                is_fresh = true;
+            }
+            for (int l = 0; l < levels; l++) {
+                uint64_t npx = (uint64_t)(kEle >> l) * (kEle >> l);
+                stats.region_px[l] += npx;
+                if (is_fresh) stats.fresh_px[l] += npx;
+            }
+        }
+    if (ox1 <= ox0) return M2D_OK;  // this shard owns nothing under the frame
+    r.wx0 = ox0; r.wy0 = oy0; r.wnx = ox1 - ox0; r.wny = oy1 - oy0;
+    if (dirty) { int rc = upload_table_rows(fb.x0, fb.y0, fb.x1, fb.y1); if (rc != M2D_OK) return rc; }
+    { int rc = ensure_weight_images(w, h); if (rc != M2D_OK) return rc; }
+    const uint8_t* d_img = img;
+    int d_stride = (int)stride;
+    if (!on_device) { int rc = stage_frame(img, w, h, stride, &d_img, &d_stride); if (rc != M2D_OK) return rc; }
+    int rc = (type == M2D_TYPE_MULTIBAND) ? run_multiband(fb, r, fresh, d_img, d_stride)
+                                          : run_weighted(fb, r, fresh, d_img, d_stride);
+    if (rc != M2D_OK) return rc;
+    return mark_frame_done();
+}
+
+int m2d_map::run_weighted(const FrameBounds& fb, const FrameRect& r, const uint32_t* fresh, const uint8_t* d_img, int d_stride) {
+    WeightedParams p{};
+    memcpy(p.hinv, fb.hinv, sizeof p.hinv);
+    p.src = d_img; p.src_stride = d_stride; p.sw = (int)g.cam_w; p.sh = (int)g.cam_h;
+    p.alpha = d_alpha; p.table = d_table; p.grid_w = g.w; p.r = r;
+    memcpy(p.fresh, fresh, sizeof p.fresh);
+    p.stats = cfg.collect_stats ? d_stats + 16 : nullptr;
+    LAUNCH(launch_weighted(p, stream));
+    return M2D_OK;
+}
+
+int m2d_map::run_multiband(const FrameBounds& fb, const FrameRect& r, const uint32_t* fresh, const uint8_t* d_img, int d_stride) {
+    MultibandParams p{};
+    memcpy(p.hinv, fb.hinv, sizeof p.hinv);
+    p.src = d_img; p.src_stride = d_stride; p.sw = (int)g.cam_w; p.sh = (int)g.cam_h;
+    p.wimg = d_wimg; p.table = d_table; p.grid_w = g.w; p.r = r;
+    memcpy(p.fresh, fresh, sizeof p.fresh);
+    p.levels = levels;
+    p.stats = cfg.collect_stats ? d_stats : nullptr;
+    // Pyramid window: owned tiles + one tile ring (>= the 94-px level-0 support of the deepest Laplacian tap),
+    // clipped to the frame region so the reflect-101 border lands where the reference puts it.
+    int wx0 = std::max(r.wx0 - 1, r.rx0), wy0 = std::max(r.wy0 - 1, r.ry0);
+    int wx1 = std::min(r.wx0 + r.wnx + 1, r.rx0 + r.nx), wy1 = std::min(r.wy0 + r.wny + 1, r.ry0 + r.ny);
+    if (cfg.shard_count <= 1) { wx0 = r.rx0; wy0 = r.ry0; wx1 = r.rx0 + r.nx; wy1 = r.ry0 + r.ny; }
+    size_t off = 0;
+    size_t offs[M2D_MAX_LEVELS][4];
+    for (int l = 0; l < levels; l++) {
+        int n = kEle >> l;
+        PyrLevel& L = p.lv[l];
+        L.ww = (wx1 - wx0) * n; L.wh = (wy1 - wy0) * n;
+        L.rw = r.nx * n; L.rh = r.ny * n;
+        L.ox = (wx0 - r.rx0) * n; L.oy = (wy0 - r.ry0) * n;
+        size_t px = (size_t)L.ww * L.wh;
+        for (int c = 0; c < 3; c++) { offs[l][c] = off; off += (px * sizeof(int16_t) + 255) & ~(size_t)255; }
+        offs[l][3] = off; off += (px * sizeof(float) + 255) & ~(size_t)255;
+    }
+    { int rc = ensure_scratch(off); if (rc != M2D_OK) return rc; }
+    for (int l = 0; l < levels; l++) {
+        for (int c = 0; c < 3; c++) p.lv[l].g[c] = reinterpret_cast<int16_t*>(d_scratch + offs[l][c]);
+        p.lv[l].w = reinterpret_cast<float*>(d_scratch + offs[l][3]);
+    }
+    LAUNCH(launch_mb_warp(p, stream));
+    for (int l = 0; l + 1 < levels; l++) LAUNCH(launch_mb_pyrdown(p, l, stream));
+    LAUNCH(launch_mb_select(p, lay, stream));
+    return M2D_OK;
+}
+
+bool m2d_map::tile_bbox(int& x0, int& y0, int& x1, int& y1) const {
+    x0 = y0 = INT32_MAX; x1 = y1 = INT32_MIN;
+    for (int y = 0; y < g.h; y++)
+        for (int x = 0; x < g.w; x++)
+            if (table[(size_t)y * g.w + x]) {
+                x0 = std::min(x0, x); y0 = std::min(y0, y); x1 = std::max(x1, x + 1); y1 = std::max(y1, y + 1);
+            }
+    return x1 > x0;
+}
+
+// save() in memory — Map2DCPU.cpp:523-560 / MultiBandMap2DCPU.cpp:779-841
+int m2d_map::get_image(uint8_t* out, int* w, int* h, int* channels, int* tmx, int* tmy) {
+    if (!valid || g.w == 0 || g.h == 0) return M2D_REJECTED;
+    int x0, y0, x1, y1;
+    if (!tile_bbox(x0, y0, x1, y1)) return M2D_REJECTED;
+    int tw = x1 - x0, th = y1 - y0;
+    int cn = (type == M2D_TYPE_MULTIBAND) ? 3 : 4;
+    *w = tw * kEle; *h = th * kEle; *channels = cn; *tmx = x0; *tmy = y0;
+    if (!out) return M2D_OK;
+    CU(cudaSetDevice(cfg.device));
+    size_t W = (size_t)*w, H = (size_t)*h;
+    if (type != M2D_TYPE_MULTIBAND) {
+        memset(out, 0, W * H * 4);
+        for (int y = y0; y < y1; y++)
+            for (int x = x0; x < x1; x++) {
+                const uint8_t* t = table[(size_t)y * g.w + x];
+                if (!t) continue;
+                CU(cudaMemcpy2DAsync(out + ((size_t)(y - y0) * kEle * W + (size_t)(x - x0) * kEle) * 4, W * 4, t, (size_t)kEle * 4,
+                                     (size_t)kEle * 4, kEle, cudaMemcpyDeviceToHost, stream));
+            }
+        CU(cudaStreamSynchronize(stream));
+        return M2D_OK;
+    }
+    // multi-band: collapse on the GPU
+    std::vector<MosaicLevel> ml(levels);
+    std::vector<void*> tmp;
+    auto cleanup = [&]() { for (void* q : tmp) cudaFree(q); };
+    float* w0 = nullptr;
+    uint8_t* d_out = nullptr;
+    cudaError_t e = cudaSuccess;
+    for (int l = 0; l < levels && e == cudaSuccess; l++) {
+        int n = kEle >> l;
+        ml[l].w = tw * n; ml[l].h = th * n;
+        size_t px = (size_t)ml[l].w * ml[l].h;
+        for (int c = 0; c < 3 && e == cudaSuccess; c++) {
+            void* q = nullptr;
+            e = cudaMalloc(&q, px * sizeof(int16_t));
+            if (e == cudaSuccess) { tmp.push_back(q); ml[l].g[c] = (int16_t*)q; }
+        }
+    }
+    if (e == cudaSuccess) { e = cudaMalloc((void**)&w0, W * H * sizeof(float)); if (e == cudaSuccess) tmp.push_back(w0); }
+    if (e == cudaSuccess) { e = cudaMalloc((void**)&d_out, W * H * 3); if (e == cudaSuccess) tmp.push_back(d_out); }
+    if (e != cudaSuccess) {
+        cleanup();
+        err = std::string("collapse cudaMalloc failed: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        return M2D_ERR_NOMEM;
+    }
+    int rc = M2D_OK;
+    auto body = [&]() -> int {
+        for (int l = 0; l < levels; l++) LAUNCH(launch_mosaic_clear(ml[l], l == 0 ? w0 : nullptr, stream));
+        for (int y = y0; y < y1; y++)
+            for (int x = x0; x < x1; x++) {
+                const uint8_t* t = table[(size_t)y * g.w + x];
+                if (!t) continue;
+                for (int l = 0; l < levels; l++) LAUNCH(launch_mosaic_paste(t, lay, l, ml[l], w0, x - x0, y - y0, stream));
+            }
+        for (int l = levels - 1; l > 0; l--) LAUNCH(launch_mosaic_upadd(ml[l], ml[l - 1], stream));
+        LAUNCH(launch_mosaic_final(ml[0], w0, cfg.background, d_out, stream));
+        CU(cudaMemcpyAsync(out, d_out, W * H * 3, cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+        return M2D_OK;
+    };
+    rc = body();
+    cleanup();
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// extern "C"
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+void m2d_config_default(m2d_config* c) {
+    memset(c, 0, sizeof *c);
+    c->scale = 1.0; c->band_number = 5; c->shard_count = 1; c->shard_axis = 1; c->shard_span = 4;
+}
+
+int m2d_create(int type, const m2d_config* cfg, m2d_handle* out) {
+    if (!out) return M2D_ERR_ARG;
+    *out = nullptr;
+    if (type == M2D_TYPE_GPU) type = M2D_TYPE_CPU;  // Map2D.cpp:57-65: TypeGPU yields the Map2DCPU semantics
+    if (type != M2D_TYPE_CPU && type != M2D_TYPE_MULTIBAND) return M2D_ERR_UNSUPPORTED;
+    m2d_config c;
+    if (cfg) c = *cfg; else m2d_config_default(&c);
+    if (c.force_float) return M2D_ERR_UNSUPPORTED;
+    if (c.scale == 0) c.scale = 1.0;
+    if (c.shard_count < 1) c.shard_count = 1;
+    if (c.shard_rank < 0 || c.shard_rank >= c.shard_count) return M2D_ERR_ARG;
+    m2d_map* m = new m2d_map();
+    m->type = type;
+    m->cfg = c;
+    int bn = c.band_number > 0 ? c.band_number : 5;
+    m->band_num = std::min(bn, (int)ceil(log((double)kEle) / log(2.0)));  // MultiBandMap2DCPU.cpp:263
+    int rc = m->init();
+    if (rc != M2D_OK) {
+        fprintf(stderr, "m2d_create: %s\n", m->err.c_str());
+        m->release();
+        delete m;
+        return rc;
+    }
+    *out = m;
+    return M2D_OK;
+}
+
+void m2d_destroy(m2d_handle h) {
+    if (!h) return;
+    h->release();
+    delete h;
+}
+
+int m2d_prepare(m2d_handle h, const double* plane, const double* camera, int n, const double* poses) {
+    if (!h || !plane || !camera) return M2D_ERR_ARG;
+    return h->prepare(plane, camera, n, poses);
+}
+
+int m2d_feed(m2d_handle h, const uint8_t* bgr, int w, int hpx, size_t stride, const double* pose) {
+    if (!h) return M2D_ERR_ARG;
+    return h->feed(bgr, w, hpx, stride, pose, false);
+}
+int m2d_feed_device(m2d_handle h, const uint8_t* d_bgr, int w, int hpx, size_t stride, const double* pose) {
+    if (!h) return M2D_ERR_ARG;
+    return h->feed(d_bgr, w, hpx, stride, pose, true);
+}
+int m2d_feed_batch(m2d_handle h, int n, const uint8_t* base, size_t frame_stride, int w, int hpx, size_t stride,
+                   const double* poses, int on_device, int* result) {
+    if (!h || n < 0 || !base || !poses) return M2D_ERR_ARG;
+    int worst = M2D_OK;
+    for (int i = 0; i < n; i++) {
+        int rc = h->feed(base + (size_t)i * frame_stride, w, hpx, stride, poses + 7 * (size_t)i, on_device != 0);
+        if (result) result[i] = rc;
+        if (rc < 0) { worst = rc; break; }
+    }
+    return worst;
+}
+
+int m2d_sync(m2d_handle h) { return h ? h->sync() : M2D_ERR_ARG; }
+int m2d_queue_size(m2d_handle h) { return h ? h->queue_size() : 0; }
+int m2d_set_stream(m2d_handle h, void* s) {
+    if (!h) return M2D_ERR_ARG;
+    cudaSetDevice(h->cfg.device);
+    cudaStreamSynchronize(h->stream);
+    if (s) {
+        if (h->own_stream) cudaStreamDestroy(h->stream);
+        h->stream = (cudaStream_t)s;
+        h->own_stream = false;
+    } else if (!h->own_stream) {
+        if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return M2D_ERR_CUDA;
+        h->own_stream = true;
+    }
+    return M2D_OK;
+}
+int m2d_reset(m2d_handle h) { return h ? h->reset() : M2D_ERR_ARG; }
+
+int m2d_get_grid(m2d_handle h, int* w, int* ht, double* mn, double* mx, double* lp) {
+    if (!h) return M2D_ERR_ARG;
+    if (!h->valid) return M2D_ERR_STATE;
+    if (w) *w = h->g.w;
+    if (ht) *ht = h->g.h;
+    if (mn) { mn[0] = h->g.min_x; mn[1] = h->g.min_y; mn[2] = h->min_z; }
+    if (mx) { mx[0] = h->g.max_x; mx[1] = h->g.max_y; mx[2] = h->max_z; }
+    if (lp) *lp = h->length_pixel;
+    return M2D_OK;
+}
+int m2d_last_rect(m2d_handle h, int* rect) {
+    if (!h || !rect) return M2D_ERR_ARG;
+    memcpy(rect, h->last_rect, sizeof(int) * 4);
+    return M2D_OK;
+}
+
+int m2d_get_tile(m2d_handle h, int tx, int ty, int level, void* data, float* weight) {
+    if (!h || !data) return M2D_ERR_ARG;
+    m2d_map& m = *h;
+    std::string& err = m.err;
+    if (!m.valid || tx < 0 || ty < 0 || tx >= m.g.w || ty >= m.g.h) return M2D_ERR_ARG;
+    const uint8_t* t = m.table[(size_t)ty * m.g.w + tx];
+    if (!t) return M2D_REJECTED;
+    CU(cudaSetDevice(m.cfg.device));
+    if (m.type != M2D_TYPE_MULTIBAND) {
+        if (level != 0) return M2D_ERR_ARG;
+        CU(cudaMemcpyAsync(data, t, (size_t)kEle * kEle * 4, cudaMemcpyDeviceToHost, m.stream));
+        CU(cudaStreamSynchronize(m.stream));
+        return M2D_OK;
+    }
+    if (level < 0 || level >= m.levels) return M2D_ERR_ARG;
+    size_t n = (size_t)(kEle >> level), px = n * n;
+    std::vector<int16_t> planes(px * 3);
+    CU(cudaMemcpyAsync(planes.data(), t + m.lay.lap_off[level], px * 3 * sizeof(int16_t), cudaMemcpyDeviceToHost, m.stream));
+    if (weight) CU(cudaMemcpyAsync(weight, t + m.lay.wgt_off[level], px * sizeof(float), cudaMemcpyDeviceToHost, m.stream));
+    CU(cudaStreamSynchronize(m.stream));
+    int16_t* o = (int16_t*)data;  // planar state -> the reference's interleaved CV_16SC3
+    for (size_t i = 0; i < px; i++) { o[3 * i] = planes[i]; o[3 * i + 1] = planes[px + i]; o[3 * i + 2] = planes[2 * px + i]; }
+    return M2D_OK;
+}
+
+int m2d_get_image(m2d_handle h, uint8_t* out, int* w, int* hpx, int* channels, int* tmx, int* tmy) {
+    if (!h || !w || !hpx || !channels || !tmx || !tmy) return M2D_ERR_ARG;
+    return h->get_image(out, w, hpx, channels, tmx, tmy);
+}
+
+int m2d_save(m2d_handle h, const char* filename) {
+    if (!h || !filename) return M2D_ERR_ARG;
+    int w, hp, cn, tx, ty;
+    int rc = h->get_image(nullptr, &w, &hp, &cn, &tx, &ty);
+    if (rc != M2D_OK) return rc;
+    std::vector<uint8_t> img((size_t)w * hp * cn);
+    rc = h->get_image(img.data(), &w, &hp, &cn, &tx, &ty);
+    if (rc != M2D_OK) return rc;
+    if (m2d_write_png(filename, img.data(), w, hp, cn) != 0) {
+        h->err = std::string("cannot write ") + filename;
+        return M2D_ERR_IO;
+    }
+    return M2D_OK;
+}
+
+int m2d_get_stats(m2d_handle h, m2d_stats* out) {
+    if (!h || !out) return M2D_ERR_ARG;
+    m2d_map& m = *h;
+    std::string& err = m.err;
+    CU(cudaSetDevice(m.cfg.device));
+    unsigned long long d[32];
+    CU(cudaMemcpyAsync(d, m.d_stats, sizeof d, cudaMemcpyDeviceToHost, m.stream));
+    CU(cudaStreamSynchronize(m.stream));
+    *out = m.stats;
+    if (m.type == M2D_TYPE_MULTIBAND) for (int l = 0; l < M2D_MAX_LEVELS; l++) out->win_px[l] = d[l];
+    else { out->win_px[0] = d[17]; out->footprint_px = d[16]; }
+    return M2D_OK;
+}
+
+const char* m2d_last_error(m2d_handle h) { return h ? h->err.c_str() : "null handle"; }
+uint64_t m2d_launch_count(m2d_handle h) { return h ? h->launches : 0; }
+
+void* m2d_alloc_host(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void m2d_free_host(void* p) { if (p) cudaFreeHost(p); }
+
+int m2d_compute_bounds(m2d_handle h, int n, const double* poses, int* rects, double* hinv) {
+    if (!h || n < 0 || !poses || !rects || !hinv) return M2D_ERR_ARG;
+    m2d_map& m = *h;
+    std::string& err = m.err;
+    uint64_t& launches = m.launches;
+    if (!m.valid) return M2D_ERR_STATE;
+    if (n == 0) return M2D_OK;
+    CU(cudaSetDevice(m.cfg.device));
+    double* d_poses = nullptr;
+    FrameBounds* d_fb = nullptr;
+    CU(cudaMalloc(&d_poses, (size_t)n * 7 * sizeof(double)));
+    cudaError_t e = cudaMalloc(&d_fb, (size_t)n * sizeof(FrameBounds));
+    if (e != cudaSuccess) { cudaFree(d_poses); err = "cudaMalloc"; return M2D_ERR_NOMEM; }
+    std::vector<FrameBounds> fb(n);
+    auto body = [&]() -> int {
+        CU(cudaMemcpyAsync(d_poses, poses, (size_t)n * 7 * sizeof(double), cudaMemcpyHostToDevice, m.stream));
+        LAUNCH(launch_bounds(m.g, n, d_poses, d_fb, m.stream));
+        CU(cudaMemcpyAsync(fb.data(), d_fb, (size_t)n * sizeof(FrameBounds), cudaMemcpyDeviceToHost, m.stream));
+        CU(cudaStreamSynchronize(m.stream));
+        return M2D_OK;
+    };
+    int rc = body();
+    cudaFree(d_poses);
+    cudaFree(d_fb);
+    if (rc != M2D_OK) return rc;
+    for (int i = 0; i < n; i++) {
+        if (fb[i].ok) { memcpy(rects + 4 * i, &fb[i].x0, 4 * sizeof(int)); memcpy(hinv + 9 * i, fb[i].hinv, 9 * sizeof(double)); }
+        else { for (int k = 0; k < 4; k++) rects[4 * i + k] = -1; for (int k = 0; k < 9; k++) hinv[9 * i + k] = 0; }
+    }
+    return M2D_OK;
+}
+
+}  // extern "C"

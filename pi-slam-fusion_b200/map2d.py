@@ -1,0 +1,254 @@
+"""Host-side mirror of the reference's Map2D plugin interface (Map2DFusion/Map2D.h:79-98) on top of the C-ABI
+library libmap2d_b200.so (include/map2d_b200.h).
+
+    m = Map2D.create(Map2D.TypeMultiBandCPU, thread=False)     # Map2D::create      Map2D.cpp:51-66
+    m.prepare(plane, camera, poses)                           # Map2D::prepare     Map2D.h:88
+    m.feed(img_bgr_u8, pose_c2w)                              # Map2D::feed        Map2D.h:91
+    m.save("result.png")                                      # Map2D::save        Map2D.h:95
+    m.queueSize()                                             # Map2D::queueSize   Map2D.h:97
+
+Same names, argument meaning and return convention (bool) as the reference.  There is no CPU path: if the shared
+library or a CUDA device is missing, importing works but create() raises.  This module never imports oracle/.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmap2d_b200.so")
+MAX_LEVELS = 9
+OK, REJECTED = 0, 1
+
+
+class Config(C.Structure):
+    """m2d_config"""
+    _fields_ = [("scale", C.c_double), ("resolution", C.c_double), ("weight_type", C.c_int),
+                ("band_number", C.c_int), ("force_float", C.c_int), ("background", C.c_int),
+                ("thread", C.c_int), ("device", C.c_int), ("shard_rank", C.c_int), ("shard_count", C.c_int),
+                ("shard_axis", C.c_int), ("shard_span", C.c_int), ("collect_stats", C.c_int),
+                ("batch_frames", C.c_int)]
+
+
+class Stats(C.Structure):
+    """m2d_stats"""
+    _fields_ = [("frames_fed", C.c_uint64), ("frames_fused", C.c_uint64), ("input_px", C.c_uint64),
+                ("region_px", C.c_uint64 * MAX_LEVELS), ("fresh_px", C.c_uint64 * MAX_LEVELS),
+                ("win_px", C.c_uint64 * MAX_LEVELS), ("footprint_px", C.c_uint64)]
+
+    def as_dict(self):
+        return {"frames_fed": self.frames_fed, "frames_fused": self.frames_fused, "input_px": self.input_px,
+                "region_px": list(self.region_px), "fresh_px": list(self.fresh_px), "win_px": list(self.win_px),
+                "footprint_px": self.footprint_px}
+
+
+EXPORTS = ["m2d_config_default", "m2d_create", "m2d_destroy", "m2d_prepare", "m2d_feed", "m2d_feed_device",
+           "m2d_feed_batch", "m2d_sync", "m2d_queue_size", "m2d_set_stream", "m2d_reset", "m2d_get_grid",
+           "m2d_last_rect", "m2d_get_tile", "m2d_get_image", "m2d_save", "m2d_get_stats", "m2d_last_error",
+           "m2d_launch_count", "m2d_alloc_host", "m2d_free_host", "m2d_compute_bounds"]
+
+_lib = None
+
+
+def lib():
+    """Load libmap2d_b200.so (built by __graft_entry__.build() / csrc/Makefile).  Fails loudly if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libmap2d_b200.so is not built (%s); run `python __graft_entry__.py` or "
+                           "`make -C pi-slam-fusion_b200/csrc`.  There is no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, dp, ip = C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)
+    L.m2d_config_default.argtypes = [C.POINTER(Config)]
+    L.m2d_config_default.restype = None
+    L.m2d_create.argtypes = [C.c_int, C.POINTER(Config), C.POINTER(vp)]
+    L.m2d_destroy.argtypes = [vp]
+    L.m2d_destroy.restype = None
+    L.m2d_prepare.argtypes = [vp, dp, dp, C.c_int, dp]
+    L.m2d_feed.argtypes = [vp, vp, C.c_int, C.c_int, C.c_size_t, dp]
+    L.m2d_feed_device.argtypes = [vp, vp, C.c_int, C.c_int, C.c_size_t, dp]
+    L.m2d_feed_batch.argtypes = [vp, C.c_int, vp, C.c_size_t, C.c_int, C.c_int, C.c_size_t, dp, C.c_int, ip]
+    L.m2d_sync.argtypes = [vp]
+    L.m2d_queue_size.argtypes = [vp]
+    L.m2d_set_stream.argtypes = [vp, vp]
+    L.m2d_reset.argtypes = [vp]
+    L.m2d_get_grid.argtypes = [vp, ip, ip, dp, dp, dp]
+    L.m2d_last_rect.argtypes = [vp, ip]
+    L.m2d_get_tile.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp]
+    L.m2d_get_image.argtypes = [vp, vp, ip, ip, ip, ip, ip]
+    L.m2d_save.argtypes = [vp, C.c_char_p]
+    L.m2d_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.m2d_last_error.argtypes = [vp]
+    L.m2d_last_error.restype = C.c_char_p
+    L.m2d_launch_count.argtypes = [vp]
+    L.m2d_launch_count.restype = C.c_uint64
+    L.m2d_alloc_host.argtypes = [C.c_size_t]
+    L.m2d_alloc_host.restype = vp
+    L.m2d_free_host.argtypes = [vp]
+    L.m2d_free_host.restype = None
+    L.m2d_compute_bounds.argtypes = [vp, C.c_int, dp, ip, dp]
+    _lib = L
+    return L
+
+
+def default_config(**kw):
+    c = Config()
+    lib().m2d_config_default(C.byref(c))
+    for k, v in kw.items():
+        setattr(c, k, v)
+    return c
+
+
+def _dptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def pinned_empty(shape, dtype=np.uint8):
+    """numpy array backed by page-locked host memory from m2d_alloc_host (truly asynchronous feeds)."""
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = lib().m2d_alloc_host(n)
+    if not p:
+        raise MemoryError("m2d_alloc_host(%d) failed" % n)
+    buf = (C.c_uint8 * n).from_address(p)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    arr._m2d_pinned = p  # keeps nothing alive on purpose: free with free_pinned
+    return arr, p
+
+
+def free_pinned(p):
+    lib().m2d_free_host(p)
+
+
+class Map2D:
+    """Reference-shaped object; see module docstring."""
+    NoType, TypeCPU, TypeGPU, TypeMultiBandCPU, TypeRender = 0, 1, 2, 3, 4  # Map2D.h:83
+
+    def __init__(self, type_, cfg):
+        self.cfg = cfg
+        self.type = self.TypeCPU if type_ == self.TypeGPU else type_
+        self._h = C.c_void_p()
+        rc = lib().m2d_create(type_, C.byref(cfg), C.byref(self._h))
+        if rc != OK:
+            raise RuntimeError("m2d_create(type=%d) failed with status %d (no CUDA device? unsupported type?)" % (type_, rc))
+        self.levels = (min(cfg.band_number if cfg.band_number > 0 else 5, 8) + 1) if self.type == self.TypeMultiBandCPU else 1
+
+    @classmethod
+    def create(cls, type_=1, thread=True, **kw):
+        """Map2D::create(type, thread) — returns None for NoType like the reference's null SPtr."""
+        if type_ == cls.NoType:
+            return None
+        cfg = kw.pop("cfg", None) or default_config(thread=int(bool(thread)), **kw)
+        return cls(type_, cfg)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().m2d_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc < 0:
+            raise RuntimeError("map2d_b200 error %d: %s" % (rc, lib().m2d_last_error(self._h).decode()))
+        return rc == OK
+
+    # --- Map2D interface -----------------------------------------------------------------------------
+    def prepare(self, plane, camera, frames):
+        """frames: sequence of poses (n x 7) or of (img, pose) pairs like the reference's deque."""
+        poses = [f[1] if isinstance(f, (tuple, list)) and len(f) == 2 and np.ndim(f[1]) == 1 else f for f in frames]
+        poses = np.ascontiguousarray(np.asarray(poses, np.float64).reshape(-1, 7))
+        plane = np.ascontiguousarray(plane, np.float64).reshape(7)
+        camera = np.ascontiguousarray(camera, np.float64).reshape(6)
+        return self._check(lib().m2d_prepare(self._h, _dptr(plane), _dptr(camera), len(poses), _dptr(poses)))
+
+    def feed(self, img, pose):
+        img = np.asarray(img)
+        if img.dtype != np.uint8 or img.ndim != 3 or img.shape[2] != 3 or img.strides[2] != 1 or img.strides[1] != 3:
+            print("Map2DB200::feed: image must be CV_8UC3")  # reference: type()!=CV_8UC3 -> false
+            return False
+        pose = np.ascontiguousarray(pose, np.float64).reshape(7)
+        return self._check(lib().m2d_feed(self._h, img.ctypes.data, img.shape[1], img.shape[0], img.strides[0], _dptr(pose)))
+
+    def feed_device(self, dev_ptr, w, h, stride, pose):
+        pose = np.ascontiguousarray(pose, np.float64).reshape(7)
+        return self._check(lib().m2d_feed_device(self._h, dev_ptr, w, h, stride, _dptr(pose)))
+
+    def feed_batch(self, base_ptr, n, frame_stride, w, h, stride, poses, on_device):
+        poses = np.ascontiguousarray(poses, np.float64).reshape(-1, 7)
+        res = np.zeros(n, np.int32)
+        rc = lib().m2d_feed_batch(self._h, n, base_ptr, frame_stride, w, h, stride, _dptr(poses), int(on_device),
+                                  res.ctypes.data_as(C.POINTER(C.c_int)))
+        self._check(rc)
+        return res
+
+    def save(self, filename):
+        return self._check(lib().m2d_save(self._h, os.fsencode(filename)))
+
+    def queueSize(self):
+        return lib().m2d_queue_size(self._h)
+
+    def draw(self):  # GL display is out of scope; kept so the interface is complete
+        return None
+
+    # --- additions over the reference (in-memory getters) -----------------------------
+    def sync(self):
+        return self._check(lib().m2d_sync(self._h))
+
+    def reset(self):
+        return self._check(lib().m2d_reset(self._h))
+
+    def set_stream(self, cuda_stream):
+        return self._check(lib().m2d_set_stream(self._h, cuda_stream))
+
+    def grid(self):
+        w, h, lp = C.c_int(), C.c_int(), C.c_double()
+        mn, mx = np.zeros(3), np.zeros(3)
+        rc = lib().m2d_get_grid(self._h, C.byref(w), C.byref(h), _dptr(mn), _dptr(mx), C.byref(lp))
+        if rc:
+            raise RuntimeError("not prepared")
+        return {"w": w.value, "h": h.value, "min": mn, "max": mx, "length_pixel": lp.value}
+
+    def last_rect(self):
+        r = (C.c_int * 4)()
+        lib().m2d_last_rect(self._h, r)
+        return tuple(r)
+
+    def get_tile(self, tx, ty, level=0):
+        n = 256 >> level
+        if self.type == self.TypeMultiBandCPU:
+            lap, wgt = np.zeros((n, n, 3), np.int16), np.zeros((n, n), np.float32)
+            rc = lib().m2d_get_tile(self._h, tx, ty, level, lap.ctypes.data, wgt.ctypes.data)
+            return (lap, wgt) if self._check(rc) else None
+        out = np.zeros((256, 256, 4), np.uint8)
+        rc = lib().m2d_get_tile(self._h, tx, ty, 0, out.ctypes.data, None)
+        return out if self._check(rc) else None
+
+    def get_image(self):
+        w, h, cn, tx, ty = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        rc = lib().m2d_get_image(self._h, None, C.byref(w), C.byref(h), C.byref(cn), C.byref(tx), C.byref(ty))
+        if not self._check(rc):
+            return None
+        out = np.zeros((h.value, w.value, cn.value), np.uint8)
+        self._check(lib().m2d_get_image(self._h, out.ctypes.data, C.byref(w), C.byref(h), C.byref(cn), C.byref(tx), C.byref(ty)))
+        return out, (tx.value, ty.value)
+
+    def stats(self):
+        s = Stats()
+        self._check(lib().m2d_get_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def launch_count(self):
+        return int(lib().m2d_launch_count(self._h))
+
+    def compute_bounds(self, poses):
+        poses = np.ascontiguousarray(poses, np.float64).reshape(-1, 7)
+        n = len(poses)
+        rects = np.zeros((n, 4), np.int32)
+        hinv = np.zeros((n, 9), np.float64)
+        self._check(lib().m2d_compute_bounds(self._h, n, _dptr(poses), rects.ctypes.data_as(C.POINTER(C.c_int)), _dptr(hinv)))
+        return rects, hinv.reshape(n, 3, 3)

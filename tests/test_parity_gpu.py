@@ -1,0 +1,227 @@
+"""GPU parity tests proper: the CUDA path, called through the C-ABI, against the CPU oracle on the same seeded
+inputs.  Bar: tile footprint / indexing and all integer state bit-exact; float weights bit-exact too (tolerance
+stated: max relative error <= 1e-5 is the contract, we assert equality and report)."""
+import numpy as np
+import pytest
+
+import pi_slam_fusion_b200.map2d as m2d
+import pi_slam_fusion_b200.synth as synth
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+W_TOL = 1e-5  # north_star: float state max relative error
+
+
+def run_pair(typ, seq, **cfg):
+    g = m2d.Map2D.create(typ, thread=False, **cfg)
+    o = O.OracleMap2D.create(typ, **cfg)
+    assert g.prepare(seq.plane, seq.camera, seq.prepare_poses) == o.prepare(seq.plane, seq.camera, seq.prepare_poses)
+    go, oo = g.grid(), o.grid()
+    assert (go["w"], go["h"]) == (oo["w"], oo["h"])
+    assert np.array_equal(go["min"], oo["min"]) and np.array_equal(go["max"], oo["max"]) and go["length_pixel"] == oo["length_pixel"]
+    for k in range(seq.n):
+        f = seq.frame(k)
+        rg, ro = g.feed(f, seq.poses[k]), o.feed(f, seq.poses[k])
+        assert rg == ro, "frame %d accept mismatch" % k
+        if rg:
+            assert g.last_rect() == o.last_rect(), "frame %d tile rect mismatch" % k
+    g.sync()
+    return g, o
+
+
+def compare_state(g, o, typ):
+    gg, og = g.grid(), o.grid()
+    assert (gg["w"], gg["h"]) == (og["w"], og["h"])
+    assert np.array_equal(gg["min"], og["min"]) and np.array_equal(gg["max"], og["max"])
+    ntiles = 0
+    for ty in range(og["h"]):
+        for tx in range(og["w"]):
+            if typ == 1:
+                ot, gt = o.get_tile(tx, ty), g.get_tile(tx, ty)
+                assert (ot is None) == (gt is None), "tile (%d,%d) presence" % (tx, ty)
+                if ot is None:
+                    continue
+                ntiles += 1
+                assert np.array_equal(ot, gt), "tile (%d,%d): %d bytes differ" % (tx, ty, int((ot != gt).sum()))
+            else:
+                for l in range(o.levels):
+                    ot, gt = o.get_tile(tx, ty, l), g.get_tile(tx, ty, l)
+                    assert (ot is None) == (gt is None), "tile (%d,%d) presence" % (tx, ty)
+                    if ot is None:
+                        break
+                    ntiles += (l == 0)
+                    assert np.array_equal(ot[1], gt[1]), "tile (%d,%d) L%d weights: max rel err %g" % (
+                        tx, ty, l, float(np.max(np.abs(ot[1] - gt[1]) / np.maximum(np.abs(ot[1]), 1e-30))))
+                    assert np.array_equal(ot[0], gt[0]), "tile (%d,%d) L%d laplacian: %d values differ" % (
+                        tx, ty, l, int((ot[0] != gt[0]).sum()))
+    assert ntiles > 0
+    gi, oi = g.get_image(), o.get_image()
+    assert gi[1] == oi[1] and gi[0].shape == oi[0].shape
+    assert np.array_equal(gi[0], oi[0]), "mosaic: %d bytes differ" % int((gi[0] != oi[0]).sum())
+    return ntiles
+
+
+@pytest.mark.parametrize("typ", [1, 3])
+@pytest.mark.parametrize("jitter,noise", [(False, False), (True, True)])
+def test_small_sequence_bit_exact(typ, jitter, noise):
+    seq = synth.Sequence(14, 320, 180, seed=7, jitter=jitter, noise=noise, fpl=5, prepare_frames=6)
+    g, o = run_pair(typ, seq)
+    compare_state(g, o, typ)
+    g.close()
+
+
+@pytest.mark.parametrize("typ", [1, 3])
+def test_spread_map_and_rejects(typ):
+    """Prepare on 3 frames only so later frames leave the grid (spreadMap, Map2DCPU.cpp:339-382); include an
+    oblique pose that must be rejected (Map2DCPU.cpp:179-182) and a wrong-sized frame (:158-162)."""
+    seq = synth.Sequence(12, 256, 144, seed=3, jitter=True, fpl=3, prepare_frames=2, cross=1.5, along=0.9)
+    g = m2d.Map2D.create(typ, thread=False)
+    o = O.OracleMap2D.create(typ)
+    assert g.prepare(seq.plane, seq.camera, seq.prepare_poses) and o.prepare(seq.plane, seq.camera, seq.prepare_poses)
+    w0 = g.grid()["w"] * g.grid()["h"]
+    for k in range(seq.n):
+        f = seq.frame(k)
+        assert g.feed(f, seq.poses[k]) == o.feed(f, seq.poses[k])
+        assert g.last_rect() == o.last_rect()
+    oblique = seq.poses[0].copy()
+    oblique[3:] = [0.5, 0.5, 0.5, 0.5]  # optical axis horizontal
+    assert g.feed(seq.frame(0), oblique) is False and o.feed(seq.frame(0), oblique) is False
+    assert g.feed(np.zeros((10, 10, 3), np.uint8), seq.poses[0]) is False
+    g.sync()
+    assert g.grid()["w"] * g.grid()["h"] > w0, "test did not exercise spreadMap"
+    compare_state(g, o, typ)
+    g.close()
+
+
+def test_weight_type_and_scale():
+    seq = synth.Sequence(8, 320, 180, seed=5, jitter=True, fpl=4, prepare_frames=4)
+    for typ in (1, 3):
+        g, o = run_pair(typ, seq, weight_type=1, scale=1.5, background=255)
+        compare_state(g, o, typ)
+        g.close()
+
+
+def test_band_number_variants():
+    seq = synth.Sequence(6, 320, 180, seed=9, jitter=True, fpl=3, prepare_frames=3)
+    for bands in (1, 3, 8):
+        g, o = run_pair(3, seq, band_number=bands)
+        assert g.levels == o.levels == bands + 1
+        compare_state(g, o, 3)
+        g.close()
+
+
+def test_bounds_kernel_matches_oracle():
+    seq = synth.Sequence(64, 1280, 720, seed=2, jitter=True)
+    g = m2d.Map2D.create(1, thread=False)
+    o = O.OracleMap2D.create(1)
+    assert g.prepare(seq.plane, seq.camera, seq.prepare_poses) and o.prepare(seq.plane, seq.camera, seq.prepare_poses)
+    poses = seq.poses.copy()
+    poses[5, 3:] = [0.5, 0.5, 0.5, 0.5]
+    rg, hg = g.compute_bounds(poses)
+    ro, ho = o.compute_bounds(poses)
+    assert np.array_equal(rg, ro)
+    assert np.array_equal(hg, ho), "inverse homographies differ in %d entries" % int((hg != ho).sum())
+    assert (rg[5] == -1).all()
+    g.close()
+
+
+@pytest.mark.parametrize("typ", [1, 3])
+def test_stats_match_oracle(typ):
+    seq = synth.Sequence(10, 320, 180, seed=4, jitter=True, fpl=5, prepare_frames=5)
+    g, o = run_pair(typ, seq, collect_stats=1)
+    sg, so = g.stats(), o.stats()
+    for k in ("frames_fed", "frames_fused", "input_px", "region_px", "fresh_px", "win_px"):
+        assert sg[k] == so[k], (k, sg[k], so[k])
+    if typ == 1:
+        assert sg["footprint_px"] == so["footprint_px"]
+    g.close()
+
+
+@pytest.mark.parametrize("typ", [1, 3])
+def test_full_size_720p_prefix(typ):
+    """BASELINE.json configs[0]/[1] frame size, first 24 frames of the seeded survey, bit-exact vs the oracle."""
+    seq = synth.Sequence(100 if typ == 1 else 500, 1280, 720, seed=typ)
+    g = m2d.Map2D.create(typ, thread=False)
+    o = O.OracleMap2D.create(typ)
+    O.set_threads(8)
+    try:
+        assert g.prepare(seq.plane, seq.camera, seq.prepare_poses) and o.prepare(seq.plane, seq.camera, seq.prepare_poses)
+        for k in range(24):
+            f = seq.frame(k)
+            assert g.feed(f, seq.poses[k]) == o.feed(f, seq.poses[k])
+            assert g.last_rect() == o.last_rect()
+        g.sync()
+        compare_state(g, o, typ)
+    finally:
+        O.set_threads(1)
+    g.close()
+
+
+def test_feed_paths_agree():
+    """feed (host, staged), feed_device and feed_batch must leave identical state."""
+    import torch
+    seq = synth.Sequence(10, 320, 180, seed=8, jitter=True, fpl=5, prepare_frames=5)
+    frames = seq.frames()
+    dev = torch.from_numpy(frames).cuda()
+    for typ in (1, 3):
+        a = m2d.Map2D.create(typ, thread=False)
+        b = m2d.Map2D.create(typ, thread=False)
+        c = m2d.Map2D.create(typ, thread=False)
+        for m in (a, b, c):
+            assert m.prepare(seq.plane, seq.camera, seq.prepare_poses)
+        for k in range(seq.n):
+            assert a.feed(frames[k], seq.poses[k])
+            assert b.feed_device(dev[k].data_ptr(), seq.w, seq.h, seq.w * 3, seq.poses[k])
+        res = c.feed_batch(dev.data_ptr(), seq.n, seq.w * seq.h * 3, seq.w, seq.h, seq.w * 3, seq.poses, True)
+        assert (res == 0).all()
+        for m in (a, b, c):
+            m.sync()
+        ia, ib, ic = a.get_image(), b.get_image(), c.get_image()
+        assert np.array_equal(ia[0], ib[0]) and np.array_equal(ia[0], ic[0])
+        assert a.queueSize() == 0
+        for m in (a, b, c):
+            m.close()
+
+
+def test_idempotence_and_order_property():
+    """Size-independent properties at BASELINE frame size: feeding the same frame twice changes nothing in
+    weighted mode (strict '<'), and the mosaic alpha equals the per-pixel max of the individual frames' alphas."""
+    seq = synth.Sequence(6, 1280, 720, seed=6, jitter=True, fpl=3, prepare_frames=6)
+    g = m2d.Map2D.create(1, thread=False)
+    assert g.prepare(seq.plane, seq.camera, seq.prepare_poses)
+    for k in range(seq.n):
+        assert g.feed(seq.frame(k), seq.poses[k])
+    first, org = g.get_image()
+    for k in range(seq.n):
+        assert g.feed(seq.frame(k), seq.poses[k])
+    again, org2 = g.get_image()
+    assert org == org2 and np.array_equal(first, again)
+    singles = []
+    for k in range(seq.n):
+        s = m2d.Map2D.create(1, thread=False)
+        assert s.prepare(seq.plane, seq.camera, seq.prepare_poses)
+        assert s.feed(seq.frame(k), seq.poses[k])
+        img, o1 = s.get_image()
+        full = np.zeros(first.shape[:2], np.uint8)
+        y0, x0 = (o1[1] - org[1]) * 256, (o1[0] - org[0]) * 256
+        full[y0:y0 + img.shape[0], x0:x0 + img.shape[1]] = img[..., 3]
+        singles.append(full)
+        s.close()
+    assert np.array_equal(first[..., 3], np.max(singles, axis=0))
+    g.close()
+
+
+def test_save_png_roundtrip(tmp_path):
+    cv2 = pytest.importorskip("cv2")
+    seq = synth.Sequence(4, 320, 180, seed=1, fpl=2, prepare_frames=4)
+    for typ in (1, 3):
+        g = m2d.Map2D.create(typ, thread=False)
+        assert g.prepare(seq.plane, seq.camera, seq.prepare_poses)
+        for k in range(seq.n):
+            assert g.feed(seq.frame(k), seq.poses[k])
+        path = str(tmp_path / ("m%d.png" % typ))
+        assert g.save(path)
+        img = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+        assert np.array_equal(img, g.get_image()[0])
+        g.close()
