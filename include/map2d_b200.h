@@ -139,6 +139,14 @@ const char* m2d_last_error(m2d_handle h);
 /* Number of CUDA kernels this handle has launched so far (bench.py's gpu_launches). */
 uint64_t m2d_launch_count(m2d_handle h);
 
+/* Per-kernel-class device timing: while enabled, every launch on the handle's stream is bracketed by CUDA
+ * events; m2d_get_kernel_times synchronises and returns accumulated milliseconds and launch counts per class
+ * (and clears them).  bench.py uses it for the live roofline measurement; leave it off otherwise. */
+#define M2D_KERNEL_CLASSES 8
+enum { M2D_K_WEIGHTED = 0, M2D_K_MB_WARP = 1, M2D_K_MB_PYRDOWN = 2, M2D_K_MB_SELECT = 3, M2D_K_COLLAPSE = 4, M2D_K_MISC = 5 };
+int m2d_profile(m2d_handle h, int enable);
+int m2d_get_kernel_times(m2d_handle h, double* ms /* M2D_KERNEL_CLASSES */, uint64_t* count /* M2D_KERNEL_CLASSES */);
+
 /* Pinned host staging helpers for callers that want truly asynchronous m2d_feed(). */
 void* m2d_alloc_host(size_t bytes);
 void m2d_free_host(void* p);

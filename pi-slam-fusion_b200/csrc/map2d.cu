@@ -32,11 +32,24 @@ using namespace m2d;
             return M2D_ERR_CUDA;                                                                      \
         }                                                                                             \
     } while (0)
-#define LAUNCH(call)  \
-    do {              \
-        CU(call);     \
-        launches++;   \
+#define LAUNCHK(kind, call)                                   \
+    do {                                                      \
+        cudaEvent_t pe0_ = nullptr, pe1_ = nullptr;           \
+        if (profiling) {                                      \
+            CU(cudaEventCreate(&pe0_));                       \
+            CU(cudaEventCreate(&pe1_));                       \
+            CU(cudaEventRecord(pe0_, stream));                \
+        }                                                     \
+        CU(call);                                             \
+        launches++;                                           \
+        if (profiling) {                                      \
+            CU(cudaEventRecord(pe1_, stream));                \
+            prof.push_back(ProfRec{kind, pe0_, pe1_});        \
+        }                                                     \
     } while (0)
+#define LAUNCH(call) LAUNCHK(M2D_K_MISC, call)
+
+struct ProfRec { int kind; cudaEvent_t e0, e1; };
 
 struct m2d_map {
     int type = 0;
@@ -45,6 +58,8 @@ struct m2d_map {
     bool valid = false;
     std::string err;
     uint64_t launches = 0;
+    bool profiling = false;
+    std::vector<ProfRec> prof;
 
     // Map2DPrepare + Map2DCPUData
     GridGeom g{};
@@ -437,7 +452,7 @@ int m2d_map::run_weighted(const FrameBounds& fb, const FrameRect& r, const uint3
     p.alpha = d_alpha; p.table = d_table; p.grid_w = g.w; p.r = r;
     memcpy(p.fresh, fresh, sizeof p.fresh);
     p.stats = cfg.collect_stats ? d_stats + 16 : nullptr;
-    LAUNCH(launch_weighted(p, stream));
+    LAUNCHK(M2D_K_WEIGHTED, launch_weighted(p, stream));
     return M2D_OK;
 }
 
@@ -471,9 +486,9 @@ int m2d_map::run_multiband(const FrameBounds& fb, const FrameRect& r, const uint
         for (int c = 0; c < 3; c++) p.lv[l].g[c] = reinterpret_cast<int16_t*>(d_scratch + offs[l][c]);
         p.lv[l].w = reinterpret_cast<float*>(d_scratch + offs[l][3]);
     }
-    LAUNCH(launch_mb_warp(p, stream));
-    for (int l = 0; l + 1 < levels; l++) LAUNCH(launch_mb_pyrdown(p, l, stream));
-    LAUNCH(launch_mb_select(p, lay, stream));
+    LAUNCHK(M2D_K_MB_WARP, launch_mb_warp(p, stream));
+    for (int l = 0; l + 1 < levels; l++) LAUNCHK(M2D_K_MB_PYRDOWN, launch_mb_pyrdown(p, l, stream));
+    LAUNCHK(M2D_K_MB_SELECT, launch_mb_select(p, lay, stream));
     return M2D_OK;
 }
 
@@ -537,15 +552,15 @@ int m2d_map::get_image(uint8_t* out, int* w, int* h, int* channels, int* tmx, in
     }
     int rc = M2D_OK;
     auto body = [&]() -> int {
-        for (int l = 0; l < levels; l++) LAUNCH(launch_mosaic_clear(ml[l], l == 0 ? w0 : nullptr, stream));
+        for (int l = 0; l < levels; l++) LAUNCHK(M2D_K_COLLAPSE, launch_mosaic_clear(ml[l], l == 0 ? w0 : nullptr, stream));
         for (int y = y0; y < y1; y++)
             for (int x = x0; x < x1; x++) {
                 const uint8_t* t = table[(size_t)y * g.w + x];
                 if (!t) continue;
-                for (int l = 0; l < levels; l++) LAUNCH(launch_mosaic_paste(t, lay, l, ml[l], w0, x - x0, y - y0, stream));
+                for (int l = 0; l < levels; l++) LAUNCHK(M2D_K_COLLAPSE, launch_mosaic_paste(t, lay, l, ml[l], w0, x - x0, y - y0, stream));
             }
-        for (int l = levels - 1; l > 0; l--) LAUNCH(launch_mosaic_upadd(ml[l], ml[l - 1], stream));
-        LAUNCH(launch_mosaic_final(ml[0], w0, cfg.background, d_out, stream));
+        for (int l = levels - 1; l > 0; l--) LAUNCHK(M2D_K_COLLAPSE, launch_mosaic_upadd(ml[l], ml[l - 1], stream));
+        LAUNCHK(M2D_K_COLLAPSE, launch_mosaic_final(ml[0], w0, cfg.background, d_out, stream));
         CU(cudaMemcpyAsync(out, d_out, W * H * 3, cudaMemcpyDeviceToHost, stream));
         CU(cudaStreamSynchronize(stream));
         return M2D_OK;
@@ -716,6 +731,28 @@ int m2d_get_stats(m2d_handle h, m2d_stats* out) {
     return M2D_OK;
 }
 
+int m2d_profile(m2d_handle h, int enable) {
+    if (!h) return M2D_ERR_ARG;
+    h->profiling = enable != 0;
+    return M2D_OK;
+}
+int m2d_get_kernel_times(m2d_handle h, double* ms, uint64_t* count) {
+    if (!h || !ms || !count) return M2D_ERR_ARG;
+    m2d_map& m = *h;
+    std::string& err = m.err;
+    CU(cudaSetDevice(m.cfg.device));
+    CU(cudaStreamSynchronize(m.stream));
+    for (int i = 0; i < M2D_KERNEL_CLASSES; i++) { ms[i] = 0; count[i] = 0; }
+    for (ProfRec& r : m.prof) {
+        float t = 0;
+        if (cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess && r.kind >= 0 && r.kind < M2D_KERNEL_CLASSES) { ms[r.kind] += t; count[r.kind]++; }
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    m.prof.clear();
+    return M2D_OK;
+}
+
 const char* m2d_last_error(m2d_handle h) { return h ? h->err.c_str() : "null handle"; }
 uint64_t m2d_launch_count(m2d_handle h) { return h ? h->launches : 0; }
 
@@ -731,6 +768,9 @@ int m2d_compute_bounds(m2d_handle h, int n, const double* poses, int* rects, dou
     m2d_map& m = *h;
     std::string& err = m.err;
     uint64_t& launches = m.launches;
+    bool& profiling = m.profiling;
+    std::vector<ProfRec>& prof = m.prof;
+    cudaStream_t stream = m.stream;
     if (!m.valid) return M2D_ERR_STATE;
     if (n == 0) return M2D_OK;
     CU(cudaSetDevice(m.cfg.device));

@@ -45,7 +45,7 @@ class Stats(C.Structure):
 EXPORTS = ["m2d_config_default", "m2d_create", "m2d_destroy", "m2d_prepare", "m2d_feed", "m2d_feed_device",
            "m2d_feed_batch", "m2d_sync", "m2d_queue_size", "m2d_set_stream", "m2d_reset", "m2d_get_grid",
            "m2d_last_rect", "m2d_get_tile", "m2d_get_image", "m2d_save", "m2d_get_stats", "m2d_last_error",
-           "m2d_launch_count", "m2d_alloc_host", "m2d_free_host", "m2d_compute_bounds"]
+           "m2d_launch_count", "m2d_profile", "m2d_get_kernel_times", "m2d_alloc_host", "m2d_free_host", "m2d_compute_bounds"]
 
 _lib = None
 
@@ -83,6 +83,8 @@ def lib():
     L.m2d_last_error.restype = C.c_char_p
     L.m2d_launch_count.argtypes = [vp]
     L.m2d_launch_count.restype = C.c_uint64
+    L.m2d_profile.argtypes = [vp, C.c_int]
+    L.m2d_get_kernel_times.argtypes = [vp, dp, C.POINTER(C.c_uint64)]
     L.m2d_alloc_host.argtypes = [C.c_size_t]
     L.m2d_alloc_host.restype = vp
     L.m2d_free_host.argtypes = [vp]
@@ -112,8 +114,7 @@ def pinned_empty(shape, dtype=np.uint8):
         raise MemoryError("m2d_alloc_host(%d) failed" % n)
     buf = (C.c_uint8 * n).from_address(p)
     arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
-    arr._m2d_pinned = p  # keeps nothing alive on purpose: free with free_pinned
-    return arr, p
+    return arr, p  # free with free_pinned(p) once arr is no longer used
 
 
 def free_pinned(p):
@@ -244,6 +245,18 @@ class Map2D:
 
     def launch_count(self):
         return int(lib().m2d_launch_count(self._h))
+
+    KERNEL_CLASSES = ("weighted_fuse", "mb_warp", "mb_pyrdown", "mb_select", "collapse", "misc", "k6", "k7")
+
+    def profile(self, enable):
+        return self._check(lib().m2d_profile(self._h, int(enable)))
+
+    def kernel_times(self):
+        """{class: (total_ms, launches)} accumulated since the last call (synchronises)."""
+        ms = np.zeros(8, np.float64)
+        cnt = np.zeros(8, np.uint64)
+        self._check(lib().m2d_get_kernel_times(self._h, _dptr(ms), cnt.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.KERNEL_CLASSES) if cnt[i]}
 
     def compute_bounds(self, poses):
         poses = np.ascontiguousarray(poses, np.float64).reshape(-1, 7)
