@@ -1,0 +1,127 @@
+"""Oracle (CPU, no cv2 needed) and CUDA path (gpu) against the committed golden fixtures of tests/golden/
+(generated from real OpenCV 4.13 by tests/golden/make_golden.py)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+import pi_slam_fusion_b200.synth as synth
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+with open(os.path.join(HERE, "golden", "golden.json")) as f:
+    GOLD = json.load(f)
+KAT = np.load(os.path.join(HERE, "golden", "kat.npz"))
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def state_record(m, typ, levels=6):
+    rec = {}
+    g = m.grid()
+    for ty in range(g["h"]):
+        for tx in range(g["w"]):
+            if typ == 1:
+                t = m.get_tile(tx, ty)
+                if t is not None:
+                    rec["%d,%d" % (tx, ty)] = sha(t)
+            else:
+                if m.get_tile(tx, ty, 0) is None:
+                    continue
+                rec["%d,%d" % (tx, ty)] = [[sha(m.get_tile(tx, ty, l)[0]), sha(m.get_tile(tx, ty, l)[1])] for l in range(levels)]
+    return rec
+
+
+@pytest.fixture(autouse=True)
+def _mode():
+    O.set_f32_mode(0)
+    O.set_threads(1)
+    yield
+    O.set_f32_mode(0)
+
+
+def test_primitive_kats():
+    M = KAT["H"]
+    assert np.array_equal(O.get_perspective_transform(KAT["H_src"], KAT["H_dst"]), M)
+    assert np.array_equal(O.invert3x3(M), KAT["H_inv"])
+    p = GOLD["cv2"]["primitives"]
+    assert sha(O.warp_u8c4(KAT["warp_src_u8c4"], M, (256, 256))) == p["warp_u8c4_256"]
+    assert sha(O.warp_s16c3_reflect(KAT["warp_src_s16c3"], M, (256, 256))) == p["warp_s16c3_reflect_256"]
+    assert sha(O.warp_f32_nearest(KAT["warp_src_f32"], M, (256, 256))) == p["warp_f32_nearest_249_256"]
+    for key in ("16x16", "5x7", "64x48"):
+        a, f = KAT["pyr_s16_" + key], KAT["pyr_f32_" + key]
+        assert np.array_equal(O.pyrdown_s16(a), KAT["pyrdown_s16_" + key])
+        assert np.array_equal(O.pyrup_s16(a), KAT["pyrup_s16_" + key])
+        assert np.array_equal(O.pyrdown_f32(f), KAT["pyrdown_f32_249_" + key])
+        O.set_f32_mode(1)
+        assert np.array_equal(O.pyrdown_f32(f), KAT["pyrdown_f32_cv2_" + key])
+        O.set_f32_mode(0)
+
+
+@pytest.mark.parametrize("name", sorted(GOLD["sequences"]))
+@pytest.mark.parametrize("typ", [1, 3])
+def test_oracle_reproduces_opencv_goldens(name, typ):
+    gold = GOLD["cv2"]["%s/type%d" % (name, typ)]
+    seq = synth.Sequence(**GOLD["sequences"][name])
+    O.set_f32_mode(1)  # cv2 4.x float association for the weight pyramid; everything else is mode-independent
+    o = O.OracleMap2D(typ)
+    assert o.prepare(seq.plane, seq.camera, seq.prepare_poses)
+    for k in range(seq.n):
+        assert o.feed(seq.frame(k), seq.poses[k]) == gold["accepted"][k]
+        if gold["accepted"][k]:
+            assert list(o.last_rect()) == gold["rects"][k]
+    g = o.grid()
+    assert (g["w"], g["h"]) == (gold["grid"]["w"], gold["grid"]["h"])
+    assert list(g["min"]) == gold["grid"]["min"] and list(g["max"]) == gold["grid"]["max"]
+    assert g["length_pixel"] == gold["grid"]["length_pixel"]
+    assert state_record(o, typ) == gold["tiles"]
+    img, org = o.get_image()
+    assert sha(img) == gold["mosaic"] and list(org) == gold["mosaic_origin"] and list(img.shape) == gold["mosaic_shape"]
+
+
+@pytest.mark.parametrize("name", sorted(GOLD["sequences"]))
+@pytest.mark.parametrize("typ", [1, 3])
+def test_oracle_default_mode_goldens(name, typ):
+    gold = GOLD["oracle249"]["%s/type%d" % (name, typ)]
+    seq = synth.Sequence(**GOLD["sequences"][name])
+    o = O.OracleMap2D(typ)
+    assert o.prepare(seq.plane, seq.camera, seq.prepare_poses)
+    for k in range(seq.n):
+        o.feed(seq.frame(k), seq.poses[k])
+    assert state_record(o, typ) == gold["tiles"]
+    assert sha(o.get_image()[0]) == gold["mosaic"]
+    assert o.stats() == gold["stats"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(GOLD["sequences"]))
+@pytest.mark.parametrize("typ", [1, 3])
+def test_cuda_path_reproduces_goldens(name, typ):
+    """The CUDA path through the C-ABI against the committed fixtures: tile rects and grid against the OpenCV
+    goldens (float-association independent), raw state and mosaic against the 2.4.9-association goldens."""
+    import pi_slam_fusion_b200.map2d as m2d
+    cvg = GOLD["cv2"]["%s/type%d" % (name, typ)]
+    gold = GOLD["oracle249"]["%s/type%d" % (name, typ)]
+    seq = synth.Sequence(**GOLD["sequences"][name])
+    g = m2d.Map2D.create(typ, thread=False, collect_stats=1)
+    assert g.prepare(seq.plane, seq.camera, seq.prepare_poses)
+    for k in range(seq.n):
+        assert g.feed(seq.frame(k), seq.poses[k]) == cvg["accepted"][k]
+        if cvg["accepted"][k]:
+            assert list(g.last_rect()) == cvg["rects"][k]
+    gg = g.grid()
+    assert (gg["w"], gg["h"]) == (cvg["grid"]["w"], cvg["grid"]["h"])
+    assert list(gg["min"]) == cvg["grid"]["min"] and list(gg["max"]) == cvg["grid"]["max"]
+    assert state_record(g, typ) == gold["tiles"]
+    img, org = g.get_image()
+    assert sha(img) == gold["mosaic"] and list(org) == gold["mosaic_origin"]
+    if typ == 1:  # weighted state is integer-only: it must also equal the pure-OpenCV golden
+        assert state_record(g, typ) == cvg["tiles"] and sha(img) == cvg["mosaic"]
+    s = g.stats()
+    for k in ("frames_fused", "input_px", "region_px", "fresh_px", "win_px"):
+        assert s[k] == gold["stats"][k], k
+    g.close()
