@@ -31,24 +31,6 @@ __device__ __forceinline__ int reflect101_idx(int p, int len) {  // BORDER_REFLE
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 __device__ __forceinline__ int sat16(int v) { return min(max(v, -32768), 32767); }
 
-// cv::warpPerspectiveInvoker coordinate for destination px (x,y): the row base is formed at the first column of
-// the 64-px block and advanced by M0*x1 (same association as OpenCV; region widths are multiples of 256).
-// Returns the un-quantised source coordinate; INTER_LINEAR uses rint(32*f), INTER_NEAREST rint(f) — 32/W is
-// exactly 32*(1/W) in binary floating point, so one division serves both.
-__device__ __forceinline__ void warp_coord(const double* M, int x, int y, double& fx, double& fy) {
-    int xb = x & ~63, x1 = x & 63;
-    double X0 = M[0] * xb + M[1] * y + M[2];
-    double Y0 = M[3] * xb + M[4] * y + M[5];
-    double W0 = M[6] * xb + M[7] * y + M[8];
-    double W = W0 + M[6] * x1;
-    W = (W != 0.0) ? 1.0 / W : 0.0;
-    fx = (X0 + M[0] * x1) * W;
-    fy = (Y0 + M[3] * x1) * W;
-}
-__device__ __forceinline__ int round_coord(double f) {  // saturate_cast<int>(max(INT_MIN, min(INT_MAX, f)))
-    return __double2int_rn(fmax(-2147483648.0, fmin(2147483647.0, f)));
-}
-
 __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
@@ -104,186 +86,300 @@ cudaError_t launch_bounds(const GridGeom& g, int n, const double* d_poses, Frame
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// weighted mode: fused warp (8UC4 bilinear, constant-0 border) + max-alpha select  (Map2DCPU.cpp:282-333)
-// One CTA = 4 rows x 256 px of one tile; one thread = 4 consecutive px (one 16-byte state vector).
+// shared sampling helpers
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t fetch_bgra(const WeightedParams& p, int sx, int sy) {
-    if ((unsigned)sx >= (unsigned)p.sw || (unsigned)sy >= (unsigned)p.sh) return 0u;
-    const uint8_t* q = p.src + (size_t)sy * p.src_stride + 3 * sx;
-    uint32_t a = __ldg(p.alpha + (size_t)sy * p.sw + sx);
-    return (uint32_t)__ldg(q) | ((uint32_t)__ldg(q + 1) << 8) | ((uint32_t)__ldg(q + 2) << 16) | (a << 24);
+// Row base of cv::warpPerspectiveInvoker for the 64-px block containing x: X0 = M0*xb + M1*y + M2, etc.
+struct RowBase { double X0, Y0, W0; };
+__device__ __forceinline__ RowBase row_base(const double* M, int x, int y) {
+    int xb = x & ~63;
+    RowBase r;
+    r.X0 = M[0] * xb + M[1] * y + M[2];
+    r.Y0 = M[3] * xb + M[4] * y + M[5];
+    r.W0 = M[6] * xb + M[7] * y + M[8];
+    return r;
 }
+// Un-quantised source coordinate of the px at offset x1 (as a double, exactly the int->double value OpenCV
+// multiplies by) inside the block.  INTER_LINEAR rounds 32*f, INTER_NEAREST rounds f (32/W == 32*(1/W) exactly).
+__device__ __forceinline__ void px_coord(const double* M, const RowBase& r, double x1, double& fx, double& fy) {
+    double W = r.W0 + M[6] * x1;
+    W = (W != 0.0) ? 1.0 / W : 0.0;
+    fx = (r.X0 + M[0] * x1) * W;
+    fy = (r.Y0 + M[3] * x1) * W;
+}
+// saturate_cast<int>(double): __double2int_rn rounds half to even and saturates, which equals OpenCV's
+// max(INT_MIN, min(INT_MAX, f)) followed by cvRound for every non-NaN input.
+__device__ __forceinline__ int rnd(double f) { return __double2int_rn(f); }
+__device__ __forceinline__ int sat_s16(int v) { return min(max(v, -32768), 32767); }
 
-__device__ __forceinline__ uint32_t sample_bgra(const WeightedParams& p, int x, int y) {
-    double fx, fy;
-    warp_coord(p.hinv, x, y, fx, fy);
-    int X = round_coord(fx * 32.0), Y = round_coord(fy * 32.0);
-    int sx = clampi(X >> 5, -32768, 32767), sy = clampi(Y >> 5, -32768, 32767);
-    if (sx >= p.sw || sx + 1 < 0 || sy >= p.sh || sy + 1 < 0) return 0u;
-    int a = X & 31, b = Y & 31;
-    uint32_t w00 = (32 - a) * (32 - b), w01 = a * (32 - b), w10 = (32 - a) * b, w11 = a * b;
-    uint32_t v00 = fetch_bgra(p, sx, sy), v01 = fetch_bgra(p, sx + 1, sy);
-    uint32_t v10 = fetch_bgra(p, sx, sy + 1), v11 = fetch_bgra(p, sx + 1, sy + 1);
-    uint32_t out = 0;
-#pragma unroll
-    for (int c = 0; c < 4; c++) {
-        int sh = 8 * c;
-        uint32_t v = ((v00 >> sh) & 255u) * w00 + ((v01 >> sh) & 255u) * w01 + ((v10 >> sh) & 255u) * w10 +
-                     ((v11 >> sh) & 255u) * w11;
-        out |= ((v + 512u) >> 10) << sh;  // == (sum*32 + 16384) >> 15 of FixedPtCast<int,uchar,15>; <= 255
+constexpr uint32_t kM2 = 0x00FF00FFu;  // two 16-bit lanes holding one byte each
+
+// ---------------------------------------------------------------------------------------------------------
+// pack: BGR8 -> u8x4 (B,G,R,A).  Weighted mode: A = distance-to-centre alpha, i.e. exactly the reference's 8UC4
+// `src` image (Map2DCPU.cpp:259-275) built at HBM speed; multi-band: A = 0.  One thread = 4 px.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_kernel(const __grid_constant__ GroupParams p) {
+    const FrameJob& J = p.jobs[blockIdx.y];
+    size_t npx = (size_t)p.sw * p.sh;
+    size_t i = ((size_t)blockIdx.x * 256 + threadIdx.x) * 4;
+    if (i >= npx) return;
+    bool fast = ((p.sw & 3) == 0) && ((J.raw_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(J.raw) & 3) == 0);
+    uint32_t o[4];
+    if (fast) {
+        int row = (int)(i / p.sw), col = (int)(i % p.sw);
+        const uint32_t* q = reinterpret_cast<const uint32_t*>(J.raw + (size_t)row * J.raw_stride + 3 * col);
+        uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+        o[0] = w0 & 0x00FFFFFFu;
+        o[1] = (w0 >> 24) | ((w1 & 0xFFFFu) << 8);
+        o[2] = (w1 >> 16) | ((w2 & 0xFFu) << 16);
+        o[3] = w2 >> 8;
+        if (p.alpha) {
+            uint32_t a4 = __ldg(reinterpret_cast<const uint32_t*>(p.alpha + i));
+            o[0] |= (a4 & 0xFFu) << 24; o[1] |= (a4 & 0xFF00u) << 16; o[2] |= (a4 & 0xFF0000u) << 8; o[3] |= a4 & 0xFF000000u;
+        }
+        *reinterpret_cast<uint4*>(J.packed + i) = make_uint4(o[0], o[1], o[2], o[3]);
+    } else {
+        for (int k = 0; k < 4 && i + k < npx; k++) {
+            int row = (int)((i + k) / p.sw), col = (int)((i + k) % p.sw);
+            const uint8_t* q = J.raw + (size_t)row * J.raw_stride + 3 * col;
+            uint32_t v = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16);
+            if (p.alpha) v |= (uint32_t)p.alpha[i + k] << 24;
+            J.packed[i + k] = v;
+        }
     }
-    return out;
+}
+cudaError_t launch_pack(const GroupParams& p, cudaStream_t stream) {
+    size_t npx = (size_t)p.sw * p.sh;
+    dim3 g((unsigned)((npx / 4 + 255) / 256 + 1), p.n_frames);
+    pack_kernel<<<g, 256, 0, stream>>>(p);
+    return cudaGetLastError();
 }
 
-__global__ void __launch_bounds__(256) weighted_fuse_kernel(const __grid_constant__ WeightedParams p) {
-    int twx = blockIdx.x % p.r.wnx, twy = blockIdx.x / p.r.wnx;
-    int tx = p.r.wx0 + twx, ty = p.r.wy0 + twy;
-    uint8_t* tp = p.table[(size_t)ty * p.grid_w + tx];
-    if (!tp) return;
-    int rtx = tx - p.r.rx0, rty = ty - p.r.ry0;
-    int bit = rty * p.r.nx + rtx;
-    bool fresh = (p.fresh[bit >> 5] >> (bit & 31)) & 1u;
+// ---------------------------------------------------------------------------------------------------------
+// weighted mode, tile-centric: one CTA = 4 rows x 256 px of one tile, one thread = 4 consecutive px (one 16-byte
+// state vector).  The thread walks the group's frames that touch the tile IN FEED ORDER, warps each (8UC4
+// bilinear, constant-0 border, Map2DCPU.cpp:282-299) and keeps the strictly-larger alpha (Map2DCPU.cpp:324-329);
+// the tile is read once and written once per group.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t tap_const0(const uint32_t* img, int sw, int sh, int sx, int sy) {
+    return ((unsigned)sx < (unsigned)sw && (unsigned)sy < (unsigned)sh) ? __ldg(img + (size_t)sy * sw + sx) : 0u;
+}
+
+// Returns the warped BGRA px, or 0 when its alpha cannot beat `cur_alpha` (colour math skipped).
+__device__ __forceinline__ uint32_t sample_bgra(const uint32_t* img, int sw, int sh, double fx, double fy, uint32_t cur_alpha,
+                                                uint32_t& out_alpha) {
+    int X = rnd(fx * 32.0), Y = rnd(fy * 32.0);
+    int sx = sat_s16(X >> 5), sy = sat_s16(Y >> 5);
+    out_alpha = 0;
+    if (sx >= sw || sx + 1 < 0 || sy >= sh || sy + 1 < 0) return 0u;
+    uint32_t v00, v01, v10, v11;
+    if ((unsigned)sx < (unsigned)(sw - 1) && (unsigned)sy < (unsigned)(sh - 1)) {
+        const uint32_t* q = img + (size_t)sy * sw + sx;
+        v00 = __ldg(q); v01 = __ldg(q + 1); v10 = __ldg(q + sw); v11 = __ldg(q + sw + 1);
+    } else {
+        v00 = tap_const0(img, sw, sh, sx, sy); v01 = tap_const0(img, sw, sh, sx + 1, sy);
+        v10 = tap_const0(img, sw, sh, sx, sy + 1); v11 = tap_const0(img, sw, sh, sx + 1, sy + 1);
+    }
+    uint32_t a = X & 31, b = Y & 31, wa0 = 32 - a, wb0 = 32 - b;
+    // horizontal pass on packed 16-bit lanes (max 255*32 = 8160 per lane)
+    uint32_t ga0 = ((v00 >> 8) & kM2) * wa0 + ((v01 >> 8) & kM2) * a;
+    uint32_t ga1 = ((v10 >> 8) & kM2) * wa0 + ((v11 >> 8) & kM2) * a;
+    uint32_t A = ((ga0 >> 16) * wb0 + (ga1 >> 16) * b + 512u) >> 10;  // == (sum*32 + 16384) >> 15 (FixedPtCast<int,uchar,15>)
+    out_alpha = A;
+    if (A <= cur_alpha) return 0u;
+    uint32_t br0 = (v00 & kM2) * wa0 + (v01 & kM2) * a;
+    uint32_t br1 = (v10 & kM2) * wa0 + (v11 & kM2) * a;
+    uint32_t B = ((br0 & 0xFFFFu) * wb0 + (br1 & 0xFFFFu) * b + 512u) >> 10;
+    uint32_t R = ((br0 >> 16) * wb0 + (br1 >> 16) * b + 512u) >> 10;
+    uint32_t G = ((ga0 & 0xFFFFu) * wb0 + (ga1 & 0xFFFFu) * b + 512u) >> 10;
+    return B | (G << 8) | (R << 16) | (A << 24);
+}
+
+__global__ void __launch_bounds__(256) weighted_group_kernel(const __grid_constant__ GroupParams p) {
+    const TileWork T = p.tiles[blockIdx.x];
     int px = (threadIdx.x & 63) * 4, py = blockIdx.y * 4 + (threadIdx.x >> 6);
-    int X = rtx * kEle + px, Y = rty * kEle + py;
-    uint4* sp = reinterpret_cast<uint4*>(tp + ((size_t)py * kEle + px) * 4);
-    uint4 st = fresh ? make_uint4(0u, 0u, 0u, 0u) : *sp;
+    uint4* sp = reinterpret_cast<uint4*>(T.state + ((size_t)py * kEle + px) * 4);
+    uint4 st = T.fresh ? make_uint4(0u, 0u, 0u, 0u) : *sp;
     uint32_t s[4] = {st.x, st.y, st.z, st.w};
-    bool changed = fresh;
+    bool changed = T.fresh != 0;
     unsigned wins = 0, foot = 0;
+    const float lim_x = (float)p.sw + 0.25f, lim_y = (float)p.sh + 0.25f;
+    for (int e = 0; e < T.count; e++) {
+        const TileEntry E = p.entries[T.first + e];
+        const FrameJob& J = p.jobs[E.frame];
+        int X = E.rtx * kEle + px, Y = E.rty * kEle + py;
+        RowBase rb = row_base(J.hinv, X, Y);
+        double x1 = (double)(X & 63);
+        double fx[4], fy[4];
+        px_coord(J.hinv, rb, x1, fx[0], fy[0]);
+        px_coord(J.hinv, rb, x1 + 3.0, fx[3], fy[3]);
+        // The 4 px lie on a line in the source too: if both ends are off the same side (with a margin far above
+        // the rounding error) every tap of every px is outside the frame -> all four warp to 0.
+        float ax = (float)fx[0], bx = (float)fx[3], ay = (float)fy[0], by = (float)fy[3];
+        bool off = (ax < -1.25f && bx < -1.25f) || (ax > lim_x && bx > lim_x) || (ay < -1.25f && by < -1.25f) || (ay > lim_y && by > lim_y);
+        if (off) continue;
+        px_coord(J.hinv, rb, x1 + 1.0, fx[1], fy[1]);
+        px_coord(J.hinv, rb, x1 + 2.0, fx[2], fy[2]);
+        bool count_wins = !(T.fresh && e == 0);
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        uint32_t d = sample_bgra(p, X + i, Y);
-        foot += (d >> 24) != 0u;
-        if ((s[i] >> 24) < (d >> 24)) {  // strict '<' : Map2DCPU.cpp:327
-            s[i] = d;
-            changed = true;
-            wins++;
+        for (int j = 0; j < 4; j++) {
+            uint32_t alpha;
+            uint32_t d = sample_bgra(J.packed, p.sw, p.sh, fx[j], fy[j], s[j] >> 24, alpha);
+            foot += alpha != 0u;
+            if (d) {  // d != 0 <=> alpha beats the state's (strict '<', Map2DCPU.cpp:327)
+                s[j] = d;
+                changed = true;
+                wins += count_wins;
+            }
         }
     }
     if (changed) *sp = make_uint4(s[0], s[1], s[2], s[3]);
     if (p.stats) {
-        unsigned long long f = warp_sum(foot), w = warp_sum(fresh ? 0u : wins);
+        unsigned long long f = warp_sum(foot), w = warp_sum(wins);
         if ((threadIdx.x & 31) == 0) {
-            if (f) atomicAdd(p.stats + 0, f);
-            if (w) atomicAdd(p.stats + 1, w);
+            if (f) atomicAdd(p.stats + 16, f);
+            if (w) atomicAdd(p.stats + 17, w);
         }
     }
 }
-cudaError_t launch_weighted(const WeightedParams& p, cudaStream_t stream) {
-    dim3 g(p.r.wnx * p.r.wny, kEle / 4);
-    weighted_fuse_kernel<<<g, 256, 0, stream>>>(p);
+cudaError_t launch_weighted_group(const GroupParams& p, cudaStream_t stream) {
+    if (p.n_tiles == 0) return cudaSuccess;
+    dim3 g(p.n_tiles, kEle / 4);
+    weighted_group_kernel<<<g, 256, 0, stream>>>(p);
     return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// multi-band, stage 1: warp the frame into level 0 of the scratch pyramid over the window
-//   image : 16SC3 bilinear with BORDER_REFLECT, exact integer form of remapBilinear<Cast<float,short>> + cvRound
+// multi-band stage 1: warp every frame of the group into level 0 of its scratch pyramid (over its window).
+//   image : 16SC3 bilinear, BORDER_REFLECT, exact integer form of remapBilinear<Cast<float,short>> + cvRound; the
+//           result is always in [0,255] so it is stored as packed u8x4 (B,G,R,0)
 //   weight: nearest from the float weight image, constant-0 border
-// One thread = 2 horizontally adjacent px; planar outputs.
+// grid = (256 px x 4 rows blocks, frame); one thread = 4 consecutive px.
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void mb_sample(const MultibandParams& p, int x, int y, int& b, int& g, int& r, float& w) {
-    double fx, fy;
-    warp_coord(p.hinv, x, y, fx, fy);
-    // weight: INTER_NEAREST
-    int nx = clampi(round_coord(fx), -32768, 32767), ny = clampi(round_coord(fy), -32768, 32767);
-    w = ((unsigned)nx < (unsigned)p.sw && (unsigned)ny < (unsigned)p.sh) ? __ldg(p.wimg + (size_t)ny * p.sw + nx) : 0.f;
-    // image: INTER_LINEAR + BORDER_REFLECT
-    int X = round_coord(fx * 32.0), Y = round_coord(fy * 32.0);
-    int sx = clampi(X >> 5, -32768, 32767), sy = clampi(Y >> 5, -32768, 32767);
-    int a = X & 31, bb = Y & 31;
-    int w00 = (32 - a) * (32 - bb), w01 = a * (32 - bb), w10 = (32 - a) * bb, w11 = a * bb;
-    int sx0 = reflect_idx(sx, p.sw), sx1 = reflect_idx(sx + 1, p.sw);
-    int sy0 = reflect_idx(sy, p.sh), sy1 = reflect_idx(sy + 1, p.sh);
-    const uint8_t* r0 = p.src + (size_t)sy0 * p.src_stride;
-    const uint8_t* r1 = p.src + (size_t)sy1 * p.src_stride;
-    const uint8_t *p00 = r0 + 3 * sx0, *p01 = r0 + 3 * sx1, *p10 = r1 + 3 * sx0, *p11 = r1 + 3 * sx1;
-    int out[3];
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-        // the float sum S00*w0+S01*w1+S10*w2+S11*w3 is exact (<= 18 bits), so cvRound(sum) == RNE(v/1024)
-        int v = (int)__ldg(p00 + c) * w00 + (int)__ldg(p01 + c) * w01 + (int)__ldg(p10 + c) * w10 + (int)__ldg(p11 + c) * w11;
-        int q = v >> 10, rem = v & 1023;
-        q += (rem > 512) || (rem == 512 && (q & 1));
-        out[c] = q;
-    }
-    b = out[0]; g = out[1]; r = out[2];
+__device__ __forceinline__ uint32_t bilinear_rne_bgr(uint32_t v00, uint32_t v01, uint32_t v10, uint32_t v11, uint32_t a, uint32_t b) {
+    uint32_t wa0 = 32 - a, wb0 = 32 - b;
+    uint32_t br0 = (v00 & kM2) * wa0 + (v01 & kM2) * a, br1 = (v10 & kM2) * wa0 + (v11 & kM2) * a;
+    uint32_t g0 = ((v00 >> 8) & 0xFFu) * wa0 + ((v01 >> 8) & 0xFFu) * a, g1 = ((v10 >> 8) & 0xFFu) * wa0 + ((v11 >> 8) & 0xFFu) * a;
+    uint32_t B = (br0 & 0xFFFFu) * wb0 + (br1 & 0xFFFFu) * b;
+    uint32_t R = (br0 >> 16) * wb0 + (br1 >> 16) * b;
+    uint32_t G = g0 * wb0 + g1 * b;
+    // the float sum S00*w0+S01*w1+S10*w2+S11*w3 is exact (<= 18 bits), so cvRound(sum) == RNE(v / 1024)
+    B = (B + 511u + ((B >> 10) & 1u)) >> 10;
+    G = (G + 511u + ((G >> 10) & 1u)) >> 10;
+    R = (R + 511u + ((R >> 10) & 1u)) >> 10;
+    return B | (G << 8) | (R << 16);
 }
 
-__global__ void __launch_bounds__(256) mb_warp_kernel(const __grid_constant__ MultibandParams p) {
-    const PyrLevel& L = p.lv[0];
-    int u = (blockIdx.x * 32 + threadIdx.x) * 2, v = blockIdx.y * 8 + threadIdx.y;
-    if (u >= L.ww || v >= L.wh) return;
-    int x = u + L.ox, y = v + L.oy;
-    int b0, g0, r0, b1, g1, r1;
-    float w0, w1;
-    mb_sample(p, x, y, b0, g0, r0, w0);
-    mb_sample(p, x + 1, y, b1, g1, r1, w1);
-    size_t o = (size_t)v * L.ww + u;
-    *reinterpret_cast<short2*>(L.g[0] + o) = make_short2((short)b0, (short)b1);
-    *reinterpret_cast<short2*>(L.g[1] + o) = make_short2((short)g0, (short)g1);
-    *reinterpret_cast<short2*>(L.g[2] + o) = make_short2((short)r0, (short)r1);
-    *reinterpret_cast<float2*>(L.w + o) = make_float2(w0, w1);
+__global__ void __launch_bounds__(256) mb_warp_kernel(const __grid_constant__ GroupParams p) {
+    const FrameJob& J = p.jobs[blockIdx.y];
+    const int ww = J.wnx * kEle, wh = J.wny * kEle;
+    const int bpr = J.wnx;  // 256-px blocks per window row
+    int by = blockIdx.x / bpr, bx = blockIdx.x - by * bpr;
+    if (by * 4 >= wh) return;
+    int u = bx * kEle + (threadIdx.x & 63) * 4, v = by * 4 + (threadIdx.x >> 6);
+    int x = u + J.wx * kEle, y = v + J.wy * kEle;  // region coordinates
+    RowBase rb = row_base(J.hinv, x, y);
+    double x1 = (double)(x & 63);
+    const int sw = p.sw, sh = p.sh;
+    const uint32_t* img = J.packed;
+    uint32_t g[4];
+    float w[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        double fx, fy;
+        px_coord(J.hinv, rb, x1 + (double)j, fx, fy);
+        int nx = sat_s16(rnd(fx)), ny = sat_s16(rnd(fy));
+        w[j] = ((unsigned)nx < (unsigned)sw && (unsigned)ny < (unsigned)sh) ? __ldg(p.wimg + (size_t)ny * sw + nx) : 0.f;
+        int X = rnd(fx * 32.0), Y = rnd(fy * 32.0);
+        int sx = sat_s16(X >> 5), sy = sat_s16(Y >> 5);
+        uint32_t v00, v01, v10, v11;
+        if ((unsigned)sx < (unsigned)(sw - 1) && (unsigned)sy < (unsigned)(sh - 1)) {
+            const uint32_t* q = img + (size_t)sy * sw + sx;
+            v00 = __ldg(q); v01 = __ldg(q + 1); v10 = __ldg(q + sw); v11 = __ldg(q + sw + 1);
+        } else {
+            int sx0 = reflect_idx(sx, sw), sx1 = reflect_idx(sx + 1, sw), sy0 = reflect_idx(sy, sh), sy1 = reflect_idx(sy + 1, sh);
+            const uint32_t *r0 = img + (size_t)sy0 * sw, *r1 = img + (size_t)sy1 * sw;
+            v00 = __ldg(r0 + sx0); v01 = __ldg(r0 + sx1); v10 = __ldg(r1 + sx0); v11 = __ldg(r1 + sx1);
+        }
+        g[j] = bilinear_rne_bgr(v00, v01, v10, v11, X & 31, Y & 31);
+    }
+    size_t o = (size_t)v * ww + u;
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint32_t*>(p.scratch + J.g_off[0]) + o) = make_uint4(g[0], g[1], g[2], g[3]);
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.scratch + J.w_off[0]) + o) = make_float4(w[0], w[1], w[2], w[3]);
 }
-cudaError_t launch_mb_warp(const MultibandParams& p, cudaStream_t stream) {
-    dim3 b(32, 8), g((p.lv[0].ww / 2 + 31) / 32, (p.lv[0].wh + 7) / 8);
-    mb_warp_kernel<<<g, b, 0, stream>>>(p);
+cudaError_t launch_mb_warp(const GroupParams& p, cudaStream_t stream) {
+    dim3 g(p.max_wnx * p.max_wny * (kEle / 4), p.n_frames);
+    mb_warp_kernel<<<g, 256, 0, stream>>>(p);
     return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// multi-band, stage 2: pyrDown level l -> l+1 of the scratch pyramid (3 int16 planes + f32 weight plane).
-// Border = BORDER_REFLECT_101 in REGION coordinates (the window may be a sub-rectangle when tiles are sharded).
+// multi-band stage 2: pyrDown level l -> l+1 for every frame of the group (u8x4 Gaussian + f32 weight).
+// Separable [1 4 6 4 1], BORDER_REFLECT_101 in REGION coordinates.  The int path runs on packed 16-bit lanes
+// (B,R in one register, G alone): row sums <= 4080, column sums <= 65280, (x+128)>>8 -- no lane ever overflows.
+// One thread = one output column x 4 consecutive output rows (11 input rows, sliding window).
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) mb_pyrdown_kernel(const __grid_constant__ MultibandParams p, int l) {
-    const PyrLevel& S = p.lv[l];
-    const PyrLevel& D = p.lv[l + 1];
-    int u = blockIdx.x * 32 + threadIdx.x, v = blockIdx.y * 8 + threadIdx.y;
-    if (u >= D.ww || v >= D.wh) return;
-    int U = u + D.ox, V = v + D.oy;
-    int xs[5], ys[5];
+__global__ void __launch_bounds__(256) mb_pyrdown_kernel(const __grid_constant__ GroupParams p, int l) {
+    const FrameJob& J = p.jobs[blockIdx.y];
+    const int ns = kEle >> l, nd = kEle >> (l + 1);
+    const int sww = J.wnx * ns, swh = J.wny * ns, srw = J.nx * ns, srh = J.ny * ns, sox = J.wx * ns, soy = J.wy * ns;
+    const int dww = J.wnx * nd, dwh = J.wny * nd, dox = J.wx * nd, doy = J.wy * nd;
+    const int bpr = (dww + 31) / 32;
+    int by = blockIdx.x / bpr, bx = blockIdx.x - by * bpr;
+    int u = bx * 32 + threadIdx.x, v0 = (by * 8 + threadIdx.y) * 4;
+    if (u >= dww || v0 >= dwh) return;
+    const uint32_t* SG = reinterpret_cast<const uint32_t*>(p.scratch + J.g_off[l]);
+    const float* SW = reinterpret_cast<const float*>(p.scratch + J.w_off[l]);
+    uint32_t* DG = reinterpret_cast<uint32_t*>(p.scratch + J.g_off[l + 1]);
+    float* DW = reinterpret_cast<float*>(p.scratch + J.w_off[l + 1]);
+    int U = u + dox;
+    int xs[5];
 #pragma unroll
-    for (int d = 0; d < 5; d++) {
-        xs[d] = clampi(reflect101_idx(2 * U + d - 2, S.rw) - S.ox, 0, S.ww - 1);
-        ys[d] = clampi(reflect101_idx(2 * V + d - 2, S.rh) - S.oy, 0, S.wh - 1);
+    for (int d = 0; d < 5; d++) xs[d] = clampi(reflect101_idx(2 * U + d - 2, srw) - sox, 0, sww - 1);
+    uint32_t hbr[11], hg[11];
+    float hw[11];
+    int V0 = v0 + doy;
+#pragma unroll
+    for (int r = 0; r < 11; r++) {
+        int ys = clampi(reflect101_idx(2 * V0 + r - 2, srh) - soy, 0, swh - 1);
+        const uint32_t* gr = SG + (size_t)ys * sww;
+        const float* wr = SW + (size_t)ys * sww;
+        uint32_t a = gr[xs[0]], b = gr[xs[1]], c = gr[xs[2]], d = gr[xs[3]], e = gr[xs[4]];
+        hbr[r] = (c & kM2) * 6u + ((b & kM2) + (d & kM2)) * 4u + (a & kM2) + (e & kM2);
+        hg[r] = ((c >> 8) & 0xFFu) * 6u + (((b >> 8) & 0xFFu) + ((d >> 8) & 0xFFu)) * 4u + ((a >> 8) & 0xFFu) + ((e >> 8) & 0xFFu);
+        // f32, OpenCV 2.4.9 association: s0*6 + (s-1 + s1)*4 + s-2 + s2, left to right
+        hw[r] = wr[xs[2]] * 6.f + (wr[xs[1]] + wr[xs[3]]) * 4.f + wr[xs[0]] + wr[xs[4]];
     }
-    size_t o = (size_t)v * D.ww + u;
 #pragma unroll
-    for (int c = 0; c < 3; c++) {
-        const int16_t* G = S.g[c];
-        int acc = 0;
-#pragma unroll
-        for (int d = 0; d < 5; d++) {
-            const int16_t* row = G + (size_t)ys[d] * S.ww;
-            int h = row[xs[2]] * 6 + (row[xs[1]] + row[xs[3]]) * 4 + row[xs[0]] + row[xs[4]];
-            const int kv = (d == 0 || d == 4) ? 1 : ((d == 2) ? 6 : 4);
-            acc += kv * h;
-        }
-        D.g[c][o] = (int16_t)sat16((acc + 128) >> 8);
-    }
-    {
-        // f32, OpenCV 2.4.9 association: rows s0*6 + (s-1+s1)*4 + s-2 + s2 (left to right);
-        // columns ((r0+r4)+(r2+r2)) + ((r1+r3)+r2)*4, scaled by 1/256.
-        float h[5];
-#pragma unroll
-        for (int d = 0; d < 5; d++) {
-            const float* row = S.w + (size_t)ys[d] * S.ww;
-            h[d] = row[xs[2]] * 6.f + (row[xs[1]] + row[xs[3]]) * 4.f + row[xs[0]] + row[xs[4]];
-        }
-        float t0 = (h[0] + h[4]) + (h[2] + h[2]);
-        float t1 = (h[1] + h[3]) + h[2];
-        D.w[o] = (t0 + t1 * 4.f) * (1.f / 256.f);
+    for (int k = 0; k < 4; k++) {
+        int v = v0 + k;
+        if (v >= dwh) break;
+        int r = 2 * k;
+        uint32_t vbr = hbr[r] + hbr[r + 4] + (hbr[r + 1] + hbr[r + 3]) * 4u + hbr[r + 2] * 6u;
+        uint32_t vg = hg[r] + hg[r + 4] + (hg[r + 1] + hg[r + 3]) * 4u + hg[r + 2] * 6u;
+        uint32_t obr = ((vbr + 0x00800080u) >> 8) & kM2;
+        uint32_t og = (vg + 128u) >> 8;
+        // columns ((r0+r4)+(r2+r2)) + ((r1+r3)+r2)*4, scaled by 1/256 (PyrDownVec_32f of OpenCV 2.4.9)
+        float t0 = (hw[r] + hw[r + 4]) + (hw[r + 2] + hw[r + 2]);
+        float t1 = (hw[r + 1] + hw[r + 3]) + hw[r + 2];
+        size_t o = (size_t)v * dww + u;
+        DG[o] = obr | (og << 8);
+        DW[o] = (t0 + t1 * 4.f) * (1.f / 256.f);
     }
 }
-cudaError_t launch_mb_pyrdown(const MultibandParams& p, int level, cudaStream_t stream) {
-    const PyrLevel& D = p.lv[level + 1];
-    dim3 b(32, 8), g((D.ww + 31) / 32, (D.wh + 7) / 8);
+cudaError_t launch_mb_pyrdown(const GroupParams& p, int level, cudaStream_t stream) {
+    // grid.x bound: the widest / tallest window of the group at level+1, in 32 x 32 output blocks
+    int nd = kEle >> (level + 1);
+    int blocks = ((p.max_wnx * nd + 31) / 32) * ((p.max_wny * nd + 31) / 32);
+    dim3 b(32, 8), g(blocks, p.n_frames);
     mb_pyrdown_kernel<<<g, b, 0, stream>>>(p, level);
     return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// multi-band, stage 3: Laplacian (G_l - pyrUp(G_{l+1}), never materialised) + per-band '>=' select into the
-// tile state, all levels in one launch.  One thread = 2 horizontally adjacent px of one level of one tile.
+// multi-band stage 3, tile-centric: per tile px (all levels in one launch) find the LAST frame of the group whose
+// weight is >= everything before it (state included) -- exactly what sequential `if (srcW >= dstW)` updates leave
+// behind (MultiBandMap2DCPU.cpp:539-547; 0 >= 0 ties overwrite) -- and only for that frame form the Laplacian
+// G_l - pyrUp(G_{l+1}) (never materialised) and store it.  One thread = 2 horizontally adjacent px.
 // ---------------------------------------------------------------------------------------------------------
 TileLayout make_tile_layout(int levels) {
     TileLayout t{};
@@ -309,16 +405,56 @@ TileLayout make_tile_layout(int levels) {
 __device__ __forceinline__ int pyrup_axis_lo(int i, int n) { return i < 0 ? (n > 1 ? 1 : 0) : i; }  // reflect-101 at -1
 __device__ __forceinline__ int pyrup_axis_hi(int i, int n) { return i >= n ? n - 1 : i; }          // replicate at n
 
-__global__ void __launch_bounds__(256) mb_select_kernel(const __grid_constant__ MultibandParams p,
-                                                        const __grid_constant__ TileLayout lay) {
-    int twx = blockIdx.x % p.r.wnx, twy = blockIdx.x / p.r.wnx;
-    int tx = p.r.wx0 + twx, ty = p.r.wy0 + twy;
-    uint8_t* tp = p.table[(size_t)ty * p.grid_w + tx];
-    if (!tp) return;
-    int rtx = tx - p.r.rx0, rty = ty - p.r.ry0;
-    int bit = rty * p.r.nx + rtx;
-    bool fresh = (p.fresh[bit >> 5] >> (bit & 31)) & 1u;
+// Laplacian of the px pair (X, X+1) at row Y of level l of frame J (region coordinates).
+__device__ __forceinline__ void lap_pair(const GroupParams& p, const FrameJob& J, int l, int X, int Y, bool two, int* lap0, int* lap1) {
+    const int n = kEle >> l;
+    const int ww = J.wnx * n, ox = J.wx * n, oy = J.wy * n;
+    const uint32_t* G = reinterpret_cast<const uint32_t*>(p.scratch + J.g_off[l]);
+    size_t so = (size_t)(Y - oy) * ww + (X - ox);
+    uint32_t g0 = G[so], g1 = two ? G[so + 1] : 0u;
+    if (l == p.levels - 1) {
+        lap0[0] = g0 & 0xFF; lap0[1] = (g0 >> 8) & 0xFF; lap0[2] = (g0 >> 16) & 0xFF;
+        lap1[0] = g1 & 0xFF; lap1[1] = (g1 >> 8) & 0xFF; lap1[2] = (g1 >> 16) & 0xFF;
+        return;
+    }
+    const int nc = n >> 1;
+    const int cww = J.wnx * nc, cwh = J.wny * nc, crw = J.nx * nc, crh = J.ny * nc, cox = J.wx * nc, coy = J.wy * nc;
+    const uint32_t* C = reinterpret_cast<const uint32_t*>(p.scratch + J.g_off[l + 1]);
+    int i = X >> 1, j = Y >> 1;
+    int c0 = clampi(pyrup_axis_lo(i - 1, crw) - cox, 0, cww - 1), c1 = clampi(i - cox, 0, cww - 1);
+    int c2 = clampi(pyrup_axis_hi(i + 1, crw) - cox, 0, cww - 1);
+    int r0 = clampi(pyrup_axis_lo(j - 1, crh) - coy, 0, cwh - 1), r1 = clampi(j - coy, 0, cwh - 1);
+    int r2 = clampi(pyrup_axis_hi(j + 1, crh) - coy, 0, cwh - 1);
+    const uint32_t *q0 = C + (size_t)r0 * cww, *q1 = C + (size_t)r1 * cww, *q2 = C + (size_t)r2 * cww;
+    uint32_t ebr[3], eg[3], obr[3], og[3];  // even / odd column sums per coarse row, packed lanes (<= 2040)
+    {
+        uint32_t a = q0[c0], b = q0[c1], c = q0[c2];
+        ebr[0] = (a & kM2) + (b & kM2) * 6u + (c & kM2); obr[0] = ((b & kM2) + (c & kM2)) * 4u;
+        eg[0] = ((a >> 8) & 0xFFu) + ((b >> 8) & 0xFFu) * 6u + ((c >> 8) & 0xFFu); og[0] = (((b >> 8) & 0xFFu) + ((c >> 8) & 0xFFu)) * 4u;
+        a = q1[c0]; b = q1[c1]; c = q1[c2];
+        ebr[1] = (a & kM2) + (b & kM2) * 6u + (c & kM2); obr[1] = ((b & kM2) + (c & kM2)) * 4u;
+        eg[1] = ((a >> 8) & 0xFFu) + ((b >> 8) & 0xFFu) * 6u + ((c >> 8) & 0xFFu); og[1] = (((b >> 8) & 0xFFu) + ((c >> 8) & 0xFFu)) * 4u;
+        a = q2[c0]; b = q2[c1]; c = q2[c2];
+        ebr[2] = (a & kM2) + (b & kM2) * 6u + (c & kM2); obr[2] = ((b & kM2) + (c & kM2)) * 4u;
+        eg[2] = ((a >> 8) & 0xFFu) + ((b >> 8) & 0xFFu) * 6u + ((c >> 8) & 0xFFu); og[2] = (((b >> 8) & 0xFFu) + ((c >> 8) & 0xFFu)) * 4u;
+    }
+    bool yodd = Y & 1;
+    uint32_t vebr = yodd ? (ebr[1] + ebr[2]) * 4u : (ebr[0] + ebr[1] * 6u + ebr[2]);   // <= 16320 per lane
+    uint32_t vobr = yodd ? (obr[1] + obr[2]) * 4u : (obr[0] + obr[1] * 6u + obr[2]);
+    uint32_t veg = yodd ? (eg[1] + eg[2]) * 4u : (eg[0] + eg[1] * 6u + eg[2]);
+    uint32_t vog = yodd ? (og[1] + og[2]) * 4u : (og[0] + og[1] * 6u + og[2]);
+    uint32_t uebr = ((vebr + 0x00200020u) >> 6) & kM2, uobr = ((vobr + 0x00200020u) >> 6) & kM2;  // pyrUp px, <= 255
+    int ueg = (int)((veg + 32u) >> 6), uog = (int)((vog + 32u) >> 6);
+    lap0[0] = (int)(g0 & 0xFF) - (int)(uebr & 0xFFFF);
+    lap0[1] = (int)((g0 >> 8) & 0xFF) - ueg;
+    lap0[2] = (int)((g0 >> 16) & 0xFF) - (int)(uebr >> 16);
+    lap1[0] = (int)(g1 & 0xFF) - (int)(uobr & 0xFFFF);
+    lap1[1] = (int)((g1 >> 8) & 0xFF) - uog;
+    lap1[2] = (int)((g1 >> 16) & 0xFF) - (int)(uobr >> 16);
+}
 
+__global__ void __launch_bounds__(256) mb_select_kernel(const __grid_constant__ GroupParams p, const __grid_constant__ TileLayout lay) {
+    const TileWork T = p.tiles[blockIdx.x];
     // flat pair index -> (level, row, column pair)
     int pair = blockIdx.y * 256 + threadIdx.x;
     int l = 0, n = kEle, half = kEle / 2;
@@ -331,85 +467,75 @@ __global__ void __launch_bounds__(256) mb_select_kernel(const __grid_constant__ 
     }
     bool valid = l < p.levels;
     if (!valid) { l = p.levels - 1; n = kEle >> l; half = n > 1 ? n / 2 : 1; pair = 0; }
-    int py = pair / half, px = (pair % half) * 2;
+    int py = pair / half, px = (pair - py * half) * 2;
     bool two = n > 1;
-    const PyrLevel& L = p.lv[l];
-    int X = rtx * n + px, Y = rty * n + py;  // region coordinates at level l
-    size_t so = (size_t)(Y - L.oy) * L.ww + (X - L.ox);
-    float sw0 = L.w[so], sw1 = two ? L.w[so + 1] : 0.f;
     size_t to = (size_t)py * n + px;
-    float* tw = reinterpret_cast<float*>(tp + lay.wgt_off[l]) + to;
-    bool win0, win1;
-    if (fresh) { win0 = true; win1 = two; }
-    else {
-        float dw0 = tw[0], dw1 = two ? tw[1] : 0.f;
-        win0 = sw0 >= dw0;            // '>=' : MultiBandMap2DCPU.cpp:542 (0 >= 0 ties overwrite)
-        win1 = two && (sw1 >= dw1);
+    float* tw = reinterpret_cast<float*>(T.state + lay.wgt_off[l]) + to;
+    float bw0, bw1;
+    if (T.fresh) { bw0 = -INFINITY; bw1 = -INFINITY; }  // first toucher copies unconditionally (:498-504)
+    else if (two) { float2 t = *reinterpret_cast<const float2*>(tw); bw0 = t.x; bw1 = t.y; }
+    else { bw0 = tw[0]; bw1 = 0.f; }
+    int best0 = -1, best1 = -1;
+    unsigned wins = 0;
+    for (int e = 0; e < T.count; e++) {
+        const TileEntry E = p.entries[T.first + e];
+        const FrameJob& J = p.jobs[E.frame];
+        const int ww = J.wnx * n;
+        const float* W = reinterpret_cast<const float*>(p.scratch + J.w_off[l]);
+        size_t so = (size_t)(E.rty * n + py - J.wy * n) * ww + (E.rtx * n + px - J.wx * n);
+        float s0, s1;
+        if (two) { float2 t = *reinterpret_cast<const float2*>(W + so); s0 = t.x; s1 = t.y; }
+        else { s0 = W[so]; s1 = 0.f; }
+        bool count_wins = !(T.fresh && e == 0);
+        if (s0 >= bw0) { bw0 = s0; best0 = e; wins += count_wins; }   // '>=' : MultiBandMap2DCPU.cpp:542
+        if (two && s1 >= bw1) { bw1 = s1; best1 = e; wins += count_wins; }
     }
-    win0 = win0 && valid; win1 = win1 && valid;
+    if (!valid) { best0 = best1 = -1; wins = 0; }
     if (p.stats) {  // block-uniform branch: every lane reaches the shuffle
-        unsigned long long w = warp_sum(fresh ? 0u : ((unsigned)win0 + (unsigned)win1));
+        unsigned long long w = warp_sum(wins);
         if ((threadIdx.x & 31) == 0 && w) atomicAdd(p.stats + l, w);
     }
-    if (!win0 && !win1) return;
+    if (best0 < 0 && best1 < 0) return;
 
-    int lap0[3], lap1[3];
-    if (l == p.levels - 1) {
-#pragma unroll
-        for (int c = 0; c < 3; c++) { lap0[c] = L.g[c][so]; lap1[c] = two ? L.g[c][so + 1] : 0; }
-    } else {
-        const PyrLevel& C = p.lv[l + 1];
-        int i = X >> 1, j = Y >> 1;
-        int c0 = clampi(pyrup_axis_lo(i - 1, C.rw) - C.ox, 0, C.ww - 1);
-        int c1 = clampi(i - C.ox, 0, C.ww - 1);
-        int c2 = clampi(pyrup_axis_hi(i + 1, C.rw) - C.ox, 0, C.ww - 1);
-        int r0 = clampi(pyrup_axis_lo(j - 1, C.rh) - C.oy, 0, C.wh - 1);
-        int r1 = clampi(j - C.oy, 0, C.wh - 1);
-        int r2 = clampi(pyrup_axis_hi(j + 1, C.rh) - C.oy, 0, C.wh - 1);
-        bool yodd = Y & 1;
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            const int16_t* G = C.g[c];
-            const int16_t *q0 = G + (size_t)r0 * C.ww, *q1 = G + (size_t)r1 * C.ww, *q2 = G + (size_t)r2 * C.ww;
-            int e0 = q0[c0] + q0[c1] * 6 + q0[c2], o0 = (q0[c1] + q0[c2]) * 4;   // even / odd column, row j-1
-            int e1 = q1[c0] + q1[c1] * 6 + q1[c2], o1 = (q1[c1] + q1[c2]) * 4;   // row j
-            int e2 = q2[c0] + q2[c1] * 6 + q2[c2], o2 = (q2[c1] + q2[c2]) * 4;   // row j+1
-            int ve = yodd ? (e1 + e2) * 4 : (e0 + e1 * 6 + e2);
-            int vo = yodd ? (o1 + o2) * 4 : (o0 + o1 * 6 + o2);
-            int upe = sat16((ve + 32) >> 6), upo = sat16((vo + 32) >> 6);
-            lap0[c] = sat16((int)L.g[c][so] - upe);
-            lap1[c] = two ? sat16((int)L.g[c][so + 1] - upo) : 0;
-        }
+    int lap0[3] = {0, 0, 0}, lap1[3] = {0, 0, 0}, tmp0[3], tmp1[3];
+    if (best0 >= 0) {
+        const TileEntry E = p.entries[T.first + best0];
+        lap_pair(p, p.jobs[E.frame], l, E.rtx * n + px, E.rty * n + py, two, lap0, tmp1);
+        if (best1 == best0) { lap1[0] = tmp1[0]; lap1[1] = tmp1[1]; lap1[2] = tmp1[2]; }
+    }
+    if (best1 >= 0 && best1 != best0) {
+        const TileEntry E = p.entries[T.first + best1];
+        lap_pair(p, p.jobs[E.frame], l, E.rtx * n + px, E.rty * n + py, two, tmp0, lap1);
     }
     size_t plane = (size_t)n * n;
-    int16_t* tl = reinterpret_cast<int16_t*>(tp + lay.lap_off[l]) + to;
+    int16_t* tl = reinterpret_cast<int16_t*>(T.state + lay.lap_off[l]) + to;
     if (!two) {
         tl[0] = (int16_t)lap0[0]; tl[plane] = (int16_t)lap0[1]; tl[2 * plane] = (int16_t)lap0[2];
-        tw[0] = sw0;
+        tw[0] = bw0;
         return;
     }
-    if (win0 && win1) {
+    if (best0 >= 0 && best1 >= 0) {
 #pragma unroll
-        for (int c = 0; c < 3; c++)
-            *reinterpret_cast<short2*>(tl + c * plane) = make_short2((short)lap0[c], (short)lap1[c]);
-        *reinterpret_cast<float2*>(tw) = make_float2(sw0, sw1);
-    } else if (win0) {
+        for (int c = 0; c < 3; c++) *reinterpret_cast<short2*>(tl + c * plane) = make_short2((short)lap0[c], (short)lap1[c]);
+        *reinterpret_cast<float2*>(tw) = make_float2(bw0, bw1);
+    } else if (best0 >= 0) {
 #pragma unroll
         for (int c = 0; c < 3; c++) tl[c * plane] = (int16_t)lap0[c];
-        tw[0] = sw0;
+        tw[0] = bw0;
     } else {
 #pragma unroll
         for (int c = 0; c < 3; c++) tl[c * plane + 1] = (int16_t)lap1[c];
-        tw[1] = sw1;
+        tw[1] = bw1;
     }
 }
-cudaError_t launch_mb_select(const MultibandParams& p, const TileLayout& lay, cudaStream_t stream) {
+cudaError_t launch_mb_select(const GroupParams& p, const TileLayout& lay, cudaStream_t stream) {
+    if (p.n_tiles == 0) return cudaSuccess;
     int pairs = 0;
     for (int l = 0; l < p.levels; l++) {
         int n = kEle >> l;
         pairs += n * (n > 1 ? n / 2 : 1);
     }
-    dim3 g(p.r.wnx * p.r.wny, (pairs + 255) / 256);
+    dim3 g(p.n_tiles, (pairs + 255) / 256);
     mb_select_kernel<<<g, 256, 0, stream>>>(p, lay);
     return cudaGetLastError();
 }

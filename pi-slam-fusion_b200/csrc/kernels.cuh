@@ -1,4 +1,9 @@
 // kernels.cuh — launch parameter blocks and host-callable launchers of the sm_100a kernels.
+//
+// Execution model: frames are fused in GROUPS of up to K frames.  All per-frame stages of a group
+// (pack, warp, pyramid) run as single launches over (work, frame); the order-dependent stage (select) is
+// TILE-CENTRIC: one work item per touched tile, looping over the group's frames in feed order, so every map tile
+// is read and written once per group and the result equals K sequential feed() calls.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -9,74 +14,67 @@
 namespace m2d {
 
 constexpr int kEle = M2D_ELE_PIXELS;
-constexpr int kMaxRectTiles = 1024;  // fresh-tile bitmask capacity per frame (32 x 32 tiles = 67 Mpx region)
 
-// Geometry of one frame against the tile grid, as the kernels need it.
-struct FrameRect {
-    int rx0, ry0, nx, ny;     // frame region: origin tile (grid indexing) and size in tiles
-    int wx0, wy0, wnx, wny;   // window = bbox of the tiles this shard owns inside the region (grid indexing)
+// One frame of a group, as the kernels see it.  Lives in a device array (uploaded once per group).
+struct FrameJob {
+    double hinv[9];            // region px -> source px (inverse homography, cv::warpPerspective convention)
+    const uint8_t* raw;        // BGR8 source in HBM
+    uint32_t* packed;          // u8x4 source (B,G,R,A) built by the pack kernel; A = alpha (weighted) or 0
+    int raw_stride;
+    int nx, ny;                // frame region in tiles
+    int wx, wy, wnx, wny;      // pyramid window inside the region (tiles, relative to the region origin)
+    unsigned long long g_off[M2D_MAX_LEVELS];  // byte offset in the group scratch of level l's u8x4 Gaussian
+    unsigned long long w_off[M2D_MAX_LEVELS];  // ... of level l's f32 weight plane
 };
 
-// ------------------------------------------------------------------ weighted mode (Map2DCPU)
-struct WeightedParams {
-    double hinv[9];               // region px -> source px
-    const uint8_t* src;           // BGR8 frame in HBM
-    int src_stride, sw, sh;
-    const uint8_t* alpha;         // sw*sh distance-to-centre alpha (Map2DCPU.cpp:236-258), built once per size
-    uint8_t* const* table;        // device tile table: pointer per grid slot (NULL = none / not owned)
-    int grid_w;
-    FrameRect r;
-    uint32_t fresh[kMaxRectTiles / 32];  // bit (ty-ry0)*nx+(tx-rx0): tile allocated by this frame (skip the read)
-    unsigned long long* stats;    // optional: [0] footprint px, [1] wins on non-fresh tiles
+// Tile-centric work list of a group.
+struct TileWork {
+    uint8_t* state;            // tile state in HBM
+    int first, count;          // entries [first, first+count) in feed order
+    int fresh;                 // tile allocated by this group: no state to read
+};
+struct TileEntry {
+    int frame;                 // index into the group's FrameJob array
+    short rtx, rty;            // tile position inside that frame's region
 };
 
-// ------------------------------------------------------------------ multi-band mode (MultiBandMap2DCPU)
-// Per-frame scratch pyramid over the window (planar: 3 x int16 Gaussian planes + 1 x f32 weight plane).
-struct PyrLevel {
-    int16_t* g[3];
-    float* w;
-    int ww, wh;   // window size at this level (px)
-    int rw, rh;   // full frame-region size at this level (px): borders reflect HERE, not at the window edge
-    int ox, oy;   // window origin inside the region at this level (px)
-};
-
-struct MultibandParams {
-    double hinv[9];
-    const uint8_t* src;
-    int src_stride, sw, sh;
-    const float* wimg;            // sw*sh float weight image (MultiBandMap2DCPU.cpp:396-418)
-    uint8_t* const* table;
-    int grid_w;
-    FrameRect r;
-    uint32_t fresh[kMaxRectTiles / 32];
-    int levels;                   // band_num + 1
-    PyrLevel lv[M2D_MAX_LEVELS];
-    unsigned long long* stats;    // optional: [l] wins on non-fresh tiles at level l
+struct GroupParams {
+    const FrameJob* jobs;
+    const TileWork* tiles;
+    const TileEntry* entries;
+    int n_frames, n_tiles;
+    int sw, sh;                // source frame size
+    int levels;                // multi-band: band_num + 1
+    const uint8_t* alpha;      // weighted: sw*sh alpha image (Map2DCPU.cpp:236-258)
+    const float* wimg;         // multi-band: sw*sh float weight image (MultiBandMap2DCPU.cpp:396-418)
+    uint8_t* scratch;          // multi-band: group scratch pyramid
+    unsigned long long* stats; // optional counters (collect_stats)
+    int max_wnx, max_wny;      // largest pyramid window of the group (tiles): grid bounds of per-frame kernels
 };
 
 // Tile state layout in HBM (multi-band): for each level l (side n = 256>>l): B,G,R int16 planes then f32 weight.
 struct TileLayout {
     int levels;
-    size_t lap_off[M2D_MAX_LEVELS];  // byte offset of the first int16 plane of level l
-    size_t wgt_off[M2D_MAX_LEVELS];  // byte offset of the f32 weight plane of level l
+    size_t lap_off[M2D_MAX_LEVELS];
+    size_t wgt_off[M2D_MAX_LEVELS];
     size_t bytes;
-    int px_off[M2D_MAX_LEVELS + 1];  // cumulative pixel count (for flat work decomposition)
+    int px_off[M2D_MAX_LEVELS + 1];
 };
 TileLayout make_tile_layout(int levels);
 
-// Collapse (save / get_image): per-level mosaics over the bbox of touched tiles.
 struct MosaicLevel {
     int16_t* g[3];
     int w, h;
 };
 
-// launchers (all asynchronous on `stream`; return the cudaError of the launch)
+// launchers (asynchronous on `stream`; return the launch error)
 cudaError_t launch_weight_images(int sw, int sh, int weight_type, uint8_t* alpha, float* wimg, cudaStream_t stream);
 cudaError_t launch_bounds(const GridGeom& g, int n, const double* d_poses, FrameBounds* d_out, cudaStream_t stream);
-cudaError_t launch_weighted(const WeightedParams& p, cudaStream_t stream);
-cudaError_t launch_mb_warp(const MultibandParams& p, cudaStream_t stream);
-cudaError_t launch_mb_pyrdown(const MultibandParams& p, int level /* src level */, cudaStream_t stream);
-cudaError_t launch_mb_select(const MultibandParams& p, const TileLayout& lay, cudaStream_t stream);
+cudaError_t launch_pack(const GroupParams& p, cudaStream_t stream);
+cudaError_t launch_weighted_group(const GroupParams& p, cudaStream_t stream);
+cudaError_t launch_mb_warp(const GroupParams& p, cudaStream_t stream);
+cudaError_t launch_mb_pyrdown(const GroupParams& p, int level /* src level */, cudaStream_t stream);
+cudaError_t launch_mb_select(const GroupParams& p, const TileLayout& lay, cudaStream_t stream);
 cudaError_t launch_mosaic_clear(MosaicLevel m, float* w0, cudaStream_t stream);
 cudaError_t launch_mosaic_paste(const uint8_t* tile, const TileLayout& lay, int level, MosaicLevel m, float* w0,
                                 int tx, int ty, cudaStream_t stream);

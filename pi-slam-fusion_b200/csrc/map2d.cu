@@ -1,9 +1,11 @@
 // map2d.cu — host side of libmap2d_b200.so: the Map2D object behind the C-ABI of include/map2d_b200.h.
 //
 // Mirrors the reference classes Map2DCPU / MultiBandMap2DCPU (Map2DFusion/Map2DCPU.cpp, MultiBandMap2DCPU.cpp):
-// prepare() lays out the tile grid, feed() decides the frame's tile rectangle on the host in FP64 (geom.h, the
-// same code the bounds kernel runs), allocates first-touch tiles from a slab pool in HBM, and enqueues the fusion
-// kernels on the handle's stream.  There is no CPU fallback: without a CUDA device every call fails loudly.
+// prepare() lays out the tile grid; feed()/feed_batch() decide every frame's tile rectangle on the host in FP64
+// (geom.h, the same code the bounds kernel runs), allocate first-touch tiles from a slab pool in HBM, build the
+// group's tile-centric work list and enqueue the fusion kernels on the handle's stream.  Frames are fused in
+// groups of up to K (m2d_config.batch_frames); a single feed() is a group of one.  There is no CPU fallback:
+// without a CUDA device every call fails loudly.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -12,6 +14,7 @@
 #include <cstring>
 #include <deque>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/map2d_b200.h"
@@ -51,6 +54,23 @@ using namespace m2d;
 
 struct ProfRec { int kind; cudaEvent_t e0, e1; };
 
+// Device + pinned buffers of one in-flight group.  Two contexts alternate so that the host can prepare group g+1
+// (bounds, tile allocation, work lists, H2D copies) while the GPU fuses group g.
+struct GroupCtx {
+    cudaEvent_t done = nullptr;       // recorded after the group's last kernel
+    bool busy = false;
+    int frames = 0;
+    uint8_t* h_blob = nullptr;        // pinned: [FrameJob x K | TileWork x T | TileEntry x E]
+    uint8_t* d_blob = nullptr;
+    size_t blob_cap = 0;
+    uint32_t* d_packed = nullptr;     // K x sw*sh u8x4
+    size_t packed_cap = 0;
+    uint8_t* d_raw = nullptr;         // K x sw*sh*3 staging for host frames
+    size_t raw_cap = 0;
+    uint8_t* d_scratch = nullptr;     // multi-band pyramids of the group
+    size_t scratch_cap = 0;
+};
+
 struct m2d_map {
     int type = 0;
     m2d_config cfg{};
@@ -64,10 +84,8 @@ struct m2d_map {
     // Map2DPrepare + Map2DCPUData
     GridGeom g{};
     double min_z = 0, max_z = 0, length_pixel = 0;
-    int org_x = 0, org_y = 0;  // absolute tile coordinate of grid slot (0,0); moves under spreadMap
-    std::vector<uint8_t*> table;  // host mirror of the device tile table (w*h), NULL = untouched / not owned
-    uint8_t** d_table = nullptr;
-    size_t d_table_cap = 0;
+    int org_x = 0, org_y = 0;       // absolute tile coordinate of grid slot (0,0); moves under spreadMap
+    std::vector<uint8_t*> table;    // tile state pointer per grid slot (w*h), NULL = untouched / not owned
     int last_rect[4] = {-1, -1, -1, -1};
 
     // tile pool
@@ -82,20 +100,12 @@ struct m2d_map {
     uint8_t* d_alpha = nullptr;
     float* d_wimg = nullptr;
 
-    // frame staging ring (host images -> HBM)
-    static constexpr int kRing = 4;
-    uint8_t* d_ring[kRing] = {nullptr, nullptr, nullptr, nullptr};
-    size_t ring_bytes = 0;
-    int ring_next = 0;
-
-    // multi-band scratch pyramid
-    uint8_t* d_scratch = nullptr;
-    size_t scratch_bytes = 0;
+    static constexpr int kCtx = 2;
+    GroupCtx ctx[kCtx];
+    int ctx_next = 0;
 
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    std::deque<cudaEvent_t> inflight;
-    std::vector<cudaEvent_t> event_pool;
 
     unsigned long long* d_stats = nullptr;  // [0..8] level wins, [16] footprint, [17] weighted wins
     m2d_stats stats{};
@@ -104,18 +114,17 @@ struct m2d_map {
     void release();
     int prepare(const double* plane, const double* cam, int n, const double* poses);
     int spread(double xmin, double ymin, double xmax, double ymax);
-    int feed(const uint8_t* img, int w, int h, size_t stride, const double* pose, bool on_device);
+    int feed_frames(int n, const uint8_t* base, size_t frame_stride, int w, int h, size_t stride, const double* poses,
+                    bool on_device, int* result);
+    int run_group(int n, const uint8_t* base, size_t frame_stride, int w, int h, size_t stride, const double* poses,
+                  bool on_device, int* result);
     int ensure_weight_images(int w, int h);
-    int stage_frame(const uint8_t* img, int w, int h, size_t stride, const uint8_t** d_img, int* d_stride);
     int alloc_tile(uint8_t** out);
-    int upload_table_rows(int x0, int y0, int x1, int y1);
-    int ensure_scratch(size_t bytes);
-    int run_weighted(const FrameBounds& fb, const FrameRect& r, const uint32_t* fresh, const uint8_t* d_img, int d_stride);
-    int run_multiband(const FrameBounds& fb, const FrameRect& r, const uint32_t* fresh, const uint8_t* d_img, int d_stride);
+    int grow(void** p, size_t* cap, size_t need, bool pinned);
+    int group_size(int w, int h) const;
     bool owns(int tx, int ty) const;
     bool tile_bbox(int& x0, int& y0, int& x1, int& y1) const;
     int get_image(uint8_t* out, int* w, int* h, int* channels, int* tmx, int* tmy);
-    int mark_frame_done();
     int queue_size();
     int sync();
     int reset();
@@ -144,6 +153,7 @@ int m2d_map::init() {
     own_stream = true;
     CU(cudaMalloc(&d_stats, 32 * sizeof(unsigned long long)));
     CU(cudaMemsetAsync(d_stats, 0, 32 * sizeof(unsigned long long), stream));
+    for (int i = 0; i < kCtx; i++) CU(cudaEventCreateWithFlags(&ctx[i].done, cudaEventDisableTiming));
     levels = (type == M2D_TYPE_MULTIBAND) ? band_num + 1 : 1;
     if (type == M2D_TYPE_MULTIBAND) {
         lay = make_tile_layout(levels);
@@ -160,15 +170,19 @@ void m2d_map::release() {
     for (void* c : chunks) cudaFree(c);
     chunks.clear();
     free_tiles.clear();
-    if (d_table) cudaFree(d_table);
     if (d_alpha) cudaFree(d_alpha);
     if (d_wimg) cudaFree(d_wimg);
-    for (int i = 0; i < kRing; i++)
-        if (d_ring[i]) cudaFree(d_ring[i]);
-    if (d_scratch) cudaFree(d_scratch);
+    for (int i = 0; i < kCtx; i++) {
+        GroupCtx& c = ctx[i];
+        if (c.done) cudaEventDestroy(c.done);
+        if (c.h_blob) cudaFreeHost(c.h_blob);
+        if (c.d_blob) cudaFree(c.d_blob);
+        if (c.d_packed) cudaFree(c.d_packed);
+        if (c.d_raw) cudaFree(c.d_raw);
+        if (c.d_scratch) cudaFree(c.d_scratch);
+    }
     if (d_stats) cudaFree(d_stats);
-    for (cudaEvent_t ev : inflight) cudaEventDestroy(ev);
-    for (cudaEvent_t ev : event_pool) cudaEventDestroy(ev);
+    for (ProfRec& r : prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     if (own_stream && stream) cudaStreamDestroy(stream);
 }
 
@@ -222,18 +236,13 @@ int m2d_map::prepare(const double* plane7, const double* cam, int n, const doubl
     min_z = mn.z; max_z = mx.z; length_pixel = lp;
     org_x = org_y = 0;
     table.assign((size_t)w * h, nullptr);
-    if ((size_t)w * h > d_table_cap) {
-        if (d_table) { CU(cudaStreamSynchronize(stream)); CU(cudaFree(d_table)); d_table = nullptr; }
-        d_table_cap = (size_t)w * h * 2;
-        CU(cudaMalloc(&d_table, d_table_cap * sizeof(uint8_t*)));
-    }
-    CU(cudaMemsetAsync(d_table, 0, (size_t)w * h * sizeof(uint8_t*), stream));
     last_rect[0] = last_rect[1] = last_rect[2] = last_rect[3] = -1;
     valid = true;
     return M2D_OK;
 }
 
-// spreadMap — Map2DCPU.cpp:339-382: grow the grid (never shrinks) and re-index the tile table; no pixel moves.
+// spreadMap — Map2DCPU.cpp:339-382: grow the grid (never shrinks) and re-index the tile table; no pixel moves and,
+// because kernels address tiles by pointer, nothing on the device changes.
 int m2d_map::spread(double xmin, double ymin, double xmax, double ymax) {
     int xminInt = (int)floor((xmin - g.min_x) * g.ele_size_inv), yminInt = (int)floor((ymin - g.min_y) * g.ele_size_inv);
     int xmaxInt = (int)ceil((xmax - g.min_x) * g.ele_size_inv), ymaxInt = (int)ceil((ymax - g.min_y) * g.ele_size_inv);
@@ -250,17 +259,6 @@ int m2d_map::spread(double xmin, double ymin, double xmax, double ymax) {
     g.min_x = nminx; g.min_y = nminy; g.max_x = nmaxx; g.max_y = nmaxy;
     g.w = nw; g.h = nh;
     org_x += xminInt; org_y += yminInt;
-    if ((size_t)nw * nh > d_table_cap) {
-        CU(cudaStreamSynchronize(stream));
-        CU(cudaFree(d_table));
-        d_table = nullptr;
-        d_table_cap = (size_t)nw * nh * 2;
-        CU(cudaMalloc(&d_table, d_table_cap * sizeof(uint8_t*)));
-    }
-    // the whole index changed: re-upload it (stream-ordered after the kernels that used the old one)
-    CU(cudaStreamSynchronize(stream));
-    CU(cudaMemcpyAsync(d_table, table.data(), table.size() * sizeof(uint8_t*), cudaMemcpyHostToDevice, stream));
-    CU(cudaStreamSynchronize(stream));
     return M2D_OK;
 }
 
@@ -270,30 +268,9 @@ int m2d_map::ensure_weight_images(int w, int h) {
     if (d_alpha) { CU(cudaFree(d_alpha)); d_alpha = nullptr; }
     if (d_wimg) { CU(cudaFree(d_wimg)); d_wimg = nullptr; }
     if (type == M2D_TYPE_MULTIBAND) CU(cudaMalloc(&d_wimg, (size_t)w * h * sizeof(float)));
-    else CU(cudaMalloc(&d_alpha, (size_t)w * h));
+    else CU(cudaMalloc(&d_alpha, (size_t)w * h + 16));
     LAUNCH(launch_weight_images(w, h, cfg.weight_type, d_alpha, d_wimg, stream));
     wimg_w = w; wimg_h = h;
-    return M2D_OK;
-}
-
-int m2d_map::stage_frame(const uint8_t* img, int w, int h, size_t stride, const uint8_t** d_img, int* d_stride) {
-    size_t need = (size_t)w * h * 3;
-    if (need > ring_bytes) {
-        CU(cudaStreamSynchronize(stream));
-        for (int i = 0; i < kRing; i++) {
-            if (d_ring[i]) { CU(cudaFree(d_ring[i])); d_ring[i] = nullptr; }
-            CU(cudaMalloc(&d_ring[i], need + 256));
-        }
-        ring_bytes = need;
-    }
-    uint8_t* dst = d_ring[ring_next];
-    ring_next = (ring_next + 1) % kRing;
-    // Stream-ordered: the slot's previous consumer kernels precede this copy on the same stream.  Pageable
-    // sources are staged by the runtime before the call returns; pinned sources are DMA'd asynchronously.
-    if (stride == (size_t)w * 3) CU(cudaMemcpyAsync(dst, img, need, cudaMemcpyHostToDevice, stream));
-    else CU(cudaMemcpy2DAsync(dst, (size_t)w * 3, img, stride, (size_t)w * 3, h, cudaMemcpyHostToDevice, stream));
-    *d_img = dst;
-    *d_stride = w * 3;
     return M2D_OK;
 }
 
@@ -316,180 +293,240 @@ int m2d_map::alloc_tile(uint8_t** out) {
     return M2D_OK;
 }
 
-int m2d_map::upload_table_rows(int x0, int y0, int x1, int y1) {
-    for (int y = y0; y < y1; y++)
-        CU(cudaMemcpyAsync(d_table + (size_t)y * g.w + x0, table.data() + (size_t)y * g.w + x0,
-                           (size_t)(x1 - x0) * sizeof(uint8_t*), cudaMemcpyHostToDevice, stream));
+// (Re)allocate a device or pinned buffer.  Safe against in-flight use: callers only grow buffers of a context whose
+// previous group has completed (cudaEventSynchronize on ctx.done).
+int m2d_map::grow(void** p, size_t* cap, size_t need, bool pinned) {
+    if (need <= *cap) return M2D_OK;
+    size_t ncap = need + need / 4 + 4096;
+    if (*p) { if (pinned) CU(cudaFreeHost(*p)); else CU(cudaFree(*p)); *p = nullptr; *cap = 0; }
+    if (pinned) CU(cudaMallocHost(p, ncap)); else CU(cudaMalloc(p, ncap));
+    *cap = ncap;
     return M2D_OK;
 }
 
-int m2d_map::ensure_scratch(size_t bytes) {
-    if (bytes <= scratch_bytes) return M2D_OK;
-    CU(cudaStreamSynchronize(stream));
-    if (d_scratch) { CU(cudaFree(d_scratch)); d_scratch = nullptr; }
-    scratch_bytes = bytes + bytes / 4;
-    CU(cudaMalloc(&d_scratch, scratch_bytes));
-    return M2D_OK;
-}
-
-int m2d_map::mark_frame_done() {
-    while (!inflight.empty() && cudaEventQuery(inflight.front()) == cudaSuccess) {
-        event_pool.push_back(inflight.front());
-        inflight.pop_front();
-    }
-    cudaEvent_t ev;
-    if (!event_pool.empty()) { ev = event_pool.back(); event_pool.pop_back(); }
-    else CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    CU(cudaEventRecord(ev, stream));
-    inflight.push_back(ev);
-    return M2D_OK;
+int m2d_map::group_size(int w, int h) const {
+    if (cfg.batch_frames > 0) return std::min(cfg.batch_frames, 64);
+    double mpx = (double)w * h / 1e6;
+    int k = (int)(16.0 / std::max(mpx, 0.25));  // ~16 Mpx of source per group
+    return std::max(1, std::min(k, 32));
 }
 
 int m2d_map::queue_size() {
-    while (!inflight.empty() && cudaEventQuery(inflight.front()) == cudaSuccess) {
-        event_pool.push_back(inflight.front());
-        inflight.pop_front();
+    int q = 0;
+    for (int i = 0; i < kCtx; i++) {
+        GroupCtx& c = ctx[i];
+        if (c.busy && cudaEventQuery(c.done) == cudaSuccess) c.busy = false;
+        if (c.busy) q += c.frames;
     }
     cudaGetLastError();
-    return (int)inflight.size();
+    return q;
 }
 
 int m2d_map::sync() {
     CU(cudaSetDevice(cfg.device));
     CU(cudaStreamSynchronize(stream));
-    queue_size();
+    for (int i = 0; i < kCtx; i++) ctx[i].busy = false;
     return M2D_OK;
 }
 
 int m2d_map::reset() {
     CU(cudaSetDevice(cfg.device));
     CU(cudaStreamSynchronize(stream));
+    for (int i = 0; i < kCtx; i++) ctx[i].busy = false;
     for (uint8_t*& t : table)
         if (t) { free_tiles.push_back(t); t = nullptr; tiles_in_use--; }
-    if (d_table && !table.empty()) CU(cudaMemsetAsync(d_table, 0, table.size() * sizeof(uint8_t*), stream));
     CU(cudaMemsetAsync(d_stats, 0, 32 * sizeof(unsigned long long), stream));
     memset(&stats, 0, sizeof stats);
     last_rect[0] = last_rect[1] = last_rect[2] = last_rect[3] = -1;
     return M2D_OK;
 }
 
-// feed() + renderFrame() — Map2DCPU.cpp:127-336 / MultiBandMap2DCPU.cpp:288-558
-int m2d_map::feed(const uint8_t* img, int w, int h, size_t stride, const double* pose, bool on_device) {
-    stats.frames_fed++;
-    if (!valid) return M2D_REJECTED;                       // Map2DCPU.cpp:129
-    if (!img || !pose) return M2D_ERR_ARG;
-    if (w != g.cam_w || h != g.cam_h) {                    // Map2DCPU.cpp:158-162
+int m2d_map::feed_frames(int n, const uint8_t* base, size_t frame_stride, int w, int h, size_t stride, const double* poses,
+                         bool on_device, int* result) {
+    if (!valid) {                                         // Map2DCPU.cpp:129
+        stats.frames_fed += n;
+        for (int i = 0; i < n && result; i++) result[i] = M2D_REJECTED;
+        return M2D_REJECTED;
+    }
+    if (!base || !poses) return M2D_ERR_ARG;
+    if (w != g.cam_w || h != g.cam_h) {                   // Map2DCPU.cpp:158-162
         fprintf(stderr, "Map2DB200::renderFrame: frame size != camera size\n");
+        stats.frames_fed += n;
+        for (int i = 0; i < n && result; i++) result[i] = M2D_REJECTED;
         return M2D_REJECTED;
     }
     if (stride < (size_t)w * 3) return M2D_ERR_ARG;
     CU(cudaSetDevice(cfg.device));
-    FrameBounds fb;
-    frame_bounds(g, pose, &fb);
-    if (!fb.ok) return M2D_REJECTED;                       // oblique view (Map2DCPU.cpp:179-182)
-    if (fb.gx0 < g.min_x || fb.gx1 > g.max_x || fb.gy0 < g.min_y || fb.gy1 > g.max_y) {
-        int rc = spread(fb.gx0, fb.gy0, fb.gx1, fb.gy1);   // Map2DCPU.cpp:199-218
-        if (rc != M2D_OK) return rc;
-        frame_bounds(g, pose, &fb);
-        if (!fb.ok) return M2D_REJECTED;
-    }
-    if (fb.x0 < 0 || fb.y0 < 0 || fb.x1 > g.w || fb.y1 > g.h || fb.x0 >= fb.x1 || fb.y0 >= fb.y1) {
-        fprintf(stderr, "Map2DB200::renderFrame:should never happen!\n");  // Map2DCPU.cpp:223-227
-        return M2D_REJECTED;
-    }
-    FrameRect r{};
-    r.rx0 = fb.x0; r.ry0 = fb.y0; r.nx = fb.x1 - fb.x0; r.ny = fb.y1 - fb.y0;
-    if ((long long)r.nx * r.ny > kMaxRectTiles) {
-        err = "frame covers more than 1024 tiles";
-        return M2D_ERR_UNSUPPORTED;
-    }
-    memcpy(last_rect, &fb.x0, sizeof(int) * 4);
-    stats.frames_fused++;
-    stats.input_px += (uint64_t)w * h;
-
-    // owned tiles inside the rect; first-touch allocation (Map2DCPU.cpp:311-319)
-    uint32_t fresh[kMaxRectTiles / 32];
-    memset(fresh, 0, sizeof fresh);
-    int ox0 = INT32_MAX, oy0 = INT32_MAX, ox1 = INT32_MIN, oy1 = INT32_MIN;
-    bool dirty = false;
-    for (int ty = fb.y0; ty < fb.y1; ty++)
-        for (int tx = fb.x0; tx < fb.x1; tx++) {
-            if (!owns(tx, ty)) continue;
-            ox0 = std::min(ox0, tx); oy0 = std::min(oy0, ty); ox1 = std::max(ox1, tx + 1); oy1 = std::max(oy1, ty + 1);
-            uint8_t*& slot = table[(size_t)ty * g.w + tx];
-            bool is_fresh = false;
-            if (!slot) {
-                int rc = alloc_tile(&slot);
-                if (rc != M2D_OK) return rc;
-                int bit = (ty - fb.y0) * r.nx + (tx - fb.x0);
-                fresh[bit >> 5] |= 1u << (bit & 31);
-                dirty = true;
-                is_fresh = true;
-            }
-            for (int l = 0; l < levels; l++) {
-                uint64_t npx = (uint64_t)(kEle >> l) * (kEle >> l);
-                stats.region_px[l] += npx;
-                if (is_fresh) stats.fresh_px[l] += npx;
-            }
-        }
-    if (ox1 <= ox0) return M2D_OK;  // this shard owns nothing under the frame
-    r.wx0 = ox0; r.wy0 = oy0; r.wnx = ox1 - ox0; r.wny = oy1 - oy0;
-    if (dirty) { int rc = upload_table_rows(fb.x0, fb.y0, fb.x1, fb.y1); if (rc != M2D_OK) return rc; }
     { int rc = ensure_weight_images(w, h); if (rc != M2D_OK) return rc; }
-    const uint8_t* d_img = img;
-    int d_stride = (int)stride;
-    if (!on_device) { int rc = stage_frame(img, w, h, stride, &d_img, &d_stride); if (rc != M2D_OK) return rc; }
-    int rc = (type == M2D_TYPE_MULTIBAND) ? run_multiband(fb, r, fresh, d_img, d_stride)
-                                          : run_weighted(fb, r, fresh, d_img, d_stride);
-    if (rc != M2D_OK) return rc;
-    return mark_frame_done();
+    int K = group_size(w, h);
+    int worst = M2D_OK;
+    for (int i = 0; i < n; i += K) {
+        int m = std::min(K, n - i);
+        int rc = run_group(m, base + (size_t)i * frame_stride, frame_stride, w, h, stride, poses + 7 * (size_t)i, on_device,
+                           result ? result + i : nullptr);
+        if (rc < 0) return rc;
+        if (rc != M2D_OK) worst = rc;
+    }
+    return worst;
 }
 
-int m2d_map::run_weighted(const FrameBounds& fb, const FrameRect& r, const uint32_t* fresh, const uint8_t* d_img, int d_stride) {
-    WeightedParams p{};
-    memcpy(p.hinv, fb.hinv, sizeof p.hinv);
-    p.src = d_img; p.src_stride = d_stride; p.sw = (int)g.cam_w; p.sh = (int)g.cam_h;
-    p.alpha = d_alpha; p.table = d_table; p.grid_w = g.w; p.r = r;
-    memcpy(p.fresh, fresh, sizeof p.fresh);
-    p.stats = cfg.collect_stats ? d_stats + 16 : nullptr;
-    LAUNCHK(M2D_K_WEIGHTED, launch_weighted(p, stream));
-    return M2D_OK;
-}
+// One group: feed() semantics for frames [0,n) in order (Map2DCPU.cpp:127-336 / MultiBandMap2DCPU.cpp:288-558).
+int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, int h, size_t stride, const double* poses,
+                       bool on_device, int* result) {
+    GroupCtx& c = ctx[ctx_next];
+    ctx_next = (ctx_next + 1) % kCtx;
+    if (c.busy) { CU(cudaEventSynchronize(c.done)); c.busy = false; }
 
-int m2d_map::run_multiband(const FrameBounds& fb, const FrameRect& r, const uint32_t* fresh, const uint8_t* d_img, int d_stride) {
-    MultibandParams p{};
-    memcpy(p.hinv, fb.hinv, sizeof p.hinv);
-    p.src = d_img; p.src_stride = d_stride; p.sw = (int)g.cam_w; p.sh = (int)g.cam_h;
-    p.wimg = d_wimg; p.table = d_table; p.grid_w = g.w; p.r = r;
-    memcpy(p.fresh, fresh, sizeof p.fresh);
-    p.levels = levels;
+    std::vector<FrameJob> jobs;
+    std::vector<TileWork> tiles;
+    std::vector<std::vector<TileEntry>> per_tile;
+    std::unordered_map<uint8_t*, int> tile_index;
+    std::vector<int> src_index;  // frame index (within the call) of every accepted job
+    jobs.reserve(n);
+    size_t scratch = 0;
+    int max_wnx = 1, max_wny = 1, any_rejected = 0;
+    const size_t npx = (size_t)w * h;
+
+    for (int i = 0; i < n; i++) {
+        stats.frames_fed++;
+        int status = M2D_REJECTED;
+        do {
+            FrameBounds fb;
+            const double* pose = poses + 7 * (size_t)i;
+            frame_bounds(g, pose, &fb);
+            if (!fb.ok) break;                                   // oblique view (Map2DCPU.cpp:179-182)
+            if (fb.gx0 < g.min_x || fb.gx1 > g.max_x || fb.gy0 < g.min_y || fb.gy1 > g.max_y) {
+                if (spread(fb.gx0, fb.gy0, fb.gx1, fb.gy1) != M2D_OK) break;   // Map2DCPU.cpp:199-218
+                frame_bounds(g, pose, &fb);
+                if (!fb.ok) break;
+            }
+            if (fb.x0 < 0 || fb.y0 < 0 || fb.x1 > g.w || fb.y1 > g.h || fb.x0 >= fb.x1 || fb.y0 >= fb.y1) {
+                fprintf(stderr, "Map2DB200::renderFrame:should never happen!\n");  // Map2DCPU.cpp:223-227
+                break;
+            }
+            int nx = fb.x1 - fb.x0, ny = fb.y1 - fb.y0;
+            if (nx > 32767 || ny > 32767) { err = "frame region too large"; return M2D_ERR_UNSUPPORTED; }
+            memcpy(last_rect, &fb.x0, sizeof(int) * 4);
+            stats.frames_fused++;
+            stats.input_px += (uint64_t)npx;
+            status = M2D_OK;
+
+            // owned tiles under the frame; first-touch allocation (Map2DCPU.cpp:311-319)
+            int job_idx = (int)jobs.size();
+            int ox0 = INT32_MAX, oy0 = INT32_MAX, ox1 = INT32_MIN, oy1 = INT32_MIN;
+            for (int ty = fb.y0; ty < fb.y1; ty++)
+                for (int tx = fb.x0; tx < fb.x1; tx++) {
+                    if (!owns(tx, ty)) continue;
+                    ox0 = std::min(ox0, tx); oy0 = std::min(oy0, ty); ox1 = std::max(ox1, tx + 1); oy1 = std::max(oy1, ty + 1);
+                    uint8_t*& slot = table[(size_t)ty * g.w + tx];
+                    bool is_fresh = false;
+                    if (!slot) {
+                        int rc = alloc_tile(&slot);
+                        if (rc != M2D_OK) return rc;
+                        is_fresh = true;
+                    }
+                    auto it = tile_index.find(slot);
+                    int ti;
+                    if (it == tile_index.end()) {
+                        ti = (int)tiles.size();
+                        tile_index.emplace(slot, ti);
+                        tiles.push_back(TileWork{slot, 0, 0, is_fresh ? 1 : 0});
+                        per_tile.emplace_back();
+                    } else ti = it->second;
+                    per_tile[ti].push_back(TileEntry{job_idx, (short)(tx - fb.x0), (short)(ty - fb.y0)});
+                    for (int l = 0; l < levels; l++) {
+                        uint64_t lpx = (uint64_t)(kEle >> l) * (kEle >> l);
+                        stats.region_px[l] += lpx;
+                        if (is_fresh) stats.fresh_px[l] += lpx;
+                    }
+                }
+            if (ox1 <= ox0) break;  // this shard owns nothing under the frame: accepted, no work
+            FrameJob J{};
+            memcpy(J.hinv, fb.hinv, sizeof J.hinv);
+            J.nx = nx; J.ny = ny;
+            // Pyramid window: owned tiles + one tile ring (>= the 94-px level-0 support of the deepest Laplacian
+            // tap), clipped to the frame region so the reflect-101 border lands where the reference puts it.
+            if (cfg.shard_count <= 1) { J.wx = 0; J.wy = 0; J.wnx = nx; J.wny = ny; }
+            else {
+                int wx0 = std::max(ox0 - 1, fb.x0), wy0 = std::max(oy0 - 1, fb.y0);
+                int wx1 = std::min(ox1 + 1, fb.x1), wy1 = std::min(oy1 + 1, fb.y1);
+                J.wx = wx0 - fb.x0; J.wy = wy0 - fb.y0; J.wnx = wx1 - wx0; J.wny = wy1 - wy0;
+            }
+            max_wnx = std::max(max_wnx, J.wnx); max_wny = std::max(max_wny, J.wny);
+            if (type == M2D_TYPE_MULTIBAND)
+                for (int l = 0; l < levels; l++) {
+                    size_t lpx = (size_t)J.wnx * J.wny * (kEle >> l) * (kEle >> l);
+                    J.g_off[l] = scratch; scratch += (lpx * 4 + 255) & ~(size_t)255;
+                    J.w_off[l] = scratch; scratch += (lpx * 4 + 255) & ~(size_t)255;
+                }
+            jobs.push_back(J);
+            src_index.push_back(i);
+        } while (0);
+        if (result) result[i] = status;
+        if (status != M2D_OK) any_rejected = 1;
+    }
+    int nj = (int)jobs.size();
+    if (nj == 0) return any_rejected ? M2D_REJECTED : M2D_OK;
+
+    // ---- device buffers of this context
+    size_t n_entries = 0;
+    for (auto& v : per_tile) n_entries += v.size();
+    size_t off_tiles = ((size_t)nj * sizeof(FrameJob) + 255) & ~(size_t)255;
+    size_t off_entries = (off_tiles + tiles.size() * sizeof(TileWork) + 255) & ~(size_t)255;
+    size_t blob = off_entries + n_entries * sizeof(TileEntry) + 256;
+    { size_t cap = c.blob_cap; int rc = grow((void**)&c.h_blob, &cap, blob, true); if (rc != M2D_OK) return rc;
+      rc = grow((void**)&c.d_blob, &c.blob_cap, blob, false); if (rc != M2D_OK) return rc; }
+    { int rc = grow((void**)&c.d_packed, &c.packed_cap, (size_t)nj * npx * 4 + 256, false); if (rc != M2D_OK) return rc; }
+    if (!on_device) { int rc = grow((void**)&c.d_raw, &c.raw_cap, (size_t)nj * npx * 3 + 256, false); if (rc != M2D_OK) return rc; }
+    if (scratch) { int rc = grow((void**)&c.d_scratch, &c.scratch_cap, scratch, false); if (rc != M2D_OK) return rc; }
+
+    // ---- frames: host images are staged into HBM (stream-ordered), device images are used in place
+    for (int j = 0; j < nj; j++) {
+        const uint8_t* src = base + (size_t)src_index[j] * frame_stride;
+        if (on_device) { jobs[j].raw = src; jobs[j].raw_stride = (int)stride; }
+        else {
+            uint8_t* dst = c.d_raw + (size_t)j * npx * 3;
+            if (stride == (size_t)w * 3) CU(cudaMemcpyAsync(dst, src, npx * 3, cudaMemcpyHostToDevice, stream));
+            else CU(cudaMemcpy2DAsync(dst, (size_t)w * 3, src, stride, (size_t)w * 3, h, cudaMemcpyHostToDevice, stream));
+            jobs[j].raw = dst; jobs[j].raw_stride = w * 3;
+        }
+        jobs[j].packed = c.d_packed + (size_t)j * npx;
+    }
+    // ---- work lists
+    memcpy(c.h_blob, jobs.data(), (size_t)nj * sizeof(FrameJob));
+    TileEntry* he = reinterpret_cast<TileEntry*>(c.h_blob + off_entries);
+    int first = 0;
+    for (size_t t = 0; t < tiles.size(); t++) {
+        tiles[t].first = first;
+        tiles[t].count = (int)per_tile[t].size();
+        memcpy(he + first, per_tile[t].data(), per_tile[t].size() * sizeof(TileEntry));
+        first += tiles[t].count;
+    }
+    memcpy(c.h_blob + off_tiles, tiles.data(), tiles.size() * sizeof(TileWork));
+    CU(cudaMemcpyAsync(c.d_blob, c.h_blob, blob, cudaMemcpyHostToDevice, stream));
+
+    GroupParams p{};
+    p.jobs = reinterpret_cast<const FrameJob*>(c.d_blob);
+    p.tiles = reinterpret_cast<const TileWork*>(c.d_blob + off_tiles);
+    p.entries = reinterpret_cast<const TileEntry*>(c.d_blob + off_entries);
+    p.n_frames = nj; p.n_tiles = (int)tiles.size();
+    p.sw = w; p.sh = h; p.levels = levels;
+    p.alpha = d_alpha; p.wimg = d_wimg; p.scratch = c.d_scratch;
     p.stats = cfg.collect_stats ? d_stats : nullptr;
-    // Pyramid window: owned tiles + one tile ring (>= the 94-px level-0 support of the deepest Laplacian tap),
-    // clipped to the frame region so the reflect-101 border lands where the reference puts it.
-    int wx0 = std::max(r.wx0 - 1, r.rx0), wy0 = std::max(r.wy0 - 1, r.ry0);
-    int wx1 = std::min(r.wx0 + r.wnx + 1, r.rx0 + r.nx), wy1 = std::min(r.wy0 + r.wny + 1, r.ry0 + r.ny);
-    if (cfg.shard_count <= 1) { wx0 = r.rx0; wy0 = r.ry0; wx1 = r.rx0 + r.nx; wy1 = r.ry0 + r.ny; }
-    size_t off = 0;
-    size_t offs[M2D_MAX_LEVELS][4];
-    for (int l = 0; l < levels; l++) {
-        int n = kEle >> l;
-        PyrLevel& L = p.lv[l];
-        L.ww = (wx1 - wx0) * n; L.wh = (wy1 - wy0) * n;
-        L.rw = r.nx * n; L.rh = r.ny * n;
-        L.ox = (wx0 - r.rx0) * n; L.oy = (wy0 - r.ry0) * n;
-        size_t px = (size_t)L.ww * L.wh;
-        for (int c = 0; c < 3; c++) { offs[l][c] = off; off += (px * sizeof(int16_t) + 255) & ~(size_t)255; }
-        offs[l][3] = off; off += (px * sizeof(float) + 255) & ~(size_t)255;
+    p.max_wnx = max_wnx; p.max_wny = max_wny;
+
+    LAUNCHK(M2D_K_PACK, launch_pack(p, stream));
+    if (type == M2D_TYPE_MULTIBAND) {
+        LAUNCHK(M2D_K_MB_WARP, launch_mb_warp(p, stream));
+        for (int l = 0; l + 1 < levels; l++) LAUNCHK(M2D_K_MB_PYRDOWN, launch_mb_pyrdown(p, l, stream));
+        LAUNCHK(M2D_K_MB_SELECT, launch_mb_select(p, lay, stream));
+    } else {
+        LAUNCHK(M2D_K_WEIGHTED, launch_weighted_group(p, stream));
     }
-    { int rc = ensure_scratch(off); if (rc != M2D_OK) return rc; }
-    for (int l = 0; l < levels; l++) {
-        for (int c = 0; c < 3; c++) p.lv[l].g[c] = reinterpret_cast<int16_t*>(d_scratch + offs[l][c]);
-        p.lv[l].w = reinterpret_cast<float*>(d_scratch + offs[l][3]);
-    }
-    LAUNCHK(M2D_K_MB_WARP, launch_mb_warp(p, stream));
-    for (int l = 0; l + 1 < levels; l++) LAUNCHK(M2D_K_MB_PYRDOWN, launch_mb_pyrdown(p, l, stream));
-    LAUNCHK(M2D_K_MB_SELECT, launch_mb_select(p, lay, stream));
-    return M2D_OK;
+    CU(cudaEventRecord(c.done, stream));
+    c.busy = true;
+    c.frames = nj;
+    return any_rejected ? M2D_REJECTED : M2D_OK;
 }
 
 bool m2d_map::tile_bbox(int& x0, int& y0, int& x1, int& y1) const {
@@ -620,22 +657,22 @@ int m2d_prepare(m2d_handle h, const double* plane, const double* camera, int n, 
 
 int m2d_feed(m2d_handle h, const uint8_t* bgr, int w, int hpx, size_t stride, const double* pose) {
     if (!h) return M2D_ERR_ARG;
-    return h->feed(bgr, w, hpx, stride, pose, false);
+    int r = M2D_REJECTED;
+    int rc = h->feed_frames(1, bgr, 0, w, hpx, stride, pose, false, &r);
+    return rc < 0 ? rc : r;
 }
 int m2d_feed_device(m2d_handle h, const uint8_t* d_bgr, int w, int hpx, size_t stride, const double* pose) {
     if (!h) return M2D_ERR_ARG;
-    return h->feed(d_bgr, w, hpx, stride, pose, true);
+    int r = M2D_REJECTED;
+    int rc = h->feed_frames(1, d_bgr, 0, w, hpx, stride, pose, true, &r);
+    return rc < 0 ? rc : r;
 }
 int m2d_feed_batch(m2d_handle h, int n, const uint8_t* base, size_t frame_stride, int w, int hpx, size_t stride,
                    const double* poses, int on_device, int* result) {
     if (!h || n < 0 || !base || !poses) return M2D_ERR_ARG;
-    int worst = M2D_OK;
-    for (int i = 0; i < n; i++) {
-        int rc = h->feed(base + (size_t)i * frame_stride, w, hpx, stride, poses + 7 * (size_t)i, on_device != 0);
-        if (result) result[i] = rc;
-        if (rc < 0) { worst = rc; break; }
-    }
-    return worst;
+    if (n == 0) return M2D_OK;
+    int rc = h->feed_frames(n, base, frame_stride, w, hpx, stride, poses, on_device != 0, result);
+    return rc < 0 ? rc : M2D_OK;
 }
 
 int m2d_sync(m2d_handle h) { return h ? h->sync() : M2D_ERR_ARG; }

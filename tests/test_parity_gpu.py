@@ -184,6 +184,53 @@ def test_feed_paths_agree():
             m.close()
 
 
+@pytest.mark.parametrize("typ", [1, 3])
+@pytest.mark.parametrize("batch", [1, 3, 7, 64])
+def test_group_size_does_not_change_results(typ, batch):
+    """m2d_feed_batch fuses frames in groups of batch_frames; any grouping must equal sequential feed() calls
+    (tile-centric select preserves per-tile frame order, ties included), and must match the oracle bit for bit."""
+    import torch
+    seq = synth.Sequence(20, 320, 180, seed=12, jitter=True, fpl=5, prepare_frames=3, cross=0.7, along=0.5)
+    frames = seq.frames()
+    dev = torch.from_numpy(frames).cuda()
+    poses = seq.poses.copy()
+    poses[9, 3:] = [0.5, 0.5, 0.5, 0.5]  # one rejected frame in the middle of a group
+    g = m2d.Map2D.create(typ, thread=False, batch_frames=batch, collect_stats=1)
+    o = O.OracleMap2D.create(typ)
+    assert g.prepare(seq.plane, seq.camera, seq.prepare_poses) and o.prepare(seq.plane, seq.camera, seq.prepare_poses)
+    res = g.feed_batch(dev.data_ptr(), seq.n, seq.w * seq.h * 3, seq.w, seq.h, seq.w * 3, poses, True)
+    exp = np.array([0 if o.feed(frames[k], poses[k]) else 1 for k in range(seq.n)])
+    assert np.array_equal(res, exp) and res[9] == 1
+    g.sync()
+    compare_state(g, o, typ)
+    sg, so = g.stats(), o.stats()
+    for k in ("frames_fed", "frames_fused", "input_px", "region_px", "fresh_px", "win_px"):
+        assert sg[k] == so[k], (k, sg[k], so[k])
+    g.close()
+
+
+def test_ties_keep_reference_order():
+    """Exact weight ties: the same frame fed twice.  Weighted keeps the first ('<'), multi-band takes the last
+    ('>=') -- observable through the win counters; state must stay identical to the oracle either way."""
+    seq = synth.Sequence(3, 320, 180, seed=13, fpl=3, prepare_frames=3)
+    for typ in (1, 3):
+        for batch in (1, 8):
+            g = m2d.Map2D.create(typ, thread=False, batch_frames=batch, collect_stats=1)
+            o = O.OracleMap2D.create(typ)
+            assert g.prepare(seq.plane, seq.camera, seq.prepare_poses) and o.prepare(seq.plane, seq.camera, seq.prepare_poses)
+            frames = np.stack([seq.frame(0), seq.frame(0), seq.frame(1), seq.frame(1), seq.frame(0)])
+            poses = np.stack([seq.poses[0], seq.poses[0], seq.poses[1], seq.poses[1], seq.poses[0]])
+            import torch
+            dev = torch.from_numpy(frames).cuda()
+            g.feed_batch(dev.data_ptr(), 5, seq.w * seq.h * 3, seq.w, seq.h, seq.w * 3, poses, True)
+            for k in range(5):
+                assert o.feed(frames[k], poses[k])
+            g.sync()
+            compare_state(g, o, typ)
+            assert g.stats()["win_px"] == o.stats()["win_px"]
+            g.close()
+
+
 def test_idempotence_and_order_property():
     """Size-independent properties at BASELINE frame size: feeding the same frame twice changes nothing in
     weighted mode (strict '<'), and the mosaic alpha equals the per-pixel max of the individual frames' alphas."""
