@@ -275,11 +275,12 @@ def main():
         img, _ = me.get_image()
         out_bytes = img.nbytes
         del img
+        out_pinned, out_ptr = m2d.pinned_empty((out_bytes,))
 
         def step_e2e():
             me.reset()
             me.feed_batch(host_ptr, n, frame_bytes, W, H, W * 3, seq.poses, False)
-            return me.get_image()
+            return me.get_image(out=out_pinned)
 
         for _ in range(2):
             step_e2e()
@@ -299,6 +300,7 @@ def main():
                "d2h_bytes_per_step": out_bytes, "ms_per_step": ms_e2e,
                "what": "m2d_feed_batch(host pinned frames) + m2d_get_image (collapse + D2H of the mosaic)"}
         me.close()
+        m2d.free_pinned(out_ptr)
 
     # ---- CPU baseline: the oracle, one thread, bounded sample
     cpu = None

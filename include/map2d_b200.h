@@ -134,6 +134,16 @@ int m2d_get_image(m2d_handle h, uint8_t* out, int* w, int* h_px, int* channels, 
 /* Map2D::save — writes the same image as a PNG (8-bit BGRA/BGR stored as RGBA/RGB). */
 int m2d_save(m2d_handle h, const char* filename);
 
+/* Final tile gather of a sharded run.  A tile travels as its raw HBM state (m2d_tile_bytes bytes,
+ * library-private layout) plus its ABSOLUTE tile coordinate (stable under spreadMap and identical on every
+ * shard, because every shard sees every pose).  export copies all tiles held by this handle into `dst`
+ * (device or host memory) and their coordinates into abs_xy (2 ints per tile); import inserts foreign tiles
+ * so that m2d_get_image()/m2d_save() on the root cover the whole map. */
+size_t m2d_tile_bytes(m2d_handle h);
+int m2d_tile_count(m2d_handle h);
+int m2d_export_tiles(m2d_handle h, int max_tiles, int* abs_xy, uint8_t* dst, int dst_on_device, int* n_out);
+int m2d_import_tiles(m2d_handle h, int n, const int* abs_xy, const uint8_t* src, int src_on_device);
+
 int m2d_get_stats(m2d_handle h, m2d_stats* out);
 const char* m2d_last_error(m2d_handle h);
 /* Number of CUDA kernels this handle has launched so far (bench.py's gpu_launches). */

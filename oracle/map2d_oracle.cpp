@@ -441,6 +441,23 @@ struct Map {
     std::vector<float> wimg_f32;
     int last_rect[4] = {-1, -1, -1, -1};
     m2d_stats stats{};
+    int org_x = 0, org_y = 0;  // absolute tile coordinate of slot (0,0): test stand-in for the sharded CUDA library
+
+    bool owns(int tx, int ty) const {  // same rule as include/map2d_b200.h m2d_config.shard_*
+        if (cfg.shard_count <= 1) return true;
+        int a = (cfg.shard_axis == 0) ? tx + org_x : ty + org_y;
+        int span = cfg.shard_span > 0 ? cfg.shard_span : 1;
+        int q = (a >= 0) ? a / span : -((-a + span - 1) / span);
+        int r = q % cfg.shard_count;
+        if (r < 0) r += cfg.shard_count;
+        return r == cfg.shard_rank;
+    }
+    size_t tile_bytes() const {
+        if (type != M2D_TYPE_MULTIBAND) return (size_t)M2D_ELE_PIXELS * M2D_ELE_PIXELS * 4;
+        size_t b = 0;
+        for (int l = 0; l <= band_num; l++) { size_t n = (size_t)(M2D_ELE_PIXELS >> l); b += n * n * (3 * sizeof(int16_t) + sizeof(float)); }
+        return b;
+    }
 
     Vec3 unproject(double u, double v) const { return Vec3{(u - cx) * fxinv, (v - cy) * fyinv, 1.}; }  // Map2D.h:60-64
 
@@ -494,6 +511,7 @@ bool Map::prepare(const double* plane7, const double* cam6, int n, const double*
     mx.x = mn.x + ele_size * w;
     mx.y = mn.y + ele_size * h;
     vmin = mn; vmax = mx;
+    org_x = org_y = 0;
     data.assign((size_t)w * h, nullptr);
     wimg_w = wimg_h = 0;
     valid = true;
@@ -517,6 +535,7 @@ bool Map::spread(double xmin, double ymin, double xmax, double ymax) {
     data.swap(copy);
     vmin.x = nminx; vmin.y = nminy; vmax.x = nmaxx; vmax.y = nmaxy;
     w = nw; h = nh;
+    org_x += xminInt; org_y += yminInt;
     return true;
 }
 
@@ -590,6 +609,7 @@ bool Map::render_weighted(const uint8_t* bgr, size_t stride, const double* Minv,
     warp_u8c4_linear_const0(src.data(), fh, fw, (size_t)fw * 4, Minv, dst.data(), dh, dw);
     for (int x = x0; x < x1; x++)
         for (int y = y0; y < y1; y++) {
+            if (!owns(x, y)) continue;
             std::shared_ptr<Tile>& ele = data[(size_t)y * w + x];
             bool fresh = false;
             if (!ele) ele = std::make_shared<Tile>();
@@ -640,6 +660,7 @@ bool Map::render_multiband(const uint8_t* bgr, size_t stride, const double* Minv
     }
     for (int x = x0; x < x1; x++)
         for (int y = y0; y < y1; y++) {
+            if (!owns(x, y)) continue;
             std::shared_ptr<Tile>& ele = data[(size_t)y * w + x];
             if (!ele) ele = std::make_shared<Tile>();
             if (ele->lap.empty()) { ele->lap.resize(band_num + 1); ele->wgt.resize(band_num + 1); }
@@ -826,6 +847,54 @@ int orc_get_image(orc_map* o, uint8_t* out, int* w, int* h, int* channels, int* 
     for (size_t p = 0; p < npx; p++) {
         if (w0[p] == 0) { out[3 * p] = out[3 * p + 1] = out[3 * p + 2] = bg; continue; }
         out[3 * p] = sat_u8(pyr[0].d[3 * p]); out[3 * p + 1] = sat_u8(pyr[0].d[3 * p + 1]); out[3 * p + 2] = sat_u8(pyr[0].d[3 * p + 2]);
+    }
+    return M2D_OK;
+}
+size_t orc_tile_bytes(orc_map* o) { return o->m.tile_bytes(); }
+int orc_tile_count(orc_map* o) {
+    int n = 0;
+    for (auto& e : o->m.data) if (e && !(o->m.type == M2D_TYPE_MULTIBAND ? e->lap.empty() : e->bgra.empty())) n++;
+    return n;
+}
+int orc_export_tiles(orc_map* o, int max_tiles, int* abs_xy, uint8_t* dst, int, int* n_out) {
+    Map& m = o->m;
+    int n = 0;
+    size_t tb = m.tile_bytes();
+    for (int y = 0; y < m.h; y++)
+        for (int x = 0; x < m.w; x++) {
+            const auto& e = m.data[(size_t)y * m.w + x];
+            if (!e || (m.type == M2D_TYPE_MULTIBAND ? e->lap.empty() : e->bgra.empty())) continue;
+            if (n >= max_tiles) return M2D_ERR_ARG;
+            abs_xy[2 * n] = x + m.org_x; abs_xy[2 * n + 1] = y + m.org_y;
+            uint8_t* d = dst + (size_t)n * tb;
+            if (m.type != M2D_TYPE_MULTIBAND) memcpy(d, e->bgra.data(), tb);
+            else for (int l = 0; l <= m.band_num; l++) {
+                memcpy(d, e->lap[l].data(), e->lap[l].size() * sizeof(int16_t)); d += e->lap[l].size() * sizeof(int16_t);
+                memcpy(d, e->wgt[l].data(), e->wgt[l].size() * sizeof(float)); d += e->wgt[l].size() * sizeof(float);
+            }
+            n++;
+        }
+    *n_out = n;
+    return M2D_OK;
+}
+int orc_import_tiles(orc_map* o, int n, const int* abs_xy, const uint8_t* src, int) {
+    Map& m = o->m;
+    size_t tb = m.tile_bytes();
+    for (int i = 0; i < n; i++) {
+        int x = abs_xy[2 * i] - m.org_x, y = abs_xy[2 * i + 1] - m.org_y;
+        if (x < 0 || y < 0 || x >= m.w || y >= m.h) return M2D_ERR_ARG;
+        auto& e = m.data[(size_t)y * m.w + x];
+        if (!e) e = std::make_shared<Tile>();
+        const uint8_t* d = src + (size_t)i * tb;
+        if (m.type != M2D_TYPE_MULTIBAND) e->bgra.assign(d, d + tb);
+        else {
+            e->lap.resize(m.band_num + 1); e->wgt.resize(m.band_num + 1);
+            for (int l = 0; l <= m.band_num; l++) {
+                size_t px = (size_t)(M2D_ELE_PIXELS >> l) * (M2D_ELE_PIXELS >> l);
+                e->lap[l].assign((const int16_t*)d, (const int16_t*)d + px * 3); d += px * 3 * sizeof(int16_t);
+                e->wgt[l].assign((const float*)d, (const float*)d + px); d += px * sizeof(float);
+            }
+        }
     }
     return M2D_OK;
 }

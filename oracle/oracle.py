@@ -74,6 +74,11 @@ def lib():
         L.orc_get_tile.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp]
         L.orc_get_image.argtypes = [vp, vp, ip, ip, ip, ip, ip]
         L.orc_get_stats.argtypes = [vp, C.POINTER(Stats)]
+        L.orc_tile_bytes.argtypes = [vp]
+        L.orc_tile_bytes.restype = C.c_size_t
+        L.orc_tile_count.argtypes = [vp]
+        L.orc_export_tiles.argtypes = [vp, C.c_int, ip, vp, C.c_int, ip]
+        L.orc_import_tiles.argtypes = [vp, C.c_int, ip, vp, C.c_int]
         L.orc_compute_bounds.argtypes = [vp, C.c_int, dp, ip, dp]
         L.orc_set_threads.argtypes = [C.c_int]
         L.orc_set_threads.restype = None
@@ -257,6 +262,34 @@ class OracleMap2D:
         out = np.zeros((h.value, w.value, cn.value), np.uint8)
         lib().orc_get_image(self._h, out.ctypes.data, C.byref(w), C.byref(h), C.byref(cn), C.byref(tx), C.byref(ty))
         return out, (tx.value, ty.value)
+
+    # --- CPU stand-in of the sharded library (world_size-2 gloo tests of the N>1 host logic) ------------------
+    def tile_bytes(self):
+        return int(lib().orc_tile_bytes(self._h))
+
+    def tile_count(self):
+        return int(lib().orc_tile_count(self._h))
+
+    def export_tiles(self, dst_ptr, max_tiles, on_device=False):
+        xy = np.zeros((max(max_tiles, 1), 2), np.int32)
+        n = C.c_int()
+        rc = lib().orc_export_tiles(self._h, max_tiles, xy.ctypes.data_as(C.POINTER(C.c_int)), dst_ptr, 0, C.byref(n))
+        assert rc == 0
+        return xy[:n.value].copy()
+
+    def import_tiles(self, xy, src_ptr, on_device=False):
+        xy = np.ascontiguousarray(xy, np.int32).reshape(-1, 2)
+        return lib().orc_import_tiles(self._h, len(xy), xy.ctypes.data_as(C.POINTER(C.c_int)), src_ptr, 0) == 0
+
+    def feed_batch(self, base_ptr, n, frame_stride, w, h, stride, poses, on_device=False):
+        poses = np.ascontiguousarray(poses, np.float64).reshape(-1, 7)
+        res = np.zeros(n, np.int32)
+        for k in range(n):
+            res[k] = lib().orc_feed(self._h, base_ptr + k * frame_stride, w, h, stride, _dptr(poses[k]))
+        return res
+
+    def sync(self):
+        return True
 
     def stats(self):
         s = Stats()

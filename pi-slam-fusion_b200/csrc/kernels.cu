@@ -316,60 +316,101 @@ cudaError_t launch_mb_warp(const GroupParams& p, cudaStream_t stream) {
 // multi-band stage 2: pyrDown level l -> l+1 for every frame of the group (u8x4 Gaussian + f32 weight).
 // Separable [1 4 6 4 1], BORDER_REFLECT_101 in REGION coordinates.  The int path runs on packed 16-bit lanes
 // (B,R in one register, G alone): row sums <= 4080, column sums <= 65280, (x+128)>>8 -- no lane ever overflows.
-// One thread = one output column x 4 consecutive output rows (11 input rows, sliding window).
+// One thread = 2 adjacent output columns x 4 output rows: 11 input rows stream through a 5-row register window,
+// each fetched with four 8-byte loads per plane (7 input columns), so every input px is loaded ~1.1x.
 // ---------------------------------------------------------------------------------------------------------
+struct HRow { uint32_t br0, g0, br1, g1; float w0, w1; };  // horizontal sums for output columns u and u+1
+
+__device__ __forceinline__ HRow pyr_hrow(const uint32_t* __restrict__ gr, const float* __restrict__ wr, const int* xs, bool fast) {
+    uint32_t e[7];
+    float f[7];
+    if (fast) {  // xs[0] is even and the 7 columns are consecutive: 8-byte vector loads
+        const uint2* g2 = reinterpret_cast<const uint2*>(gr + xs[0]);
+        const float2* w2 = reinterpret_cast<const float2*>(wr + xs[0]);
+        uint2 a = g2[0], b = g2[1], c = g2[2];
+        float2 fa = w2[0], fb = w2[1], fc = w2[2];
+        e[0] = a.x; e[1] = a.y; e[2] = b.x; e[3] = b.y; e[4] = c.x; e[5] = c.y; e[6] = gr[xs[0] + 6];
+        f[0] = fa.x; f[1] = fa.y; f[2] = fb.x; f[3] = fb.y; f[4] = fc.x; f[5] = fc.y; f[6] = wr[xs[0] + 6];
+    } else {
+#pragma unroll
+        for (int d = 0; d < 7; d++) { e[d] = gr[xs[d]]; f[d] = wr[xs[d]]; }
+    }
+    uint32_t br[7], g[7];
+#pragma unroll
+    for (int d = 0; d < 7; d++) { br[d] = e[d] & kM2; g[d] = (e[d] >> 8) & 0xFFu; }
+    HRow h;
+    h.br0 = br[2] * 6u + (br[1] + br[3]) * 4u + br[0] + br[4];
+    h.br1 = br[4] * 6u + (br[3] + br[5]) * 4u + br[2] + br[6];
+    h.g0 = g[2] * 6u + (g[1] + g[3]) * 4u + g[0] + g[4];
+    h.g1 = g[4] * 6u + (g[3] + g[5]) * 4u + g[2] + g[6];
+    // f32, OpenCV 2.4.9 association: s0*6 + (s-1 + s1)*4 + s-2 + s2, left to right
+    h.w0 = f[2] * 6.f + (f[1] + f[3]) * 4.f + f[0] + f[4];
+    h.w1 = f[4] * 6.f + (f[3] + f[5]) * 4.f + f[2] + f[6];
+    return h;
+}
+
 __global__ void __launch_bounds__(256) mb_pyrdown_kernel(const __grid_constant__ GroupParams p, int l) {
     const FrameJob& J = p.jobs[blockIdx.y];
     const int ns = kEle >> l, nd = kEle >> (l + 1);
     const int sww = J.wnx * ns, swh = J.wny * ns, srw = J.nx * ns, srh = J.ny * ns, sox = J.wx * ns, soy = J.wy * ns;
     const int dww = J.wnx * nd, dwh = J.wny * nd, dox = J.wx * nd, doy = J.wy * nd;
-    const int bpr = (dww + 31) / 32;
+    const int bpr = (dww + 63) / 64;
     int by = blockIdx.x / bpr, bx = blockIdx.x - by * bpr;
-    int u = bx * 32 + threadIdx.x, v0 = (by * 8 + threadIdx.y) * 4;
+    int u = (bx * 32 + threadIdx.x) * 2, v0 = (by * 8 + threadIdx.y) * 4;
     if (u >= dww || v0 >= dwh) return;
     const uint32_t* SG = reinterpret_cast<const uint32_t*>(p.scratch + J.g_off[l]);
     const float* SW = reinterpret_cast<const float*>(p.scratch + J.w_off[l]);
     uint32_t* DG = reinterpret_cast<uint32_t*>(p.scratch + J.g_off[l + 1]);
     float* DW = reinterpret_cast<float*>(p.scratch + J.w_off[l + 1]);
+    const bool two = (u + 1) < dww;  // dww is odd only for the 1-px-wide top levels
     int U = u + dox;
-    int xs[5];
+    int xs[7];
+    int c0 = 2 * U - 2 - sox;
+    const bool fast = (2 * U - 2 >= 0) && (2 * U + 4 < srw) && (c0 >= 0) && (c0 + 6 < sww);
+    if (fast) {
 #pragma unroll
-    for (int d = 0; d < 5; d++) xs[d] = clampi(reflect101_idx(2 * U + d - 2, srw) - sox, 0, sww - 1);
-    uint32_t hbr[11], hg[11];
-    float hw[11];
+        for (int d = 0; d < 7; d++) xs[d] = c0 + d;
+    } else {
+#pragma unroll
+        for (int d = 0; d < 7; d++) xs[d] = clampi(reflect101_idx(2 * U + d - 2, srw) - sox, 0, sww - 1);
+    }
     int V0 = v0 + doy;
+    HRow h[5];
 #pragma unroll
     for (int r = 0; r < 11; r++) {
         int ys = clampi(reflect101_idx(2 * V0 + r - 2, srh) - soy, 0, swh - 1);
-        const uint32_t* gr = SG + (size_t)ys * sww;
-        const float* wr = SW + (size_t)ys * sww;
-        uint32_t a = gr[xs[0]], b = gr[xs[1]], c = gr[xs[2]], d = gr[xs[3]], e = gr[xs[4]];
-        hbr[r] = (c & kM2) * 6u + ((b & kM2) + (d & kM2)) * 4u + (a & kM2) + (e & kM2);
-        hg[r] = ((c >> 8) & 0xFFu) * 6u + (((b >> 8) & 0xFFu) + ((d >> 8) & 0xFFu)) * 4u + ((a >> 8) & 0xFFu) + ((e >> 8) & 0xFFu);
-        // f32, OpenCV 2.4.9 association: s0*6 + (s-1 + s1)*4 + s-2 + s2, left to right
-        hw[r] = wr[xs[2]] * 6.f + (wr[xs[1]] + wr[xs[3]]) * 4.f + wr[xs[0]] + wr[xs[4]];
-    }
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        int v = v0 + k;
-        if (v >= dwh) break;
-        int r = 2 * k;
-        uint32_t vbr = hbr[r] + hbr[r + 4] + (hbr[r + 1] + hbr[r + 3]) * 4u + hbr[r + 2] * 6u;
-        uint32_t vg = hg[r] + hg[r + 4] + (hg[r + 1] + hg[r + 3]) * 4u + hg[r + 2] * 6u;
-        uint32_t obr = ((vbr + 0x00800080u) >> 8) & kM2;
-        uint32_t og = (vg + 128u) >> 8;
-        // columns ((r0+r4)+(r2+r2)) + ((r1+r3)+r2)*4, scaled by 1/256 (PyrDownVec_32f of OpenCV 2.4.9)
-        float t0 = (hw[r] + hw[r + 4]) + (hw[r + 2] + hw[r + 2]);
-        float t1 = (hw[r + 1] + hw[r + 3]) + hw[r + 2];
-        size_t o = (size_t)v * dww + u;
-        DG[o] = obr | (og << 8);
-        DW[o] = (t0 + t1 * 4.f) * (1.f / 256.f);
+        h[r % 5] = pyr_hrow(SG + (size_t)ys * sww, SW + (size_t)ys * sww, xs, fast);
+        if (r >= 4 && (r & 1) == 0) {
+            int k = (r - 4) >> 1, v = v0 + k;
+            if (v < dwh) {
+                const HRow &r0 = h[(r - 4) % 5], &r1 = h[(r - 3) % 5], &r2 = h[(r - 2) % 5], &r3 = h[(r - 1) % 5], &r4 = h[r % 5];
+                uint32_t vbr0 = r0.br0 + r4.br0 + (r1.br0 + r3.br0) * 4u + r2.br0 * 6u;
+                uint32_t vbr1 = r0.br1 + r4.br1 + (r1.br1 + r3.br1) * 4u + r2.br1 * 6u;
+                uint32_t vg0 = r0.g0 + r4.g0 + (r1.g0 + r3.g0) * 4u + r2.g0 * 6u;
+                uint32_t vg1 = r0.g1 + r4.g1 + (r1.g1 + r3.g1) * 4u + r2.g1 * 6u;
+                uint32_t o0 = (((vbr0 + 0x00800080u) >> 8) & kM2) | (((vg0 + 128u) >> 8) << 8);
+                uint32_t o1 = (((vbr1 + 0x00800080u) >> 8) & kM2) | (((vg1 + 128u) >> 8) << 8);
+                // columns ((r0+r4)+(r2+r2)) + ((r1+r3)+r2)*4, scaled by 1/256 (PyrDownVec_32f of OpenCV 2.4.9)
+                float t00 = (r0.w0 + r4.w0) + (r2.w0 + r2.w0), t10 = (r1.w0 + r3.w0) + r2.w0;
+                float t01 = (r0.w1 + r4.w1) + (r2.w1 + r2.w1), t11 = (r1.w1 + r3.w1) + r2.w1;
+                float ow0 = (t00 + t10 * 4.f) * (1.f / 256.f), ow1 = (t01 + t11 * 4.f) * (1.f / 256.f);
+                size_t o = (size_t)v * dww + u;
+                if (two && !(dww & 1)) {  // 8-byte stores need an even row pitch (odd only at 1-px tile levels)
+                    *reinterpret_cast<uint2*>(DG + o) = make_uint2(o0, o1);
+                    *reinterpret_cast<float2*>(DW + o) = make_float2(ow0, ow1);
+                } else {
+                    DG[o] = o0;
+                    DW[o] = ow0;
+                    if (two) { DG[o + 1] = o1; DW[o + 1] = ow1; }
+                }
+            }
+        }
     }
 }
 cudaError_t launch_mb_pyrdown(const GroupParams& p, int level, cudaStream_t stream) {
-    // grid.x bound: the widest / tallest window of the group at level+1, in 32 x 32 output blocks
+    // grid.x bound: the widest / tallest window of the group at level+1, in 64 x 32 output blocks
     int nd = kEle >> (level + 1);
-    int blocks = ((p.max_wnx * nd + 31) / 32) * ((p.max_wny * nd + 31) / 32);
+    int blocks = ((p.max_wnx * nd + 63) / 64) * ((p.max_wny * nd + 31) / 32);
     dim3 b(32, 8), g(blocks, p.n_frames);
     mb_pyrdown_kernel<<<g, b, 0, stream>>>(p, level);
     return cudaGetLastError();
@@ -477,18 +518,48 @@ __global__ void __launch_bounds__(256) mb_select_kernel(const __grid_constant__ 
     else { bw0 = tw[0]; bw1 = 0.f; }
     int best0 = -1, best1 = -1;
     unsigned wins = 0;
-    for (int e = 0; e < T.count; e++) {
-        const TileEntry E = p.entries[T.first + e];
-        const FrameJob& J = p.jobs[E.frame];
-        const int ww = J.wnx * n;
-        const float* W = reinterpret_cast<const float*>(p.scratch + J.w_off[l]);
-        size_t so = (size_t)(E.rty * n + py - J.wy * n) * ww + (E.rtx * n + px - J.wx * n);
-        float s0, s1;
-        if (two) { float2 t = *reinterpret_cast<const float2*>(W + so); s0 = t.x; s1 = t.y; }
-        else { s0 = W[so]; s1 = 0.f; }
-        bool count_wins = !(T.fresh && e == 0);
-        if (s0 >= bw0) { bw0 = s0; best0 = e; wins += count_wins; }   // '>=' : MultiBandMap2DCPU.cpp:542
-        if (two && s1 >= bw1) { bw1 = s1; best1 = e; wins += count_wins; }
+    const int lane = threadIdx.x & 31;
+    // Levels 0..5 have a multiple of 32 px pairs, so a warp normally sits inside one level: then each lane resolves
+    // ONE entry's weight-plane address (job lookup, window offset) and the warp shares them by shuffle.
+    const bool uniform = __all_sync(0xffffffffu, l == __shfl_sync(0xffffffffu, l, 0));
+    if (uniform) {
+        for (int c0 = 0; c0 < T.count; c0 += 32) {
+            unsigned long long wb = 0ull;
+            int stride = 0;
+            if (c0 + lane < T.count) {
+                const TileEntry E = p.entries[T.first + c0 + lane];
+                const FrameJob& J = p.jobs[E.frame];
+                stride = J.wnx * n;
+                wb = reinterpret_cast<unsigned long long>(p.scratch + J.w_off[l]) +
+                     4ull * ((size_t)((E.rty - J.wy) * n) * stride + (size_t)((E.rtx - J.wx) * n));
+            }
+            const int m = min(32, T.count - c0);
+            for (int i = 0; i < m; i++) {
+                const float* W = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, wb, i));
+                const int st = __shfl_sync(0xffffffffu, stride, i);
+                const float* q = W + (size_t)py * st + px;
+                float s0, s1;
+                if (two) { float2 t = *reinterpret_cast<const float2*>(q); s0 = t.x; s1 = t.y; }
+                else { s0 = q[0]; s1 = 0.f; }
+                const unsigned cw = !(T.fresh && (c0 + i) == 0);
+                if (s0 >= bw0) { bw0 = s0; best0 = c0 + i; wins += cw; }   // '>=' : MultiBandMap2DCPU.cpp:542
+                if (two && s1 >= bw1) { bw1 = s1; best1 = c0 + i; wins += cw; }
+            }
+        }
+    } else {
+        for (int e = 0; e < T.count; e++) {
+            const TileEntry E = p.entries[T.first + e];
+            const FrameJob& J = p.jobs[E.frame];
+            const int ww = J.wnx * n;
+            const float* W = reinterpret_cast<const float*>(p.scratch + J.w_off[l]);
+            size_t so = (size_t)(E.rty * n + py - J.wy * n) * ww + (E.rtx * n + px - J.wx * n);
+            float s0, s1;
+            if (two) { float2 t = *reinterpret_cast<const float2*>(W + so); s0 = t.x; s1 = t.y; }
+            else { s0 = W[so]; s1 = 0.f; }
+            const unsigned cw = !(T.fresh && e == 0);
+            if (s0 >= bw0) { bw0 = s0; best0 = e; wins += cw; }
+            if (two && s1 >= bw1) { bw1 = s1; best1 = e; wins += cw; }
+        }
     }
     if (!valid) { best0 = best1 = -1; wins = 0; }
     if (p.stats) {  // block-uniform branch: every lane reaches the shuffle
@@ -544,33 +615,28 @@ cudaError_t launch_mb_select(const GroupParams& p, const TileLayout& lay, cudaSt
 // collapse (MultiBandMap2DCPU::save, :779-841): paste tiles into per-level mosaics, restore from the Laplacian
 // pyramid coarse -> fine (pyrUp + saturating add), convert to 8-bit and paint the background where weight == 0.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void mosaic_clear_kernel(MosaicLevel m, float* w0) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, n = (size_t)m.w * m.h;
-    if (i >= n) return;
-    m.g[0][i] = 0; m.g[1][i] = 0; m.g[2][i] = 0;
-    if (w0) w0[i] = 0.f;
-}
-cudaError_t launch_mosaic_clear(MosaicLevel m, float* w0, cudaStream_t stream) {
-    size_t n = (size_t)m.w * m.h;
-    mosaic_clear_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(m, w0);
-    return cudaGetLastError();
-}
-__global__ void mosaic_paste_kernel(const uint8_t* __restrict__ tile, size_t lap_off, size_t wgt_off, int n, MosaicLevel m,
-                                    float* w0, int tx, int ty) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n * n) return;
-    int y = i / n, x = i % n;
-    const int16_t* tl = reinterpret_cast<const int16_t*>(tile + lap_off);
-    size_t o = (size_t)(ty * n + y) * m.w + (size_t)tx * n + x;
+// One launch pastes every touched tile (all levels) into the zero-initialised per-level mosaics.
+__global__ void __launch_bounds__(256) mosaic_paste_kernel(const PasteItem* __restrict__ items, const __grid_constant__ TileLayout lay,
+                                                           const __grid_constant__ MosaicSet ms) {
+    const PasteItem it = items[blockIdx.x];
+    int i = blockIdx.y * 256 + threadIdx.x;
+    if (i >= lay.px_off[lay.levels]) return;
+    int l = 0;
+    while (i >= lay.px_off[l + 1]) l++;
+    i -= lay.px_off[l];
+    const int n = kEle >> l;
+    int y = i / n, x = i - y * n;
+    const int16_t* tl = reinterpret_cast<const int16_t*>(it.tile + lay.lap_off[l]);
+    const MosaicLevel& m = ms.lv[l];
+    size_t o = (size_t)(it.ty * n + y) * m.w + (size_t)it.tx * n + x;
     size_t plane = (size_t)n * n;
     m.g[0][o] = tl[i]; m.g[1][o] = tl[plane + i]; m.g[2][o] = tl[2 * plane + i];
-    if (w0) w0[o] = reinterpret_cast<const float*>(tile + wgt_off)[i];
+    if (l == 0) ms.w0[o] = reinterpret_cast<const float*>(it.tile + lay.wgt_off[0])[i];
 }
-cudaError_t launch_mosaic_paste(const uint8_t* tile, const TileLayout& lay, int level, MosaicLevel m, float* w0, int tx,
-                                int ty, cudaStream_t stream) {
-    int n = kEle >> level;
-    mosaic_paste_kernel<<<(n * n + 255) / 256, 256, 0, stream>>>(tile, lay.lap_off[level], lay.wgt_off[level], n, m,
-                                                                 level == 0 ? w0 : nullptr, tx, ty);
+cudaError_t launch_mosaic_paste(const PasteItem* d_items, int n_items, const TileLayout& lay, const MosaicSet& ms, cudaStream_t stream) {
+    if (n_items == 0) return cudaSuccess;
+    dim3 g(n_items, (lay.px_off[lay.levels] + 255) / 256);
+    mosaic_paste_kernel<<<g, 256, 0, stream>>>(d_items, lay, ms);
     return cudaGetLastError();
 }
 // fine += pyrUp(coarse), saturating int16 (restoreImageFromLaplacePyr)

@@ -66,6 +66,14 @@ struct MosaicLevel {
     int16_t* g[3];
     int w, h;
 };
+struct MosaicSet {
+    MosaicLevel lv[M2D_MAX_LEVELS];
+    float* w0;                 // level-0 weight mosaic (background mask)
+};
+struct PasteItem {
+    const uint8_t* tile;
+    int tx, ty;                // tile position inside the mosaic
+};
 
 // launchers (asynchronous on `stream`; return the launch error)
 cudaError_t launch_weight_images(int sw, int sh, int weight_type, uint8_t* alpha, float* wimg, cudaStream_t stream);
@@ -75,9 +83,7 @@ cudaError_t launch_weighted_group(const GroupParams& p, cudaStream_t stream);
 cudaError_t launch_mb_warp(const GroupParams& p, cudaStream_t stream);
 cudaError_t launch_mb_pyrdown(const GroupParams& p, int level /* src level */, cudaStream_t stream);
 cudaError_t launch_mb_select(const GroupParams& p, const TileLayout& lay, cudaStream_t stream);
-cudaError_t launch_mosaic_clear(MosaicLevel m, float* w0, cudaStream_t stream);
-cudaError_t launch_mosaic_paste(const uint8_t* tile, const TileLayout& lay, int level, MosaicLevel m, float* w0,
-                                int tx, int ty, cudaStream_t stream);
+cudaError_t launch_mosaic_paste(const PasteItem* d_items, int n_items, const TileLayout& lay, const MosaicSet& ms, cudaStream_t stream);
 cudaError_t launch_mosaic_upadd(MosaicLevel coarse, MosaicLevel fine, cudaStream_t stream);
 cudaError_t launch_mosaic_final(MosaicLevel m0, const float* w0, int background, uint8_t* out_bgr, cudaStream_t stream);
 

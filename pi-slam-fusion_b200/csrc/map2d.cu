@@ -100,6 +100,9 @@ struct m2d_map {
     uint8_t* d_alpha = nullptr;
     float* d_wimg = nullptr;
 
+    uint8_t* d_collapse = nullptr;  // cached buffers of get_image()/save()
+    size_t collapse_cap = 0;
+
     static constexpr int kCtx = 2;
     GroupCtx ctx[kCtx];
     int ctx_next = 0;
@@ -182,6 +185,7 @@ void m2d_map::release() {
         if (c.d_scratch) cudaFree(c.d_scratch);
     }
     if (d_stats) cudaFree(d_stats);
+    if (d_collapse) cudaFree(d_collapse);
     for (ProfRec& r : prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     if (own_stream && stream) cudaStreamDestroy(stream);
 }
@@ -562,49 +566,39 @@ int m2d_map::get_image(uint8_t* out, int* w, int* h, int* channels, int* tmx, in
         CU(cudaStreamSynchronize(stream));
         return M2D_OK;
     }
-    // multi-band: collapse on the GPU
-    std::vector<MosaicLevel> ml(levels);
-    std::vector<void*> tmp;
-    auto cleanup = [&]() { for (void* q : tmp) cudaFree(q); };
-    float* w0 = nullptr;
-    uint8_t* d_out = nullptr;
-    cudaError_t e = cudaSuccess;
-    for (int l = 0; l < levels && e == cudaSuccess; l++) {
+    // multi-band: collapse on the GPU.  Buffers are cached in the handle (grow-only): cudaMalloc/cudaFree of ~1 GB
+    // per call costs far more than the collapse itself.
+    std::vector<PasteItem> items;
+    for (int y = y0; y < y1; y++)
+        for (int x = x0; x < x1; x++)
+            if (const uint8_t* t = table[(size_t)y * g.w + x]) items.push_back(PasteItem{t, x - x0, y - y0});
+    MosaicSet ms{};
+    size_t off = 0, offs[M2D_MAX_LEVELS][3];
+    for (int l = 0; l < levels; l++) {
         int n = kEle >> l;
-        ml[l].w = tw * n; ml[l].h = th * n;
-        size_t px = (size_t)ml[l].w * ml[l].h;
-        for (int c = 0; c < 3 && e == cudaSuccess; c++) {
-            void* q = nullptr;
-            e = cudaMalloc(&q, px * sizeof(int16_t));
-            if (e == cudaSuccess) { tmp.push_back(q); ml[l].g[c] = (int16_t*)q; }
-        }
+        ms.lv[l].w = tw * n; ms.lv[l].h = th * n;
+        size_t px = (size_t)ms.lv[l].w * ms.lv[l].h;
+        for (int c = 0; c < 3; c++) { offs[l][c] = off; off += (px * sizeof(int16_t) + 255) & ~(size_t)255; }
     }
-    if (e == cudaSuccess) { e = cudaMalloc((void**)&w0, W * H * sizeof(float)); if (e == cudaSuccess) tmp.push_back(w0); }
-    if (e == cudaSuccess) { e = cudaMalloc((void**)&d_out, W * H * 3); if (e == cudaSuccess) tmp.push_back(d_out); }
-    if (e != cudaSuccess) {
-        cleanup();
-        err = std::string("collapse cudaMalloc failed: ") + cudaGetErrorString(e);
-        cudaGetLastError();
-        return M2D_ERR_NOMEM;
-    }
-    int rc = M2D_OK;
-    auto body = [&]() -> int {
-        for (int l = 0; l < levels; l++) LAUNCHK(M2D_K_COLLAPSE, launch_mosaic_clear(ml[l], l == 0 ? w0 : nullptr, stream));
-        for (int y = y0; y < y1; y++)
-            for (int x = x0; x < x1; x++) {
-                const uint8_t* t = table[(size_t)y * g.w + x];
-                if (!t) continue;
-                for (int l = 0; l < levels; l++) LAUNCHK(M2D_K_COLLAPSE, launch_mosaic_paste(t, lay, l, ml[l], w0, x - x0, y - y0, stream));
-            }
-        for (int l = levels - 1; l > 0; l--) LAUNCHK(M2D_K_COLLAPSE, launch_mosaic_upadd(ml[l], ml[l - 1], stream));
-        LAUNCHK(M2D_K_COLLAPSE, launch_mosaic_final(ml[0], w0, cfg.background, d_out, stream));
-        CU(cudaMemcpyAsync(out, d_out, W * H * 3, cudaMemcpyDeviceToHost, stream));
-        CU(cudaStreamSynchronize(stream));
-        return M2D_OK;
-    };
-    rc = body();
-    cleanup();
-    return rc;
+    size_t off_w0 = off; off += (W * H * sizeof(float) + 255) & ~(size_t)255;
+    size_t zero_bytes = off;  // everything up to here must start at 0 (tiles never touched stay 0 / weight 0)
+    size_t off_out = off; off += (W * H * 3 + 255) & ~(size_t)255;
+    size_t off_items = off; off += items.size() * sizeof(PasteItem) + 256;
+    CU(cudaStreamSynchronize(stream));
+    { int rc = grow((void**)&d_collapse, &collapse_cap, off, false); if (rc != M2D_OK) return rc; }
+    for (int l = 0; l < levels; l++)
+        for (int c = 0; c < 3; c++) ms.lv[l].g[c] = reinterpret_cast<int16_t*>(d_collapse + offs[l][c]);
+    ms.w0 = reinterpret_cast<float*>(d_collapse + off_w0);
+    uint8_t* d_out = d_collapse + off_out;
+    PasteItem* d_items = reinterpret_cast<PasteItem*>(d_collapse + off_items);
+    CU(cudaMemsetAsync(d_collapse, 0, zero_bytes, stream));
+    CU(cudaMemcpyAsync(d_items, items.data(), items.size() * sizeof(PasteItem), cudaMemcpyHostToDevice, stream));
+    LAUNCHK(M2D_K_COLLAPSE, launch_mosaic_paste(d_items, (int)items.size(), lay, ms, stream));
+    for (int l = levels - 1; l > 0; l--) LAUNCHK(M2D_K_COLLAPSE, launch_mosaic_upadd(ms.lv[l], ms.lv[l - 1], stream));
+    LAUNCHK(M2D_K_COLLAPSE, launch_mosaic_final(ms.lv[0], ms.w0, cfg.background, d_out, stream));
+    CU(cudaMemcpyAsync(out, d_out, W * H * 3, cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    return M2D_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -751,6 +745,49 @@ int m2d_save(m2d_handle h, const char* filename) {
         h->err = std::string("cannot write ") + filename;
         return M2D_ERR_IO;
     }
+    return M2D_OK;
+}
+
+size_t m2d_tile_bytes(m2d_handle h) { return h ? h->tile_bytes : 0; }
+int m2d_tile_count(m2d_handle h) { return h ? (int)h->tiles_in_use : 0; }
+
+int m2d_export_tiles(m2d_handle h, int max_tiles, int* abs_xy, uint8_t* dst, int dst_on_device, int* n_out) {
+    if (!h || !abs_xy || !dst || !n_out) return M2D_ERR_ARG;
+    m2d_map& m = *h;
+    std::string& err = m.err;
+    if (!m.valid) return M2D_ERR_STATE;
+    CU(cudaSetDevice(m.cfg.device));
+    int n = 0;
+    for (int y = 0; y < m.g.h; y++)
+        for (int x = 0; x < m.g.w; x++) {
+            const uint8_t* t = m.table[(size_t)y * m.g.w + x];
+            if (!t) continue;
+            if (n >= max_tiles) return M2D_ERR_ARG;
+            abs_xy[2 * n] = x + m.org_x; abs_xy[2 * n + 1] = y + m.org_y;
+            CU(cudaMemcpyAsync(dst + (size_t)n * m.tile_bytes, t, m.tile_bytes,
+                               dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, m.stream));
+            n++;
+        }
+    CU(cudaStreamSynchronize(m.stream));
+    *n_out = n;
+    return M2D_OK;
+}
+
+int m2d_import_tiles(m2d_handle h, int n, const int* abs_xy, const uint8_t* src, int src_on_device) {
+    if (!h || n < 0 || (n && (!abs_xy || !src))) return M2D_ERR_ARG;
+    m2d_map& m = *h;
+    std::string& err = m.err;
+    if (!m.valid) return M2D_ERR_STATE;
+    CU(cudaSetDevice(m.cfg.device));
+    for (int i = 0; i < n; i++) {
+        int x = abs_xy[2 * i] - m.org_x, y = abs_xy[2 * i + 1] - m.org_y;
+        if (x < 0 || y < 0 || x >= m.g.w || y >= m.g.h) { err = "import: tile outside the grid (shards must see the same poses)"; return M2D_ERR_ARG; }
+        uint8_t*& slot = m.table[(size_t)y * m.g.w + x];
+        if (!slot) { int rc = m.alloc_tile(&slot); if (rc != M2D_OK) return rc; }
+        CU(cudaMemcpyAsync(slot, src + (size_t)i * m.tile_bytes, m.tile_bytes,
+                           src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, m.stream));
+    }
+    CU(cudaStreamSynchronize(m.stream));
     return M2D_OK;
 }
 

@@ -44,7 +44,8 @@ class Stats(C.Structure):
 
 EXPORTS = ["m2d_config_default", "m2d_create", "m2d_destroy", "m2d_prepare", "m2d_feed", "m2d_feed_device",
            "m2d_feed_batch", "m2d_sync", "m2d_queue_size", "m2d_set_stream", "m2d_reset", "m2d_get_grid",
-           "m2d_last_rect", "m2d_get_tile", "m2d_get_image", "m2d_save", "m2d_get_stats", "m2d_last_error",
+           "m2d_last_rect", "m2d_get_tile", "m2d_get_image", "m2d_save", "m2d_tile_bytes", "m2d_tile_count",
+           "m2d_export_tiles", "m2d_import_tiles", "m2d_get_stats", "m2d_last_error",
            "m2d_launch_count", "m2d_profile", "m2d_get_kernel_times", "m2d_alloc_host", "m2d_free_host", "m2d_compute_bounds"]
 
 _lib = None
@@ -78,6 +79,11 @@ def lib():
     L.m2d_get_tile.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp]
     L.m2d_get_image.argtypes = [vp, vp, ip, ip, ip, ip, ip]
     L.m2d_save.argtypes = [vp, C.c_char_p]
+    L.m2d_tile_bytes.argtypes = [vp]
+    L.m2d_tile_bytes.restype = C.c_size_t
+    L.m2d_tile_count.argtypes = [vp]
+    L.m2d_export_tiles.argtypes = [vp, C.c_int, ip, vp, C.c_int, ip]
+    L.m2d_import_tiles.argtypes = [vp, C.c_int, ip, vp, C.c_int]
     L.m2d_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.m2d_last_error.argtypes = [vp]
     L.m2d_last_error.restype = C.c_char_p
@@ -229,14 +235,38 @@ class Map2D:
         rc = lib().m2d_get_tile(self._h, tx, ty, 0, out.ctypes.data, None)
         return out if self._check(rc) else None
 
-    def get_image(self):
+    def get_image(self, out=None):
+        """In-memory save(): (image, (tile_min_x, tile_min_y)).  `out`: optional preallocated uint8 buffer (e.g. from
+        pinned_empty) of at least h*w*channels bytes; a view of it is returned."""
         w, h, cn, tx, ty = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
         rc = lib().m2d_get_image(self._h, None, C.byref(w), C.byref(h), C.byref(cn), C.byref(tx), C.byref(ty))
         if not self._check(rc):
             return None
-        out = np.zeros((h.value, w.value, cn.value), np.uint8)
-        self._check(lib().m2d_get_image(self._h, out.ctypes.data, C.byref(w), C.byref(h), C.byref(cn), C.byref(tx), C.byref(ty)))
-        return out, (tx.value, ty.value)
+        nbytes = h.value * w.value * cn.value
+        if out is None:
+            out = np.empty(nbytes, np.uint8)
+        flat = out.reshape(-1)
+        assert flat.dtype == np.uint8 and flat.size >= nbytes and flat.flags["C_CONTIGUOUS"]
+        self._check(lib().m2d_get_image(self._h, flat.ctypes.data, C.byref(w), C.byref(h), C.byref(cn), C.byref(tx), C.byref(ty)))
+        return flat[:nbytes].reshape(h.value, w.value, cn.value), (tx.value, ty.value)
+
+    # --- sharded runs: final tile gather -----------------------------------------------------------------
+    def tile_bytes(self):
+        return int(lib().m2d_tile_bytes(self._h))
+
+    def tile_count(self):
+        return int(lib().m2d_tile_count(self._h))
+
+    def export_tiles(self, dst_ptr, max_tiles, on_device):
+        """Copy every tile this shard holds to dst_ptr; returns their absolute tile coordinates (n x 2 int32)."""
+        xy = np.zeros((max(max_tiles, 1), 2), np.int32)
+        n = C.c_int()
+        self._check(lib().m2d_export_tiles(self._h, max_tiles, xy.ctypes.data_as(C.POINTER(C.c_int)), dst_ptr, int(on_device), C.byref(n)))
+        return xy[:n.value].copy()
+
+    def import_tiles(self, xy, src_ptr, on_device):
+        xy = np.ascontiguousarray(xy, np.int32).reshape(-1, 2)
+        return self._check(lib().m2d_import_tiles(self._h, len(xy), xy.ctypes.data_as(C.POINTER(C.c_int)), src_ptr, int(on_device)))
 
     def stats(self):
         s = Stats()

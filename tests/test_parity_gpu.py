@@ -209,6 +209,42 @@ def test_group_size_does_not_change_results(typ, batch):
     g.close()
 
 
+@pytest.mark.parametrize("typ", [1, 3])
+@pytest.mark.parametrize("axis,span,count", [(0, 1, 2), (1, 1, 3), (0, 2, 2)])
+def test_tile_shards_on_one_gpu_equal_unsharded(typ, axis, span, count):
+    """Spatial tile ownership emulated on ONE GPU: `count` shard handles each fuse only the tiles
+    they own (multi-band: warped window = owned bbox + one tile ring, clipped to the frame region), then the final
+    gather (export -> import into shard 0).  Every tile must be bit-identical to the oracle's unsharded run."""
+    import torch
+    seq = synth.Sequence(14, 320, 180, seed=21, jitter=True, fpl=4, prepare_frames=3, cross=0.9, along=0.6)
+    frames = seq.frames()
+    dev = torch.from_numpy(frames).cuda()
+    shards = [m2d.Map2D.create(typ, thread=False, shard_rank=r, shard_count=count, shard_axis=axis, shard_span=span, batch_frames=5)
+              for r in range(count)]
+    o = O.OracleMap2D.create(typ)
+    assert o.prepare(seq.plane, seq.camera, seq.prepare_poses)
+    for k in range(seq.n):
+        assert o.feed(frames[k], seq.poses[k])
+    for m in shards:
+        assert m.prepare(seq.plane, seq.camera, seq.prepare_poses)
+        res = m.feed_batch(dev.data_ptr(), seq.n, seq.w * seq.h * 3, seq.w, seq.h, seq.w * 3, seq.poses, True)
+        assert (res == 0).all()
+        m.sync()
+    counts = [m.tile_count() for m in shards]
+    assert sum(c > 0 for c in counts) >= 2, counts
+    tb = shards[0].tile_bytes()
+    for m in shards[1:]:
+        n = m.tile_count()
+        buf = torch.empty(max(n, 1) * tb, dtype=torch.uint8, device="cuda")
+        xy = m.export_tiles(buf.data_ptr(), n, True)
+        assert len(xy) == n
+        assert shards[0].import_tiles(xy, buf.data_ptr(), True)
+    assert shards[0].tile_count() == sum(counts), "ownership must be disjoint and complete"
+    compare_state(shards[0], o, typ)
+    for m in shards:
+        m.close()
+
+
 def test_ties_keep_reference_order():
     """Exact weight ties: the same frame fed twice.  Weighted keeps the first ('<'), multi-band takes the last
     ('>=') -- observable through the win counters; state must stay identical to the oracle either way."""
