@@ -1,0 +1,103 @@
+/*
+ * Map2DB200.h — header-only C++ adapter: `class Map2DB200 : public Map2D` over the C-ABI of map2d_b200.h.
+ *
+ * This is the binding a pi-slam-fusion maintainer adds to the reference tree (next to Map2DFusion/Map2DCPU.h) so
+ * that `Map2D::create(type)` hands the existing host code (Map2DFusion/Map2DFusion.cpp:273-329, the only caller)
+ * a B200-backed object with unchanged semantics.  It is compiled in the REFERENCE build (it needs the reference's
+ * Map2D.h, cv::Mat and pi::SE3d); this repository cannot compile it (no OpenCV C++/Qt/GL headers here) and ships
+ * tests/adapter_stub/ to syntax-check it against minimal stand-ins.  See INTEGRATION.md.
+ *
+ *   reference member                         -> C-ABI call
+ *   Map2D::prepare(plane,camera,frames)      -> m2d_prepare        (Map2D.h:88,  Map2DCPU.cpp:105-125)
+ *   Map2D::feed(img,pose)                    -> m2d_feed           (Map2D.h:91,  Map2DCPU.cpp:127-148)
+ *   Map2D::save(filename)                    -> m2d_save           (Map2D.h:95,  Map2DCPU.cpp:523-564)
+ *   Map2D::queueSize()                       -> m2d_queue_size     (Map2D.h:97)
+ *   Map2D::draw()                            -> no-op (GL display is out of scope; use getImage())
+ */
+#ifndef MAP2D_B200_ADAPTER_H
+#define MAP2D_B200_ADAPTER_H
+
+#include <deque>
+#include <iostream>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "Map2D.h"       /* reference: Map2DFusion/Map2D.h (Map2D, PinHoleParameters, cv::Mat, pi::SE3d, svar) */
+#include "map2d_b200.h"
+
+class Map2DB200 : public Map2D {
+public:
+    /* type: Map2D::TypeCPU / TypeGPU (weighted) or TypeMultiBandCPU.  The svar keys the CPU classes read
+     * (Map2DCPU.cpp:75,246; MultiBandMap2DCPU.cpp:228,235,260,444,840) are copied into the config once. */
+    explicit Map2DB200(int type, bool thread = true, int device = 0) : _h(NULL) {
+        m2d_config cfg;
+        m2d_config_default(&cfg);
+        cfg.scale = svar.GetDouble("Map2D.Scale", 1);
+        cfg.resolution = svar.GetDouble("Map2D.Resolution", 0);
+        cfg.weight_type = svar.GetInt("Map2D.WeightType", 0);
+        cfg.band_number = svar.GetInt("MultiBandMap2DCPU.BandNumber", 5);
+        cfg.force_float = svar.GetInt("MultiBandMap2DCPU.ForceFloat", 0);
+        cfg.background = svar.GetInt("Result.BackGroundColor");
+        cfg.thread = thread ? 1 : 0;
+        cfg.device = device;
+        int rc = m2d_create(type, &cfg, &_h);
+        if (rc != M2D_OK) std::cerr << "Map2DB200: m2d_create failed (" << rc << "); no CPU fallback is taken.\n";
+    }
+    virtual ~Map2DB200() { m2d_destroy(_h); }
+
+    virtual bool prepare(const pi::SE3d& plane, const PinHoleParameters& camera,
+                         const std::deque<std::pair<cv::Mat, pi::SE3d> >& frames) {
+        if (!_h) return false;
+        double p[7], cam[6] = {camera.w, camera.h, camera.fx, camera.fy, camera.cx, camera.cy};
+        pose7(plane, p);
+        std::vector<double> poses(frames.size() * 7);
+        size_t i = 0;
+        for (std::deque<std::pair<cv::Mat, pi::SE3d> >::const_iterator it = frames.begin(); it != frames.end(); ++it, ++i)
+            pose7(it->second, &poses[7 * i]);
+        return m2d_prepare(_h, p, cam, (int)frames.size(), poses.empty() ? NULL : &poses[0]) == M2D_OK;
+    }
+
+    /* pose is camera-to-world; the library left-multiplies plane^-1 like Map2DCPU.cpp:136. */
+    virtual bool feed(cv::Mat img, const pi::SE3d& pose) {
+        if (!_h) return false;
+        if (img.type() != CV_8UC3) {  /* Map2DCPU.cpp:158-162 */
+            std::cerr << "Map2DB200::feed: frame.type()!=CV_8UC3\n";
+            return false;
+        }
+        double p[7];
+        pose7(pose, p);
+        return m2d_feed(_h, img.data, img.cols, img.rows, img.step, p) == M2D_OK;
+    }
+
+    virtual void draw() {}
+
+    virtual bool save(const std::string& filename) { return _h && m2d_save(_h, filename.c_str()) == M2D_OK; }
+
+    virtual uint queueSize() { return _h ? (uint)m2d_queue_size(_h) : 0; }
+
+    /* Addition over the reference: the saved image in memory, BGRA (weighted) or BGR. */
+    cv::Mat getImage(int* tile_min_x = NULL, int* tile_min_y = NULL) {
+        int w, h, cn, tx, ty;
+        if (!_h || m2d_get_image(_h, NULL, &w, &h, &cn, &tx, &ty) != M2D_OK) return cv::Mat();
+        cv::Mat out(h, w, cn == 4 ? CV_8UC4 : CV_8UC3);
+        if (m2d_get_image(_h, out.data, &w, &h, &cn, &tx, &ty) != M2D_OK) return cv::Mat();
+        if (tile_min_x) *tile_min_x = tx;
+        if (tile_min_y) *tile_min_y = ty;
+        return out;
+    }
+
+    m2d_handle handle() const { return _h; }
+
+private:
+    static void pose7(const pi::SE3d& s, double* o) { /* stream order x y z qx qy qz qw, SE3.h:105-117 */
+        const pi::Point3d& t = s.get_translation();
+        const pi::SO3d& r = s.get_rotation();
+        o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = r.x; o[4] = r.y; o[5] = r.z; o[6] = r.w;
+    }
+    m2d_handle _h;
+    Map2DB200(const Map2DB200&);
+    Map2DB200& operator=(const Map2DB200&);
+};
+
+#endif /* MAP2D_B200_ADAPTER_H */

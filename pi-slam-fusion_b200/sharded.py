@@ -29,6 +29,8 @@ class ShardedMap2D:
         self.device = device
         kw = dict(cfg)
         kw.update(shard_rank=rank, shard_count=world)
+        if self.cuda:
+            kw["device"] = device  # the library must run on the rank's own GPU (m2d_config.device)
         self.map = factory(type_, **kw)
 
     # Map2D::prepare — identical on every rank
@@ -37,23 +39,43 @@ class ShardedMap2D:
 
     def feed_all(self, frames, poses, w, h, chunk=32):
         """frames: uint8 tensor [n,h,w,3] on rank 0 (CUDA tensor for NCCL, CPU tensor for gloo); other ranks pass None.
+        Chunks are double-buffered: the broadcast of chunk c+1 is in flight while the library fuses chunk c.
         Returns the per-frame status array (identical on all ranks)."""
         poses = np.ascontiguousarray(poses, np.float64).reshape(-1, 7)
         n = len(poses)
         dev = torch.device("cuda", self.device) if self.cuda else torch.device("cpu")
         res = np.zeros(n, np.int32)
-        for c0 in range(0, n, chunk):
+        starts = list(range(0, n, chunk))
+        bufs = [None, None]
+
+        def start(ci):
+            c0 = starts[ci]
             m = min(chunk, n - c0)
             if self.rank == 0:
-                buf = frames[c0:c0 + m].contiguous()
+                buf = frames[c0:c0 + m]
             else:
-                buf = torch.empty((m, h, w, 3), dtype=torch.uint8, device=dev)
-            if self.world > 1:
-                dist.broadcast(buf, src=0)
+                if bufs[ci % 2] is None:
+                    bufs[ci % 2] = torch.empty((chunk, h, w, 3), dtype=torch.uint8, device=dev)
+                buf = bufs[ci % 2][:m]
+            work = dist.broadcast(buf, src=0, async_op=True) if self.world > 1 else None
+            return buf, work, c0, m
+
+        cur = start(0) if starts else None
+        for ci in range(len(starts)):
+            buf, work, c0, m = cur
+            if work is not None:
+                work.wait()
                 if self.cuda:
-                    torch.cuda.current_stream().synchronize()  # the library runs on its own stream
+                    torch.cuda.current_stream().synchronize()  # the library consumes buf on its own stream
+            if ci + 1 < len(starts):
+                if ci >= 1:
+                    self.map.sync()  # chunk ci-1 has been consumed: its buffer may be overwritten by chunk ci+1
+                nxt = start(ci + 1)
+            else:
+                nxt = None
             res[c0:c0 + m] = self.map.feed_batch(buf.data_ptr(), m, w * h * 3, w, h, w * 3, poses[c0:c0 + m], self.cuda)
-            self.map.sync()  # buf is reused / freed next iteration
+            cur = nxt
+        self.map.sync()
         return res
 
     def gather_to_root(self):
