@@ -112,7 +112,9 @@ def stage_bytes(mode, stats, levels, nframes):
         return out
     D = [stats["region_px"][l] / nframes for l in range(levels)]
     out["mb_warp"] = 3 * W * H + 10 * D[0]
-    out["mb_pyrdown"] = sum(10 * D[l] + 10 * D[l + 1] for l in range(levels - 1)) / max(levels - 1, 1)
+    nfull = min(3, levels - 1)  # levels handled by full-grid pyrDown launches; the rest by the tail kernel
+    out["mb_pyrdown"] = sum(10 * D[l] + 10 * D[l + 1] for l in range(nfull)) / max(nfull, 1)
+    out["mb_pyrtail"] = sum(10 * D[l] + 10 * D[l + 1] for l in range(nfull, levels - 1))
     sel = 0.0
     for l in range(levels):
         nonfresh = (stats["region_px"][l] - stats["fresh_px"][l]) / nframes
@@ -168,6 +170,9 @@ def main():
     ap.add_argument("--frames", type=int, default=NFRAMES)
     ap.add_argument("--ref-frames", type=int, default=24)
     ap.add_argument("--cpu-frames", type=int, default=48)
+    ap.add_argument("--batch", type=int, default=0, help="m2d_config.batch_frames (0 = library default)")
+    ap.add_argument("--stream-latency", type=int, default=0,
+                    help="also measure synchronous per-frame feed() latency (BASELINE cfg5: 1920x1080, pose jitter, H2D included) over N frames")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -202,7 +207,7 @@ def main():
     torch.cuda.synchronize()
 
     stream = torch.cuda.Stream()
-    m = m2d.Map2D.create(typ, thread=False, device=local_rank)
+    m = m2d.Map2D.create(typ, thread=False, device=local_rank, batch_frames=args.batch)
     m.set_stream(stream.cuda_stream)
     assert m.prepare(seq.plane, seq.camera, seq.prepare_poses)
 
@@ -212,7 +217,7 @@ def main():
         return res
 
     # ---- exact algorithmic bytes from one counted pass (separate handle, outside every timed region)
-    mc = m2d.Map2D.create(typ, thread=False, device=local_rank, collect_stats=1)
+    mc = m2d.Map2D.create(typ, thread=False, device=local_rank, collect_stats=1, batch_frames=args.batch)
     assert mc.prepare(seq.plane, seq.camera, seq.prepare_poses)
     mc.feed_batch(dev.data_ptr(), n, frame_bytes, W, H, W * 3, seq.poses, True)
     mc.sync()
@@ -268,7 +273,7 @@ def main():
     # ---- e2e: host buffers through the public API, H2D inside, mosaic read back
     e2e = None
     if not args.no_e2e:
-        me = m2d.Map2D.create(typ, thread=False, device=local_rank)
+        me = m2d.Map2D.create(typ, thread=False, device=local_rank, batch_frames=args.batch)
         me.set_stream(stream.cuda_stream)
         assert me.prepare(seq.plane, seq.camera, seq.prepare_poses)
         me.feed_batch(host_ptr, n, frame_bytes, W, H, W * 3, seq.poses, False)
@@ -318,13 +323,37 @@ def main():
                "sample": "first %d frames of the workload, oracle/map2d_oracle.cpp single thread (%.1f s)" % (ns, dt),
                "host_cores": os.cpu_count()}
 
+    # ---- optional: streaming latency (cfg5), one synchronous feed() per frame through the host-buffer API
+    stream_lat = None
+    if args.stream_latency > 0:
+        ns = args.stream_latency
+        s5 = synth.Sequence(ns, 1920, 1080, seed=5, jitter=True)
+        hf, hfp = m2d.pinned_empty((1080, 1920, 3))
+        ms5 = m2d.Map2D.create(typ, thread=False, device=local_rank)
+        assert ms5.prepare(s5.plane, s5.camera, s5.prepare_poses)
+        lat = []
+        for k in range(ns):
+            hf[:] = s5.frame(k)
+            t0 = time.perf_counter()
+            ms5.feed(hf, s5.poses[k])
+            ms5.sync()
+            lat.append((time.perf_counter() - t0) * 1e3)
+        lat = np.array(lat[10:])  # first frames allocate pool slabs and staging buffers
+        stream_lat = {"workload": "cfg5: %d synchronous feed() calls, 1920x1080, pose jitter, host->device copy included" % ns,
+                      "p50_ms": float(np.percentile(lat, 50)), "p99_ms": float(np.percentile(lat, 99)), "mean_ms": float(lat.mean()),
+                      "fps_sustained": float(1e3 / lat.mean())}
+        ms5.close()
+        m2d.free_pinned(hfp)
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "s16",
             "data": "synthetic",
             "config": {"workload": workload_name(mode, n), "mode": mode, "frames": n, "frames_fused": fused,
                        "frame": [W, H], "bands": levels - 1, "l2": "inputs %.2f GB per step > 126 MB L2 (no flush needed)" % (n * frame_bytes / 1e9),
-                       "parallelism": "1 GPU"},
+                       "parallelism": "1 GPU", "batch_frames": args.batch},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+    if stream_lat:
+        line["stream_latency"] = stream_lat
     print(json.dumps(line))
     m.close()
     m2d.free_pinned(host_ptr)

@@ -28,6 +28,13 @@ __device__ __forceinline__ int reflect101_idx(int p, int len) {  // BORDER_REFLE
     } while ((unsigned)p >= (unsigned)len);
     return p;
 }
+// BORDER_REFLECT for the common case of at most one fold per side, branch-free; falls back to the loop otherwise.
+__device__ __forceinline__ int reflect_once(int p, int len) {
+    int q = (p < 0) ? (-p - 1) : p;
+    q = (q >= len) ? (2 * len - 1 - q) : q;
+    if (__builtin_expect((unsigned)q >= (unsigned)len, 0)) q = reflect_idx(p, len);
+    return q;
+}
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 __device__ __forceinline__ int sat16(int v) { return min(max(v, -32768), 32767); }
 
@@ -161,36 +168,39 @@ cudaError_t launch_pack(const GroupParams& p, cudaStream_t stream) {
 // the tile is read once and written once per group.
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t tap_const0(const uint32_t* img, int sw, int sh, int sx, int sy) {
-    return ((unsigned)sx < (unsigned)sw && (unsigned)sy < (unsigned)sh) ? __ldg(img + (size_t)sy * sw + sx) : 0u;
+    return ((unsigned)sx < (unsigned)sw && (unsigned)sy < (unsigned)sh) ? __ldg(img + (sy * sw + sx)) : 0u;
 }
 
 // Returns the warped BGRA px, or 0 when its alpha cannot beat `cur_alpha` (colour math skipped).
-__device__ __forceinline__ uint32_t sample_bgra(const uint32_t* img, int sw, int sh, double fx, double fy, uint32_t cur_alpha,
+__device__ __forceinline__ uint32_t sample_bgra(const uint32_t* __restrict__ img, int sw, int sh, double fx, double fy, uint32_t cur_alpha,
                                                 uint32_t& out_alpha) {
     int X = rnd(fx * 32.0), Y = rnd(fy * 32.0);
-    int sx = sat_s16(X >> 5), sy = sat_s16(Y >> 5);
+    int sx = X >> 5, sy = Y >> 5;
+    if (__builtin_expect((unsigned)(X + 1048544) >= 2097088u || (unsigned)(Y + 1048544) >= 2097088u, 0)) {
+        sx = sat_s16(sx); sy = sat_s16(sy);  // saturate_cast<short>: only beyond +-32767 px
+    }
     out_alpha = 0;
     if (sx >= sw || sx + 1 < 0 || sy >= sh || sy + 1 < 0) return 0u;
     uint32_t v00, v01, v10, v11;
     if ((unsigned)sx < (unsigned)(sw - 1) && (unsigned)sy < (unsigned)(sh - 1)) {
-        const uint32_t* q = img + (size_t)sy * sw + sx;
+        const uint32_t* q = img + (sy * sw + sx);
         v00 = __ldg(q); v01 = __ldg(q + 1); v10 = __ldg(q + sw); v11 = __ldg(q + sw + 1);
     } else {
         v00 = tap_const0(img, sw, sh, sx, sy); v01 = tap_const0(img, sw, sh, sx + 1, sy);
         v10 = tap_const0(img, sw, sh, sx, sy + 1); v11 = tap_const0(img, sw, sh, sx + 1, sy + 1);
     }
     uint32_t a = X & 31, b = Y & 31, wa0 = 32 - a, wb0 = 32 - b;
-    // horizontal pass on packed 16-bit lanes (max 255*32 = 8160 per lane)
-    uint32_t ga0 = ((v00 >> 8) & kM2) * wa0 + ((v01 >> 8) & kM2) * a;
-    uint32_t ga1 = ((v10 >> 8) & kM2) * wa0 + ((v11 >> 8) & kM2) * a;
-    uint32_t A = ((ga0 >> 16) * wb0 + (ga1 >> 16) * b + 512u) >> 10;  // == (sum*32 + 16384) >> 15 (FixedPtCast<int,uchar,15>)
+    // horizontal pass on packed 16-bit lanes (max 255*32 = 8160 per lane); lanes (G,A) come out of one PRMT
+    uint32_t ga0 = __byte_perm(v00, 0u, 0x4341) * wa0 + __byte_perm(v01, 0u, 0x4341) * a;
+    uint32_t ga1 = __byte_perm(v10, 0u, 0x4341) * wa0 + __byte_perm(v11, 0u, 0x4341) * a;
+    uint32_t A = ((ga0 >> 16) * wb0 + ((ga1 >> 16) * b + 512u)) >> 10;  // == (sum*32 + 16384) >> 15 (FixedPtCast<int,uchar,15>)
     out_alpha = A;
     if (A <= cur_alpha) return 0u;
     uint32_t br0 = (v00 & kM2) * wa0 + (v01 & kM2) * a;
     uint32_t br1 = (v10 & kM2) * wa0 + (v11 & kM2) * a;
-    uint32_t B = ((br0 & 0xFFFFu) * wb0 + (br1 & 0xFFFFu) * b + 512u) >> 10;
-    uint32_t R = ((br0 >> 16) * wb0 + (br1 >> 16) * b + 512u) >> 10;
-    uint32_t G = ((ga0 & 0xFFFFu) * wb0 + (ga1 & 0xFFFFu) * b + 512u) >> 10;
+    uint32_t B = (__byte_perm(br0, 0u, 0x4410) * wb0 + (__byte_perm(br1, 0u, 0x4410) * b + 512u)) >> 10;
+    uint32_t R = ((br0 >> 16) * wb0 + ((br1 >> 16) * b + 512u)) >> 10;
+    uint32_t G = (__byte_perm(ga0, 0u, 0x4410) * wb0 + (__byte_perm(ga1, 0u, 0x4410) * b + 512u)) >> 10;
     return B | (G << 8) | (R << 16) | (A << 24);
 }
 
@@ -207,18 +217,21 @@ __global__ void __launch_bounds__(256) weighted_group_kernel(const __grid_consta
         const TileEntry E = p.entries[T.first + e];
         const FrameJob& J = p.jobs[E.frame];
         int X = E.rtx * kEle + px, Y = E.rty * kEle + py;
-        RowBase rb = row_base(J.hinv, X, Y);
+        double M[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) M[i] = J.hinv[i];
+        RowBase rb = row_base(M, X, Y);
         double x1 = (double)(X & 63);
         double fx[4], fy[4];
-        px_coord(J.hinv, rb, x1, fx[0], fy[0]);
-        px_coord(J.hinv, rb, x1 + 3.0, fx[3], fy[3]);
+        px_coord(M, rb, x1, fx[0], fy[0]);
+        px_coord(M, rb, x1 + 3.0, fx[3], fy[3]);
         // The 4 px lie on a line in the source too: if both ends are off the same side (with a margin far above
         // the rounding error) every tap of every px is outside the frame -> all four warp to 0.
         float ax = (float)fx[0], bx = (float)fx[3], ay = (float)fy[0], by = (float)fy[3];
         bool off = (ax < -1.25f && bx < -1.25f) || (ax > lim_x && bx > lim_x) || (ay < -1.25f && by < -1.25f) || (ay > lim_y && by > lim_y);
         if (off) continue;
-        px_coord(J.hinv, rb, x1 + 1.0, fx[1], fy[1]);
-        px_coord(J.hinv, rb, x1 + 2.0, fx[2], fy[2]);
+        px_coord(M, rb, x1 + 1.0, fx[1], fy[1]);
+        px_coord(M, rb, x1 + 2.0, fx[2], fy[2]);
         bool count_wins = !(T.fresh && e == 0);
 #pragma unroll
         for (int j = 0; j < 4; j++) {
@@ -257,15 +270,19 @@ cudaError_t launch_weighted_group(const GroupParams& p, cudaStream_t stream) {
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t bilinear_rne_bgr(uint32_t v00, uint32_t v01, uint32_t v10, uint32_t v11, uint32_t a, uint32_t b) {
     uint32_t wa0 = 32 - a, wb0 = 32 - b;
+    // horizontal pass: B,R on packed 16-bit lanes (<= 8160), G alone; byte 1 extracted with one PRMT
     uint32_t br0 = (v00 & kM2) * wa0 + (v01 & kM2) * a, br1 = (v10 & kM2) * wa0 + (v11 & kM2) * a;
-    uint32_t g0 = ((v00 >> 8) & 0xFFu) * wa0 + ((v01 >> 8) & 0xFFu) * a, g1 = ((v10 >> 8) & 0xFFu) * wa0 + ((v11 >> 8) & 0xFFu) * a;
-    uint32_t B = (br0 & 0xFFFFu) * wb0 + (br1 & 0xFFFFu) * b;
-    uint32_t R = (br0 >> 16) * wb0 + (br1 >> 16) * b;
-    uint32_t G = g0 * wb0 + g1 * b;
-    // the float sum S00*w0+S01*w1+S10*w2+S11*w3 is exact (<= 18 bits), so cvRound(sum) == RNE(v / 1024)
-    B = (B + 511u + ((B >> 10) & 1u)) >> 10;
-    G = (G + 511u + ((G >> 10) & 1u)) >> 10;
-    R = (R + 511u + ((R >> 10) & 1u)) >> 10;
+    uint32_t g0 = __byte_perm(v00, 0u, 0x4441) * wa0 + __byte_perm(v01, 0u, 0x4441) * a;
+    uint32_t g1 = __byte_perm(v10, 0u, 0x4441) * wa0 + __byte_perm(v11, 0u, 0x4441) * a;
+    // vertical pass with the +511 of the rounding folded into the multiply-add chain
+    uint32_t B = __byte_perm(br0, 0u, 0x4410) * wb0 + (__byte_perm(br1, 0u, 0x4410) * b + 511u);
+    uint32_t R = __byte_perm(br0, 0u, 0x4432) * wb0 + (__byte_perm(br1, 0u, 0x4432) * b + 511u);
+    uint32_t G = g0 * wb0 + (g1 * b + 511u);
+    // the float sum S00*w0+S01*w1+S10*w2+S11*w3 is exact (<= 18 bits), so cvRound(sum) == RNE(v / 1024):
+    // (v + 511 + bit10(v)) >> 10, with bit10(v) = bit10((v+511) - 511)
+    B = (B + (((B - 511u) >> 10) & 1u)) >> 10;
+    G = (G + (((G - 511u) >> 10) & 1u)) >> 10;
+    R = (R + (((R - 511u) >> 10) & 1u)) >> 10;
     return B | (G << 8) | (R << 16);
 }
 
@@ -277,30 +294,40 @@ __global__ void __launch_bounds__(256) mb_warp_kernel(const __grid_constant__ Gr
     if (by * 4 >= wh) return;
     int u = bx * kEle + (threadIdx.x & 63) * 4, v = by * 4 + (threadIdx.x >> 6);
     int x = u + J.wx * kEle, y = v + J.wy * kEle;  // region coordinates
-    RowBase rb = row_base(J.hinv, x, y);
+    double M[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) M[i] = J.hinv[i];
+    RowBase rb = row_base(M, x, y);
     double x1 = (double)(x & 63);
     const int sw = p.sw, sh = p.sh;
-    const uint32_t* img = J.packed;
+    const uint32_t* __restrict__ img = J.packed;
+    const float* __restrict__ wimg = p.wimg;
     uint32_t g[4];
     float w[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         double fx, fy;
-        px_coord(J.hinv, rb, x1 + (double)j, fx, fy);
-        int nx = sat_s16(rnd(fx)), ny = sat_s16(rnd(fy));
-        w[j] = ((unsigned)nx < (unsigned)sw && (unsigned)ny < (unsigned)sh) ? __ldg(p.wimg + (size_t)ny * sw + nx) : 0.f;
+        px_coord(M, rb, x1 + (double)j, fx, fy);
         int X = rnd(fx * 32.0), Y = rnd(fy * 32.0);
-        int sx = sat_s16(X >> 5), sy = sat_s16(Y >> 5);
+        int nx = rnd(fx), ny = rnd(fy);
+        // saturate_cast<short> of the integer coordinates only matters beyond +-32767 px: test once, clamp rarely
+        if (__builtin_expect((unsigned)(X + 1048544) >= 2097088u || (unsigned)(Y + 1048544) >= 2097088u, 0)) {
+            nx = sat_s16(nx); ny = sat_s16(ny);
+            X = (sat_s16(X >> 5) << 5) | (X & 31); Y = (sat_s16(Y >> 5) << 5) | (Y & 31);
+        }
+        int sx = X >> 5, sy = Y >> 5;
+        w[j] = ((unsigned)nx < (unsigned)sw && (unsigned)ny < (unsigned)sh) ? __ldg(wimg + (ny * sw + nx)) : 0.f;
         uint32_t v00, v01, v10, v11;
         if ((unsigned)sx < (unsigned)(sw - 1) && (unsigned)sy < (unsigned)(sh - 1)) {
-            const uint32_t* q = img + (size_t)sy * sw + sx;
+            const uint32_t* q = img + (sy * sw + sx);
             v00 = __ldg(q); v01 = __ldg(q + 1); v10 = __ldg(q + sw); v11 = __ldg(q + sw + 1);
         } else {
-            int sx0 = reflect_idx(sx, sw), sx1 = reflect_idx(sx + 1, sw), sy0 = reflect_idx(sy, sh), sy1 = reflect_idx(sy + 1, sh);
-            const uint32_t *r0 = img + (size_t)sy0 * sw, *r1 = img + (size_t)sy1 * sw;
+            int sx0 = reflect_once(sx, sw), sx1 = reflect_once(sx + 1, sw), sy0 = reflect_once(sy, sh), sy1 = reflect_once(sy + 1, sh);
+            const uint32_t *r0 = img + sy0 * sw, *r1 = img + sy1 * sw;
             v00 = __ldg(r0 + sx0); v01 = __ldg(r0 + sx1); v10 = __ldg(r1 + sx0); v11 = __ldg(r1 + sx1);
         }
-        g[j] = bilinear_rne_bgr(v00, v01, v10, v11, X & 31, Y & 31);
+        // a = X & 31 as X - 32*sx: an IMAD on the FMA pipe instead of a LOP3 on the (saturated) ALU pipe
+        g[j] = bilinear_rne_bgr(v00, v01, v10, v11, (uint32_t)(X - 32 * sx), (uint32_t)(Y - 32 * sy));
     }
     size_t o = (size_t)v * ww + u;
     *reinterpret_cast<uint4*>(reinterpret_cast<uint32_t*>(p.scratch + J.g_off[0]) + o) = make_uint4(g[0], g[1], g[2], g[3]);
@@ -416,6 +443,54 @@ cudaError_t launch_mb_pyrdown(const GroupParams& p, int level, cudaStream_t stre
     return cudaGetLastError();
 }
 
+// Pyramid tail: the deepest levels are a few thousand px per frame -- too small for a launch each (a launch costs
+// ~10 us of ramp/drain here).  One CTA per frame walks levels l_first..levels-2 in sequence, __syncthreads()
+// between levels (the CTA itself wrote what it reads next).  Same arithmetic as mb_pyrdown_kernel, one px per thread.
+__global__ void __launch_bounds__(1024) mb_pyrtail_kernel(const __grid_constant__ GroupParams p, int l_first) {
+    const FrameJob& J = p.jobs[blockIdx.x];
+    for (int l = l_first; l + 1 < p.levels; l++) {
+        const int ns = kEle >> l, nd = kEle >> (l + 1);
+        const int sww = J.wnx * ns, swh = J.wny * ns, srw = J.nx * ns, srh = J.ny * ns, sox = J.wx * ns, soy = J.wy * ns;
+        const int dww = J.wnx * nd, dwh = J.wny * nd, dox = J.wx * nd, doy = J.wy * nd;
+        const uint32_t* SG = reinterpret_cast<const uint32_t*>(p.scratch + J.g_off[l]);
+        const float* SW = reinterpret_cast<const float*>(p.scratch + J.w_off[l]);
+        uint32_t* DG = reinterpret_cast<uint32_t*>(p.scratch + J.g_off[l + 1]);
+        float* DW = reinterpret_cast<float*>(p.scratch + J.w_off[l + 1]);
+        for (int o = threadIdx.x; o < dww * dwh; o += blockDim.x) {
+            int v = o / dww, u = o - v * dww;
+            int U = u + dox, V = v + doy;
+            int xs[5], ys[5];
+#pragma unroll
+            for (int d = 0; d < 5; d++) {
+                xs[d] = clampi(reflect101_idx(2 * U + d - 2, srw) - sox, 0, sww - 1);
+                ys[d] = clampi(reflect101_idx(2 * V + d - 2, srh) - soy, 0, swh - 1);
+            }
+            uint32_t hbr[5], hg[5];
+            float hw[5];
+#pragma unroll
+            for (int r = 0; r < 5; r++) {
+                const uint32_t* gr = SG + (size_t)ys[r] * sww;
+                const float* wr = SW + (size_t)ys[r] * sww;
+                uint32_t a = gr[xs[0]], b = gr[xs[1]], c = gr[xs[2]], d = gr[xs[3]], e = gr[xs[4]];
+                hbr[r] = (c & kM2) * 6u + ((b & kM2) + (d & kM2)) * 4u + (a & kM2) + (e & kM2);
+                hg[r] = ((c >> 8) & 0xFFu) * 6u + (((b >> 8) & 0xFFu) + ((d >> 8) & 0xFFu)) * 4u + ((a >> 8) & 0xFFu) + ((e >> 8) & 0xFFu);
+                hw[r] = wr[xs[2]] * 6.f + (wr[xs[1]] + wr[xs[3]]) * 4.f + wr[xs[0]] + wr[xs[4]];
+            }
+            uint32_t vbr = hbr[0] + hbr[4] + (hbr[1] + hbr[3]) * 4u + hbr[2] * 6u;
+            uint32_t vg = hg[0] + hg[4] + (hg[1] + hg[3]) * 4u + hg[2] * 6u;
+            float t0 = (hw[0] + hw[4]) + (hw[2] + hw[2]);
+            float t1 = (hw[1] + hw[3]) + hw[2];
+            DG[o] = (((vbr + 0x00800080u) >> 8) & kM2) | (((vg + 128u) >> 8) << 8);
+            DW[o] = (t0 + t1 * 4.f) * (1.f / 256.f);
+        }
+        __syncthreads();
+    }
+}
+cudaError_t launch_mb_pyrtail(const GroupParams& p, int l_first, cudaStream_t stream) {
+    mb_pyrtail_kernel<<<p.n_frames, 1024, 0, stream>>>(p, l_first);
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // multi-band stage 3, tile-centric: per tile px (all levels in one launch) find the LAST frame of the group whose
 // weight is >= everything before it (state included) -- exactly what sequential `if (srcW >= dstW)` updates leave
@@ -446,16 +521,21 @@ TileLayout make_tile_layout(int levels) {
 __device__ __forceinline__ int pyrup_axis_lo(int i, int n) { return i < 0 ? (n > 1 ? 1 : 0) : i; }  // reflect-101 at -1
 __device__ __forceinline__ int pyrup_axis_hi(int i, int n) { return i >= n ? n - 1 : i; }          // replicate at n
 
-// Laplacian of the px pair (X, X+1) at row Y of level l of frame J (region coordinates).
-__device__ __forceinline__ void lap_pair(const GroupParams& p, const FrameJob& J, int l, int X, int Y, bool two, int* lap0, int* lap1) {
+// Laplacian G_l - pyrUp(G_{l+1}) of the 2x2 quad whose top-left px is (X, Y) (both even, region coordinates of
+// level l) of frame J.  The four px share one 3x3 neighbourhood of the coarser level.  out[k][c]: k = 2*row + col.
+__device__ __forceinline__ void lap_quad(const GroupParams& p, const FrameJob& J, int l, int X, int Y, bool quad, int out[4][3]) {
     const int n = kEle >> l;
     const int ww = J.wnx * n, ox = J.wx * n, oy = J.wy * n;
     const uint32_t* G = reinterpret_cast<const uint32_t*>(p.scratch + J.g_off[l]);
     size_t so = (size_t)(Y - oy) * ww + (X - ox);
-    uint32_t g0 = G[so], g1 = two ? G[so + 1] : 0u;
+    uint32_t g[4];
+    if (quad) {
+        uint2 r0 = *reinterpret_cast<const uint2*>(G + so), r1 = *reinterpret_cast<const uint2*>(G + so + ww);
+        g[0] = r0.x; g[1] = r0.y; g[2] = r1.x; g[3] = r1.y;
+    } else { g[0] = G[so]; g[1] = g[2] = g[3] = 0u; }
     if (l == p.levels - 1) {
-        lap0[0] = g0 & 0xFF; lap0[1] = (g0 >> 8) & 0xFF; lap0[2] = (g0 >> 16) & 0xFF;
-        lap1[0] = g1 & 0xFF; lap1[1] = (g1 >> 8) & 0xFF; lap1[2] = (g1 >> 16) & 0xFF;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { out[k][0] = g[k] & 0xFF; out[k][1] = (g[k] >> 8) & 0xFF; out[k][2] = (g[k] >> 16) & 0xFF; }
         return;
     }
     const int nc = n >> 1;
@@ -466,147 +546,156 @@ __device__ __forceinline__ void lap_pair(const GroupParams& p, const FrameJob& J
     int c2 = clampi(pyrup_axis_hi(i + 1, crw) - cox, 0, cww - 1);
     int r0 = clampi(pyrup_axis_lo(j - 1, crh) - coy, 0, cwh - 1), r1 = clampi(j - coy, 0, cwh - 1);
     int r2 = clampi(pyrup_axis_hi(j + 1, crh) - coy, 0, cwh - 1);
-    const uint32_t *q0 = C + (size_t)r0 * cww, *q1 = C + (size_t)r1 * cww, *q2 = C + (size_t)r2 * cww;
+    const int rr[3] = {r0, r1, r2};
     uint32_t ebr[3], eg[3], obr[3], og[3];  // even / odd column sums per coarse row, packed lanes (<= 2040)
-    {
-        uint32_t a = q0[c0], b = q0[c1], c = q0[c2];
-        ebr[0] = (a & kM2) + (b & kM2) * 6u + (c & kM2); obr[0] = ((b & kM2) + (c & kM2)) * 4u;
-        eg[0] = ((a >> 8) & 0xFFu) + ((b >> 8) & 0xFFu) * 6u + ((c >> 8) & 0xFFu); og[0] = (((b >> 8) & 0xFFu) + ((c >> 8) & 0xFFu)) * 4u;
-        a = q1[c0]; b = q1[c1]; c = q1[c2];
-        ebr[1] = (a & kM2) + (b & kM2) * 6u + (c & kM2); obr[1] = ((b & kM2) + (c & kM2)) * 4u;
-        eg[1] = ((a >> 8) & 0xFFu) + ((b >> 8) & 0xFFu) * 6u + ((c >> 8) & 0xFFu); og[1] = (((b >> 8) & 0xFFu) + ((c >> 8) & 0xFFu)) * 4u;
-        a = q2[c0]; b = q2[c1]; c = q2[c2];
-        ebr[2] = (a & kM2) + (b & kM2) * 6u + (c & kM2); obr[2] = ((b & kM2) + (c & kM2)) * 4u;
-        eg[2] = ((a >> 8) & 0xFFu) + ((b >> 8) & 0xFFu) * 6u + ((c >> 8) & 0xFFu); og[2] = (((b >> 8) & 0xFFu) + ((c >> 8) & 0xFFu)) * 4u;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const uint32_t* q = C + (size_t)rr[k] * cww;
+        uint32_t a = q[c0], b = q[c1], c = q[c2];
+        uint32_t abr = a & kM2, bbr = b & kM2, cbr = c & kM2, ag = (a >> 8) & 0xFFu, bg = (b >> 8) & 0xFFu, cg = (c >> 8) & 0xFFu;
+        ebr[k] = abr + bbr * 6u + cbr; obr[k] = (bbr + cbr) * 4u;
+        eg[k] = ag + bg * 6u + cg; og[k] = (bg + cg) * 4u;
     }
-    bool yodd = Y & 1;
-    uint32_t vebr = yodd ? (ebr[1] + ebr[2]) * 4u : (ebr[0] + ebr[1] * 6u + ebr[2]);   // <= 16320 per lane
-    uint32_t vobr = yodd ? (obr[1] + obr[2]) * 4u : (obr[0] + obr[1] * 6u + obr[2]);
-    uint32_t veg = yodd ? (eg[1] + eg[2]) * 4u : (eg[0] + eg[1] * 6u + eg[2]);
-    uint32_t vog = yodd ? (og[1] + og[2]) * 4u : (og[0] + og[1] * 6u + og[2]);
-    uint32_t uebr = ((vebr + 0x00200020u) >> 6) & kM2, uobr = ((vobr + 0x00200020u) >> 6) & kM2;  // pyrUp px, <= 255
-    int ueg = (int)((veg + 32u) >> 6), uog = (int)((vog + 32u) >> 6);
-    lap0[0] = (int)(g0 & 0xFF) - (int)(uebr & 0xFFFF);
-    lap0[1] = (int)((g0 >> 8) & 0xFF) - ueg;
-    lap0[2] = (int)((g0 >> 16) & 0xFF) - (int)(uebr >> 16);
-    lap1[0] = (int)(g1 & 0xFF) - (int)(uobr & 0xFFFF);
-    lap1[1] = (int)((g1 >> 8) & 0xFF) - uog;
-    lap1[2] = (int)((g1 >> 16) & 0xFF) - (int)(uobr >> 16);
+    // even output row: r0 + 6 r1 + r2 ; odd output row: 4 (r1 + r2)   (<= 16320 per lane), then (x + 32) >> 6
+    uint32_t up_br[4], up_g[4];
+    up_br[0] = (((ebr[0] + ebr[1] * 6u + ebr[2]) + 0x00200020u) >> 6) & kM2;
+    up_br[1] = (((obr[0] + obr[1] * 6u + obr[2]) + 0x00200020u) >> 6) & kM2;
+    up_br[2] = ((((ebr[1] + ebr[2]) * 4u) + 0x00200020u) >> 6) & kM2;
+    up_br[3] = ((((obr[1] + obr[2]) * 4u) + 0x00200020u) >> 6) & kM2;
+    up_g[0] = ((eg[0] + eg[1] * 6u + eg[2]) + 32u) >> 6;
+    up_g[1] = ((og[0] + og[1] * 6u + og[2]) + 32u) >> 6;
+    up_g[2] = (((eg[1] + eg[2]) * 4u) + 32u) >> 6;
+    up_g[3] = (((og[1] + og[2]) * 4u) + 32u) >> 6;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        out[k][0] = (int)(g[k] & 0xFF) - (int)(up_br[k] & 0xFFFF);
+        out[k][1] = (int)((g[k] >> 8) & 0xFF) - (int)up_g[k];
+        out[k][2] = (int)((g[k] >> 16) & 0xFF) - (int)(up_br[k] >> 16);
+    }
 }
 
 __global__ void __launch_bounds__(256) mb_select_kernel(const __grid_constant__ GroupParams p, const __grid_constant__ TileLayout lay) {
     const TileWork T = p.tiles[blockIdx.x];
-    // flat pair index -> (level, row, column pair)
-    int pair = blockIdx.y * 256 + threadIdx.x;
+    // flat quad index -> (level, quad row, quad column); level l has (n/2)^2 quads (1 for the 1-px level)
+    int q = blockIdx.y * 256 + threadIdx.x;
     int l = 0, n = kEle, half = kEle / 2;
     for (; l < p.levels; l++) {
         n = kEle >> l;
         half = n > 1 ? n / 2 : 1;
-        int cnt = n * half;
-        if (pair < cnt) break;
-        pair -= cnt;
+        int cnt = half * half;
+        if (q < cnt) break;
+        q -= cnt;
     }
-    bool valid = l < p.levels;
-    if (!valid) { l = p.levels - 1; n = kEle >> l; half = n > 1 ? n / 2 : 1; pair = 0; }
-    int py = pair / half, px = (pair - py * half) * 2;
-    bool two = n > 1;
-    size_t to = (size_t)py * n + px;
+    const bool valid = l < p.levels;
+    if (!valid) { l = p.levels - 1; n = kEle >> l; half = n > 1 ? n / 2 : 1; q = 0; }
+    const int qy = q / half, qx = q - qy * half;
+    const int py = qy * 2, px = qx * 2;
+    const bool quad = n > 1;
+    const size_t to = (size_t)py * n + px;
     float* tw = reinterpret_cast<float*>(T.state + lay.wgt_off[l]) + to;
-    float bw0, bw1;
-    if (T.fresh) { bw0 = -INFINITY; bw1 = -INFINITY; }  // first toucher copies unconditionally (:498-504)
-    else if (two) { float2 t = *reinterpret_cast<const float2*>(tw); bw0 = t.x; bw1 = t.y; }
-    else { bw0 = tw[0]; bw1 = 0.f; }
-    int best0 = -1, best1 = -1;
+    float bw[4];
+    if (T.fresh) { bw[0] = bw[1] = bw[2] = bw[3] = -INFINITY; }  // first toucher copies unconditionally (:498-504)
+    else if (quad) {
+        float2 t0 = *reinterpret_cast<const float2*>(tw), t1 = *reinterpret_cast<const float2*>(tw + n);
+        bw[0] = t0.x; bw[1] = t0.y; bw[2] = t1.x; bw[3] = t1.y;
+    } else { bw[0] = tw[0]; bw[1] = bw[2] = bw[3] = 0.f; }
+    int best[4] = {-1, -1, -1, -1};
     unsigned wins = 0;
     const int lane = threadIdx.x & 31;
-    // Levels 0..5 have a multiple of 32 px pairs, so a warp normally sits inside one level: then each lane resolves
+    // Levels 0..4 have a multiple of 32 quads, so a warp normally sits inside one level: then each lane resolves
     // ONE entry's weight-plane address (job lookup, window offset) and the warp shares them by shuffle.
     const bool uniform = __all_sync(0xffffffffu, l == __shfl_sync(0xffffffffu, l, 0));
-    if (uniform) {
-        for (int c0 = 0; c0 < T.count; c0 += 32) {
-            unsigned long long wb = 0ull;
-            int stride = 0;
-            if (c0 + lane < T.count) {
-                const TileEntry E = p.entries[T.first + c0 + lane];
-                const FrameJob& J = p.jobs[E.frame];
-                stride = J.wnx * n;
-                wb = reinterpret_cast<unsigned long long>(p.scratch + J.w_off[l]) +
-                     4ull * ((size_t)((E.rty - J.wy) * n) * stride + (size_t)((E.rtx - J.wx) * n));
-            }
-            const int m = min(32, T.count - c0);
-            for (int i = 0; i < m; i++) {
-                const float* W = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, wb, i));
-                const int st = __shfl_sync(0xffffffffu, stride, i);
-                const float* q = W + (size_t)py * st + px;
-                float s0, s1;
-                if (two) { float2 t = *reinterpret_cast<const float2*>(q); s0 = t.x; s1 = t.y; }
-                else { s0 = q[0]; s1 = 0.f; }
-                const unsigned cw = !(T.fresh && (c0 + i) == 0);
-                if (s0 >= bw0) { bw0 = s0; best0 = c0 + i; wins += cw; }   // '>=' : MultiBandMap2DCPU.cpp:542
-                if (two && s1 >= bw1) { bw1 = s1; best1 = c0 + i; wins += cw; }
-            }
-        }
-    } else {
-        for (int e = 0; e < T.count; e++) {
-            const TileEntry E = p.entries[T.first + e];
+    for (int c0 = 0; c0 < T.count; c0 += 32) {
+        unsigned long long wb = 0ull;
+        int stride = 0;
+        if (uniform && c0 + lane < T.count) {
+            const TileEntry E = p.entries[T.first + c0 + lane];
             const FrameJob& J = p.jobs[E.frame];
-            const int ww = J.wnx * n;
-            const float* W = reinterpret_cast<const float*>(p.scratch + J.w_off[l]);
-            size_t so = (size_t)(E.rty * n + py - J.wy * n) * ww + (E.rtx * n + px - J.wx * n);
-            float s0, s1;
-            if (two) { float2 t = *reinterpret_cast<const float2*>(W + so); s0 = t.x; s1 = t.y; }
-            else { s0 = W[so]; s1 = 0.f; }
-            const unsigned cw = !(T.fresh && e == 0);
-            if (s0 >= bw0) { bw0 = s0; best0 = e; wins += cw; }
-            if (two && s1 >= bw1) { bw1 = s1; best1 = e; wins += cw; }
+            stride = J.wnx * n;
+            wb = reinterpret_cast<unsigned long long>(p.scratch + J.w_off[l]) +
+                 4ull * ((size_t)((E.rty - J.wy) * n) * stride + (size_t)((E.rtx - J.wx) * n));
+        }
+        const int m = min(32, T.count - c0);
+#pragma unroll 4
+        for (int i = 0; i < m; i++) {
+            const float* W;
+            int st;
+            if (uniform) {
+                W = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, wb, i));
+                st = __shfl_sync(0xffffffffu, stride, i);
+            } else {
+                const TileEntry E = p.entries[T.first + c0 + i];
+                const FrameJob& J = p.jobs[E.frame];
+                st = J.wnx * n;
+                W = reinterpret_cast<const float*>(p.scratch + J.w_off[l]) + (size_t)((E.rty - J.wy) * n) * st + (size_t)((E.rtx - J.wx) * n);
+            }
+            const float* qp = W + (size_t)py * st + px;
+            float s[4];
+            if (quad) {
+                float2 t0 = *reinterpret_cast<const float2*>(qp), t1 = *reinterpret_cast<const float2*>(qp + st);
+                s[0] = t0.x; s[1] = t0.y; s[2] = t1.x; s[3] = t1.y;
+            } else { s[0] = qp[0]; s[1] = s[2] = s[3] = -INFINITY; }
+            const unsigned cw = !(T.fresh && (c0 + i) == 0);
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if ((quad || k == 0) && s[k] >= bw[k]) { bw[k] = s[k]; best[k] = c0 + i; wins += cw; }   // '>=' : MultiBandMap2DCPU.cpp:542
         }
     }
-    if (!valid) { best0 = best1 = -1; wins = 0; }
+    if (!valid) { best[0] = best[1] = best[2] = best[3] = -1; wins = 0; }
     if (p.stats) {  // block-uniform branch: every lane reaches the shuffle
         unsigned long long w = warp_sum(wins);
-        if ((threadIdx.x & 31) == 0 && w) atomicAdd(p.stats + l, w);
+        if (lane == 0 && w) atomicAdd(p.stats + l, w);
     }
-    if (best0 < 0 && best1 < 0) return;
+    if ((best[0] & best[1] & best[2] & best[3]) < 0 && best[0] < 0 && best[1] < 0 && best[2] < 0 && best[3] < 0) return;
 
-    int lap0[3] = {0, 0, 0}, lap1[3] = {0, 0, 0}, tmp0[3], tmp1[3];
-    if (best0 >= 0) {
-        const TileEntry E = p.entries[T.first + best0];
-        lap_pair(p, p.jobs[E.frame], l, E.rtx * n + px, E.rty * n + py, two, lap0, tmp1);
-        if (best1 == best0) { lap1[0] = tmp1[0]; lap1[1] = tmp1[1]; lap1[2] = tmp1[2]; }
+    int lap[4][3];
+    bool done[4] = {best[0] < 0, best[1] < 0, best[2] < 0, best[3] < 0};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (done[k]) continue;
+        const int f = best[k];
+        const TileEntry E = p.entries[T.first + f];
+        int tmp[4][3];
+        lap_quad(p, p.jobs[E.frame], l, E.rtx * n + px, E.rty * n + py, quad, tmp);
+#pragma unroll
+        for (int k2 = k; k2 < 4; k2++)
+            if (!done[k2] && best[k2] == f) { lap[k2][0] = tmp[k2][0]; lap[k2][1] = tmp[k2][1]; lap[k2][2] = tmp[k2][2]; done[k2] = true; }
     }
-    if (best1 >= 0 && best1 != best0) {
-        const TileEntry E = p.entries[T.first + best1];
-        lap_pair(p, p.jobs[E.frame], l, E.rtx * n + px, E.rty * n + py, two, tmp0, lap1);
-    }
-    size_t plane = (size_t)n * n;
+    const size_t plane = (size_t)n * n;
     int16_t* tl = reinterpret_cast<int16_t*>(T.state + lay.lap_off[l]) + to;
-    if (!two) {
-        tl[0] = (int16_t)lap0[0]; tl[plane] = (int16_t)lap0[1]; tl[2 * plane] = (int16_t)lap0[2];
-        tw[0] = bw0;
+    if (!quad) {
+        tl[0] = (int16_t)lap[0][0]; tl[plane] = (int16_t)lap[0][1]; tl[2 * plane] = (int16_t)lap[0][2];
+        tw[0] = bw[0];
         return;
     }
-    if (best0 >= 0 && best1 >= 0) {
 #pragma unroll
-        for (int c = 0; c < 3; c++) *reinterpret_cast<short2*>(tl + c * plane) = make_short2((short)lap0[c], (short)lap1[c]);
-        *reinterpret_cast<float2*>(tw) = make_float2(bw0, bw1);
-    } else if (best0 >= 0) {
+    for (int r = 0; r < 2; r++) {
+        const int k0 = 2 * r, k1 = 2 * r + 1;
+        int16_t* tr = tl + (size_t)r * n;
+        float* wr = tw + (size_t)r * n;
+        if (best[k0] >= 0 && best[k1] >= 0) {
 #pragma unroll
-        for (int c = 0; c < 3; c++) tl[c * plane] = (int16_t)lap0[c];
-        tw[0] = bw0;
-    } else {
+            for (int c = 0; c < 3; c++) *reinterpret_cast<short2*>(tr + c * plane) = make_short2((short)lap[k0][c], (short)lap[k1][c]);
+            *reinterpret_cast<float2*>(wr) = make_float2(bw[k0], bw[k1]);
+        } else if (best[k0] >= 0) {
 #pragma unroll
-        for (int c = 0; c < 3; c++) tl[c * plane + 1] = (int16_t)lap1[c];
-        tw[1] = bw1;
+            for (int c = 0; c < 3; c++) tr[c * plane] = (int16_t)lap[k0][c];
+            wr[0] = bw[k0];
+        } else if (best[k1] >= 0) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) tr[c * plane + 1] = (int16_t)lap[k1][c];
+            wr[1] = bw[k1];
+        }
     }
 }
 cudaError_t launch_mb_select(const GroupParams& p, const TileLayout& lay, cudaStream_t stream) {
     if (p.n_tiles == 0) return cudaSuccess;
-    int pairs = 0;
+    int quads = 0;
     for (int l = 0; l < p.levels; l++) {
-        int n = kEle >> l;
-        pairs += n * (n > 1 ? n / 2 : 1);
+        int n = kEle >> l, half = n > 1 ? n / 2 : 1;
+        quads += half * half;
     }
-    dim3 g(p.n_tiles, (pairs + 255) / 256);
+    dim3 g(p.n_tiles, (quads + 255) / 256);
     mb_select_kernel<<<g, 256, 0, stream>>>(p, lay);
     return cudaGetLastError();
 }

@@ -82,6 +82,7 @@ cudaError_t launch_pack(const GroupParams& p, cudaStream_t stream);
 cudaError_t launch_weighted_group(const GroupParams& p, cudaStream_t stream);
 cudaError_t launch_mb_warp(const GroupParams& p, cudaStream_t stream);
 cudaError_t launch_mb_pyrdown(const GroupParams& p, int level /* src level */, cudaStream_t stream);
+cudaError_t launch_mb_pyrtail(const GroupParams& p, int l_first, cudaStream_t stream);
 cudaError_t launch_mb_select(const GroupParams& p, const TileLayout& lay, cudaStream_t stream);
 cudaError_t launch_mosaic_paste(const PasteItem* d_items, int n_items, const TileLayout& lay, const MosaicSet& ms, cudaStream_t stream);
 cudaError_t launch_mosaic_upadd(MosaicLevel coarse, MosaicLevel fine, cudaStream_t stream);

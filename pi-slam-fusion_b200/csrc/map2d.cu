@@ -57,6 +57,7 @@ struct ProfRec { int kind; cudaEvent_t e0, e1; };
 // Device + pinned buffers of one in-flight group.  Two contexts alternate so that the host can prepare group g+1
 // (bounds, tile allocation, work lists, H2D copies) while the GPU fuses group g.
 struct GroupCtx {
+    cudaEvent_t copied = nullptr;     // host frames of the group have landed in d_raw (copy stream)
     cudaEvent_t done = nullptr;       // recorded after the group's last kernel
     bool busy = false;
     int frames = 0;
@@ -109,6 +110,7 @@ struct m2d_map {
 
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t copy_stream = nullptr;  // H2D staging of host frames overlaps the previous group's kernels
 
     unsigned long long* d_stats = nullptr;  // [0..8] level wins, [16] footprint, [17] weighted wins
     m2d_stats stats{};
@@ -156,7 +158,11 @@ int m2d_map::init() {
     own_stream = true;
     CU(cudaMalloc(&d_stats, 32 * sizeof(unsigned long long)));
     CU(cudaMemsetAsync(d_stats, 0, 32 * sizeof(unsigned long long), stream));
-    for (int i = 0; i < kCtx; i++) CU(cudaEventCreateWithFlags(&ctx[i].done, cudaEventDisableTiming));
+    CU(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < kCtx; i++) {
+        CU(cudaEventCreateWithFlags(&ctx[i].done, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx[i].copied, cudaEventDisableTiming));
+    }
     levels = (type == M2D_TYPE_MULTIBAND) ? band_num + 1 : 1;
     if (type == M2D_TYPE_MULTIBAND) {
         lay = make_tile_layout(levels);
@@ -178,6 +184,7 @@ void m2d_map::release() {
     for (int i = 0; i < kCtx; i++) {
         GroupCtx& c = ctx[i];
         if (c.done) cudaEventDestroy(c.done);
+        if (c.copied) cudaEventDestroy(c.copied);
         if (c.h_blob) cudaFreeHost(c.h_blob);
         if (c.d_blob) cudaFree(c.d_blob);
         if (c.d_packed) cudaFree(c.d_packed);
@@ -187,6 +194,7 @@ void m2d_map::release() {
     if (d_stats) cudaFree(d_stats);
     if (d_collapse) cudaFree(d_collapse);
     for (ProfRec& r : prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
     if (own_stream && stream) cudaStreamDestroy(stream);
 }
 
@@ -311,7 +319,7 @@ int m2d_map::grow(void** p, size_t* cap, size_t need, bool pinned) {
 int m2d_map::group_size(int w, int h) const {
     if (cfg.batch_frames > 0) return std::min(cfg.batch_frames, 64);
     double mpx = (double)w * h / 1e6;
-    int k = (int)(16.0 / std::max(mpx, 0.25));  // ~16 Mpx of source per group
+    int k = (int)(30.0 / std::max(mpx, 0.25));  // ~30 Mpx of source per group (measured: larger groups amortise better)
     return std::max(1, std::min(k, 32));
 }
 
@@ -484,17 +492,22 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
     if (!on_device) { int rc = grow((void**)&c.d_raw, &c.raw_cap, (size_t)nj * npx * 3 + 256, false); if (rc != M2D_OK) return rc; }
     if (scratch) { int rc = grow((void**)&c.d_scratch, &c.scratch_cap, scratch, false); if (rc != M2D_OK) return rc; }
 
-    // ---- frames: host images are staged into HBM (stream-ordered), device images are used in place
+    // ---- frames: host images are staged into HBM on the copy stream (this context's previous group has finished,
+    // so d_raw is free; the copy overlaps the OTHER context's kernels); device images are used in place
     for (int j = 0; j < nj; j++) {
         const uint8_t* src = base + (size_t)src_index[j] * frame_stride;
         if (on_device) { jobs[j].raw = src; jobs[j].raw_stride = (int)stride; }
         else {
             uint8_t* dst = c.d_raw + (size_t)j * npx * 3;
-            if (stride == (size_t)w * 3) CU(cudaMemcpyAsync(dst, src, npx * 3, cudaMemcpyHostToDevice, stream));
-            else CU(cudaMemcpy2DAsync(dst, (size_t)w * 3, src, stride, (size_t)w * 3, h, cudaMemcpyHostToDevice, stream));
+            if (stride == (size_t)w * 3) CU(cudaMemcpyAsync(dst, src, npx * 3, cudaMemcpyHostToDevice, copy_stream));
+            else CU(cudaMemcpy2DAsync(dst, (size_t)w * 3, src, stride, (size_t)w * 3, h, cudaMemcpyHostToDevice, copy_stream));
             jobs[j].raw = dst; jobs[j].raw_stride = w * 3;
         }
         jobs[j].packed = c.d_packed + (size_t)j * npx;
+    }
+    if (!on_device) {
+        CU(cudaEventRecord(c.copied, copy_stream));
+        CU(cudaStreamWaitEvent(stream, c.copied, 0));
     }
     // ---- work lists
     memcpy(c.h_blob, jobs.data(), (size_t)nj * sizeof(FrameJob));
@@ -522,7 +535,10 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
     LAUNCHK(M2D_K_PACK, launch_pack(p, stream));
     if (type == M2D_TYPE_MULTIBAND) {
         LAUNCHK(M2D_K_MB_WARP, launch_mb_warp(p, stream));
-        for (int l = 0; l + 1 < levels; l++) LAUNCHK(M2D_K_MB_PYRDOWN, launch_mb_pyrdown(p, l, stream));
+        // full-grid pyrDown while a level is big enough; the small deep levels go through one tail launch
+        int l = 0;
+        for (; l + 1 < levels && (l < 3 || levels - 1 - l < 2); l++) LAUNCHK(M2D_K_MB_PYRDOWN, launch_mb_pyrdown(p, l, stream));
+        if (l + 1 < levels) LAUNCHK(M2D_K_MB_PYRTAIL, launch_mb_pyrtail(p, l, stream));
         LAUNCHK(M2D_K_MB_SELECT, launch_mb_select(p, lay, stream));
     } else {
         LAUNCHK(M2D_K_WEIGHTED, launch_weighted_group(p, stream));

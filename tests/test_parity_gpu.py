@@ -158,6 +158,31 @@ def test_full_size_720p_prefix(typ):
     g.close()
 
 
+@pytest.mark.parametrize("typ", [1, 3])
+def test_full_size_4000x3000_prefix(typ):
+    """BASELINE.json configs[2]/[3] frame size (Phantom/Mavic-class 12 Mpx): a 17x13-tile region per frame, 200 MB of
+    scratch pyramid per frame.  First frames of the seeded survey, fed as one batch, bit-exact vs the oracle."""
+    import torch
+    seq = synth.Sequence(1000, 4000, 3000, seed=3, jitter=(typ == 3))
+    n = 3
+    frames = np.stack([seq.frame(k) for k in range(n)])
+    dev = torch.from_numpy(frames).cuda()
+    g = m2d.Map2D.create(typ, thread=False)
+    o = O.OracleMap2D.create(typ)
+    O.set_threads(16)
+    try:
+        assert g.prepare(seq.plane, seq.camera, seq.prepare_poses) and o.prepare(seq.plane, seq.camera, seq.prepare_poses)
+        res = g.feed_batch(dev.data_ptr(), n, 4000 * 3000 * 3, 4000, 3000, 4000 * 3, seq.poses[:n], True)
+        for k in range(n):
+            assert (res[k] == 0) == o.feed(frames[k], seq.poses[k])
+        g.sync()
+        assert g.last_rect() == o.last_rect()
+        compare_state(g, o, typ)
+    finally:
+        O.set_threads(1)
+    g.close()
+
+
 def test_feed_paths_agree():
     """feed (host, staged), feed_device and feed_batch must leave identical state."""
     import torch
