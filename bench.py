@@ -104,24 +104,36 @@ def algorithmic_bytes(mode, stats, levels):
     return b
 
 
-def stage_bytes(mode, stats, levels, nframes):
-    """Per kernel class: bytes the stage must move per launch given ITS inputs/outputs (scratch pyramid counted)."""
-    out = {}
+def stage_bytes(mode, stats, levels):
+    """Per kernel class, per STEP: bytes the stage must move given ITS inputs/outputs (scratch pyramid counted at the
+    reference's element sizes: 6 B int16x3 + 4 B f32 per px).  Divided by the class's launch count -> per launch."""
+    out = {"pack": 7 * stats["input_px"]}
     if mode == "weighted":
-        out["weighted_fuse"] = algorithmic_bytes(mode, stats, levels) / nframes
+        out["weighted_fuse"] = algorithmic_bytes(mode, stats, levels)
         return out
-    D = [stats["region_px"][l] / nframes for l in range(levels)]
-    out["mb_warp"] = 3 * W * H + 10 * D[0]
+    D = [stats["region_px"][l] for l in range(levels)]
+    out["mb_warp"] = 3 * stats["input_px"] + 10 * D[0]
     nfull = min(3, levels - 1)  # levels handled by full-grid pyrDown launches; the rest by the tail kernel
-    out["mb_pyrdown"] = sum(10 * D[l] + 10 * D[l + 1] for l in range(nfull)) / max(nfull, 1)
+    out["mb_pyrdown"] = sum(10 * D[l] + 10 * D[l + 1] for l in range(nfull))
     out["mb_pyrtail"] = sum(10 * D[l] + 10 * D[l + 1] for l in range(nfull, levels - 1))
     sel = 0.0
     for l in range(levels):
-        nonfresh = (stats["region_px"][l] - stats["fresh_px"][l]) / nframes
-        written = (stats["fresh_px"][l] + stats["win_px"][l]) / nframes
+        nonfresh = stats["region_px"][l] - stats["fresh_px"][l]
+        written = stats["fresh_px"][l] + stats["win_px"][l]
         sel += 4 * D[l] + 4 * nonfresh + written * (6 + 10 + (6 / 4 if l + 1 < levels else 0))
     out["mb_select"] = sel
     return out
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed ncu --set full capture of
+    this same workload (profiles/ncu_traffic.json, written by scripts/ncu_summary.py); None if absent."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        t = json.load(f)
+    return t.get(kernel, {}).get("dram_bytes_per_launch")
 
 
 def run_reference(args, rank):
@@ -253,19 +265,20 @@ def main():
     kt = m.kernel_times()
     m.profile(False)
     peak, peak_src = peaks()
-    sb = stage_bytes(mode, stats, levels, fused)
+    sb = stage_bytes(mode, stats, levels)
     total_kernel_ms = sum(v[0] for v in kt.values())
     dom = max(kt.items(), key=lambda kv: kv[1][0])[0]
     per_kernel = {}
     for k, (ms, cnt) in kt.items():
         per_launch_us = ms / cnt * 1e3
-        ach = sb[k] / (ms / cnt * 1e-3) / 1e9 if k in sb else None
+        bpl = sb[k] / cnt if k in sb else None  # the profiled pass is exactly one step
+        ach = bpl / (ms / cnt * 1e-3) / 1e9 if bpl else None
         per_kernel[k] = {"launches": cnt, "avg_us": round(per_launch_us, 3), "share": round(ms / total_kernel_ms, 4),
-                         "bytes_per_launch": sb.get(k), "achieved_gbs": ach}
+                         "bytes_per_launch": bpl, "achieved_gbs": ach, "frames_per_launch": round(fused * (3 if k == "mb_pyrdown" else 1) / cnt, 2)}
     path_bytes = algorithmic_bytes(mode, stats, levels)
     path_ach = path_bytes / (ms_step * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": per_kernel[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": (per_kernel[dom]["achieved_gbs"] or 0) / peak, "traffic": None, "peak_source": peak_src,
+                "frac": (per_kernel[dom]["achieved_gbs"] or 0) / peak, "traffic": ncu_traffic(dom), "peak_source": peak_src,
                 "kernels": per_kernel,
                 "path": {"bytes_per_step": path_bytes, "bytes_per_input_px": path_bytes / (fused * W * H),
                          "achieved": path_ach, "frac": path_ach / peak}}

@@ -376,7 +376,7 @@ __device__ __forceinline__ HRow pyr_hrow(const uint32_t* __restrict__ gr, const 
     return h;
 }
 
-__global__ void __launch_bounds__(256) mb_pyrdown_kernel(const __grid_constant__ GroupParams p, int l) {
+__global__ void __launch_bounds__(256, 4) mb_pyrdown_kernel(const __grid_constant__ GroupParams p, int l) {
     const FrameJob& J = p.jobs[blockIdx.y];
     const int ns = kEle >> l, nd = kEle >> (l + 1);
     const int sww = J.wnx * ns, swh = J.wny * ns, srw = J.nx * ns, srh = J.ny * ns, sox = J.wx * ns, soy = J.wy * ns;
@@ -701,9 +701,42 @@ cudaError_t launch_mb_select(const GroupParams& p, const TileLayout& lay, cudaSt
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// final tile gather of a sharded run: pack the raw state of n tiles into one contiguous buffer (or back)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tile_copy_kernel(uint8_t* const* __restrict__ tiles, uint8_t* __restrict__ buf, size_t tile_bytes, int to_buf) {
+    const size_t n16 = tile_bytes / 16;
+    uint4* t = reinterpret_cast<uint4*>(tiles[blockIdx.x]);
+    uint4* b = reinterpret_cast<uint4*>(buf + (size_t)blockIdx.x * tile_bytes);
+    for (size_t i = (size_t)blockIdx.y * 256 + threadIdx.x; i < n16; i += (size_t)gridDim.y * 256) {
+        if (to_buf) b[i] = t[i]; else t[i] = b[i];
+    }
+}
+cudaError_t launch_tile_copy(uint8_t* const* d_tiles, int n, uint8_t* buf, size_t tile_bytes, int to_buf, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    dim3 g(n, 32);
+    tile_copy_kernel<<<g, 256, 0, stream>>>(d_tiles, buf, tile_bytes, to_buf);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // collapse (MultiBandMap2DCPU::save, :779-841): paste tiles into per-level mosaics, restore from the Laplacian
 // pyramid coarse -> fine (pyrUp + saturating add), convert to 8-bit and paint the background where weight == 0.
 // ---------------------------------------------------------------------------------------------------------
+// Weighted save(): paste every touched 256x256 BGRA tile into the zero-initialised mosaic (16 bytes per thread).
+__global__ void __launch_bounds__(256) bgra_paste_kernel(const PasteItem* __restrict__ items, uint32_t* __restrict__ mosaic, int mosaic_w) {
+    const PasteItem it = items[blockIdx.x];
+    int i = blockIdx.y * 256 + threadIdx.x;          // 16-byte chunk index inside the tile: 64 per row, 256 rows
+    int y = i >> 6, x = (i & 63) * 4;
+    uint4 v = reinterpret_cast<const uint4*>(it.tile)[i];
+    *reinterpret_cast<uint4*>(mosaic + (size_t)(it.ty * kEle + y) * mosaic_w + (size_t)it.tx * kEle + x) = v;
+}
+cudaError_t launch_bgra_paste(const PasteItem* d_items, int n_items, uint32_t* mosaic, int mosaic_w, cudaStream_t stream) {
+    if (n_items == 0) return cudaSuccess;
+    dim3 g(n_items, kEle * kEle / 4 / 256);
+    bgra_paste_kernel<<<g, 256, 0, stream>>>(d_items, mosaic, mosaic_w);
+    return cudaGetLastError();
+}
+
 // One launch pastes every touched tile (all levels) into the zero-initialised per-level mosaics.
 __global__ void __launch_bounds__(256) mosaic_paste_kernel(const PasteItem* __restrict__ items, const __grid_constant__ TileLayout lay,
                                                            const __grid_constant__ MosaicSet ms) {

@@ -84,6 +84,8 @@ cudaError_t launch_mb_warp(const GroupParams& p, cudaStream_t stream);
 cudaError_t launch_mb_pyrdown(const GroupParams& p, int level /* src level */, cudaStream_t stream);
 cudaError_t launch_mb_pyrtail(const GroupParams& p, int l_first, cudaStream_t stream);
 cudaError_t launch_mb_select(const GroupParams& p, const TileLayout& lay, cudaStream_t stream);
+cudaError_t launch_tile_copy(uint8_t* const* d_tiles, int n, uint8_t* buf, size_t tile_bytes, int to_buf, cudaStream_t stream);
+cudaError_t launch_bgra_paste(const PasteItem* d_items, int n_items, uint32_t* mosaic, int mosaic_w, cudaStream_t stream);
 cudaError_t launch_mosaic_paste(const PasteItem* d_items, int n_items, const TileLayout& lay, const MosaicSet& ms, cudaStream_t stream);
 cudaError_t launch_mosaic_upadd(MosaicLevel coarse, MosaicLevel fine, cudaStream_t stream);
 cudaError_t launch_mosaic_final(MosaicLevel m0, const float* w0, int background, uint8_t* out_bgr, cudaStream_t stream);

@@ -35,21 +35,22 @@ using namespace m2d;
             return M2D_ERR_CUDA;                                                                      \
         }                                                                                             \
     } while (0)
-#define LAUNCHK(kind, call)                                   \
+#define LAUNCHKS(kind, strm, call)                            \
     do {                                                      \
         cudaEvent_t pe0_ = nullptr, pe1_ = nullptr;           \
         if (profiling) {                                      \
             CU(cudaEventCreate(&pe0_));                       \
             CU(cudaEventCreate(&pe1_));                       \
-            CU(cudaEventRecord(pe0_, stream));                \
+            CU(cudaEventRecord(pe0_, strm));                  \
         }                                                     \
         CU(call);                                             \
         launches++;                                           \
         if (profiling) {                                      \
-            CU(cudaEventRecord(pe1_, stream));                \
+            CU(cudaEventRecord(pe1_, strm));                  \
             prof.push_back(ProfRec{kind, pe0_, pe1_});        \
         }                                                     \
     } while (0)
+#define LAUNCHK(kind, call) LAUNCHKS(kind, stream, call)
 #define LAUNCH(call) LAUNCHK(M2D_K_MISC, call)
 
 struct ProfRec { int kind; cudaEvent_t e0, e1; };
@@ -58,7 +59,9 @@ struct ProfRec { int kind; cudaEvent_t e0, e1; };
 // (bounds, tile allocation, work lists, H2D copies) while the GPU fuses group g.
 struct GroupCtx {
     cudaEvent_t copied = nullptr;     // host frames of the group have landed in d_raw (copy stream)
+    cudaEvent_t staged = nullptr;     // order-independent stages (pack / warp / pyramid) finished on `stage`
     cudaEvent_t done = nullptr;       // recorded after the group's last kernel
+    cudaStream_t stage = nullptr;     // per-context stream: stages of group g+1 overlap the select of group g
     bool busy = false;
     int frames = 0;
     uint8_t* h_blob = nullptr;        // pinned: [FrameJob x K | TileWork x T | TileEntry x E]
@@ -104,7 +107,7 @@ struct m2d_map {
     uint8_t* d_collapse = nullptr;  // cached buffers of get_image()/save()
     size_t collapse_cap = 0;
 
-    static constexpr int kCtx = 2;
+    static constexpr int kCtx = 3;
     GroupCtx ctx[kCtx];
     int ctx_next = 0;
 
@@ -162,6 +165,8 @@ int m2d_map::init() {
     for (int i = 0; i < kCtx; i++) {
         CU(cudaEventCreateWithFlags(&ctx[i].done, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ctx[i].copied, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx[i].staged, cudaEventDisableTiming));
+        CU(cudaStreamCreateWithFlags(&ctx[i].stage, cudaStreamNonBlocking));
     }
     levels = (type == M2D_TYPE_MULTIBAND) ? band_num + 1 : 1;
     if (type == M2D_TYPE_MULTIBAND) {
@@ -185,6 +190,8 @@ void m2d_map::release() {
         GroupCtx& c = ctx[i];
         if (c.done) cudaEventDestroy(c.done);
         if (c.copied) cudaEventDestroy(c.copied);
+        if (c.staged) cudaEventDestroy(c.staged);
+        if (c.stage) { cudaStreamSynchronize(c.stage); cudaStreamDestroy(c.stage); }
         if (c.h_blob) cudaFreeHost(c.h_blob);
         if (c.d_blob) cudaFree(c.d_blob);
         if (c.d_packed) cudaFree(c.d_packed);
@@ -282,6 +289,7 @@ int m2d_map::ensure_weight_images(int w, int h) {
     if (type == M2D_TYPE_MULTIBAND) CU(cudaMalloc(&d_wimg, (size_t)w * h * sizeof(float)));
     else CU(cudaMalloc(&d_alpha, (size_t)w * h + 16));
     LAUNCH(launch_weight_images(w, h, cfg.weight_type, d_alpha, d_wimg, stream));
+    CU(cudaStreamSynchronize(stream));  // read by kernels on the per-context stage streams
     wimg_w = w; wimg_h = h;
     return M2D_OK;
 }
@@ -507,7 +515,7 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
     }
     if (!on_device) {
         CU(cudaEventRecord(c.copied, copy_stream));
-        CU(cudaStreamWaitEvent(stream, c.copied, 0));
+        CU(cudaStreamWaitEvent(c.stage, c.copied, 0));
     }
     // ---- work lists
     memcpy(c.h_blob, jobs.data(), (size_t)nj * sizeof(FrameJob));
@@ -520,7 +528,7 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
         first += tiles[t].count;
     }
     memcpy(c.h_blob + off_tiles, tiles.data(), tiles.size() * sizeof(TileWork));
-    CU(cudaMemcpyAsync(c.d_blob, c.h_blob, blob, cudaMemcpyHostToDevice, stream));
+    CU(cudaMemcpyAsync(c.d_blob, c.h_blob, blob, cudaMemcpyHostToDevice, c.stage));
 
     GroupParams p{};
     p.jobs = reinterpret_cast<const FrameJob*>(c.d_blob);
@@ -532,15 +540,27 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
     p.stats = cfg.collect_stats ? d_stats : nullptr;
     p.max_wnx = max_wnx; p.max_wny = max_wny;
 
-    LAUNCHK(M2D_K_PACK, launch_pack(p, stream));
+    // Order-independent stages run on the context's own stream (they overlap the previous group's select); the
+    // order-dependent tile-centric stage runs on the handle's stream, which serialises groups in feed order.
+    // While m2d_profile is on, nothing may overlap (per-kernel event timings must be clean): the stage stream
+    // first waits for everything already enqueued on the handle's stream.
+    if (profiling) {
+        CU(cudaEventRecord(c.staged, stream));
+        CU(cudaStreamWaitEvent(c.stage, c.staged, 0));
+    }
+    LAUNCHKS(M2D_K_PACK, c.stage, launch_pack(p, c.stage));
     if (type == M2D_TYPE_MULTIBAND) {
-        LAUNCHK(M2D_K_MB_WARP, launch_mb_warp(p, stream));
+        LAUNCHKS(M2D_K_MB_WARP, c.stage, launch_mb_warp(p, c.stage));
         // full-grid pyrDown while a level is big enough; the small deep levels go through one tail launch
         int l = 0;
-        for (; l + 1 < levels && (l < 3 || levels - 1 - l < 2); l++) LAUNCHK(M2D_K_MB_PYRDOWN, launch_mb_pyrdown(p, l, stream));
-        if (l + 1 < levels) LAUNCHK(M2D_K_MB_PYRTAIL, launch_mb_pyrtail(p, l, stream));
+        for (; l + 1 < levels && (l < 3 || levels - 1 - l < 2); l++) LAUNCHKS(M2D_K_MB_PYRDOWN, c.stage, launch_mb_pyrdown(p, l, c.stage));
+        if (l + 1 < levels) LAUNCHKS(M2D_K_MB_PYRTAIL, c.stage, launch_mb_pyrtail(p, l, c.stage));
+        CU(cudaEventRecord(c.staged, c.stage));
+        CU(cudaStreamWaitEvent(stream, c.staged, 0));
         LAUNCHK(M2D_K_MB_SELECT, launch_mb_select(p, lay, stream));
     } else {
+        CU(cudaEventRecord(c.staged, c.stage));
+        CU(cudaStreamWaitEvent(stream, c.staged, 0));
         LAUNCHK(M2D_K_WEIGHTED, launch_weighted_group(p, stream));
     }
     CU(cudaEventRecord(c.done, stream));
@@ -571,14 +591,19 @@ int m2d_map::get_image(uint8_t* out, int* w, int* h, int* channels, int* tmx, in
     CU(cudaSetDevice(cfg.device));
     size_t W = (size_t)*w, H = (size_t)*h;
     if (type != M2D_TYPE_MULTIBAND) {
-        memset(out, 0, W * H * 4);
+        // assemble the BGRA mosaic in HBM (one paste launch), then ONE device->host copy
+        std::vector<PasteItem> items;
         for (int y = y0; y < y1; y++)
-            for (int x = x0; x < x1; x++) {
-                const uint8_t* t = table[(size_t)y * g.w + x];
-                if (!t) continue;
-                CU(cudaMemcpy2DAsync(out + ((size_t)(y - y0) * kEle * W + (size_t)(x - x0) * kEle) * 4, W * 4, t, (size_t)kEle * 4,
-                                     (size_t)kEle * 4, kEle, cudaMemcpyDeviceToHost, stream));
-            }
+            for (int x = x0; x < x1; x++)
+                if (const uint8_t* t = table[(size_t)y * g.w + x]) items.push_back(PasteItem{t, x - x0, y - y0});
+        size_t off_items = (W * H * 4 + 255) & ~(size_t)255;
+        CU(cudaStreamSynchronize(stream));
+        { int rc = grow((void**)&d_collapse, &collapse_cap, off_items + items.size() * sizeof(PasteItem) + 256, false); if (rc != M2D_OK) return rc; }
+        PasteItem* d_items = reinterpret_cast<PasteItem*>(d_collapse + off_items);
+        CU(cudaMemsetAsync(d_collapse, 0, W * H * 4, stream));  // untouched tiles: the reference leaves them undefined, we define 0
+        CU(cudaMemcpyAsync(d_items, items.data(), items.size() * sizeof(PasteItem), cudaMemcpyHostToDevice, stream));
+        LAUNCHK(M2D_K_COLLAPSE, launch_bgra_paste(d_items, (int)items.size(), reinterpret_cast<uint32_t*>(d_collapse), (int)W, stream));
+        CU(cudaMemcpyAsync(out, d_collapse, W * H * 4, cudaMemcpyDeviceToHost, stream));
         CU(cudaStreamSynchronize(stream));
         return M2D_OK;
     }
@@ -771,21 +796,36 @@ int m2d_export_tiles(m2d_handle h, int max_tiles, int* abs_xy, uint8_t* dst, int
     if (!h || !abs_xy || !dst || !n_out) return M2D_ERR_ARG;
     m2d_map& m = *h;
     std::string& err = m.err;
+    uint64_t& launches = m.launches;
+    bool& profiling = m.profiling;
+    std::vector<ProfRec>& prof = m.prof;
+    cudaStream_t stream = m.stream;
     if (!m.valid) return M2D_ERR_STATE;
     CU(cudaSetDevice(m.cfg.device));
-    int n = 0;
+    std::vector<uint8_t*> ptrs;
     for (int y = 0; y < m.g.h; y++)
         for (int x = 0; x < m.g.w; x++) {
-            const uint8_t* t = m.table[(size_t)y * m.g.w + x];
+            uint8_t* t = m.table[(size_t)y * m.g.w + x];
             if (!t) continue;
-            if (n >= max_tiles) return M2D_ERR_ARG;
-            abs_xy[2 * n] = x + m.org_x; abs_xy[2 * n + 1] = y + m.org_y;
-            CU(cudaMemcpyAsync(dst + (size_t)n * m.tile_bytes, t, m.tile_bytes,
-                               dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, m.stream));
-            n++;
+            if ((int)ptrs.size() >= max_tiles) return M2D_ERR_ARG;
+            abs_xy[2 * ptrs.size()] = x + m.org_x; abs_xy[2 * ptrs.size() + 1] = y + m.org_y;
+            ptrs.push_back(t);
         }
-    CU(cudaStreamSynchronize(m.stream));
+    int n = (int)ptrs.size();
     *n_out = n;
+    if (n == 0) return M2D_OK;
+    if (dst_on_device && (m.tile_bytes % 16) == 0 && (reinterpret_cast<uintptr_t>(dst) % 16) == 0) {
+        // one gather kernel instead of n small copies
+        CU(cudaStreamSynchronize(stream));
+        { int rc = m.grow((void**)&m.d_collapse, &m.collapse_cap, (size_t)n * sizeof(uint8_t*) + 256, false); if (rc != M2D_OK) return rc; }
+        CU(cudaMemcpyAsync(m.d_collapse, ptrs.data(), (size_t)n * sizeof(uint8_t*), cudaMemcpyHostToDevice, stream));
+        LAUNCHK(M2D_K_MISC, launch_tile_copy(reinterpret_cast<uint8_t* const*>(m.d_collapse), n, dst, m.tile_bytes, 1, stream));
+    } else {
+        for (int i = 0; i < n; i++)
+            CU(cudaMemcpyAsync(dst + (size_t)i * m.tile_bytes, ptrs[i], m.tile_bytes,
+                               dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, stream));
+    }
+    CU(cudaStreamSynchronize(stream));
     return M2D_OK;
 }
 
@@ -793,17 +833,32 @@ int m2d_import_tiles(m2d_handle h, int n, const int* abs_xy, const uint8_t* src,
     if (!h || n < 0 || (n && (!abs_xy || !src))) return M2D_ERR_ARG;
     m2d_map& m = *h;
     std::string& err = m.err;
+    uint64_t& launches = m.launches;
+    bool& profiling = m.profiling;
+    std::vector<ProfRec>& prof = m.prof;
+    cudaStream_t stream = m.stream;
     if (!m.valid) return M2D_ERR_STATE;
+    if (n == 0) return M2D_OK;
     CU(cudaSetDevice(m.cfg.device));
+    std::vector<uint8_t*> ptrs(n);
     for (int i = 0; i < n; i++) {
         int x = abs_xy[2 * i] - m.org_x, y = abs_xy[2 * i + 1] - m.org_y;
         if (x < 0 || y < 0 || x >= m.g.w || y >= m.g.h) { err = "import: tile outside the grid (shards must see the same poses)"; return M2D_ERR_ARG; }
         uint8_t*& slot = m.table[(size_t)y * m.g.w + x];
         if (!slot) { int rc = m.alloc_tile(&slot); if (rc != M2D_OK) return rc; }
-        CU(cudaMemcpyAsync(slot, src + (size_t)i * m.tile_bytes, m.tile_bytes,
-                           src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, m.stream));
+        ptrs[i] = slot;
     }
-    CU(cudaStreamSynchronize(m.stream));
+    if (src_on_device && (m.tile_bytes % 16) == 0 && (reinterpret_cast<uintptr_t>(src) % 16) == 0) {
+        CU(cudaStreamSynchronize(stream));
+        { int rc = m.grow((void**)&m.d_collapse, &m.collapse_cap, (size_t)n * sizeof(uint8_t*) + 256, false); if (rc != M2D_OK) return rc; }
+        CU(cudaMemcpyAsync(m.d_collapse, ptrs.data(), (size_t)n * sizeof(uint8_t*), cudaMemcpyHostToDevice, stream));
+        LAUNCHK(M2D_K_MISC, launch_tile_copy(reinterpret_cast<uint8_t* const*>(m.d_collapse), n, const_cast<uint8_t*>(src), m.tile_bytes, 0, stream));
+    } else {
+        for (int i = 0; i < n; i++)
+            CU(cudaMemcpyAsync(ptrs[i], src + (size_t)i * m.tile_bytes, m.tile_bytes,
+                               src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream));
+    }
+    CU(cudaStreamSynchronize(stream));
     return M2D_OK;
 }
 

@@ -22,3 +22,21 @@ out.writerow([hdr[i] for i in idx])
 out.writerow([units[i] for i in idx])
 for r in rows[2:]:
     out.writerow([r[i] for i in idx])
+
+# also refresh profiles/ncu_traffic.json (per-kernel DRAM bytes per launch, largest launch of each kernel)
+if len(sys.argv) > 2 and sys.argv[2] == "--traffic":
+    import json, os
+    names = {"mb_warp_kernel": "mb_warp", "mb_pyrdown_kernel": "mb_pyrdown", "mb_select_kernel": "mb_select", "pack_kernel": "pack",
+             "weighted_group_kernel": "weighted_fuse", "mb_pyrtail_kernel": "mb_pyrtail"}
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_traffic.json")
+    t = json.load(open(path)) if os.path.exists(path) else {}
+    ik, ir, iw, it = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("gpu__time_duration.sum")
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for r in rows[2:]:
+        k = names.get(r[ik].split("(")[0])
+        if not k:
+            continue
+        tot = float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]]
+        if k not in t or tot > t[k]["dram_bytes_per_launch"]:
+            t[k] = {"dram_bytes_per_launch": tot, "duration_us": float(r[it]), "source": os.path.basename(sys.argv[1])}
+    json.dump(t, open(path, "w"), indent=1, sort_keys=True)
