@@ -171,9 +171,10 @@ __device__ __forceinline__ uint32_t tap_const0(const uint32_t* img, int sw, int 
     return ((unsigned)sx < (unsigned)sw && (unsigned)sy < (unsigned)sh) ? __ldg(img + (sy * sw + sx)) : 0u;
 }
 
-// Returns the warped BGRA px, or 0 when its alpha cannot beat `cur_alpha` (colour math skipped).
+// Returns the warped BGRA px, or 0 when its alpha cannot beat `cur_alpha` (colour math skipped).  `tie_wins`: an
+// equal alpha also replaces (used when frames are visited out of feed order and this frame is the earlier one).
 __device__ __forceinline__ uint32_t sample_bgra(const uint32_t* __restrict__ img, int sw, int sh, double fx, double fy, uint32_t cur_alpha,
-                                                uint32_t& out_alpha) {
+                                                bool tie_wins, uint32_t& out_alpha) {
     int X = rnd(fx * 32.0), Y = rnd(fy * 32.0);
     int sx = X >> 5, sy = Y >> 5;
     if (__builtin_expect((unsigned)(X + 1048544) >= 2097088u || (unsigned)(Y + 1048544) >= 2097088u, 0)) {
@@ -195,7 +196,7 @@ __device__ __forceinline__ uint32_t sample_bgra(const uint32_t* __restrict__ img
     uint32_t ga1 = __byte_perm(v10, 0u, 0x4341) * wa0 + __byte_perm(v11, 0u, 0x4341) * a;
     uint32_t A = ((ga0 >> 16) * wb0 + ((ga1 >> 16) * b + 512u)) >> 10;  // == (sum*32 + 16384) >> 15 (FixedPtCast<int,uchar,15>)
     out_alpha = A;
-    if (A <= cur_alpha) return 0u;
+    if (A < cur_alpha || (A == cur_alpha && !tie_wins) || A == 0u) return 0u;
     uint32_t br0 = (v00 & kM2) * wa0 + (v01 & kM2) * a;
     uint32_t br1 = (v10 & kM2) * wa0 + (v11 & kM2) * a;
     uint32_t B = (__byte_perm(br0, 0u, 0x4410) * wb0 + (__byte_perm(br1, 0u, 0x4410) * b + 512u)) >> 10;
@@ -204,15 +205,38 @@ __device__ __forceinline__ uint32_t sample_bgra(const uint32_t* __restrict__ img
     return B | (G << 8) | (R << 16) | (A << 24);
 }
 
+// Upper bound of the warped alpha over a 4-px group whose source positions run from (ax,ay) to (bx,by): every tap
+// lies within 1.5 px of that segment and the alpha image decreases with the distance to the frame centre
+// (Map2DCPU.cpp:243-256), so alpha <= alpha(distance(centre, segment) - 1.5).  Conservative by construction (+1).
+__device__ __forceinline__ uint32_t alpha_upper_bound(float ax, float ay, float bx, float by, float xc, float yc, float inv_dmax, int weight_type) {
+    float vx = bx - ax, vy = by - ay, cx = xc - ax, cy = yc - ay;
+    float vv = vx * vx + vy * vy;
+    float t = vv > 0.f ? __fdividef(cx * vx + cy * vy, vv) : 0.f;
+    t = fminf(fmaxf(t, 0.f), 1.f);
+    float dx = cx - t * vx, dy = cy - t * vy;
+    float r = fmaxf(sqrtf(dx * dx + dy * dy) - 1.5f, 0.f);
+    float dis = fminf(1.f - r * inv_dmax + 1e-4f, 1.f);
+    if (dis <= 0.f) return 2u;
+    float v = weight_type == 0 ? dis * 254.f : dis * dis * 254.f;
+    return (uint32_t)v + 2u;
+}
+
 __global__ void __launch_bounds__(256) weighted_group_kernel(const __grid_constant__ GroupParams p) {
     const TileWork T = p.tiles[blockIdx.x];
     int px = (threadIdx.x & 63) * 4, py = blockIdx.y * 4 + (threadIdx.x >> 6);
     uint4* sp = reinterpret_cast<uint4*>(T.state + ((size_t)py * kEle + px) * 4);
     uint4 st = T.fresh ? make_uint4(0u, 0u, 0u, 0u) : *sp;
     uint32_t s[4] = {st.x, st.y, st.z, st.w};
+    // Frame (feed-order index) that currently holds each px; -1 = the state that was there before this group, which
+    // wins every tie.  Needed because entries may be visited best-first instead of in feed order: the result of the
+    // reference's sequential `if (tile.a < dst.a)` is "largest alpha, earliest frame on ties", which is order-free.
+    int who[4] = {-1, -1, -1, -1};
     bool changed = T.fresh != 0;
     unsigned wins = 0, foot = 0;
     const float lim_x = (float)p.sw + 0.25f, lim_y = (float)p.sh + 0.25f;
+    const float xc = (float)(p.sw / 2), yc = (float)(p.sh / 2);
+    const float inv_dmax = rsqrtf(xc * xc + yc * yc) * 0.9999f;  // smaller => larger (conservative) alpha bound
+    const bool cull_by_alpha = p.stats == nullptr;  // the counters follow the sequential semantics: no shortcuts then
     for (int e = 0; e < T.count; e++) {
         const TileEntry E = p.entries[T.first + e];
         const FrameJob& J = p.jobs[E.frame];
@@ -230,16 +254,22 @@ __global__ void __launch_bounds__(256) weighted_group_kernel(const __grid_consta
         float ax = (float)fx[0], bx = (float)fx[3], ay = (float)fy[0], by = (float)fy[3];
         bool off = (ax < -1.25f && bx < -1.25f) || (ax > lim_x && bx > lim_x) || (ay < -1.25f && by < -1.25f) || (ay > lim_y && by > lim_y);
         if (off) continue;
+        if (cull_by_alpha) {
+            uint32_t amin = min(min(s[0] >> 24, s[1] >> 24), min(s[2] >> 24, s[3] >> 24));
+            if (alpha_upper_bound(ax, ay, bx, by, xc, yc, inv_dmax, p.weight_type) < amin) continue;  // cannot win or tie
+        }
         px_coord(M, rb, x1 + 1.0, fx[1], fy[1]);
         px_coord(M, rb, x1 + 2.0, fx[2], fy[2]);
         bool count_wins = !(T.fresh && e == 0);
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             uint32_t alpha;
-            uint32_t d = sample_bgra(J.packed, p.sw, p.sh, fx[j], fy[j], s[j] >> 24, alpha);
+            bool tie_wins = who[j] >= 0 && E.frame < who[j];
+            uint32_t d = sample_bgra(J.packed, p.sw, p.sh, fx[j], fy[j], s[j] >> 24, tie_wins, alpha);
             foot += alpha != 0u;
-            if (d) {  // d != 0 <=> alpha beats the state's (strict '<', Map2DCPU.cpp:327)
+            if (d) {  // alpha beats the holder's (strict '<', Map2DCPU.cpp:327), or equals it and this frame is earlier
                 s[j] = d;
+                who[j] = E.frame;
                 changed = true;
                 wins += count_wins;
             }

@@ -45,6 +45,7 @@ struct GroupParams {
     int n_frames, n_tiles;
     int sw, sh;                // source frame size
     int levels;                // multi-band: band_num + 1
+    int weight_type;           // Map2D.WeightType (alpha = dis or dis^2)
     const uint8_t* alpha;      // weighted: sw*sh alpha image (Map2DCPU.cpp:236-258)
     const float* wimg;         // multi-band: sw*sh float weight image (MultiBandMap2DCPU.cpp:396-418)
     uint8_t* scratch;          // multi-band: group scratch pyramid

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <string>
@@ -107,8 +108,9 @@ struct m2d_map {
     uint8_t* d_collapse = nullptr;  // cached buffers of get_image()/save()
     size_t collapse_cap = 0;
 
-    static constexpr int kCtx = 3;
-    GroupCtx ctx[kCtx];
+    static constexpr int kMaxCtx = 8;
+    int kCtx = 3;                   // group contexts in flight (M2D_CTX env overrides, for tuning)
+    GroupCtx ctx[kMaxCtx];
     int ctx_next = 0;
 
     cudaStream_t stream = nullptr;
@@ -161,6 +163,7 @@ int m2d_map::init() {
     own_stream = true;
     CU(cudaMalloc(&d_stats, 32 * sizeof(unsigned long long)));
     CU(cudaMemsetAsync(d_stats, 0, 32 * sizeof(unsigned long long), stream));
+    if (const char* e = getenv("M2D_CTX")) kCtx = std::max(2, std::min(atoi(e), (int)kMaxCtx));
     CU(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < kCtx; i++) {
         CU(cudaEventCreateWithFlags(&ctx[i].done, cudaEventDisableTiming));
@@ -186,7 +189,7 @@ void m2d_map::release() {
     free_tiles.clear();
     if (d_alpha) cudaFree(d_alpha);
     if (d_wimg) cudaFree(d_wimg);
-    for (int i = 0; i < kCtx; i++) {
+    for (int i = 0; i < kMaxCtx; i++) {
         GroupCtx& c = ctx[i];
         if (c.done) cudaEventDestroy(c.done);
         if (c.copied) cudaEventDestroy(c.copied);
@@ -400,8 +403,10 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
     std::vector<FrameJob> jobs;
     std::vector<TileWork> tiles;
     std::vector<std::vector<TileEntry>> per_tile;
+    std::vector<std::pair<int, int>> tile_abs;  // absolute tile coordinate of every TileWork
     std::unordered_map<uint8_t*, int> tile_index;
     std::vector<int> src_index;  // frame index (within the call) of every accepted job
+    std::vector<std::pair<float, float>> job_centre;  // frame footprint centre in ABSOLUTE tile units (ordering heuristic)
     jobs.reserve(n);
     size_t scratch = 0;
     int max_wnx = 1, max_wny = 1, any_rejected = 0;
@@ -452,6 +457,7 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
                         tile_index.emplace(slot, ti);
                         tiles.push_back(TileWork{slot, 0, 0, is_fresh ? 1 : 0});
                         per_tile.emplace_back();
+                        tile_abs.emplace_back(tx + org_x, ty + org_y);
                     } else ti = it->second;
                     per_tile[ti].push_back(TileEntry{job_idx, (short)(tx - fb.x0), (short)(ty - fb.y0)});
                     for (int l = 0; l < levels; l++) {
@@ -481,6 +487,8 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
                 }
             jobs.push_back(J);
             src_index.push_back(i);
+            job_centre.emplace_back((float)((0.5 * (fb.gx0 + fb.gx1) - g.min_x) * g.ele_size_inv) + (float)org_x,
+                                    (float)((0.5 * (fb.gy0 + fb.gy1) - g.min_y) * g.ele_size_inv) + (float)org_y);
         } while (0);
         if (result) result[i] = status;
         if (status != M2D_OK) any_rejected = 1;
@@ -521,7 +529,19 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
     memcpy(c.h_blob, jobs.data(), (size_t)nj * sizeof(FrameJob));
     TileEntry* he = reinterpret_cast<TileEntry*>(c.h_blob + off_entries);
     int first = 0;
+    // Weighted mode visits a tile's frames best-first (closest footprint centre first): the result is order-free
+    // ("largest alpha, earliest frame on ties", tracked per px by the kernel) and almost every later frame is then
+    // rejected by the alpha upper bound before any sampling.  With collect_stats the sequential order is kept.
+    const bool best_first = (type != M2D_TYPE_MULTIBAND) && !cfg.collect_stats;
     for (size_t t = 0; t < tiles.size(); t++) {
+        if (best_first && per_tile[t].size() > 1) {
+            float cx = (float)tile_abs[t].first + 0.5f, cy = (float)tile_abs[t].second + 0.5f;
+            std::stable_sort(per_tile[t].begin(), per_tile[t].end(), [&](const TileEntry& a, const TileEntry& b) {
+                float ax = job_centre[a.frame].first - cx, ay = job_centre[a.frame].second - cy;
+                float bx = job_centre[b.frame].first - cx, by = job_centre[b.frame].second - cy;
+                return ax * ax + ay * ay < bx * bx + by * by;
+            });
+        }
         tiles[t].first = first;
         tiles[t].count = (int)per_tile[t].size();
         memcpy(he + first, per_tile[t].data(), per_tile[t].size() * sizeof(TileEntry));
@@ -535,7 +555,7 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
     p.tiles = reinterpret_cast<const TileWork*>(c.d_blob + off_tiles);
     p.entries = reinterpret_cast<const TileEntry*>(c.d_blob + off_entries);
     p.n_frames = nj; p.n_tiles = (int)tiles.size();
-    p.sw = w; p.sh = h; p.levels = levels;
+    p.sw = w; p.sh = h; p.levels = levels; p.weight_type = cfg.weight_type;
     p.alpha = d_alpha; p.wimg = d_wimg; p.scratch = c.d_scratch;
     p.stats = cfg.collect_stats ? d_stats : nullptr;
     p.max_wnx = max_wnx; p.max_wny = max_wny;
