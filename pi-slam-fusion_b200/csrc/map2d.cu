@@ -724,8 +724,9 @@ int m2d_feed_device(m2d_handle h, const uint8_t* d_bgr, int w, int hpx, size_t s
 }
 int m2d_feed_batch(m2d_handle h, int n, const uint8_t* base, size_t frame_stride, int w, int hpx, size_t stride,
                    const double* poses, int on_device, int* result) {
-    if (!h || n < 0 || !base || !poses) return M2D_ERR_ARG;
-    if (n == 0) return M2D_OK;
+    if (!h || n < 0) return M2D_ERR_ARG;
+    if (n == 0) return M2D_OK;  // empty batch: nothing to do
+    if (!base || !poses) return M2D_ERR_ARG;
     int rc = h->feed_frames(n, base, frame_stride, w, hpx, stride, poses, on_device != 0, result);
     return rc < 0 ? rc : M2D_OK;
 }

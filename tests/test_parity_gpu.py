@@ -183,6 +183,39 @@ def test_full_size_4000x3000_prefix(typ):
     g.close()
 
 
+@pytest.mark.parametrize("typ", [1, 3])
+def test_ragged_shapes_and_strides(typ):
+    """Frame width not a multiple of 4 (generic pack path, unaligned rows), odd height, a padded row stride on the
+    host path, and a 1-frame batch: everything must still match the oracle bit for bit."""
+    import torch
+    seq = synth.Sequence(7, 322, 181, seed=17, jitter=True, fpl=4, prepare_frames=3)
+    g = m2d.Map2D.create(typ, thread=False, batch_frames=3)
+    o = O.OracleMap2D.create(typ)
+    assert g.prepare(seq.plane, seq.camera, seq.prepare_poses) and o.prepare(seq.plane, seq.camera, seq.prepare_poses)
+    padded = np.zeros((181, 322 * 3 + 13), np.uint8)
+    for k in range(seq.n):
+        f = seq.frame(k)
+        assert o.feed(f, seq.poses[k])
+        if k % 3 == 0:    # host image with a padded stride
+            padded[:, :322 * 3] = f.reshape(181, -1)
+            view = padded[:, :322 * 3].reshape(181, 322, 3)
+            assert g.feed(view, seq.poses[k])
+        elif k % 3 == 1:  # device image, tight
+            d = torch.from_numpy(f).cuda()
+            assert g.feed_device(d.data_ptr(), 322, 181, 322 * 3, seq.poses[k])
+            g.sync()
+        else:             # device image with a padded stride, as a 1-frame batch
+            d = torch.from_numpy(padded.copy()).cuda()
+            d[:, :322 * 3] = torch.from_numpy(f.reshape(181, -1)).cuda()
+            res = g.feed_batch(d.data_ptr(), 1, 0, 322, 181, 322 * 3 + 13, seq.poses[k:k + 1], True)
+            assert res[0] == 0
+            g.sync()
+    g.sync()
+    compare_state(g, o, typ)
+    assert g.feed_batch(0, 0, 0, 322, 181, 322 * 3, seq.poses[:0], True).size == 0  # empty batch is a no-op
+    g.close()
+
+
 def test_feed_paths_agree():
     """feed (host, staged), feed_device and feed_batch must leave identical state."""
     import torch
