@@ -22,7 +22,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, typ, q):
+def _worker(rank, world, port, typ, distributed_input, q):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -37,7 +37,12 @@ def _worker(rank, world, port, typ, q):
         assert sm.prepare(seq.plane, seq.camera, seq.prepare_poses)
         poses = seq.poses.copy()
         poses[6, 3:] = [0.5, 0.5, 0.5, 0.5]  # rejected on every rank alike
-        res = sm.feed_all(frames, poses, seq.w, seq.h, chunk=5)
+        if distributed_input:
+            ids = ShardedMap2D.local_frame_ids(seq.n, rank, world, block=3)
+            local = torch.from_numpy(seq.frames(ids))
+            res = sm.feed_all_distributed(local, poses, seq.w, seq.h, block=3)
+        else:
+            res = sm.feed_all(frames, poses, seq.w, seq.h, chunk=5)
         owned = sm.map.tile_count()
         counts = [None] * world
         dist.all_gather_object(counts, owned)
@@ -75,12 +80,13 @@ def _worker(rank, world, port, typ, q):
 
 
 @pytest.mark.parametrize("typ", [1, 3])
-def test_two_rank_sharded_equals_unsharded(typ):
+@pytest.mark.parametrize("distributed_input", [False, True])
+def test_two_rank_sharded_equals_unsharded(typ, distributed_input):
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, typ, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, typ, distributed_input, q)) for r in range(world)]
     for p in procs:
         p.start()
     outs = [q.get(timeout=240) for _ in range(world)]
