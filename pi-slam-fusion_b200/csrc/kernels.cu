@@ -167,14 +167,38 @@ cudaError_t launch_pack(const GroupParams& p, cudaStream_t stream) {
 // bilinear, constant-0 border, Map2DCPU.cpp:282-299) and keeps the strictly-larger alpha (Map2DCPU.cpp:324-329);
 // the tile is read once and written once per group.
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t tap_const0(const uint32_t* img, int sw, int sh, int sx, int sy) {
-    return ((unsigned)sx < (unsigned)sw && (unsigned)sy < (unsigned)sh) ? __ldg(img + (sy * sw + sx)) : 0u;
+// ---- weighted sampling straight from the caller's BGR8 frame + the alpha plane (no packed copy of the frame) ----
+// One tap = 3 bytes at an arbitrary byte offset: fetch the aligned 32-bit words around it and funnel-shift.
+struct RawSrc {
+    const uint32_t* words;   // frame base rounded down to 4 bytes
+    int mis;                 // base & 3
+    int stride;              // bytes per row
+    const uint8_t* alpha;    // sw*sh alpha plane (Map2DCPU.cpp:236-258)
+    int sw, sh;
+};
+__device__ __forceinline__ uint32_t raw_tap(const RawSrc& R, int sx, int sy) {  // border-safe single tap (rare path)
+    if ((unsigned)sx >= (unsigned)R.sw || (unsigned)sy >= (unsigned)R.sh) return 0u;
+    const uint8_t* q = reinterpret_cast<const uint8_t*>(R.words) + R.mis + (size_t)sy * R.stride + 3 * sx;
+    return (uint32_t)__ldg(q) | ((uint32_t)__ldg(q + 1) << 8) | ((uint32_t)__ldg(q + 2) << 16) |
+           ((uint32_t)__ldg(R.alpha + sy * R.sw + sx) << 24);
+}
+// Two horizontally adjacent interior taps (sx, sx+1) of row sy: 6 consecutive bytes -> 3 aligned words.
+__device__ __forceinline__ void raw_tap_pair(const RawSrc& R, int sx, int sy, uint32_t& v0, uint32_t& v1) {
+    unsigned o = (unsigned)(sy * R.stride + 3 * sx + R.mis);
+    const uint32_t* w = R.words + (o >> 2);
+    unsigned sh = (o & 3u) * 8u;
+    uint32_t lo = __ldg(w), mid = __ldg(w + 1), hi = __ldg(w + 2);
+    uint32_t f0 = __funnelshift_r(lo, mid, sh), f1 = __funnelshift_r(mid, hi, sh);  // bytes o..o+3, o+4..o+7
+    const uint8_t* ap = R.alpha + (sy * R.sw + sx);
+    v0 = (f0 & 0x00FFFFFFu) | ((uint32_t)__ldg(ap) << 24);
+    v1 = __byte_perm(f0, f1, 0x0543) & 0x00FFFFFFu;   // bytes o+3, o+4, o+5
+    v1 |= (uint32_t)__ldg(ap + 1) << 24;
 }
 
 // Returns the warped BGRA px, or 0 when its alpha cannot beat `cur_alpha` (colour math skipped).  `tie_wins`: an
 // equal alpha also replaces (used when frames are visited out of feed order and this frame is the earlier one).
-__device__ __forceinline__ uint32_t sample_bgra(const uint32_t* __restrict__ img, int sw, int sh, double fx, double fy, uint32_t cur_alpha,
-                                                bool tie_wins, uint32_t& out_alpha) {
+__device__ __forceinline__ uint32_t sample_bgra(const RawSrc& R, double fx, double fy, uint32_t cur_alpha, bool tie_wins, uint32_t& out_alpha) {
+    const int sw = R.sw, sh = R.sh;
     int X = rnd(fx * 32.0), Y = rnd(fy * 32.0);
     int sx = X >> 5, sy = Y >> 5;
     if (__builtin_expect((unsigned)(X + 1048544) >= 2097088u || (unsigned)(Y + 1048544) >= 2097088u, 0)) {
@@ -184,11 +208,11 @@ __device__ __forceinline__ uint32_t sample_bgra(const uint32_t* __restrict__ img
     if (sx >= sw || sx + 1 < 0 || sy >= sh || sy + 1 < 0) return 0u;
     uint32_t v00, v01, v10, v11;
     if ((unsigned)sx < (unsigned)(sw - 1) && (unsigned)sy < (unsigned)(sh - 1)) {
-        const uint32_t* q = img + (sy * sw + sx);
-        v00 = __ldg(q); v01 = __ldg(q + 1); v10 = __ldg(q + sw); v11 = __ldg(q + sw + 1);
+        raw_tap_pair(R, sx, sy, v00, v01);
+        raw_tap_pair(R, sx, sy + 1, v10, v11);
     } else {
-        v00 = tap_const0(img, sw, sh, sx, sy); v01 = tap_const0(img, sw, sh, sx + 1, sy);
-        v10 = tap_const0(img, sw, sh, sx, sy + 1); v11 = tap_const0(img, sw, sh, sx + 1, sy + 1);
+        v00 = raw_tap(R, sx, sy); v01 = raw_tap(R, sx + 1, sy);
+        v10 = raw_tap(R, sx, sy + 1); v11 = raw_tap(R, sx + 1, sy + 1);
     }
     uint32_t a = X & 31, b = Y & 31, wa0 = 32 - a, wb0 = 32 - b;
     // horizontal pass on packed 16-bit lanes (max 255*32 = 8160 per lane); lanes (G,A) come out of one PRMT
@@ -200,9 +224,9 @@ __device__ __forceinline__ uint32_t sample_bgra(const uint32_t* __restrict__ img
     uint32_t br0 = (v00 & kM2) * wa0 + (v01 & kM2) * a;
     uint32_t br1 = (v10 & kM2) * wa0 + (v11 & kM2) * a;
     uint32_t B = (__byte_perm(br0, 0u, 0x4410) * wb0 + (__byte_perm(br1, 0u, 0x4410) * b + 512u)) >> 10;
-    uint32_t R = ((br0 >> 16) * wb0 + ((br1 >> 16) * b + 512u)) >> 10;
+    uint32_t R_ = ((br0 >> 16) * wb0 + ((br1 >> 16) * b + 512u)) >> 10;
     uint32_t G = (__byte_perm(ga0, 0u, 0x4410) * wb0 + (__byte_perm(ga1, 0u, 0x4410) * b + 512u)) >> 10;
-    return B | (G << 8) | (R << 16) | (A << 24);
+    return B | (G << 8) | (R_ << 16) | (A << 24);
 }
 
 // Upper bound of the warped alpha over a 4-px group whose source positions run from (ax,ay) to (bx,by): every tap
@@ -260,12 +284,16 @@ __global__ void __launch_bounds__(256) weighted_group_kernel(const __grid_consta
         }
         px_coord(M, rb, x1 + 1.0, fx[1], fy[1]);
         px_coord(M, rb, x1 + 2.0, fx[2], fy[2]);
+        RawSrc R;
+        R.mis = (int)(reinterpret_cast<uintptr_t>(J.raw) & 3);
+        R.words = reinterpret_cast<const uint32_t*>(J.raw - R.mis);
+        R.stride = J.raw_stride; R.alpha = p.alpha; R.sw = p.sw; R.sh = p.sh;
         bool count_wins = !(T.fresh && e == 0);
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             uint32_t alpha;
             bool tie_wins = who[j] >= 0 && E.frame < who[j];
-            uint32_t d = sample_bgra(J.packed, p.sw, p.sh, fx[j], fy[j], s[j] >> 24, tie_wins, alpha);
+            uint32_t d = sample_bgra(R, fx[j], fy[j], s[j] >> 24, tie_wins, alpha);
             foot += alpha != 0u;
             if (d) {  // alpha beats the holder's (strict '<', Map2DCPU.cpp:327), or equals it and this frame is earlier
                 s[j] = d;

@@ -504,7 +504,7 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
     size_t blob = off_entries + n_entries * sizeof(TileEntry) + 256;
     { size_t cap = c.blob_cap; int rc = grow((void**)&c.h_blob, &cap, blob, true); if (rc != M2D_OK) return rc;
       rc = grow((void**)&c.d_blob, &c.blob_cap, blob, false); if (rc != M2D_OK) return rc; }
-    { int rc = grow((void**)&c.d_packed, &c.packed_cap, (size_t)nj * npx * 4 + 256, false); if (rc != M2D_OK) return rc; }
+    if (type == M2D_TYPE_MULTIBAND) { int rc = grow((void**)&c.d_packed, &c.packed_cap, (size_t)nj * npx * 4 + 256, false); if (rc != M2D_OK) return rc; }
     if (!on_device) { int rc = grow((void**)&c.d_raw, &c.raw_cap, (size_t)nj * npx * 3 + 256, false); if (rc != M2D_OK) return rc; }
     if (scratch) { int rc = grow((void**)&c.d_scratch, &c.scratch_cap, scratch, false); if (rc != M2D_OK) return rc; }
 
@@ -568,8 +568,8 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
         CU(cudaEventRecord(c.staged, stream));
         CU(cudaStreamWaitEvent(c.stage, c.staged, 0));
     }
-    LAUNCHKS(M2D_K_PACK, c.stage, launch_pack(p, c.stage));
     if (type == M2D_TYPE_MULTIBAND) {
+        LAUNCHKS(M2D_K_PACK, c.stage, launch_pack(p, c.stage));
         LAUNCHKS(M2D_K_MB_WARP, c.stage, launch_mb_warp(p, c.stage));
         // full-grid pyrDown while a level is big enough; the small deep levels go through one tail launch
         int l = 0;
@@ -579,6 +579,7 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
         CU(cudaStreamWaitEvent(stream, c.staged, 0));
         LAUNCHK(M2D_K_MB_SELECT, launch_mb_select(p, lay, stream));
     } else {
+        // weighted mode samples the caller's BGR8 frames in place (plus the alpha plane): no packed copy
         CU(cudaEventRecord(c.staged, c.stage));
         CU(cudaStreamWaitEvent(stream, c.staged, 0));
         LAUNCHK(M2D_K_WEIGHTED, launch_weighted_group(p, stream));

@@ -17,11 +17,17 @@ import torch
 import torch.distributed as dist
 
 
-def default_shard(w, h, world):
-    """Strips across the survey's line-advance axis.  Narrow strips (half a frame width) keep all ranks busy on small
-    surveys at the price of more ring recomputation; a frame then lands on <= 3 ranks."""
-    fw = int(np.ceil(w / 256.0)) + 1
-    return {"shard_axis": 0, "shard_span": max(2, fw // 2 if world > 4 else fw)}
+def default_shard(w, h, world, poses=None, camera=None):
+    """Contiguous strips along the axis on which the survey is longer, sized so that every rank owns about one strip
+    (strip count ~ world): balanced load with the least ring recomputation.  Falls back to one frame width."""
+    fw, fh = int(np.ceil(w / 256.0)) + 1, int(np.ceil(h / 256.0)) + 1
+    if poses is None or camera is None or len(poses) < 2:
+        return {"shard_axis": 0, "shard_span": max(2, fw)}
+    poses = np.asarray(poses, np.float64).reshape(-1, 7)
+    gsd = float(np.median(np.abs(poses[:, 2]))) / float(camera[2])          # ground size of a map px at scale 1
+    ext = [(poses[:, 0].max() - poses[:, 0].min()) / (256.0 * gsd) + fw, (poses[:, 1].max() - poses[:, 1].min()) / (256.0 * gsd) + fh]
+    axis = 0 if ext[0] >= ext[1] else 1
+    return {"shard_axis": axis, "shard_span": max(2, int(np.ceil(ext[axis] / world)))}
 
 
 class ShardedMap2D:
@@ -193,16 +199,18 @@ def bench_main(args, rank, world, local_rank):
     n = args.frames
     seq = synth.Sequence(n, W, H, seed=SEED)
     dev = torch.device("cuda", local_rank)
-    ids = ShardedMap2D.local_frame_ids(n, rank, world)
+    block = max(8, 128 // world)
+    ids = ShardedMap2D.local_frame_ids(n, rank, world, block)
     frames = torch.from_numpy(np.stack([seq.frame(k) for k in ids])).to(dev)  # inputs resident in HBM, spread over the job's GPUs
-    shard = default_shard(W, H, world)
+    shard = default_shard(W, H, world, seq.poses, seq.camera)
+    block = max(8, 128 // world)
     sm = ShardedMap2D(lambda t, **kw: m2d.Map2D.create(t, thread=False, **kw), typ, rank, world, device=local_rank, **shard)
     assert sm.prepare(seq.plane, seq.camera, seq.prepare_poses)
 
     def step():
         sm.map.reset()
         t0 = time.perf_counter()
-        res = sm.feed_all_distributed(frames, seq.poses, W, H)
+        res = sm.feed_all_distributed(frames, seq.poses, W, H, block)
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         sm.gather_to_root()
