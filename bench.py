@@ -107,7 +107,7 @@ def algorithmic_bytes(mode, stats, levels):
 def stage_bytes(mode, stats, levels):
     """Per kernel class, per STEP: bytes the stage must move given ITS inputs/outputs (scratch pyramid counted at the
     reference's element sizes: 6 B int16x3 + 4 B f32 per px).  Divided by the class's launch count -> per launch."""
-    out = {"pack": 7 * stats["input_px"]}
+    out = {}
     if mode == "weighted":
         out["weighted_fuse"] = algorithmic_bytes(mode, stats, levels)
         return out

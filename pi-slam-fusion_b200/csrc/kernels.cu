@@ -121,51 +121,10 @@ __device__ __forceinline__ int sat_s16(int v) { return min(max(v, -32768), 32767
 constexpr uint32_t kM2 = 0x00FF00FFu;  // two 16-bit lanes holding one byte each
 
 // ---------------------------------------------------------------------------------------------------------
-// pack: BGR8 -> u8x4 (B,G,R,A).  Weighted mode: A = distance-to-centre alpha, i.e. exactly the reference's 8UC4
-// `src` image (Map2DCPU.cpp:259-275) built at HBM speed; multi-band: A = 0.  One thread = 4 px.
-// ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) pack_kernel(const __grid_constant__ GroupParams p) {
-    const FrameJob& J = p.jobs[blockIdx.y];
-    size_t npx = (size_t)p.sw * p.sh;
-    size_t i = ((size_t)blockIdx.x * 256 + threadIdx.x) * 4;
-    if (i >= npx) return;
-    bool fast = ((p.sw & 3) == 0) && ((J.raw_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(J.raw) & 3) == 0);
-    uint32_t o[4];
-    if (fast) {
-        int row = (int)(i / p.sw), col = (int)(i % p.sw);
-        const uint32_t* q = reinterpret_cast<const uint32_t*>(J.raw + (size_t)row * J.raw_stride + 3 * col);
-        uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
-        o[0] = w0 & 0x00FFFFFFu;
-        o[1] = (w0 >> 24) | ((w1 & 0xFFFFu) << 8);
-        o[2] = (w1 >> 16) | ((w2 & 0xFFu) << 16);
-        o[3] = w2 >> 8;
-        if (p.alpha) {
-            uint32_t a4 = __ldg(reinterpret_cast<const uint32_t*>(p.alpha + i));
-            o[0] |= (a4 & 0xFFu) << 24; o[1] |= (a4 & 0xFF00u) << 16; o[2] |= (a4 & 0xFF0000u) << 8; o[3] |= a4 & 0xFF000000u;
-        }
-        *reinterpret_cast<uint4*>(J.packed + i) = make_uint4(o[0], o[1], o[2], o[3]);
-    } else {
-        for (int k = 0; k < 4 && i + k < npx; k++) {
-            int row = (int)((i + k) / p.sw), col = (int)((i + k) % p.sw);
-            const uint8_t* q = J.raw + (size_t)row * J.raw_stride + 3 * col;
-            uint32_t v = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16);
-            if (p.alpha) v |= (uint32_t)p.alpha[i + k] << 24;
-            J.packed[i + k] = v;
-        }
-    }
-}
-cudaError_t launch_pack(const GroupParams& p, cudaStream_t stream) {
-    size_t npx = (size_t)p.sw * p.sh;
-    dim3 g((unsigned)((npx / 4 + 255) / 256 + 1), p.n_frames);
-    pack_kernel<<<g, 256, 0, stream>>>(p);
-    return cudaGetLastError();
-}
-
-// ---------------------------------------------------------------------------------------------------------
 // weighted mode, tile-centric: one CTA = 4 rows x 256 px of one tile, one thread = 4 consecutive px (one 16-byte
 // state vector).  The thread walks the group's frames that touch the tile IN FEED ORDER, warps each (8UC4
 // bilinear, constant-0 border, Map2DCPU.cpp:282-299) and keeps the strictly-larger alpha (Map2DCPU.cpp:324-329);
-// the tile is read once and written once per group.
+// the tile is read once and written once per group.  Frames are sampled in place (caller's BGR8 + alpha plane).
 // ---------------------------------------------------------------------------------------------------------
 // ---- weighted sampling straight from the caller's BGR8 frame + the alpha plane (no packed copy of the frame) ----
 // One tap = 3 bytes at an arbitrary byte offset: fetch the aligned 32-bit words around it and funnel-shift.
@@ -193,6 +152,20 @@ __device__ __forceinline__ void raw_tap_pair(const RawSrc& R, int sx, int sy, ui
     v0 = (f0 & 0x00FFFFFFu) | ((uint32_t)__ldg(ap) << 24);
     v1 = __byte_perm(f0, f1, 0x0543) & 0x00FFFFFFu;   // bytes o+3, o+4, o+5
     v1 |= (uint32_t)__ldg(ap + 1) << 24;
+}
+
+__device__ __forceinline__ uint32_t raw_tap_bgr(const RawSrc& R, int sx, int sy) {  // in-range single tap, no alpha
+    const uint8_t* q = reinterpret_cast<const uint8_t*>(R.words) + R.mis + (size_t)sy * R.stride + 3 * sx;
+    return (uint32_t)__ldg(q) | ((uint32_t)__ldg(q + 1) << 8) | ((uint32_t)__ldg(q + 2) << 16);
+}
+__device__ __forceinline__ void raw_tap_pair_bgr(const RawSrc& R, int sx, int sy, uint32_t& v0, uint32_t& v1) {
+    unsigned o = (unsigned)(sy * R.stride + 3 * sx + R.mis);
+    const uint32_t* w = R.words + (o >> 2);
+    unsigned sh = (o & 3u) * 8u;
+    uint32_t lo = __ldg(w), mid = __ldg(w + 1), hi = __ldg(w + 2);
+    uint32_t f0 = __funnelshift_r(lo, mid, sh), f1 = __funnelshift_r(mid, hi, sh);
+    v0 = f0 & 0x00FFFFFFu;
+    v1 = __byte_perm(f0, f1, 0x4543);   // bytes o+3, o+4, o+5, 0
 }
 
 // Returns the warped BGRA px, or 0 when its alpha cannot beat `cur_alpha` (colour math skipped).  `tie_wins`: an
@@ -358,7 +331,10 @@ __global__ void __launch_bounds__(256) mb_warp_kernel(const __grid_constant__ Gr
     RowBase rb = row_base(M, x, y);
     double x1 = (double)(x & 63);
     const int sw = p.sw, sh = p.sh;
-    const uint32_t* __restrict__ img = J.packed;
+    RawSrc R;
+    R.mis = (int)(reinterpret_cast<uintptr_t>(J.raw) & 3);
+    R.words = reinterpret_cast<const uint32_t*>(J.raw - R.mis);
+    R.stride = J.raw_stride; R.alpha = nullptr; R.sw = sw; R.sh = sh;
     const float* __restrict__ wimg = p.wimg;
     uint32_t g[4];
     float w[4];
@@ -377,12 +353,11 @@ __global__ void __launch_bounds__(256) mb_warp_kernel(const __grid_constant__ Gr
         w[j] = ((unsigned)nx < (unsigned)sw && (unsigned)ny < (unsigned)sh) ? __ldg(wimg + (ny * sw + nx)) : 0.f;
         uint32_t v00, v01, v10, v11;
         if ((unsigned)sx < (unsigned)(sw - 1) && (unsigned)sy < (unsigned)(sh - 1)) {
-            const uint32_t* q = img + (sy * sw + sx);
-            v00 = __ldg(q); v01 = __ldg(q + 1); v10 = __ldg(q + sw); v11 = __ldg(q + sw + 1);
+            raw_tap_pair_bgr(R, sx, sy, v00, v01);
+            raw_tap_pair_bgr(R, sx, sy + 1, v10, v11);
         } else {
             int sx0 = reflect_once(sx, sw), sx1 = reflect_once(sx + 1, sw), sy0 = reflect_once(sy, sh), sy1 = reflect_once(sy + 1, sh);
-            const uint32_t *r0 = img + sy0 * sw, *r1 = img + sy1 * sw;
-            v00 = __ldg(r0 + sx0); v01 = __ldg(r0 + sx1); v10 = __ldg(r1 + sx0); v11 = __ldg(r1 + sx1);
+            v00 = raw_tap_bgr(R, sx0, sy0); v01 = raw_tap_bgr(R, sx1, sy0); v10 = raw_tap_bgr(R, sx0, sy1); v11 = raw_tap_bgr(R, sx1, sy1);
         }
         // a = X & 31 as X - 32*sx: an IMAD on the FMA pipe instead of a LOP3 on the (saturated) ALU pipe
         g[j] = bilinear_rne_bgr(v00, v01, v10, v11, (uint32_t)(X - 32 * sx), (uint32_t)(Y - 32 * sy));

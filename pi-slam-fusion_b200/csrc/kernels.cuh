@@ -1,7 +1,7 @@
 // kernels.cuh — launch parameter blocks and host-callable launchers of the sm_100a kernels.
 //
 // Execution model: frames are fused in GROUPS of up to K frames.  All per-frame stages of a group
-// (pack, warp, pyramid) run as single launches over (work, frame); the order-dependent stage (select) is
+// (warp, pyramid) run as single launches over (work, frame); the order-dependent stage (select) is
 // TILE-CENTRIC: one work item per touched tile, looping over the group's frames in feed order, so every map tile
 // is read and written once per group and the result equals K sequential feed() calls.
 #pragma once
@@ -18,8 +18,7 @@ constexpr int kEle = M2D_ELE_PIXELS;
 // One frame of a group, as the kernels see it.  Lives in a device array (uploaded once per group).
 struct FrameJob {
     double hinv[9];            // region px -> source px (inverse homography, cv::warpPerspective convention)
-    const uint8_t* raw;        // BGR8 source in HBM
-    uint32_t* packed;          // u8x4 source (B,G,R,A) built by the pack kernel; A = alpha (weighted) or 0
+    const uint8_t* raw;        // BGR8 source in HBM, sampled in place (3-byte taps via aligned word loads)
     int raw_stride;
     int nx, ny;                // frame region in tiles
     int wx, wy, wnx, wny;      // pyramid window inside the region (tiles, relative to the region origin)
@@ -79,7 +78,6 @@ struct PasteItem {
 // launchers (asynchronous on `stream`; return the launch error)
 cudaError_t launch_weight_images(int sw, int sh, int weight_type, uint8_t* alpha, float* wimg, cudaStream_t stream);
 cudaError_t launch_bounds(const GridGeom& g, int n, const double* d_poses, FrameBounds* d_out, cudaStream_t stream);
-cudaError_t launch_pack(const GroupParams& p, cudaStream_t stream);
 cudaError_t launch_weighted_group(const GroupParams& p, cudaStream_t stream);
 cudaError_t launch_mb_warp(const GroupParams& p, cudaStream_t stream);
 cudaError_t launch_mb_pyrdown(const GroupParams& p, int level /* src level */, cudaStream_t stream);

@@ -68,8 +68,6 @@ struct GroupCtx {
     uint8_t* h_blob = nullptr;        // pinned: [FrameJob x K | TileWork x T | TileEntry x E]
     uint8_t* d_blob = nullptr;
     size_t blob_cap = 0;
-    uint32_t* d_packed = nullptr;     // K x sw*sh u8x4
-    size_t packed_cap = 0;
     uint8_t* d_raw = nullptr;         // K x sw*sh*3 staging for host frames
     size_t raw_cap = 0;
     uint8_t* d_scratch = nullptr;     // multi-band pyramids of the group
@@ -197,7 +195,6 @@ void m2d_map::release() {
         if (c.stage) { cudaStreamSynchronize(c.stage); cudaStreamDestroy(c.stage); }
         if (c.h_blob) cudaFreeHost(c.h_blob);
         if (c.d_blob) cudaFree(c.d_blob);
-        if (c.d_packed) cudaFree(c.d_packed);
         if (c.d_raw) cudaFree(c.d_raw);
         if (c.d_scratch) cudaFree(c.d_scratch);
     }
@@ -504,7 +501,6 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
     size_t blob = off_entries + n_entries * sizeof(TileEntry) + 256;
     { size_t cap = c.blob_cap; int rc = grow((void**)&c.h_blob, &cap, blob, true); if (rc != M2D_OK) return rc;
       rc = grow((void**)&c.d_blob, &c.blob_cap, blob, false); if (rc != M2D_OK) return rc; }
-    if (type == M2D_TYPE_MULTIBAND) { int rc = grow((void**)&c.d_packed, &c.packed_cap, (size_t)nj * npx * 4 + 256, false); if (rc != M2D_OK) return rc; }
     if (!on_device) { int rc = grow((void**)&c.d_raw, &c.raw_cap, (size_t)nj * npx * 3 + 256, false); if (rc != M2D_OK) return rc; }
     if (scratch) { int rc = grow((void**)&c.d_scratch, &c.scratch_cap, scratch, false); if (rc != M2D_OK) return rc; }
 
@@ -519,7 +515,6 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
             else CU(cudaMemcpy2DAsync(dst, (size_t)w * 3, src, stride, (size_t)w * 3, h, cudaMemcpyHostToDevice, copy_stream));
             jobs[j].raw = dst; jobs[j].raw_stride = w * 3;
         }
-        jobs[j].packed = c.d_packed + (size_t)j * npx;
     }
     if (!on_device) {
         CU(cudaEventRecord(c.copied, copy_stream));
@@ -569,7 +564,6 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
         CU(cudaStreamWaitEvent(c.stage, c.staged, 0));
     }
     if (type == M2D_TYPE_MULTIBAND) {
-        LAUNCHKS(M2D_K_PACK, c.stage, launch_pack(p, c.stage));
         LAUNCHKS(M2D_K_MB_WARP, c.stage, launch_mb_warp(p, c.stage));
         // full-grid pyrDown while a level is big enough; the small deep levels go through one tail launch
         int l = 0;
