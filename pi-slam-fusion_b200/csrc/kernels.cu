@@ -607,7 +607,7 @@ __device__ __forceinline__ void lap_quad(const GroupParams& p, const FrameJob& J
     }
 }
 
-__global__ void __launch_bounds__(256) mb_select_kernel(const __grid_constant__ GroupParams p, const __grid_constant__ TileLayout lay) {
+__global__ void __launch_bounds__(256, 6) mb_select_kernel(const __grid_constant__ GroupParams p, const __grid_constant__ TileLayout lay) {
     const TileWork T = p.tiles[blockIdx.x];
     // flat quad index -> (level, quad row, quad column); level l has (n/2)^2 quads (1 for the 1-px level)
     int q = blockIdx.y * 256 + threadIdx.x;
