@@ -153,7 +153,7 @@ uint64_t m2d_launch_count(m2d_handle h);
  * events; m2d_get_kernel_times synchronises and returns accumulated milliseconds and launch counts per class
  * (and clears them).  bench.py uses it for the live roofline measurement; leave it off otherwise. */
 #define M2D_KERNEL_CLASSES 8
-enum { M2D_K_WEIGHTED = 0, M2D_K_MB_WARP = 1, M2D_K_MB_PYRDOWN = 2, M2D_K_MB_SELECT = 3, M2D_K_COLLAPSE = 4, M2D_K_MISC = 5, M2D_K_RESERVED6 = 6, M2D_K_MB_PYRTAIL = 7 };
+enum { M2D_K_WEIGHTED = 0, M2D_K_MB_WARP = 1, M2D_K_MB_PYRDOWN = 2, M2D_K_MB_SELECT = 3, M2D_K_COLLAPSE = 4, M2D_K_MISC = 5, M2D_K_MB_PYRTAIL = 6 };
 int m2d_profile(m2d_handle h, int enable);
 int m2d_get_kernel_times(m2d_handle h, double* ms /* M2D_KERNEL_CLASSES */, uint64_t* count /* M2D_KERNEL_CLASSES */);
 

@@ -2,8 +2,9 @@
 //
 // Execution model: frames are fused in GROUPS of up to K frames.  All per-frame stages of a group
 // (warp, pyramid) run as single launches over (work, frame); the order-dependent stage (select) is
-// TILE-CENTRIC: one work item per touched tile, looping over the group's frames in feed order, so every map tile
-// is read and written once per group and the result equals K sequential feed() calls.
+// TILE-CENTRIC: one work item per touched tile, looping over the group's frames that cover it (feed order for
+// multi-band, best-first for weighted -- both rules are order-free once the frame index is carried along), so every
+// map tile is read and written once per group and the result equals K sequential feed() calls.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -29,11 +30,11 @@ struct FrameJob {
 // Tile-centric work list of a group.
 struct TileWork {
     uint8_t* state;            // tile state in HBM
-    int first, count;          // entries [first, first+count) in feed order
+    int first, count;          // entries [first, first+count): feed order (multi-band) / best-first (weighted)
     int fresh;                 // tile allocated by this group: no state to read
 };
 struct TileEntry {
-    int frame;                 // index into the group's FrameJob array
+    int frame;                 // index into the group's FrameJob array == feed order inside the group
     short rtx, rty;            // tile position inside that frame's region
 };
 

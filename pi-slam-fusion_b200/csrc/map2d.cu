@@ -60,7 +60,7 @@ struct ProfRec { int kind; cudaEvent_t e0, e1; };
 // (bounds, tile allocation, work lists, H2D copies) while the GPU fuses group g.
 struct GroupCtx {
     cudaEvent_t copied = nullptr;     // host frames of the group have landed in d_raw (copy stream)
-    cudaEvent_t staged = nullptr;     // order-independent stages (pack / warp / pyramid) finished on `stage`
+    cudaEvent_t staged = nullptr;     // order-independent stages (warp / pyramid) finished on `stage`
     cudaEvent_t done = nullptr;       // recorded after the group's last kernel
     cudaStream_t stage = nullptr;     // per-context stream: stages of group g+1 overlap the select of group g
     bool busy = false;
@@ -128,6 +128,7 @@ struct m2d_map {
                   bool on_device, int* result);
     int ensure_weight_images(int w, int h);
     int alloc_tile(uint8_t** out);
+    int reserve_tiles(size_t n);
     int grow(void** p, size_t* cap, size_t need, bool pinned);
     int group_size(int w, int h) const;
     bool owns(int tx, int ty) const;
@@ -257,6 +258,10 @@ int m2d_map::prepare(const double* plane7, const double* cam, int n, const doubl
     table.assign((size_t)w * h, nullptr);
     last_rect[0] = last_rect[1] = last_rect[2] = last_rect[3] = -1;
     valid = true;
+    // Pre-reserve pool slabs for a quarter of the prepared grid (prepare() doubles the pose bbox about its centre,
+    // so ~1/4 of the grid is what the prepare-frames actually cover), capped at 2 GiB; failure here is not fatal.
+    size_t want = std::min<size_t>(((size_t)w * h + 3) / 4, ((size_t)2 << 30) / tile_bytes);
+    if (reserve_tiles(want) != M2D_OK) err.clear();
     return M2D_OK;
 }
 
@@ -294,8 +299,10 @@ int m2d_map::ensure_weight_images(int w, int h) {
     return M2D_OK;
 }
 
-int m2d_map::alloc_tile(uint8_t** out) {
-    if (free_tiles.empty()) {
+// Grow the pool until at least n tiles are free (128 MiB slabs).  Called from prepare() for the prepared grid, so
+// that streaming feed() calls do not hit a cudaMalloc (a multi-millisecond stall) in steady state.
+int m2d_map::reserve_tiles(size_t n) {
+    while (free_tiles.size() < n) {
         size_t per_chunk = std::max<size_t>(16, ((size_t)128 << 20) / tile_bytes);
         void* c = nullptr;
         cudaError_t e = cudaMalloc(&c, per_chunk * tile_bytes);
@@ -306,6 +313,14 @@ int m2d_map::alloc_tile(uint8_t** out) {
         }
         chunks.push_back(c);
         for (size_t i = per_chunk; i-- > 0;) free_tiles.push_back((uint8_t*)c + i * tile_bytes);
+    }
+    return M2D_OK;
+}
+
+int m2d_map::alloc_tile(uint8_t** out) {
+    if (free_tiles.empty()) {
+        int rc = reserve_tiles(1);
+        if (rc != M2D_OK) return rc;
     }
     *out = free_tiles.back();
     free_tiles.pop_back();

@@ -276,7 +276,7 @@ class Map2D:
     def launch_count(self):
         return int(lib().m2d_launch_count(self._h))
 
-    KERNEL_CLASSES = ("weighted_fuse", "mb_warp", "mb_pyrdown", "mb_select", "collapse", "misc", "k6", "mb_pyrtail")
+    KERNEL_CLASSES = ("weighted_fuse", "mb_warp", "mb_pyrdown", "mb_select", "collapse", "misc", "mb_pyrtail", "k7")
 
     def profile(self, enable):
         return self._check(lib().m2d_profile(self._h, int(enable)))
