@@ -218,9 +218,19 @@ __device__ __forceinline__ uint32_t alpha_upper_bound(float ax, float ay, float 
     return (uint32_t)v + 2u;
 }
 
+// FP32 image of region px (x, y) under the inverse homography: only used for conservative culling (error << 1 px).
+__device__ __forceinline__ void proj_f32(const float* __restrict__ m, float x, float y, float& sx, float& sy) {
+    float w = m[6] * x + m[7] * y + m[8];
+    float r = __fdividef(1.f, w);
+    sx = (m[0] * x + m[1] * y + m[2]) * r;
+    sy = (m[3] * x + m[4] * y + m[5]) * r;
+}
+
 __global__ void __launch_bounds__(256) weighted_group_kernel(const __grid_constant__ GroupParams p) {
     const TileWork T = p.tiles[blockIdx.x];
+    const int lane = threadIdx.x & 31;
     int px = (threadIdx.x & 63) * 4, py = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int wpx0 = px & 128;  // a warp covers 128 consecutive px of one tile row
     uint4* sp = reinterpret_cast<uint4*>(T.state + ((size_t)py * kEle + px) * 4);
     uint4 st = T.fresh ? make_uint4(0u, 0u, 0u, 0u) : *sp;
     uint32_t s[4] = {st.x, st.y, st.z, st.w};
@@ -234,52 +244,86 @@ __global__ void __launch_bounds__(256) weighted_group_kernel(const __grid_consta
     const float xc = (float)(p.sw / 2), yc = (float)(p.sh / 2);
     const float inv_dmax = rsqrtf(xc * xc + yc * yc) * 0.9999f;  // smaller => larger (conservative) alpha bound
     const bool cull_by_alpha = p.stats == nullptr;  // the counters follow the sequential semantics: no shortcuts then
-    for (int e = 0; e < T.count; e++) {
-        const TileEntry E = p.entries[T.first + e];
-        const FrameJob& J = p.jobs[E.frame];
-        int X = E.rtx * kEle + px, Y = E.rty * kEle + py;
-        double M[9];
-#pragma unroll
-        for (int i = 0; i < 9; i++) M[i] = J.hinv[i];
-        RowBase rb = row_base(M, X, Y);
-        double x1 = (double)(X & 63);
-        double fx[4], fy[4];
-        px_coord(M, rb, x1, fx[0], fy[0]);
-        px_coord(M, rb, x1 + 3.0, fx[3], fy[3]);
-        // The 4 px lie on a line in the source too: if both ends are off the same side (with a margin far above
-        // the rounding error) every tap of every px is outside the frame -> all four warp to 0.
-        float ax = (float)fx[0], bx = (float)fx[3], ay = (float)fy[0], by = (float)fy[3];
-        bool off = (ax < -1.25f && bx < -1.25f) || (ax > lim_x && bx > lim_x) || (ay < -1.25f && by < -1.25f) || (ay > lim_y && by > lim_y);
-        if (off) continue;
-        if (cull_by_alpha) {
-            uint32_t amin = min(min(s[0] >> 24, s[1] >> 24), min(s[2] >> 24, s[3] >> 24));
-            if (alpha_upper_bound(ax, ay, bx, by, xc, yc, inv_dmax, p.weight_type) < amin) continue;  // cannot win or tie
+
+    for (int c0 = 0; c0 < T.count; c0 += 32) {
+        // ---- warp-level filter: lane i judges entry c0+i for the warp's whole 128-px row segment, in FP32 ----
+        uint32_t ub = 0xFFFFFFFFu;   // alpha upper bound of "my" entry over the segment
+        bool alive = c0 + lane < T.count;
+        if (alive && cull_by_alpha) {
+            const TileEntry E = p.entries[T.first + c0 + lane];
+            const float* m = p.jobs[E.frame].hinvf;
+            float X0 = (float)(E.rtx * kEle + wpx0), Y0 = (float)(E.rty * kEle + py), ax, ay, bx, by;
+            proj_f32(m, X0, Y0, ax, ay);
+            proj_f32(m, X0 + 127.f, Y0, bx, by);
+            // margins: 1.5 px tap reach (see alpha_upper_bound) + 1 px for the FP32 coordinate error
+            bool off = (ax < -2.25f && bx < -2.25f) || (ax > lim_x + 1.f && bx > lim_x + 1.f) || (ay < -2.25f && by < -2.25f) || (ay > lim_y + 1.f && by > lim_y + 1.f);
+            // alpha_upper_bound already allows 1.5 px of tap reach; +2 alpha levels cover the FP32 coordinate error
+            // (~0.01 px; the alpha image changes by 254/dmax per px)
+            ub = alpha_upper_bound(ax, ay, bx, by, xc, yc, inv_dmax, p.weight_type) + 2u;
+            alive = !off;
         }
-        px_coord(M, rb, x1 + 1.0, fx[1], fy[1]);
-        px_coord(M, rb, x1 + 2.0, fx[2], fy[2]);
-        RawSrc R;
-        R.mis = (int)(reinterpret_cast<uintptr_t>(J.raw) & 3);
-        R.words = reinterpret_cast<const uint32_t*>(J.raw - R.mis);
-        R.stride = J.raw_stride; R.alpha = p.alpha; R.sw = p.sw; R.sh = p.sh;
-        bool count_wins = !(T.fresh && e == 0);
+        uint32_t amin = min(min(s[0] >> 24, s[1] >> 24), min(s[2] >> 24, s[3] >> 24));
+        uint32_t wmin = cull_by_alpha ? __reduce_min_sync(0xffffffffu, amin) : 0u;
+        unsigned mask = __ballot_sync(0xffffffffu, alive && ub >= wmin);
+        while (mask) {
+            const int i = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const int e = c0 + i;
+            // ---- exact path for entry e (per thread: 4 px) ----
+            const TileEntry E = p.entries[T.first + e];
+            const FrameJob& J = p.jobs[E.frame];
+            int X = E.rtx * kEle + px, Y = E.rty * kEle + py;
+            double M[9];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            uint32_t alpha;
-            bool tie_wins = who[j] >= 0 && E.frame < who[j];
-            uint32_t d = sample_bgra(R, fx[j], fy[j], s[j] >> 24, tie_wins, alpha);
-            foot += alpha != 0u;
-            if (d) {  // alpha beats the holder's (strict '<', Map2DCPU.cpp:327), or equals it and this frame is earlier
-                s[j] = d;
-                who[j] = E.frame;
-                changed = true;
-                wins += count_wins;
+            for (int k = 0; k < 9; k++) M[k] = J.hinv[k];
+            RowBase rb = row_base(M, X, Y);
+            double x1 = (double)(X & 63);
+            double fx[4], fy[4];
+            px_coord(M, rb, x1, fx[0], fy[0]);
+            px_coord(M, rb, x1 + 3.0, fx[3], fy[3]);
+            // The 4 px lie on a line in the source too: if both ends are off the same side (with a margin far above
+            // the rounding error) every tap of every px is outside the frame -> all four warp to 0.
+            float ax = (float)fx[0], bx = (float)fx[3], ay = (float)fy[0], by = (float)fy[3];
+            bool off = (ax < -1.25f && bx < -1.25f) || (ax > lim_x && bx > lim_x) || (ay < -1.25f && by < -1.25f) || (ay > lim_y && by > lim_y);
+            bool skip = off;
+            if (!skip && cull_by_alpha) {
+                uint32_t a4 = min(min(s[0] >> 24, s[1] >> 24), min(s[2] >> 24, s[3] >> 24));
+                skip = alpha_upper_bound(ax, ay, bx, by, xc, yc, inv_dmax, p.weight_type) < a4;  // cannot win or tie
+            }
+            if (!skip) {
+                px_coord(M, rb, x1 + 1.0, fx[1], fy[1]);
+                px_coord(M, rb, x1 + 2.0, fx[2], fy[2]);
+                RawSrc R;
+                R.mis = (int)(reinterpret_cast<uintptr_t>(J.raw) & 3);
+                R.words = reinterpret_cast<const uint32_t*>(J.raw - R.mis);
+                R.stride = J.raw_stride; R.alpha = p.alpha; R.sw = p.sw; R.sh = p.sh;
+                bool count_wins = !(T.fresh && e == 0);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    uint32_t alpha;
+                    bool tie_wins = who[j] >= 0 && E.frame < who[j];
+                    uint32_t d = sample_bgra(R, fx[j], fy[j], s[j] >> 24, tie_wins, alpha);
+                    foot += alpha != 0u;
+                    if (d) {  // alpha beats the holder's (strict '<', Map2DCPU.cpp:327), or equals it and this frame is earlier
+                        s[j] = d;
+                        who[j] = E.frame;
+                        changed = true;
+                        wins += count_wins;
+                    }
+                }
+            }
+            // the state only improves: re-filter the entries still queued against the new segment minimum
+            if (cull_by_alpha && mask) {
+                amin = min(min(s[0] >> 24, s[1] >> 24), min(s[2] >> 24, s[3] >> 24));
+                wmin = __reduce_min_sync(0xffffffffu, amin);
+                mask &= __ballot_sync(0xffffffffu, ub >= wmin);
             }
         }
     }
     if (changed) *sp = make_uint4(s[0], s[1], s[2], s[3]);
     if (p.stats) {
         unsigned long long f = warp_sum(foot), w = warp_sum(wins);
-        if ((threadIdx.x & 31) == 0) {
+        if (lane == 0) {
             if (f) atomicAdd(p.stats + 16, f);
             if (w) atomicAdd(p.stats + 17, w);
         }

@@ -19,6 +19,7 @@ constexpr int kEle = M2D_ELE_PIXELS;
 // One frame of a group, as the kernels see it.  Lives in a device array (uploaded once per group).
 struct FrameJob {
     double hinv[9];            // region px -> source px (inverse homography, cv::warpPerspective convention)
+    float hinvf[9];            // the same in FP32: conservative culling only, never for sampling
     const uint8_t* raw;        // BGR8 source in HBM, sampled in place (3-byte taps via aligned word loads)
     int raw_stride;
     int nx, ny;                // frame region in tiles

@@ -481,6 +481,7 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
             if (ox1 <= ox0) break;  // this shard owns nothing under the frame: accepted, no work
             FrameJob J{};
             memcpy(J.hinv, fb.hinv, sizeof J.hinv);
+            for (int k = 0; k < 9; k++) J.hinvf[k] = (float)fb.hinv[k];
             J.nx = nx; J.ny = ny;
             // Pyramid window: owned tiles + one tile ring (>= the 94-px level-0 support of the deepest Laplacian
             // tap), clipped to the frame region so the reflect-101 border lands where the reference puts it.
