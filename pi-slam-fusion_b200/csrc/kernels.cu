@@ -361,27 +361,12 @@ __device__ __forceinline__ uint32_t bilinear_rne_bgr(uint32_t v00, uint32_t v01,
     return B | (G << 8) | (R << 16);
 }
 
-__global__ void __launch_bounds__(256) mb_warp_kernel(const __grid_constant__ GroupParams p) {
-    const FrameJob& J = p.jobs[blockIdx.y];
-    const int ww = J.wnx * kEle, wh = J.wny * kEle;
-    const int bpr = J.wnx;  // 256-px blocks per window row
-    int by = blockIdx.x / bpr, bx = blockIdx.x - by * bpr;
-    if (by * 4 >= wh) return;
-    int u = bx * kEle + (threadIdx.x & 63) * 4, v = by * 4 + (threadIdx.x >> 6);
-    int x = u + J.wx * kEle, y = v + J.wy * kEle;  // region coordinates
-    double M[9];
-#pragma unroll
-    for (int i = 0; i < 9; i++) M[i] = J.hinv[i];
+// Warp 4 consecutive region px (x..x+3 on row y; x is a multiple of 4, so they share one 64-px coordinate block).
+__device__ __forceinline__ void mb_sample4(const GroupParams& p, const RawSrc& R, const double* M, int x, int y, uint32_t* g, float* w) {
     RowBase rb = row_base(M, x, y);
     double x1 = (double)(x & 63);
-    const int sw = p.sw, sh = p.sh;
-    RawSrc R;
-    R.mis = (int)(reinterpret_cast<uintptr_t>(J.raw) & 3);
-    R.words = reinterpret_cast<const uint32_t*>(J.raw - R.mis);
-    R.stride = J.raw_stride; R.alpha = nullptr; R.sw = sw; R.sh = sh;
+    const int sw = R.sw, sh = R.sh;
     const float* __restrict__ wimg = p.wimg;
-    uint32_t g[4];
-    float w[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         double fx, fy;
@@ -406,6 +391,26 @@ __global__ void __launch_bounds__(256) mb_warp_kernel(const __grid_constant__ Gr
         // a = X & 31 as X - 32*sx: an IMAD on the FMA pipe instead of a LOP3 on the (saturated) ALU pipe
         g[j] = bilinear_rne_bgr(v00, v01, v10, v11, (uint32_t)(X - 32 * sx), (uint32_t)(Y - 32 * sy));
     }
+}
+
+__global__ void __launch_bounds__(256) mb_warp_kernel(const __grid_constant__ GroupParams p) {
+    const FrameJob& J = p.jobs[blockIdx.y];
+    const int ww = J.wnx * kEle, wh = J.wny * kEle;
+    const int bpr = J.wnx;  // 256-px blocks per window row
+    int by = blockIdx.x / bpr, bx = blockIdx.x - by * bpr;
+    if (by * 4 >= wh) return;
+    int u = bx * kEle + (threadIdx.x & 63) * 4, v = by * 4 + (threadIdx.x >> 6);
+    int x = u + J.wx * kEle, y = v + J.wy * kEle;  // region coordinates
+    double M[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) M[i] = J.hinv[i];
+    RawSrc R;
+    R.mis = (int)(reinterpret_cast<uintptr_t>(J.raw) & 3);
+    R.words = reinterpret_cast<const uint32_t*>(J.raw - R.mis);
+    R.stride = J.raw_stride; R.alpha = nullptr; R.sw = p.sw; R.sh = p.sh;
+    uint32_t g[4];
+    float w[4];
+    mb_sample4(p, R, M, x, y, g, w);
     size_t o = (size_t)v * ww + u;
     *reinterpret_cast<uint4*>(reinterpret_cast<uint32_t*>(p.scratch + J.g_off[0]) + o) = make_uint4(g[0], g[1], g[2], g[3]);
     *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.scratch + J.w_off[0]) + o) = make_float4(w[0], w[1], w[2], w[3]);
@@ -413,6 +418,92 @@ __global__ void __launch_bounds__(256) mb_warp_kernel(const __grid_constant__ Gr
 cudaError_t launch_mb_warp(const GroupParams& p, cudaStream_t stream) {
     dim3 g(p.max_wnx * p.max_wny * (kEle / 4), p.n_frames);
     mb_warp_kernel<<<g, 256, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// multi-band stages 1+2a fused: warp a 128 x 32 px block of level 0 PLUS the halo the first pyrDown needs into shared
+// memory, write the block to the level-0 scratch, and produce its 64 x 16 px of level 1 straight from shared memory.
+// The level-0 scratch (12.6 MB per 720p frame) is then never read back by a pyrDown pass; the price is re-warping
+// the halo (136 x 35 instead of 128 x 32 samples).  Borders: the pyrDown taps are reflected (BORDER_REFLECT_101) in
+// REGION coordinates, which always lands inside the block itself, so px outside the region are never sampled.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kFW = 128, kFH = 32;            // level-0 block
+constexpr int kFSW = kFW + 8, kFSH = kFH + 3;  // shared tile: columns x0-4 .. x0+131 (4-px aligned groups), rows y0-2 .. y0+32
+
+__global__ void __launch_bounds__(256, 5) mb_warp_pyr_kernel(const __grid_constant__ GroupParams p) {
+    __shared__ uint32_t sG[kFSH][kFSW];
+    __shared__ float sW[kFSH][kFSW];
+    const FrameJob& J = p.jobs[blockIdx.y];
+    const int ww = J.wnx * kEle, wh = J.wny * kEle, rw = J.nx * kEle, rh = J.ny * kEle;
+    const int bpr = ww / kFW;
+    int by = blockIdx.x / bpr, bx = blockIdx.x - by * bpr;
+    if (by * kFH >= wh) return;
+    const int x0 = bx * kFW + J.wx * kEle, y0 = by * kFH + J.wy * kEle;  // block origin, region coordinates
+    double M[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) M[i] = J.hinv[i];
+    RawSrc R;
+    R.mis = (int)(reinterpret_cast<uintptr_t>(J.raw) & 3);
+    R.words = reinterpret_cast<const uint32_t*>(J.raw - R.mis);
+    R.stride = J.raw_stride; R.alpha = nullptr; R.sw = p.sw; R.sh = p.sh;
+    uint32_t* G0 = reinterpret_cast<uint32_t*>(p.scratch + J.g_off[0]);
+    float* W0 = reinterpret_cast<float*>(p.scratch + J.w_off[0]);
+    // ---- phase 1: sample the block + halo, 4-px groups
+    constexpr int kGroups = (kFSW / 4) * kFSH;
+    for (int gi = threadIdx.x; gi < kGroups; gi += 256) {
+        int r = gi / (kFSW / 4), c = (gi - r * (kFSW / 4)) * 4;
+        int x = x0 - 4 + c, y = y0 - 2 + r;
+        if (x < 0 || x >= rw || y < 0 || y >= rh) continue;  // outside the region: reflected taps never read it
+        uint32_t g[4];
+        float w[4];
+        mb_sample4(p, R, M, x, y, g, w);
+        *reinterpret_cast<uint4*>(&sG[r][c]) = make_uint4(g[0], g[1], g[2], g[3]);
+        *reinterpret_cast<float4*>(&sW[r][c]) = make_float4(w[0], w[1], w[2], w[3]);
+        if (c >= 4 && c < 4 + kFW && r >= 2 && r < 2 + kFH) {  // the block itself goes to the level-0 scratch
+            size_t o = (size_t)(y - J.wy * kEle) * ww + (x - J.wx * kEle);
+            *reinterpret_cast<uint4*>(G0 + o) = make_uint4(g[0], g[1], g[2], g[3]);
+            *reinterpret_cast<float4*>(W0 + o) = make_float4(w[0], w[1], w[2], w[3]);
+        }
+    }
+    __syncthreads();
+    // ---- phase 2: level 1 of the block from shared memory: thread = 1 output column x 4 output rows
+    const int dww = ww >> 1;
+    uint32_t* G1 = reinterpret_cast<uint32_t*>(p.scratch + J.g_off[1]);
+    float* W1 = reinterpret_cast<float*>(p.scratch + J.w_off[1]);
+    const int ul = threadIdx.x & 63, vl0 = (threadIdx.x >> 6) * 4;
+    const int U = (x0 >> 1) + ul, V0 = (y0 >> 1) + vl0;  // region coordinates at level 1
+    int cs[5];
+#pragma unroll
+    for (int d = 0; d < 5; d++) cs[d] = reflect101_idx(2 * U + d - 2, rw) - (x0 - 4);
+    uint32_t hbr[5], hg[5];  // 5-row sliding window of horizontal sums
+    float hw[5];
+#pragma unroll
+    for (int r = 0; r < 11; r++) {
+        int rr = reflect101_idx(2 * V0 + r - 2, rh) - (y0 - 2);
+        const uint32_t* gr = sG[rr];
+        const float* wr = sW[rr];
+        uint32_t a = gr[cs[0]], b = gr[cs[1]], c = gr[cs[2]], d = gr[cs[3]], e = gr[cs[4]];
+        hbr[r % 5] = (c & kM2) * 6u + ((b & kM2) + (d & kM2)) * 4u + (a & kM2) + (e & kM2);
+        hg[r % 5] = ((c >> 8) & 0xFFu) * 6u + (((b >> 8) & 0xFFu) + ((d >> 8) & 0xFFu)) * 4u + ((a >> 8) & 0xFFu) + ((e >> 8) & 0xFFu);
+        // f32, OpenCV 2.4.9 association: s0*6 + (s-1 + s1)*4 + s-2 + s2, left to right
+        hw[r % 5] = wr[cs[2]] * 6.f + (wr[cs[1]] + wr[cs[3]]) * 4.f + wr[cs[0]] + wr[cs[4]];
+        if (r >= 4 && (r & 1) == 0) {
+            const int k = (r - 4) >> 1, i0 = (r - 4) % 5, i1 = (r - 3) % 5, i2 = (r - 2) % 5, i3 = (r - 1) % 5, i4 = r % 5;
+            uint32_t vbr = hbr[i0] + hbr[i4] + (hbr[i1] + hbr[i3]) * 4u + hbr[i2] * 6u;
+            uint32_t vg = hg[i0] + hg[i4] + (hg[i1] + hg[i3]) * 4u + hg[i2] * 6u;
+            // columns ((r0+r4)+(r2+r2)) + ((r1+r3)+r2)*4, scaled by 1/256 (PyrDownVec_32f of OpenCV 2.4.9)
+            float t0 = (hw[i0] + hw[i4]) + (hw[i2] + hw[i2]);
+            float t1 = (hw[i1] + hw[i3]) + hw[i2];
+            size_t o = (size_t)(V0 + k - ((J.wy * kEle) >> 1)) * dww + (U - ((J.wx * kEle) >> 1));
+            G1[o] = (((vbr + 0x00800080u) >> 8) & kM2) | (((vg + 128u) >> 8) << 8);
+            W1[o] = (t0 + t1 * 4.f) * (1.f / 256.f);
+        }
+    }
+}
+cudaError_t launch_mb_warp_pyr(const GroupParams& p, cudaStream_t stream) {
+    dim3 g(p.max_wnx * p.max_wny * (kEle / kFW) * (kEle / kFH), p.n_frames);
+    mb_warp_pyr_kernel<<<g, 256, 0, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -82,6 +82,7 @@ cudaError_t launch_weight_images(int sw, int sh, int weight_type, uint8_t* alpha
 cudaError_t launch_bounds(const GridGeom& g, int n, const double* d_poses, FrameBounds* d_out, cudaStream_t stream);
 cudaError_t launch_weighted_group(const GroupParams& p, cudaStream_t stream);
 cudaError_t launch_mb_warp(const GroupParams& p, cudaStream_t stream);
+cudaError_t launch_mb_warp_pyr(const GroupParams& p, cudaStream_t stream);  // warp + first pyrDown fused
 cudaError_t launch_mb_pyrdown(const GroupParams& p, int level /* src level */, cudaStream_t stream);
 cudaError_t launch_mb_pyrtail(const GroupParams& p, int l_first, cudaStream_t stream);
 cudaError_t launch_mb_select(const GroupParams& p, const TileLayout& lay, cudaStream_t stream);

@@ -107,7 +107,8 @@ struct m2d_map {
     size_t collapse_cap = 0;
 
     static constexpr int kMaxCtx = 8;
-    int kCtx = 3;                   // group contexts in flight (M2D_CTX env overrides, for tuning)
+    int kCtx = 4;                   // group contexts in flight (M2D_CTX env overrides, for tuning)
+    bool fused_warp_pyr = false;    // M2D_FUSED=1: warp + first pyrDown in one shared-memory kernel (measured 7 % slower, kept for A/B)
     GroupCtx ctx[kMaxCtx];
     int ctx_next = 0;
 
@@ -163,6 +164,7 @@ int m2d_map::init() {
     CU(cudaMalloc(&d_stats, 32 * sizeof(unsigned long long)));
     CU(cudaMemsetAsync(d_stats, 0, 32 * sizeof(unsigned long long), stream));
     if (const char* e = getenv("M2D_CTX")) kCtx = std::max(2, std::min(atoi(e), (int)kMaxCtx));
+    if (const char* e = getenv("M2D_FUSED")) fused_warp_pyr = atoi(e) != 0;
     CU(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < kCtx; i++) {
         CU(cudaEventCreateWithFlags(&ctx[i].done, cudaEventDisableTiming));
@@ -580,9 +582,14 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
         CU(cudaStreamWaitEvent(c.stage, c.staged, 0));
     }
     if (type == M2D_TYPE_MULTIBAND) {
-        LAUNCHKS(M2D_K_MB_WARP, c.stage, launch_mb_warp(p, c.stage));
         // full-grid pyrDown while a level is big enough; the small deep levels go through one tail launch
         int l = 0;
+        if (fused_warp_pyr && levels >= 2) {
+            LAUNCHKS(M2D_K_MB_WARP, c.stage, launch_mb_warp_pyr(p, c.stage));  // level 0 and level 1 in one pass
+            l = 1;
+        } else {
+            LAUNCHKS(M2D_K_MB_WARP, c.stage, launch_mb_warp(p, c.stage));
+        }
         for (; l + 1 < levels && (l < 3 || levels - 1 - l < 2); l++) LAUNCHKS(M2D_K_MB_PYRDOWN, c.stage, launch_mb_pyrdown(p, l, c.stage));
         if (l + 1 < levels) LAUNCHKS(M2D_K_MB_PYRTAIL, c.stage, launch_mb_pyrtail(p, l, c.stage));
         CU(cudaEventRecord(c.staged, c.stage));

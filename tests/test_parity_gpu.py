@@ -303,6 +303,25 @@ def test_tile_shards_on_one_gpu_equal_unsharded(typ, axis, span, count):
         m.close()
 
 
+def test_fused_warp_pyramid_variant_is_bit_exact(monkeypatch):
+    """M2D_FUSED=1 selects the shared-memory kernel that warps a block plus halo and emits level 1 directly (an A/B
+    alternative to the two-pass path).  Same bits, including sharded windows and 8 bands."""
+    import torch
+    monkeypatch.setenv("M2D_FUSED", "1")
+    seq = synth.Sequence(12, 320, 180, seed=23, jitter=True, noise=True, fpl=4, prepare_frames=4)
+    dev = torch.from_numpy(seq.frames()).cuda()
+    for kw in ({}, {"band_number": 8}, {"band_number": 1}, {"shard_rank": 1, "shard_count": 2, "shard_axis": 0, "shard_span": 1}):
+        g = m2d.Map2D.create(3, thread=False, batch_frames=5, **kw)
+        o = O.OracleMap2D.create(3, **kw)
+        assert g.prepare(seq.plane, seq.camera, seq.prepare_poses) and o.prepare(seq.plane, seq.camera, seq.prepare_poses)
+        res = g.feed_batch(dev.data_ptr(), seq.n, seq.w * seq.h * 3, seq.w, seq.h, seq.w * 3, seq.poses, True)
+        for k in range(seq.n):
+            assert (res[k] == 0) == o.feed(seq.frame(k), seq.poses[k])
+        g.sync()
+        compare_state(g, o, 3)
+        g.close()
+
+
 def test_ties_keep_reference_order():
     """Exact weight ties: the same frame fed twice.  Weighted keeps the first ('<'), multi-band takes the last
     ('>=') -- observable through the win counters; state must stay identical to the oracle either way."""
