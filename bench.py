@@ -113,9 +113,10 @@ def stage_bytes(mode, stats, levels):
         return out
     D = [stats["region_px"][l] for l in range(levels)]
     out["mb_warp"] = 3 * stats["input_px"] + 10 * D[0]
-    nfull = min(3, levels - 1)  # levels handled by full-grid pyrDown launches; the rest by the tail kernel
-    out["mb_pyrdown"] = sum(10 * D[l] + 10 * D[l + 1] for l in range(nfull))
-    out["mb_pyrtail"] = sum(10 * D[l] + 10 * D[l + 1] for l in range(nfull, levels - 1))
+    # pyrDown bytes are reported for both pyramid kernel classes together under "mb_pyrdown" (which levels go to the
+    # tail kernel depends on the frame size); the tiny tail gets the deepest level's share
+    out["mb_pyrdown"] = sum(10 * D[l] + 10 * D[l + 1] for l in range(levels - 2))
+    out["mb_pyrtail"] = sum(10 * D[l] + 10 * D[l + 1] for l in range(max(levels - 2, 0), levels - 1))
     sel = 0.0
     for l in range(levels):
         nonfresh = stats["region_px"][l] - stats["fresh_px"][l]
@@ -180,6 +181,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--mode", default="multiband", choices=["multiband", "weighted"])
     ap.add_argument("--frames", type=int, default=NFRAMES)
+    ap.add_argument("--size", default="", help="WxH of the synthetic frames (default 1280x720 = BASELINE configs[1]); e.g. 4000x3000 for cfg3-sized frames")
     ap.add_argument("--ref-frames", type=int, default=24)
     ap.add_argument("--cpu-frames", type=int, default=48)
     ap.add_argument("--batch", type=int, default=0, help="m2d_config.batch_frames (0 = library default)")
@@ -188,6 +190,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    if args.size:
+        global W, H
+        W, H = (int(v) for v in args.size.lower().split("x"))
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -99,8 +99,11 @@ void m2d_destroy(m2d_handle h);
 int m2d_prepare(m2d_handle h, const double plane[7], const double camera[6], int n_frames,
                 const double* poses /* n_frames x 7 */);
 
-/* Map2D::feed — host image (pageable or pinned). stride in bytes. Returns after the frame's work is
- * enqueued on the handle's stream; the host buffer may be reused immediately (it is staged). */
+/* Map2D::feed — host image, stride in bytes. Returns after the frame's work is enqueued.  A PAGEABLE buffer
+ * (cv::Mat, malloc) has been staged by the time the call returns and may be reused immediately, like the
+ * reference's refcounted cv::Mat.  A PINNED buffer (m2d_alloc_host / cudaHostAlloc) is read by DMA
+ * asynchronously: leave it untouched until m2d_sync() (or until m2d_queue_size() shows the frame done).
+ * A handle is not thread-safe: call it from one thread at a time (the reference serialises on its own mutex). */
 int m2d_feed(m2d_handle h, const uint8_t* bgr, int w, int h_px, size_t stride, const double pose_c2w[7]);
 /* Same, the image already lives in device memory (must stay valid until m2d_sync). */
 int m2d_feed_device(m2d_handle h, const uint8_t* d_bgr, int w, int h_px, size_t stride,

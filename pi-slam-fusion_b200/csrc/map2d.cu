@@ -344,8 +344,8 @@ int m2d_map::grow(void** p, size_t* cap, size_t need, bool pinned) {
 int m2d_map::group_size(int w, int h) const {
     if (cfg.batch_frames > 0) return std::min(cfg.batch_frames, 64);
     double mpx = (double)w * h / 1e6;
-    int k = (int)(30.0 / std::max(mpx, 0.25));  // ~30 Mpx of source per group (measured: larger groups amortise better)
-    return std::max(1, std::min(k, 32));
+    int k = (int)(100.0 / std::max(mpx, 0.25));  // ~100 Mpx of source per group (measured: larger groups amortise better)
+    return std::max(1, std::min(k, 64));
 }
 
 int m2d_map::queue_size() {
@@ -590,7 +590,9 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
         } else {
             LAUNCHKS(M2D_K_MB_WARP, c.stage, launch_mb_warp(p, c.stage));
         }
-        for (; l + 1 < levels && (l < 3 || levels - 1 - l < 2); l++) LAUNCHKS(M2D_K_MB_PYRDOWN, c.stage, launch_mb_pyrdown(p, l, c.stage));
+        // (a level goes to the tail only when its output is small: <= 16 K px per frame, i.e. one 1024-thread CTA's worth)
+        auto small_level = [&](int lv) { long long nd = kEle >> (lv + 1); return (long long)max_wnx * nd * max_wny * nd <= 16384; };
+        for (; l + 1 < levels && (!small_level(l) || levels - 1 - l < 2); l++) LAUNCHKS(M2D_K_MB_PYRDOWN, c.stage, launch_mb_pyrdown(p, l, c.stage));
         if (l + 1 < levels) LAUNCHKS(M2D_K_MB_PYRTAIL, c.stage, launch_mb_pyrtail(p, l, c.stage));
         CU(cudaEventRecord(c.staged, c.stage));
         CU(cudaStreamWaitEvent(stream, c.staged, 0));
