@@ -89,6 +89,11 @@ struct m2d_map {
     double min_z = 0, max_z = 0, length_pixel = 0;
     int org_x = 0, org_y = 0;       // absolute tile coordinate of grid slot (0,0); moves under spreadMap
     std::vector<uint8_t*> table;    // tile state pointer per grid slot (w*h), NULL = untouched / not owned
+    // host work-list scratch, reused across groups (no per-group allocation or hashing on the feed path)
+    std::vector<int> slot_work;             // per grid slot: index into the current group's TileWork list ...
+    std::vector<uint32_t> slot_epoch;       // ... valid only when the epoch matches
+    uint32_t group_epoch = 0;
+    std::vector<std::vector<TileEntry>> per_tile_pool;
     int last_rect[4] = {-1, -1, -1, -1};
 
     // tile pool
@@ -131,7 +136,7 @@ struct m2d_map {
     int alloc_tile(uint8_t** out);
     int reserve_tiles(size_t n);
     int grow(void** p, size_t* cap, size_t need, bool pinned);
-    int group_size(int w, int h) const;
+    int group_size(int w, int h, bool on_device) const;
     bool owns(int tx, int ty) const;
     bool tile_bbox(int& x0, int& y0, int& x1, int& y1) const;
     int get_image(uint8_t* out, int* w, int* h, int* channels, int* tmx, int* tmy);
@@ -258,6 +263,8 @@ int m2d_map::prepare(const double* plane7, const double* cam, int n, const doubl
     min_z = mn.z; max_z = mx.z; length_pixel = lp;
     org_x = org_y = 0;
     table.assign((size_t)w * h, nullptr);
+    slot_work.assign((size_t)w * h, -1);
+    slot_epoch.assign((size_t)w * h, 0);
     last_rect[0] = last_rect[1] = last_rect[2] = last_rect[3] = -1;
     valid = true;
     // Pre-reserve pool slabs for a quarter of the prepared grid (prepare() doubles the pose bbox about its centre,
@@ -279,9 +286,14 @@ int m2d_map::spread(double xmin, double ymin, double xmax, double ymax) {
     double nminx = g.min_x + g.ele_size * xminInt, nminy = g.min_y + g.ele_size * yminInt;
     double nmaxx = nminx + nw * g.ele_size, nmaxy = nminy + nh * g.ele_size;
     std::vector<uint8_t*> nt((size_t)nw * nh, nullptr);
+    std::vector<int> nsw((size_t)nw * nh, -1);
+    std::vector<uint32_t> nse((size_t)nw * nh, 0);
     for (int x = 0; x < g.w; x++)
-        for (int y = 0; y < g.h; y++) nt[(size_t)(x - xminInt) + (size_t)(y - yminInt) * nw] = table[(size_t)y * g.w + x];
-    table.swap(nt);
+        for (int y = 0; y < g.h; y++) {
+            size_t o = (size_t)y * g.w + x, n = (size_t)(x - xminInt) + (size_t)(y - yminInt) * nw;
+            nt[n] = table[o]; nsw[n] = slot_work[o]; nse[n] = slot_epoch[o];
+        }
+    table.swap(nt); slot_work.swap(nsw); slot_epoch.swap(nse);
     g.min_x = nminx; g.min_y = nminy; g.max_x = nmaxx; g.max_y = nmaxy;
     g.w = nw; g.h = nh;
     org_x += xminInt; org_y += yminInt;
@@ -341,8 +353,12 @@ int m2d_map::grow(void** p, size_t* cap, size_t need, bool pinned) {
     return M2D_OK;
 }
 
-int m2d_map::group_size(int w, int h) const {
-    if (cfg.batch_frames > 0) return std::min(cfg.batch_frames, 64);
+int m2d_map::group_size(int w, int h, bool on_device) const {
+    if (cfg.batch_frames > 0) return std::min(cfg.batch_frames, 512);
+    // Weighted mode keeps no per-frame scratch, and its best-first culling gets sharper the more frames a group holds:
+    // device-resident batches are fused in groups of 192 frames (larger single launches stop overlapping host preparation) (host batches stay small so that the H2D
+    // staging of one group overlaps the fusion of the previous one).
+    if (type != M2D_TYPE_MULTIBAND && on_device) return 192;
     double mpx = (double)w * h / 1e6;
     int k = (int)(100.0 / std::max(mpx, 0.25));  // ~100 Mpx of source per group (measured: larger groups amortise better)
     return std::max(1, std::min(k, 64));
@@ -395,7 +411,7 @@ int m2d_map::feed_frames(int n, const uint8_t* base, size_t frame_stride, int w,
     if (stride < (size_t)w * 3) return M2D_ERR_ARG;
     CU(cudaSetDevice(cfg.device));
     { int rc = ensure_weight_images(w, h); if (rc != M2D_OK) return rc; }
-    int K = group_size(w, h);
+    int K = group_size(w, h, on_device);
     int worst = M2D_OK;
     for (int i = 0; i < n; i += K) {
         int m = std::min(K, n - i);
@@ -416,9 +432,9 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
 
     std::vector<FrameJob> jobs;
     std::vector<TileWork> tiles;
-    std::vector<std::vector<TileEntry>> per_tile;
+    std::vector<std::vector<TileEntry>>& per_tile = per_tile_pool;  // entry i is live for i < tiles.size()
     std::vector<std::pair<int, int>> tile_abs;  // absolute tile coordinate of every TileWork
-    std::unordered_map<uint8_t*, int> tile_index;
+    if (++group_epoch == 0) { std::fill(slot_epoch.begin(), slot_epoch.end(), 0u); group_epoch = 1; }
     std::vector<int> src_index;  // frame index (within the call) of every accepted job
     std::vector<std::pair<float, float>> job_centre;  // frame footprint centre in ABSOLUTE tile units (ordering heuristic)
     jobs.reserve(n);
@@ -464,15 +480,17 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
                         if (rc != M2D_OK) return rc;
                         is_fresh = true;
                     }
-                    auto it = tile_index.find(slot);
+                    const size_t gi = (size_t)ty * g.w + tx;
                     int ti;
-                    if (it == tile_index.end()) {
+                    if (slot_epoch[gi] != group_epoch) {
                         ti = (int)tiles.size();
-                        tile_index.emplace(slot, ti);
+                        slot_epoch[gi] = group_epoch;
+                        slot_work[gi] = ti;
                         tiles.push_back(TileWork{slot, 0, 0, is_fresh ? 1 : 0});
-                        per_tile.emplace_back();
+                        if (per_tile.size() <= (size_t)ti) per_tile.emplace_back();
+                        per_tile[ti].clear();
                         tile_abs.emplace_back(tx + org_x, ty + org_y);
-                    } else ti = it->second;
+                    } else ti = slot_work[gi];
                     per_tile[ti].push_back(TileEntry{job_idx, (short)(tx - fb.x0), (short)(ty - fb.y0)});
                     for (int l = 0; l < levels; l++) {
                         uint64_t lpx = (uint64_t)(kEle >> l) * (kEle >> l);
@@ -513,7 +531,7 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
 
     // ---- device buffers of this context
     size_t n_entries = 0;
-    for (auto& v : per_tile) n_entries += v.size();
+    for (size_t t = 0; t < tiles.size(); t++) n_entries += per_tile[t].size();
     size_t off_tiles = ((size_t)nj * sizeof(FrameJob) + 255) & ~(size_t)255;
     size_t off_entries = (off_tiles + tiles.size() * sizeof(TileWork) + 255) & ~(size_t)255;
     size_t blob = off_entries + n_entries * sizeof(TileEntry) + 256;
