@@ -542,12 +542,19 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
 
     // ---- frames: host images are staged into HBM on the copy stream (this context's previous group has finished,
     // so d_raw is free; the copy overlaps the OTHER context's kernels); device images are used in place
+    const bool tight = stride == (size_t)w * 3 && frame_stride == npx * 3;  // frames back to back: copy runs, not frames
     for (int j = 0; j < nj; j++) {
         const uint8_t* src = base + (size_t)src_index[j] * frame_stride;
         if (on_device) { jobs[j].raw = src; jobs[j].raw_stride = (int)stride; }
         else {
             uint8_t* dst = c.d_raw + (size_t)j * npx * 3;
-            if (stride == (size_t)w * 3) CU(cudaMemcpyAsync(dst, src, npx * 3, cudaMemcpyHostToDevice, copy_stream));
+            if (tight) {
+                if (j == 0 || src_index[j] != src_index[j - 1] + 1) {  // start of a run of consecutive accepted frames
+                    int e = j;
+                    while (e + 1 < nj && src_index[e + 1] == src_index[e] + 1) e++;
+                    CU(cudaMemcpyAsync(dst, src, (size_t)(e - j + 1) * npx * 3, cudaMemcpyHostToDevice, copy_stream));
+                }
+            } else if (stride == (size_t)w * 3) CU(cudaMemcpyAsync(dst, src, npx * 3, cudaMemcpyHostToDevice, copy_stream));
             else CU(cudaMemcpy2DAsync(dst, (size_t)w * 3, src, stride, (size_t)w * 3, h, cudaMemcpyHostToDevice, copy_stream));
             jobs[j].raw = dst; jobs[j].raw_stride = w * 3;
         }
