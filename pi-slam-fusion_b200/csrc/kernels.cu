@@ -134,7 +134,16 @@ struct RawSrc {
     int stride;              // bytes per row
     const uint8_t* alpha;    // sw*sh alpha plane (Map2DCPU.cpp:236-258)
     int sw, sh;
+    unsigned last_word;      // index of the word holding the frame's last byte: the 3-word fetch never reads past it
 };
+__device__ __forceinline__ RawSrc make_raw_src(const uint8_t* raw, int stride, const uint8_t* alpha, int sw, int sh) {
+    RawSrc R;
+    R.mis = (int)(reinterpret_cast<uintptr_t>(raw) & 3);
+    R.words = reinterpret_cast<const uint32_t*>(raw - R.mis);
+    R.stride = stride; R.alpha = alpha; R.sw = sw; R.sh = sh;
+    R.last_word = (unsigned)((sh - 1) * stride + 3 * sw - 1 + R.mis) >> 2;
+    return R;
+}
 __device__ __forceinline__ uint32_t raw_tap(const RawSrc& R, int sx, int sy) {  // border-safe single tap (rare path)
     if ((unsigned)sx >= (unsigned)R.sw || (unsigned)sy >= (unsigned)R.sh) return 0u;
     const uint8_t* q = reinterpret_cast<const uint8_t*>(R.words) + R.mis + (size_t)sy * R.stride + 3 * sx;
@@ -146,7 +155,9 @@ __device__ __forceinline__ void raw_tap_pair(const RawSrc& R, int sx, int sy, ui
     unsigned o = (unsigned)(sy * R.stride + 3 * sx + R.mis);
     const uint32_t* w = R.words + (o >> 2);
     unsigned sh = (o & 3u) * 8u;
-    uint32_t lo = __ldg(w), mid = __ldg(w + 1), hi = __ldg(w + 2);
+    // the third word is only needed when bytes o+4/o+5 spill into it, and then it lies inside the frame: clamping
+    // its index to the frame's last word therefore never changes a used byte, and never reads past the caller's buffer
+    uint32_t lo = __ldg(w), mid = __ldg(w + 1), hi = __ldg(R.words + min((o >> 2) + 2u, R.last_word));
     uint32_t f0 = __funnelshift_r(lo, mid, sh), f1 = __funnelshift_r(mid, hi, sh);  // bytes o..o+3, o+4..o+7
     const uint8_t* ap = R.alpha + (sy * R.sw + sx);
     v0 = (f0 & 0x00FFFFFFu) | ((uint32_t)__ldg(ap) << 24);
@@ -162,7 +173,7 @@ __device__ __forceinline__ void raw_tap_pair_bgr(const RawSrc& R, int sx, int sy
     unsigned o = (unsigned)(sy * R.stride + 3 * sx + R.mis);
     const uint32_t* w = R.words + (o >> 2);
     unsigned sh = (o & 3u) * 8u;
-    uint32_t lo = __ldg(w), mid = __ldg(w + 1), hi = __ldg(w + 2);
+    uint32_t lo = __ldg(w), mid = __ldg(w + 1), hi = __ldg(R.words + min((o >> 2) + 2u, R.last_word));  // see raw_tap_pair
     uint32_t f0 = __funnelshift_r(lo, mid, sh), f1 = __funnelshift_r(mid, hi, sh);
     v0 = f0 & 0x00FFFFFFu;
     v1 = __byte_perm(f0, f1, 0x4543);   // bytes o+3, o+4, o+5, 0
@@ -293,10 +304,7 @@ __global__ void __launch_bounds__(256) weighted_group_kernel(const __grid_consta
             if (!skip) {
                 px_coord(M, rb, x1 + 1.0, fx[1], fy[1]);
                 px_coord(M, rb, x1 + 2.0, fx[2], fy[2]);
-                RawSrc R;
-                R.mis = (int)(reinterpret_cast<uintptr_t>(J.raw) & 3);
-                R.words = reinterpret_cast<const uint32_t*>(J.raw - R.mis);
-                R.stride = J.raw_stride; R.alpha = p.alpha; R.sw = p.sw; R.sh = p.sh;
+                const RawSrc R = make_raw_src(J.raw, J.raw_stride, p.alpha, p.sw, p.sh);
                 bool count_wins = !(T.fresh && e == 0);
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
@@ -404,10 +412,7 @@ __global__ void __launch_bounds__(256) mb_warp_kernel(const __grid_constant__ Gr
     double M[9];
 #pragma unroll
     for (int i = 0; i < 9; i++) M[i] = J.hinv[i];
-    RawSrc R;
-    R.mis = (int)(reinterpret_cast<uintptr_t>(J.raw) & 3);
-    R.words = reinterpret_cast<const uint32_t*>(J.raw - R.mis);
-    R.stride = J.raw_stride; R.alpha = nullptr; R.sw = p.sw; R.sh = p.sh;
+    const RawSrc R = make_raw_src(J.raw, J.raw_stride, nullptr, p.sw, p.sh);
     uint32_t g[4];
     float w[4];
     mb_sample4(p, R, M, x, y, g, w);
@@ -443,10 +448,7 @@ __global__ void __launch_bounds__(256, 5) mb_warp_pyr_kernel(const __grid_consta
     double M[9];
 #pragma unroll
     for (int i = 0; i < 9; i++) M[i] = J.hinv[i];
-    RawSrc R;
-    R.mis = (int)(reinterpret_cast<uintptr_t>(J.raw) & 3);
-    R.words = reinterpret_cast<const uint32_t*>(J.raw - R.mis);
-    R.stride = J.raw_stride; R.alpha = nullptr; R.sw = p.sw; R.sh = p.sh;
+    const RawSrc R = make_raw_src(J.raw, J.raw_stride, nullptr, p.sw, p.sh);
     uint32_t* G0 = reinterpret_cast<uint32_t*>(p.scratch + J.g_off[0]);
     float* W0 = reinterpret_cast<float*>(p.scratch + J.w_off[0]);
     // ---- phase 1: sample the block + halo, 4-px groups
