@@ -147,6 +147,14 @@ int m2d_tile_count(m2d_handle h);
 int m2d_export_tiles(m2d_handle h, int max_tiles, int* abs_xy, uint8_t* dst, int dst_on_device, int* n_out);
 int m2d_import_tiles(m2d_handle h, int n, const int* abs_xy, const uint8_t* src, int src_on_device);
 
+/* Checkpoint / resume of the mosaic (the reference can only save the final PNG; its SLAM map has
+ * MapHash::save/load, GSLAM-DIYSLAM/src/zhaoyong/MapHash.cpp:376,458).  save_state writes the prepared grid
+ * (camera, plane, extents, origin) and the raw state of every tile held by this handle; load_state restores them
+ * into a handle created with the same type and band number, after which feeding continues exactly as if it had
+ * never been interrupted (bit-identical results).  File format: private, versioned, little-endian. */
+int m2d_save_state(m2d_handle h, const char* filename);
+int m2d_load_state(m2d_handle h, const char* filename);
+
 int m2d_get_stats(m2d_handle h, m2d_stats* out);
 const char* m2d_last_error(m2d_handle h);
 /* Number of CUDA kernels this handle has launched so far (bench.py's gpu_launches). */

@@ -15,7 +15,6 @@
 #include <cstring>
 #include <deque>
 #include <string>
-#include <unordered_map>
 #include <vector>
 
 #include "../../include/map2d_b200.h"
@@ -926,6 +925,76 @@ int m2d_import_tiles(m2d_handle h, int n, const int* abs_xy, const uint8_t* src,
     }
     CU(cudaStreamSynchronize(stream));
     return M2D_OK;
+}
+
+namespace {
+struct StateHeader {
+    char magic[8];            // "M2DSTATE"
+    uint32_t version, type, levels, reserved;
+    uint64_t tile_bytes, n_tiles;
+    GridGeom g;
+    double min_z, max_z, length_pixel;
+    int32_t org_x, org_y;
+};
+}  // namespace
+
+int m2d_save_state(m2d_handle h, const char* filename) {
+    if (!h || !filename) return M2D_ERR_ARG;
+    m2d_map& m = *h;
+    if (!m.valid) return M2D_ERR_STATE;
+    int n = (int)m.tiles_in_use;
+    std::vector<int> xy((size_t)std::max(n, 1) * 2);
+    std::vector<uint8_t> buf((size_t)std::max(n, 1) * m.tile_bytes);
+    int got = 0;
+    int rc = m2d_export_tiles(h, n, xy.data(), buf.data(), 0, &got);
+    if (rc != M2D_OK) return rc;
+    StateHeader hd{};
+    memcpy(hd.magic, "M2DSTATE", 8);
+    hd.version = 1; hd.type = (uint32_t)m.type; hd.levels = (uint32_t)m.levels;
+    hd.tile_bytes = m.tile_bytes; hd.n_tiles = (uint64_t)got;
+    hd.g = m.g; hd.min_z = m.min_z; hd.max_z = m.max_z; hd.length_pixel = m.length_pixel;
+    hd.org_x = m.org_x; hd.org_y = m.org_y;
+    FILE* f = fopen(filename, "wb");
+    if (!f) { m.err = std::string("cannot open ") + filename; return M2D_ERR_IO; }
+    bool ok = fwrite(&hd, sizeof hd, 1, f) == 1 && (got == 0 || fwrite(xy.data(), sizeof(int) * 2, got, f) == (size_t)got) &&
+              (got == 0 || fwrite(buf.data(), m.tile_bytes, got, f) == (size_t)got);
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) { m.err = std::string("short write to ") + filename; return M2D_ERR_IO; }
+    return M2D_OK;
+}
+
+int m2d_load_state(m2d_handle h, const char* filename) {
+    if (!h || !filename) return M2D_ERR_ARG;
+    m2d_map& m = *h;
+    std::string& err = m.err;
+    FILE* f = fopen(filename, "rb");
+    if (!f) { err = std::string("cannot open ") + filename; return M2D_ERR_IO; }
+    StateHeader hd{};
+    if (fread(&hd, sizeof hd, 1, f) != 1 || memcmp(hd.magic, "M2DSTATE", 8) != 0 || hd.version != 1) {
+        fclose(f); err = "not a map2d_b200 state file"; return M2D_ERR_IO;
+    }
+    if ((int)hd.type != m.type || (int)hd.levels != m.levels || hd.tile_bytes != m.tile_bytes) {
+        fclose(f); err = "state file was written by a handle of another type / band number"; return M2D_ERR_ARG;
+    }
+    if (hd.g.w <= 0 || hd.g.h <= 0 || (long long)hd.g.w * hd.g.h > (1ll << 26) || hd.n_tiles > (uint64_t)hd.g.w * hd.g.h) {
+        fclose(f); err = "corrupt state header"; return M2D_ERR_IO;
+    }
+    std::vector<int> xy((size_t)std::max<uint64_t>(hd.n_tiles, 1) * 2);
+    std::vector<uint8_t> buf((size_t)std::max<uint64_t>(hd.n_tiles, 1) * m.tile_bytes);
+    bool ok = (hd.n_tiles == 0 || fread(xy.data(), sizeof(int) * 2, hd.n_tiles, f) == hd.n_tiles) &&
+              (hd.n_tiles == 0 || fread(buf.data(), m.tile_bytes, hd.n_tiles, f) == hd.n_tiles);
+    fclose(f);
+    if (!ok) { err = "truncated state file"; return M2D_ERR_IO; }
+    CU(cudaSetDevice(m.cfg.device));
+    if (m.valid) { int rc = m.reset(); if (rc != M2D_OK) return rc; }
+    m.g = hd.g; m.min_z = hd.min_z; m.max_z = hd.max_z; m.length_pixel = hd.length_pixel;
+    m.org_x = hd.org_x; m.org_y = hd.org_y;
+    m.table.assign((size_t)hd.g.w * hd.g.h, nullptr);
+    m.slot_work.assign((size_t)hd.g.w * hd.g.h, -1);
+    m.slot_epoch.assign((size_t)hd.g.w * hd.g.h, 0);
+    m.last_rect[0] = m.last_rect[1] = m.last_rect[2] = m.last_rect[3] = -1;
+    m.valid = true;
+    return m2d_import_tiles(h, (int)hd.n_tiles, xy.data(), buf.data(), 0);
 }
 
 int m2d_get_stats(m2d_handle h, m2d_stats* out) {

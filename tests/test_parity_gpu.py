@@ -372,6 +372,33 @@ def test_idempotence_and_order_property():
     g.close()
 
 
+@pytest.mark.parametrize("typ", [1, 3])
+def test_checkpoint_resume_is_transparent(tmp_path, typ):
+    """Feed half the survey, m2d_save_state, restore into a NEW handle, feed the rest: every tile must equal the
+    uninterrupted oracle run (the grid after spreadMap, the tile origin and all pyramid levels are part of the state)."""
+    seq = synth.Sequence(14, 320, 180, seed=29, jitter=True, fpl=4, prepare_frames=2, cross=1.2, along=0.8)
+    o = O.OracleMap2D.create(typ)
+    a = m2d.Map2D.create(typ, thread=False)
+    assert o.prepare(seq.plane, seq.camera, seq.prepare_poses) and a.prepare(seq.plane, seq.camera, seq.prepare_poses)
+    for k in range(7):
+        assert o.feed(seq.frame(k), seq.poses[k]) and a.feed(seq.frame(k), seq.poses[k])
+    path = str(tmp_path / "state.m2d")
+    assert a.save_state(path)
+    a.close()
+    b = m2d.Map2D.create(typ, thread=False)
+    assert b.load_state(path)                       # no prepare(): the grid comes from the file
+    assert b.grid()["w"] == o.grid()["w"] and np.array_equal(b.grid()["min"], o.grid()["min"])
+    for k in range(7, seq.n):
+        assert o.feed(seq.frame(k), seq.poses[k]) and b.feed(seq.frame(k), seq.poses[k])
+    b.sync()
+    compare_state(b, o, typ)
+    other = m2d.Map2D.create(4 - typ, thread=False)  # wrong type must be refused loudly
+    with pytest.raises(RuntimeError):
+        other.load_state(path)
+    other.close()
+    b.close()
+
+
 def test_save_png_roundtrip(tmp_path):
     cv2 = pytest.importorskip("cv2")
     seq = synth.Sequence(4, 320, 180, seed=1, fpl=2, prepare_frames=4)
