@@ -12,7 +12,8 @@
  *   Map2D::feed(img,pose)                    -> m2d_feed           (Map2D.h:91,  Map2DCPU.cpp:127-148)
  *   Map2D::save(filename)                    -> m2d_save           (Map2D.h:95,  Map2DCPU.cpp:523-564)
  *   Map2D::queueSize()                       -> m2d_queue_size     (Map2D.h:97)
- *   Map2D::draw()                            -> no-op (GL display is out of scope; use getImage())
+ *   Map2D::draw()                            -> no-op (GL is out of scope); its data path is m2d_poll_changed +
+ *                                               m2d_get_tile_image: changed tiles and their blended textures
  */
 #ifndef MAP2D_B200_ADAPTER_H
 #define MAP2D_B200_ADAPTER_H

@@ -147,6 +147,15 @@ int m2d_tile_count(m2d_handle h);
 int m2d_export_tiles(m2d_handle h, int max_tiles, int* abs_xy, uint8_t* dst, int dst_on_device, int* n_out);
 int m2d_import_tiles(m2d_handle h, int n, const int* abs_xy, const uint8_t* src, int src_on_device);
 
+/* Display path without GL (Map2D::draw, Map2D.h:93): the reference marks tiles `Ischanged` in renderFrame and, on the GL
+ * thread, re-blends each changed tile into a texture (MultiBandMap2DCPU.cpp:702-742 -> Ele::updateTexture -> Ele::blend
+ * :77-188: with HighQualityShow and all 8 neighbours present, a border of 1<<(levels-1-i) px per level is borrowed from
+ * them before the restore; weighted mode uploads the BGRA tile as is, Map2DCPU.cpp:497-505).
+ * m2d_poll_changed lists (and clears) the tiles touched since the last poll, in current grid coordinates;
+ * m2d_get_tile_image returns one tile exactly as the reference would texture it: 256x256 BGR (multi-band) or BGRA. */
+int m2d_poll_changed(m2d_handle h, int max_tiles, int* xy /* 2 ints per tile */, int* n_out);
+int m2d_get_tile_image(m2d_handle h, int tx, int ty, int high_quality, uint8_t* out, int* channels);
+
 /* Checkpoint / resume of the mosaic (the reference can only save the final PNG; its SLAM map has
  * MapHash::save/load, GSLAM-DIYSLAM/src/zhaoyong/MapHash.cpp:376,458).  save_state writes the prepared grid
  * (camera, plane, extents, origin) and the raw state of every tile held by this handle; load_state restores them

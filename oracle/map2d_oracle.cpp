@@ -898,6 +898,63 @@ int orc_import_tiles(orc_map* o, int n, const int* abs_xy, const uint8_t* src, i
     }
     return M2D_OK;
 }
+// Display-time per-tile collapse — MultiBandMap2DCPUEle::blend + updateTexture (MultiBandMap2DCPU.cpp:77-188) as driven
+// by draw() (:702-742): with HighQualityShow and all 9 neighbours present, every level is extended by a border of
+// 1 << (levels-1-i) px taken from the neighbours, restored, and the centre 256x256 is cropped; otherwise the tile is
+// restored alone.  Pixels with weights[0]==0 are zeroed, then 16S -> 8U.  Weighted mode shows the BGRA tile itself
+// (Map2DCPU.cpp:497-505).
+int orc_get_tile_image(orc_map* o, int tx, int ty, int high_quality, uint8_t* out, int* channels) {
+    Map& m = o->m;
+    if (!m.valid || tx < 0 || ty < 0 || tx >= m.w || ty >= m.h) return M2D_ERR_ARG;
+    const auto& e = m.data[(size_t)ty * m.w + tx];
+    if (!e) return M2D_REJECTED;
+    const int E = M2D_ELE_PIXELS;
+    if (m.type != M2D_TYPE_MULTIBAND) {
+        if (e->bgra.empty()) return M2D_REJECTED;
+        *channels = 4;
+        memcpy(out, e->bgra.data(), e->bgra.size());
+        return M2D_OK;
+    }
+    if (e->lap.empty()) return M2D_REJECTED;
+    *channels = 3;
+    const int L = m.band_num, levels = L + 1;
+    bool all9 = high_quality != 0;
+    const Tile* nb[9];
+    for (int yi = ty - 1, k = 0; yi <= ty + 1; yi++)
+        for (int xi = tx - 1; xi <= tx + 1; xi++, k++) {
+            const Tile* t = (yi < 0 || yi >= m.h || xi < 0 || xi >= m.w) ? nullptr : m.data[(size_t)yi * m.w + xi].get();
+            if (!t || t->lap.empty()) all9 = false;
+            nb[k] = t;
+        }
+    std::vector<Img16> pyr(levels);
+    int b0 = 0;
+    for (int i = 0; i < levels; i++) {
+        int n = E >> i, b = all9 ? (1 << (levels - i - 1)) : 0, d = n + 2 * b;
+        if (i == 0) b0 = b;
+        pyr[i].rows = pyr[i].cols = d;
+        pyr[i].d.assign((size_t)d * d * 3, 0);
+        for (int y = 0; y < 3; y++)
+            for (int x = 0; x < 3; x++) {
+                if (!all9 && !(x == 1 && y == 1)) continue;
+                const Tile* t = all9 ? nb[3 * y + x] : e.get();
+                int sw_ = (x == 1) ? n : b, sh_ = (y == 1) ? n : b;
+                int sx = (x == 0) ? (n - b) : 0, sy = (y == 0) ? (n - b) : 0;
+                int dx = (x == 0) ? 0 : ((x == 1) ? b : (d - b)), dy = (y == 0) ? 0 : ((y == 1) ? b : (d - b));
+                for (int r = 0; r < sh_; r++)
+                    memcpy(&pyr[i].d[((size_t)(dy + r) * d + dx) * 3], &t->lap[i][((size_t)(sy + r) * n + sx) * 3], (size_t)sw_ * 3 * sizeof(int16_t));
+            }
+    }
+    restore_from_laplace_pyr(pyr);
+    const int d0 = pyr[0].cols;
+    for (int y = 0; y < E; y++)
+        for (int x = 0; x < E; x++) {
+            const int16_t* s = &pyr[0].d[((size_t)(y + b0) * d0 + (x + b0)) * 3];
+            uint8_t* q = out + ((size_t)y * E + x) * 3;
+            if (e->wgt[0][(size_t)y * E + x] == 0) { q[0] = q[1] = q[2] = 0; continue; }
+            q[0] = sat_u8(s[0]); q[1] = sat_u8(s[1]); q[2] = sat_u8(s[2]);
+        }
+    return M2D_OK;
+}
 int orc_get_stats(orc_map* o, m2d_stats* out) { *out = o->m.stats; return M2D_OK; }
 
 // Bounds only, against the current grid, without spreadMap (what m2d_compute_bounds returns).

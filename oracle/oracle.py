@@ -73,6 +73,7 @@ def lib():
         L.orc_last_rect.argtypes = [vp, ip]
         L.orc_get_tile.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp]
         L.orc_get_image.argtypes = [vp, vp, ip, ip, ip, ip, ip]
+        L.orc_get_tile_image.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, ip]
         L.orc_get_stats.argtypes = [vp, C.POINTER(Stats)]
         L.orc_tile_bytes.argtypes = [vp]
         L.orc_tile_bytes.restype = C.c_size_t
@@ -253,6 +254,12 @@ class OracleMap2D:
         out = np.zeros((256, 256, 4), np.uint8)
         rc = lib().orc_get_tile(self._h, tx, ty, 0, out.ctypes.data, None)
         return None if rc else out
+
+    def get_tile_image(self, tx, ty, high_quality=True):
+        out = np.zeros(256 * 256 * 4, np.uint8)
+        cn = C.c_int()
+        rc = lib().orc_get_tile_image(self._h, tx, ty, int(high_quality), out.ctypes.data, C.byref(cn))
+        return None if rc else out[:256 * 256 * cn.value].reshape(256, 256, cn.value).copy()
 
     def get_image(self):
         w, h, cn, tx, ty = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()

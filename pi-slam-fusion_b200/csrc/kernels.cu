@@ -931,6 +931,42 @@ cudaError_t launch_mosaic_paste(const PasteItem* d_items, int n_items, const Til
     mosaic_paste_kernel<<<g, 256, 0, stream>>>(d_items, lay, ms);
     return cudaGetLastError();
 }
+// Display-time collapse of ONE tile (MultiBandMap2DCPUEle::blend, MultiBandMap2DCPU.cpp:77-146): paste sub-rectangles of
+// the tile and its 8 neighbours into a bordered per-level pyramid, then the usual restore chain, then crop + mask.
+__global__ void __launch_bounds__(256) sub_paste_kernel(const SubPaste* __restrict__ items, const __grid_constant__ TileLayout lay,
+                                                        const __grid_constant__ MosaicSet ms) {
+    const SubPaste it = items[blockIdx.x];
+    int i = blockIdx.y * 256 + threadIdx.x;
+    if (i >= it.w * it.h) return;
+    int y = i / it.w, x = i - y * it.w;
+    const int n = kEle >> it.level;
+    const int16_t* tl = reinterpret_cast<const int16_t*>(it.tile + lay.lap_off[it.level]);
+    size_t s = (size_t)(it.sy + y) * n + (it.sx + x), plane = (size_t)n * n;
+    const MosaicLevel& m = ms.lv[it.level];
+    size_t o = (size_t)(it.dy + y) * m.w + (it.dx + x);
+    m.g[0][o] = tl[s]; m.g[1][o] = tl[plane + s]; m.g[2][o] = tl[2 * plane + s];
+}
+cudaError_t launch_sub_paste(const SubPaste* d_items, int n_items, const TileLayout& lay, const MosaicSet& ms, cudaStream_t stream) {
+    if (n_items == 0) return cudaSuccess;
+    dim3 g(n_items, kEle * kEle / 256);
+    sub_paste_kernel<<<g, 256, 0, stream>>>(d_items, lay, ms);
+    return cudaGetLastError();
+}
+__global__ void tile_crop_kernel(MosaicLevel m0, int border, const float* __restrict__ w0, uint8_t* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= kEle * kEle) return;
+    int y = i / kEle, x = i - y * kEle;
+    size_t o = (size_t)(y + border) * m0.w + (x + border);
+    bool keep = w0[i] != 0.f;  // result.setTo(0, weights[0]==0), then convertTo(CV_8UC3)
+    out[3 * i] = keep ? (uint8_t)min(max((int)m0.g[0][o], 0), 255) : 0;
+    out[3 * i + 1] = keep ? (uint8_t)min(max((int)m0.g[1][o], 0), 255) : 0;
+    out[3 * i + 2] = keep ? (uint8_t)min(max((int)m0.g[2][o], 0), 255) : 0;
+}
+cudaError_t launch_tile_crop(MosaicLevel m0, int border, const float* w0, uint8_t* out, cudaStream_t stream) {
+    tile_crop_kernel<<<kEle * kEle / 256, 256, 0, stream>>>(m0, border, w0, out);
+    return cudaGetLastError();
+}
+
 // fine += pyrUp(coarse), saturating int16 (restoreImageFromLaplacePyr)
 __global__ void __launch_bounds__(256) mosaic_upadd_kernel(MosaicLevel C, MosaicLevel F) {
     int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;

@@ -72,6 +72,10 @@ struct MosaicSet {
     MosaicLevel lv[M2D_MAX_LEVELS];
     float* w0;                 // level-0 weight mosaic (background mask)
 };
+struct SubPaste {               // a rectangle of one level of one tile -> a position in the bordered tile pyramid
+    const uint8_t* tile;
+    int level, sx, sy, w, h, dx, dy;
+};
 struct PasteItem {
     const uint8_t* tile;
     int tx, ty;                // tile position inside the mosaic
@@ -89,6 +93,8 @@ cudaError_t launch_mb_select(const GroupParams& p, const TileLayout& lay, cudaSt
 cudaError_t launch_tile_copy(uint8_t* const* d_tiles, int n, uint8_t* buf, size_t tile_bytes, int to_buf, cudaStream_t stream);
 cudaError_t launch_bgra_paste(const PasteItem* d_items, int n_items, uint32_t* mosaic, int mosaic_w, cudaStream_t stream);
 cudaError_t launch_mosaic_paste(const PasteItem* d_items, int n_items, const TileLayout& lay, const MosaicSet& ms, cudaStream_t stream);
+cudaError_t launch_sub_paste(const SubPaste* d_items, int n_items, const TileLayout& lay, const MosaicSet& ms, cudaStream_t stream);
+cudaError_t launch_tile_crop(MosaicLevel m0, int border, const float* w0, uint8_t* out, cudaStream_t stream);
 cudaError_t launch_mosaic_upadd(MosaicLevel coarse, MosaicLevel fine, cudaStream_t stream);
 cudaError_t launch_mosaic_final(MosaicLevel m0, const float* w0, int background, uint8_t* out_bgr, cudaStream_t stream);
 

@@ -89,6 +89,7 @@ struct m2d_map {
     int org_x = 0, org_y = 0;       // absolute tile coordinate of grid slot (0,0); moves under spreadMap
     std::vector<uint8_t*> table;    // tile state pointer per grid slot (w*h), NULL = untouched / not owned
     // host work-list scratch, reused across groups (no per-group allocation or hashing on the feed path)
+    std::vector<uint8_t> changed;           // per grid slot: the reference's Ele::Ischanged (set by feed, cleared by poll)
     std::vector<int> slot_work;             // per grid slot: index into the current group's TileWork list ...
     std::vector<uint32_t> slot_epoch;       // ... valid only when the epoch matches
     uint32_t group_epoch = 0;
@@ -264,6 +265,7 @@ int m2d_map::prepare(const double* plane7, const double* cam, int n, const doubl
     table.assign((size_t)w * h, nullptr);
     slot_work.assign((size_t)w * h, -1);
     slot_epoch.assign((size_t)w * h, 0);
+    changed.assign((size_t)w * h, 0);
     last_rect[0] = last_rect[1] = last_rect[2] = last_rect[3] = -1;
     valid = true;
     // Pre-reserve pool slabs for a quarter of the prepared grid (prepare() doubles the pose bbox about its centre,
@@ -287,12 +289,13 @@ int m2d_map::spread(double xmin, double ymin, double xmax, double ymax) {
     std::vector<uint8_t*> nt((size_t)nw * nh, nullptr);
     std::vector<int> nsw((size_t)nw * nh, -1);
     std::vector<uint32_t> nse((size_t)nw * nh, 0);
+    std::vector<uint8_t> nch((size_t)nw * nh, 0);
     for (int x = 0; x < g.w; x++)
         for (int y = 0; y < g.h; y++) {
             size_t o = (size_t)y * g.w + x, n = (size_t)(x - xminInt) + (size_t)(y - yminInt) * nw;
-            nt[n] = table[o]; nsw[n] = slot_work[o]; nse[n] = slot_epoch[o];
+            nt[n] = table[o]; nsw[n] = slot_work[o]; nse[n] = slot_epoch[o]; nch[n] = changed[o];
         }
-    table.swap(nt); slot_work.swap(nsw); slot_epoch.swap(nse);
+    table.swap(nt); slot_work.swap(nsw); slot_epoch.swap(nse); changed.swap(nch);
     g.min_x = nminx; g.min_y = nminy; g.max_x = nmaxx; g.max_y = nmaxy;
     g.w = nw; g.h = nh;
     org_x += xminInt; org_y += yminInt;
@@ -387,6 +390,7 @@ int m2d_map::reset() {
     for (int i = 0; i < kCtx; i++) ctx[i].busy = false;
     for (uint8_t*& t : table)
         if (t) { free_tiles.push_back(t); t = nullptr; tiles_in_use--; }
+    std::fill(changed.begin(), changed.end(), 0);
     CU(cudaMemsetAsync(d_stats, 0, 32 * sizeof(unsigned long long), stream));
     memset(&stats, 0, sizeof stats);
     last_rect[0] = last_rect[1] = last_rect[2] = last_rect[3] = -1;
@@ -480,6 +484,7 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
                         is_fresh = true;
                     }
                     const size_t gi = (size_t)ty * g.w + tx;
+                    changed[gi] = 1;  // ele->Ischanged = true (Map2DCPU.cpp:330)
                     int ti;
                     if (slot_epoch[gi] != group_epoch) {
                         ti = (int)tiles.size();
@@ -927,6 +932,88 @@ int m2d_import_tiles(m2d_handle h, int n, const int* abs_xy, const uint8_t* src,
     return M2D_OK;
 }
 
+int m2d_poll_changed(m2d_handle h, int max_tiles, int* xy, int* n_out) {
+    if (!h || !xy || !n_out || max_tiles < 0) return M2D_ERR_ARG;
+    m2d_map& m = *h;
+    if (!m.valid) return M2D_ERR_STATE;
+    int n = 0;
+    for (int y = 0; y < m.g.h && n < max_tiles; y++)
+        for (int x = 0; x < m.g.w && n < max_tiles; x++) {
+            size_t gi = (size_t)y * m.g.w + x;
+            if (m.changed[gi] && m.table[gi]) { xy[2 * n] = x; xy[2 * n + 1] = y; n++; m.changed[gi] = 0; }
+        }
+    *n_out = n;
+    return M2D_OK;
+}
+
+int m2d_get_tile_image(m2d_handle h, int tx, int ty, int high_quality, uint8_t* out, int* channels) {
+    if (!h || !out || !channels) return M2D_ERR_ARG;
+    m2d_map& m = *h;
+    std::string& err = m.err;
+    uint64_t& launches = m.launches;
+    bool& profiling = m.profiling;
+    std::vector<ProfRec>& prof = m.prof;
+    cudaStream_t stream = m.stream;
+    if (!m.valid || tx < 0 || ty < 0 || tx >= m.g.w || ty >= m.g.h) return M2D_ERR_ARG;
+    const uint8_t* t = m.table[(size_t)ty * m.g.w + tx];
+    if (!t) return M2D_REJECTED;
+    CU(cudaSetDevice(m.cfg.device));
+    if (m.type != M2D_TYPE_MULTIBAND) {
+        *channels = 4;
+        CU(cudaMemcpyAsync(out, t, (size_t)kEle * kEle * 4, cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+        return M2D_OK;
+    }
+    *channels = 3;
+    const int levels = m.levels;
+    const uint8_t* nb[9];
+    bool all9 = high_quality != 0;
+    for (int yi = ty - 1, k = 0; yi <= ty + 1; yi++)
+        for (int xi = tx - 1; xi <= tx + 1; xi++, k++) {
+            nb[k] = (yi < 0 || yi >= m.g.h || xi < 0 || xi >= m.g.w) ? nullptr : m.table[(size_t)yi * m.g.w + xi];
+            if (!nb[k]) all9 = false;
+        }
+    MosaicSet ms{};
+    std::vector<SubPaste> items;
+    size_t off = 0, offs[M2D_MAX_LEVELS][3];
+    int b0 = 0;
+    for (int i = 0; i < levels; i++) {
+        int n = kEle >> i, b = all9 ? (1 << (levels - i - 1)) : 0, d = n + 2 * b;
+        if (i == 0) b0 = b;
+        ms.lv[i].w = ms.lv[i].h = d;
+        for (int c = 0; c < 3; c++) { offs[i][c] = off; off += ((size_t)d * d * sizeof(int16_t) + 255) & ~(size_t)255; }
+        for (int y = 0; y < 3; y++)
+            for (int x = 0; x < 3; x++) {
+                if (!all9 && !(x == 1 && y == 1)) continue;
+                SubPaste sp;
+                sp.tile = all9 ? nb[3 * y + x] : t;
+                sp.level = i;
+                sp.w = (x == 1) ? n : b; sp.h = (y == 1) ? n : b;
+                sp.sx = (x == 0) ? (n - b) : 0; sp.sy = (y == 0) ? (n - b) : 0;
+                sp.dx = (x == 0) ? 0 : ((x == 1) ? b : (d - b)); sp.dy = (y == 0) ? 0 : ((y == 1) ? b : (d - b));
+                if (sp.w > 0 && sp.h > 0) items.push_back(sp);
+            }
+    }
+    size_t zero_bytes = off;
+    size_t off_out = off; off += (size_t)kEle * kEle * 3 + 256;
+    size_t off_items = (off + 255) & ~(size_t)255; off = off_items + items.size() * sizeof(SubPaste) + 256;
+    CU(cudaStreamSynchronize(stream));
+    { int rc = m.grow((void**)&m.d_collapse, &m.collapse_cap, off, false); if (rc != M2D_OK) return rc; }
+    for (int i = 0; i < levels; i++)
+        for (int c = 0; c < 3; c++) ms.lv[i].g[c] = reinterpret_cast<int16_t*>(m.d_collapse + offs[i][c]);
+    ms.w0 = nullptr;
+    SubPaste* d_items = reinterpret_cast<SubPaste*>(m.d_collapse + off_items);
+    uint8_t* d_out = m.d_collapse + off_out;
+    CU(cudaMemsetAsync(m.d_collapse, 0, zero_bytes, stream));
+    CU(cudaMemcpyAsync(d_items, items.data(), items.size() * sizeof(SubPaste), cudaMemcpyHostToDevice, stream));
+    LAUNCHK(M2D_K_COLLAPSE, launch_sub_paste(d_items, (int)items.size(), m.lay, ms, stream));
+    for (int l = levels - 1; l > 0; l--) LAUNCHK(M2D_K_COLLAPSE, launch_mosaic_upadd(ms.lv[l], ms.lv[l - 1], stream));
+    LAUNCHK(M2D_K_COLLAPSE, launch_tile_crop(ms.lv[0], b0, reinterpret_cast<const float*>(t + m.lay.wgt_off[0]), d_out, stream));
+    CU(cudaMemcpyAsync(out, d_out, (size_t)kEle * kEle * 3, cudaMemcpyDeviceToHost, stream));
+    CU(cudaStreamSynchronize(stream));
+    return M2D_OK;
+}
+
 namespace {
 struct StateHeader {
     char magic[8];            // "M2DSTATE"
@@ -992,6 +1079,7 @@ int m2d_load_state(m2d_handle h, const char* filename) {
     m.table.assign((size_t)hd.g.w * hd.g.h, nullptr);
     m.slot_work.assign((size_t)hd.g.w * hd.g.h, -1);
     m.slot_epoch.assign((size_t)hd.g.w * hd.g.h, 0);
+    m.changed.assign((size_t)hd.g.w * hd.g.h, 1);
     m.last_rect[0] = m.last_rect[1] = m.last_rect[2] = m.last_rect[3] = -1;
     m.valid = true;
     return m2d_import_tiles(h, (int)hd.n_tiles, xy.data(), buf.data(), 0);

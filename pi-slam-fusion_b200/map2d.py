@@ -45,7 +45,7 @@ class Stats(C.Structure):
 EXPORTS = ["m2d_config_default", "m2d_create", "m2d_destroy", "m2d_prepare", "m2d_feed", "m2d_feed_device",
            "m2d_feed_batch", "m2d_sync", "m2d_queue_size", "m2d_set_stream", "m2d_reset", "m2d_get_grid",
            "m2d_last_rect", "m2d_get_tile", "m2d_get_image", "m2d_save", "m2d_tile_bytes", "m2d_tile_count",
-           "m2d_export_tiles", "m2d_import_tiles", "m2d_save_state", "m2d_load_state", "m2d_get_stats", "m2d_last_error",
+           "m2d_export_tiles", "m2d_import_tiles", "m2d_poll_changed", "m2d_get_tile_image", "m2d_save_state", "m2d_load_state", "m2d_get_stats", "m2d_last_error",
            "m2d_launch_count", "m2d_profile", "m2d_get_kernel_times", "m2d_alloc_host", "m2d_free_host", "m2d_compute_bounds"]
 
 _lib = None
@@ -84,6 +84,8 @@ def lib():
     L.m2d_tile_count.argtypes = [vp]
     L.m2d_export_tiles.argtypes = [vp, C.c_int, ip, vp, C.c_int, ip]
     L.m2d_import_tiles.argtypes = [vp, C.c_int, ip, vp, C.c_int]
+    L.m2d_poll_changed.argtypes = [vp, C.c_int, ip, ip]
+    L.m2d_get_tile_image.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, ip]
     L.m2d_save_state.argtypes = [vp, C.c_char_p]
     L.m2d_load_state.argtypes = [vp, C.c_char_p]
     L.m2d_get_stats.argtypes = [vp, C.POINTER(Stats)]
@@ -269,6 +271,23 @@ class Map2D:
     def import_tiles(self, xy, src_ptr, on_device):
         xy = np.ascontiguousarray(xy, np.int32).reshape(-1, 2)
         return self._check(lib().m2d_import_tiles(self._h, len(xy), xy.ctypes.data_as(C.POINTER(C.c_int)), src_ptr, int(on_device)))
+
+    # --- display path without GL: changed tiles and their textures (Map2D::draw) ------------------------------
+    def poll_changed(self, max_tiles=65536):
+        """Tiles touched since the last poll (the reference's Ele::Ischanged), as (tx, ty) grid coordinates."""
+        xy = np.zeros((max_tiles, 2), np.int32)
+        n = C.c_int()
+        self._check(lib().m2d_poll_changed(self._h, max_tiles, xy.ctypes.data_as(C.POINTER(C.c_int)), C.byref(n)))
+        return [tuple(int(v) for v in r) for r in xy[:n.value]]
+
+    def get_tile_image(self, tx, ty, high_quality=True):
+        """One tile as the reference would texture it (Ele::blend with neighbour borders when high_quality)."""
+        out = np.zeros(256 * 256 * 4, np.uint8)
+        cn = C.c_int()
+        rc = lib().m2d_get_tile_image(self._h, tx, ty, int(high_quality), out.ctypes.data, C.byref(cn))
+        if not self._check(rc):
+            return None
+        return out[:256 * 256 * cn.value].reshape(256, 256, cn.value).copy()
 
     # --- checkpoint / resume ----------------------------------------------------------------------------
     def save_state(self, filename):

@@ -399,6 +399,42 @@ def test_checkpoint_resume_is_transparent(tmp_path, typ):
     b.close()
 
 
+@pytest.mark.parametrize("typ", [1, 3])
+def test_display_tiles_match_reference_blend(typ):
+    """Map2D::draw without GL: changed-tile polling (Ele::Ischanged) and per-tile textures.  Multi-band tiles with all 8
+    neighbours present are collapsed with the borrowed borders of Ele::blend (MultiBandMap2DCPU.cpp:77-146), the others
+    alone; both must equal the oracle's restatement byte for byte."""
+    seq = synth.Sequence(5, 1024, 768, seed=7, jitter=True, fpl=3, prepare_frames=5)
+    g = m2d.Map2D.create(typ, thread=False)
+    o = O.OracleMap2D.create(typ)
+    assert g.prepare(seq.plane, seq.camera, seq.prepare_poses) and o.prepare(seq.plane, seq.camera, seq.prepare_poses)
+    assert g.poll_changed() == []
+    for k in range(3):
+        assert g.feed(seq.frame(k), seq.poses[k]) and o.feed(seq.frame(k), seq.poses[k])
+    first = g.poll_changed()
+    assert len(first) == g.tile_count() and g.poll_changed() == []   # flags are cleared by the poll
+    for k in range(3, seq.n):
+        assert g.feed(seq.frame(k), seq.poses[k]) and o.feed(seq.frame(k), seq.poses[k])
+    x0, y0, x1, y1 = g.last_rect()
+    again = g.poll_changed()
+    assert (x0, y0) in again and len(again) >= (x1 - x0) * (y1 - y0)
+    gr = o.grid()
+    hq_differs = 0
+    for ty in range(gr["h"]):
+        for tx in range(gr["w"]):
+            for hq in (True, False):
+                a, b = o.get_tile_image(tx, ty, hq), g.get_tile_image(tx, ty, hq)
+                assert (a is None) == (b is None)
+                if a is not None:
+                    assert np.array_equal(a, b), "tile (%d,%d) hq=%s: %d bytes differ" % (tx, ty, hq, int((a != b).sum()))
+            a, b = g.get_tile_image(tx, ty, True), g.get_tile_image(tx, ty, False)
+            if a is not None and not np.array_equal(a, b):
+                hq_differs += 1
+    if typ == 3:
+        assert hq_differs >= 4, "the survey must contain interior tiles (all 8 neighbours present)"
+    g.close()
+
+
 def test_save_png_roundtrip(tmp_path):
     cv2 = pytest.importorskip("cv2")
     seq = synth.Sequence(4, 320, 180, seed=1, fpl=2, prepare_frames=4)
