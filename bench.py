@@ -187,6 +187,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="m2d_config.batch_frames (0 = library default)")
     ap.add_argument("--stream-latency", type=int, default=0,
                     help="also measure synchronous per-frame feed() latency (BASELINE cfg5: 1920x1080, pose jitter, H2D included) over N frames")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N>1 only. weak: N x the survey, --frames per GPU, strips of tiles, halo frames by P2P; strong: the same --frames cut into N shards")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -114,6 +114,19 @@ int m2d_feed_device(m2d_handle h, const uint8_t* d_bgr, int w, int h_px, size_t 
 int m2d_feed_batch(m2d_handle h, int n, const uint8_t* base, size_t frame_stride, int w, int h_px,
                    size_t stride, const double* poses /* n x 7 */, int on_device, int* result);
 
+/* Sharded runs: the frames a shard does NOT need pixels for.  Applies exactly what feed() does to
+ * the grid for each pose (bounds, reject test, spreadMap — Map2DCPU.cpp:163-233) and nothing else, so that every
+ * shard takes the same grid decisions as an unsharded run while frame pixels travel only to the shards that own
+ * tiles under them.  A pose whose footprint touches a tile this shard owns is an error (M2D_ERR_ARG, grid already
+ * grown, no tile touched): the caller's delivery plan was wrong.  result[i] as for m2d_feed_batch (may be NULL). */
+int m2d_feed_poses(m2d_handle h, int n, const double* poses /* n x 7 */, int* result);
+
+/* Re-partition the tile ownership of a handle that holds no tiles yet (after m2d_prepare or m2d_reset; else
+ * M2D_ERR_STATE).  Same rule as m2d_config.shard_*, with strip 0 starting at absolute tile coordinate `origin`:
+ * owner = floor((abs - origin) / span) mod count.  Lets the host align contiguous strips with the surveyed area,
+ * which is only known once prepare() has fixed the grid. */
+int m2d_set_shard(m2d_handle h, int rank, int count, int axis, int span, int origin);
+
 int m2d_sync(m2d_handle h);
 int m2d_queue_size(m2d_handle h);                 /* frames enqueued and not yet finished on the GPU */
 int m2d_set_stream(m2d_handle h, void* cuda_stream /* cudaStream_t, NULL = library-owned */);

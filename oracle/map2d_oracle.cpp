@@ -442,10 +442,12 @@ struct Map {
     int last_rect[4] = {-1, -1, -1, -1};
     m2d_stats stats{};
     int org_x = 0, org_y = 0;  // absolute tile coordinate of slot (0,0): test stand-in for the sharded CUDA library
+    bool pose_only_violation = false;
+    int shard_origin = 0;
 
     bool owns(int tx, int ty) const {  // same rule as include/map2d_b200.h m2d_config.shard_*
         if (cfg.shard_count <= 1) return true;
-        int a = (cfg.shard_axis == 0) ? tx + org_x : ty + org_y;
+        int a = ((cfg.shard_axis == 0) ? tx + org_x : ty + org_y) - shard_origin;
         int span = cfg.shard_span > 0 ? cfg.shard_span : 1;
         int q = (a >= 0) ? a / span : -((-a + span - 1) / span);
         int r = q % cfg.shard_count;
@@ -583,6 +585,12 @@ bool Map::feed(const uint8_t* bgr, int fw, int fh, size_t stride, const double* 
     if (!get_perspective_transform(srcp, dstp, M)) return false;
     if (!invert3x3(M, Mi)) return false;  // warpPerspective inverts the forward map itself
     last_rect[0] = xminInt; last_rect[1] = yminInt; last_rect[2] = xmaxInt; last_rect[3] = ymaxInt;
+    if (!bgr) {  // pose-only feed of a sharded run (m2d_feed_poses): grid decisions only
+        for (int y = yminInt; y < ymaxInt; y++)
+            for (int x = xminInt; x < xmaxInt; x++)
+                if (owns(x, y)) pose_only_violation = true;
+        return true;
+    }
     stats.frames_fused++;
     stats.input_px += (uint64_t)fw * fh;
     if (type == M2D_TYPE_MULTIBAND) return render_multiband(bgr, stride, Mi, xminInt, yminInt, xmaxInt, ymaxInt);
@@ -772,6 +780,24 @@ int orc_prepare(orc_map* o, const double* plane, const double* cam, int n, const
 }
 int orc_feed(orc_map* o, const uint8_t* bgr, int w, int h, size_t stride, const double* pose) {
     return o->m.feed(bgr, w, h, stride, pose) ? M2D_OK : M2D_REJECTED;
+}
+int orc_set_shard(orc_map* o, int rank, int count, int axis, int span, int origin) {  // stand-in for m2d_set_shard
+    if (count < 1 || rank < 0 || rank >= count || (axis != 0 && axis != 1) || span < 1) return M2D_ERR_ARG;
+    for (const auto& e : o->m.data) if (e) return M2D_ERR_STATE;
+    o->m.cfg.shard_rank = rank; o->m.cfg.shard_count = count; o->m.cfg.shard_axis = axis; o->m.cfg.shard_span = span;
+    o->m.shard_origin = origin;
+    return M2D_OK;
+}
+int orc_feed_poses(orc_map* o, int n, const double* poses, int* result) {  // stand-in for m2d_feed_poses
+    int violations = 0;
+    for (int i = 0; i < n; i++) {
+        o->m.pose_only_violation = false;
+        bool ok = o->m.feed(nullptr, (int)o->m.cam_w, (int)o->m.cam_h, 0, poses + 7 * (size_t)i);
+        int st = !ok ? M2D_REJECTED : o->m.pose_only_violation ? M2D_ERR_ARG : M2D_OK;
+        violations += st == M2D_ERR_ARG;
+        if (result) result[i] = st;
+    }
+    return violations ? M2D_ERR_ARG : M2D_OK;
 }
 int orc_get_grid(orc_map* o, int* w, int* h, double* mn, double* mx, double* lp) {
     if (!o->m.valid) return M2D_ERR_STATE;

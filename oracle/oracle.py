@@ -69,6 +69,8 @@ def lib():
         L.orc_destroy.restype = None
         L.orc_prepare.argtypes = [vp, dp, dp, C.c_int, dp]
         L.orc_feed.argtypes = [vp, vp, C.c_int, C.c_int, C.c_size_t, dp]
+        L.orc_feed_poses.argtypes = [vp, C.c_int, dp, C.POINTER(C.c_int)]
+        L.orc_set_shard.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.orc_get_grid.argtypes = [vp, ip, ip, dp, dp, dp]
         L.orc_last_rect.argtypes = [vp, ip]
         L.orc_get_tile.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp]
@@ -287,6 +289,17 @@ class OracleMap2D:
     def import_tiles(self, xy, src_ptr, on_device=False):
         xy = np.ascontiguousarray(xy, np.int32).reshape(-1, 2)
         return lib().orc_import_tiles(self._h, len(xy), xy.ctypes.data_as(C.POINTER(C.c_int)), src_ptr, 0) == 0
+
+    def set_shard(self, rank, count, axis, span, origin=0):
+        return lib().orc_set_shard(self._h, rank, count, axis, span, origin) == 0
+
+    def feed_poses(self, poses):
+        poses = np.ascontiguousarray(poses, np.float64).reshape(-1, 7)
+        res = np.zeros(len(poses), np.int32)
+        rc = lib().orc_feed_poses(self._h, len(poses), _dptr(poses), res.ctypes.data_as(C.POINTER(C.c_int)))
+        if rc < 0:
+            raise RuntimeError("feed_poses: a pose touches tiles this shard owns")
+        return res
 
     def feed_batch(self, base_ptr, n, frame_stride, w, h, stride, poses, on_device=False):
         poses = np.ascontiguousarray(poses, np.float64).reshape(-1, 7)

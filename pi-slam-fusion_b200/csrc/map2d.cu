@@ -87,6 +87,7 @@ struct m2d_map {
     GridGeom g{};
     double min_z = 0, max_z = 0, length_pixel = 0;
     int org_x = 0, org_y = 0;       // absolute tile coordinate of grid slot (0,0); moves under spreadMap
+    int shard_origin = 0;           // absolute tile coordinate at which strip 0 starts (m2d_set_shard)
     std::vector<uint8_t*> table;    // tile state pointer per grid slot (w*h), NULL = untouched / not owned
     // host work-list scratch, reused across groups (no per-group allocation or hashing on the feed path)
     std::vector<uint8_t> changed;           // per grid slot: the reference's Ele::Ischanged (set by feed, cleared by poll)
@@ -149,7 +150,7 @@ static inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b -
 
 bool m2d_map::owns(int tx, int ty) const {
     if (cfg.shard_count <= 1) return true;
-    int a = (cfg.shard_axis == 0) ? tx + org_x : ty + org_y;
+    int a = ((cfg.shard_axis == 0) ? tx + org_x : ty + org_y) - shard_origin;
     int span = cfg.shard_span > 0 ? cfg.shard_span : 1;
     int s = floordiv(a, span) % cfg.shard_count;
     if (s < 0) s += cfg.shard_count;
@@ -778,6 +779,50 @@ int m2d_feed_batch(m2d_handle h, int n, const uint8_t* base, size_t frame_stride
     if (!base || !poses) return M2D_ERR_ARG;
     int rc = h->feed_frames(n, base, frame_stride, w, hpx, stride, poses, on_device != 0, result);
     return rc < 0 ? rc : M2D_OK;
+}
+
+int m2d_feed_poses(m2d_handle h, int n, const double* poses, int* result) {
+    if (!h || n < 0) return M2D_ERR_ARG;
+    if (n == 0) return M2D_OK;
+    if (!poses) return M2D_ERR_ARG;
+    m2d_map& m = *h;
+    int violations = 0;
+    for (int i = 0; i < n; i++) {
+        m.stats.frames_fed++;
+        int status = M2D_REJECTED;
+        do {
+            if (!m.valid) break;
+            FrameBounds fb;
+            const double* pose = poses + 7 * (size_t)i;
+            frame_bounds(m.g, pose, &fb);
+            if (!fb.ok) break;
+            if (fb.gx0 < m.g.min_x || fb.gx1 > m.g.max_x || fb.gy0 < m.g.min_y || fb.gy1 > m.g.max_y) {
+                if (m.spread(fb.gx0, fb.gy0, fb.gx1, fb.gy1) != M2D_OK) break;
+                frame_bounds(m.g, pose, &fb);
+                if (!fb.ok) break;
+            }
+            if (fb.x0 < 0 || fb.y0 < 0 || fb.x1 > m.g.w || fb.y1 > m.g.h || fb.x0 >= fb.x1 || fb.y0 >= fb.y1) break;
+            memcpy(m.last_rect, &fb.x0, sizeof(int) * 4);
+            status = M2D_OK;
+            for (int ty = fb.y0; ty < fb.y1 && status == M2D_OK; ty++)
+                for (int tx = fb.x0; tx < fb.x1; tx++)
+                    if (m.owns(tx, ty)) { status = M2D_ERR_ARG; violations++; break; }
+        } while (0);
+        if (result) result[i] = status;
+    }
+    if (violations) {
+        m.err = "m2d_feed_poses: " + std::to_string(violations) + " pose(s) touch tiles this shard owns; their pixels are required";
+        return M2D_ERR_ARG;
+    }
+    return M2D_OK;
+}
+
+int m2d_set_shard(m2d_handle h, int rank, int count, int axis, int span, int origin) {
+    if (!h || count < 1 || rank < 0 || rank >= count || (axis != 0 && axis != 1) || span < 1) return M2D_ERR_ARG;
+    if (h->tiles_in_use != 0) { h->err = "m2d_set_shard: the map already holds tiles"; return M2D_ERR_STATE; }
+    h->cfg.shard_rank = rank; h->cfg.shard_count = count; h->cfg.shard_axis = axis; h->cfg.shard_span = span;
+    h->shard_origin = origin;
+    return M2D_OK;
 }
 
 int m2d_sync(m2d_handle h) { return h ? h->sync() : M2D_ERR_ARG; }

@@ -30,6 +30,78 @@ def default_shard(w, h, world, poses=None, camera=None):
     return {"shard_axis": axis, "shard_span": max(2, int(np.ceil(ext[axis] / world)))}
 
 
+def strip_owner(a, span, world, origin=0):
+    """Owner of absolute tile coordinate `a` along the shard axis (the rule of m2d_config.shard_* / m2d_set_shard)."""
+    return int(np.floor((a - origin) / float(span))) % world
+
+
+class DeliveryPlan:
+    """Which frame pixels travel where when frames originate on the GPUs that captured them ("deliver
+    frame + H + tile rect to owners ... P2P of just what maps into each owner's tiles").
+
+    rects     [n,4] int: x0,y0,x1,y1 tile rect of every frame in ABSOLUTE tile coordinates (-1 = rejected), as returned
+              by compute_bounds() right after prepare();
+    resident  per rank, the half-open range [lo,hi) of feed-order frame indices whose pixels start out on that rank.
+    A rank needs the pixels of every frame whose rect (grown by `margin` tiles: the rect is recomputed by feed() after
+    spreadMap and may move by one tile on a knife edge) contains a tile it owns; it is handed the contiguous hull
+    [a,b) of those frames (a serpentine survey cut into strips makes the needed frames contiguous; a hull that covers
+    a few unneeded frames costs only their transfer — feeding a frame under which a shard owns nothing is a no-op).
+    Frames outside the hull are fed as poses only (m2d_feed_poses), so every rank grows its grid like an unsharded run.
+    """
+
+    def __init__(self, rects, axis, span, world, resident, origin=0, margin=1):
+        rects = np.asarray(rects, np.int64).reshape(-1, 4)
+        self.n, self.world = len(rects), world
+        self.resident = [tuple(r) for r in resident]
+        assert len(self.resident) == world
+        need = [[] for _ in range(world)]
+        for k, (x0, y0, x1, y1) in enumerate(rects):
+            if x1 <= x0 or y1 <= y0:      # rejected frame: nobody needs its pixels
+                continue
+            lo, hi = (x0, x1) if axis == 0 else (y0, y1)
+            if hi - lo + 2 * margin >= span * world:
+                owners = range(world)
+            else:
+                owners = {strip_owner(a, span, world, origin) for a in range(lo - margin, hi + margin)}
+            for r in owners:
+                need[r].append(k)
+        self.needed = [np.array(v, np.int64) for v in need]
+        self.hull = [(int(v[0]), int(v[-1]) + 1) if len(v) else (0, 0) for v in self.needed]
+        # buffer of rank r = hull U resident range (its own frames live inside the buffer: no copy in the timed region)
+        self.buffer = []
+        for r in range(world):
+            (a, b), (lo, hi) = self.hull[r], self.resident[r]
+            if a == b:
+                self.buffer.append((lo, hi))
+            elif lo == hi:
+                self.buffer.append((a, b))
+            else:
+                self.buffer.append((min(a, lo), max(b, hi)))
+        # transfers (src, dst, lo, hi): the part of dst's hull that is resident on src
+        self.transfers = []
+        for d in range(world):
+            a, b = self.hull[d]
+            for s_ in range(world):
+                if s_ == d:
+                    continue
+                lo, hi = max(a, self.resident[s_][0]), min(b, self.resident[s_][1])
+                if lo < hi:
+                    self.transfers.append((s_, d, lo, hi))
+        covered = [sum(min(b, hi) - max(a, lo) for (lo, hi) in [self.resident[r]] + [(t[2], t[3]) for t in self.transfers if t[1] == r]
+                       if min(b, hi) > max(a, lo)) for r, (a, b) in enumerate(self.hull)]
+        for r, (a, b) in enumerate(self.hull):
+            assert covered[r] == b - a, "resident ranges must partition the sequence"
+
+    def frames_moved(self):
+        return sum(hi - lo for (_, _, lo, hi) in self.transfers)
+
+
+def even_split(n, world):
+    """Contiguous, near-equal feed-order ranges: frames stay on the GPU whose flight lines produced them."""
+    cuts = [(n * r) // world for r in range(world + 1)]
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
 class ShardedMap2D:
     def __init__(self, factory, type_, rank, world, device=None, **cfg):
         self.rank, self.world, self.type = rank, world, type_
@@ -143,6 +215,63 @@ class ShardedMap2D:
         self.map.sync()
         return res
 
+    # ---- frames originate where they were captured; only halo frames move (weak scaling over survey area) ----
+    def align_strips(self, poses, axis=None):
+        """After prepare(): cut the tile range the survey will touch into `world` contiguous strips (one per rank)
+        and install them with set_shard.  Every rank computes the same cut from the same poses.  Returns
+        (rects, axis, span, origin) for DeliveryPlan."""
+        rects, _ = self.map.compute_bounds(poses)
+        rects = np.asarray(rects, np.int64).reshape(-1, 4)
+        ok = rects[rects[:, 2] > rects[:, 0]]
+        if len(ok) == 0:
+            raise ValueError("no frame of the sequence is accepted")
+        ext = [(int(ok[:, 0].min()), int(ok[:, 2].max())), (int(ok[:, 1].min()), int(ok[:, 3].max()))]
+        if axis is None:
+            axis = 0 if ext[0][1] - ext[0][0] >= ext[1][1] - ext[1][0] else 1
+        # one spare tile at either end, so that DeliveryPlan's knife-edge margin never wraps round to the far rank
+        lo, hi = ext[axis][0] - 1, ext[axis][1] + 1
+        span = max(1, -(-(hi - lo) // self.world))
+        self.map.set_shard(self.rank, self.world, axis, span, lo)
+        return rects, axis, span, lo
+
+    def alloc_owned_buffer(self, plan, w, h):
+        """uint8 [frames of plan.buffer[rank], h, w, 3] on this rank's device, and the view of it that holds the
+        rank's resident frames (to be filled by the caller before the timed region)."""
+        dev = torch.device("cuda", self.device) if self.cuda else torch.device("cpu")
+        b0, b1 = plan.buffer[self.rank]
+        buf = torch.empty((max(b1 - b0, 1), h, w, 3), dtype=torch.uint8, device=dev)
+        lo, hi = plan.resident[self.rank]
+        return buf, buf[lo - b0:hi - b0]
+
+    def feed_all_owned(self, plan, buf, poses, w, h):
+        """One pass over the whole sequence: halo frames by P2P from the ranks they are resident on (one batched
+        isend/irecv group), then feed in global order: poses only outside this rank's hull, pixels inside."""
+        poses = np.ascontiguousarray(poses, np.float64).reshape(-1, 7)
+        n = len(poses)
+        assert n == plan.n
+        b0, _ = plan.buffer[self.rank]
+        ops = []
+        for (src, dst, lo, hi) in plan.transfers:
+            if src == self.rank:
+                ops.append(dist.P2POp(dist.isend, buf[lo - b0:hi - b0], dst))
+            elif dst == self.rank:
+                ops.append(dist.P2POp(dist.irecv, buf[lo - b0:hi - b0], src))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+            if self.cuda:
+                torch.cuda.current_stream().synchronize()  # the library consumes buf on its own stream
+        a, b = plan.hull[self.rank]
+        res = np.zeros(n, np.int32)
+        if a > 0:
+            res[:a] = self.map.feed_poses(poses[:a])
+        if b > a:
+            res[a:b] = self.map.feed_batch(buf[a - b0:].data_ptr(), b - a, w * h * 3, w, h, w * 3, poses[a:b], self.cuda)
+        if b < n:
+            res[b:] = self.map.feed_poses(poses[b:])
+        self.map.sync()
+        return res
+
     def gather_to_root(self):
         """Raw owned tiles -> rank 0 (which imports them).  Returns the number of tiles received by the root."""
         tb = self.map.tile_bytes()
@@ -184,7 +313,149 @@ class ShardedMap2D:
 
 
 def bench_main(args, rank, world, local_rank):
-    """bench.py --gpus N (N>1), launched by torchrun: strong scaling of the BASELINE workload over N tile shards."""
+    """bench.py --gpus N (N>1), launched by torchrun.  Default: weak scaling over survey area (bench_weak);
+    --scaling strong keeps the BASELINE workload fixed and cuts it into N tile shards (bench_strong)."""
+    if getattr(args, "scaling", "weak") == "strong":
+        return bench_strong(args, rank, world, local_rank)
+    return bench_weak(args, rank, world, local_rank)
+
+
+def bench_weak(args, rank, world, local_rank):
+    """N x the BASELINE survey (same flight-line length, N x the lines), cut into N strips of tiles.  Every rank holds
+    the frames of its own flight lines in HBM (args.frames each); per step the halo frames cross NVLink by P2P
+    (inside the timed region), every rank sees every pose and fuses the tiles it owns.  The final tile gather is
+    timed separately (it is the sharded half of save(), which the 1-GPU `value` does not contain either)."""
+    import json
+    import pi_slam_fusion_b200.map2d as m2d
+    import pi_slam_fusion_b200.synth as synth
+    import bench as B
+
+    saved_stdout = os.dup(1)   # NCCL prints its banner to stdout; the contract is ONE JSON line there
+    os.dup2(2, 1)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if args.size:   # `bench` imported here is a second copy of the module bench.py runs as __main__
+        B.W, B.H = (int(v) for v in args.size.lower().split("x"))
+    W, H = B.W, B.H
+    mode = args.mode
+    typ = 3 if mode == "multiband" else 1
+    per_gpu = args.frames
+    n = per_gpu * world
+    fpl = synth.frames_per_line(per_gpu, W, H)
+    seq = synth.Sequence(n, W, H, seed=B.SEED, fpl=fpl)
+    dev = torch.device("cuda", local_rank)
+    sm = ShardedMap2D(lambda t, **kw: m2d.Map2D.create(t, thread=False, **kw), typ, rank, world, device=local_rank,
+                      shard_axis=0, shard_span=4, batch_frames=args.batch)
+    assert sm.prepare(seq.plane, seq.camera, seq.prepare_poses)
+    rects, axis, span, origin = sm.align_strips(seq.poses)
+    plan = DeliveryPlan(rects, axis, span, world, even_split(n, world), origin)
+    buf, mine = sm.alloc_owned_buffer(plan, W, H)
+    lo, hi = plan.resident[rank]
+    host_t = torch.empty((hi - lo, H, W, 3), dtype=torch.uint8, pin_memory=True)
+    host = host_t.numpy()
+    for k in range(lo, hi):
+        host[k - lo] = seq.frame(k)
+    mine.copy_(host_t)            # inputs resident in HBM before the timed region, on the GPU that "captured" them
+    torch.cuda.synchronize()
+
+    def step():
+        sm.map.reset()
+        return sm.feed_all_owned(plan, buf, seq.poses, W, H)
+
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        res = step()
+    sampler = B.ClockSampler(local_rank)
+    sampler.start()
+    l0 = sm.map.launch_count()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = step()           # ends with m2d_sync: the library's streams have drained
+    ev1.record()
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms = max(ev0.elapsed_time(ev1) / args.steps, wall_ms)
+    launches = float(sm.map.launch_count() - l0) / args.steps
+    clocks = sampler.result()
+
+    # final tile gather + mosaic on the root, timed on its own (one repetition)
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    sm.gather_to_root()
+    torch.cuda.synchronize()
+    gather_ms = (time.perf_counter() - t0) * 1e3
+
+    # e2e: host buffers -> H2D of the rank's own frames, halo exchange, fuse, tile gather, mosaic D2H on the root
+    e2e_ms = out_bytes = None
+    if not args.no_e2e:
+        out_pinned = None
+        if rank == 0:
+            img, _ = sm.map.get_image()
+            out_bytes = img.nbytes
+            del img
+            out_pinned = torch.empty(out_bytes, dtype=torch.uint8, pin_memory=True).numpy()
+
+        def step_e2e():
+            sm.map.reset()
+            mine.copy_(host_t, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            sm.feed_all_owned(plan, buf, seq.poses, W, H)
+            sm.gather_to_root()
+            if rank == 0:
+                sm.map.get_image(out=out_pinned)
+
+        step_e2e()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        reps = 2
+        for _ in range(reps):
+            step_e2e()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / reps
+
+    t = torch.tensor([ms, gather_ms, e2e_ms or 0.0, launches], device=dev, dtype=torch.float64)
+    tmax = t.clone()
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    hull = torch.tensor([plan.hull[rank][1] - plan.hull[rank][0]], device=dev, dtype=torch.float64)
+    dist.all_reduce(hull, op=dist.ReduceOp.MAX)
+    fused = int((res == 0).sum())
+    if rank == 0:
+        ms_step = float(tmax[0])
+        px = fused * W * H
+        e2e = None
+        if e2e_ms is not None:
+            e2e = {"value": px / (float(tmax[2]) * 1e-3) / 1e6, "unit": B.UNIT, "h2d_bytes_per_step": n * W * H * 3,
+                   "d2h_bytes_per_step": out_bytes, "ms_per_step": float(tmax[2]),
+                   "what": "per rank: H2D of its own pinned host frames, halo exchange, m2d_feed_batch; then tile gather to rank 0 and m2d_get_image (collapse + D2H of the whole mosaic)"}
+        line = {"metric": B.METRIC, "value": px / (ms_step * 1e-3) / 1e6, "unit": B.UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "s16" if mode == "multiband" else "u8", "data": "synthetic",
+                "config": {"workload": B.workload_name(mode, per_gpu) + " x %d GPUs: %d frames, %d flight lines of %d" % (world, n, -(-n // fpl), fpl),
+                           "mode": mode, "frames": n, "frames_per_gpu": per_gpu, "frames_fused": fused,
+                           "parallelism": "%d strips of %d tiles along axis %d (tile ownership); frames resident on the GPU of their own flight lines, "
+                                          "%d halo frames exchanged by NCCL P2P per step (inside the timed region), poses to all ranks; "
+                                          "largest rank feeds %d frames" % (world, span, axis, plan.frames_moved(), int(hull.item())),
+                           "final_tile_gather": "not in `value` (like save() at 1 GPU); %.2f ms to rank 0, see breakdown_ms" % float(tmax[1]),
+                           "l2": "inputs %.2f GB per GPU per step > 126 MB L2" % (per_gpu * W * H * 3 / 1e9)},
+                "clocks": clocks, "gpu_launches": int(float(t[3])),
+                "breakdown_ms": {"exchange_plus_fuse": ms_step, "tile_gather_to_root": float(tmax[1]),
+                                 "value_incl_gather": px / ((ms_step + float(tmax[1])) * 1e-3) / 1e6},
+                "e2e": e2e, "roofline": None, "cpu_baseline": None}
+        os.write(saved_stdout, (json.dumps(line) + "\n").encode())
+    dist.destroy_process_group()
+
+
+def bench_strong(args, rank, world, local_rank):
+    """Strong scaling of the BASELINE workload over N tile shards (frames block-cyclic over the GPUs, all_gather)."""
     import json
     import pi_slam_fusion_b200.map2d as m2d
     import pi_slam_fusion_b200.synth as synth

@@ -22,24 +22,48 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, typ, distributed_input, q):
+def _worker(rank, world, port, typ, distributed_input, q, backend="gloo"):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    cuda = backend == "nccl"
+    if cuda:
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from oracle import oracle as O
         import pi_slam_fusion_b200.synth as synth
         from pi_slam_fusion_b200.sharded import ShardedMap2D
-        seq = synth.Sequence(14, 320, 180, seed=21, jitter=True, fpl=4, prepare_frames=3, cross=0.9, along=0.6)
-        frames = torch.from_numpy(seq.frames()) if rank == 0 else None
-        sm = ShardedMap2D(lambda t, **kw: O.OracleMap2D.create(t, **kw), typ, rank, world, device=None, shard_axis=0, shard_span=1)
+        if cuda:   # the product: the CUDA library on this rank's GPU (the oracle only checks the result on rank 0)
+            import pi_slam_fusion_b200.map2d as m2d
+            factory, device, tdev = (lambda t, **kw: m2d.Map2D.create(t, thread=False, **kw)), rank, torch.device("cuda", rank)
+        else:
+            factory, device, tdev = (lambda t, **kw: O.OracleMap2D.create(t, **kw)), None, torch.device("cpu")
+        from pi_slam_fusion_b200.sharded import DeliveryPlan, even_split
+        if distributed_input == "owned":   # a longer strip survey, so that some frames are needed by one rank only
+            seq = synth.Sequence(30, 320, 180, seed=23, jitter=True, fpl=3, prepare_frames=3, cross=0.9, along=0.6)
+        else:
+            seq = synth.Sequence(14, 320, 180, seed=21, jitter=True, fpl=4, prepare_frames=3, cross=0.9, along=0.6)
+        frames = torch.from_numpy(seq.frames()).to(tdev) if rank == 0 else None
+        sm = ShardedMap2D(factory, typ, rank, world, device=device, shard_axis=0, shard_span=1)
         assert sm.prepare(seq.plane, seq.camera, seq.prepare_poses)
         poses = seq.poses.copy()
         poses[6, 3:] = [0.5, 0.5, 0.5, 0.5]  # rejected on every rank alike
-        if distributed_input:
+        extra = {}
+        if distributed_input == "owned":
+            rects, axis, span, origin = sm.align_strips(poses)
+            plan = DeliveryPlan(rects, axis, span, world, even_split(seq.n, world), origin)
+            buf, mine = sm.alloc_owned_buffer(plan, seq.w, seq.h)
+            buf.fill_(7)  # halo slots start as garbage: they must be overwritten by the exchange
+            lo, hi = plan.resident[rank]
+            mine.copy_(torch.from_numpy(seq.frames(range(lo, hi))))
+            res = sm.feed_all_owned(plan, buf, poses, seq.w, seq.h)
+            extra = {"hull": plan.hull, "moved": plan.frames_moved(), "n": seq.n}
+        elif distributed_input:
             ids = ShardedMap2D.local_frame_ids(seq.n, rank, world, block=3)
-            local = torch.from_numpy(seq.frames(ids))
+            local = torch.from_numpy(seq.frames(ids)).to(tdev)
             res = sm.feed_all_distributed(local, poses, seq.w, seq.h, block=3)
         else:
             res = sm.feed_all(frames, poses, seq.w, seq.h, chunk=5)
@@ -48,6 +72,7 @@ def _worker(rank, world, port, typ, distributed_input, q):
         dist.all_gather_object(counts, owned)
         got = sm.gather_to_root()
         out = {"rank": rank, "res": res.tolist(), "counts": counts, "received": got}
+        out.update(extra)
         if rank == 0:
             ref = O.OracleMap2D.create(typ)
             assert ref.prepare(seq.plane, seq.camera, seq.prepare_poses)
@@ -80,7 +105,7 @@ def _worker(rank, world, port, typ, distributed_input, q):
 
 
 @pytest.mark.parametrize("typ", [1, 3])
-@pytest.mark.parametrize("distributed_input", [False, True])
+@pytest.mark.parametrize("distributed_input", [False, True, "owned"])
 def test_two_rank_sharded_equals_unsharded(typ, distributed_input):
     world = 2
     ctx = mp.get_context("spawn")
@@ -101,3 +126,30 @@ def test_two_rank_sharded_equals_unsharded(typ, distributed_input):
     assert root["received"] == root["counts"][1]
     assert root["ntiles"] == sum(root["counts"]), "ownership must be disjoint and complete"
     assert root["bad"] == 0 and root["image_equal"]
+    if distributed_input == "owned":
+        # the plan really kept pixels away from ranks that do not need them, and really moved the halo frames
+        assert any(tuple(h) != (0, root["n"]) for h in root["hull"]) and 0 < root["moved"] < root["n"]
+
+
+def test_delivery_plan_properties():
+    import sys
+    sys.path.insert(0, ROOT)
+    from pi_slam_fusion_b200.sharded import DeliveryPlan, even_split, strip_owner
+    rng = np.random.default_rng(5)
+    n, world, span, origin = 60, 4, 6, -7
+    x0 = np.sort(rng.integers(-7, 14, n))
+    rects = np.stack([x0, rng.integers(0, 3, n), x0 + rng.integers(1, 5, n), rng.integers(4, 6, n)], 1)
+    rects[11] = -1
+    plan = DeliveryPlan(rects, 0, span, world, even_split(n, world), origin, margin=1)
+    for r in range(world):
+        a, b = plan.hull[r]
+        for k in range(n):
+            owners = {strip_owner(t, span, world, origin) for t in range(rects[k, 0], rects[k, 2])} if k != 11 else set()
+            if r in owners:
+                assert a <= k < b, "a frame that touches an owned tile must be inside the rank's hull"
+        lo, hi = plan.buffer[r]
+        assert lo <= min(a, plan.resident[r][0]) and hi >= max(b, plan.resident[r][1])
+        got = sorted([(t[2], t[3]) for t in plan.transfers if t[1] == r] + [plan.resident[r]])
+        cover = [k for (u, v) in got for k in range(max(u, a), min(v, b))]
+        assert cover == list(range(a, b)), "hull = own frames + received ranges, without overlap"
+    assert strip_owner(origin, span, world, origin) == 0 and strip_owner(origin - 1, span, world, origin) == world - 1
