@@ -121,6 +121,12 @@ int m2d_feed_batch(m2d_handle h, int n, const uint8_t* base, size_t frame_stride
  * grown, no tile touched): the caller's delivery plan was wrong.  result[i] as for m2d_feed_batch (may be NULL). */
 int m2d_feed_poses(m2d_handle h, int n, const double* poses /* n x 7 */, int* result);
 
+/* Dry run of the bounds half of feed() (Map2DCPU.cpp:163-233) for n poses in feed order, on a COPY of the grid:
+ * rects[i] = {x0,y0,x1,y1} in ABSOLUTE tile coordinates exactly as sequential feed()/m2d_feed_poses calls will
+ * compute them (spreadMap growth included), or all -1 for a frame they will reject.  The map is not modified.
+ * This is what a sharded host needs to decide which shard needs which frame's pixels. */
+int m2d_plan_rects(m2d_handle h, int n, const double* poses /* n x 7 */, int* rects /* n x 4 */);
+
 /* Re-partition the tile ownership of a handle that holds no tiles yet (after m2d_prepare or m2d_reset; else
  * M2D_ERR_STATE).  Same rule as m2d_config.shard_*, with strip 0 starting at absolute tile coordinate `origin`:
  * owner = floor((abs - origin) / span) mod count.  Lets the host align contiguous strips with the surveyed area,

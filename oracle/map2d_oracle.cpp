@@ -781,6 +781,20 @@ int orc_prepare(orc_map* o, const double* plane, const double* cam, int n, const
 int orc_feed(orc_map* o, const uint8_t* bgr, int w, int h, size_t stride, const double* pose) {
     return o->m.feed(bgr, w, h, stride, pose) ? M2D_OK : M2D_REJECTED;
 }
+int orc_plan_rects(orc_map* o, int n, const double* poses, int* rects) {  // stand-in for m2d_plan_rects
+    if (!o->m.valid) return M2D_ERR_STATE;
+    Map tmp = o->m;  // tiles are shared pointers: the copy is metadata only, and a pose-only feed never touches them
+    for (int i = 0; i < n; i++) {
+        int* r = rects + 4 * (size_t)i;
+        tmp.last_rect[0] = tmp.last_rect[1] = tmp.last_rect[2] = tmp.last_rect[3] = -1;
+        bool ok = tmp.feed(nullptr, (int)tmp.cam_w, (int)tmp.cam_h, 0, poses + 7 * (size_t)i);
+        if (ok && tmp.last_rect[2] > tmp.last_rect[0]) {
+            r[0] = tmp.last_rect[0] + tmp.org_x; r[1] = tmp.last_rect[1] + tmp.org_y;
+            r[2] = tmp.last_rect[2] + tmp.org_x; r[3] = tmp.last_rect[3] + tmp.org_y;
+        } else r[0] = r[1] = r[2] = r[3] = -1;
+    }
+    return M2D_OK;
+}
 int orc_set_shard(orc_map* o, int rank, int count, int axis, int span, int origin) {  // stand-in for m2d_set_shard
     if (count < 1 || rank < 0 || rank >= count || (axis != 0 && axis != 1) || span < 1) return M2D_ERR_ARG;
     for (const auto& e : o->m.data) if (e) return M2D_ERR_STATE;

@@ -70,6 +70,7 @@ def lib():
         L.orc_prepare.argtypes = [vp, dp, dp, C.c_int, dp]
         L.orc_feed.argtypes = [vp, vp, C.c_int, C.c_int, C.c_size_t, dp]
         L.orc_feed_poses.argtypes = [vp, C.c_int, dp, C.POINTER(C.c_int)]
+        L.orc_plan_rects.argtypes = [vp, C.c_int, dp, C.POINTER(C.c_int)]
         L.orc_set_shard.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         L.orc_get_grid.argtypes = [vp, ip, ip, dp, dp, dp]
         L.orc_last_rect.argtypes = [vp, ip]
@@ -289,6 +290,12 @@ class OracleMap2D:
     def import_tiles(self, xy, src_ptr, on_device=False):
         xy = np.ascontiguousarray(xy, np.int32).reshape(-1, 2)
         return lib().orc_import_tiles(self._h, len(xy), xy.ctypes.data_as(C.POINTER(C.c_int)), src_ptr, 0) == 0
+
+    def plan_rects(self, poses):
+        poses = np.ascontiguousarray(poses, np.float64).reshape(-1, 7)
+        rects = np.zeros((len(poses), 4), np.int32)
+        assert lib().orc_plan_rects(self._h, len(poses), _dptr(poses), rects.ctypes.data_as(C.POINTER(C.c_int))) == 0
+        return rects
 
     def set_shard(self, rank, count, axis, span, origin=0):
         return lib().orc_set_shard(self._h, rank, count, axis, span, origin) == 0

@@ -278,7 +278,9 @@ int m2d_map::prepare(const double* plane7, const double* cam, int n, const doubl
 
 // spreadMap — Map2DCPU.cpp:339-382: grow the grid (never shrinks) and re-index the tile table; no pixel moves and,
 // because kernels address tiles by pointer, nothing on the device changes.
-int m2d_map::spread(double xmin, double ymin, double xmax, double ymax) {
+// The geometry half of spreadMap (no tile table): new extent in whole tiles around the old origin.
+static int grow_geom(GridGeom& g, int& org_x, int& org_y, double xmin, double ymin, double xmax, double ymax,
+                     int* dx, int* dy) {
     int xminInt = (int)floor((xmin - g.min_x) * g.ele_size_inv), yminInt = (int)floor((ymin - g.min_y) * g.ele_size_inv);
     int xmaxInt = (int)ceil((xmax - g.min_x) * g.ele_size_inv), ymaxInt = (int)ceil((ymax - g.min_y) * g.ele_size_inv);
     xminInt = std::min(xminInt, 0); yminInt = std::min(yminInt, 0);
@@ -287,19 +289,28 @@ int m2d_map::spread(double xmin, double ymin, double xmax, double ymax) {
     if (nw <= 0 || nh <= 0 || (long long)nw * nh > (1ll << 26)) return M2D_REJECTED;
     double nminx = g.min_x + g.ele_size * xminInt, nminy = g.min_y + g.ele_size * yminInt;
     double nmaxx = nminx + nw * g.ele_size, nmaxy = nminy + nh * g.ele_size;
+    g.min_x = nminx; g.min_y = nminy; g.max_x = nmaxx; g.max_y = nmaxy;
+    g.w = nw; g.h = nh;
+    org_x += xminInt; org_y += yminInt;
+    *dx = xminInt; *dy = yminInt;
+    return M2D_OK;
+}
+
+int m2d_map::spread(double xmin, double ymin, double xmax, double ymax) {
+    const int ow = g.w, oh = g.h;
+    int xminInt = 0, yminInt = 0;
+    { int rc = grow_geom(g, org_x, org_y, xmin, ymin, xmax, ymax, &xminInt, &yminInt); if (rc != M2D_OK) return rc; }
+    const int nw = g.w, nh = g.h;
     std::vector<uint8_t*> nt((size_t)nw * nh, nullptr);
     std::vector<int> nsw((size_t)nw * nh, -1);
     std::vector<uint32_t> nse((size_t)nw * nh, 0);
     std::vector<uint8_t> nch((size_t)nw * nh, 0);
-    for (int x = 0; x < g.w; x++)
-        for (int y = 0; y < g.h; y++) {
-            size_t o = (size_t)y * g.w + x, n = (size_t)(x - xminInt) + (size_t)(y - yminInt) * nw;
+    for (int x = 0; x < ow; x++)
+        for (int y = 0; y < oh; y++) {
+            size_t o = (size_t)y * ow + x, n = (size_t)(x - xminInt) + (size_t)(y - yminInt) * nw;
             nt[n] = table[o]; nsw[n] = slot_work[o]; nse[n] = slot_epoch[o]; nch[n] = changed[o];
         }
     table.swap(nt); slot_work.swap(nsw); slot_epoch.swap(nse); changed.swap(nch);
-    g.min_x = nminx; g.min_y = nminy; g.max_x = nmaxx; g.max_y = nmaxy;
-    g.w = nw; g.h = nh;
-    org_x += xminInt; org_y += yminInt;
     return M2D_OK;
 }
 
@@ -813,6 +824,30 @@ int m2d_feed_poses(m2d_handle h, int n, const double* poses, int* result) {
     if (violations) {
         m.err = "m2d_feed_poses: " + std::to_string(violations) + " pose(s) touch tiles this shard owns; their pixels are required";
         return M2D_ERR_ARG;
+    }
+    return M2D_OK;
+}
+
+int m2d_plan_rects(m2d_handle h, int n, const double* poses, int* rects) {
+    if (!h || n < 0 || (n && (!poses || !rects))) return M2D_ERR_ARG;
+    if (!h->valid) return M2D_ERR_STATE;
+    GridGeom g = h->g;   // dry run on a copy: the map itself is not touched
+    int org_x = h->org_x, org_y = h->org_y;
+    for (int i = 0; i < n; i++) {
+        int* r = rects + 4 * (size_t)i;
+        r[0] = r[1] = r[2] = r[3] = -1;
+        FrameBounds fb;
+        const double* pose = poses + 7 * (size_t)i;
+        frame_bounds(g, pose, &fb);
+        if (!fb.ok) continue;
+        if (fb.gx0 < g.min_x || fb.gx1 > g.max_x || fb.gy0 < g.min_y || fb.gy1 > g.max_y) {
+            int dx, dy;
+            if (grow_geom(g, org_x, org_y, fb.gx0, fb.gy0, fb.gx1, fb.gy1, &dx, &dy) != M2D_OK) continue;
+            frame_bounds(g, pose, &fb);
+            if (!fb.ok) continue;
+        }
+        if (fb.x0 < 0 || fb.y0 < 0 || fb.x1 > g.w || fb.y1 > g.h || fb.x0 >= fb.x1 || fb.y0 >= fb.y1) continue;
+        r[0] = fb.x0 + org_x; r[1] = fb.y0 + org_y; r[2] = fb.x1 + org_x; r[3] = fb.y1 + org_y;
     }
     return M2D_OK;
 }

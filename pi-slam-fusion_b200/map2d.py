@@ -43,7 +43,7 @@ class Stats(C.Structure):
 
 
 EXPORTS = ["m2d_config_default", "m2d_create", "m2d_destroy", "m2d_prepare", "m2d_feed", "m2d_feed_device",
-           "m2d_feed_batch", "m2d_feed_poses", "m2d_set_shard", "m2d_sync", "m2d_queue_size", "m2d_set_stream", "m2d_reset", "m2d_get_grid",
+           "m2d_feed_batch", "m2d_feed_poses", "m2d_plan_rects", "m2d_set_shard", "m2d_sync", "m2d_queue_size", "m2d_set_stream", "m2d_reset", "m2d_get_grid",
            "m2d_last_rect", "m2d_get_tile", "m2d_get_image", "m2d_save", "m2d_tile_bytes", "m2d_tile_count",
            "m2d_export_tiles", "m2d_import_tiles", "m2d_poll_changed", "m2d_get_tile_image", "m2d_save_state", "m2d_load_state", "m2d_get_stats", "m2d_last_error",
            "m2d_launch_count", "m2d_profile", "m2d_get_kernel_times", "m2d_alloc_host", "m2d_free_host", "m2d_compute_bounds"]
@@ -71,6 +71,7 @@ def lib():
     L.m2d_feed_device.argtypes = [vp, vp, C.c_int, C.c_int, C.c_size_t, dp]
     L.m2d_feed_batch.argtypes = [vp, C.c_int, vp, C.c_size_t, C.c_int, C.c_int, C.c_size_t, dp, C.c_int, ip]
     L.m2d_feed_poses.argtypes = [vp, C.c_int, dp, ip]
+    L.m2d_plan_rects.argtypes = [vp, C.c_int, dp, ip]
     L.m2d_set_shard.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     L.m2d_sync.argtypes = [vp]
     L.m2d_queue_size.argtypes = [vp]
@@ -205,6 +206,13 @@ class Map2D:
         res = np.zeros(len(poses), np.int32)
         self._check(lib().m2d_feed_poses(self._h, len(poses), _dptr(poses), res.ctypes.data_as(C.POINTER(C.c_int))))
         return res
+
+    def plan_rects(self, poses):
+        """Absolute tile rect of every frame as sequential feeds will compute it (dry run), see m2d_plan_rects."""
+        poses = np.ascontiguousarray(poses, np.float64).reshape(-1, 7)
+        rects = np.zeros((len(poses), 4), np.int32)
+        self._check(lib().m2d_plan_rects(self._h, len(poses), _dptr(poses), rects.ctypes.data_as(C.POINTER(C.c_int))))
+        return rects
 
     def set_shard(self, rank, count, axis, span, origin=0):
         """Re-partition tile ownership (only while the map holds no tiles), see m2d_set_shard."""

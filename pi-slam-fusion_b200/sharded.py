@@ -39,17 +39,17 @@ class DeliveryPlan:
     """Which frame pixels travel where when frames originate on the GPUs that captured them ("deliver
     frame + H + tile rect to owners ... P2P of just what maps into each owner's tiles").
 
-    rects     [n,4] int: x0,y0,x1,y1 tile rect of every frame in ABSOLUTE tile coordinates (-1 = rejected), as returned
-              by compute_bounds() right after prepare();
+    rects     [n,4] int: x0,y0,x1,y1 tile rect of every frame in ABSOLUTE tile coordinates (-1 = rejected), exactly as
+              the sequential feeds will compute them: plan_rects() (m2d_plan_rects, a dry run that includes spreadMap);
     resident  per rank, the half-open range [lo,hi) of feed-order frame indices whose pixels start out on that rank.
-    A rank needs the pixels of every frame whose rect (grown by `margin` tiles: the rect is recomputed by feed() after
-    spreadMap and may move by one tile on a knife edge) contains a tile it owns; it is handed the contiguous hull
+    A rank needs the pixels of every frame whose rect (optionally grown by `margin` tiles) contains a tile it owns
+    (a wrong plan is caught: m2d_feed_poses refuses a pose under which the shard owns a tile); it is handed the hull
     [a,b) of those frames (a serpentine survey cut into strips makes the needed frames contiguous; a hull that covers
     a few unneeded frames costs only their transfer — feeding a frame under which a shard owns nothing is a no-op).
     Frames outside the hull are fed as poses only (m2d_feed_poses), so every rank grows its grid like an unsharded run.
     """
 
-    def __init__(self, rects, axis, span, world, resident, origin=0, margin=1):
+    def __init__(self, rects, axis, span, world, resident, origin=0, margin=0):
         rects = np.asarray(rects, np.int64).reshape(-1, 4)
         self.n, self.world = len(rects), world
         self.resident = [tuple(r) for r in resident]
@@ -220,16 +220,14 @@ class ShardedMap2D:
         """After prepare(): cut the tile range the survey will touch into `world` contiguous strips (one per rank)
         and install them with set_shard.  Every rank computes the same cut from the same poses.  Returns
         (rects, axis, span, origin) for DeliveryPlan."""
-        rects, _ = self.map.compute_bounds(poses)
-        rects = np.asarray(rects, np.int64).reshape(-1, 4)
+        rects = np.asarray(self.map.plan_rects(poses), np.int64).reshape(-1, 4)
         ok = rects[rects[:, 2] > rects[:, 0]]
         if len(ok) == 0:
             raise ValueError("no frame of the sequence is accepted")
         ext = [(int(ok[:, 0].min()), int(ok[:, 2].max())), (int(ok[:, 1].min()), int(ok[:, 3].max()))]
         if axis is None:
             axis = 0 if ext[0][1] - ext[0][0] >= ext[1][1] - ext[1][0] else 1
-        # one spare tile at either end, so that DeliveryPlan's knife-edge margin never wraps round to the far rank
-        lo, hi = ext[axis][0] - 1, ext[axis][1] + 1
+        lo, hi = ext[axis]
         span = max(1, -(-(hi - lo) // self.world))
         self.map.set_shard(self.rank, self.world, axis, span, lo)
         return rects, axis, span, lo
@@ -244,29 +242,45 @@ class ShardedMap2D:
         return buf, buf[lo - b0:hi - b0]
 
     def feed_all_owned(self, plan, buf, poses, w, h):
-        """One pass over the whole sequence: halo frames by P2P from the ranks they are resident on (one batched
-        isend/irecv group), then feed in global order: poses only outside this rank's hull, pixels inside."""
+        """One pass over the whole sequence.  Halo frames come by P2P from the ranks they are resident on, in two
+        batched isend/irecv groups posted up front: first the transfers that fill receivers' LOWER halos (frames
+        that precede the receiver's own ones in feed order), then the UPPER halos.  The rank feeds in global order —
+        poses only outside its hull, pixels inside — and waits for the upper halos only after it has enqueued its
+        lower halo and its own frames, so that transfer overlaps the fusion."""
         poses = np.ascontiguousarray(poses, np.float64).reshape(-1, 7)
         n = len(poses)
         assert n == plan.n
         b0, _ = plan.buffer[self.rank]
-        ops = []
-        for (src, dst, lo, hi) in plan.transfers:
-            if src == self.rank:
-                ops.append(dist.P2POp(dist.isend, buf[lo - b0:hi - b0], dst))
-            elif dst == self.rank:
-                ops.append(dist.P2POp(dist.irecv, buf[lo - b0:hi - b0], src))
-        if ops:
-            for req in dist.batch_isend_irecv(ops):
+
+        def post(lower):
+            ops = []
+            for (src, dst, lo, hi) in plan.transfers:
+                if (lo < plan.resident[dst][0]) != lower:
+                    continue
+                if src == self.rank:
+                    ops.append(dist.P2POp(dist.isend, buf[lo - b0:hi - b0], dst))
+                elif dst == self.rank:
+                    ops.append(dist.P2POp(dist.irecv, buf[lo - b0:hi - b0], src))
+            return dist.batch_isend_irecv(ops) if ops else []
+
+        def wait(reqs):
+            for req in reqs:
                 req.wait()
-            if self.cuda:
+            if reqs and self.cuda:
                 torch.cuda.current_stream().synchronize()  # the library consumes buf on its own stream
+
+        first, second = post(True), post(False)
         a, b = plan.hull[self.rank]
+        split = min(max(plan.resident[self.rank][1], a), b)   # [a,split): lower halo + own frames, [split,b): upper halo
         res = np.zeros(n, np.int32)
         if a > 0:
             res[:a] = self.map.feed_poses(poses[:a])
-        if b > a:
-            res[a:b] = self.map.feed_batch(buf[a - b0:].data_ptr(), b - a, w * h * 3, w, h, w * 3, poses[a:b], self.cuda)
+        wait(first)
+        if split > a:
+            res[a:split] = self.map.feed_batch(buf[a - b0:].data_ptr(), split - a, w * h * 3, w, h, w * 3, poses[a:split], self.cuda)
+        wait(second)
+        if b > split:
+            res[split:b] = self.map.feed_batch(buf[split - b0:].data_ptr(), b - split, w * h * 3, w, h, w * 3, poses[split:b], self.cuda)
         if b < n:
             res[b:] = self.map.feed_poses(poses[b:])
         self.map.sync()

@@ -126,6 +126,37 @@ def test_bounds_kernel_matches_oracle():
     g.close()
 
 
+def test_plan_rects_and_pose_only_feed():
+    """m2d_plan_rects predicts the absolute rect of every frame exactly (spreadMap included) without touching the
+    map; m2d_feed_poses grows the grid like feed() and refuses poses under which the shard owns tiles."""
+    seq = synth.Sequence(40, 320, 180, seed=9, jitter=True, fpl=4, prepare_frames=3, cross=0.9, along=0.6)
+    poses = seq.poses.copy()
+    poses[7, 3:] = [0.5, 0.5, 0.5, 0.5]
+    g = m2d.Map2D.create(1, thread=False)
+    o = O.OracleMap2D.create(1)
+    assert g.prepare(seq.plane, seq.camera, seq.prepare_poses) and o.prepare(seq.plane, seq.camera, seq.prepare_poses)
+    g0 = g.grid()
+    plan = g.plan_rects(poses)
+    assert np.array_equal(plan, o.plan_rects(poses)) and (plan[7] == -1).all()
+    g1 = g.grid()
+    assert (g0["w"], g0["h"]) == (g1["w"], g1["h"]) and g.tile_count() == 0, "the dry run must not touch the map"
+    # a shard that owns nothing under the survey: pose-only feed of everything reproduces the unsharded grid
+    far = int(plan[plan[:, 2] > 0, 2].max()) + 5
+    g.set_shard(1, 2, 0, 1 << 20, far - (1 << 20))   # rank 1 owns abs x >= far only
+    res = g.feed_poses(poses)
+    frames = seq.frames()
+    exp = [0 if o.feed(frames[k], poses[k]) else 1 for k in range(seq.n)]
+    assert res.tolist() == exp and g.tile_count() == 0
+    gg, go = g.grid(), o.grid()
+    assert (gg["w"], gg["h"]) == (go["w"], go["h"]) and np.array_equal(gg["min"], go["min"]) and gg["w"] > g0["w"]
+    # ... and one that owns everything is refused (its pixels are required), loudly
+    g.reset()
+    g.set_shard(0, 2, 0, 1 << 20, -(1 << 19))
+    with pytest.raises(RuntimeError):
+        g.feed_poses(poses[:3])
+    g.close()
+
+
 @pytest.mark.parametrize("typ", [1, 3])
 def test_stats_match_oracle(typ):
     seq = synth.Sequence(10, 320, 180, seed=4, jitter=True, fpl=5, prepare_frames=5)

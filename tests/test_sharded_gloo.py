@@ -104,10 +104,9 @@ def _worker(rank, world, port, typ, distributed_input, q, backend="gloo"):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("typ", [1, 3])
-@pytest.mark.parametrize("distributed_input", [False, True, "owned"])
-def test_two_rank_sharded_equals_unsharded(typ, distributed_input):
-    world = 2
+@pytest.mark.parametrize("typ,distributed_input,world", [(1, False, 2), (3, False, 2), (1, True, 2), (3, True, 2),
+                                                         (1, "owned", 2), (3, "owned", 2), (3, "owned", 3)])
+def test_two_rank_sharded_equals_unsharded(typ, distributed_input, world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
@@ -119,11 +118,12 @@ def test_two_rank_sharded_equals_unsharded(typ, distributed_input):
         p.join(timeout=60)
         assert p.exitcode == 0
     root = [o for o in outs if o["rank"] == 0][0]
-    other = [o for o in outs if o["rank"] == 1][0]
-    assert root["res"] == other["res"] == root["exp"] and root["res"][6] == 1
+    for other in outs:
+        assert other["res"] == root["exp"]
+    assert root["res"][6] == 1
     assert root["same_grid"]
     assert min(root["counts"]) > 0, "both shards must own tiles in this layout"
-    assert root["received"] == root["counts"][1]
+    assert root["received"] == sum(root["counts"][1:])
     assert root["ntiles"] == sum(root["counts"]), "ownership must be disjoint and complete"
     assert root["bad"] == 0 and root["image_equal"]
     if distributed_input == "owned":
@@ -141,6 +141,8 @@ def test_delivery_plan_properties():
     rects = np.stack([x0, rng.integers(0, 3, n), x0 + rng.integers(1, 5, n), rng.integers(4, 6, n)], 1)
     rects[11] = -1
     plan = DeliveryPlan(rects, 0, span, world, even_split(n, world), origin, margin=1)
+    exact = DeliveryPlan(rects, 0, span, world, even_split(n, world), origin)
+    assert all(e[0] >= h[0] and e[1] <= h[1] for e, h in zip(exact.hull, plan.hull))
     for r in range(world):
         a, b = plan.hull[r]
         for k in range(n):
@@ -153,3 +155,36 @@ def test_delivery_plan_properties():
         cover = [k for (u, v) in got for k in range(max(u, a), min(v, b))]
         assert cover == list(range(a, b)), "hull = own frames + received ranges, without overlap"
     assert strip_owner(origin, span, world, origin) == 0 and strip_owner(origin - 1, span, world, origin) == world - 1
+
+
+def test_oracle_plan_rects_equal_sequential_feed_rects():
+    """The CPU stand-in's dry run (orc_plan_rects) against what feeding the frames one by one really does."""
+    sys.path.insert(0, ROOT)
+    from oracle import oracle as O
+    import pi_slam_fusion_b200.synth as synth
+    seq = synth.Sequence(26, 320, 180, seed=31, jitter=True, fpl=3, prepare_frames=3, cross=0.9, along=0.6)
+    poses = seq.poses[::-1].copy()   # fly the survey backwards: the grid then also grows towards negative coordinates
+    poses[4, 3:] = [0.5, 0.5, 0.5, 0.5]
+    o = O.OracleMap2D.create(1)
+    assert o.prepare(seq.plane, seq.camera, poses[:3])
+    plan = o.plan_rects(poses)
+    g0 = o.grid()
+    ref = O.OracleMap2D.create(1)
+    assert ref.prepare(seq.plane, seq.camera, poses[:3])
+    org = np.zeros(2)
+    m0 = ref.grid()["min"][:2].copy()
+    es = 256 * ref.grid()["length_pixel"]
+    grew = False
+    for k in range(seq.n):
+        ok = ref.feed(seq.frame(seq.n - 1 - k), poses[k])
+        if not ok:
+            assert (plan[k] == -1).all()
+            continue
+        g = ref.grid()
+        org = np.round((g["min"][:2] - m0) / es).astype(int)   # absolute coordinate of slot (0,0) after the growth
+        grew |= bool(org.any())
+        r = np.array(ref.last_rect())
+        assert (plan[k] == r + [org[0], org[1], org[0], org[1]]).all(), k
+    assert grew, "the sequence must exercise spreadMap towards negative coordinates"
+    g1 = o.grid()
+    assert (g0["w"], g0["h"]) == (g1["w"], g1["h"]) and o.tile_count() == 0
