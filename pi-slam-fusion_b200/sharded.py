@@ -397,7 +397,9 @@ def bench_weak(args, rank, world, local_rank):
     launches = float(sm.map.launch_count() - l0) / args.steps
     clocks = sampler.result()
 
-    # final tile gather + mosaic on the root, timed on its own (one repetition)
+    # final tile gather to the root, timed on its own; the first call pays NCCL's lazy connection set-up between
+    # the root and the ranks it has not exchanged halos with, and the root's tile-pool growth: warm once, then time
+    sm.gather_to_root()
     dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
