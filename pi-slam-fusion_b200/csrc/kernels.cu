@@ -370,6 +370,7 @@ __device__ __forceinline__ uint32_t bilinear_rne_bgr(uint32_t v00, uint32_t v01,
 }
 
 // Warp 4 consecutive region px (x..x+3 on row y; x is a multiple of 4, so they share one 64-px coordinate block).
+template <bool WGT = true>
 __device__ __forceinline__ void mb_sample4(const GroupParams& p, const RawSrc& R, const double* M, int x, int y, uint32_t* g, float* w) {
     RowBase rb = row_base(M, x, y);
     double x1 = (double)(x & 63);
@@ -380,14 +381,15 @@ __device__ __forceinline__ void mb_sample4(const GroupParams& p, const RawSrc& R
         double fx, fy;
         px_coord(M, rb, x1 + (double)j, fx, fy);
         int X = rnd(fx * 32.0), Y = rnd(fy * 32.0);
-        int nx = rnd(fx), ny = rnd(fy);
+        int nx = 0, ny = 0;
+        if constexpr (WGT) { nx = rnd(fx); ny = rnd(fy); }
         // saturate_cast<short> of the integer coordinates only matters beyond +-32767 px: test once, clamp rarely
         if (__builtin_expect((unsigned)(X + 1048544) >= 2097088u || (unsigned)(Y + 1048544) >= 2097088u, 0)) {
             nx = sat_s16(nx); ny = sat_s16(ny);
             X = (sat_s16(X >> 5) << 5) | (X & 31); Y = (sat_s16(Y >> 5) << 5) | (Y & 31);
         }
         int sx = X >> 5, sy = Y >> 5;
-        w[j] = ((unsigned)nx < (unsigned)sw && (unsigned)ny < (unsigned)sh) ? __ldg(wimg + (ny * sw + nx)) : 0.f;
+        if constexpr (WGT) w[j] = ((unsigned)nx < (unsigned)sw && (unsigned)ny < (unsigned)sh) ? __ldg(wimg + (ny * sw + nx)) : 0.f;
         uint32_t v00, v01, v10, v11;
         if ((unsigned)sx < (unsigned)(sw - 1) && (unsigned)sy < (unsigned)(sh - 1)) {
             raw_tap_pair_bgr(R, sx, sy, v00, v01);
@@ -867,6 +869,545 @@ cudaError_t launch_mb_select(const GroupParams& p, const TileLayout& lay, cudaSt
     }
     dim3 g(p.n_tiles, (quads + 255) / 256);
     mb_select_kernel<<<g, 256, 0, stream>>>(p, lay);
+    return cudaGetLastError();
+}
+
+// =========================================================================================================
+// multi-band, WEIGHTS-FIRST variant.  The weight pyramids depend on geometry only, so the winner of
+// every pyramid px can be decided before a single image sample is taken; image warp and image pyrDown then run
+// only where a winner's Laplacian needs them.  Stages per group:
+//   1. mbw_warp / mbw_pyrdown / mbw_pyrtail   weights only, dense                      (order-independent)
+//   2. mbs_decide                             tile-centric arg-max -> tile weights, winner map, `win` cell flags
+//   3. mbs_propagate                          per frame: `need` = win, dilated down the dependency cone
+//   4. mbs_warp / mbs_pyrdown / mbs_pyrtail   image only, only in needed cells
+//   5. mbs_lap                                winner-only Laplacian -> tile state
+// A CELL is 32 x 32 level-0 px of a frame's window; at level l it is (32 >> l)^2 px (requires levels <= 6), so one
+// cell grid (8 x 8 cells per tile) serves every level: cell of level-l px p = (p << l) >> 5.  Dependencies in cell
+// space: Laplacian l needs G_{l+1} at (p>>1)-1 .. (p>>1)+1 -> cells c-1..c+1; G_{l+1}(u) needs G_l at 2u-2 .. 2u+2
+// -> cells c-1..c+1 (borders reflect inwards, never further).  Px of G outside needed cells are never read by a
+// needed px, so they may hold anything.  Results are identical to the dense path.
+// =========================================================================================================
+__device__ __forceinline__ size_t cell_base(const GroupParams& p, int frame, int l) { return ((size_t)frame * p.levels + l) * p.cells_max; }
+
+// ---- 1a. weight warp (nearest, constant 0): one thread = 4 px; px far outside the frame skip the FP64 path ----
+__global__ void __launch_bounds__(256) mbw_warp_kernel(const __grid_constant__ GroupParams p) {
+    const FrameJob& J = p.jobs[blockIdx.y];
+    const int ww = J.wnx * kEle, wh = J.wny * kEle;
+    const int bpr = J.wnx;
+    int by = blockIdx.x / bpr, bx = blockIdx.x - by * bpr;
+    if (by * 4 >= wh) return;
+    int u = bx * kEle + (threadIdx.x & 63) * 4, v = by * 4 + (threadIdx.x >> 6);
+    int x = u + J.wx * kEle, y = v + J.wy * kEle;
+    float w[4] = {0.f, 0.f, 0.f, 0.f};
+    // conservative FP32 test: both ends of the 4-px run map outside the same side of the source (denominators safely
+    // positive) -> every px of the run is outside (a projective map keeps the run a straight segment) -> weight 0
+    const float* mf = J.hinvf;
+    float wa = mf[6] * (float)x + mf[7] * (float)y + mf[8], wb = wa + 3.f * mf[6];
+    bool off = false;
+    if (wa > 1e-3f && wb > 1e-3f) {
+        float ax, ay, bx_, by_;
+        proj_f32(mf, (float)x, (float)y, ax, ay);
+        proj_f32(mf, (float)(x + 3), (float)y, bx_, by_);
+        const float lim_x = (float)p.sw + 0.25f, lim_y = (float)p.sh + 0.25f;
+        off = (ax < -1.25f && bx_ < -1.25f) || (ax > lim_x && bx_ > lim_x) || (ay < -1.25f && by_ < -1.25f) || (ay > lim_y && by_ > lim_y);
+    }
+    if (!off) {
+        double M[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) M[i] = J.hinv[i];
+        RowBase rb = row_base(M, x, y);
+        double x1 = (double)(x & 63);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            double fx, fy;
+            px_coord(M, rb, x1 + (double)j, fx, fy);
+            int nx = rnd(fx), ny = rnd(fy);   // saturate_cast<short> cannot change an in/out decision for sw, sh <= 32767
+            w[j] = ((unsigned)nx < (unsigned)p.sw && (unsigned)ny < (unsigned)p.sh) ? __ldg(p.wimg + (ny * p.sw + nx)) : 0.f;
+        }
+    }
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.scratch + J.w_off[0]) + (size_t)v * ww + u) = make_float4(w[0], w[1], w[2], w[3]);
+}
+cudaError_t launch_mbw_warp(const GroupParams& p, cudaStream_t stream) {
+    dim3 g(p.max_wnx * p.max_wny * (kEle / 4), p.n_frames);
+    mbw_warp_kernel<<<g, 256, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// ---- 1b. weight pyrDown l -> l+1 (f32, OpenCV 2.4.9 association), same tiling as mb_pyrdown_kernel ----
+__global__ void __launch_bounds__(256) mbw_pyrdown_kernel(const __grid_constant__ GroupParams p, int l) {
+    const FrameJob& J = p.jobs[blockIdx.y];
+    const int ns = kEle >> l, nd = kEle >> (l + 1);
+    const int sww = J.wnx * ns, swh = J.wny * ns, srw = J.nx * ns, srh = J.ny * ns, sox = J.wx * ns, soy = J.wy * ns;
+    const int dww = J.wnx * nd, dwh = J.wny * nd, dox = J.wx * nd, doy = J.wy * nd;
+    const int bpr = (dww + 63) / 64;
+    int by = blockIdx.x / bpr, bx = blockIdx.x - by * bpr;
+    int u = (bx * 32 + threadIdx.x) * 2, v0 = (by * 8 + threadIdx.y) * 4;
+    if (u >= dww || v0 >= dwh) return;
+    const float* SW = reinterpret_cast<const float*>(p.scratch + J.w_off[l]);
+    float* DW = reinterpret_cast<float*>(p.scratch + J.w_off[l + 1]);
+    const bool two = (u + 1) < dww;
+    int U = u + dox;
+    int xs[7];
+    int c0 = 2 * U - 2 - sox;
+    const bool fast = (2 * U - 2 >= 0) && (2 * U + 4 < srw) && (c0 >= 0) && (c0 + 6 < sww);
+    if (fast) {
+#pragma unroll
+        for (int d = 0; d < 7; d++) xs[d] = c0 + d;
+    } else {
+#pragma unroll
+        for (int d = 0; d < 7; d++) xs[d] = clampi(reflect101_idx(2 * U + d - 2, srw) - sox, 0, sww - 1);
+    }
+    int V0 = v0 + doy;
+    float h0[5], h1[5];
+#pragma unroll
+    for (int r = 0; r < 11; r++) {
+        int ys = clampi(reflect101_idx(2 * V0 + r - 2, srh) - soy, 0, swh - 1);
+        const float* wr = SW + (size_t)ys * sww;
+        float f[7];
+        if (fast) {
+            const float2* w2 = reinterpret_cast<const float2*>(wr + xs[0]);
+            float2 fa = w2[0], fb = w2[1], fc = w2[2];
+            f[0] = fa.x; f[1] = fa.y; f[2] = fb.x; f[3] = fb.y; f[4] = fc.x; f[5] = fc.y; f[6] = wr[xs[0] + 6];
+        } else {
+#pragma unroll
+            for (int d = 0; d < 7; d++) f[d] = wr[xs[d]];
+        }
+        h0[r % 5] = f[2] * 6.f + (f[1] + f[3]) * 4.f + f[0] + f[4];
+        h1[r % 5] = f[4] * 6.f + (f[3] + f[5]) * 4.f + f[2] + f[6];
+        if (r >= 4 && (r & 1) == 0) {
+            int k = (r - 4) >> 1, v = v0 + k;
+            if (v < dwh) {
+                const int i0 = (r - 4) % 5, i1 = (r - 3) % 5, i2 = (r - 2) % 5, i3 = (r - 1) % 5, i4 = r % 5;
+                float t00 = (h0[i0] + h0[i4]) + (h0[i2] + h0[i2]), t10 = (h0[i1] + h0[i3]) + h0[i2];
+                float t01 = (h1[i0] + h1[i4]) + (h1[i2] + h1[i2]), t11 = (h1[i1] + h1[i3]) + h1[i2];
+                float ow0 = (t00 + t10 * 4.f) * (1.f / 256.f), ow1 = (t01 + t11 * 4.f) * (1.f / 256.f);
+                size_t o = (size_t)v * dww + u;
+                if (two && !(dww & 1)) *reinterpret_cast<float2*>(DW + o) = make_float2(ow0, ow1);
+                else { DW[o] = ow0; if (two) DW[o + 1] = ow1; }
+            }
+        }
+    }
+}
+cudaError_t launch_mbw_pyrdown(const GroupParams& p, int level, cudaStream_t stream) {
+    int nd = kEle >> (level + 1);
+    int blocks = ((p.max_wnx * nd + 63) / 64) * ((p.max_wny * nd + 31) / 32);
+    dim3 b(32, 8), g(blocks, p.n_frames);
+    mbw_pyrdown_kernel<<<g, b, 0, stream>>>(p, level);
+    return cudaGetLastError();
+}
+
+// ---- 1c. weight pyramid tail (small deep levels, one CTA per frame) ----
+__global__ void __launch_bounds__(1024) mbw_pyrtail_kernel(const __grid_constant__ GroupParams p, int l_first) {
+    const FrameJob& J = p.jobs[blockIdx.x];
+    for (int l = l_first; l + 1 < p.levels; l++) {
+        const int ns = kEle >> l, nd = kEle >> (l + 1);
+        const int sww = J.wnx * ns, swh = J.wny * ns, srw = J.nx * ns, srh = J.ny * ns, sox = J.wx * ns, soy = J.wy * ns;
+        const int dww = J.wnx * nd, dwh = J.wny * nd, dox = J.wx * nd, doy = J.wy * nd;
+        const float* SW = reinterpret_cast<const float*>(p.scratch + J.w_off[l]);
+        float* DW = reinterpret_cast<float*>(p.scratch + J.w_off[l + 1]);
+        for (int o = threadIdx.x; o < dww * dwh; o += blockDim.x) {
+            int v = o / dww, u = o - v * dww;
+            int U = u + dox, V = v + doy;
+            int xs[5], ys[5];
+#pragma unroll
+            for (int d = 0; d < 5; d++) {
+                xs[d] = clampi(reflect101_idx(2 * U + d - 2, srw) - sox, 0, sww - 1);
+                ys[d] = clampi(reflect101_idx(2 * V + d - 2, srh) - soy, 0, swh - 1);
+            }
+            float hw[5];
+#pragma unroll
+            for (int r = 0; r < 5; r++) {
+                const float* wr = SW + (size_t)ys[r] * sww;
+                hw[r] = wr[xs[2]] * 6.f + (wr[xs[1]] + wr[xs[3]]) * 4.f + wr[xs[0]] + wr[xs[4]];
+            }
+            float t0 = (hw[0] + hw[4]) + (hw[2] + hw[2]);
+            float t1 = (hw[1] + hw[3]) + hw[2];
+            DW[o] = (t0 + t1 * 4.f) * (1.f / 256.f);
+        }
+        __syncthreads();
+    }
+}
+cudaError_t launch_mbw_pyrtail(const GroupParams& p, int l_first, cudaStream_t stream) {
+    mbw_pyrtail_kernel<<<p.n_frames, 1024, 0, stream>>>(p, l_first);
+    return cudaGetLastError();
+}
+
+// ---- 2. decide: the scan of mb_select_kernel without the Laplacian; winners go to the winner map + cell flags ----
+__global__ void __launch_bounds__(256, 6) mbs_decide_kernel(const __grid_constant__ GroupParams p, const __grid_constant__ TileLayout lay) {
+    const TileWork T = p.tiles[blockIdx.x];
+    int q = blockIdx.y * 256 + threadIdx.x;
+    int l = 0, n = kEle, half = kEle / 2;
+    for (; l < p.levels; l++) {
+        n = kEle >> l;
+        half = n > 1 ? n / 2 : 1;
+        int cnt = half * half;
+        if (q < cnt) break;
+        q -= cnt;
+    }
+    const bool valid = l < p.levels;
+    if (!valid) { l = p.levels - 1; n = kEle >> l; half = n > 1 ? n / 2 : 1; q = 0; }
+    const int qy = q / half, qx = q - qy * half;
+    const int py = qy * 2, px = qx * 2;
+    const bool quad = n > 1;
+    const size_t to = (size_t)py * n + px;
+    float* tw = reinterpret_cast<float*>(T.state + lay.wgt_off[l]) + to;
+    float bw[4];
+    if (T.fresh) { bw[0] = bw[1] = bw[2] = bw[3] = -INFINITY; }
+    else if (quad) {
+        float2 t0 = *reinterpret_cast<const float2*>(tw), t1 = *reinterpret_cast<const float2*>(tw + n);
+        bw[0] = t0.x; bw[1] = t0.y; bw[2] = t1.x; bw[3] = t1.y;
+    } else { bw[0] = tw[0]; bw[1] = bw[2] = bw[3] = 0.f; }
+    int best[4] = {-1, -1, -1, -1};
+    unsigned wins = 0;
+    const int lane = threadIdx.x & 31;
+    const bool uniform = __all_sync(0xffffffffu, l == __shfl_sync(0xffffffffu, l, 0));
+    for (int c0 = 0; c0 < T.count; c0 += 32) {
+        unsigned long long wb = 0ull;
+        int stride = 0;
+        if (uniform && c0 + lane < T.count) {
+            const TileEntry E = p.entries[T.first + c0 + lane];
+            const FrameJob& J = p.jobs[E.frame];
+            stride = J.wnx * n;
+            wb = reinterpret_cast<unsigned long long>(p.scratch + J.w_off[l]) +
+                 4ull * ((size_t)((E.rty - J.wy) * n) * stride + (size_t)((E.rtx - J.wx) * n));
+        }
+        const int m = min(32, T.count - c0);
+#pragma unroll 4
+        for (int i = 0; i < m; i++) {
+            const float* W;
+            int st;
+            if (uniform) {
+                W = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, wb, i));
+                st = __shfl_sync(0xffffffffu, stride, i);
+            } else {
+                const TileEntry E = p.entries[T.first + c0 + i];
+                const FrameJob& J = p.jobs[E.frame];
+                st = J.wnx * n;
+                W = reinterpret_cast<const float*>(p.scratch + J.w_off[l]) + (size_t)((E.rty - J.wy) * n) * st + (size_t)((E.rtx - J.wx) * n);
+            }
+            const float* qp = W + (size_t)py * st + px;
+            float s[4];
+            if (quad) {
+                float2 t0 = *reinterpret_cast<const float2*>(qp), t1 = *reinterpret_cast<const float2*>(qp + st);
+                s[0] = t0.x; s[1] = t0.y; s[2] = t1.x; s[3] = t1.y;
+            } else { s[0] = qp[0]; s[1] = s[2] = s[3] = -INFINITY; }
+            const unsigned cw = !(T.fresh && (c0 + i) == 0);
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if ((quad || k == 0) && s[k] >= bw[k]) { bw[k] = s[k]; best[k] = c0 + i; wins += cw; }   // '>=' : MultiBandMap2DCPU.cpp:542
+        }
+    }
+    if (!valid) { best[0] = best[1] = best[2] = best[3] = -1; wins = 0; }
+    if (p.stats) {
+        unsigned long long w = warp_sum(wins);
+        if (lane == 0 && w) atomicAdd(p.stats + l, w);
+    }
+    if (!valid) return;
+    // winner map: entry index inside the tile's list, 0xFFFF = the state stands
+    uint16_t* wm = p.wmap + (size_t)blockIdx.x * p.wmap_stride + lay.px_off[l] + to;
+    if (!quad) {
+        wm[0] = (uint16_t)(best[0] < 0 ? 0xFFFF : best[0]);
+        if (best[0] >= 0) tw[0] = bw[0];
+    } else {
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            const int k0 = 2 * r, k1 = 2 * r + 1;
+            *reinterpret_cast<ushort2*>(wm + (size_t)r * n) =
+                make_ushort2((unsigned short)(best[k0] < 0 ? 0xFFFF : best[k0]), (unsigned short)(best[k1] < 0 ? 0xFFFF : best[k1]));
+            float* wr = tw + (size_t)r * n;
+            if (best[k0] >= 0 && best[k1] >= 0) *reinterpret_cast<float2*>(wr) = make_float2(bw[k0], bw[k1]);
+            else if (best[k0] >= 0) wr[0] = bw[k0];
+            else if (best[k1] >= 0) wr[1] = bw[k1];
+        }
+    }
+    // cell flags of the winning frames (a 2x2 quad sits inside one cell while cells are >= 2 px, i.e. l <= 4)
+    size_t marked[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        marked[k] = ~(size_t)0;
+        if (best[k] < 0) continue;
+        const TileEntry E = p.entries[T.first + best[k]];
+        const FrameJob& J = p.jobs[E.frame];
+        int wpx = (E.rtx - J.wx) * n + px + (k & 1), wpy = (E.rty - J.wy) * n + py + (k >> 1);
+        size_t idx = cell_base(p, E.frame, l) + (size_t)((wpy << l) >> 5) * (J.wnx * 8) + ((wpx << l) >> 5);
+        bool dup = false;
+#pragma unroll
+        for (int k2 = 0; k2 < k; k2++) dup |= marked[k2] == idx;
+        marked[k] = idx;
+        if (!dup && !p.win[idx]) p.win[idx] = 1;
+    }
+}
+cudaError_t launch_mbs_decide(const GroupParams& p, const TileLayout& lay, cudaStream_t stream) {
+    if (p.n_tiles == 0) return cudaSuccess;
+    int quads = 0;
+    for (int l = 0; l < p.levels; l++) {
+        int n = kEle >> l, half = n > 1 ? n / 2 : 1;
+        quads += half * half;
+    }
+    dim3 g(p.n_tiles, (quads + 255) / 256);
+    mbs_decide_kernel<<<g, 256, 0, stream>>>(p, lay);
+    return cudaGetLastError();
+}
+
+// ---- 3. propagate: need[l] = win[l] | dilate3(win[l-1]) (Laplacian taps), then top-down need[l] |= dilate3(need[l+1]) ----
+__device__ __forceinline__ bool any3x3(const uint8_t* f, int cx, int cy, int cw, int ch) {
+    bool v = false;
+    for (int dy = -1; dy <= 1; dy++) {
+        int y = cy + dy;
+        if ((unsigned)y >= (unsigned)ch) continue;
+        for (int dx = -1; dx <= 1; dx++) {
+            int x = cx + dx;
+            if ((unsigned)x < (unsigned)cw) v |= f[y * cw + x] != 0;
+        }
+    }
+    return v;
+}
+__global__ void __launch_bounds__(256) mbs_propagate_kernel(const __grid_constant__ GroupParams p) {
+    const int f = blockIdx.x;
+    const FrameJob& J = p.jobs[f];
+    const int cw = J.wnx * 8, ch = J.wny * 8, nc = cw * ch;
+    for (int l = 0; l < p.levels; l++) {
+        const uint8_t* w = p.win + cell_base(p, f, l);
+        const uint8_t* wf = l > 0 ? p.win + cell_base(p, f, l - 1) : nullptr;
+        uint8_t* nd = p.need + cell_base(p, f, l);
+        for (int c = threadIdx.x; c < nc; c += blockDim.x) {
+            bool v = w[c] != 0;
+            if (!v && wf) { int cy = c / cw; v = any3x3(wf, c - cy * cw, cy, cw, ch); }
+            nd[c] = v ? 1 : 0;
+        }
+    }
+    __syncthreads();
+    for (int l = p.levels - 2; l >= 0; l--) {
+        const uint8_t* up = p.need + cell_base(p, f, l + 1);
+        uint8_t* nd = p.need + cell_base(p, f, l);
+        for (int c = threadIdx.x; c < nc; c += blockDim.x) {
+            if (nd[c]) continue;
+            int cy = c / cw;
+            if (any3x3(up, c - cy * cw, cy, cw, ch)) nd[c] = 1;
+        }
+        __syncthreads();
+    }
+}
+cudaError_t launch_mbs_propagate(const GroupParams& p, cudaStream_t stream) {
+    mbs_propagate_kernel<<<p.n_frames, 256, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// ---- 4a. image warp of the needed level-0 cells: one CTA = one 32 x 32 cell, one thread = 4 px ----
+__global__ void __launch_bounds__(256) mbs_warp_kernel(const __grid_constant__ GroupParams p) {
+    const FrameJob& J = p.jobs[blockIdx.y];
+    const int cw = J.wnx * 8, ch = J.wny * 8;
+    const int cy = blockIdx.x / cw, cx = blockIdx.x - cy * cw;
+    if (cy >= ch) return;
+    if (!p.need[cell_base(p, blockIdx.y, 0) + blockIdx.x]) return;
+    const int ww = J.wnx * kEle;
+    int u = cx * 32 + (threadIdx.x & 7) * 4, v = cy * 32 + (threadIdx.x >> 3);
+    int x = u + J.wx * kEle, y = v + J.wy * kEle;
+    double M[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) M[i] = J.hinv[i];
+    const RawSrc R = make_raw_src(J.raw, J.raw_stride, nullptr, p.sw, p.sh);
+    uint32_t g[4];
+    mb_sample4<false>(p, R, M, x, y, g, nullptr);
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint32_t*>(p.scratch + J.g_off[0]) + (size_t)v * ww + u) = make_uint4(g[0], g[1], g[2], g[3]);
+}
+cudaError_t launch_mbs_warp(const GroupParams& p, cudaStream_t stream) {
+    dim3 g(p.max_wnx * 8 * p.max_wny * 8, p.n_frames);
+    mbs_warp_kernel<<<g, 256, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// true when any cell under the output patch [u, u+nu) x [v, v+nv) of level L is needed
+__device__ __forceinline__ bool patch_needed(const uint8_t* need, int L, int u, int v, int nu, int nv, int cw, int ch) {
+    int cxa = (u << L) >> 5, cxb = min(((u + nu - 1) << L) >> 5, cw - 1), cya = (v << L) >> 5, cyb = min(((v + nv - 1) << L) >> 5, ch - 1);
+    bool any = false;
+    for (int cy = cya; cy <= cyb; cy++)
+        for (int cx = cxa; cx <= cxb; cx++) any |= need[cy * cw + cx] != 0;
+    return any;
+}
+
+// ---- 4b. image pyrDown l -> l+1 in needed cells.  One thread = 2 x 4 outputs; a warp = 16 x 16 outputs (one cell of level 1) ----
+__global__ void __launch_bounds__(256, 4) mbs_pyrdown_kernel(const __grid_constant__ GroupParams p, int l) {
+    const FrameJob& J = p.jobs[blockIdx.y];
+    const int ns = kEle >> l, nd = kEle >> (l + 1);
+    const int sww = J.wnx * ns, swh = J.wny * ns, srw = J.nx * ns, srh = J.ny * ns, sox = J.wx * ns, soy = J.wy * ns;
+    const int dww = J.wnx * nd, dwh = J.wny * nd, dox = J.wx * nd, doy = J.wy * nd;
+    const int bpr = (dww + 15) / 16;
+    int by = blockIdx.x / bpr, bx = blockIdx.x - by * bpr;
+    int u = (bx * 8 + threadIdx.x) * 2, v0 = (by * 32 + threadIdx.y) * 4;
+    if (u >= dww || v0 >= dwh) return;
+    if (!patch_needed(p.need + cell_base(p, blockIdx.y, l + 1), l + 1, u, v0, 2, 4, J.wnx * 8, J.wny * 8)) return;
+    const uint32_t* SG = reinterpret_cast<const uint32_t*>(p.scratch + J.g_off[l]);
+    uint32_t* DG = reinterpret_cast<uint32_t*>(p.scratch + J.g_off[l + 1]);
+    const bool two = (u + 1) < dww;
+    int U = u + dox;
+    int xs[7];
+    int c0 = 2 * U - 2 - sox;
+    const bool fast = (2 * U - 2 >= 0) && (2 * U + 4 < srw) && (c0 >= 0) && (c0 + 6 < sww);
+    if (fast) {
+#pragma unroll
+        for (int d = 0; d < 7; d++) xs[d] = c0 + d;
+    } else {
+#pragma unroll
+        for (int d = 0; d < 7; d++) xs[d] = clampi(reflect101_idx(2 * U + d - 2, srw) - sox, 0, sww - 1);
+    }
+    int V0 = v0 + doy;
+    uint32_t hb0[5], hg0[5], hb1[5], hg1[5];
+#pragma unroll
+    for (int r = 0; r < 11; r++) {
+        int ys = clampi(reflect101_idx(2 * V0 + r - 2, srh) - soy, 0, swh - 1);
+        const uint32_t* gr = SG + (size_t)ys * sww;
+        uint32_t e[7];
+        if (fast) {
+            const uint2* g2 = reinterpret_cast<const uint2*>(gr + xs[0]);
+            uint2 a = g2[0], b = g2[1], c = g2[2];
+            e[0] = a.x; e[1] = a.y; e[2] = b.x; e[3] = b.y; e[4] = c.x; e[5] = c.y; e[6] = gr[xs[0] + 6];
+        } else {
+#pragma unroll
+            for (int d = 0; d < 7; d++) e[d] = gr[xs[d]];
+        }
+        uint32_t br[7], g[7];
+#pragma unroll
+        for (int d = 0; d < 7; d++) { br[d] = e[d] & kM2; g[d] = (e[d] >> 8) & 0xFFu; }
+        hb0[r % 5] = br[2] * 6u + (br[1] + br[3]) * 4u + br[0] + br[4];
+        hb1[r % 5] = br[4] * 6u + (br[3] + br[5]) * 4u + br[2] + br[6];
+        hg0[r % 5] = g[2] * 6u + (g[1] + g[3]) * 4u + g[0] + g[4];
+        hg1[r % 5] = g[4] * 6u + (g[3] + g[5]) * 4u + g[2] + g[6];
+        if (r >= 4 && (r & 1) == 0) {
+            int k = (r - 4) >> 1, v = v0 + k;
+            if (v < dwh) {
+                const int i0 = (r - 4) % 5, i1 = (r - 3) % 5, i2 = (r - 2) % 5, i3 = (r - 1) % 5, i4 = r % 5;
+                uint32_t vbr0 = hb0[i0] + hb0[i4] + (hb0[i1] + hb0[i3]) * 4u + hb0[i2] * 6u;
+                uint32_t vbr1 = hb1[i0] + hb1[i4] + (hb1[i1] + hb1[i3]) * 4u + hb1[i2] * 6u;
+                uint32_t vg0 = hg0[i0] + hg0[i4] + (hg0[i1] + hg0[i3]) * 4u + hg0[i2] * 6u;
+                uint32_t vg1 = hg1[i0] + hg1[i4] + (hg1[i1] + hg1[i3]) * 4u + hg1[i2] * 6u;
+                uint32_t o0 = (((vbr0 + 0x00800080u) >> 8) & kM2) | (((vg0 + 128u) >> 8) << 8);
+                uint32_t o1 = (((vbr1 + 0x00800080u) >> 8) & kM2) | (((vg1 + 128u) >> 8) << 8);
+                size_t o = (size_t)v * dww + u;
+                if (two && !(dww & 1)) *reinterpret_cast<uint2*>(DG + o) = make_uint2(o0, o1);
+                else { DG[o] = o0; if (two) DG[o + 1] = o1; }
+            }
+        }
+    }
+}
+cudaError_t launch_mbs_pyrdown(const GroupParams& p, int level, cudaStream_t stream) {
+    int nd = kEle >> (level + 1);
+    int blocks = ((p.max_wnx * nd + 15) / 16) * ((p.max_wny * nd + 127) / 128);
+    dim3 b(8, 32), g(blocks, p.n_frames);
+    mbs_pyrdown_kernel<<<g, b, 0, stream>>>(p, level);
+    return cudaGetLastError();
+}
+
+// ---- 4c. image pyramid tail in needed cells ----
+__global__ void __launch_bounds__(1024) mbs_pyrtail_kernel(const __grid_constant__ GroupParams p, int l_first) {
+    const FrameJob& J = p.jobs[blockIdx.x];
+    const int cw = J.wnx * 8, ch = J.wny * 8;
+    for (int l = l_first; l + 1 < p.levels; l++) {
+        const int ns = kEle >> l, nd = kEle >> (l + 1);
+        const int sww = J.wnx * ns, swh = J.wny * ns, srw = J.nx * ns, srh = J.ny * ns, sox = J.wx * ns, soy = J.wy * ns;
+        const int dww = J.wnx * nd, dwh = J.wny * nd, dox = J.wx * nd, doy = J.wy * nd;
+        const uint32_t* SG = reinterpret_cast<const uint32_t*>(p.scratch + J.g_off[l]);
+        uint32_t* DG = reinterpret_cast<uint32_t*>(p.scratch + J.g_off[l + 1]);
+        const uint8_t* need = p.need + cell_base(p, blockIdx.x, l + 1);
+        for (int o = threadIdx.x; o < dww * dwh; o += blockDim.x) {
+            int v = o / dww, u = o - v * dww;
+            if (!patch_needed(need, l + 1, u, v, 1, 1, cw, ch)) continue;
+            int U = u + dox, V = v + doy;
+            int xs[5], ys[5];
+#pragma unroll
+            for (int d = 0; d < 5; d++) {
+                xs[d] = clampi(reflect101_idx(2 * U + d - 2, srw) - sox, 0, sww - 1);
+                ys[d] = clampi(reflect101_idx(2 * V + d - 2, srh) - soy, 0, swh - 1);
+            }
+            uint32_t hbr[5], hg[5];
+#pragma unroll
+            for (int r = 0; r < 5; r++) {
+                const uint32_t* gr = SG + (size_t)ys[r] * sww;
+                uint32_t a = gr[xs[0]], b = gr[xs[1]], c = gr[xs[2]], d = gr[xs[3]], e = gr[xs[4]];
+                hbr[r] = (c & kM2) * 6u + ((b & kM2) + (d & kM2)) * 4u + (a & kM2) + (e & kM2);
+                hg[r] = ((c >> 8) & 0xFFu) * 6u + (((b >> 8) & 0xFFu) + ((d >> 8) & 0xFFu)) * 4u + ((a >> 8) & 0xFFu) + ((e >> 8) & 0xFFu);
+            }
+            uint32_t vbr = hbr[0] + hbr[4] + (hbr[1] + hbr[3]) * 4u + hbr[2] * 6u;
+            uint32_t vg = hg[0] + hg[4] + (hg[1] + hg[3]) * 4u + hg[2] * 6u;
+            DG[o] = (((vbr + 0x00800080u) >> 8) & kM2) | (((vg + 128u) >> 8) << 8);
+        }
+        __syncthreads();
+    }
+}
+cudaError_t launch_mbs_pyrtail(const GroupParams& p, int l_first, cudaStream_t stream) {
+    mbs_pyrtail_kernel<<<p.n_frames, 1024, 0, stream>>>(p, l_first);
+    return cudaGetLastError();
+}
+
+// ---- 5. Laplacian of the winners (read from the winner map) into the tile state ----
+__global__ void __launch_bounds__(256, 4) mbs_lap_kernel(const __grid_constant__ GroupParams p, const __grid_constant__ TileLayout lay) {
+    const TileWork T = p.tiles[blockIdx.x];
+    int q = blockIdx.y * 256 + threadIdx.x;
+    int l = 0, n = kEle, half = kEle / 2;
+    for (; l < p.levels; l++) {
+        n = kEle >> l;
+        half = n > 1 ? n / 2 : 1;
+        int cnt = half * half;
+        if (q < cnt) break;
+        q -= cnt;
+    }
+    if (l >= p.levels) return;
+    const int qy = q / half, qx = q - qy * half;
+    const int py = qy * 2, px = qx * 2;
+    const bool quad = n > 1;
+    const size_t to = (size_t)py * n + px;
+    const uint16_t* wm = p.wmap + (size_t)blockIdx.x * p.wmap_stride + lay.px_off[l] + to;
+    int best[4] = {-1, -1, -1, -1};
+    if (quad) {
+        ushort2 a = *reinterpret_cast<const ushort2*>(wm), b = *reinterpret_cast<const ushort2*>(wm + n);
+        best[0] = a.x == 0xFFFF ? -1 : a.x; best[1] = a.y == 0xFFFF ? -1 : a.y;
+        best[2] = b.x == 0xFFFF ? -1 : b.x; best[3] = b.y == 0xFFFF ? -1 : b.y;
+    } else best[0] = wm[0] == 0xFFFF ? -1 : wm[0];
+    if (best[0] < 0 && best[1] < 0 && best[2] < 0 && best[3] < 0) return;
+    int lap[4][3];
+    bool done[4] = {best[0] < 0, best[1] < 0, best[2] < 0, best[3] < 0};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (done[k]) continue;
+        const int f = best[k];
+        const TileEntry E = p.entries[T.first + f];
+        int tmp[4][3];
+        lap_quad(p, p.jobs[E.frame], l, E.rtx * n + px, E.rty * n + py, quad, tmp);
+#pragma unroll
+        for (int k2 = k; k2 < 4; k2++)
+            if (!done[k2] && best[k2] == f) { lap[k2][0] = tmp[k2][0]; lap[k2][1] = tmp[k2][1]; lap[k2][2] = tmp[k2][2]; done[k2] = true; }
+    }
+    const size_t plane = (size_t)n * n;
+    int16_t* tl = reinterpret_cast<int16_t*>(T.state + lay.lap_off[l]) + to;
+    if (!quad) {
+        tl[0] = (int16_t)lap[0][0]; tl[plane] = (int16_t)lap[0][1]; tl[2 * plane] = (int16_t)lap[0][2];
+        return;
+    }
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const int k0 = 2 * r, k1 = 2 * r + 1;
+        int16_t* tr = tl + (size_t)r * n;
+        if (best[k0] >= 0 && best[k1] >= 0) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) *reinterpret_cast<short2*>(tr + c * plane) = make_short2((short)lap[k0][c], (short)lap[k1][c]);
+        } else if (best[k0] >= 0) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) tr[c * plane] = (int16_t)lap[k0][c];
+        } else if (best[k1] >= 0) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) tr[c * plane + 1] = (int16_t)lap[k1][c];
+        }
+    }
+}
+cudaError_t launch_mbs_lap(const GroupParams& p, const TileLayout& lay, cudaStream_t stream) {
+    if (p.n_tiles == 0) return cudaSuccess;
+    int quads = 0;
+    for (int l = 0; l < p.levels; l++) {
+        int n = kEle >> l, half = n > 1 ? n / 2 : 1;
+        quads += half * half;
+    }
+    dim3 g(p.n_tiles, (quads + 255) / 256);
+    mbs_lap_kernel<<<g, 256, 0, stream>>>(p, lay);
     return cudaGetLastError();
 }
 

@@ -52,6 +52,12 @@ struct GroupParams {
     uint8_t* scratch;          // multi-band: group scratch pyramid
     unsigned long long* stats; // optional counters (collect_stats)
     int max_wnx, max_wny;      // largest pyramid window of the group (tiles): grid bounds of per-frame kernels
+    // weights-first multi-band (kernels.cu "WEIGHTS-FIRST variant"): per (frame, level) cell flags and the winner map
+    uint8_t* win;              // [n_frames][levels][cells_max]: the frame wins a px of that cell at that level
+    uint8_t* need;             // same shape: the frame's Gaussian level must be valid in that cell
+    int cells_max;             // (max_wnx * 8) * (max_wny * 8)
+    uint16_t* wmap;            // [n_tiles][wmap_stride]: winning entry per pyramid px of the tile (0xFFFF = none)
+    int wmap_stride;           // >= TileLayout::px_off[levels], even
 };
 
 // Tile state layout in HBM (multi-band): for each level l (side n = 256>>l): B,G,R int16 planes then f32 weight.
@@ -90,6 +96,16 @@ cudaError_t launch_mb_warp_pyr(const GroupParams& p, cudaStream_t stream);  // w
 cudaError_t launch_mb_pyrdown(const GroupParams& p, int level /* src level */, cudaStream_t stream);
 cudaError_t launch_mb_pyrtail(const GroupParams& p, int l_first, cudaStream_t stream);
 cudaError_t launch_mb_select(const GroupParams& p, const TileLayout& lay, cudaStream_t stream);
+// weights-first multi-band variant
+cudaError_t launch_mbw_warp(const GroupParams& p, cudaStream_t stream);
+cudaError_t launch_mbw_pyrdown(const GroupParams& p, int level, cudaStream_t stream);
+cudaError_t launch_mbw_pyrtail(const GroupParams& p, int l_first, cudaStream_t stream);
+cudaError_t launch_mbs_decide(const GroupParams& p, const TileLayout& lay, cudaStream_t stream);
+cudaError_t launch_mbs_propagate(const GroupParams& p, cudaStream_t stream);
+cudaError_t launch_mbs_warp(const GroupParams& p, cudaStream_t stream);
+cudaError_t launch_mbs_pyrdown(const GroupParams& p, int level, cudaStream_t stream);
+cudaError_t launch_mbs_pyrtail(const GroupParams& p, int l_first, cudaStream_t stream);
+cudaError_t launch_mbs_lap(const GroupParams& p, const TileLayout& lay, cudaStream_t stream);
 cudaError_t launch_tile_copy(uint8_t* const* d_tiles, int n, uint8_t* buf, size_t tile_bytes, int to_buf, cudaStream_t stream);
 cudaError_t launch_bgra_paste(const PasteItem* d_items, int n_items, uint32_t* mosaic, int mosaic_w, cudaStream_t stream);
 cudaError_t launch_mosaic_paste(const PasteItem* d_items, int n_items, const TileLayout& lay, const MosaicSet& ms, cudaStream_t stream);

@@ -61,6 +61,7 @@ struct GroupCtx {
     cudaEvent_t copied = nullptr;     // host frames of the group have landed in d_raw (copy stream)
     cudaEvent_t staged = nullptr;     // order-independent stages (warp / pyramid) finished on `stage`
     cudaEvent_t done = nullptr;       // recorded after the group's last kernel
+    cudaEvent_t decided = nullptr;    // weights-first multi-band: winners + need flags of the group are known
     cudaStream_t stage = nullptr;     // per-context stream: stages of group g+1 overlap the select of group g
     bool busy = false;
     int frames = 0;
@@ -114,6 +115,9 @@ struct m2d_map {
 
     static constexpr int kMaxCtx = 8;
     int kCtx = 4;                   // group contexts in flight (M2D_CTX env overrides, for tuning)
+    bool weights_first = false;     // M2D_SPARSE=1: multi-band decides winners from the weight pyramids first, then warps and
+                                    // filters the image only where a winner needs it (kernels.cu "WEIGHTS-FIRST variant")
+    cudaStream_t decide_stream = nullptr;  // chain of the groups' decide stages (tile weights), ahead of the Laplacian chain
     bool fused_warp_pyr = false;    // M2D_FUSED=1: warp + first pyrDown in one shared-memory kernel (measured 7 % slower, kept for A/B)
     GroupCtx ctx[kMaxCtx];
     int ctx_next = 0;
@@ -171,11 +175,14 @@ int m2d_map::init() {
     CU(cudaMemsetAsync(d_stats, 0, 32 * sizeof(unsigned long long), stream));
     if (const char* e = getenv("M2D_CTX")) kCtx = std::max(2, std::min(atoi(e), (int)kMaxCtx));
     if (const char* e = getenv("M2D_FUSED")) fused_warp_pyr = atoi(e) != 0;
+    if (const char* e = getenv("M2D_SPARSE")) weights_first = atoi(e) != 0;
     CU(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&decide_stream, cudaStreamNonBlocking));
     for (int i = 0; i < kCtx; i++) {
         CU(cudaEventCreateWithFlags(&ctx[i].done, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ctx[i].copied, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ctx[i].staged, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx[i].decided, cudaEventDisableTiming));
         CU(cudaStreamCreateWithFlags(&ctx[i].stage, cudaStreamNonBlocking));
     }
     levels = (type == M2D_TYPE_MULTIBAND) ? band_num + 1 : 1;
@@ -201,6 +208,7 @@ void m2d_map::release() {
         if (c.done) cudaEventDestroy(c.done);
         if (c.copied) cudaEventDestroy(c.copied);
         if (c.staged) cudaEventDestroy(c.staged);
+        if (c.decided) cudaEventDestroy(c.decided);
         if (c.stage) { cudaStreamSynchronize(c.stage); cudaStreamDestroy(c.stage); }
         if (c.h_blob) cudaFreeHost(c.h_blob);
         if (c.d_blob) cudaFree(c.d_blob);
@@ -211,6 +219,7 @@ void m2d_map::release() {
     if (d_collapse) cudaFree(d_collapse);
     for (ProfRec& r : prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
+    if (decide_stream) { cudaStreamSynchronize(decide_stream); cudaStreamDestroy(decide_stream); }
     if (own_stream && stream) cudaStreamDestroy(stream);
 }
 
@@ -554,6 +563,17 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
     { size_t cap = c.blob_cap; int rc = grow((void**)&c.h_blob, &cap, blob, true); if (rc != M2D_OK) return rc;
       rc = grow((void**)&c.d_blob, &c.blob_cap, blob, false); if (rc != M2D_OK) return rc; }
     if (!on_device) { int rc = grow((void**)&c.d_raw, &c.raw_cap, (size_t)nj * npx * 3 + 256, false); if (rc != M2D_OK) return rc; }
+    // weights-first multi-band: cell flags (win | need) and the winner map live behind the pyramids
+    const bool sparse = weights_first && type == M2D_TYPE_MULTIBAND && levels <= 6 && !fused_warp_pyr && !tiles.empty();
+    const int cells_max = max_wnx * 8 * max_wny * 8;
+    const int wmap_stride = (lay.px_off[levels] + 7) & ~7;
+    size_t off_win = 0, off_need = 0, off_wmap = 0, flag_bytes = 0;
+    if (sparse) {
+        flag_bytes = ((size_t)nj * levels * cells_max + 255) & ~(size_t)255;
+        off_win = scratch; scratch += flag_bytes;
+        off_need = scratch; scratch += flag_bytes;
+        off_wmap = scratch; scratch += ((size_t)tiles.size() * wmap_stride * sizeof(uint16_t) + 255) & ~(size_t)255;
+    }
     if (scratch) { int rc = grow((void**)&c.d_scratch, &c.scratch_cap, scratch, false); if (rc != M2D_OK) return rc; }
 
     // ---- frames: host images are staged into HBM on the copy stream (this context's previous group has finished,
@@ -613,6 +633,10 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
     p.alpha = d_alpha; p.wimg = d_wimg; p.scratch = c.d_scratch;
     p.stats = cfg.collect_stats ? d_stats : nullptr;
     p.max_wnx = max_wnx; p.max_wny = max_wny;
+    if (sparse) {
+        p.win = c.d_scratch + off_win; p.need = c.d_scratch + off_need; p.cells_max = cells_max;
+        p.wmap = reinterpret_cast<uint16_t*>(c.d_scratch + off_wmap); p.wmap_stride = wmap_stride;
+    }
 
     // Order-independent stages run on the context's own stream (they overlap the previous group's select); the
     // order-dependent tile-centric stage runs on the handle's stream, which serialises groups in feed order.
@@ -622,7 +646,34 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
         CU(cudaEventRecord(c.staged, stream));
         CU(cudaStreamWaitEvent(c.stage, c.staged, 0));
     }
-    if (type == M2D_TYPE_MULTIBAND) {
+    if (sparse) {
+        // (a level goes to the tail only when its output is small: <= 16 K px per frame)
+        auto small_level = [&](int lv) { long long nd = kEle >> (lv + 1); return (long long)max_wnx * nd * max_wny * nd <= 16384; };
+        int l_tail = 0;
+        for (; l_tail + 1 < levels && (!small_level(l_tail) || levels - 1 - l_tail < 2); l_tail++) {}
+        // 1. weights only, dense, on the context's stream
+        CU(cudaMemsetAsync(p.win, 0, flag_bytes, c.stage));
+        LAUNCHKS(M2D_K_MB_WARP, c.stage, launch_mbw_warp(p, c.stage));
+        for (int l = 0; l < l_tail; l++) LAUNCHKS(M2D_K_MB_PYRDOWN, c.stage, launch_mbw_pyrdown(p, l, c.stage));
+        if (l_tail + 1 < levels) LAUNCHKS(M2D_K_MB_PYRTAIL, c.stage, launch_mbw_pyrtail(p, l_tail, c.stage));
+        CU(cudaEventRecord(c.staged, c.stage));
+        // 2.+3. winners and need flags: the decide chain serialises groups in feed order (tile weights only), and runs
+        // ahead of the Laplacian chain on the handle's stream (which writes the Laplacian planes only)
+        cudaStream_t ds = profiling ? stream : decide_stream;
+        CU(cudaStreamWaitEvent(ds, c.staged, 0));
+        LAUNCHKS(M2D_K_MB_SELECT, ds, launch_mbs_decide(p, lay, ds));
+        LAUNCHKS(M2D_K_MISC, ds, launch_mbs_propagate(p, ds));
+        CU(cudaEventRecord(c.decided, ds));
+        // 4. image work in the needed cells, back on the context's stream
+        CU(cudaStreamWaitEvent(c.stage, c.decided, 0));
+        LAUNCHKS(M2D_K_MB_WARP, c.stage, launch_mbs_warp(p, c.stage));
+        for (int l = 0; l < l_tail; l++) LAUNCHKS(M2D_K_MB_PYRDOWN, c.stage, launch_mbs_pyrdown(p, l, c.stage));
+        if (l_tail + 1 < levels) LAUNCHKS(M2D_K_MB_PYRTAIL, c.stage, launch_mbs_pyrtail(p, l_tail, c.stage));
+        CU(cudaEventRecord(c.staged, c.stage));
+        // 5. winners' Laplacians into the tiles, in feed order on the handle's stream
+        CU(cudaStreamWaitEvent(stream, c.staged, 0));
+        LAUNCHK(M2D_K_MB_SELECT, launch_mbs_lap(p, lay, stream));
+    } else if (type == M2D_TYPE_MULTIBAND) {
         // full-grid pyrDown while a level is big enough; the small deep levels go through one tail launch
         int l = 0;
         if (fused_warp_pyr && levels >= 2) {

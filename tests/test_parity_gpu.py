@@ -353,6 +353,41 @@ def test_fused_warp_pyramid_variant_is_bit_exact(monkeypatch):
         g.close()
 
 
+def test_weights_first_variant_is_bit_exact(monkeypatch):
+    """M2D_SPARSE=1 selects the weights-first multi-band pipeline (winners decided from the weight pyramids, image
+    warp/pyrDown only in the cells a winner's Laplacian needs).  Same bits as the oracle: jittered
+    and noisy frames, several groups, 1/3/5 bands, a sharded window, stats, and the dense fallback for 8 bands."""
+    import torch
+    monkeypatch.setenv("M2D_SPARSE", "1")
+    seq = synth.Sequence(14, 320, 180, seed=29, jitter=True, noise=True, fpl=4, prepare_frames=4)
+    dev = torch.from_numpy(seq.frames()).cuda()
+    for kw in ({}, {"band_number": 3}, {"band_number": 1}, {"band_number": 8}, {"collect_stats": 1},
+               {"shard_rank": 1, "shard_count": 2, "shard_axis": 0, "shard_span": 1}):
+        g = m2d.Map2D.create(3, thread=False, batch_frames=5, **kw)
+        o = O.OracleMap2D.create(3, **kw)
+        assert g.prepare(seq.plane, seq.camera, seq.prepare_poses) and o.prepare(seq.plane, seq.camera, seq.prepare_poses)
+        res = g.feed_batch(dev.data_ptr(), seq.n, seq.w * seq.h * 3, seq.w, seq.h, seq.w * 3, seq.poses, True)
+        for k in range(seq.n):
+            assert (res[k] == 0) == o.feed(seq.frame(k), seq.poses[k])
+        g.sync()
+        compare_state(g, o, 3)
+        if kw.get("collect_stats"):
+            assert g.stats()["win_px"] == o.stats()["win_px"]
+        g.close()
+    # a realistic overlap pattern at full tile scale: 720p serpentine prefix, two groups
+    seq = synth.Sequence(24, 1280, 720, seed=2, fpl=6, prepare_frames=6)
+    dev = torch.from_numpy(seq.frames()).cuda()
+    g = m2d.Map2D.create(3, thread=False, batch_frames=16)
+    o = O.OracleMap2D.create(3)
+    assert g.prepare(seq.plane, seq.camera, seq.prepare_poses) and o.prepare(seq.plane, seq.camera, seq.prepare_poses)
+    g.feed_batch(dev.data_ptr(), seq.n, seq.w * seq.h * 3, seq.w, seq.h, seq.w * 3, seq.poses, True)
+    for k in range(seq.n):
+        assert o.feed(seq.frame(k), seq.poses[k])
+    g.sync()
+    compare_state(g, o, 3)
+    g.close()
+
+
 def test_ties_keep_reference_order():
     """Exact weight ties: the same frame fed twice.  Weighted keeps the first ('<'), multi-band takes the last
     ('>=') -- observable through the win counters; state must stay identical to the oracle either way."""
