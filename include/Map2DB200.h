@@ -12,6 +12,8 @@
  *   Map2D::feed(img,pose)                    -> m2d_feed           (Map2D.h:91,  Map2DCPU.cpp:127-148)
  *   Map2D::save(filename)                    -> m2d_save           (Map2D.h:95,  Map2DCPU.cpp:523-564)
  *   Map2D::queueSize()                       -> m2d_queue_size     (Map2D.h:97)
+ *   thread=true (Map2DCPU.cpp:119-120,139-142,397-413: worker thread + frame queue of 20, drop-oldest)
+ *                                            -> m2d_ingest_open(20) at prepare(), feed() = m2d_ingest_push
  *   Map2D::draw()                            -> no-op (GL is out of scope); its data path is m2d_poll_changed +
  *                                               m2d_get_tile_image: changed tiles and their blended textures
  */
@@ -31,7 +33,7 @@ class Map2DB200 : public Map2D {
 public:
     /* type: Map2D::TypeCPU / TypeGPU (weighted) or TypeMultiBandCPU.  The svar keys the CPU classes read
      * (Map2DCPU.cpp:75,246; MultiBandMap2DCPU.cpp:228,235,260,444,840) are copied into the config once. */
-    explicit Map2DB200(int type, bool thread = true, int device = 0) : _h(NULL) {
+    explicit Map2DB200(int type, bool thread = true, int device = 0) : _h(NULL), _thread(thread) {
         m2d_config cfg;
         m2d_config_default(&cfg);
         cfg.scale = svar.GetDouble("Map2D.Scale", 1);
@@ -56,7 +58,11 @@ public:
         size_t i = 0;
         for (std::deque<std::pair<cv::Mat, pi::SE3d> >::const_iterator it = frames.begin(); it != frames.end(); ++it, ++i)
             pose7(it->second, &poses[7 * i]);
-        return m2d_prepare(_h, p, cam, (int)frames.size(), poses.empty() ? NULL : &poses[0]) == M2D_OK;
+        if (m2d_prepare(_h, p, cam, (int)frames.size(), poses.empty() ? NULL : &poses[0]) != M2D_OK) return false;
+        /* thread=true: the reference starts its worker here (Map2DCPU.cpp:119-120); its frame queue holds 20 and
+         * drops the oldest beyond that (:139-142).  A second prepare() keeps the queue that is already open. */
+        if (_thread) { m2d_ingest_close(_h); return m2d_ingest_open(_h, 20, 0) == M2D_OK; }
+        return true;
     }
 
     /* pose is camera-to-world; the library left-multiplies plane^-1 like Map2DCPU.cpp:136. */
@@ -68,18 +74,25 @@ public:
         }
         double p[7];
         pose7(pose, p);
+        if (_thread) return m2d_ingest_push(_h, img.data, img.cols, img.rows, img.step, 3, p) == M2D_OK;  /* enqueue only */
         return m2d_feed(_h, img.data, img.cols, img.rows, img.step, p) == M2D_OK;
     }
 
     virtual void draw() {}
 
-    virtual bool save(const std::string& filename) { return _h && m2d_save(_h, filename.c_str()) == M2D_OK; }
+    /* thread=true: frames still queued are fused first (the reference would save without them). */
+    virtual bool save(const std::string& filename) {
+        if (!_h) return false;
+        if (_thread) m2d_ingest_drain(_h);
+        return m2d_save(_h, filename.c_str()) == M2D_OK;
+    }
 
     virtual uint queueSize() { return _h ? (uint)m2d_queue_size(_h) : 0; }
 
     /* Addition over the reference: the saved image in memory, BGRA (weighted) or BGR. */
     cv::Mat getImage(int* tile_min_x = NULL, int* tile_min_y = NULL) {
         int w, h, cn, tx, ty;
+        if (_h && _thread) m2d_ingest_drain(_h);
         if (!_h || m2d_get_image(_h, NULL, &w, &h, &cn, &tx, &ty) != M2D_OK) return cv::Mat();
         cv::Mat out(h, w, cn == 4 ? CV_8UC4 : CV_8UC3);
         if (m2d_get_image(_h, out.data, &w, &h, &cn, &tx, &ty) != M2D_OK) return cv::Mat();
@@ -97,6 +110,7 @@ private:
         o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = r.x; o[4] = r.y; o[5] = r.z; o[6] = r.w;
     }
     m2d_handle _h;
+    bool _thread;
     Map2DB200(const Map2DB200&);
     Map2DB200& operator=(const Map2DB200&);
 };

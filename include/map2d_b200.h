@@ -150,7 +150,9 @@ int m2d_last_rect(m2d_handle h, int rect[4]);
 int m2d_get_tile(m2d_handle h, int tx, int ty, int level, void* data, float* weight);
 /* In-memory save(): bbox of touched tiles. Call with out == NULL to get the geometry, then with a buffer of
  * w*h*channels bytes. Weighted -> 4 channels BGRA (untouched tiles zero); multi-band -> 3 channels BGR,
- * collapsed, background where weight[0]==0. */
+ * collapsed, background where weight[0]==0.  While an ingest queue is open the map can grow between the two
+ * calls: the second call then reads *w, *h_px, *channels (as left by the first) as the capacity of `out` and returns
+ * M2D_ERR_STATE instead of overrunning it — query again. */
 int m2d_get_image(m2d_handle h, uint8_t* out, int* w, int* h_px, int* channels, int* tile_min_x,
                   int* tile_min_y);
 /* Map2D::save — writes the same image as a PNG (8-bit BGRA/BGR stored as RGBA/RGB). */
@@ -195,6 +197,25 @@ uint64_t m2d_launch_count(m2d_handle h);
 enum { M2D_K_WEIGHTED = 0, M2D_K_MB_WARP = 1, M2D_K_MB_PYRDOWN = 2, M2D_K_MB_SELECT = 3, M2D_K_COLLAPSE = 4, M2D_K_MISC = 5, M2D_K_MB_PYRTAIL = 6 };
 int m2d_profile(m2d_handle h, int enable);
 int m2d_get_kernel_times(m2d_handle h, double* ms /* M2D_KERNEL_CLASSES */, uint64_t* count /* M2D_KERNEL_CLASSES */);
+
+/* Ingest seam — the step in front of feed().  In the reference the tracker thread converts each
+ * frame BGRA -> BGR (GSLAM-DIYSLAM/src/zhaoyong/TrackerOpt.cpp:374-383) and hands (image, pose) over through a bounded
+ * queue that DROPS THE OLDEST entry when full (src/DataTrans.h:54-68, capacity 30; Map2DCPU's own thread=true queue does
+ * the same with capacity 20, Map2DCPU.cpp:139-142,397-413).  m2d_ingest_open (after m2d_prepare) allocates a ring of
+ * pinned BGR8 slots and starts one worker thread that pops the queue in order and feeds it in grouped launches.
+ * m2d_ingest_push copies (channels 3 = BGR) or converts (channels 4 = BGRA) the caller's pixels into a slot and
+ * returns at once — the caller's buffer is free again; it never blocks, a full queue loses its oldest frame.  Returns
+ * M2D_REJECTED for a frame whose size is not the camera's.  push may be called from any thread; while ingest is open
+ * every other call on the handle is serialised with the worker.  m2d_queue_size counts queued frames too.
+ * pause(1) holds the worker (frames keep queueing/dropping), drain blocks until everything queued has been fused,
+ * close drains, joins the worker and frees the ring (m2d_destroy closes implicitly). */
+int m2d_ingest_open(m2d_handle h, int capacity, int start_paused);
+int m2d_ingest_push(m2d_handle h, const uint8_t* pixels, int w, int h_px, size_t stride, int channels,
+                    const double pose_c2w[7]);
+int m2d_ingest_pause(m2d_handle h, int paused);
+int m2d_ingest_drain(m2d_handle h);
+int m2d_ingest_close(m2d_handle h);
+int m2d_ingest_stats(m2d_handle h, uint64_t* pushed, uint64_t* dropped, uint64_t* fed, uint64_t* fused);
 
 /* Pinned host staging helpers for callers that want truly asynchronous m2d_feed(). */
 void* m2d_alloc_host(size_t bytes);

@@ -13,8 +13,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <deque>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/map2d_b200.h"
@@ -55,6 +58,12 @@ using namespace m2d;
 
 struct ProfRec { int kind; cudaEvent_t e0, e1; };
 
+// While an ingest worker exists it shares the handle with the caller's threads: every entry point then serialises on
+// the handle's mutex (no cost otherwise; a handle without ingest stays single-threaded by contract).
+#define API_LOCK(h)                                         \
+    std::unique_lock<std::recursive_mutex> api_lk_;         \
+    if ((h) && (h)->ingest) api_lk_ = std::unique_lock<std::recursive_mutex>((h)->api)
+
 // Device + pinned buffers of one in-flight group.  Two contexts alternate so that the host can prepare group g+1
 // (bounds, tile allocation, work lists, H2D copies) while the GPU fuses group g.
 struct GroupCtx {
@@ -73,6 +82,24 @@ struct GroupCtx {
     uint8_t* d_scratch = nullptr;     // multi-band pyramids of the group
     size_t scratch_cap = 0;
 };
+
+// Ingest seam: bounded drop-oldest frame queue in front of feed(), pinned slots, one worker thread.
+struct IngestItem { int slot; double pose[7]; };
+struct Ingest {
+    std::mutex mu;
+    std::condition_variable cv, cv_idle;
+    std::deque<IngestItem> q;          // frames waiting, oldest first
+    std::vector<int> free_slots;
+    uint8_t* ring = nullptr;           // pinned: n_slots x slot_bytes of packed BGR8
+    size_t slot_bytes = 0;
+    int capacity = 0, n_slots = 0, w = 0, h = 0;
+    bool paused = false, stop = false, busy = false;
+    uint64_t pushed = 0, dropped = 0, fed = 0, fused = 0;
+    int last_rc = M2D_OK;
+    std::thread worker;
+};
+constexpr int kIngestBatch = 16;       // frames the worker hands to feed() at once
+constexpr int kIngestSpare = 4;        // slots for producers that are mid-copy
 
 struct m2d_map {
     int type = 0;
@@ -122,6 +149,9 @@ struct m2d_map {
     GroupCtx ctx[kMaxCtx];
     int ctx_next = 0;
 
+    Ingest* ingest = nullptr;
+    std::recursive_mutex api;       // serialises the ingest worker with API calls (taken only while ingest is open)
+
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaStream_t copy_stream = nullptr;  // H2D staging of host frames overlaps the previous group's kernels
@@ -133,10 +163,11 @@ struct m2d_map {
     void release();
     int prepare(const double* plane, const double* cam, int n, const double* poses);
     int spread(double xmin, double ymin, double xmax, double ymax);
+    // frame i = ptrs ? ptrs[i] : base + i * frame_stride
     int feed_frames(int n, const uint8_t* base, size_t frame_stride, int w, int h, size_t stride, const double* poses,
-                    bool on_device, int* result);
+                    bool on_device, int* result, const uint8_t* const* ptrs = nullptr);
     int run_group(int n, const uint8_t* base, size_t frame_stride, int w, int h, size_t stride, const double* poses,
-                  bool on_device, int* result);
+                  bool on_device, int* result, const uint8_t* const* ptrs);
     int ensure_weight_images(int w, int h);
     int alloc_tile(uint8_t** out);
     int reserve_tiles(size_t n);
@@ -419,13 +450,13 @@ int m2d_map::reset() {
 }
 
 int m2d_map::feed_frames(int n, const uint8_t* base, size_t frame_stride, int w, int h, size_t stride, const double* poses,
-                         bool on_device, int* result) {
+                         bool on_device, int* result, const uint8_t* const* ptrs) {
     if (!valid) {                                         // Map2DCPU.cpp:129
         stats.frames_fed += n;
         for (int i = 0; i < n && result; i++) result[i] = M2D_REJECTED;
         return M2D_REJECTED;
     }
-    if (!base || !poses) return M2D_ERR_ARG;
+    if ((!base && !ptrs) || !poses) return M2D_ERR_ARG;
     if (w != g.cam_w || h != g.cam_h) {                   // Map2DCPU.cpp:158-162
         fprintf(stderr, "Map2DB200::renderFrame: frame size != camera size\n");
         stats.frames_fed += n;
@@ -439,8 +470,8 @@ int m2d_map::feed_frames(int n, const uint8_t* base, size_t frame_stride, int w,
     int worst = M2D_OK;
     for (int i = 0; i < n; i += K) {
         int m = std::min(K, n - i);
-        int rc = run_group(m, base + (size_t)i * frame_stride, frame_stride, w, h, stride, poses + 7 * (size_t)i, on_device,
-                           result ? result + i : nullptr);
+        int rc = run_group(m, ptrs ? nullptr : base + (size_t)i * frame_stride, frame_stride, w, h, stride, poses + 7 * (size_t)i,
+                           on_device, result ? result + i : nullptr, ptrs ? ptrs + i : nullptr);
         if (rc < 0) return rc;
         if (rc != M2D_OK) worst = rc;
     }
@@ -449,7 +480,7 @@ int m2d_map::feed_frames(int n, const uint8_t* base, size_t frame_stride, int w,
 
 // One group: feed() semantics for frames [0,n) in order (Map2DCPU.cpp:127-336 / MultiBandMap2DCPU.cpp:288-558).
 int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, int h, size_t stride, const double* poses,
-                       bool on_device, int* result) {
+                       bool on_device, int* result, const uint8_t* const* ptrs) {
     GroupCtx& c = ctx[ctx_next];
     ctx_next = (ctx_next + 1) % kCtx;
     if (c.busy) { CU(cudaEventSynchronize(c.done)); c.busy = false; }
@@ -578,9 +609,9 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
 
     // ---- frames: host images are staged into HBM on the copy stream (this context's previous group has finished,
     // so d_raw is free; the copy overlaps the OTHER context's kernels); device images are used in place
-    const bool tight = stride == (size_t)w * 3 && frame_stride == npx * 3;  // frames back to back: copy runs, not frames
+    const bool tight = !ptrs && stride == (size_t)w * 3 && frame_stride == npx * 3;  // frames back to back: copy runs, not frames
     for (int j = 0; j < nj; j++) {
-        const uint8_t* src = base + (size_t)src_index[j] * frame_stride;
+        const uint8_t* src = ptrs ? ptrs[src_index[j]] : base + (size_t)src_index[j] * frame_stride;
         if (on_device) { jobs[j].raw = src; jobs[j].raw_stride = (int)stride; }
         else {
             uint8_t* dst = c.d_raw + (size_t)j * npx * 3;
@@ -813,22 +844,26 @@ int m2d_create(int type, const m2d_config* cfg, m2d_handle* out) {
 
 void m2d_destroy(m2d_handle h) {
     if (!h) return;
+    m2d_ingest_close(h);
     h->release();
     delete h;
 }
 
 int m2d_prepare(m2d_handle h, const double* plane, const double* camera, int n, const double* poses) {
+    API_LOCK(h);
     if (!h || !plane || !camera) return M2D_ERR_ARG;
     return h->prepare(plane, camera, n, poses);
 }
 
 int m2d_feed(m2d_handle h, const uint8_t* bgr, int w, int hpx, size_t stride, const double* pose) {
+    API_LOCK(h);
     if (!h) return M2D_ERR_ARG;
     int r = M2D_REJECTED;
     int rc = h->feed_frames(1, bgr, 0, w, hpx, stride, pose, false, &r);
     return rc < 0 ? rc : r;
 }
 int m2d_feed_device(m2d_handle h, const uint8_t* d_bgr, int w, int hpx, size_t stride, const double* pose) {
+    API_LOCK(h);
     if (!h) return M2D_ERR_ARG;
     int r = M2D_REJECTED;
     int rc = h->feed_frames(1, d_bgr, 0, w, hpx, stride, pose, true, &r);
@@ -836,6 +871,7 @@ int m2d_feed_device(m2d_handle h, const uint8_t* d_bgr, int w, int hpx, size_t s
 }
 int m2d_feed_batch(m2d_handle h, int n, const uint8_t* base, size_t frame_stride, int w, int hpx, size_t stride,
                    const double* poses, int on_device, int* result) {
+    API_LOCK(h);
     if (!h || n < 0) return M2D_ERR_ARG;
     if (n == 0) return M2D_OK;  // empty batch: nothing to do
     if (!base || !poses) return M2D_ERR_ARG;
@@ -844,6 +880,7 @@ int m2d_feed_batch(m2d_handle h, int n, const uint8_t* base, size_t frame_stride
 }
 
 int m2d_feed_poses(m2d_handle h, int n, const double* poses, int* result) {
+    API_LOCK(h);
     if (!h || n < 0) return M2D_ERR_ARG;
     if (n == 0) return M2D_OK;
     if (!poses) return M2D_ERR_ARG;
@@ -880,6 +917,7 @@ int m2d_feed_poses(m2d_handle h, int n, const double* poses, int* result) {
 }
 
 int m2d_plan_rects(m2d_handle h, int n, const double* poses, int* rects) {
+    API_LOCK(h);
     if (!h || n < 0 || (n && (!poses || !rects))) return M2D_ERR_ARG;
     if (!h->valid) return M2D_ERR_STATE;
     GridGeom g = h->g;   // dry run on a copy: the map itself is not touched
@@ -904,6 +942,7 @@ int m2d_plan_rects(m2d_handle h, int n, const double* poses, int* rects) {
 }
 
 int m2d_set_shard(m2d_handle h, int rank, int count, int axis, int span, int origin) {
+    API_LOCK(h);
     if (!h || count < 1 || rank < 0 || rank >= count || (axis != 0 && axis != 1) || span < 1) return M2D_ERR_ARG;
     if (h->tiles_in_use != 0) { h->err = "m2d_set_shard: the map already holds tiles"; return M2D_ERR_STATE; }
     h->cfg.shard_rank = rank; h->cfg.shard_count = count; h->cfg.shard_axis = axis; h->cfg.shard_span = span;
@@ -911,9 +950,183 @@ int m2d_set_shard(m2d_handle h, int rank, int count, int axis, int span, int ori
     return M2D_OK;
 }
 
-int m2d_sync(m2d_handle h) { return h ? h->sync() : M2D_ERR_ARG; }
-int m2d_queue_size(m2d_handle h) { return h ? h->queue_size() : 0; }
+
+// ---------------------------------------------------------------------------------------------------------
+// Ingest seam — SURVEY.md §8(f) N4.  In the reference the tracker thread converts the frame BGRA -> BGR
+// (GSLAM-DIYSLAM/src/zhaoyong/TrackerOpt.cpp:374-383) and hands (image, pose) to Map2DFusion through a bounded queue
+// that drops the OLDEST entry when full (src/DataTrans.h:54-68, capacity 30); Map2DCPU's own worker queue behaves the
+// same with capacity 20 (Map2DCPU.cpp:139-142).  Here: m2d_ingest_push() copies/converts into a pinned slot and never
+// blocks; one worker thread pops up to kIngestBatch frames at a time and feeds them in order (grouped launches).
+// ---------------------------------------------------------------------------------------------------------
+static void ingest_worker(m2d_map* m) {
+    Ingest& I = *m->ingest;
+    std::vector<IngestItem> batch;
+    std::vector<const uint8_t*> ptrs;
+    std::vector<double> poses;
+    std::vector<int> res;
+    for (;;) {
+        {
+            std::unique_lock<std::mutex> lk(I.mu);
+            I.cv.wait(lk, [&] { return I.stop || (!I.paused && !I.q.empty()); });
+            if (I.paused || I.q.empty()) {
+                if (I.stop) break;
+                continue;
+            }
+            batch.clear();
+            while (!I.q.empty() && (int)batch.size() < kIngestBatch) { batch.push_back(I.q.front()); I.q.pop_front(); }
+            I.busy = true;
+        }
+        ptrs.resize(batch.size()); poses.resize(batch.size() * 7); res.assign(batch.size(), M2D_REJECTED);
+        for (size_t i = 0; i < batch.size(); i++) {
+            ptrs[i] = I.ring + (size_t)batch[i].slot * I.slot_bytes;
+            memcpy(&poses[7 * i], batch[i].pose, sizeof(double) * 7);
+        }
+        int rc, fused = 0;
+        {
+            std::lock_guard<std::recursive_mutex> g(m->api);
+            rc = m->feed_frames((int)batch.size(), nullptr, 0, I.w, I.h, (size_t)I.w * 3, poses.data(), false, res.data(), ptrs.data());
+            int rs = m->sync();   // the slots are read by DMA until here
+            if (rc >= 0 && rs < 0) rc = rs;
+        }
+        for (int r : res) fused += r == M2D_OK;
+        {
+            std::lock_guard<std::mutex> lk(I.mu);
+            for (const IngestItem& b : batch) I.free_slots.push_back(b.slot);
+            I.fed += batch.size();
+            I.fused += (uint64_t)fused;
+            if (rc < 0) I.last_rc = rc;
+            I.busy = false;
+        }
+        I.cv_idle.notify_all();
+    }
+}
+
+int m2d_ingest_open(m2d_handle h, int capacity, int start_paused) {
+    if (!h || capacity < 1 || capacity > 4096) return M2D_ERR_ARG;
+    if (h->ingest) return M2D_ERR_STATE;
+    if (!h->valid) { h->err = "m2d_ingest_open: prepare() first (the frame size comes from the camera)"; return M2D_ERR_STATE; }
+    if (cudaSetDevice(h->cfg.device) != cudaSuccess) return M2D_ERR_CUDA;
+    Ingest* I = new Ingest();
+    I->capacity = capacity; I->w = (int)h->g.cam_w; I->h = (int)h->g.cam_h;
+    I->slot_bytes = ((size_t)I->w * I->h * 3 + 255) & ~(size_t)255;
+    I->n_slots = capacity + kIngestBatch + kIngestSpare;
+    if (cudaHostAlloc((void**)&I->ring, I->slot_bytes * I->n_slots, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        delete I;
+        h->err = "m2d_ingest_open: pinned ring allocation failed";
+        return M2D_ERR_NOMEM;
+    }
+    for (int i = I->n_slots - 1; i >= 0; i--) I->free_slots.push_back(i);
+    I->paused = start_paused != 0;
+    h->ingest = I;
+    I->worker = std::thread(ingest_worker, h);
+    return M2D_OK;
+}
+
+int m2d_ingest_push(m2d_handle h, const uint8_t* pixels, int w, int hpx, size_t stride, int channels, const double* pose) {
+    if (!h || !pixels || !pose || (channels != 3 && channels != 4)) return M2D_ERR_ARG;
+    Ingest* I = h->ingest;
+    if (!I) return M2D_ERR_STATE;
+    if (w != I->w || hpx != I->h) {                       // Map2DCPU.cpp:158-162, rejected at the seam already
+        fprintf(stderr, "Map2DB200::ingest: frame size != camera size\n");
+        return M2D_REJECTED;
+    }
+    if (stride < (size_t)w * channels) return M2D_ERR_ARG;
+    int slot = -1;
+    {
+        std::lock_guard<std::mutex> lk(I->mu);
+        if (I->stop) return M2D_ERR_STATE;
+        while ((int)I->q.size() >= I->capacity || (I->free_slots.empty() && !I->q.empty())) {   // DataTrans.h:57-64: drop the oldest
+            I->free_slots.push_back(I->q.front().slot);
+            I->q.pop_front();
+            I->dropped++;
+        }
+        if (I->free_slots.empty()) return M2D_ERR_STATE;  // more than kIngestSpare producers mid-copy
+        slot = I->free_slots.back();
+        I->free_slots.pop_back();
+    }
+    uint8_t* dst = I->ring + (size_t)slot * I->slot_bytes;
+    for (int y = 0; y < hpx; y++) {
+        const uint8_t* s = pixels + (size_t)y * stride;
+        uint8_t* d = dst + (size_t)y * w * 3;
+        if (channels == 3) memcpy(d, s, (size_t)w * 3);
+        else for (int x = 0; x < w; x++) { d[3 * x] = s[4 * x]; d[3 * x + 1] = s[4 * x + 1]; d[3 * x + 2] = s[4 * x + 2]; }  // CV_BGRA2BGR
+    }
+    {
+        std::lock_guard<std::mutex> lk(I->mu);
+        IngestItem it;
+        it.slot = slot;
+        memcpy(it.pose, pose, sizeof it.pose);
+        I->q.push_back(it);
+        I->pushed++;
+    }
+    I->cv.notify_one();
+    return M2D_OK;
+}
+
+int m2d_ingest_pause(m2d_handle h, int paused) {
+    if (!h) return M2D_ERR_ARG;
+    Ingest* I = h->ingest;
+    if (!I) return M2D_ERR_STATE;
+    { std::lock_guard<std::mutex> lk(I->mu); I->paused = paused != 0; }
+    I->cv.notify_all();
+    return M2D_OK;
+}
+
+int m2d_ingest_drain(m2d_handle h) {
+    if (!h) return M2D_ERR_ARG;
+    Ingest* I = h->ingest;
+    if (!I) return M2D_OK;
+    std::unique_lock<std::mutex> lk(I->mu);
+    if (I->paused) { h->err = "m2d_ingest_drain: the queue is paused"; return M2D_ERR_STATE; }
+    I->cv_idle.wait(lk, [&] { return I->q.empty() && !I->busy; });
+    return I->last_rc < 0 ? I->last_rc : M2D_OK;
+}
+
+int m2d_ingest_close(m2d_handle h) {
+    if (!h) return M2D_ERR_ARG;
+    Ingest* I = h->ingest;
+    if (!I) return M2D_OK;
+    { std::lock_guard<std::mutex> lk(I->mu); I->paused = false; I->stop = true; }   // the worker drains what is queued, then exits
+    I->cv.notify_all();
+    if (I->worker.joinable()) I->worker.join();
+    int rc = I->last_rc;
+    {
+        std::lock_guard<std::recursive_mutex> g(h->api);
+        h->ingest = nullptr;
+    }
+    cudaSetDevice(h->cfg.device);
+    cudaFreeHost(I->ring);
+    delete I;
+    return rc < 0 ? rc : M2D_OK;
+}
+
+int m2d_ingest_stats(m2d_handle h, uint64_t* pushed, uint64_t* dropped, uint64_t* fed, uint64_t* fused) {
+    if (!h) return M2D_ERR_ARG;
+    Ingest* I = h->ingest;
+    if (!I) return M2D_ERR_STATE;
+    std::lock_guard<std::mutex> lk(I->mu);
+    if (pushed) *pushed = I->pushed;
+    if (dropped) *dropped = I->dropped;
+    if (fed) *fed = I->fed;
+    if (fused) *fused = I->fused;
+    return M2D_OK;
+}
+
+int m2d_sync(m2d_handle h) { API_LOCK(h); return h ? h->sync() : M2D_ERR_ARG; }
+int m2d_queue_size(m2d_handle h) {
+    if (!h) return 0;
+    int q = 0;
+    if (Ingest* I = h->ingest) {   // frames still queued or in the worker's hands count as "not yet rendered" (Map2D.h:97)
+        std::lock_guard<std::mutex> lk(I->mu);
+        q = (int)I->q.size();
+        if (I->busy) return q + 1;   // the worker holds the handle: do not wait for it, report its batch as one pending unit
+    }
+    API_LOCK(h);
+    return q + h->queue_size();
+}
 int m2d_set_stream(m2d_handle h, void* s) {
+    API_LOCK(h);
     if (!h) return M2D_ERR_ARG;
     cudaSetDevice(h->cfg.device);
     cudaStreamSynchronize(h->stream);
@@ -927,9 +1140,10 @@ int m2d_set_stream(m2d_handle h, void* s) {
     }
     return M2D_OK;
 }
-int m2d_reset(m2d_handle h) { return h ? h->reset() : M2D_ERR_ARG; }
+int m2d_reset(m2d_handle h) { API_LOCK(h); return h ? h->reset() : M2D_ERR_ARG; }
 
 int m2d_get_grid(m2d_handle h, int* w, int* ht, double* mn, double* mx, double* lp) {
+    API_LOCK(h);
     if (!h) return M2D_ERR_ARG;
     if (!h->valid) return M2D_ERR_STATE;
     if (w) *w = h->g.w;
@@ -940,12 +1154,14 @@ int m2d_get_grid(m2d_handle h, int* w, int* ht, double* mn, double* mx, double* 
     return M2D_OK;
 }
 int m2d_last_rect(m2d_handle h, int* rect) {
+    API_LOCK(h);
     if (!h || !rect) return M2D_ERR_ARG;
     memcpy(rect, h->last_rect, sizeof(int) * 4);
     return M2D_OK;
 }
 
 int m2d_get_tile(m2d_handle h, int tx, int ty, int level, void* data, float* weight) {
+    API_LOCK(h);
     if (!h || !data) return M2D_ERR_ARG;
     m2d_map& m = *h;
     std::string& err = m.err;
@@ -971,11 +1187,22 @@ int m2d_get_tile(m2d_handle h, int tx, int ty, int level, void* data, float* wei
 }
 
 int m2d_get_image(m2d_handle h, uint8_t* out, int* w, int* hpx, int* channels, int* tmx, int* tmy) {
+    API_LOCK(h);
     if (!h || !w || !hpx || !channels || !tmx || !tmy) return M2D_ERR_ARG;
+    if (out && h->ingest) {
+        // The ingest worker may have grown the mosaic since the caller's size query: *w x *h x *channels (as returned by
+        // that query) is then the capacity of `out`.  Refuse instead of overrunning it; the caller queries again.
+        long long cap = (long long)*w * *hpx * *channels;
+        int qw, qh, qc, qx, qy;
+        int rc = h->get_image(nullptr, &qw, &qh, &qc, &qx, &qy);
+        if (rc != M2D_OK) return rc;
+        if ((long long)qw * qh * qc > cap) { h->err = "m2d_get_image: the mosaic grew since the size query; query again"; return M2D_ERR_STATE; }
+    }
     return h->get_image(out, w, hpx, channels, tmx, tmy);
 }
 
 int m2d_save(m2d_handle h, const char* filename) {
+    API_LOCK(h);
     if (!h || !filename) return M2D_ERR_ARG;
     int w, hp, cn, tx, ty;
     int rc = h->get_image(nullptr, &w, &hp, &cn, &tx, &ty);
@@ -991,9 +1218,10 @@ int m2d_save(m2d_handle h, const char* filename) {
 }
 
 size_t m2d_tile_bytes(m2d_handle h) { return h ? h->tile_bytes : 0; }
-int m2d_tile_count(m2d_handle h) { return h ? (int)h->tiles_in_use : 0; }
+int m2d_tile_count(m2d_handle h) { API_LOCK(h); return h ? (int)h->tiles_in_use : 0; }
 
 int m2d_export_tiles(m2d_handle h, int max_tiles, int* abs_xy, uint8_t* dst, int dst_on_device, int* n_out) {
+    API_LOCK(h);
     if (!h || !abs_xy || !dst || !n_out) return M2D_ERR_ARG;
     m2d_map& m = *h;
     std::string& err = m.err;
@@ -1031,6 +1259,7 @@ int m2d_export_tiles(m2d_handle h, int max_tiles, int* abs_xy, uint8_t* dst, int
 }
 
 int m2d_import_tiles(m2d_handle h, int n, const int* abs_xy, const uint8_t* src, int src_on_device) {
+    API_LOCK(h);
     if (!h || n < 0 || (n && (!abs_xy || !src))) return M2D_ERR_ARG;
     m2d_map& m = *h;
     std::string& err = m.err;
@@ -1064,6 +1293,7 @@ int m2d_import_tiles(m2d_handle h, int n, const int* abs_xy, const uint8_t* src,
 }
 
 int m2d_poll_changed(m2d_handle h, int max_tiles, int* xy, int* n_out) {
+    API_LOCK(h);
     if (!h || !xy || !n_out || max_tiles < 0) return M2D_ERR_ARG;
     m2d_map& m = *h;
     if (!m.valid) return M2D_ERR_STATE;
@@ -1078,6 +1308,7 @@ int m2d_poll_changed(m2d_handle h, int max_tiles, int* xy, int* n_out) {
 }
 
 int m2d_get_tile_image(m2d_handle h, int tx, int ty, int high_quality, uint8_t* out, int* channels) {
+    API_LOCK(h);
     if (!h || !out || !channels) return M2D_ERR_ARG;
     m2d_map& m = *h;
     std::string& err = m.err;
@@ -1157,6 +1388,7 @@ struct StateHeader {
 }  // namespace
 
 int m2d_save_state(m2d_handle h, const char* filename) {
+    API_LOCK(h);
     if (!h || !filename) return M2D_ERR_ARG;
     m2d_map& m = *h;
     if (!m.valid) return M2D_ERR_STATE;
@@ -1182,6 +1414,7 @@ int m2d_save_state(m2d_handle h, const char* filename) {
 }
 
 int m2d_load_state(m2d_handle h, const char* filename) {
+    API_LOCK(h);
     if (!h || !filename) return M2D_ERR_ARG;
     m2d_map& m = *h;
     std::string& err = m.err;
@@ -1217,6 +1450,7 @@ int m2d_load_state(m2d_handle h, const char* filename) {
 }
 
 int m2d_get_stats(m2d_handle h, m2d_stats* out) {
+    API_LOCK(h);
     if (!h || !out) return M2D_ERR_ARG;
     m2d_map& m = *h;
     std::string& err = m.err;
@@ -1231,11 +1465,13 @@ int m2d_get_stats(m2d_handle h, m2d_stats* out) {
 }
 
 int m2d_profile(m2d_handle h, int enable) {
+    API_LOCK(h);
     if (!h) return M2D_ERR_ARG;
     h->profiling = enable != 0;
     return M2D_OK;
 }
 int m2d_get_kernel_times(m2d_handle h, double* ms, uint64_t* count) {
+    API_LOCK(h);
     if (!h || !ms || !count) return M2D_ERR_ARG;
     m2d_map& m = *h;
     std::string& err = m.err;
@@ -1263,6 +1499,7 @@ void* m2d_alloc_host(size_t bytes) {
 void m2d_free_host(void* p) { if (p) cudaFreeHost(p); }
 
 int m2d_compute_bounds(m2d_handle h, int n, const double* poses, int* rects, double* hinv) {
+    API_LOCK(h);
     if (!h || n < 0 || !poses || !rects || !hinv) return M2D_ERR_ARG;
     m2d_map& m = *h;
     std::string& err = m.err;

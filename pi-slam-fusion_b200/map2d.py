@@ -19,6 +19,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmap2d_b200.so")
 MAX_LEVELS = 9
 OK, REJECTED = 0, 1
+ERR_ARG, ERR_STATE, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED, ERR_IO = -1, -2, -3, -4, -5, -6
 
 
 class Config(C.Structure):
@@ -46,7 +47,8 @@ EXPORTS = ["m2d_config_default", "m2d_create", "m2d_destroy", "m2d_prepare", "m2
            "m2d_feed_batch", "m2d_feed_poses", "m2d_plan_rects", "m2d_set_shard", "m2d_sync", "m2d_queue_size", "m2d_set_stream", "m2d_reset", "m2d_get_grid",
            "m2d_last_rect", "m2d_get_tile", "m2d_get_image", "m2d_save", "m2d_tile_bytes", "m2d_tile_count",
            "m2d_export_tiles", "m2d_import_tiles", "m2d_poll_changed", "m2d_get_tile_image", "m2d_save_state", "m2d_load_state", "m2d_get_stats", "m2d_last_error",
-           "m2d_launch_count", "m2d_profile", "m2d_get_kernel_times", "m2d_alloc_host", "m2d_free_host", "m2d_compute_bounds"]
+           "m2d_launch_count", "m2d_profile", "m2d_get_kernel_times", "m2d_alloc_host", "m2d_free_host", "m2d_compute_bounds",
+           "m2d_ingest_open", "m2d_ingest_push", "m2d_ingest_pause", "m2d_ingest_drain", "m2d_ingest_close", "m2d_ingest_stats"]
 
 _lib = None
 
@@ -72,6 +74,13 @@ def lib():
     L.m2d_feed_batch.argtypes = [vp, C.c_int, vp, C.c_size_t, C.c_int, C.c_int, C.c_size_t, dp, C.c_int, ip]
     L.m2d_feed_poses.argtypes = [vp, C.c_int, dp, ip]
     L.m2d_plan_rects.argtypes = [vp, C.c_int, dp, ip]
+    L.m2d_ingest_open.argtypes = [vp, C.c_int, C.c_int]
+    L.m2d_ingest_push.argtypes = [vp, vp, C.c_int, C.c_int, C.c_size_t, C.c_int, dp]
+    L.m2d_ingest_pause.argtypes = [vp, C.c_int]
+    L.m2d_ingest_drain.argtypes = [vp]
+    L.m2d_ingest_close.argtypes = [vp]
+    u64p = C.POINTER(C.c_uint64)
+    L.m2d_ingest_stats.argtypes = [vp, u64p, u64p, u64p, u64p]
     L.m2d_set_shard.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     L.m2d_sync.argtypes = [vp]
     L.m2d_queue_size.argtypes = [vp]
@@ -214,6 +223,32 @@ class Map2D:
         self._check(lib().m2d_plan_rects(self._h, len(poses), _dptr(poses), rects.ctypes.data_as(C.POINTER(C.c_int))))
         return rects
 
+    # --- ingest seam: bounded drop-oldest queue + worker in front of feed() --------------
+    def ingest_open(self, capacity=30, start_paused=False):
+        return self._check(lib().m2d_ingest_open(self._h, capacity, int(start_paused)))
+
+    def ingest_push(self, img, pose):
+        """img: HxWx3 (BGR) or HxWx4 (BGRA) uint8.  Never blocks; a full queue drops its oldest frame."""
+        img = np.asarray(img)
+        if img.dtype != np.uint8 or img.ndim != 3 or img.shape[2] not in (3, 4) or img.strides[2] != 1 or img.strides[1] != img.shape[2]:
+            raise ValueError("ingest_push needs a uint8 HxWx3 or HxWx4 image with packed pixels")
+        pose = np.ascontiguousarray(pose, np.float64).reshape(7)
+        return self._check(lib().m2d_ingest_push(self._h, img.ctypes.data, img.shape[1], img.shape[0], img.strides[0], img.shape[2], _dptr(pose)))
+
+    def ingest_pause(self, paused=True):
+        return self._check(lib().m2d_ingest_pause(self._h, int(paused)))
+
+    def ingest_drain(self):
+        return self._check(lib().m2d_ingest_drain(self._h))
+
+    def ingest_close(self):
+        return self._check(lib().m2d_ingest_close(self._h))
+
+    def ingest_stats(self):
+        v = [C.c_uint64() for _ in range(4)]
+        self._check(lib().m2d_ingest_stats(self._h, *[C.byref(x) for x in v]))
+        return dict(zip(("pushed", "dropped", "fed", "fused"), (int(x.value) for x in v)))
+
     def set_shard(self, rank, count, axis, span, origin=0):
         """Re-partition tile ownership (only while the map holds no tiles), see m2d_set_shard."""
         return self._check(lib().m2d_set_shard(self._h, rank, count, axis, span, origin))
@@ -264,16 +299,20 @@ class Map2D:
         """In-memory save(): (image, (tile_min_x, tile_min_y)).  `out`: optional preallocated uint8 buffer (e.g. from
         pinned_empty) of at least h*w*channels bytes; a view of it is returned."""
         w, h, cn, tx, ty = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
-        rc = lib().m2d_get_image(self._h, None, C.byref(w), C.byref(h), C.byref(cn), C.byref(tx), C.byref(ty))
-        if not self._check(rc):
-            return None
-        nbytes = h.value * w.value * cn.value
-        if out is None:
-            out = np.empty(nbytes, np.uint8)
-        flat = out.reshape(-1)
-        assert flat.dtype == np.uint8 and flat.size >= nbytes and flat.flags["C_CONTIGUOUS"]
-        self._check(lib().m2d_get_image(self._h, flat.ctypes.data, C.byref(w), C.byref(h), C.byref(cn), C.byref(tx), C.byref(ty)))
-        return flat[:nbytes].reshape(h.value, w.value, cn.value), (tx.value, ty.value)
+        for _ in range(8):   # more than one round only while an ingest worker is growing the map under us
+            rc = lib().m2d_get_image(self._h, None, C.byref(w), C.byref(h), C.byref(cn), C.byref(tx), C.byref(ty))
+            if not self._check(rc):
+                return None
+            nbytes = h.value * w.value * cn.value
+            buf = np.empty(nbytes, np.uint8) if out is None else out
+            flat = buf.reshape(-1)
+            assert flat.dtype == np.uint8 and flat.size >= nbytes and flat.flags["C_CONTIGUOUS"]
+            rc = lib().m2d_get_image(self._h, flat.ctypes.data, C.byref(w), C.byref(h), C.byref(cn), C.byref(tx), C.byref(ty))
+            if rc == ERR_STATE:
+                continue
+            self._check(rc)
+            return flat[:nbytes].reshape(h.value, w.value, cn.value), (tx.value, ty.value)
+        raise RuntimeError("get_image: the mosaic kept growing; pause or drain the ingest queue first")
 
     # --- sharded runs: final tile gather -----------------------------------------------------------------
     def tile_bytes(self):

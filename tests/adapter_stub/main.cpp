@@ -7,8 +7,9 @@
 int main(int argc, char** argv) {
     int type = argc > 1 ? atoi(argv[1]) : Map2D::TypeMultiBandCPU;
     const char* out = argc > 2 ? argv[2] : "/tmp/adapter_stub.png";
+    const bool threaded = argc > 3 && atoi(argv[3]) != 0;   // Map2D::create(type, thread)
     const int W = 320, H = 180;
-    Map2DB200 map(type, /*thread=*/false);
+    Map2DB200 map(type, threaded);
     std::deque<std::pair<cv::Mat, pi::SE3d> > frames;
     for (int k = 0; k < 4; k++) {
         cv::Mat img(H, W, CV_8UC3);

@@ -48,3 +48,17 @@ def test_adapter_drives_the_gpu_path(tmp_path, typ):
     assert r["handle"] == "1" and r["prepared"] == "1" and r["fed"] == "4" and r["oblique_accepted"] == "0" and r["saved"] == "1"
     w, h = map(int, re.match(r"(\d+)x(\d+)", r["image"]).groups())
     assert w > 0 and w % 256 == 0 and h % 256 == 0 and os.path.getsize(png) > 1000
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("typ", [1, 3])
+def test_adapter_thread_mode_uses_the_ingest_queue(tmp_path, typ):
+    """thread=true: feed() only enqueues (so even the oblique frame is 'accepted', like the reference's enqueue),
+    save()/getImage() drain the queue first, and the result is the same mosaic as the synchronous run."""
+    exe = build(tmp_path)
+    a, b = str(tmp_path / "sync.png"), str(tmp_path / "thread.png")
+    r0 = run(exe, str(typ), a, "0")
+    r1 = run(exe, str(typ), b, "1")
+    assert r1["handle"] == "1" and r1["prepared"] == "1" and r1["fed"] == "4" and r1["oblique_accepted"] == "1" and r1["saved"] == "1"
+    assert r1["image"] == r0["image"] and r1["queue"] == "0"
+    assert open(a, "rb").read() == open(b, "rb").read()
