@@ -1149,48 +1149,73 @@ cudaError_t launch_mbs_decide(const GroupParams& p, const TileLayout& lay, cudaS
     return cudaGetLastError();
 }
 
-// ---- 3. propagate: need[l] = win[l] | dilate3(win[l-1]) (Laplacian taps), then top-down need[l] |= dilate3(need[l+1]) ----
-__device__ __forceinline__ bool any3x3(const uint8_t* f, int cx, int cy, int cw, int ch) {
-    bool v = false;
-    for (int dy = -1; dy <= 1; dy++) {
-        int y = cy + dy;
-        if ((unsigned)y >= (unsigned)ch) continue;
-        for (int dx = -1; dx <= 1; dx++) {
-            int x = cx + dx;
-            if ((unsigned)x < (unsigned)cw) v |= f[y * cw + x] != 0;
-        }
-    }
-    return v;
-}
-__global__ void __launch_bounds__(256) mbs_propagate_kernel(const __grid_constant__ GroupParams p) {
+// ---- 3. propagate: need[k] = cells within reach of a win.  A win of level m in cell c' needs G_k valid in cells
+// [c' - reach_lo[m][k], c' + reach_hi[m][k]] (both axes): the host derives the table by interval arithmetic over the
+// exact taps (make_reach_table).  One CTA per frame; the win flags of all levels sit in shared memory when they fit.
+__global__ void __launch_bounds__(512) mbs_propagate_kernel(const __grid_constant__ GroupParams p, int smem_cells) {
+    extern __shared__ uint8_t s_win[];
     const int f = blockIdx.x;
     const FrameJob& J = p.jobs[f];
-    const int cw = J.wnx * 8, ch = J.wny * 8, nc = cw * ch;
-    for (int l = 0; l < p.levels; l++) {
-        const uint8_t* w = p.win + cell_base(p, f, l);
-        const uint8_t* wf = l > 0 ? p.win + cell_base(p, f, l - 1) : nullptr;
-        uint8_t* nd = p.need + cell_base(p, f, l);
-        for (int c = threadIdx.x; c < nc; c += blockDim.x) {
-            bool v = w[c] != 0;
-            if (!v && wf) { int cy = c / cw; v = any3x3(wf, c - cy * cw, cy, cw, ch); }
-            nd[c] = v ? 1 : 0;
-        }
-    }
-    __syncthreads();
-    for (int l = p.levels - 2; l >= 0; l--) {
-        const uint8_t* up = p.need + cell_base(p, f, l + 1);
-        uint8_t* nd = p.need + cell_base(p, f, l);
-        for (int c = threadIdx.x; c < nc; c += blockDim.x) {
-            if (nd[c]) continue;
-            int cy = c / cw;
-            if (any3x3(up, c - cy * cw, cy, cw, ch)) nd[c] = 1;
-        }
+    const int cw = J.wnx * 8, ch = J.wny * 8, nc = cw * ch, L = p.levels;
+    const bool in_smem = nc <= smem_cells;
+    if (in_smem) {
+        for (int i = threadIdx.x; i < L * nc; i += blockDim.x) { int l = i / nc; s_win[i] = p.win[cell_base(p, f, l) + (i - l * nc)]; }
         __syncthreads();
+    }
+    for (int i = threadIdx.x; i < L * nc; i += blockDim.x) {
+        const int k = i / nc, c = i - k * nc, cy = c / cw, cx = c - cy * cw;
+        bool v = false;
+        for (int m = max(k - 1, 0); m < L && !v; m++) {
+            const int rl = p.reach_lo[m][k], rh = p.reach_hi[m][k];
+            if (rl == 0xFF) continue;
+            const uint8_t* w = in_smem ? s_win + m * nc : p.win + cell_base(p, f, m);
+            // c is required by a win in c' iff c' - rl <= c <= c' + rh  <=>  c - rh <= c' <= c + rl
+            const int y0 = max(cy - rh, 0), y1 = min(cy + rl, ch - 1), x0 = max(cx - rh, 0), x1 = min(cx + rl, cw - 1);
+            for (int y = y0; y <= y1 && !v; y++)
+                for (int x = x0; x <= x1; x++) v |= w[y * cw + x] != 0;
+        }
+        p.need[cell_base(p, f, k) + c] = v ? 1 : 0;
     }
 }
 cudaError_t launch_mbs_propagate(const GroupParams& p, cudaStream_t stream) {
-    mbs_propagate_kernel<<<p.n_frames, 256, 0, stream>>>(p);
+    const size_t smem_max = 200 * 1024;
+    size_t want = (size_t)p.levels * p.cells_max;
+    int smem = want <= smem_max ? (int)want : 0;   // does not fit: the kernel reads the flags from global memory
+    if (smem > 48 * 1024) {  // opt in per launch: the attribute is per device, and a process may drive several
+        cudaError_t e = cudaFuncSetAttribute(mbs_propagate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+        if (e != cudaSuccess) return e;
+    }
+    mbs_propagate_kernel<<<p.n_frames, 512, smem, stream>>>(p, smem ? p.cells_max : 0);
     return cudaGetLastError();
+}
+
+// Reach table of the weights-first variant.  A win of level m occupying cell c (level-m px [c*B, (c+1)*B - 1], B = 32 >> m)
+// needs: its own px of G_m; if m is not the top level, G_{m+1} on [(lo >> 1) - 1, (hi >> 1) + 1] (the pyrUp taps of
+// lap_quad); and every G_{k+1} px u needs G_k on [2u - 2, 2u + 2] (pyrDown taps; borders reflect inwards only).
+// Cell of level-k px q = (q << k) >> 5.  The table is translation invariant (cells are aligned at every level).
+void make_reach_table(int levels, unsigned char lo_tab[6][6], unsigned char hi_tab[6][6]) {
+    for (int m = 0; m < 6; m++)
+        for (int k = 0; k < 6; k++) lo_tab[m][k] = hi_tab[m][k] = 0xFF;
+    const long long c = 1 << 12;
+    for (int m = 0; m < levels && m < 6; m++) {
+        const long long B = 32 >> m;
+        long long a = c * B, b = (c + 1) * B - 1;
+        int k = m;
+        auto put = [&](int lvl, long long x0, long long x1) {
+            long long c0 = (x0 << lvl) >> 5, c1 = (x1 << lvl) >> 5;
+            lo_tab[m][lvl] = (unsigned char)(c - c0);
+            hi_tab[m][lvl] = (unsigned char)(c1 - c);
+        };
+        if (m + 1 < levels) {
+            a = (a >> 1) - 1; b = (b >> 1) + 1;
+            k = m + 1;
+        }
+        put(k, a, b);
+        for (; k > 0; k--) {
+            a = 2 * a - 2; b = 2 * b + 2;
+            put(k - 1, a, b);
+        }
+    }
 }
 
 // ---- 4a. image warp of the needed level-0 cells: one CTA = one 32 x 32 cell, one thread = 4 px ----

@@ -58,6 +58,7 @@ struct GroupParams {
     int cells_max;             // (max_wnx * 8) * (max_wny * 8)
     uint16_t* wmap;            // [n_tiles][wmap_stride]: winning entry per pyramid px of the tile (0xFFFF = none)
     int wmap_stride;           // >= TileLayout::px_off[levels], even
+    unsigned char reach_lo[6][6], reach_hi[6][6];  // [win level m][Gaussian level k] in cells, 0xFF = no dependency (make_reach_table)
 };
 
 // Tile state layout in HBM (multi-band): for each level l (side n = 256>>l): B,G,R int16 planes then f32 weight.
@@ -102,6 +103,7 @@ cudaError_t launch_mbw_pyrdown(const GroupParams& p, int level, cudaStream_t str
 cudaError_t launch_mbw_pyrtail(const GroupParams& p, int l_first, cudaStream_t stream);
 cudaError_t launch_mbs_decide(const GroupParams& p, const TileLayout& lay, cudaStream_t stream);
 cudaError_t launch_mbs_propagate(const GroupParams& p, cudaStream_t stream);
+void make_reach_table(int levels, unsigned char lo_tab[6][6], unsigned char hi_tab[6][6]);
 cudaError_t launch_mbs_warp(const GroupParams& p, cudaStream_t stream);
 cudaError_t launch_mbs_pyrdown(const GroupParams& p, int level, cudaStream_t stream);
 cudaError_t launch_mbs_pyrtail(const GroupParams& p, int l_first, cudaStream_t stream);

@@ -667,6 +667,7 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
     if (sparse) {
         p.win = c.d_scratch + off_win; p.need = c.d_scratch + off_need; p.cells_max = cells_max;
         p.wmap = reinterpret_cast<uint16_t*>(c.d_scratch + off_wmap); p.wmap_stride = wmap_stride;
+        make_reach_table(levels, p.reach_lo, p.reach_hi);
     }
 
     // Order-independent stages run on the context's own stream (they overlap the previous group's select); the
