@@ -1151,41 +1151,29 @@ cudaError_t launch_mbs_decide(const GroupParams& p, const TileLayout& lay, cudaS
 
 // ---- 3. propagate: need[k] = cells within reach of a win.  A win of level m in cell c' needs G_k valid in cells
 // [c' - reach_lo[m][k], c' + reach_hi[m][k]] (both axes): the host derives the table by interval arithmetic over the
-// exact taps (make_reach_table).  One CTA per frame; the win flags of all levels sit in shared memory when they fit.
-__global__ void __launch_bounds__(512) mbs_propagate_kernel(const __grid_constant__ GroupParams p, int smem_cells) {
-    extern __shared__ uint8_t s_win[];
-    const int f = blockIdx.x;
+// exact taps (make_reach_table).  One thread per (frame, level, cell).
+__global__ void __launch_bounds__(256) mbs_propagate_kernel(const __grid_constant__ GroupParams p) {
+    const int f = blockIdx.y;
     const FrameJob& J = p.jobs[f];
     const int cw = J.wnx * 8, ch = J.wny * 8, nc = cw * ch, L = p.levels;
-    const bool in_smem = nc <= smem_cells;
-    if (in_smem) {
-        for (int i = threadIdx.x; i < L * nc; i += blockDim.x) { int l = i / nc; s_win[i] = p.win[cell_base(p, f, l) + (i - l * nc)]; }
-        __syncthreads();
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= L * nc) return;
+    const int k = i / nc, c = i - k * nc, cy = c / cw, cx = c - cy * cw;
+    bool v = false;
+    for (int m = max(k - 1, 0); m < L && !v; m++) {
+        const int rl = p.reach_lo[m][k], rh = p.reach_hi[m][k];
+        if (rl == 0xFF) continue;
+        const uint8_t* w = p.win + cell_base(p, f, m);   // a frame's flags are a few KB: L1/L2 resident
+        // c is required by a win in c' iff c' - rl <= c <= c' + rh  <=>  c - rh <= c' <= c + rl
+        const int y0 = max(cy - rh, 0), y1 = min(cy + rl, ch - 1), x0 = max(cx - rh, 0), x1 = min(cx + rl, cw - 1);
+        for (int y = y0; y <= y1 && !v; y++)
+            for (int x = x0; x <= x1; x++) v |= w[y * cw + x] != 0;
     }
-    for (int i = threadIdx.x; i < L * nc; i += blockDim.x) {
-        const int k = i / nc, c = i - k * nc, cy = c / cw, cx = c - cy * cw;
-        bool v = false;
-        for (int m = max(k - 1, 0); m < L && !v; m++) {
-            const int rl = p.reach_lo[m][k], rh = p.reach_hi[m][k];
-            if (rl == 0xFF) continue;
-            const uint8_t* w = in_smem ? s_win + m * nc : p.win + cell_base(p, f, m);
-            // c is required by a win in c' iff c' - rl <= c <= c' + rh  <=>  c - rh <= c' <= c + rl
-            const int y0 = max(cy - rh, 0), y1 = min(cy + rl, ch - 1), x0 = max(cx - rh, 0), x1 = min(cx + rl, cw - 1);
-            for (int y = y0; y <= y1 && !v; y++)
-                for (int x = x0; x <= x1; x++) v |= w[y * cw + x] != 0;
-        }
-        p.need[cell_base(p, f, k) + c] = v ? 1 : 0;
-    }
+    p.need[cell_base(p, f, k) + c] = v ? 1 : 0;
 }
 cudaError_t launch_mbs_propagate(const GroupParams& p, cudaStream_t stream) {
-    const size_t smem_max = 200 * 1024;
-    size_t want = (size_t)p.levels * p.cells_max;
-    int smem = want <= smem_max ? (int)want : 0;   // does not fit: the kernel reads the flags from global memory
-    if (smem > 48 * 1024) {  // opt in per launch: the attribute is per device, and a process may drive several
-        cudaError_t e = cudaFuncSetAttribute(mbs_propagate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
-        if (e != cudaSuccess) return e;
-    }
-    mbs_propagate_kernel<<<p.n_frames, 512, smem, stream>>>(p, smem ? p.cells_max : 0);
+    dim3 g((p.levels * p.cells_max + 255) / 256, p.n_frames);
+    mbs_propagate_kernel<<<g, 256, 0, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -142,8 +142,9 @@ struct m2d_map {
 
     static constexpr int kMaxCtx = 8;
     int kCtx = 4;                   // group contexts in flight (M2D_CTX env overrides, for tuning)
-    bool weights_first = false;     // M2D_SPARSE=1: multi-band decides winners from the weight pyramids first, then warps and
-                                    // filters the image only where a winner needs it (kernels.cu "WEIGHTS-FIRST variant")
+    bool weights_first = true;      // multi-band decides winners from the weight pyramids first, then warps and filters the
+                                    // image only where a winner needs it (kernels.cu "WEIGHTS-FIRST variant"); M2D_SPARSE=0
+                                    // selects the dense pipeline (every frame fully warped and filtered) for A/B runs
     cudaStream_t decide_stream = nullptr;  // chain of the groups' decide stages (tile weights), ahead of the Laplacian chain
     bool fused_warp_pyr = false;    // M2D_FUSED=1: warp + first pyrDown in one shared-memory kernel (measured 7 % slower, kept for A/B)
     GroupCtx ctx[kMaxCtx];

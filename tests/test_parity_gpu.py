@@ -353,12 +353,14 @@ def test_fused_warp_pyramid_variant_is_bit_exact(monkeypatch):
         g.close()
 
 
-def test_weights_first_variant_is_bit_exact(monkeypatch):
-    """M2D_SPARSE=1 selects the weights-first multi-band pipeline (winners decided from the weight pyramids, image
-    warp/pyrDown only in the cells a winner's Laplacian needs).  Same bits as the oracle: jittered
-    and noisy frames, several groups, 1/3/5 bands, a sharded window, stats, and the dense fallback for 8 bands."""
+@pytest.mark.parametrize("sparse", ["1", "0"])
+def test_weights_first_and_dense_pipelines_are_bit_exact(monkeypatch, sparse):
+    """Multi-band has two pipelines: weights-first (default; winners decided from the weight pyramids, image
+    warp/pyrDown only in the cells a winner's Laplacian needs) and dense (M2D_SPARSE=0).  Same bits as
+    the oracle from both: jittered and noisy frames, several groups, 1/3/5 bands, a sharded window, stats, and the
+    dense fallback the weights-first pipeline takes for 8 bands."""
     import torch
-    monkeypatch.setenv("M2D_SPARSE", "1")
+    monkeypatch.setenv("M2D_SPARSE", sparse)
     seq = synth.Sequence(14, 320, 180, seed=29, jitter=True, noise=True, fpl=4, prepare_frames=4)
     dev = torch.from_numpy(seq.frames()).cuda()
     for kw in ({}, {"band_number": 3}, {"band_number": 1}, {"band_number": 8}, {"collect_stats": 1},
