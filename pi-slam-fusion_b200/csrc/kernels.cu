@@ -889,7 +889,12 @@ cudaError_t launch_mb_select(const GroupParams& p, const TileLayout& lay, cudaSt
 // =========================================================================================================
 __device__ __forceinline__ size_t cell_base(const GroupParams& p, int frame, int l) { return ((size_t)frame * p.levels + l) * p.cells_max; }
 
-// ---- 1a. weight warp (nearest, constant 0): one thread = 4 px; px far outside the frame skip the FP64 path ----
+// ---- 1a. weight warp (nearest, constant 0): one thread = 4 px ----
+// The weight of a px is wimg[rnd(fy)][rnd(fx)]: only the ROUNDED source coordinate matters.  So the coordinate is first
+// evaluated in FP32; its distance to the exact FP64 value OpenCV computes is below a few ulps of the largest
+// intermediate (bounded per thread by `mag`), hence rnd() of both agree unless the FP32 value lies within `thr` =
+// 48 ulps(mag) of a rounding boundary (x.5).  Only those px (~2 %) take the exact FP64 path; lanes pick their own
+// ambiguous px, so a warp normally runs that path once instead of four times.  Px far outside the frame skip both.
 __global__ void __launch_bounds__(256) mbw_warp_kernel(const __grid_constant__ GroupParams p) {
     const FrameJob& J = p.jobs[blockIdx.y];
     const int ww = J.wnx * kEle, wh = J.wny * kEle;
@@ -898,34 +903,59 @@ __global__ void __launch_bounds__(256) mbw_warp_kernel(const __grid_constant__ G
     if (by * 4 >= wh) return;
     int u = bx * kEle + (threadIdx.x & 63) * 4, v = by * 4 + (threadIdx.x >> 6);
     int x = u + J.wx * kEle, y = v + J.wy * kEle;
-    float w[4] = {0.f, 0.f, 0.f, 0.f};
-    // conservative FP32 test: both ends of the 4-px run map outside the same side of the source (denominators safely
-    // positive) -> every px of the run is outside (a projective map keeps the run a straight segment) -> weight 0
+    float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
     const float* mf = J.hinvf;
-    float wa = mf[6] * (float)x + mf[7] * (float)y + mf[8], wb = wa + 3.f * mf[6];
-    bool off = false;
-    if (wa > 1e-3f && wb > 1e-3f) {
-        float ax, ay, bx_, by_;
-        proj_f32(mf, (float)x, (float)y, ax, ay);
-        proj_f32(mf, (float)(x + 3), (float)y, bx_, by_);
+    const float xf = (float)x, yf = (float)y;
+    const float den0 = mf[7] * yf + mf[8], nx0 = mf[1] * yf + mf[2], ny0 = mf[4] * yf + mf[5];
+    const float wa = mf[6] * xf + den0, wb = mf[6] * (xf + 3.f) + den0;
+    const bool den_ok = wa > 1e-3f && wb > 1e-3f;   // denominators safely positive: FP32 reasoning is valid
+    unsigned amb = 0xFu;                             // px that need the exact path
+    if (den_ok) {
         const float lim_x = (float)p.sw + 0.25f, lim_y = (float)p.sh + 0.25f;
-        off = (ax < -1.25f && bx_ < -1.25f) || (ax > lim_x && bx_ > lim_x) || (ay < -1.25f && by_ < -1.25f) || (ay > lim_y && by_ > lim_y);
+        float ra = __fdividef(1.f, wa), rb_ = __fdividef(1.f, wb);
+        float ax = (mf[0] * xf + nx0) * ra, ay = (mf[3] * xf + ny0) * ra;
+        float bx_ = (mf[0] * (xf + 3.f) + nx0) * rb_, by_ = (mf[3] * (xf + 3.f) + ny0) * rb_;
+        // both ends of the 4-px run outside the same side of the source -> every px of the run is outside (a projective
+        // map keeps the run a straight segment) -> weight 0
+        const bool off = (ax < -1.25f && bx_ < -1.25f) || (ax > lim_x && bx_ > lim_x) || (ay < -1.25f && by_ < -1.25f) || (ay > lim_y && by_ > lim_y);
+        if (off) amb = 0u;
+        else {
+            const float rmax = fmaxf(ra, rb_);
+            const float magx = (fabsf(mf[0]) * (xf + 3.f) + fabsf(mf[1]) * yf + fabsf(mf[2])) * rmax;
+            const float magy = (fabsf(mf[3]) * (xf + 3.f) + fabsf(mf[4]) * yf + fabsf(mf[5])) * rmax;
+            const float thr_x = 48.f * 5.97e-8f * magx + 1e-6f, thr_y = 48.f * 5.97e-8f * magy + 1e-6f;
+            amb = 0u;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float xj = xf + (float)j;
+                const float r = __fdividef(1.f, mf[6] * xj + den0);
+                const float fx = (mf[0] * xj + nx0) * r, fy = (mf[3] * xj + ny0) * r;
+                const float rx = rintf(fx), ry = rintf(fy);
+                const bool near_half = (0.5f - fabsf(fx - rx) < thr_x) || (0.5f - fabsf(fy - ry) < thr_y);
+                float wv = 0.f;
+                if (rx >= 0.f && rx < (float)p.sw && ry >= 0.f && ry < (float)p.sh) wv = __ldg(p.wimg + ((int)ry * p.sw + (int)rx));
+                if (near_half) amb |= 1u << j;
+                if (j == 0) w0 = wv; else if (j == 1) w1 = wv; else if (j == 2) w2 = wv; else w3 = wv;
+            }
+        }
     }
-    if (!off) {
+    if (amb) {   // exact OpenCV arithmetic for the px the FP32 pass could not decide
         double M[9];
 #pragma unroll
         for (int i = 0; i < 9; i++) M[i] = J.hinv[i];
         RowBase rb = row_base(M, x, y);
-        double x1 = (double)(x & 63);
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
+        const double x1 = (double)(x & 63);
+        while (amb) {
+            const int j = __ffs(amb) - 1;
+            amb &= amb - 1;
             double fx, fy;
             px_coord(M, rb, x1 + (double)j, fx, fy);
             int nx = rnd(fx), ny = rnd(fy);   // saturate_cast<short> cannot change an in/out decision for sw, sh <= 32767
-            w[j] = ((unsigned)nx < (unsigned)p.sw && (unsigned)ny < (unsigned)p.sh) ? __ldg(p.wimg + (ny * p.sw + nx)) : 0.f;
+            float wv = ((unsigned)nx < (unsigned)p.sw && (unsigned)ny < (unsigned)p.sh) ? __ldg(p.wimg + (ny * p.sw + nx)) : 0.f;
+            if (j == 0) w0 = wv; else if (j == 1) w1 = wv; else if (j == 2) w2 = wv; else w3 = wv;
         }
     }
-    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.scratch + J.w_off[0]) + (size_t)v * ww + u) = make_float4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.scratch + J.w_off[0]) + (size_t)v * ww + u) = make_float4(w0, w1, w2, w3);
 }
 cudaError_t launch_mbw_warp(const GroupParams& p, cudaStream_t stream) {
     dim3 g(p.max_wnx * p.max_wny * (kEle / 4), p.n_frames);
