@@ -117,12 +117,24 @@ def stage_bytes(mode, stats, levels):
     # tail kernel depends on the frame size); the tiny tail gets the deepest level's share
     out["mb_pyrdown"] = sum(10 * D[l] + 10 * D[l + 1] for l in range(levels - 2))
     out["mb_pyrtail"] = sum(10 * D[l] + 10 * D[l + 1] for l in range(max(levels - 2, 0), levels - 1))
-    sel = 0.0
+    sel = dec = lap = 0.0
     for l in range(levels):
         nonfresh = stats["region_px"][l] - stats["fresh_px"][l]
         written = stats["fresh_px"][l] + stats["win_px"][l]
         sel += 4 * D[l] + 4 * nonfresh + written * (6 + 10 + (6 / 4 if l + 1 < levels else 0))
+        dec += 4 * D[l] + 4 * nonfresh + 4 * written           # every frame's weight, the tile weight, the new weight
+        lap += written * (6 + 6 + (6 / 4 if l + 1 < levels else 0))  # winner's G_l, its share of G_{l+1}, the Laplacian out
     out["mb_select"] = sel
+    # weights-first pipeline (default): weights dense (4 B f32 per px), image only where a winner needs it.  need_px[l] =
+    # px of the frames' level l that had to be computed (counted exactly by the library with collect_stats); the image
+    # stages are charged the reference's 6 B int16x3 per needed px, the source at 3 B per needed level-0 px.
+    N = stats.get("need_px", [0] * levels)
+    out["mbw_warp"] = 4 * D[0]
+    out["mbw_pyramid"] = sum(4 * D[l] + 4 * D[l + 1] for l in range(levels - 1))
+    out["mbs_decide"] = dec
+    out["mbs_warp"] = (3 + 6) * N[0]
+    out["mbs_pyramid"] = sum(6 * N[l] + 6 * N[l + 1] for l in range(levels - 1))
+    out["mbs_lap"] = lap
     return out
 
 
@@ -276,12 +288,13 @@ def main():
     total_kernel_ms = sum(v[0] for v in kt.values())
     dom = max(kt.items(), key=lambda kv: kv[1][0])[0]
     per_kernel = {}
+    groups = max([c for k, (_, c) in kt.items() if k in ("mbs_decide", "mb_select", "weighted_fuse")] or [1])  # launch groups per step
     for k, (ms, cnt) in kt.items():
         per_launch_us = ms / cnt * 1e3
         bpl = sb[k] / cnt if k in sb else None  # the profiled pass is exactly one step
         ach = bpl / (ms / cnt * 1e-3) / 1e9 if bpl else None
         per_kernel[k] = {"launches": cnt, "avg_us": round(per_launch_us, 3), "share": round(ms / total_kernel_ms, 4),
-                         "bytes_per_launch": bpl, "achieved_gbs": ach, "frames_per_launch": round(fused * (3 if k == "mb_pyrdown" else 1) / cnt, 2)}
+                         "bytes_per_launch": bpl, "achieved_gbs": ach, "frames_per_launch": round(fused / groups, 2)}
     path_bytes = algorithmic_bytes(mode, stats, levels)
     path_ach = path_bytes / (ms_step * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": per_kernel[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",

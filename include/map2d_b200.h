@@ -83,6 +83,9 @@ typedef struct m2d_stats {
     uint64_t fresh_px[M2D_MAX_LEVELS];     /* px of D_l that fell in first-touch tiles            */
     uint64_t win_px[M2D_MAX_LEVELS];       /* px of non-fresh tiles where the frame replaced state */
     uint64_t footprint_px;                 /* weighted: region px with warped alpha > 0            */
+    uint64_t need_px[M2D_MAX_LEVELS];      /* multi-band, weights-first pipeline: px of the frames' Gaussian level l that had
+                                              to be computed (cells a winner's Laplacian depends on); 0 from the oracle and
+                                              from the dense pipeline                                */
 } m2d_stats;
 
 typedef struct m2d_map* m2d_handle;
@@ -193,8 +196,12 @@ uint64_t m2d_launch_count(m2d_handle h);
 /* Per-kernel-class device timing: while enabled, every launch on the handle's stream is bracketed by CUDA
  * events; m2d_get_kernel_times synchronises and returns accumulated milliseconds and launch counts per class
  * (and clears them).  bench.py uses it for the live roofline measurement; leave it off otherwise. */
-#define M2D_KERNEL_CLASSES 8
-enum { M2D_K_WEIGHTED = 0, M2D_K_MB_WARP = 1, M2D_K_MB_PYRDOWN = 2, M2D_K_MB_SELECT = 3, M2D_K_COLLAPSE = 4, M2D_K_MISC = 5, M2D_K_MB_PYRTAIL = 6 };
+#define M2D_KERNEL_CLASSES 16
+enum { M2D_K_WEIGHTED = 0, M2D_K_MB_WARP = 1, M2D_K_MB_PYRDOWN = 2, M2D_K_MB_SELECT = 3, M2D_K_COLLAPSE = 4, M2D_K_MISC = 5, M2D_K_MB_PYRTAIL = 6,
+       /* weights-first multi-band pipeline (default): weight warp / weight pyramid (pyrDown + tail) / decide / propagate /
+        * sparse image warp / sparse image pyramid (pyrDown + tail) / winners' Laplacian */
+       M2D_K_MBW_WARP = 7, M2D_K_MBW_PYR = 8, M2D_K_MBS_DECIDE = 9, M2D_K_MBS_PROPAGATE = 10, M2D_K_MBS_WARP = 11, M2D_K_MBS_PYR = 12,
+       M2D_K_MBS_LAP = 13 };
 int m2d_profile(m2d_handle h, int enable);
 int m2d_get_kernel_times(m2d_handle h, double* ms /* M2D_KERNEL_CLASSES */, uint64_t* count /* M2D_KERNEL_CLASSES */);
 

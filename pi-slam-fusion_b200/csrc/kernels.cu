@@ -1200,6 +1200,10 @@ __global__ void __launch_bounds__(256) mbs_propagate_kernel(const __grid_constan
             for (int x = x0; x <= x1; x++) v |= w[y * cw + x] != 0;
     }
     p.need[cell_base(p, f, k) + c] = v ? 1 : 0;
+    if (p.stats && v) {   // collect_stats: px of level k this frame has to compute (a cell is (32 >> k)^2 px, 1 px at level 5)
+        const unsigned long long side = (unsigned long long)max(32 >> k, 1);
+        atomicAdd(p.stats + 20 + k, side * side);
+    }
 }
 cudaError_t launch_mbs_propagate(const GroupParams& p, cudaStream_t stream) {
     dim3 g((p.levels * p.cells_max + 255) / 256, p.n_frames);

@@ -689,26 +689,26 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
         for (; l_tail + 1 < levels && (!small_level(l_tail) || levels - 1 - l_tail < 2); l_tail++) {}
         // 1. weights only, dense, on the context's stream
         CU(cudaMemsetAsync(p.win, 0, flag_bytes, c.stage));
-        LAUNCHKS(M2D_K_MB_WARP, c.stage, launch_mbw_warp(p, c.stage));
-        for (int l = 0; l < l_tail; l++) LAUNCHKS(M2D_K_MB_PYRDOWN, c.stage, launch_mbw_pyrdown(p, l, c.stage));
-        if (l_tail + 1 < levels) LAUNCHKS(M2D_K_MB_PYRTAIL, c.stage, launch_mbw_pyrtail(p, l_tail, c.stage));
+        LAUNCHKS(M2D_K_MBW_WARP, c.stage, launch_mbw_warp(p, c.stage));
+        for (int l = 0; l < l_tail; l++) LAUNCHKS(M2D_K_MBW_PYR, c.stage, launch_mbw_pyrdown(p, l, c.stage));
+        if (l_tail + 1 < levels) LAUNCHKS(M2D_K_MBW_PYR, c.stage, launch_mbw_pyrtail(p, l_tail, c.stage));
         CU(cudaEventRecord(c.staged, c.stage));
         // 2.+3. winners and need flags: the decide chain serialises groups in feed order (tile weights only), and runs
         // ahead of the Laplacian chain on the handle's stream (which writes the Laplacian planes only)
         cudaStream_t ds = profiling ? stream : decide_stream;
         CU(cudaStreamWaitEvent(ds, c.staged, 0));
-        LAUNCHKS(M2D_K_MB_SELECT, ds, launch_mbs_decide(p, lay, ds));
-        LAUNCHKS(M2D_K_MISC, ds, launch_mbs_propagate(p, ds));
+        LAUNCHKS(M2D_K_MBS_DECIDE, ds, launch_mbs_decide(p, lay, ds));
+        LAUNCHKS(M2D_K_MBS_PROPAGATE, ds, launch_mbs_propagate(p, ds));
         CU(cudaEventRecord(c.decided, ds));
         // 4. image work in the needed cells, back on the context's stream
         CU(cudaStreamWaitEvent(c.stage, c.decided, 0));
-        LAUNCHKS(M2D_K_MB_WARP, c.stage, launch_mbs_warp(p, c.stage));
-        for (int l = 0; l < l_tail; l++) LAUNCHKS(M2D_K_MB_PYRDOWN, c.stage, launch_mbs_pyrdown(p, l, c.stage));
-        if (l_tail + 1 < levels) LAUNCHKS(M2D_K_MB_PYRTAIL, c.stage, launch_mbs_pyrtail(p, l_tail, c.stage));
+        LAUNCHKS(M2D_K_MBS_WARP, c.stage, launch_mbs_warp(p, c.stage));
+        for (int l = 0; l < l_tail; l++) LAUNCHKS(M2D_K_MBS_PYR, c.stage, launch_mbs_pyrdown(p, l, c.stage));
+        if (l_tail + 1 < levels) LAUNCHKS(M2D_K_MBS_PYR, c.stage, launch_mbs_pyrtail(p, l_tail, c.stage));
         CU(cudaEventRecord(c.staged, c.stage));
         // 5. winners' Laplacians into the tiles, in feed order on the handle's stream
         CU(cudaStreamWaitEvent(stream, c.staged, 0));
-        LAUNCHK(M2D_K_MB_SELECT, launch_mbs_lap(p, lay, stream));
+        LAUNCHK(M2D_K_MBS_LAP, launch_mbs_lap(p, lay, stream));
     } else if (type == M2D_TYPE_MULTIBAND) {
         // full-grid pyrDown while a level is big enough; the small deep levels go through one tail launch
         int l = 0;
@@ -1464,7 +1464,7 @@ int m2d_get_stats(m2d_handle h, m2d_stats* out) {
     CU(cudaMemcpyAsync(d, m.d_stats, sizeof d, cudaMemcpyDeviceToHost, m.stream));
     CU(cudaStreamSynchronize(m.stream));
     *out = m.stats;
-    if (m.type == M2D_TYPE_MULTIBAND) for (int l = 0; l < M2D_MAX_LEVELS; l++) out->win_px[l] = d[l];
+    if (m.type == M2D_TYPE_MULTIBAND) for (int l = 0; l < M2D_MAX_LEVELS; l++) { out->win_px[l] = d[l]; out->need_px[l] = 20 + l < 32 ? d[20 + l] : 0; }
     else { out->win_px[0] = d[17]; out->footprint_px = d[16]; }
     return M2D_OK;
 }

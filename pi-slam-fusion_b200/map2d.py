@@ -35,12 +35,12 @@ class Stats(C.Structure):
     """m2d_stats"""
     _fields_ = [("frames_fed", C.c_uint64), ("frames_fused", C.c_uint64), ("input_px", C.c_uint64),
                 ("region_px", C.c_uint64 * MAX_LEVELS), ("fresh_px", C.c_uint64 * MAX_LEVELS),
-                ("win_px", C.c_uint64 * MAX_LEVELS), ("footprint_px", C.c_uint64)]
+                ("win_px", C.c_uint64 * MAX_LEVELS), ("footprint_px", C.c_uint64), ("need_px", C.c_uint64 * MAX_LEVELS)]
 
     def as_dict(self):
         return {"frames_fed": self.frames_fed, "frames_fused": self.frames_fused, "input_px": self.input_px,
                 "region_px": list(self.region_px), "fresh_px": list(self.fresh_px), "win_px": list(self.win_px),
-                "footprint_px": self.footprint_px}
+                "footprint_px": self.footprint_px, "need_px": list(self.need_px)}
 
 
 EXPORTS = ["m2d_config_default", "m2d_create", "m2d_destroy", "m2d_prepare", "m2d_feed", "m2d_feed_device",
@@ -364,15 +364,16 @@ class Map2D:
     def launch_count(self):
         return int(lib().m2d_launch_count(self._h))
 
-    KERNEL_CLASSES = ("weighted_fuse", "mb_warp", "mb_pyrdown", "mb_select", "collapse", "misc", "mb_pyrtail", "k7")
+    KERNEL_CLASSES = ("weighted_fuse", "mb_warp", "mb_pyrdown", "mb_select", "collapse", "misc", "mb_pyrtail",
+                      "mbw_warp", "mbw_pyramid", "mbs_decide", "mbs_propagate", "mbs_warp", "mbs_pyramid", "mbs_lap", "k14", "k15")
 
     def profile(self, enable):
         return self._check(lib().m2d_profile(self._h, int(enable)))
 
     def kernel_times(self):
         """{class: (total_ms, launches)} accumulated since the last call (synchronises)."""
-        ms = np.zeros(8, np.float64)
-        cnt = np.zeros(8, np.uint64)
+        ms = np.zeros(len(self.KERNEL_CLASSES), np.float64)
+        cnt = np.zeros(len(self.KERNEL_CLASSES), np.uint64)
         self._check(lib().m2d_get_kernel_times(self._h, _dptr(ms), cnt.ctypes.data_as(C.POINTER(C.c_uint64))))
         return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.KERNEL_CLASSES) if cnt[i]}
 

@@ -94,7 +94,8 @@ def test_oracle_default_mode_goldens(name, typ):
         o.feed(seq.frame(k), seq.poses[k])
     assert state_record(o, typ) == gold["tiles"]
     assert sha(o.get_image()[0]) == gold["mosaic"]
-    assert o.stats() == gold["stats"]
+    st = o.stats()   # (need_px is a GPU-pipeline counter added later: always 0 from the oracle, not part of the goldens)
+    assert {k: st[k] for k in gold["stats"]} == gold["stats"] and not any(st["need_px"])
 
 
 @pytest.mark.gpu
