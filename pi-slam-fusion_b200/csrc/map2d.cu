@@ -417,7 +417,8 @@ int m2d_map::group_size(int w, int h, bool on_device) const {
     double mpx = (double)w * h / 1e6;
     // weights-first multi-band: the more frames compete inside a group, the smaller each frame's share of winners and
     // with it the image work (measured: 32 / 64 / 128 frames of 720p -> 7.8 / 7.4 / 6.8 ms per 500 frames)
-    if (type == M2D_TYPE_MULTIBAND && weights_first && !fused_warp_pyr) return std::max(1, std::min((int)(200.0 / std::max(mpx, 0.25)), 128));
+    // (host batches keep the smaller groups: the H2D staging of the first group is not overlapped by anything)
+    if (type == M2D_TYPE_MULTIBAND && weights_first && !fused_warp_pyr && on_device) return std::max(1, std::min((int)(200.0 / std::max(mpx, 0.25)), 128));
     int k = (int)(100.0 / std::max(mpx, 0.25));  // ~100 Mpx of source per group (measured: larger groups amortise better)
     return std::max(1, std::min(k, 64));
 }
