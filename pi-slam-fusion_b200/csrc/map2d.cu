@@ -146,6 +146,8 @@ struct m2d_map {
                                     // image only where a winner needs it (kernels.cu "WEIGHTS-FIRST variant"); M2D_SPARSE=0
                                     // selects the dense pipeline (every frame fully warped and filtered) for A/B runs
     cudaStream_t decide_stream = nullptr;  // chain of the groups' decide stages (tile weights), ahead of the Laplacian chain
+    cudaEvent_t dense_done = nullptr;      // last dense-pipeline select on the handle's stream (small groups), see run_group
+    bool dense_pending = false;
     bool fused_warp_pyr = false;    // M2D_FUSED=1: warp + first pyrDown in one shared-memory kernel (measured 7 % slower, kept for A/B)
     GroupCtx ctx[kMaxCtx];
     int ctx_next = 0;
@@ -210,6 +212,7 @@ int m2d_map::init() {
     if (const char* e = getenv("M2D_SPARSE")) weights_first = atoi(e) != 0;
     CU(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&decide_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&dense_done, cudaEventDisableTiming));
     for (int i = 0; i < kCtx; i++) {
         CU(cudaEventCreateWithFlags(&ctx[i].done, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&ctx[i].copied, cudaEventDisableTiming));
@@ -252,6 +255,7 @@ void m2d_map::release() {
     for (ProfRec& r : prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
     if (decide_stream) { cudaStreamSynchronize(decide_stream); cudaStreamDestroy(decide_stream); }
+    if (dense_done) cudaEventDestroy(dense_done);
     if (own_stream && stream) cudaStreamDestroy(stream);
 }
 
@@ -600,7 +604,9 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
       rc = grow((void**)&c.d_blob, &c.blob_cap, blob, false); if (rc != M2D_OK) return rc; }
     if (!on_device) { int rc = grow((void**)&c.d_raw, &c.raw_cap, (size_t)nj * npx * 3 + 256, false); if (rc != M2D_OK) return rc; }
     // weights-first multi-band: cell flags (win | need) and the winner map live behind the pyramids
-    const bool sparse = weights_first && type == M2D_TYPE_MULTIBAND && levels <= 6 && !fused_warp_pyr && !tiles.empty();
+    // (groups of a few frames -- streaming feed() calls -- take the dense pipeline: a lone frame wins most of what it
+    // covers, so there is little to skip, and the dense pipeline needs 6 launches instead of 14)
+    const bool sparse = weights_first && type == M2D_TYPE_MULTIBAND && levels <= 6 && !fused_warp_pyr && !tiles.empty() && nj >= 4;
     const int cells_max = max_wnx * 8 * max_wny * 8;
     const int wmap_stride = (lay.px_off[levels] + 7) & ~7;
     size_t off_win = 0, off_need = 0, off_wmap = 0, flag_bytes = 0;
@@ -698,6 +704,10 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
         // ahead of the Laplacian chain on the handle's stream (which writes the Laplacian planes only)
         cudaStream_t ds = profiling ? stream : decide_stream;
         CU(cudaStreamWaitEvent(ds, c.staged, 0));
+        if (dense_pending) {   // a dense group's select (handle stream) wrote tile weights: the decide chain must see them
+            CU(cudaStreamWaitEvent(ds, dense_done, 0));
+            dense_pending = false;
+        }
         LAUNCHKS(M2D_K_MBS_DECIDE, ds, launch_mbs_decide(p, lay, ds));
         LAUNCHKS(M2D_K_MBS_PROPAGATE, ds, launch_mbs_propagate(p, ds));
         CU(cudaEventRecord(c.decided, ds));
@@ -726,6 +736,7 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
         CU(cudaEventRecord(c.staged, c.stage));
         CU(cudaStreamWaitEvent(stream, c.staged, 0));
         LAUNCHK(M2D_K_MB_SELECT, launch_mb_select(p, lay, stream));
+        if (weights_first) { CU(cudaEventRecord(dense_done, stream)); dense_pending = true; }
     } else {
         // weighted mode samples the caller's BGR8 frames in place (plus the alpha plane): no packed copy
         CU(cudaEventRecord(c.staged, c.stage));
