@@ -188,3 +188,38 @@ def test_oracle_plan_rects_equal_sequential_feed_rects():
     assert grew, "the sequence must exercise spreadMap towards negative coordinates"
     g1 = o.grid()
     assert (g0["w"], g0["h"]) == (g1["w"], g1["h"]) and o.tile_count() == 0
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_bench_scale_delivery_plan(world):
+    """The plan `bench.py --gpus N` builds (N x the 500-frame 720p survey, strips of tiles, frames resident on the
+    rank of their own flight lines), computed with the CPU stand-in: every rank's hull is a modest superset of its own
+    frames, transfers only connect neighbouring ranks, and every needed frame is either resident or received."""
+    sys.path.insert(0, ROOT)
+    from oracle import oracle as O
+    import pi_slam_fusion_b200.synth as synth
+    from pi_slam_fusion_b200.sharded import DeliveryPlan, ShardedMap2D, even_split
+    W, H, per_gpu = 1280, 720, 500
+    n = per_gpu * world
+    poses = synth.serpentine_poses(n, W, H, seed=2, fpl=synth.frames_per_line(per_gpu, W, H))
+    cam = synth.camera(W, H)
+    plans = []
+    for rank in (0, world - 1):
+        sm = ShardedMap2D(lambda t, **kw: O.OracleMap2D.create(t, **kw), 3, rank, world, device=None, shard_axis=0, shard_span=4)
+        assert sm.prepare(synth.IDENTITY_POSE, cam, poses[:20])
+        rects, axis, span, origin = sm.align_strips(poses)
+        plans.append(DeliveryPlan(rects, axis, span, world, even_split(n, world), origin))
+        # pose-only feeding of everything outside the hull must be accepted by the stand-in (no owned tile under it)
+        a, b = plans[-1].hull[rank]
+        assert (sm.map.feed_poses(poses[:a]) == 0).all() and (sm.map.feed_poses(poses[b:]) == 0).all()
+    p = plans[0]
+    assert p.hull == plans[1].hull and p.transfers == plans[1].transfers, "every rank must derive the same plan"
+    assert axis == 0
+    for r in range(world):
+        a, b = p.hull[r]
+        lo, hi = p.resident[r]
+        # equal frame counts (residency) and equal tile spans (strips) drift apart by up to ~2 flight lines of 42 at N=8
+        assert a <= lo + 100 and b >= hi - 100, "strips and residency must roughly coincide"
+        assert b - a <= 1.4 * per_gpu, "hull of rank %d is %d frames" % (r, b - a)
+    assert all(abs(s - d) == 1 for (s, d, _, _) in p.transfers), "only neighbouring strips exchange frames"
+    assert p.frames_moved() <= 0.35 * n
