@@ -176,8 +176,8 @@ def run_reference(args, rank):
     dt = (time.perf_counter() - t0) / args.steps
     val = sample * W * H / dt / 1e6
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "s16", "data": "synthetic",
+            "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": args.scaling,
+            "vs_baseline": None, "dtype": "s16" if mode == "multiband" else "u8", "data": "synthetic",
             "config": {"workload": workload_name(mode, NFRAMES), "mode": mode},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": "first %d frames of the %d-frame workload per step (oracle/map2d_oracle.cpp, OpenMP)" % (sample, NFRAMES)},
@@ -379,8 +379,8 @@ def main():
         m2d.free_pinned(hfp)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "s16",
-            "data": "synthetic",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": "s16" if mode == "multiband" else "u8", "data": "synthetic",
             "config": {"workload": workload_name(mode, n), "mode": mode, "frames": n, "frames_fused": fused,
                        "frame": [W, H], "bands": levels - 1, "l2": "inputs %.2f GB per step > 126 MB L2 (no flush needed)" % (n * frame_bytes / 1e9),
                        "parallelism": "1 GPU", "batch_frames": args.batch},
