@@ -171,3 +171,65 @@ def test_default_float_mode_stays_within_tolerance_of_opencv():
             assert np.max(np.abs(ow - cw) / np.maximum(np.abs(cw), 1e-30)) <= 1e-5
     io, ic = o.get_image()[0].astype(np.int32), c.get_image()[0].astype(np.int32)
     assert (np.abs(io - ic) <= 1).mean() >= 0.999
+
+
+def _blend_with_cv2(tiles, levels):
+    """Ele::blend (MultiBandMap2DCPU.cpp:77-146) with the real OpenCV primitives.  tiles: 3x3 of per-level (lap, wgt) lists
+    or None; returns the 8-bit tile the display path textures (zeros where weights[0] == 0)."""
+    centre = tiles[1][1]
+    if all(t is not None for row in tiles for t in row):   # flag == 0x1FF: borrow the neighbours' borders
+        clone = []
+        for i in range(levels):
+            b, n = 1 << (levels - i - 1), 256 >> i
+            d = n + 2 * b
+            m = np.zeros((d, d, 3), np.int16)
+            for y in range(3):
+                for x in range(3):
+                    src = tiles[y][x][i][0]
+                    w, h = (n if x == 1 else b), (n if y == 1 else b)
+                    sx, sy = (n - b if x == 0 else 0), (n - b if y == 0 else 0)
+                    dx = 0 if x == 0 else (b if x == 1 else d - b)
+                    dy = 0 if y == 0 else (b if y == 1 else d - b)
+                    m[dy:dy + h, dx:dx + w] = src[sy:sy + h, sx:sx + w]
+            clone.append(m)
+        border = 1 << (levels - 1)
+    else:
+        clone = [centre[i][0].copy() for i in range(levels)]
+        border = 0
+    for i in range(levels - 1, 0, -1):   # cv::detail::restoreImageFromLaplacePyr
+        up = cv2.pyrUp(clone[i], dstsize=(clone[i - 1].shape[1], clone[i - 1].shape[0]))
+        clone[i - 1] = cv2.add(up, clone[i - 1])
+    res = clone[0][border:border + 256, border:border + 256].copy()
+    res[centre[0][1] == 0] = 0
+    return np.clip(res, 0, 255).astype(np.uint8)   # convertTo(CV_8U) saturates
+
+
+def test_display_tile_blend_matches_opencv():
+    """The oracle's per-tile display collapse (orc_get_tile_image) against Ele::blend rebuilt from cv2.pyrUp / cv2.add on
+    the oracle's own tile state: interior tiles (all 8 neighbours) use the borrowed borders, the others collapse alone."""
+    seq = synth.Sequence(5, 1024, 768, seed=7, jitter=True, fpl=3, prepare_frames=5)
+    o = O.OracleMap2D.create(3)
+    assert o.prepare(seq.plane, seq.camera, seq.prepare_poses)
+    for k in range(seq.n):
+        assert o.feed(seq.frame(k), seq.poses[k])
+    g = o.grid()
+
+    def tile(tx, ty):
+        if not (0 <= tx < g["w"] and 0 <= ty < g["h"]) or o.get_tile(tx, ty, 0) is None:
+            return None
+        return [o.get_tile(tx, ty, l) for l in range(o.levels)]
+
+    interior = edge = 0
+    for ty in range(g["h"]):
+        for tx in range(g["w"]):
+            if tile(tx, ty) is None:
+                assert o.get_tile_image(tx, ty, True) is None
+                continue
+            nb = [[tile(tx + dx, ty + dy) for dx in (-1, 0, 1)] for dy in (-1, 0, 1)]
+            full = all(t is not None for row in nb for t in row)
+            interior += full
+            edge += not full
+            assert np.array_equal(o.get_tile_image(tx, ty, True), _blend_with_cv2(nb, o.levels)), (tx, ty, full)
+            alone = [[None] * 3, [None, nb[1][1], None], [None] * 3]
+            assert np.array_equal(o.get_tile_image(tx, ty, False), _blend_with_cv2(alone, o.levels)), (tx, ty)
+    assert interior >= 4 and edge >= 4
