@@ -15,7 +15,8 @@
  *   thread=true (Map2DCPU.cpp:119-120,139-142,397-413: worker thread + frame queue of 20, drop-oldest)
  *                                            -> m2d_ingest_open(20) at prepare(), feed() = m2d_ingest_push
  *   Map2D::draw()                            -> no-op (GL is out of scope); its data path is m2d_poll_changed +
- *                                               m2d_get_tile_image: changed tiles and their blended textures
+ *                                               m2d_get_tile_image (changed tiles, blended textures) and
+ *                                               m2d_tile_gps_corners (the Map2DUpdate overlay corners)
  */
 #ifndef MAP2D_B200_ADAPTER_H
 #define MAP2D_B200_ADAPTER_H

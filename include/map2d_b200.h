@@ -224,6 +224,15 @@ int m2d_ingest_drain(m2d_handle h);
 int m2d_ingest_close(m2d_handle h);
 int m2d_ingest_stats(m2d_handle h, uint64_t* pushed, uint64_t* dropped, uint64_t* fed, uint64_t* fused);
 
+/* Map2DUpdate — the Google-map overlay command of the display loop (MultiBandMap2DCPU.cpp:744-757, consumed by
+ * Map2DItem.cpp:36-99): GPS corners of tile (tx, ty).  Pure host arithmetic, no handle: the tile's ground corners are
+ * formed in FLOAT like the reference (`float x0 = min.x + x*eleSize`, `float x1 = x0 + eleSize`), moved to the world
+ * frame with plane * (x, y, 0) and converted by pi::calcLngLatFromDistance (PIL/src/hardware/Gps/utils_GPS.cpp:133-160,
+ * WGS-84 units of longitude/latitude at the origin's latitude).  gps_origin = {lng, lat} (svar "GPS.Origin");
+ * tl/br receive {lng, lat, 0}.  The texture that goes with it is m2d_get_tile_image (+ level-0 weights as alpha). */
+int m2d_tile_gps_corners(const double plane[7], double grid_min_x, double grid_min_y, double ele_size, int tx, int ty,
+                         const double gps_origin[2], double tl[3], double br[3]);
+
 /* Pinned host staging helpers for callers that want truly asynchronous m2d_feed(). */
 void* m2d_alloc_host(size_t bytes);
 void m2d_free_host(void* p);

@@ -1508,6 +1508,32 @@ int m2d_get_kernel_times(m2d_handle h, double* ms, uint64_t* count) {
 const char* m2d_last_error(m2d_handle h) { return h ? h->err.c_str() : "null handle"; }
 uint64_t m2d_launch_count(m2d_handle h) { return h ? h->launches : 0; }
 
+int m2d_tile_gps_corners(const double* plane7, double grid_min_x, double grid_min_y, double ele_size, int tx, int ty,
+                         const double* gps_origin, double* tl, double* br) {
+    if (!plane7 || !gps_origin || !tl || !br) return M2D_ERR_ARG;
+    // MultiBandMap2DCPU.cpp:709-712: the corners live in float variables
+    const float x0 = (float)(grid_min_x + tx * ele_size), y0 = (float)(grid_min_y + ty * ele_size);
+    const float x1 = (float)(x0 + ele_size), y1 = (float)(y0 + ele_size);
+    const Pose plane = pose_from7(plane7);
+    const double lng1 = gps_origin[0], lat1 = gps_origin[1];
+    // pi::calcLngLatFromDistance, utils_GPS.cpp:133-160 (EARTH_RADIUS 6378137, DEG2RAD 0.017453292519943, f = 1/298.257223563)
+    const double a = 6378137.0, deg2rad = 0.017453292519943, f = 1.0 / 298.257223563, e_2 = 2 * f - f * f;
+    const double phi = lat1 * deg2rad, sp = sin(phi);
+    const double lng_unit = deg2rad * a * cos(phi) / sqrt(1 - e_2 * (sp * sp));
+    const double lat_unit = deg2rad * a * (1 - e_2) / pow(1 - e_2 * (sp * sp), 1.5);
+    const float cx[2] = {x0, x1}, cy[2] = {y0, y1};
+    double* out[2] = {tl, br};
+    for (int i = 0; i < 2; i++) {
+        Vec3 v{(double)cx[i], (double)cy[i], 0.0};
+        Vec3 r = qrot(plane.r, v);                       // SE3 * point = t + R * p  (SE3.h:99-101)
+        const double wx = plane.t.x + r.x, wy = plane.t.y + r.y;
+        out[i][0] = wx / lng_unit + lng1;
+        out[i][1] = wy / lat_unit + lat1;
+        out[i][2] = 0.0;
+    }
+    return M2D_OK;
+}
+
 void* m2d_alloc_host(size_t bytes) {
     void* p = nullptr;
     if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }

@@ -48,7 +48,7 @@ EXPORTS = ["m2d_config_default", "m2d_create", "m2d_destroy", "m2d_prepare", "m2
            "m2d_last_rect", "m2d_get_tile", "m2d_get_image", "m2d_save", "m2d_tile_bytes", "m2d_tile_count",
            "m2d_export_tiles", "m2d_import_tiles", "m2d_poll_changed", "m2d_get_tile_image", "m2d_save_state", "m2d_load_state", "m2d_get_stats", "m2d_last_error",
            "m2d_launch_count", "m2d_profile", "m2d_get_kernel_times", "m2d_alloc_host", "m2d_free_host", "m2d_compute_bounds",
-           "m2d_ingest_open", "m2d_ingest_push", "m2d_ingest_pause", "m2d_ingest_drain", "m2d_ingest_close", "m2d_ingest_stats"]
+           "m2d_tile_gps_corners", "m2d_ingest_open", "m2d_ingest_push", "m2d_ingest_pause", "m2d_ingest_drain", "m2d_ingest_close", "m2d_ingest_stats"]
 
 _lib = None
 
@@ -74,6 +74,7 @@ def lib():
     L.m2d_feed_batch.argtypes = [vp, C.c_int, vp, C.c_size_t, C.c_int, C.c_int, C.c_size_t, dp, C.c_int, ip]
     L.m2d_feed_poses.argtypes = [vp, C.c_int, dp, ip]
     L.m2d_plan_rects.argtypes = [vp, C.c_int, dp, ip]
+    L.m2d_tile_gps_corners.argtypes = [dp, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, dp, dp, dp]
     L.m2d_ingest_open.argtypes = [vp, C.c_int, C.c_int]
     L.m2d_ingest_push.argtypes = [vp, vp, C.c_int, C.c_int, C.c_size_t, C.c_int, dp]
     L.m2d_ingest_pause.argtypes = [vp, C.c_int]
@@ -126,6 +127,39 @@ def default_config(**kw):
 
 def _dptr(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def tile_gps_corners(plane, grid, tx, ty, gps_origin):
+    """m2d_tile_gps_corners for a grid dict as returned by Map2D.grid() (works without a GPU: pure host arithmetic)."""
+    plane = np.ascontiguousarray(plane, np.float64).reshape(7)
+    org = np.ascontiguousarray(np.asarray(gps_origin, np.float64).reshape(-1)[:2])
+    tl, br = np.zeros(3), np.zeros(3)
+    rc = lib().m2d_tile_gps_corners(_dptr(plane), float(grid["min"][0]), float(grid["min"][1]), 256.0 * float(grid["length_pixel"]),
+                                    int(tx), int(ty), _dptr(org), _dptr(tl), _dptr(br))
+    if rc != OK:
+        raise RuntimeError("m2d_tile_gps_corners failed: %d" % rc)
+    return tl, br
+
+
+def map2d_update_command(plane, grid, tx, ty, gps_origin, image_name="LastTexMat"):
+    """`Map2DUpdate LastTexMat <tl> <br>` exactly as MultiBandMap2DCPU.cpp:754-755 formats it (fixed, 9 decimals,
+    Point3d streamed as `x y z`)."""
+    tl, br = tile_gps_corners(plane, grid, tx, ty, gps_origin)
+    return "Map2DUpdate %s %s %s" % (image_name, " ".join("%.9f" % v for v in tl), " ".join("%.9f" % v for v in br))
+
+
+def tile_overlay(map2d, tx, ty, high_quality=True):
+    """The pixmap Map2DItemHandle builds from (LastTexMat, LastTexMatWeight): rows upside-down; multi-band -> B,G,R,A
+    bytes (QImage::Format_ARGB32) with A = 255 where the level-0 weight is non-zero (Map2DItem.cpp:68-84); weighted
+    (no float weight image) -> R,G,B bytes (Map2DItem.cpp:56-67).  `map2d`: anything with get_tile_image/get_tile."""
+    img = map2d.get_tile_image(tx, ty, high_quality)
+    if img is None:
+        return None
+    if img.shape[2] == 3:
+        w0 = map2d.get_tile(tx, ty, 0)[1]
+        out = np.dstack([img, np.where(w0 != 0, 255, 0).astype(np.uint8)])
+        return np.ascontiguousarray(out[::-1])
+    return np.ascontiguousarray(img[::-1, :, 2::-1])
 
 
 def pinned_empty(shape, dtype=np.uint8):
@@ -348,6 +382,18 @@ class Map2D:
         if not self._check(rc):
             return None
         return out[:256 * 256 * cn.value].reshape(256, 256, cn.value).copy()
+
+    # --- Map2DUpdate: the Google-map overlay of the display loop (MultiBandMap2DCPU.cpp:744-757, Map2DItem.cpp:36-99) ---
+    def tile_gps_corners(self, tx, ty, plane, gps_origin):
+        """({lng,lat,0} of the tile's top-left, of its bottom-right) for GPS.Origin = (lng, lat[, alt])."""
+        return tile_gps_corners(plane, self.grid(), tx, ty, gps_origin)
+
+    def map2d_update_command(self, tx, ty, plane, gps_origin, image_name="LastTexMat"):
+        """The command string the reference sends to the MapWidget for an updated interior tile."""
+        return map2d_update_command(plane, self.grid(), tx, ty, gps_origin, image_name)
+
+    def tile_overlay(self, tx, ty, high_quality=True):
+        return tile_overlay(self, tx, ty, high_quality)
 
     # --- checkpoint / resume ----------------------------------------------------------------------------
     def save_state(self, filename):

@@ -5,6 +5,7 @@ import os
 import re
 import subprocess
 
+import numpy as np
 import pytest
 
 import pi_slam_fusion_b200.map2d as m2d
@@ -85,3 +86,74 @@ def test_product_never_imports_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dp, fn), errors="ignore").read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "map2d_oracle" not in txt, fn
+
+
+def test_map2d_update_gps_corners_follow_the_reference_formula():
+    """m2d_tile_gps_corners (pure host arithmetic, callable without a GPU) against a restatement of
+    MultiBandMap2DCPU.cpp:709-757 + pi::calcLngLatFromDistance (PIL/src/hardware/Gps/utils_GPS.cpp:133-160)."""
+    import math
+
+    def qmul(l, r):   # SO3.h:435-442, (x, y, z, w)
+        return (l[3] * r[0] + l[0] * r[3] + l[1] * r[2] - l[2] * r[1], l[3] * r[1] + l[1] * r[3] + l[2] * r[0] - l[0] * r[2],
+                l[3] * r[2] + l[2] * r[3] + l[0] * r[1] - l[1] * r[0], l[3] * r[3] - l[0] * r[0] - l[1] * r[1] - l[2] * r[2])
+
+    def expected(plane, gmin, ele, tx, ty, org):
+        f32 = lambda v: float(np.float32(v))
+        x0, y0 = f32(gmin[0] + tx * ele), f32(gmin[1] + ty * ele)
+        x1, y1 = f32(x0 + ele), f32(y0 + ele)
+        a, d2r, f = 6378137.0, 0.017453292519943, 1.0 / 298.257223563
+        e2 = 2 * f - f * f
+        phi = org[1] * d2r
+        lng_unit = d2r * a * math.cos(phi) / math.sqrt(1 - e2 * math.sin(phi) ** 2)
+        lat_unit = d2r * a * (1 - e2) / math.pow(1 - e2 * math.sin(phi) ** 2, 1.5)
+        q = tuple(plane[3:7])
+        out = []
+        for (x, y) in ((x0, y0), (x1, y1)):
+            r = qmul(qmul(q, (x, y, 0.0, 0.0)), (-q[0], -q[1], -q[2], q[3]))
+            out.append((( plane[0] + r[0]) / lng_unit + org[0], (plane[1] + r[1]) / lat_unit + org[1], 0.0))
+        return out
+
+    rng = np.random.default_rng(3)
+    for _ in range(50):
+        q = rng.normal(size=4)
+        q /= np.linalg.norm(q)
+        plane = np.concatenate([rng.uniform(-500, 500, 3), q])
+        grid = {"min": np.array([rng.uniform(-3000, 0), rng.uniform(-3000, 0), 0.0]), "length_pixel": rng.uniform(0.02, 0.5)}
+        org = (rng.uniform(-180, 180), rng.uniform(-80, 80))
+        tx, ty = int(rng.integers(0, 60)), int(rng.integers(0, 60))
+        tl, br = m2d.tile_gps_corners(plane, grid, tx, ty, org)
+        etl, ebr = expected(plane, grid["min"], 256.0 * grid["length_pixel"], tx, ty, org)
+        assert np.allclose(tl, etl, rtol=0, atol=1e-12) and np.allclose(br, ebr, rtol=0, atol=1e-12)
+    # identity plane, tile (0,0) at the origin: one tile of 256 * 0.1 m east and north of the GPS origin
+    grid = {"min": np.zeros(3), "length_pixel": 0.1}
+    tl, br = m2d.tile_gps_corners([0, 0, 0, 0, 0, 0, 1], grid, 0, 0, (108.0, 34.0))
+    assert tuple(tl) == (108.0, 34.0, 0.0)
+    assert abs((br[0] - 108.0) * 111320 * math.cos(math.radians(34)) - 25.6) < 0.1 and abs((br[1] - 34.0) * 110922 - 25.6) < 0.1
+
+
+def test_map2d_update_command_and_overlay_pixmap():
+    """The rest of the Map2DUpdate hand-over, on the CPU stand-in: the command string format of
+    MultiBandMap2DCPU.cpp:754-755 and the pixmap Map2DItemHandle builds (Map2DItem.cpp:56-84)."""
+    from oracle import oracle as O
+    import pi_slam_fusion_b200.synth as synth
+    grid = {"min": np.zeros(3), "length_pixel": 0.1}
+    cmd = m2d.map2d_update_command([0, 0, 0, 0, 0, 0, 1], grid, 0, 0, (108.888931, 34.257287, 400.0))
+    tok = cmd.split()
+    assert tok[:2] == ["Map2DUpdate", "LastTexMat"] and len(tok) == 8
+    assert tok[2] == "108.888931000" and tok[3] == "34.257287000" and tok[4] == "0.000000000" and tok[7] == "0.000000000"
+    assert all(re.fullmatch(r"-?\d+\.\d{9}", t) for t in tok[2:])
+    seq = synth.Sequence(3, 320, 180, seed=5, fpl=3, prepare_frames=3)
+    for typ in (1, 3):
+        o = O.OracleMap2D.create(typ)
+        assert o.prepare(seq.plane, seq.camera, seq.prepare_poses)
+        for k in range(seq.n):
+            assert o.feed(seq.frame(k), seq.poses[k])
+        x0, y0, x1, y1 = o.last_rect()
+        pix = m2d.tile_overlay(o, x0, y0, False)
+        img = o.get_tile_image(x0, y0, False)
+        if typ == 3:
+            w0 = o.get_tile(x0, y0, 0)[1]
+            assert pix.shape == (256, 256, 4) and np.array_equal(pix[::-1, :, :3], img)
+            assert np.array_equal(pix[::-1, :, 3] == 255, w0 != 0) and set(np.unique(pix[..., 3])) <= {0, 255}
+        else:
+            assert pix.shape == (256, 256, 3) and np.array_equal(pix[::-1, :, ::-1], img[..., :3])
