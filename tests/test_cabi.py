@@ -157,3 +157,25 @@ def test_map2d_update_command_and_overlay_pixmap():
             assert np.array_equal(pix[::-1, :, 3] == 255, w0 != 0) and set(np.unique(pix[..., 3])) <= {0, 255}
         else:
             assert pix.shape == (256, 256, 3) and np.array_equal(pix[::-1, :, ::-1], img[..., :3])
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/map2d_b200.h is a C header (C99, -pedantic clean): a C program links against the library, gets a loud
+    failure from m2d_create on a box without a GPU, and can call the handle-free host helpers."""
+    exe = str(tmp_path / "cabi_c")
+    libdir = os.path.dirname(m2d.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cabi_c", "main.c"), "-o", exe, "-L", libdir, "-lmap2d_b200",
+                           "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.strip().splitlines()
+    lng, lat = (float(v) for v in lines[-1].split())
+    assert 108.0002 < lng < 108.0004 and 34.0002 < lat < 34.0003
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if not has_gpu:
+        assert "rc=-3" in lines[0] and "no CPU path" in out.stderr
