@@ -233,6 +233,11 @@ int m2d_ingest_stats(m2d_handle h, uint64_t* pushed, uint64_t* dropped, uint64_t
 int m2d_tile_gps_corners(const double plane[7], double grid_min_x, double grid_min_y, double ele_size, int tx, int ty,
                          const double gps_origin[2], double tl[3], double br[3]);
 
+/* Introspection for tests: the dependency-reach table of the weights-first multi-band pipeline (kernels.cu
+ * make_reach_table).  lo/hi[m*6 + k] = how many 32-px cells below/above the cell of a level-m winner the Gaussian level
+ * k must be valid (255 = no dependency).  levels = band_number + 1 <= 6.  Pure host arithmetic, no handle. */
+int m2d_reach_table(int levels, unsigned char lo[36], unsigned char hi[36]);
+
 /* Pinned host staging helpers for callers that want truly asynchronous m2d_feed(). */
 void* m2d_alloc_host(size_t bytes);
 void m2d_free_host(void* p);

@@ -1534,6 +1534,15 @@ int m2d_tile_gps_corners(const double* plane7, double grid_min_x, double grid_mi
     return M2D_OK;
 }
 
+int m2d_reach_table(int levels, unsigned char* lo, unsigned char* hi) {
+    if (!lo || !hi || levels < 1 || levels > 6) return M2D_ERR_ARG;
+    unsigned char l[6][6], h[6][6];
+    make_reach_table(levels, l, h);
+    memcpy(lo, l, 36);
+    memcpy(hi, h, 36);
+    return M2D_OK;
+}
+
 void* m2d_alloc_host(size_t bytes) {
     void* p = nullptr;
     if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }

@@ -48,7 +48,7 @@ EXPORTS = ["m2d_config_default", "m2d_create", "m2d_destroy", "m2d_prepare", "m2
            "m2d_last_rect", "m2d_get_tile", "m2d_get_image", "m2d_save", "m2d_tile_bytes", "m2d_tile_count",
            "m2d_export_tiles", "m2d_import_tiles", "m2d_poll_changed", "m2d_get_tile_image", "m2d_save_state", "m2d_load_state", "m2d_get_stats", "m2d_last_error",
            "m2d_launch_count", "m2d_profile", "m2d_get_kernel_times", "m2d_alloc_host", "m2d_free_host", "m2d_compute_bounds",
-           "m2d_tile_gps_corners", "m2d_ingest_open", "m2d_ingest_push", "m2d_ingest_pause", "m2d_ingest_drain", "m2d_ingest_close", "m2d_ingest_stats"]
+           "m2d_tile_gps_corners", "m2d_reach_table", "m2d_ingest_open", "m2d_ingest_push", "m2d_ingest_pause", "m2d_ingest_drain", "m2d_ingest_close", "m2d_ingest_stats"]
 
 _lib = None
 
@@ -75,6 +75,7 @@ def lib():
     L.m2d_feed_poses.argtypes = [vp, C.c_int, dp, ip]
     L.m2d_plan_rects.argtypes = [vp, C.c_int, dp, ip]
     L.m2d_tile_gps_corners.argtypes = [dp, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, dp, dp, dp]
+    L.m2d_reach_table.argtypes = [C.c_int, C.POINTER(C.c_ubyte), C.POINTER(C.c_ubyte)]
     L.m2d_ingest_open.argtypes = [vp, C.c_int, C.c_int]
     L.m2d_ingest_push.argtypes = [vp, vp, C.c_int, C.c_int, C.c_size_t, C.c_int, dp]
     L.m2d_ingest_pause.argtypes = [vp, C.c_int]
@@ -139,6 +140,15 @@ def tile_gps_corners(plane, grid, tx, ty, gps_origin):
     if rc != OK:
         raise RuntimeError("m2d_tile_gps_corners failed: %d" % rc)
     return tl, br
+
+
+def reach_table(levels):
+    """(lo, hi) 6x6 uint8 arrays of m2d_reach_table: cells of Gaussian level k a level-m winner depends on."""
+    lo, hi = np.zeros(36, np.uint8), np.zeros(36, np.uint8)
+    rc = lib().m2d_reach_table(levels, lo.ctypes.data_as(C.POINTER(C.c_ubyte)), hi.ctypes.data_as(C.POINTER(C.c_ubyte)))
+    if rc != OK:
+        raise ValueError("m2d_reach_table(%d) failed: %d" % (levels, rc))
+    return lo.reshape(6, 6), hi.reshape(6, 6)
 
 
 def map2d_update_command(plane, grid, tx, ty, gps_origin, image_name="LastTexMat"):

@@ -1,0 +1,113 @@
+"""Host-side proofs behind the weights-first multi-band pipeline (kernels.cu "WEIGHTS-FIRST variant"), on the CPU:
+  * the reach table (which cells of which Gaussian level a winner depends on) against a brute-force walk of the actual
+    pyrUp / pyrDown taps, borders included;
+  * the FP32 weight-coordinate fast path of mbw_warp_kernel: wherever it does NOT flag a px as ambiguous, its rounded
+    source coordinate equals the exact FP64 one OpenCV computes."""
+import numpy as np
+import pytest
+
+import pi_slam_fusion_b200.map2d as m2d
+import pi_slam_fusion_b200.synth as synth
+from oracle import oracle as O
+
+
+def reflect101(p, n):
+    if n == 1:
+        return 0
+    while p < 0 or p >= n:
+        p = -p if p < 0 else 2 * n - 2 - p
+    return p
+
+
+@pytest.mark.parametrize("levels", [1, 2, 3, 4, 5, 6])
+def test_reach_table_covers_every_tap(levels):
+    lo, hi = (t.astype(int) for t in m2d.reach_table(levels))
+    tiles = 3                                     # a 3-tile-wide region: borders on both sides are exercised
+    size = [tiles * (256 >> l) for l in range(levels)]
+    worst = np.zeros((6, 6, 2), int)
+    for m in range(levels):
+        for p in range(size[m]):                  # every winner position of level m (1-D: the filters are separable)
+            need = {m: {p}}
+            if m + 1 < levels:                    # lap_quad: pyrUp taps around the quad's coarse px
+                n1 = size[m + 1]
+                i = (p & ~1) >> 1
+                need[m + 1] = {(1 if n1 > 1 else 0) if i - 1 < 0 else i - 1, i, min(i + 1, n1 - 1)}
+            top = max(need)
+            for k in range(top, 0, -1):           # pyrDown taps, BORDER_REFLECT_101
+                below = need.setdefault(k - 1, set())
+                for u in need[k]:
+                    below.update(reflect101(2 * u + d - 2, size[k - 1]) for d in range(5))
+            cwin = (p << m) >> 5
+            for k, pts in need.items():
+                assert lo[m][k] != 255, (m, k)
+                cells = [(q << k) >> 5 for q in pts]
+                assert min(cells) >= cwin - lo[m][k] and max(cells) <= cwin + hi[m][k], (levels, m, p, k, min(cells), max(cells), cwin)
+                worst[m][k] = np.maximum(worst[m][k], [cwin - min(cells), max(cells) - cwin])
+    for m in range(levels):                       # ... and the table is tight: every entry is reached by some winner
+        for k in range(levels):
+            if lo[m][k] != 255:
+                assert (worst[m][k] == [lo[m][k], hi[m][k]]).all(), (levels, m, k, worst[m][k], lo[m][k], hi[m][k])
+            else:
+                assert k > m + 1
+
+
+def fast_path(M, xs, ys, sw, sh):
+    """numpy float32 restatement of the FP32 pass of mbw_warp_kernel (one px at a time; the kernel shares den0/nx0/ny0
+    per 4-px run, which is the same arithmetic).  Returns rounded coords and the 'ambiguous' flag."""
+    f = np.float32
+    mf = M.astype(np.float32)
+    xf, yf = xs.astype(np.float32), ys.astype(np.float32)
+    x4 = (np.floor(xs / 4) * 4).astype(np.float32)           # first px of the thread's run
+    den0 = mf[7] * yf + mf[8]
+    nx0, ny0 = mf[1] * yf + mf[2], mf[4] * yf + mf[5]
+    wa, wb = mf[6] * x4 + den0, mf[6] * (x4 + f(3)) + den0
+    ok = (wa > f(1e-3)) & (wb > f(1e-3))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        rmax = np.maximum(f(1) / wa, f(1) / wb)
+        magx = (abs(mf[0]) * (x4 + f(3)) + abs(mf[1]) * yf + abs(mf[2])) * rmax
+        magy = (abs(mf[3]) * (x4 + f(3)) + abs(mf[4]) * yf + abs(mf[5])) * rmax
+        thr_x, thr_y = f(48) * f(5.97e-8) * magx + f(1e-6), f(48) * f(5.97e-8) * magy + f(1e-6)
+        r = f(1) / (mf[6] * xf + den0)
+        fx, fy = (mf[0] * xf + nx0) * r, (mf[3] * xf + ny0) * r
+    rx, ry = np.rint(fx), np.rint(fy)
+    # __fdividef is within 2 ulp of the IEEE quotient used here: widen the emulated ambiguity band accordingly
+    slack_x, slack_y = f(4) * f(5.97e-8) * magx, f(4) * f(5.97e-8) * magy
+    amb = ~ok | (f(0.5) - abs(fx - rx) < thr_x - slack_x) | (f(0.5) - abs(fy - ry) < thr_y - slack_y)
+    return rx, ry, amb
+
+
+@pytest.mark.parametrize("w,h,n,tilt", [(1280, 720, 120, False), (4000, 3000, 40, False), (1920, 1080, 60, True), (320, 180, 40, True)])
+def test_fp32_weight_coordinates_agree_with_fp64_when_not_ambiguous(w, h, n, tilt):
+    seq = synth.Sequence(n, w, h, seed=11, jitter=True)
+    poses = seq.poses.copy()
+    if tilt:   # strong roll/pitch (still accepted by the ray.down >= 0.4 test): large perspective terms
+        rng = np.random.default_rng(1)
+        for k in range(n):
+            q = synth._qmul(synth._qmul(synth._qaxis((0, 0, 1), rng.uniform(-3, 3)),
+                                        synth._qmul(synth._qaxis((0, 1, 0), rng.uniform(-0.5, 0.5)), synth._qaxis((1, 0, 0), rng.uniform(-0.5, 0.5)))),
+                            np.array([1.0, 0, 0, 0]))
+            poses[k, 3:] = q / np.linalg.norm(q)
+    m = O.OracleMap2D.create(3)
+    assert m.prepare(seq.plane, seq.camera, poses[:20])
+    rects, hinv = m.compute_bounds(poses)
+    rng = np.random.default_rng(0)
+    checked = ambiguous = 0
+    for k in range(n):
+        if rects[k, 0] == -1 and rects[k, 2] == -1:
+            continue
+        M = hinv[k].reshape(9)
+        nx, ny = (rects[k, 2] - rects[k, 0]) * 256, (rects[k, 3] - rects[k, 1]) * 256
+        xs = rng.integers(0, nx, 60000).astype(np.float64)
+        ys = rng.integers(0, ny, 60000).astype(np.float64)
+        xb = np.floor(xs / 64) * 64                  # OpenCV's association: X0 = M0*xb + M1*y + M2, then + M0*x1
+        x1 = xs - xb
+        W = 1.0 / (M[6] * xb + M[7] * ys + M[8] + M[6] * x1)
+        ex = np.rint((M[0] * xb + M[1] * ys + M[2] + M[0] * x1) * W)
+        ey = np.rint((M[3] * xb + M[4] * ys + M[5] + M[3] * x1) * W)
+        rx, ry, amb = fast_path(M, xs, ys, w, h)
+        sure = ~amb
+        assert np.array_equal(rx[sure], ex[sure]) and np.array_equal(ry[sure], ey[sure]), "frame %d" % k
+        checked += int(sure.sum())
+        ambiguous += int(amb.sum())
+    assert checked > 100000
+    assert ambiguous < 0.25 * (checked + ambiguous), "the fast path must decide the great majority of px"
