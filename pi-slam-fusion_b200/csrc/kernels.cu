@@ -895,14 +895,9 @@ __device__ __forceinline__ size_t cell_base(const GroupParams& p, int frame, int
 // intermediate (bounded per thread by `mag`), hence rnd() of both agree unless the FP32 value lies within `thr` =
 // 48 ulps(mag) of a rounding boundary (x.5).  Only those px (~2 %) take the exact FP64 path; lanes pick their own
 // ambiguous px, so a warp normally runs that path once instead of four times.  Px far outside the frame skip both.
-__global__ void __launch_bounds__(256) mbw_warp_kernel(const __grid_constant__ GroupParams p) {
-    const FrameJob& J = p.jobs[blockIdx.y];
-    const int ww = J.wnx * kEle, wh = J.wny * kEle;
-    const int bpr = J.wnx;
-    int by = blockIdx.x / bpr, bx = blockIdx.x - by * bpr;
-    if (by * 4 >= wh) return;
-    int u = bx * kEle + (threadIdx.x & 63) * 4, v = by * 4 + (threadIdx.x >> 6);
-    int x = u + J.wx * kEle, y = v + J.wy * kEle;
+// Weights of 4 consecutive region px (x..x+3 on row y, x a multiple of 4) of frame J: FP32 pass + exact FP64 redo of the
+// ambiguous px, as described above.
+__device__ __forceinline__ float4 mbw_weights4(const GroupParams& p, const FrameJob& J, int x, int y) {
     float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
     const float* mf = J.hinvf;
     const float xf = (float)x, yf = (float)y;
@@ -955,11 +950,77 @@ __global__ void __launch_bounds__(256) mbw_warp_kernel(const __grid_constant__ G
             if (j == 0) w0 = wv; else if (j == 1) w1 = wv; else if (j == 2) w2 = wv; else w3 = wv;
         }
     }
-    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.scratch + J.w_off[0]) + (size_t)v * ww + u) = make_float4(w0, w1, w2, w3);
+    return make_float4(w0, w1, w2, w3);
+}
+
+__global__ void __launch_bounds__(256) mbw_warp_kernel(const __grid_constant__ GroupParams p) {
+    const FrameJob& J = p.jobs[blockIdx.y];
+    const int ww = J.wnx * kEle, wh = J.wny * kEle;
+    const int bpr = J.wnx;
+    int by = blockIdx.x / bpr, bx = blockIdx.x - by * bpr;
+    if (by * 4 >= wh) return;
+    int u = bx * kEle + (threadIdx.x & 63) * 4, v = by * 4 + (threadIdx.x >> 6);
+    int x = u + J.wx * kEle, y = v + J.wy * kEle;
+    const float4 w = mbw_weights4(p, J, x, y);
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.scratch + J.w_off[0]) + (size_t)v * ww + u) = w;
 }
 cudaError_t launch_mbw_warp(const GroupParams& p, cudaStream_t stream) {
     dim3 g(p.max_wnx * p.max_wny * (kEle / 4), p.n_frames);
     mbw_warp_kernel<<<g, 256, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// ---- 1a'. EXPERIMENTAL (M2D_WFUSED=1, not the default, not yet measured): weight warp + first weight pyrDown in one
+// kernel.  A CTA computes a 128 x 32 block of level-0 weights plus the halo the 5-tap filter needs (136 x 35) into
+// shared memory with mbw_weights4 (the FP32 pass makes the 16 % halo cheap), writes the block to the level-0 plane
+// (mbs_decide reads it) and produces its 64 x 16 level-1 weights straight from shared memory, so level 0 is never read
+// back.  Same tiling and border handling as mb_warp_pyr_kernel: the pyrDown taps are reflected (BORDER_REFLECT_101) in
+// REGION coordinates, which always lands inside the block's own tile, so px outside the region are never needed.
+__global__ void __launch_bounds__(256) mbw_warp_pyr_kernel(const __grid_constant__ GroupParams p) {
+    __shared__ float sW[kFSH][kFSW];
+    const FrameJob& J = p.jobs[blockIdx.y];
+    const int ww = J.wnx * kEle, wh = J.wny * kEle, rw = J.nx * kEle, rh = J.ny * kEle;
+    const int bpr = ww / kFW;
+    int by = blockIdx.x / bpr, bx = blockIdx.x - by * bpr;
+    if (by * kFH >= wh) return;
+    const int x0 = bx * kFW + J.wx * kEle, y0 = by * kFH + J.wy * kEle;  // block origin, region coordinates
+    float* W0 = reinterpret_cast<float*>(p.scratch + J.w_off[0]);
+    constexpr int kGroups = (kFSW / 4) * kFSH;
+    for (int gi = threadIdx.x; gi < kGroups; gi += 256) {
+        int r = gi / (kFSW / 4), c = (gi - r * (kFSW / 4)) * 4;
+        int x = x0 - 4 + c, y = y0 - 2 + r;
+        if (x < 0 || x >= rw || y < 0 || y >= rh) continue;  // outside the region: reflected taps never read it
+        const float4 w = mbw_weights4(p, J, x, y);
+        *reinterpret_cast<float4*>(&sW[r][c]) = w;
+        if (c >= 4 && c < 4 + kFW && r >= 2 && r < 2 + kFH)   // the block itself goes to the level-0 plane
+            *reinterpret_cast<float4*>(W0 + (size_t)(y - J.wy * kEle) * ww + (x - J.wx * kEle)) = w;
+    }
+    __syncthreads();
+    const int dww = ww >> 1;
+    float* W1 = reinterpret_cast<float*>(p.scratch + J.w_off[1]);
+    const int ul = threadIdx.x & 63, vl0 = (threadIdx.x >> 6) * 4;
+    const int U = (x0 >> 1) + ul, V0 = (y0 >> 1) + vl0;  // region coordinates at level 1
+    int cs[5];
+#pragma unroll
+    for (int d = 0; d < 5; d++) cs[d] = reflect101_idx(2 * U + d - 2, rw) - (x0 - 4);
+    float hw[5];
+#pragma unroll
+    for (int r = 0; r < 11; r++) {
+        int rr = reflect101_idx(2 * V0 + r - 2, rh) - (y0 - 2);
+        const float* wr = sW[rr];
+        // f32, OpenCV 2.4.9 association: s0*6 + (s-1 + s1)*4 + s-2 + s2, left to right
+        hw[r % 5] = wr[cs[2]] * 6.f + (wr[cs[1]] + wr[cs[3]]) * 4.f + wr[cs[0]] + wr[cs[4]];
+        if (r >= 4 && (r & 1) == 0) {
+            const int k = (r - 4) >> 1, i0 = (r - 4) % 5, i1 = (r - 3) % 5, i2 = (r - 2) % 5, i3 = (r - 1) % 5, i4 = r % 5;
+            float t0 = (hw[i0] + hw[i4]) + (hw[i2] + hw[i2]);
+            float t1 = (hw[i1] + hw[i3]) + hw[i2];
+            W1[(size_t)(V0 + k - ((J.wy * kEle) >> 1)) * dww + (U - ((J.wx * kEle) >> 1))] = (t0 + t1 * 4.f) * (1.f / 256.f);
+        }
+    }
+}
+cudaError_t launch_mbw_warp_pyr(const GroupParams& p, cudaStream_t stream) {
+    dim3 g(p.max_wnx * p.max_wny * (kEle / kFW) * (kEle / kFH), p.n_frames);
+    mbw_warp_pyr_kernel<<<g, 256, 0, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -148,6 +148,7 @@ struct m2d_map {
     cudaStream_t decide_stream = nullptr;  // chain of the groups' decide stages (tile weights), ahead of the Laplacian chain
     cudaEvent_t dense_done = nullptr;      // last dense-pipeline select on the handle's stream (small groups), see run_group
     bool dense_pending = false;
+    bool fused_weight_pyr = false;  // M2D_WFUSED=1 (EXPERIMENTAL, unmeasured): weights-first pipeline with weight warp + first weight pyrDown fused
     bool fused_warp_pyr = false;    // M2D_FUSED=1: warp + first pyrDown in one shared-memory kernel (measured 7 % slower, kept for A/B)
     GroupCtx ctx[kMaxCtx];
     int ctx_next = 0;
@@ -210,6 +211,7 @@ int m2d_map::init() {
     if (const char* e = getenv("M2D_CTX")) kCtx = std::max(2, std::min(atoi(e), (int)kMaxCtx));
     if (const char* e = getenv("M2D_FUSED")) fused_warp_pyr = atoi(e) != 0;
     if (const char* e = getenv("M2D_SPARSE")) weights_first = atoi(e) != 0;
+    if (const char* e = getenv("M2D_WFUSED")) fused_weight_pyr = atoi(e) != 0;
     CU(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&decide_stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&dense_done, cudaEventDisableTiming));
@@ -696,8 +698,12 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
         for (; l_tail + 1 < levels && (!small_level(l_tail) || levels - 1 - l_tail < 2); l_tail++) {}
         // 1. weights only, dense, on the context's stream
         CU(cudaMemsetAsync(p.win, 0, flag_bytes, c.stage));
-        LAUNCHKS(M2D_K_MBW_WARP, c.stage, launch_mbw_warp(p, c.stage));
-        for (int l = 0; l < l_tail; l++) LAUNCHKS(M2D_K_MBW_PYR, c.stage, launch_mbw_pyrdown(p, l, c.stage));
+        int l_w = 0;   // first level the stand-alone weight pyrDown still has to produce from
+        if (fused_weight_pyr && levels >= 2) {
+            LAUNCHKS(M2D_K_MBW_WARP, c.stage, launch_mbw_warp_pyr(p, c.stage));   // levels 0 and 1 in one pass
+            l_w = 1;
+        } else LAUNCHKS(M2D_K_MBW_WARP, c.stage, launch_mbw_warp(p, c.stage));
+        for (int l = l_w; l < l_tail; l++) LAUNCHKS(M2D_K_MBW_PYR, c.stage, launch_mbw_pyrdown(p, l, c.stage));
         if (l_tail + 1 < levels) LAUNCHKS(M2D_K_MBW_PYR, c.stage, launch_mbw_pyrtail(p, l_tail, c.stage));
         CU(cudaEventRecord(c.staged, c.stage));
         // 2.+3. winners and need flags: the decide chain serialises groups in feed order (tile weights only), and runs

@@ -1,6 +1,8 @@
 """GPU parity tests proper: the CUDA path, called through the C-ABI, against the CPU oracle on the same seeded
 inputs.  Bar: tile footprint / indexing and all integer state bit-exact; float weights bit-exact too (tolerance
 stated: max relative error <= 1e-5 is the contract, we assert equality and report)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -377,6 +379,38 @@ def test_weights_first_and_dense_pipelines_are_bit_exact(monkeypatch, sparse):
             assert g.stats()["win_px"] == o.stats()["win_px"]
         g.close()
     # a realistic overlap pattern at full tile scale: 720p serpentine prefix, two groups
+    seq = synth.Sequence(24, 1280, 720, seed=2, fpl=6, prepare_frames=6)
+    dev = torch.from_numpy(seq.frames()).cuda()
+    g = m2d.Map2D.create(3, thread=False, batch_frames=16)
+    o = O.OracleMap2D.create(3)
+    assert g.prepare(seq.plane, seq.camera, seq.prepare_poses) and o.prepare(seq.plane, seq.camera, seq.prepare_poses)
+    g.feed_batch(dev.data_ptr(), seq.n, seq.w * seq.h * 3, seq.w, seq.h, seq.w * 3, seq.poses, True)
+    for k in range(seq.n):
+        assert o.feed(seq.frame(k), seq.poses[k])
+    g.sync()
+    compare_state(g, o, 3)
+    g.close()
+
+
+@pytest.mark.skipif(os.environ.get("M2D_TEST_EXPERIMENTAL") != "1",
+                    reason="experimental kernel variants are parity-checked on demand (M2D_TEST_EXPERIMENTAL=1)")
+def test_experimental_fused_weight_pyramid_is_bit_exact(monkeypatch):
+    """M2D_WFUSED=1: weights-first pipeline with weight warp + first weight pyrDown fused (written in round 1 without GPU
+    time left to measure it; must pass here before it may become a default)."""
+    import torch
+    monkeypatch.setenv("M2D_WFUSED", "1")
+    seq = synth.Sequence(14, 320, 180, seed=29, jitter=True, noise=True, fpl=4, prepare_frames=4)
+    dev = torch.from_numpy(seq.frames()).cuda()
+    for kw in ({}, {"band_number": 3}, {"band_number": 1}, {"shard_rank": 1, "shard_count": 2, "shard_axis": 0, "shard_span": 1}):
+        g = m2d.Map2D.create(3, thread=False, batch_frames=5, **kw)
+        o = O.OracleMap2D.create(3, **kw)
+        assert g.prepare(seq.plane, seq.camera, seq.prepare_poses) and o.prepare(seq.plane, seq.camera, seq.prepare_poses)
+        res = g.feed_batch(dev.data_ptr(), seq.n, seq.w * seq.h * 3, seq.w, seq.h, seq.w * 3, seq.poses, True)
+        for k in range(seq.n):
+            assert (res[k] == 0) == o.feed(seq.frame(k), seq.poses[k])
+        g.sync()
+        compare_state(g, o, 3)
+        g.close()
     seq = synth.Sequence(24, 1280, 720, seed=2, fpl=6, prepare_frames=6)
     dev = torch.from_numpy(seq.frames()).cuda()
     g = m2d.Map2D.create(3, thread=False, batch_frames=16)
