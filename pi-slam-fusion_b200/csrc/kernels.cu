@@ -953,6 +953,85 @@ __device__ __forceinline__ float4 mbw_weights4(const GroupParams& p, const Frame
     return make_float4(w0, w1, w2, w3);
 }
 
+// EXPERIMENTAL (M2D_WLEAN=1, not the default, never run on a GPU yet): the same contract as mbw_weights4 with a shorter
+// FP32 pass, aimed at what ncu shows for it (issue-bound; XU pipe 49 %, ALU 53 %, FP64 0.4 %):
+//   * explicit FMAs (the file is compiled with --fmad=false, which otherwise splits every a*b+c);
+//   * ONE reciprocal per run, carried to the next px by a Newton step r' = r + r*(1 - den'*r) on the FMA pipe (valid while
+//     the denominator moves by < 3.3e-5 relative per px: the quadratic error term stays below 0.02 ulp);
+//   * rounding by the 1.5*2^23 trick: t = f + 12582912 is f rounded half-to-even (|f| < 2^22), t - 12582912 the rounded
+//     value and bits(t) - 0x4B400000 the integer, so no rintf / float->int conversion goes to the quarter-rate XU pipe;
+//   * the off-frame test reuses the first and last px of the run.
+// The ambiguity band (48 ulps of the largest intermediate) and the exact FP64 redo are unchanged; the numpy emulation in
+// tests/test_weights_first_host.py checks that px the pass does not flag round like the exact FP64 path.
+__device__ __forceinline__ float4 mbw_weights4_lean(const GroupParams& p, const FrameJob& J, int x, int y) {
+    float w[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* mf = J.hinvf;
+    const float xf = (float)x, yf = (float)y;
+    const float den0 = __fmaf_rn(mf[7], yf, mf[8]), nx0 = __fmaf_rn(mf[1], yf, mf[2]), ny0 = __fmaf_rn(mf[4], yf, mf[5]);
+    const float wa = __fmaf_rn(mf[6], xf, den0), wb = __fmaf_rn(mf[6], xf + 3.f, den0);
+    const float wmin = fminf(wa, wb);
+    unsigned amb = 0xFu;
+    if (wmin > 1e-3f) {
+        const bool newton = fabsf(mf[6]) * 3.f < 1e-4f * wmin;   // uniform per frame in practice
+        float r[4], fx[4], fy[4];
+        r[0] = __fdividef(1.f, wa);
+#pragma unroll
+        for (int j = 1; j < 4; j++) {
+            const float den = __fmaf_rn(mf[6], xf + (float)j, den0);
+            r[j] = newton ? __fmaf_rn(r[j - 1], __fmaf_rn(-den, r[j - 1], 1.f), r[j - 1]) : __fdividef(1.f, den);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float xj = xf + (float)j;
+            fx[j] = __fmaf_rn(mf[0], xj, nx0) * r[j];
+            fy[j] = __fmaf_rn(mf[3], xj, ny0) * r[j];
+        }
+        const float lim_x = (float)p.sw + 0.25f, lim_y = (float)p.sh + 0.25f;
+        const bool off = (fx[0] < -1.25f && fx[3] < -1.25f) || (fx[0] > lim_x && fx[3] > lim_x) ||
+                         (fy[0] < -1.25f && fy[3] < -1.25f) || (fy[0] > lim_y && fy[3] > lim_y);
+        amb = 0u;
+        if (!off) {
+            const float rmax = fmaxf(r[0], r[3]);
+            const float magx = __fmaf_rn(fabsf(mf[0]), xf + 3.f, __fmaf_rn(fabsf(mf[1]), yf, fabsf(mf[2]))) * rmax;
+            const float magy = __fmaf_rn(fabsf(mf[3]), xf + 3.f, __fmaf_rn(fabsf(mf[4]), yf, fabsf(mf[5]))) * rmax;
+            const float thr_x = __fmaf_rn(48.f * 5.97e-8f, magx, 1e-6f), thr_y = __fmaf_rn(48.f * 5.97e-8f, magy, 1e-6f);
+            const float kMagic = 12582912.f;   // 1.5 * 2^23
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float tx = fx[j] + kMagic, ty = fy[j] + kMagic;
+                const float rx = tx - kMagic, ry = ty - kMagic;
+                const int ix = __float_as_int(tx) - 0x4B400000, iy = __float_as_int(ty) - 0x4B400000;
+                const bool sane = fabsf(fx[j]) < 2097152.f && fabsf(fy[j]) < 2097152.f;   // the trick is exact below 2^22
+                const bool near_half = (0.5f - fabsf(fx[j] - rx) < thr_x) || (0.5f - fabsf(fy[j] - ry) < thr_y);
+                if (sane && (unsigned)ix < (unsigned)p.sw && (unsigned)iy < (unsigned)p.sh) w[j] = __ldg(p.wimg + (iy * p.sw + ix));
+                if (sane && near_half) amb |= 1u << j;   // (not sane = millions of px away from the frame: weight 0 for sure)
+            }
+        }
+    }
+    if (amb) {   // exact OpenCV arithmetic for the px the FP32 pass could not decide
+        double M[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) M[i] = J.hinv[i];
+        RowBase rb = row_base(M, x, y);
+        const double x1 = (double)(x & 63);
+        while (amb) {
+            const int j = __ffs(amb) - 1;
+            amb &= amb - 1;
+            double fx, fy;
+            px_coord(M, rb, x1 + (double)j, fx, fy);
+            int nx = rnd(fx), ny = rnd(fy);
+            float wv = ((unsigned)nx < (unsigned)p.sw && (unsigned)ny < (unsigned)p.sh) ? __ldg(p.wimg + (ny * p.sw + nx)) : 0.f;
+            if (j == 0) w[0] = wv; else if (j == 1) w[1] = wv; else if (j == 2) w[2] = wv; else w[3] = wv;
+        }
+    }
+    return make_float4(w[0], w[1], w[2], w[3]);
+}
+template <bool LEAN>
+__device__ __forceinline__ float4 mbw_weights4_sel(const GroupParams& p, const FrameJob& J, int x, int y) {
+    if constexpr (LEAN) return mbw_weights4_lean(p, J, x, y);
+    else return mbw_weights4(p, J, x, y);
+}
+
 __global__ void __launch_bounds__(256) mbw_warp_kernel(const __grid_constant__ GroupParams p) {
     const FrameJob& J = p.jobs[blockIdx.y];
     const int ww = J.wnx * kEle, wh = J.wny * kEle;
@@ -964,9 +1043,20 @@ __global__ void __launch_bounds__(256) mbw_warp_kernel(const __grid_constant__ G
     const float4 w = mbw_weights4(p, J, x, y);
     *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.scratch + J.w_off[0]) + (size_t)v * ww + u) = w;
 }
-cudaError_t launch_mbw_warp(const GroupParams& p, cudaStream_t stream) {
+__global__ void __launch_bounds__(256) mbw_warp_lean_kernel(const __grid_constant__ GroupParams p) {   // EXPERIMENTAL, see mbw_weights4_lean
+    const FrameJob& J = p.jobs[blockIdx.y];
+    const int ww = J.wnx * kEle, wh = J.wny * kEle;
+    const int bpr = J.wnx;
+    int by = blockIdx.x / bpr, bx = blockIdx.x - by * bpr;
+    if (by * 4 >= wh) return;
+    int u = bx * kEle + (threadIdx.x & 63) * 4, v = by * 4 + (threadIdx.x >> 6);
+    const float4 w = mbw_weights4_lean(p, J, u + J.wx * kEle, v + J.wy * kEle);
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.scratch + J.w_off[0]) + (size_t)v * ww + u) = w;
+}
+cudaError_t launch_mbw_warp(const GroupParams& p, cudaStream_t stream, bool lean) {
     dim3 g(p.max_wnx * p.max_wny * (kEle / 4), p.n_frames);
-    mbw_warp_kernel<<<g, 256, 0, stream>>>(p);
+    if (lean) mbw_warp_lean_kernel<<<g, 256, 0, stream>>>(p);
+    else mbw_warp_kernel<<<g, 256, 0, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -976,6 +1066,7 @@ cudaError_t launch_mbw_warp(const GroupParams& p, cudaStream_t stream) {
 // (mbs_decide reads it) and produces its 64 x 16 level-1 weights straight from shared memory, so level 0 is never read
 // back.  Same tiling and border handling as mb_warp_pyr_kernel: the pyrDown taps are reflected (BORDER_REFLECT_101) in
 // REGION coordinates, which always lands inside the block's own tile, so px outside the region are never needed.
+template <bool LEAN>
 __global__ void __launch_bounds__(256) mbw_warp_pyr_kernel(const __grid_constant__ GroupParams p) {
     __shared__ float sW[kFSH][kFSW];
     const FrameJob& J = p.jobs[blockIdx.y];
@@ -990,7 +1081,7 @@ __global__ void __launch_bounds__(256) mbw_warp_pyr_kernel(const __grid_constant
         int r = gi / (kFSW / 4), c = (gi - r * (kFSW / 4)) * 4;
         int x = x0 - 4 + c, y = y0 - 2 + r;
         if (x < 0 || x >= rw || y < 0 || y >= rh) continue;  // outside the region: reflected taps never read it
-        const float4 w = mbw_weights4(p, J, x, y);
+        const float4 w = mbw_weights4_sel<LEAN>(p, J, x, y);
         *reinterpret_cast<float4*>(&sW[r][c]) = w;
         if (c >= 4 && c < 4 + kFW && r >= 2 && r < 2 + kFH)   // the block itself goes to the level-0 plane
             *reinterpret_cast<float4*>(W0 + (size_t)(y - J.wy * kEle) * ww + (x - J.wx * kEle)) = w;
@@ -1018,9 +1109,10 @@ __global__ void __launch_bounds__(256) mbw_warp_pyr_kernel(const __grid_constant
         }
     }
 }
-cudaError_t launch_mbw_warp_pyr(const GroupParams& p, cudaStream_t stream) {
+cudaError_t launch_mbw_warp_pyr(const GroupParams& p, cudaStream_t stream, bool lean) {
     dim3 g(p.max_wnx * p.max_wny * (kEle / kFW) * (kEle / kFH), p.n_frames);
-    mbw_warp_pyr_kernel<<<g, 256, 0, stream>>>(p);
+    if (lean) mbw_warp_pyr_kernel<true><<<g, 256, 0, stream>>>(p);
+    else mbw_warp_pyr_kernel<false><<<g, 256, 0, stream>>>(p);
     return cudaGetLastError();
 }
 

@@ -98,8 +98,8 @@ cudaError_t launch_mb_pyrdown(const GroupParams& p, int level /* src level */, c
 cudaError_t launch_mb_pyrtail(const GroupParams& p, int l_first, cudaStream_t stream);
 cudaError_t launch_mb_select(const GroupParams& p, const TileLayout& lay, cudaStream_t stream);
 // weights-first multi-band variant
-cudaError_t launch_mbw_warp(const GroupParams& p, cudaStream_t stream);
-cudaError_t launch_mbw_warp_pyr(const GroupParams& p, cudaStream_t stream);  // EXPERIMENTAL: weight warp + first weight pyrDown fused
+cudaError_t launch_mbw_warp(const GroupParams& p, cudaStream_t stream, bool lean = false);      // lean: EXPERIMENTAL FP32 pass
+cudaError_t launch_mbw_warp_pyr(const GroupParams& p, cudaStream_t stream, bool lean = false);  // EXPERIMENTAL: + first weight pyrDown fused
 cudaError_t launch_mbw_pyrdown(const GroupParams& p, int level, cudaStream_t stream);
 cudaError_t launch_mbw_pyrtail(const GroupParams& p, int l_first, cudaStream_t stream);
 cudaError_t launch_mbs_decide(const GroupParams& p, const TileLayout& lay, cudaStream_t stream);

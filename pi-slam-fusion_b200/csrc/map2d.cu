@@ -148,6 +148,7 @@ struct m2d_map {
     cudaStream_t decide_stream = nullptr;  // chain of the groups' decide stages (tile weights), ahead of the Laplacian chain
     cudaEvent_t dense_done = nullptr;      // last dense-pipeline select on the handle's stream (small groups), see run_group
     bool dense_pending = false;
+    bool lean_weights = false;      // M2D_WLEAN=1 (EXPERIMENTAL, never run on a GPU): shorter FP32 pass of the weight warp
     bool fused_weight_pyr = false;  // M2D_WFUSED=1 (EXPERIMENTAL, unmeasured): weights-first pipeline with weight warp + first weight pyrDown fused
     bool fused_warp_pyr = false;    // M2D_FUSED=1: warp + first pyrDown in one shared-memory kernel (measured 7 % slower, kept for A/B)
     GroupCtx ctx[kMaxCtx];
@@ -212,6 +213,7 @@ int m2d_map::init() {
     if (const char* e = getenv("M2D_FUSED")) fused_warp_pyr = atoi(e) != 0;
     if (const char* e = getenv("M2D_SPARSE")) weights_first = atoi(e) != 0;
     if (const char* e = getenv("M2D_WFUSED")) fused_weight_pyr = atoi(e) != 0;
+    if (const char* e = getenv("M2D_WLEAN")) lean_weights = atoi(e) != 0;
     CU(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&decide_stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&dense_done, cudaEventDisableTiming));
@@ -700,9 +702,9 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
         CU(cudaMemsetAsync(p.win, 0, flag_bytes, c.stage));
         int l_w = 0;   // first level the stand-alone weight pyrDown still has to produce from
         if (fused_weight_pyr && levels >= 2) {
-            LAUNCHKS(M2D_K_MBW_WARP, c.stage, launch_mbw_warp_pyr(p, c.stage));   // levels 0 and 1 in one pass
+            LAUNCHKS(M2D_K_MBW_WARP, c.stage, launch_mbw_warp_pyr(p, c.stage, lean_weights));   // levels 0 and 1 in one pass
             l_w = 1;
-        } else LAUNCHKS(M2D_K_MBW_WARP, c.stage, launch_mbw_warp(p, c.stage));
+        } else LAUNCHKS(M2D_K_MBW_WARP, c.stage, launch_mbw_warp(p, c.stage, lean_weights));
         for (int l = l_w; l < l_tail; l++) LAUNCHKS(M2D_K_MBW_PYR, c.stage, launch_mbw_pyrdown(p, l, c.stage));
         if (l_tail + 1 < levels) LAUNCHKS(M2D_K_MBW_PYR, c.stage, launch_mbw_pyrtail(p, l_tail, c.stage));
         CU(cudaEventRecord(c.staged, c.stage));

@@ -394,11 +394,15 @@ def test_weights_first_and_dense_pipelines_are_bit_exact(monkeypatch, sparse):
 
 @pytest.mark.skipif(os.environ.get("M2D_TEST_EXPERIMENTAL") != "1",
                     reason="experimental kernel variants are parity-checked on demand (M2D_TEST_EXPERIMENTAL=1)")
-def test_experimental_fused_weight_pyramid_is_bit_exact(monkeypatch):
-    """M2D_WFUSED=1: weights-first pipeline with weight warp + first weight pyrDown fused.  Passed on the B200 at the end
-    of round 1 but was never timed there; it stays opt-in (and this test on demand) until it has been measured."""
+@pytest.mark.parametrize("variant", [{"M2D_WFUSED": "1"}, {"M2D_WLEAN": "1"}, {"M2D_WFUSED": "1", "M2D_WLEAN": "1"}])
+def test_experimental_weight_kernels_are_bit_exact(monkeypatch, variant):
+    """Opt-in variants of the weights-first pipeline's weight stage.  M2D_WFUSED=1 (weight warp + first weight pyrDown
+    fused) passed this test on the B200 at the end of round 1 but was never timed; M2D_WLEAN=1 (shorter FP32 pass:
+    explicit FMAs, Newton-carried reciprocal, magic-number rounding) has only been checked by the numpy emulation in
+    tests/test_weights_first_host.py.  Both stay opt-in, and this test on demand, until measured."""
     import torch
-    monkeypatch.setenv("M2D_WFUSED", "1")
+    for k, v in variant.items():
+        monkeypatch.setenv(k, v)
     seq = synth.Sequence(14, 320, 180, seed=29, jitter=True, noise=True, fpl=4, prepare_frames=4)
     dev = torch.from_numpy(seq.frames()).cuda()
     for kw in ({}, {"band_number": 3}, {"band_number": 1}, {"shard_rank": 1, "shard_count": 2, "shard_axis": 0, "shard_span": 1}):

@@ -76,8 +76,55 @@ def fast_path(M, xs, ys, sw, sh):
     return rx, ry, amb
 
 
+def fma32(a, b, c):
+    """__fmaf_rn for float32 arrays: the product of two floats is exact in float64, one rounding to float32 at the end
+    (the intermediate float64 sum rounds first; a double rounding can differ from the true FMA by 1 ulp in ~1e-9 of cases,
+    far inside the 48-ulp band this test is about)."""
+    return (np.asarray(a, np.float64) * np.asarray(b, np.float64) + np.asarray(c, np.float64)).astype(np.float32)
+
+
+def lean_path(M, xs, ys, sw, sh):
+    """numpy restatement of the EXPERIMENTAL mbw_weights4_lean FP32 pass: explicit FMAs, one reciprocal per 4-px run carried
+    by Newton steps, rounding by the 1.5*2^23 trick."""
+    f = np.float32
+    mf = M.astype(np.float32)
+    xf, yf = xs.astype(np.float32), ys.astype(np.float32)
+    x4 = (np.floor(xs / 4) * 4).astype(np.float32)
+    jj = (xs - np.floor(xs / 4) * 4).astype(int)
+    den0, nx0, ny0 = fma32(mf[7], yf, mf[8]), fma32(mf[1], yf, mf[2]), fma32(mf[4], yf, mf[5])
+    wa, wb = fma32(mf[6], x4, den0), fma32(mf[6], x4 + f(3), den0)
+    wmin = np.minimum(wa, wb)
+    ok = wmin > f(1e-3)
+    newton = abs(mf[6]) * f(3) < f(1e-4) * wmin
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        r = f(1) / wa
+        r3 = r.copy()
+        for j in range(1, 4):
+            den = fma32(mf[6], x4 + f(j), den0)
+            step = np.where(newton, fma32(r3, fma32(-den, r3, f(1)), r3), f(1) / den).astype(np.float32)
+            r3 = step
+            r = np.where(jj >= j, step, r).astype(np.float32)     # the reciprocal this px ends up with
+        fx, fy = fma32(mf[0], xf, nx0) * r, fma32(mf[3], xf, ny0) * r
+        rmax = np.maximum(f(1) / wa, r3)
+        magx = fma32(abs(mf[0]), x4 + f(3), fma32(abs(mf[1]), yf, abs(mf[2]))) * rmax
+        magy = fma32(abs(mf[3]), x4 + f(3), fma32(abs(mf[4]), yf, abs(mf[5]))) * rmax
+        thr_x, thr_y = fma32(f(48) * f(5.97e-8), magx, f(1e-6)), fma32(f(48) * f(5.97e-8), magy, f(1e-6))
+        magic = f(12582912.0)
+        tx, ty = (fx + magic).astype(np.float32), (fy + magic).astype(np.float32)
+        rx, ry = tx - magic, ty - magic
+        ix = tx.view(np.int32) - 0x4B400000
+        iy = ty.view(np.int32) - 0x4B400000
+        sane = (abs(fx) < f(2097152)) & (abs(fy) < f(2097152))
+        slack_x, slack_y = f(4) * f(5.97e-8) * magx, f(4) * f(5.97e-8) * magy     # __fdividef vs IEEE division
+        amb = ~ok | (sane & ((f(0.5) - abs(fx - rx) < thr_x - slack_x) | (f(0.5) - abs(fy - ry) < thr_y - slack_y)))
+    assert np.array_equal(ix[sane & ok].astype(np.float32), rx[sane & ok]), "bits(t) - 0x4B400000 must be the rounded value"
+    far = ok & ~sane      # millions of px away: the kernel writes weight 0 without asking the exact path
+    return np.where(far, f(-1e9), rx), np.where(far, f(-1e9), ry), amb, far
+
+
+@pytest.mark.parametrize("variant", ["default", "lean"])
 @pytest.mark.parametrize("w,h,n,tilt", [(1280, 720, 120, False), (4000, 3000, 40, False), (1920, 1080, 60, True), (320, 180, 40, True)])
-def test_fp32_weight_coordinates_agree_with_fp64_when_not_ambiguous(w, h, n, tilt):
+def test_fp32_weight_coordinates_agree_with_fp64_when_not_ambiguous(w, h, n, tilt, variant):
     seq = synth.Sequence(n, w, h, seed=11, jitter=True)
     poses = seq.poses.copy()
     if tilt:   # strong roll/pitch (still accepted by the ray.down >= 0.4 test): large perspective terms
@@ -104,8 +151,14 @@ def test_fp32_weight_coordinates_agree_with_fp64_when_not_ambiguous(w, h, n, til
         W = 1.0 / (M[6] * xb + M[7] * ys + M[8] + M[6] * x1)
         ex = np.rint((M[0] * xb + M[1] * ys + M[2] + M[0] * x1) * W)
         ey = np.rint((M[3] * xb + M[4] * ys + M[5] + M[3] * x1) * W)
-        rx, ry, amb = fast_path(M, xs, ys, w, h)
-        sure = ~amb
+        if variant == "lean":
+            rx, ry, amb, far = lean_path(M, xs, ys, w, h)
+            inside = (ex >= 0) & (ex < w) & (ey >= 0) & (ey < h)
+            assert not (far & inside).any(), "a px declared 'far outside' must really be outside the frame"
+            sure = ~amb & ~far
+        else:
+            rx, ry, amb = fast_path(M, xs, ys, w, h)
+            sure = ~amb
         assert np.array_equal(rx[sure], ex[sure]) and np.array_equal(ry[sure], ey[sure]), "frame %d" % k
         checked += int(sure.sum())
         ambiguous += int(amb.sum())
