@@ -164,3 +164,70 @@ def test_fp32_weight_coordinates_agree_with_fp64_when_not_ambiguous(w, h, n, til
         ambiguous += int(amb.sum())
     assert checked > 100000
     assert ambiguous < 0.25 * (checked + ambiguous), "the fast path must decide the great majority of px"
+
+
+def level_weight_upper_bound(mf, x0, y0, x1, y1, sw, sh, weight_type):
+    """Upper bound of a frame's level-l weight over a set of level-l px, given the level-0 rect [x0,x1] x [y0,y1]
+    (region px, inclusive) that contains the supports of those px.  FP32 throughout, as a kernel would evaluate it:
+    the image of the rect under the inverse homography is the convex hull of its 4 mapped corners (denominators
+    positive), its bounding box grown by 1 px covers every rounded sampling position, and the weight image decreases
+    with the distance to the frame centre — so the weight at the box's point nearest to the centre bounds them all.
+    PyrDown is a convex combination (borders reflect inwards), so coarser levels inherit the bound; (1 + 3e-5) covers
+    the float rounding of up to five filter passes.  A plan for round 2 (cull entries in the decide stage without
+    loading them); validated here against real weight pyramids."""
+    f = np.float32
+    xs = np.array([x0, x1, x0, x1], np.float32)
+    ys = np.array([y0, y0, y1, y1], np.float32)
+    den = mf[6] * xs + mf[7] * ys + mf[8]
+    if (den <= f(1e-3)).any():
+        return np.inf
+    sx, sy = (mf[0] * xs + mf[1] * ys + mf[2]) / den, (mf[3] * xs + mf[4] * ys + mf[5]) / den
+    bx0, bx1, by0, by1 = sx.min() - f(1), sx.max() + f(1), sy.min() - f(1), sy.max() + f(1)
+    if bx1 < f(-0.5) or bx0 > f(sw) - f(0.5) or by1 < f(-0.5) or by0 > f(sh) - f(0.5):
+        return 0.0   # the whole set samples outside the frame
+    xc, yc = f(sw // 2), f(sh // 2)
+    dx = max(f(0), bx0 - xc, xc - bx1)
+    dy = max(f(0), by0 - yc, yc - by1)
+    dis = f(1) - min(np.sqrt(dx * dx + dy * dy) / np.sqrt(xc * xc + yc * yc), f(1))
+    v = dis if weight_type == 0 else dis * dis
+    return float(max(v, f(1e-5)) * f(1 + 3e-5) + f(1e-7))
+
+
+@pytest.mark.parametrize("w,h,weight_type,tilt", [(320, 180, 0, False), (320, 180, 1, True), (1280, 720, 0, True)])
+def test_level_weight_upper_bound_is_conservative(w, h, weight_type, tilt):
+    seq = synth.Sequence(12, w, h, seed=17, jitter=True)
+    poses = seq.poses.copy()
+    if tilt:
+        rng = np.random.default_rng(2)
+        for k in range(seq.n):
+            q = synth._qmul(synth._qmul(synth._qaxis((0, 0, 1), rng.uniform(-3, 3)),
+                                        synth._qmul(synth._qaxis((0, 1, 0), rng.uniform(-0.4, 0.4)), synth._qaxis((1, 0, 0), rng.uniform(-0.4, 0.4)))),
+                            np.array([1.0, 0, 0, 0]))
+            poses[k, 3:] = q / np.linalg.norm(q)
+    m = O.OracleMap2D.create(3, weight_type=weight_type)
+    assert m.prepare(seq.plane, seq.camera, poses[:6])
+    rects, hinv = m.compute_bounds(poses)
+    wimg = O.weight_image_f32(w, h, weight_type)
+    rng = np.random.default_rng(3)
+    levels, checked, useful = 6, 0, 0
+    for k in range(0, seq.n, 3 if w > 1000 else 1):
+        if rects[k, 2] <= rects[k, 0]:
+            continue
+        nx, ny = (rects[k, 2] - rects[k, 0]) * 256, (rects[k, 3] - rects[k, 1]) * 256
+        pyr = [O.warp_f32_nearest(wimg, np.linalg.inv(hinv[k]), (nx, ny))]
+        for _ in range(levels - 1):
+            pyr.append(O.pyrdown_f32(pyr[-1]))
+        mf = hinv[k].reshape(9).astype(np.float32)
+        for l in range(levels):
+            R = 0 if l == 0 else (2 << l) - 2          # level-0 half-support of a level-l px: 2^(l+1) - 2
+            H, Wd = pyr[l].shape
+            for _ in range(150):
+                cw, chh = min(64, Wd), min(max(2, 2 * (32 * 2 // max(min(64, Wd), 1))), H)   # a warp's px set: 64 x 2, or full rows
+                X0, Y0 = int(rng.integers(0, Wd - cw + 1)), int(rng.integers(0, H - chh + 1)) & ~1
+                actual = float(pyr[l][Y0:Y0 + chh, X0:X0 + cw].max())
+                ub = level_weight_upper_bound(mf, (X0 << l) - R, (Y0 << l) - R, ((X0 + cw - 1) << l) + R, ((Y0 + chh - 1) << l) + R,
+                                              w, h, weight_type)
+                assert ub >= actual, (k, l, X0, Y0, ub, actual)
+                checked += 1
+                useful += ub < 0.5
+    assert checked > 1000 and useful > 0.1 * checked, "the bound must also be tight enough to reject far-away frames"
