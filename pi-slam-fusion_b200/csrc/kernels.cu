@@ -1332,6 +1332,157 @@ cudaError_t launch_mbs_decide(const GroupParams& p, const TileLayout& lay, cudaS
     return cudaGetLastError();
 }
 
+// ---- 2'. EXPERIMENTAL (M2D_DCULL=1, not the default, never run on a GPU yet): decide with best-first order and
+// bound-based culling.  "Largest weight, latest frame on ties" (what the sequential `>=` scan leaves behind, the
+// pre-existing state counting as frame -1) is order-free, so the host sorts a tile's frames by footprint-centre distance
+// and the kernel skips, without loading anything, every frame whose weight UPPER BOUND over the warp's px is below the
+// warp's current minimum.  The bound (validated against real weight pyramids in tests/test_weights_first_host.py,
+// level_weight_upper_bound): the level-0 support rect of the warp's px, mapped through the inverse homography by its 4
+// corners, bounding box grown by 1 px; the radial weight at the box's point nearest to the frame centre bounds every
+// sample, and pyrDown (a convex combination whose borders reflect inwards) cannot exceed it beyond float rounding.
+// Lane i bounds frame c0+i, as in weighted_group_kernel.  Not used with collect_stats (the win counters follow the
+// sequential semantics).
+__device__ __forceinline__ float level_weight_upper_bound(const GroupParams& p, const float* __restrict__ m, float x0, float y0, float x1, float y1) {
+    float bx0 = 3.0e38f, bx1 = -3.0e38f, by0 = 3.0e38f, by1 = -3.0e38f;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const float x = (c & 1) ? x1 : x0, y = (c & 2) ? y1 : y0;
+        const float den = m[6] * x + m[7] * y + m[8];
+        if (!(den > 1e-3f)) return INFINITY;   // cannot reason about this frame here: never cull it
+        const float r = 1.f / den;
+        const float sx = (m[0] * x + m[1] * y + m[2]) * r, sy = (m[3] * x + m[4] * y + m[5]) * r;
+        bx0 = fminf(bx0, sx); bx1 = fmaxf(bx1, sx); by0 = fminf(by0, sy); by1 = fmaxf(by1, sy);
+    }
+    bx0 -= 1.f; bx1 += 1.f; by0 -= 1.f; by1 += 1.f;
+    if (bx1 < -0.5f || bx0 > (float)p.sw - 0.5f || by1 < -0.5f || by0 > (float)p.sh - 0.5f) return 0.f;   // samples outside the frame only
+    const float xc = (float)(p.sw / 2), yc = (float)(p.sh / 2);
+    const float dx = fmaxf(0.f, fmaxf(bx0 - xc, xc - bx1)), dy = fmaxf(0.f, fmaxf(by0 - yc, yc - by1));
+    const float dis = 1.f - fminf(sqrtf(dx * dx + dy * dy) / sqrtf(xc * xc + yc * yc), 1.f);
+    const float v = p.weight_type == 0 ? dis : dis * dis;
+    return fmaxf(v, 1e-5f) * (1.f + 3e-5f) + 1e-7f;
+}
+
+__global__ void __launch_bounds__(256, 6) mbs_decide_bf_kernel(const __grid_constant__ GroupParams p, const __grid_constant__ TileLayout lay) {
+    const TileWork T = p.tiles[blockIdx.x];
+    int q = blockIdx.y * 256 + threadIdx.x;
+    int l = 0, n = kEle, half = kEle / 2;
+    for (; l < p.levels; l++) {
+        n = kEle >> l;
+        half = n > 1 ? n / 2 : 1;
+        int cnt = half * half;
+        if (q < cnt) break;
+        q -= cnt;
+    }
+    const bool valid = l < p.levels;
+    if (!valid) { l = p.levels - 1; n = kEle >> l; half = n > 1 ? n / 2 : 1; q = 0; }
+    const int qy = q / half, qx = q - qy * half;
+    const int py = qy * 2, px = qx * 2;
+    const bool quad = n > 1;
+    const size_t to = (size_t)py * n + px;
+    float* tw = reinterpret_cast<float*>(T.state + lay.wgt_off[l]) + to;
+    float bw[4];
+    if (T.fresh) { bw[0] = bw[1] = bw[2] = bw[3] = -INFINITY; }
+    else if (quad) {
+        float2 t0 = *reinterpret_cast<const float2*>(tw), t1 = *reinterpret_cast<const float2*>(tw + n);
+        bw[0] = t0.x; bw[1] = t0.y; bw[2] = t1.x; bw[3] = t1.y;
+    } else { bw[0] = tw[0]; bw[1] = bw[2] = bw[3] = INFINITY; }   // px that do not exist never lower the warp minimum
+    int best[4] = {-1, -1, -1, -1};    // position of the winner in the tile's (sorted) entry list
+    int bestf[4] = {-1, -1, -1, -1};   // its frame index = feed order; -1 = the state, which loses every tie
+    const int lane = threadIdx.x & 31;
+    const bool uniform = __all_sync(0xffffffffu, valid && l == __shfl_sync(0xffffffffu, l, 0));
+    // the warp's px set as a rect of level-l px of the tile, and its level-0 support
+    const int pxlo = __reduce_min_sync(0xffffffffu, px), pxhi = __reduce_max_sync(0xffffffffu, px + (quad ? 1 : 0));
+    const int pylo = __reduce_min_sync(0xffffffffu, py), pyhi = __reduce_max_sync(0xffffffffu, py + (quad ? 1 : 0));
+    const int R = l == 0 ? 0 : (2 << l) - 2;
+    for (int c0 = 0; c0 < T.count; c0 += 32) {
+        unsigned long long wb = 0ull;
+        int stride = 0, myframe = 0;
+        float ub = INFINITY;
+        if (c0 + lane < T.count) {
+            const TileEntry E = p.entries[T.first + c0 + lane];
+            const FrameJob& J = p.jobs[E.frame];
+            myframe = E.frame;
+            stride = J.wnx * n;
+            wb = reinterpret_cast<unsigned long long>(p.scratch + J.w_off[l]) +
+                 4ull * ((size_t)((E.rty - J.wy) * n) * stride + (size_t)((E.rtx - J.wx) * n));
+            if (uniform) {
+                const int ox = E.rtx * n, oy = E.rty * n;   // the tile's origin in the frame's region, level-l px
+                ub = level_weight_upper_bound(p, J.hinvf, (float)(((ox + pxlo) << l) - R), (float)(((oy + pylo) << l) - R),
+                                              (float)(((ox + pxhi) << l) + R), (float)(((oy + pyhi) << l) + R));
+            }
+        }
+        float mine = fminf(fminf(bw[0], bw[1]), fminf(bw[2], bw[3]));
+        float wmin = uniform ? __int_as_float(__reduce_min_sync(0xffffffffu, __float_as_int(fmaxf(mine, 0.f)))) : -INFINITY;  // >= 0: int order == float order
+        if (T.fresh && __any_sync(0xffffffffu, mine == -INFINITY)) wmin = -INFINITY;   // nothing decided yet somewhere in the warp
+        unsigned mask = __ballot_sync(0xffffffffu, c0 + lane < T.count && ub >= wmin);
+        while (mask) {
+            const int i = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const float* W = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, wb, i));
+            const int st = __shfl_sync(0xffffffffu, stride, i);
+            const int fr = __shfl_sync(0xffffffffu, myframe, i);
+            const float* qp = W + (size_t)py * st + px;
+            float s[4];
+            if (quad) {
+                float2 t0 = *reinterpret_cast<const float2*>(qp), t1 = *reinterpret_cast<const float2*>(qp + st);
+                s[0] = t0.x; s[1] = t0.y; s[2] = t1.x; s[3] = t1.y;
+            } else { s[0] = qp[0]; s[1] = s[2] = s[3] = -INFINITY; }
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if ((quad || k == 0) && (s[k] > bw[k] || (s[k] == bw[k] && fr > bestf[k]))) { bw[k] = s[k]; best[k] = c0 + i; bestf[k] = fr; }
+            if (uniform && mask) {   // the state only improves: re-filter what is still queued
+                mine = fminf(fminf(bw[0], bw[1]), fminf(bw[2], bw[3]));
+                const bool undecided = __any_sync(0xffffffffu, mine == -INFINITY);
+                wmin = undecided ? -INFINITY : __int_as_float(__reduce_min_sync(0xffffffffu, __float_as_int(fmaxf(mine, 0.f))));
+                mask &= __ballot_sync(0xffffffffu, ub >= wmin);
+            }
+        }
+    }
+    if (!valid) return;
+    uint16_t* wm = p.wmap + (size_t)blockIdx.x * p.wmap_stride + lay.px_off[l] + to;
+    if (!quad) {
+        wm[0] = (uint16_t)(best[0] < 0 ? 0xFFFF : best[0]);
+        if (best[0] >= 0) tw[0] = bw[0];
+    } else {
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            const int k0 = 2 * r, k1 = 2 * r + 1;
+            *reinterpret_cast<ushort2*>(wm + (size_t)r * n) =
+                make_ushort2((unsigned short)(best[k0] < 0 ? 0xFFFF : best[k0]), (unsigned short)(best[k1] < 0 ? 0xFFFF : best[k1]));
+            float* wr = tw + (size_t)r * n;
+            if (best[k0] >= 0 && best[k1] >= 0) *reinterpret_cast<float2*>(wr) = make_float2(bw[k0], bw[k1]);
+            else if (best[k0] >= 0) wr[0] = bw[k0];
+            else if (best[k1] >= 0) wr[1] = bw[k1];
+        }
+    }
+    size_t marked[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        marked[k] = ~(size_t)0;
+        if (best[k] < 0) continue;
+        const TileEntry E = p.entries[T.first + best[k]];
+        const FrameJob& J = p.jobs[E.frame];
+        int wpx = (E.rtx - J.wx) * n + px + (k & 1), wpy = (E.rty - J.wy) * n + py + (k >> 1);
+        size_t idx = cell_base(p, E.frame, l) + (size_t)((wpy << l) >> 5) * (J.wnx * 8) + ((wpx << l) >> 5);
+        bool dup = false;
+#pragma unroll
+        for (int k2 = 0; k2 < k; k2++) dup |= marked[k2] == idx;
+        marked[k] = idx;
+        if (!dup && !p.win[idx]) p.win[idx] = 1;
+    }
+}
+cudaError_t launch_mbs_decide_bf(const GroupParams& p, const TileLayout& lay, cudaStream_t stream) {
+    if (p.n_tiles == 0) return cudaSuccess;
+    int quads = 0;
+    for (int l = 0; l < p.levels; l++) {
+        int n = kEle >> l, half = n > 1 ? n / 2 : 1;
+        quads += half * half;
+    }
+    dim3 g(p.n_tiles, (quads + 255) / 256);
+    mbs_decide_bf_kernel<<<g, 256, 0, stream>>>(p, lay);
+    return cudaGetLastError();
+}
+
 // ---- 3. propagate: need[k] = cells within reach of a win.  A win of level m in cell c' needs G_k valid in cells
 // [c' - reach_lo[m][k], c' + reach_hi[m][k]] (both axes): the host derives the table by interval arithmetic over the
 // exact taps (make_reach_table).  One thread per (frame, level, cell).

@@ -103,6 +103,7 @@ cudaError_t launch_mbw_warp_pyr(const GroupParams& p, cudaStream_t stream, bool 
 cudaError_t launch_mbw_pyrdown(const GroupParams& p, int level, cudaStream_t stream);
 cudaError_t launch_mbw_pyrtail(const GroupParams& p, int l_first, cudaStream_t stream);
 cudaError_t launch_mbs_decide(const GroupParams& p, const TileLayout& lay, cudaStream_t stream);
+cudaError_t launch_mbs_decide_bf(const GroupParams& p, const TileLayout& lay, cudaStream_t stream);  // EXPERIMENTAL: best-first + bound culling
 cudaError_t launch_mbs_propagate(const GroupParams& p, cudaStream_t stream);
 void make_reach_table(int levels, unsigned char lo_tab[6][6], unsigned char hi_tab[6][6]);
 cudaError_t launch_mbs_warp(const GroupParams& p, cudaStream_t stream);

@@ -148,6 +148,7 @@ struct m2d_map {
     cudaStream_t decide_stream = nullptr;  // chain of the groups' decide stages (tile weights), ahead of the Laplacian chain
     cudaEvent_t dense_done = nullptr;      // last dense-pipeline select on the handle's stream (small groups), see run_group
     bool dense_pending = false;
+    bool decide_cull = false;       // M2D_DCULL=1 (EXPERIMENTAL, never run on a GPU): best-first decide stage with bound-based culling
     bool lean_weights = false;      // M2D_WLEAN=1 (EXPERIMENTAL, never run on a GPU): shorter FP32 pass of the weight warp
     bool fused_weight_pyr = false;  // M2D_WFUSED=1 (EXPERIMENTAL, unmeasured): weights-first pipeline with weight warp + first weight pyrDown fused
     bool fused_warp_pyr = false;    // M2D_FUSED=1: warp + first pyrDown in one shared-memory kernel (measured 7 % slower, kept for A/B)
@@ -214,6 +215,7 @@ int m2d_map::init() {
     if (const char* e = getenv("M2D_SPARSE")) weights_first = atoi(e) != 0;
     if (const char* e = getenv("M2D_WFUSED")) fused_weight_pyr = atoi(e) != 0;
     if (const char* e = getenv("M2D_WLEAN")) lean_weights = atoi(e) != 0;
+    if (const char* e = getenv("M2D_DCULL")) decide_cull = atoi(e) != 0;
     CU(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&decide_stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&dense_done, cudaEventDisableTiming));
@@ -652,7 +654,9 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
     // Weighted mode visits a tile's frames best-first (closest footprint centre first): the result is order-free
     // ("largest alpha, earliest frame on ties", tracked per px by the kernel) and almost every later frame is then
     // rejected by the alpha upper bound before any sampling.  With collect_stats the sequential order is kept.
-    const bool best_first = (type != M2D_TYPE_MULTIBAND) && !cfg.collect_stats;
+    // (multi-band: only the experimental best-first decide stage wants it, M2D_DCULL=1; its rule "largest weight, latest
+    // frame on ties" is order-free as well)
+    const bool best_first = ((type != M2D_TYPE_MULTIBAND) || (sparse && decide_cull)) && !cfg.collect_stats;
     for (size_t t = 0; t < tiles.size(); t++) {
         if (best_first && per_tile[t].size() > 1) {
             float cx = (float)tile_abs[t].first + 0.5f, cy = (float)tile_abs[t].second + 0.5f;
@@ -716,7 +720,8 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
             CU(cudaStreamWaitEvent(ds, dense_done, 0));
             dense_pending = false;
         }
-        LAUNCHKS(M2D_K_MBS_DECIDE, ds, launch_mbs_decide(p, lay, ds));
+        if (decide_cull && !cfg.collect_stats) LAUNCHKS(M2D_K_MBS_DECIDE, ds, launch_mbs_decide_bf(p, lay, ds));
+        else LAUNCHKS(M2D_K_MBS_DECIDE, ds, launch_mbs_decide(p, lay, ds));
         LAUNCHKS(M2D_K_MBS_PROPAGATE, ds, launch_mbs_propagate(p, ds));
         CU(cudaEventRecord(c.decided, ds));
         // 4. image work in the needed cells, back on the context's stream

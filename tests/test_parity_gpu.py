@@ -394,12 +394,15 @@ def test_weights_first_and_dense_pipelines_are_bit_exact(monkeypatch, sparse):
 
 @pytest.mark.skipif(os.environ.get("M2D_TEST_EXPERIMENTAL") != "1",
                     reason="experimental kernel variants are parity-checked on demand (M2D_TEST_EXPERIMENTAL=1)")
-@pytest.mark.parametrize("variant", [{"M2D_WFUSED": "1"}, {"M2D_WLEAN": "1"}, {"M2D_WFUSED": "1", "M2D_WLEAN": "1"}])
+@pytest.mark.parametrize("variant", [{"M2D_WFUSED": "1"}, {"M2D_WLEAN": "1"}, {"M2D_WFUSED": "1", "M2D_WLEAN": "1"}, {"M2D_DCULL": "1"},
+                                     {"M2D_WFUSED": "1", "M2D_WLEAN": "1", "M2D_DCULL": "1"}])
 def test_experimental_weight_kernels_are_bit_exact(monkeypatch, variant):
     """Opt-in variants of the weights-first pipeline's weight stage.  M2D_WFUSED=1 (weight warp + first weight pyrDown
     fused) passed this test on the B200 at the end of round 1 but was never timed; M2D_WLEAN=1 (shorter FP32 pass:
     explicit FMAs, Newton-carried reciprocal, magic-number rounding) has only been checked by the numpy emulation in
-    tests/test_weights_first_host.py.  Both stay opt-in, and this test on demand, until measured."""
+    tests/test_weights_first_host.py; M2D_DCULL=1 (best-first decide stage that skips frames whose weight upper bound
+    cannot win) has its bound and its order-free rule checked on the CPU only.  All stay opt-in, and this test on
+    demand, until they have run and been measured on a GPU."""
     import torch
     for k, v in variant.items():
         monkeypatch.setenv(k, v)

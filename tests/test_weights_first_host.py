@@ -231,3 +231,26 @@ def test_level_weight_upper_bound_is_conservative(w, h, weight_type, tilt):
                 checked += 1
                 useful += ub < 0.5
     assert checked > 1000 and useful > 0.1 * checked, "the bound must also be tight enough to reject far-away frames"
+
+
+def test_latest_maximum_rule_equals_the_sequential_scan():
+    """The reference updates a px with `if (srcW >= dstW)` frame after frame (MultiBandMap2DCPU.cpp:539-547).  What that
+    leaves behind is order-free: the largest weight wins, the LATEST frame among equals, and the state that was there
+    before only survives if it is strictly larger than every frame.  (Basis of the experimental best-first decide stage.)"""
+    rng = np.random.default_rng(4)
+    for _ in range(2000):
+        n = int(rng.integers(1, 9))
+        vals = rng.choice([0.0, 1e-5, 0.25, 0.5, 0.75], size=n + 1).astype(np.float32)   # few distinct values: many ties
+        fresh = bool(rng.integers(0, 2))
+        state, frames = (-np.inf if fresh else vals[0]), vals[1:]
+        bw, best = state, -1
+        for k, s in enumerate(frames):            # sequential scan in feed order
+            if s >= bw:
+                bw, best = s, k
+        order = rng.permutation(n)                # any visiting order
+        bw2, best2 = state, -1
+        for k in order:
+            s = frames[k]
+            if s > bw2 or (s == bw2 and k > best2):
+                bw2, best2 = s, int(k)
+        assert (bw, best) == (bw2, best2)
