@@ -12,8 +12,10 @@
  *   Map2D::feed(img,pose)                    -> m2d_feed           (Map2D.h:91,  Map2DCPU.cpp:127-148)
  *   Map2D::save(filename)                    -> m2d_save           (Map2D.h:95,  Map2DCPU.cpp:523-564)
  *   Map2D::queueSize()                       -> m2d_queue_size     (Map2D.h:97)
- *   thread=true (Map2DCPU.cpp:119-120,139-142,397-413: worker thread + frame queue of 20, drop-oldest)
- *                                            -> m2d_ingest_open(20) at prepare(), feed() = m2d_ingest_push
+ *   thread=true (Map2DCPU.cpp:119-120,139-142,397-413: worker thread + frame queue of 20, drop-oldest; the queue
+ *   starts out holding the prepare-frames, Map2D.cpp:42, which the worker therefore renders first)
+ *                                            -> m2d_ingest_open_seeded(20, n) + m2d_ingest_push of every prepare-frame
+ *                                               at prepare(); feed() = m2d_ingest_push
  *   Map2D::draw()                            -> no-op (GL is out of scope); its data path is m2d_poll_changed +
  *                                               m2d_get_tile_image (changed tiles, blended textures) and
  *                                               m2d_tile_gps_corners (the Map2DUpdate overlay corners)
@@ -59,11 +61,25 @@ public:
         size_t i = 0;
         for (std::deque<std::pair<cv::Mat, pi::SE3d> >::const_iterator it = frames.begin(); it != frames.end(); ++it, ++i)
             pose7(it->second, &poses[7 * i]);
+        /* A second prepare() swaps in a new Prepare object with its own frame deque (Map2DCPU.cpp:105-125): whatever
+         * was still queued for the old map is never rendered.  So: discard the old queue BEFORE the grid is replaced. */
+        if (_thread) m2d_ingest_abort(_h);
         if (m2d_prepare(_h, p, cam, (int)frames.size(), poses.empty() ? NULL : &poses[0]) != M2D_OK) return false;
-        /* thread=true: the reference starts its worker here (Map2DCPU.cpp:119-120); its frame queue holds 20 and
-         * drops the oldest beyond that (:139-142).  A second prepare() keeps the queue that is already open. */
-        if (_thread) { m2d_ingest_close(_h); return m2d_ingest_open(_h, 20, 0) == M2D_OK; }
-        return true;
+        if (!_thread) return true;   /* thread=false: the prepare-frames are never rendered (only feed() renders) */
+        /* thread=true: the reference starts its worker here (Map2DCPU.cpp:119-120).  Map2DPrepare::_frames is both the
+         * prepare set and the worker's queue (Map2D.cpp:42-47), so the worker renders the prepare-frames first, in
+         * order; feed() then appends and drops one oldest entry beyond 20 (Map2DCPU.cpp:139-142). */
+        if (m2d_ingest_open_seeded(_h, 20, (int)frames.size(), 1) != M2D_OK) return false;
+        bool ok = true;
+        for (std::deque<std::pair<cv::Mat, pi::SE3d> >::const_iterator it = frames.begin(); it != frames.end(); ++it) {
+            const cv::Mat& img = it->first;
+            double q[7];
+            pose7(it->second, q);   /* the original camera-to-world pose: the library applies plane^-1 itself */
+            if (img.type() != CV_8UC3 || !img.data) continue;   /* renderFrame would reject it (Map2DCPU.cpp:158-162) */
+            int rc = m2d_ingest_push(_h, img.data, img.cols, img.rows, img.step, 3, q);
+            if (rc < 0) ok = false;
+        }
+        return m2d_ingest_pause(_h, 0) == M2D_OK && ok;
     }
 
     /* pose is camera-to-world; the library left-multiplies plane^-1 like Map2DCPU.cpp:136. */

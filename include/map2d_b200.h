@@ -62,9 +62,11 @@ typedef struct m2d_config {
     int band_number;     /* MultiBandMap2DCPU.BandNumber (MultiBandMap2DCPU.cpp:260) default 5   */
     int force_float;     /* MultiBandMap2DCPU.ForceFloat (:444) — must be 0 (int16 path only)    */
     int background;      /* Result.BackGroundColor (:840)                            default 0   */
-    int thread;          /* Map2D.Thread: 0 = feed() returns after the work is enqueued AND bounds are
-                            decided (reference thread=false semantics, result-equivalent); non-zero is
-                            accepted and treated the same: there is no drop-oldest queue on the GPU. */
+    int thread;          /* Map2D.Thread, informational: m2d_feed* always have the reference's thread=false
+                            semantics (the call returns once the frame's bounds are decided and its work is
+                            enqueued).  The thread=true behaviour -- worker thread + bounded drop-oldest queue,
+                            Map2DCPU.cpp:139-142,397-413 -- is the separate m2d_ingest_* seam below, which the
+                            C++ adapter (Map2DB200.h) and the Python mirror switch on when thread is set. */
     int device;          /* CUDA device ordinal                                       default 0   */
     /* Spatial tile ownership for multi-GPU runs. Tiles are keyed on ABSOLUTE tile
      * coordinates (anchored at prepare(), stable under spreadMap). owner = floor(abs / shard_span) mod
@@ -217,11 +219,19 @@ int m2d_get_kernel_times(m2d_handle h, double* ms /* M2D_KERNEL_CLASSES */, uint
  * pause(1) holds the worker (frames keep queueing/dropping), drain blocks until everything queued has been fused,
  * close drains, joins the worker and frees the ring (m2d_destroy closes implicitly). */
 int m2d_ingest_open(m2d_handle h, int capacity, int start_paused);
+/* The same with room for `seed_frames` frames queued up front WITHOUT dropping: in the reference Map2DPrepare::_frames is
+ * both the prepare set and the worker's queue (Map2D.cpp:42), so with thread=true the worker first renders the
+ * prepare-frames, however many there are; only a later feed() drops (one) oldest entry when the queue holds more than
+ * `capacity` (Map2DCPU.cpp:141-142).  Open paused, push the prepare-frames, then m2d_ingest_pause(h, 0). */
+int m2d_ingest_open_seeded(m2d_handle h, int capacity, int seed_frames, int start_paused);
 int m2d_ingest_push(m2d_handle h, const uint8_t* pixels, int w, int h_px, size_t stride, int channels,
                     const double pose_c2w[7]);
 int m2d_ingest_pause(m2d_handle h, int paused);
 int m2d_ingest_drain(m2d_handle h);
 int m2d_ingest_close(m2d_handle h);
+/* close WITHOUT draining: frames still queued are discarded (counted as dropped).  What a second prepare() does to the
+ * old queue in the reference: the new Map2DPrepare object brings its own frame deque (Map2DCPU.cpp:105-125). */
+int m2d_ingest_abort(m2d_handle h);
 int m2d_ingest_stats(m2d_handle h, uint64_t* pushed, uint64_t* dropped, uint64_t* fed, uint64_t* fused);
 
 /* Map2DUpdate — the Google-map overlay command of the display loop (MultiBandMap2DCPU.cpp:744-757, consumed by
@@ -245,7 +255,9 @@ void m2d_free_host(void* p);
 /* The tile-overlap/bounds kernel on its own (SURVEY.md §8a A4+A7): for n poses against the CURRENT grid,
  * rect[i] = {xminInt,yminInt,xmaxInt,ymaxInt} (or all -1 when the frame is rejected) and hinv[i] = the
  * inverse homography (region px -> source px, row-major 3x3). No spreadMap is applied: out-of-grid frames
- * report indices outside [0,w]x[0,h]. Used by m2d_feed_batch and exposed for parity tests. */
+ * report indices outside [0,w]x[0,h].  NOT on the feed path: m2d_feed* take these decisions one frame after the
+ * other on the host (the same geom.h code; a frame's grid depends on the spreadMap of the frames before it), so this
+ * kernel is a batch query for planners and for the host/device bit-equality test of geom.h. */
 int m2d_compute_bounds(m2d_handle h, int n, const double* poses, int* rects /* n x 4 */,
                        double* hinv /* n x 9 */);
 

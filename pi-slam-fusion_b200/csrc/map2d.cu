@@ -268,6 +268,8 @@ void m2d_map::release() {
 // Map2DPrepare::prepare (Map2D.cpp:32-49) + Map2DCPUData::prepare (Map2DCPU.cpp:44-92 / MultiBandMap2DCPU.cpp:199-255)
 int m2d_map::prepare(const double* plane7, const double* cam, int n, const double* poses) {
     if (n <= 0 || !poses || cam[0] <= 0 || cam[1] <= 0 || cam[2] == 0 || cam[3] == 0) return M2D_REJECTED;
+    // cv::remap keeps source coordinates in 16-bit maps (saturate_cast<short>); the kernels rely on sw, sh <= 32767
+    if (cam[0] > 32767 || cam[1] > 32767) { err = "camera larger than 32767 px: unsupported (OpenCV's remap maps are 16-bit)"; return M2D_ERR_UNSUPPORTED; }
     GridGeom ng{};
     ng.cam_w = cam[0]; ng.cam_h = cam[1]; ng.cx = cam[4]; ng.cy = cam[5];
     ng.fxinv = 1. / cam[2]; ng.fyinv = 1. / cam[3];
@@ -499,6 +501,21 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
     GroupCtx& c = ctx[ctx_next];
     ctx_next = (ctx_next + 1) % kCtx;
     if (c.busy) { CU(cudaEventSynchronize(c.done)); c.busy = false; }
+    // Tiles this group allocates are only initialised by its kernels (TileWork::fresh).  If the group is abandoned on an
+    // error before those kernels are enqueued, the slots go back to the pool: a later feed must not find them in the
+    // table and blend against recycled memory.  Keyed on ABSOLUTE tile coordinates (spreadMap re-indexes the table).
+    struct FreshGuard {
+        m2d_map* m; std::vector<std::pair<int, int>> abs; bool armed = true;
+        ~FreshGuard() {
+            if (!armed) return;
+            for (auto& a : abs) {
+                int x = a.first - m->org_x, y = a.second - m->org_y;
+                if (x < 0 || y < 0 || x >= m->g.w || y >= m->g.h) continue;
+                uint8_t*& slot = m->table[(size_t)y * m->g.w + x];
+                if (slot) { m->free_tiles.push_back(slot); slot = nullptr; m->tiles_in_use--; }
+            }
+        }
+    } fresh_guard{this};
 
     std::vector<FrameJob> jobs;
     std::vector<TileWork> tiles;
@@ -549,6 +566,7 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
                         int rc = alloc_tile(&slot);
                         if (rc != M2D_OK) return rc;
                         is_fresh = true;
+                        fresh_guard.abs.emplace_back(tx + org_x, ty + org_y);
                     }
                     const size_t gi = (size_t)ty * g.w + tx;
                     changed[gi] = 1;  // ele->Ischanged = true (Map2DCPU.cpp:330)
@@ -574,12 +592,15 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
             memcpy(J.hinv, fb.hinv, sizeof J.hinv);
             for (int k = 0; k < 9; k++) J.hinvf[k] = (float)fb.hinv[k];
             J.nx = nx; J.ny = ny;
-            // Pyramid window: owned tiles + one tile ring (>= the 94-px level-0 support of the deepest Laplacian
-            // tap), clipped to the frame region so the reflect-101 border lands where the reference puts it.
+            // Pyramid window: owned tiles + a ring of tiles that covers the level-0 support of the deepest Laplacian tap
+            // (G_{L-1} at +-1 coarse px of a level L-2 px: 3 * 2^(L-1) - 2 px = 94 for 6 levels -> 1 tile, 382 for 8
+            // levels -> 2 tiles, 766 for 9 -> 3), clipped to the frame region so the reflect-101 border lands where the
+            // reference puts it.
             if (cfg.shard_count <= 1) { J.wx = 0; J.wy = 0; J.wnx = nx; J.wny = ny; }
             else {
-                int wx0 = std::max(ox0 - 1, fb.x0), wy0 = std::max(oy0 - 1, fb.y0);
-                int wx1 = std::min(ox1 + 1, fb.x1), wy1 = std::min(oy1 + 1, fb.y1);
+                const int ring = (3 * (1 << (levels - 1)) - 2 + kEle - 1) / kEle;
+                int wx0 = std::max(ox0 - ring, fb.x0), wy0 = std::max(oy0 - ring, fb.y0);
+                int wx1 = std::min(ox1 + ring, fb.x1), wy1 = std::min(oy1 + ring, fb.y1);
                 J.wx = wx0 - fb.x0; J.wy = wy0 - fb.y0; J.wnx = wx1 - wx0; J.wny = wy1 - wy0;
             }
             max_wnx = std::max(max_wnx, J.wnx); max_wny = std::max(max_wny, J.wny);
@@ -598,7 +619,7 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
         if (status != M2D_OK) any_rejected = 1;
     }
     int nj = (int)jobs.size();
-    if (nj == 0) return any_rejected ? M2D_REJECTED : M2D_OK;
+    if (nj == 0) { fresh_guard.armed = false; return any_rejected ? M2D_REJECTED : M2D_OK; }
 
     // ---- device buffers of this context
     size_t n_entries = 0;
@@ -756,6 +777,7 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
         CU(cudaStreamWaitEvent(stream, c.staged, 0));
         LAUNCHK(M2D_K_WEIGHTED, launch_weighted_group(p, stream));
     }
+    fresh_guard.armed = false;   // every kernel of the group is enqueued: the fresh tiles will be initialised
     CU(cudaEventRecord(c.done, stream));
     c.busy = true;
     c.frames = nj;
@@ -1031,15 +1053,18 @@ static void ingest_worker(m2d_map* m) {
     }
 }
 
-int m2d_ingest_open(m2d_handle h, int capacity, int start_paused) {
-    if (!h || capacity < 1 || capacity > 4096) return M2D_ERR_ARG;
+int m2d_ingest_open(m2d_handle h, int capacity, int start_paused) { return m2d_ingest_open_seeded(h, capacity, 0, start_paused); }
+
+int m2d_ingest_open_seeded(m2d_handle h, int capacity, int seed_frames, int start_paused) {
+    if (!h || capacity < 1 || capacity > 4096 || seed_frames < 0 || seed_frames > 4096) return M2D_ERR_ARG;
     if (h->ingest) return M2D_ERR_STATE;
     if (!h->valid) { h->err = "m2d_ingest_open: prepare() first (the frame size comes from the camera)"; return M2D_ERR_STATE; }
     if (cudaSetDevice(h->cfg.device) != cudaSuccess) return M2D_ERR_CUDA;
     Ingest* I = new Ingest();
     I->capacity = capacity; I->w = (int)h->g.cam_w; I->h = (int)h->g.cam_h;
     I->slot_bytes = ((size_t)I->w * I->h * 3 + 255) & ~(size_t)255;
-    I->n_slots = capacity + kIngestBatch + kIngestSpare;
+    // the queue may hold max(capacity, seed_frames) + 1 frames for an instant (push, then drop one: Map2DCPU.cpp:141-142)
+    I->n_slots = std::max(capacity, seed_frames) + 1 + kIngestBatch + kIngestSpare;
     if (cudaHostAlloc((void**)&I->ring, I->slot_bytes * I->n_slots, cudaHostAllocDefault) != cudaSuccess) {
         cudaGetLastError();
         delete I;
@@ -1066,7 +1091,7 @@ int m2d_ingest_push(m2d_handle h, const uint8_t* pixels, int w, int hpx, size_t 
     {
         std::lock_guard<std::mutex> lk(I->mu);
         if (I->stop) return M2D_ERR_STATE;
-        while ((int)I->q.size() >= I->capacity || (I->free_slots.empty() && !I->q.empty())) {   // DataTrans.h:57-64: drop the oldest
+        if (I->free_slots.empty() && !I->q.empty()) {     // ring exhausted (many producers mid-copy): make room like a full queue does
             I->free_slots.push_back(I->q.front().slot);
             I->q.pop_front();
             I->dropped++;
@@ -1089,6 +1114,13 @@ int m2d_ingest_push(m2d_handle h, const uint8_t* pixels, int w, int hpx, size_t 
         memcpy(it.pose, pose, sizeof it.pose);
         I->q.push_back(it);
         I->pushed++;
+        // Map2DCPU.cpp:141-142 (and DataTrans.h:57-64): push, then drop ONE oldest entry if the queue is over capacity; a queue
+        // seeded with more than `capacity` prepare-frames therefore stays that long until the worker catches up
+        if ((int)I->q.size() > I->capacity) {
+            I->free_slots.push_back(I->q.front().slot);
+            I->q.pop_front();
+            I->dropped++;
+        }
     }
     I->cv.notify_one();
     return M2D_OK;
@@ -1113,11 +1145,19 @@ int m2d_ingest_drain(m2d_handle h) {
     return I->last_rc < 0 ? I->last_rc : M2D_OK;
 }
 
-int m2d_ingest_close(m2d_handle h) {
+static int ingest_shutdown(m2d_handle h, bool discard) {
     if (!h) return M2D_ERR_ARG;
     Ingest* I = h->ingest;
     if (!I) return M2D_OK;
-    { std::lock_guard<std::mutex> lk(I->mu); I->paused = false; I->stop = true; }   // the worker drains what is queued, then exits
+    {
+        std::lock_guard<std::mutex> lk(I->mu);
+        if (discard) {   // frames still queued are dropped unrendered (what a second prepare() does to the old queue, Map2DCPU.cpp:112-114)
+            I->dropped += I->q.size();
+            for (const IngestItem& it : I->q) I->free_slots.push_back(it.slot);
+            I->q.clear();
+        }
+        I->paused = false; I->stop = true;   // the worker drains what is queued, then exits
+    }
     I->cv.notify_all();
     if (I->worker.joinable()) I->worker.join();
     int rc = I->last_rc;
@@ -1130,6 +1170,8 @@ int m2d_ingest_close(m2d_handle h) {
     delete I;
     return rc < 0 ? rc : M2D_OK;
 }
+int m2d_ingest_close(m2d_handle h) { return ingest_shutdown(h, false); }
+int m2d_ingest_abort(m2d_handle h) { return ingest_shutdown(h, true); }
 
 int m2d_ingest_stats(m2d_handle h, uint64_t* pushed, uint64_t* dropped, uint64_t* fed, uint64_t* fused) {
     if (!h) return M2D_ERR_ARG;

@@ -48,7 +48,7 @@ EXPORTS = ["m2d_config_default", "m2d_create", "m2d_destroy", "m2d_prepare", "m2
            "m2d_last_rect", "m2d_get_tile", "m2d_get_image", "m2d_save", "m2d_tile_bytes", "m2d_tile_count",
            "m2d_export_tiles", "m2d_import_tiles", "m2d_poll_changed", "m2d_get_tile_image", "m2d_save_state", "m2d_load_state", "m2d_get_stats", "m2d_last_error",
            "m2d_launch_count", "m2d_profile", "m2d_get_kernel_times", "m2d_alloc_host", "m2d_free_host", "m2d_compute_bounds",
-           "m2d_tile_gps_corners", "m2d_reach_table", "m2d_ingest_open", "m2d_ingest_push", "m2d_ingest_pause", "m2d_ingest_drain", "m2d_ingest_close", "m2d_ingest_stats"]
+           "m2d_tile_gps_corners", "m2d_reach_table", "m2d_ingest_open", "m2d_ingest_open_seeded", "m2d_ingest_abort", "m2d_ingest_push", "m2d_ingest_pause", "m2d_ingest_drain", "m2d_ingest_close", "m2d_ingest_stats"]
 
 _lib = None
 
@@ -77,6 +77,8 @@ def lib():
     L.m2d_tile_gps_corners.argtypes = [dp, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, dp, dp, dp]
     L.m2d_reach_table.argtypes = [C.c_int, C.POINTER(C.c_ubyte), C.POINTER(C.c_ubyte)]
     L.m2d_ingest_open.argtypes = [vp, C.c_int, C.c_int]
+    L.m2d_ingest_open_seeded.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+    L.m2d_ingest_abort.argtypes = [vp]
     L.m2d_ingest_push.argtypes = [vp, vp, C.c_int, C.c_int, C.c_size_t, C.c_int, dp]
     L.m2d_ingest_pause.argtypes = [vp, C.c_int]
     L.m2d_ingest_drain.argtypes = [vp]
@@ -226,12 +228,29 @@ class Map2D:
 
     # --- Map2D interface -----------------------------------------------------------------------------
     def prepare(self, plane, camera, frames):
-        """frames: sequence of poses (n x 7) or of (img, pose) pairs like the reference's deque."""
+        """frames: sequence of poses (n x 7) or of (img, pose) pairs like the reference's deque.
+        thread=True (Map2D::create's second argument) behaves like the reference: prepare() starts the worker, whose
+        queue is seeded with the prepare-frames themselves (Map2D.cpp:42, Map2DCPU.cpp:384-413) -- they are rendered
+        first, in order -- and feed() only enqueues (drop-oldest beyond 20, Map2DCPU.cpp:139-142); a second prepare()
+        discards what was still queued for the old map.  thread=False never renders the prepare-frames."""
+        pairs = [f for f in frames if isinstance(f, (tuple, list)) and len(f) == 2 and np.ndim(f[1]) == 1]
         poses = [f[1] if isinstance(f, (tuple, list)) and len(f) == 2 and np.ndim(f[1]) == 1 else f for f in frames]
         poses = np.ascontiguousarray(np.asarray(poses, np.float64).reshape(-1, 7))
         plane = np.ascontiguousarray(plane, np.float64).reshape(7)
         camera = np.ascontiguousarray(camera, np.float64).reshape(6)
-        return self._check(lib().m2d_prepare(self._h, _dptr(plane), _dptr(camera), len(poses), _dptr(poses)))
+        threaded = bool(self.cfg.thread)
+        if threaded:
+            lib().m2d_ingest_abort(self._h)
+        if not self._check(lib().m2d_prepare(self._h, _dptr(plane), _dptr(camera), len(poses), _dptr(poses))):
+            return False
+        if not threaded:
+            return True
+        self._check(lib().m2d_ingest_open_seeded(self._h, 20, len(pairs), 1))
+        for img, pose in pairs:
+            img = np.asarray(img)
+            if img.dtype == np.uint8 and img.ndim == 3 and img.shape[2] == 3:
+                self.ingest_push(np.ascontiguousarray(img), pose)
+        return self.ingest_pause(False)
 
     def feed(self, img, pose):
         img = np.asarray(img)
@@ -239,7 +258,13 @@ class Map2D:
             print("Map2DB200::feed: image must be CV_8UC3")  # reference: type()!=CV_8UC3 -> false
             return False
         pose = np.ascontiguousarray(pose, np.float64).reshape(7)
+        if self.cfg.thread and self._ingest_open():
+            return self._check(lib().m2d_ingest_push(self._h, img.ctypes.data, img.shape[1], img.shape[0], img.strides[0], 3, _dptr(pose)))
         return self._check(lib().m2d_feed(self._h, img.ctypes.data, img.shape[1], img.shape[0], img.strides[0], _dptr(pose)))
+
+    def _ingest_open(self):
+        v = C.c_uint64()
+        return lib().m2d_ingest_stats(self._h, C.byref(v), None, None, None) == OK
 
     def feed_device(self, dev_ptr, w, h, stride, pose):
         pose = np.ascontiguousarray(pose, np.float64).reshape(7)
@@ -288,6 +313,13 @@ class Map2D:
     def ingest_close(self):
         return self._check(lib().m2d_ingest_close(self._h))
 
+    def ingest_abort(self):
+        """Close without draining: queued frames are discarded (what a second prepare() does to the old queue)."""
+        return self._check(lib().m2d_ingest_abort(self._h))
+
+    def ingest_open_seeded(self, capacity=20, seed_frames=0, start_paused=True):
+        return self._check(lib().m2d_ingest_open_seeded(self._h, capacity, seed_frames, int(start_paused)))
+
     def ingest_stats(self):
         v = [C.c_uint64() for _ in range(4)]
         self._check(lib().m2d_ingest_stats(self._h, *[C.byref(x) for x in v]))
@@ -298,6 +330,8 @@ class Map2D:
         return self._check(lib().m2d_set_shard(self._h, rank, count, axis, span, origin))
 
     def save(self, filename):
+        if self.cfg.thread and self._ingest_open():
+            self.ingest_drain()
         return self._check(lib().m2d_save(self._h, os.fsencode(filename)))
 
     def queueSize(self):

@@ -126,6 +126,32 @@ def replay(dataset, map2d, prepare_frames=10, batch=32, on_frame=None):
     if not map2d.prepare(dataset.plane, dataset.camera, dataset.poses[:npre]):
         raise RuntimeError("prepare() rejected the dataset (camera heights straddle the plane?)")
     accepted = []
+    batch = max(int(batch), 1)
+    if batch > 1 and hasattr(map2d, "feed_batch"):
+        # grouped launches: `batch` decoded frames at a time through m2d_feed_batch (host buffers); same results as
+        # frame-by-frame feed() calls, each map tile touched once per group instead of once per frame
+        for k0 in range(0, n, batch):
+            imgs = []
+            for k in range(k0, min(k0 + batch, n)):
+                img = dataset.image(k)
+                if img is None or img.shape[:2] != (int(dataset.camera[1]), int(dataset.camera[0])) or img.dtype != np.uint8 or img.ndim != 3:
+                    img = None   # renderFrame would reject it (Map2DCPU.cpp:158-162)
+                imgs.append(img)
+            good = [i for i, im in enumerate(imgs) if im is not None]
+            flags = [False] * len(imgs)
+            if good:
+                stack = np.ascontiguousarray(np.stack([imgs[i] for i in good]))
+                h, w = stack.shape[1:3]
+                res = map2d.feed_batch(stack.ctypes.data, len(good), w * h * 3, w, h, w * 3, dataset.poses[[k0 + i for i in good]], False)
+                if hasattr(map2d, "sync"):
+                    map2d.sync()   # `stack` is read until here
+                for i, r in zip(good, res):
+                    flags[i] = (int(r) == 0)
+            for i, ok in enumerate(flags):
+                accepted.append(ok)
+                if on_frame:
+                    on_frame(k0 + i, ok)
+        return accepted
     for k in range(n):
         ok = map2d.feed(dataset.image(k), dataset.poses[k])
         accepted.append(bool(ok))
@@ -148,12 +174,13 @@ def main(argv=None):
     ap.add_argument("--weight-type", type=int, default=0, help="Map2D.WeightType")
     ap.add_argument("--background", type=int, default=0, help="Result.BackGroundColor")
     ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("--batch", type=int, default=32, help="frames handed to m2d_feed_batch at a time (1 = one feed() per frame)")
     a = ap.parse_args(argv)
     from . import map2d as m2d
     ds = Dataset(a.dataset)
     m = m2d.Map2D.create(a.type, thread=False, scale=a.scale, resolution=a.resolution, band_number=a.bands,
                          weight_type=a.weight_type, background=a.background, device=a.device)
-    acc = replay(ds, m, a.prepare)
+    acc = replay(ds, m, a.prepare, batch=a.batch)
     ok = m.save(a.out)
     g = m.grid()
     print("frames %d fused %d  grid %dx%d tiles  lengthPixel %.6g  trajectory %.1f m  saved=%s -> %s"

@@ -54,11 +54,18 @@ def test_adapter_drives_the_gpu_path(tmp_path, typ):
 @pytest.mark.parametrize("typ", [1, 3])
 def test_adapter_thread_mode_uses_the_ingest_queue(tmp_path, typ):
     """thread=true: feed() only enqueues (so even the oblique frame is 'accepted', like the reference's enqueue),
-    save()/getImage() drain the queue first, and the result is the same mosaic as the synchronous run."""
+    save()/getImage() drain the queue first.  Map2DPrepare::_frames is the worker's queue (Map2D.cpp:42,
+    Map2DCPU.cpp:384-413), so in thread mode the prepare-frames 0..3 ARE rendered, before anything feed() adds; in
+    thread=false they are not (only feed() renders)."""
     exe = build(tmp_path)
-    a, b = str(tmp_path / "sync.png"), str(tmp_path / "thread.png")
-    r0 = run(exe, str(typ), a, "0")
-    r1 = run(exe, str(typ), b, "1")
+    a, b, c, d = (str(tmp_path / n) for n in ("sync_0to7.png", "thread_4to7.png", "thread_none.png", "sync_0to3.png"))
+    r0 = run(exe, str(typ), a, "0", "8", "0")       # synchronous: feed frames 0..7 explicitly
+    r1 = run(exe, str(typ), b, "1", "4", "4")       # threaded: prepare(0..3) seeds the queue, feed adds 4..7
     assert r1["handle"] == "1" and r1["prepared"] == "1" and r1["fed"] == "4" and r1["oblique_accepted"] == "1" and r1["saved"] == "1"
     assert r1["image"] == r0["image"] and r1["queue"] == "0"
-    assert open(a, "rb").read() == open(b, "rb").read()
+    assert open(a, "rb").read() == open(b, "rb").read(), "thread mode must render the prepare-frames first, then the fed ones"
+    r2 = run(exe, str(typ), c, "1", "0", "0")       # threaded, nothing fed: the mosaic is the prepare-frames alone
+    r3 = run(exe, str(typ), d, "0", "4", "0")
+    assert r2["saved"] == "1" and open(c, "rb").read() == open(d, "rb").read()
+    r4 = run(exe, str(typ), str(tmp_path / "sync_none.png"), "0", "0", "0")   # thread=false never renders the prepare set
+    assert r4["prepared"] == "1" and r4["saved"] == "0" and r4["image"] == "0x0"

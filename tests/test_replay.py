@@ -60,6 +60,9 @@ def test_replay_through_oracle_equals_direct_feed(tmp_path):
         assert b.prepare(plane, seq.camera, seq.poses[:4])
         assert acc == [b.feed(seq.frame(k), seq.poses[k]) for k in range(seq.n)] and all(acc)
         assert np.array_equal(a.get_image()[0], b.get_image()[0])
+        c = O.OracleMap2D.create(typ)     # frame-by-frame feed() and grouped feed_batch() replay agree
+        assert replay.replay(ds, c, prepare_frames=4, batch=1) == acc == replay.replay(ds, O.OracleMap2D.create(typ), 4, batch=3)
+        assert np.array_equal(a.get_image()[0], c.get_image()[0])
 
 
 @pytest.mark.gpu
