@@ -88,6 +88,9 @@ typedef struct m2d_stats {
     uint64_t need_px[M2D_MAX_LEVELS];      /* multi-band, weights-first pipeline: px of the frames' Gaussian level l that had
                                               to be computed (cells a winner's Laplacian depends on); 0 from the oracle and
                                               from the dense pipeline                                */
+    uint64_t needw_px[M2D_MAX_LEVELS];     /* the same for the frames' WEIGHT level l (cells in which the frame is competitive,
+                                              grown by the pyrDown reach).  need_px / needw_px are also counted while
+                                              m2d_profile is on (with culling active), not only with collect_stats */
 } m2d_stats;
 
 typedef struct m2d_map* m2d_handle;
@@ -169,6 +172,10 @@ int m2d_save(m2d_handle h, const char* filename);
  * (device or host memory) and their coordinates into abs_xy (2 ints per tile); import inserts foreign tiles
  * so that m2d_get_image()/m2d_save() on the root cover the whole map. */
 size_t m2d_tile_bytes(m2d_handle h);
+/* The leading bytes of a tile record that hold REFERENCE state (weighted: the BGRA tile; multi-band: per level the three
+ * int16 Laplacian planes and the f32 weight plane).  What follows up to m2d_tile_bytes is library-private acceleration
+ * data (per-cell lower bounds of the weight planes) that may differ between runs with identical results. */
+size_t m2d_tile_state_bytes(m2d_handle h);
 int m2d_tile_count(m2d_handle h);
 int m2d_export_tiles(m2d_handle h, int max_tiles, int* abs_xy, uint8_t* dst, int dst_on_device, int* n_out);
 int m2d_import_tiles(m2d_handle h, int n, const int* abs_xy, const uint8_t* src, int src_on_device);
@@ -200,10 +207,10 @@ uint64_t m2d_launch_count(m2d_handle h);
  * (and clears them).  bench.py uses it for the live roofline measurement; leave it off otherwise. */
 #define M2D_KERNEL_CLASSES 16
 enum { M2D_K_WEIGHTED = 0, M2D_K_MB_WARP = 1, M2D_K_MB_PYRDOWN = 2, M2D_K_MB_SELECT = 3, M2D_K_COLLAPSE = 4, M2D_K_MISC = 5, M2D_K_MB_PYRTAIL = 6,
-       /* weights-first multi-band pipeline (default): weight warp / weight pyramid (pyrDown + tail) / decide / propagate /
-        * sparse image warp / sparse image pyramid (pyrDown + tail) / winners' Laplacian */
+       /* weights-first multi-band pipeline (default): weight warp / weight pyramid / decide / propagate (weight + image side) /
+        * sparse image warp / sparse image pyramid / winners' Laplacian / competitive-cell bounds */
        M2D_K_MBW_WARP = 7, M2D_K_MBW_PYR = 8, M2D_K_MBS_DECIDE = 9, M2D_K_MBS_PROPAGATE = 10, M2D_K_MBS_WARP = 11, M2D_K_MBS_PYR = 12,
-       M2D_K_MBS_LAP = 13 };
+       M2D_K_MBS_LAP = 13, M2D_K_MBC_BOUNDS = 14 };
 int m2d_profile(m2d_handle h, int enable);
 int m2d_get_kernel_times(m2d_handle h, double* ms /* M2D_KERNEL_CLASSES */, uint64_t* count /* M2D_KERNEL_CLASSES */);
 
@@ -247,6 +254,16 @@ int m2d_tile_gps_corners(const double plane[7], double grid_min_x, double grid_m
  * make_reach_table).  lo/hi[m*6 + k] = how many 32-px cells below/above the cell of a level-m winner the Gaussian level
  * k must be valid (255 = no dependency).  levels = band_number + 1 <= 6.  Pure host arithmetic, no handle. */
 int m2d_reach_table(int levels, unsigned char lo[36], unsigned char hi[36]);
+/* The same for the WEIGHT side (kernels_wf.cu make_weight_reach_table): cells of weight level k that a frame's competitive
+ * cell of level m depends on (the pyrDown chain only). */
+int m2d_weight_reach_table(int levels, unsigned char lo[36], unsigned char hi[36]);
+/* Introspection for tests: the closed-form bounds the weights-first pipeline culls with (csrc/bounds.h, the very code the
+ * bounds kernel runs).  hinv = inverse homography of a frame (region px -> source px, as m2d_compute_bounds returns it;
+ * rounded to float like the kernel's copy), (nx, ny) its region in tiles, (sw, sh) the source size; on return
+ * lo <= W_level(u) <= hi for every px u of cell (cx, cy) (32 x 32 level-0 px of the region) of the frame's weight
+ * pyramid (MultiBandMap2DCPU.cpp:449-474).  Pure host arithmetic, no handle. */
+int m2d_cell_weight_bounds(const double hinv[9], int nx, int ny, int sw, int sh, int weight_type, int level, int cx,
+                           int cy, float* lo, float* hi);
 
 /* Pinned host staging helpers for callers that want truly asynchronous m2d_feed(). */
 void* m2d_alloc_host(size_t bytes);

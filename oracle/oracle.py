@@ -28,12 +28,13 @@ class Stats(C.Structure):
     """m2d_stats, include/map2d_b200.h"""
     _fields_ = [("frames_fed", C.c_uint64), ("frames_fused", C.c_uint64), ("input_px", C.c_uint64),
                 ("region_px", C.c_uint64 * MAX_LEVELS), ("fresh_px", C.c_uint64 * MAX_LEVELS),
-                ("win_px", C.c_uint64 * MAX_LEVELS), ("footprint_px", C.c_uint64), ("need_px", C.c_uint64 * MAX_LEVELS)]
+                ("win_px", C.c_uint64 * MAX_LEVELS), ("footprint_px", C.c_uint64), ("need_px", C.c_uint64 * MAX_LEVELS),
+                ("needw_px", C.c_uint64 * MAX_LEVELS)]
 
     def as_dict(self):
         return {"frames_fed": self.frames_fed, "frames_fused": self.frames_fused, "input_px": self.input_px,
                 "region_px": list(self.region_px), "fresh_px": list(self.fresh_px), "win_px": list(self.win_px),
-                "footprint_px": self.footprint_px, "need_px": list(self.need_px)}
+                "footprint_px": self.footprint_px, "need_px": list(self.need_px), "needw_px": list(self.needw_px)}
 
 
 def default_config(**kw):

@@ -51,14 +51,26 @@ struct GroupParams {
     const float* wimg;         // multi-band: sw*sh float weight image (MultiBandMap2DCPU.cpp:396-418)
     uint8_t* scratch;          // multi-band: group scratch pyramid
     unsigned long long* stats; // optional counters (collect_stats)
+    unsigned long long* need_stats;  // optional: [20 + k] px of Gaussian level k computed, [26 + k] px of weight level k computed
     int max_wnx, max_wny;      // largest pyramid window of the group (tiles): grid bounds of per-frame kernels
-    // weights-first multi-band (kernels.cu "WEIGHTS-FIRST variant"): per (frame, level) cell flags and the winner map
-    uint8_t* win;              // [n_frames][levels][cells_max]: the frame wins a px of that cell at that level
+    // weights-first multi-band (kernels_wf.cu): per (frame, level) cell flags, work lists and the winner map.
+    // A CELL is 32 x 32 level-0 px of a frame's window; at level l it is (32 >> l)^2 px (levels <= 6).
+    uint8_t* comp;             // [n_frames][levels][cells_max]: the frame is COMPETITIVE in that cell at that level (its
+                               // weight upper bound reaches the best lower bound of the other frames / the tile state)
+    uint8_t* needw;            // same shape: the frame's WEIGHT level must be valid in that cell
+    uint8_t* win;              // same shape: the frame wins a px of that cell at that level
     uint8_t* need;             // same shape: the frame's Gaussian level must be valid in that cell
     int cells_max;             // (max_wnx * 8) * (max_wny * 8)
+    uint32_t* cmask;           // [n_tiles][levels][64 cells][mask_words]: bit i = entry i of the tile's list is competitive
+    int mask_words;            // ceil(max entries per tile / 32)
+    uint32_t* lists;           // [2 (0 = weight, 1 = image)][levels][list_cap] work items (frame << 16 | cell) ...
+    unsigned* list_count;      // ... and their lengths [2][levels] (device counters)
+    int list_cap;              // n_frames * cells_max
     uint16_t* wmap;            // [n_tiles][wmap_stride]: winning entry per pyramid px of the tile (0xFFFF = none)
     int wmap_stride;           // >= TileLayout::px_off[levels], even
-    unsigned char reach_lo[6][6], reach_hi[6][6];  // [win level m][Gaussian level k] in cells, 0xFF = no dependency (make_reach_table)
+    unsigned char reach_lo[6][6], reach_hi[6][6];    // image: [win level m][Gaussian level k] in cells, 0xFF = none (make_reach_table)
+    unsigned char wreach_lo[6][6], wreach_hi[6][6];  // weights: [competitive level m][weight level k]   (make_weight_reach_table)
+    int cull;                  // 0: every entry of a tile is treated as competitive (collect_stats, M2D_WCULL=0)
 };
 
 // Tile state layout in HBM (multi-band): for each level l (side n = 256>>l): B,G,R int16 planes then f32 weight.
@@ -66,6 +78,8 @@ struct TileLayout {
     int levels;
     size_t lap_off[M2D_MAX_LEVELS];
     size_t wgt_off[M2D_MAX_LEVELS];
+    size_t cmin_off;           // f32 [levels][64]: lower bound of the tile's weight over each 32-px cell of each level (never
+                               // above the true minimum; weights only grow, so a stale value stays valid)
     size_t bytes;
     int px_off[M2D_MAX_LEVELS + 1];
 };
@@ -93,23 +107,19 @@ cudaError_t launch_weight_images(int sw, int sh, int weight_type, uint8_t* alpha
 cudaError_t launch_bounds(const GridGeom& g, int n, const double* d_poses, FrameBounds* d_out, cudaStream_t stream);
 cudaError_t launch_weighted_group(const GroupParams& p, cudaStream_t stream);
 cudaError_t launch_mb_warp(const GroupParams& p, cudaStream_t stream);
-cudaError_t launch_mb_warp_pyr(const GroupParams& p, cudaStream_t stream);  // warp + first pyrDown fused
 cudaError_t launch_mb_pyrdown(const GroupParams& p, int level /* src level */, cudaStream_t stream);
 cudaError_t launch_mb_pyrtail(const GroupParams& p, int l_first, cudaStream_t stream);
 cudaError_t launch_mb_select(const GroupParams& p, const TileLayout& lay, cudaStream_t stream);
-// weights-first multi-band variant
-cudaError_t launch_mbw_warp(const GroupParams& p, cudaStream_t stream, bool lean = false);      // lean: EXPERIMENTAL FP32 pass
-cudaError_t launch_mbw_warp_pyr(const GroupParams& p, cudaStream_t stream, bool lean = false);  // EXPERIMENTAL: + first weight pyrDown fused
-cudaError_t launch_mbw_pyrdown(const GroupParams& p, int level, cudaStream_t stream);
-cudaError_t launch_mbw_pyrtail(const GroupParams& p, int l_first, cudaStream_t stream);
+// weights-first multi-band pipeline (kernels_wf.cu)
+cudaError_t launch_mbc_bounds(const GroupParams& p, const TileLayout& lay, cudaStream_t stream);          // competitive cells
+cudaError_t launch_mbx_propagate(const GroupParams& p, int image, cudaStream_t stream);                   // need flags + work lists
+cudaError_t launch_mbw_warp(const GroupParams& p, int ctas, cudaStream_t stream);                         // level-0 weights, listed cells
+cudaError_t launch_mbx_pyrdown(const GroupParams& p, int image, int level, int ctas, cudaStream_t stream); // l -> l+1, listed cells
 cudaError_t launch_mbs_decide(const GroupParams& p, const TileLayout& lay, cudaStream_t stream);
-cudaError_t launch_mbs_decide_bf(const GroupParams& p, const TileLayout& lay, cudaStream_t stream);  // EXPERIMENTAL: best-first + bound culling
-cudaError_t launch_mbs_propagate(const GroupParams& p, cudaStream_t stream);
-void make_reach_table(int levels, unsigned char lo_tab[6][6], unsigned char hi_tab[6][6]);
-cudaError_t launch_mbs_warp(const GroupParams& p, cudaStream_t stream);
-cudaError_t launch_mbs_pyrdown(const GroupParams& p, int level, cudaStream_t stream);
-cudaError_t launch_mbs_pyrtail(const GroupParams& p, int l_first, cudaStream_t stream);
+cudaError_t launch_mbs_warp(const GroupParams& p, int ctas, cudaStream_t stream);                         // level-0 Gaussian, listed cells
 cudaError_t launch_mbs_lap(const GroupParams& p, const TileLayout& lay, cudaStream_t stream);
+void make_reach_table(int levels, unsigned char lo_tab[6][6], unsigned char hi_tab[6][6]);
+void make_weight_reach_table(int levels, unsigned char lo_tab[6][6], unsigned char hi_tab[6][6]);
 cudaError_t launch_tile_copy(uint8_t* const* d_tiles, int n, uint8_t* buf, size_t tile_bytes, int to_buf, cudaStream_t stream);
 cudaError_t launch_bgra_paste(const PasteItem* d_items, int n_items, uint32_t* mosaic, int mosaic_w, cudaStream_t stream);
 cudaError_t launch_mosaic_paste(const PasteItem* d_items, int n_items, const TileLayout& lay, const MosaicSet& ms, cudaStream_t stream);

@@ -1,0 +1,542 @@
+// kernels_wf.cu — the WEIGHTS-FIRST multi-band pipeline, default for groups of >= 4 frames, <= 6 levels.
+//
+// The weight pyramids depend on geometry only, so the winner of every pyramid px (MultiBandMap2DCPU.cpp:539-547: the
+// LAST frame whose weight is >= everything before it) is known before a single image sample is taken, and most of the
+// (frame, px) pairs can be ruled out before a single WEIGHT is computed.  Stages of one group:
+//
+//   0. mbc_bounds     (tile-centric)  closed-form bounds of every covering frame's weight over every 32-px cell of
+//                                     every level (bounds.h); a frame is COMPETITIVE in a cell when its upper bound
+//                                     reaches the best lower bound of the other frames / of the tile state
+//   1. mbx_propagate  (weights)       cells in which a frame's weight level k must be valid (competitive cells of the
+//                                     levels >= k, grown by the reach of the pyrDown taps) -> flags + work lists
+//      mbw_warp, mbx_pyrdown<W>       weights (f32, nearest, 2.4.9 float filter) in the listed cells only
+//   2. mbs_decide     (tile-centric)  arg-max over the competitive frames -> tile weights, winner map, `win` flags
+//   3. mbx_propagate  (image)         cells in which a frame's Gaussian level k is needed by one of its winners
+//   4. mbs_warp, mbx_pyrdown<G>       image (u8x4, 1/32-px bilinear, BORDER_REFLECT; packed integer filter), listed cells
+//   5. mbs_lap        (tile-centric)  winners only: G_l - pyrUp(G_{l+1}) -> Laplacian planes of the tile
+//
+// A CELL is 32 x 32 level-0 px of a frame's window; at level l it is (32 >> l)^2 px (levels <= 6), so one cell grid
+// (8 x 8 cells per tile) serves every level: cell of level-l px p = (p << l) >> 5.  The per-frame stages are PERSISTENT
+// kernels over compacted work lists (one CTA slot per SM x residency, grid-stride over (frame, cell) items), so an
+// empty cell costs nothing.  Px outside the listed cells are never read by a listed px: they may hold anything.
+// Results are bit-identical to the dense pipeline (kernels.cu) and to the oracle.
+#include "bounds.h"
+#include "device_common.cuh"
+
+namespace m2d {
+
+// ---------------------------------------------------------------------------------------------------------
+// cell-aligned mapping of the tile-centric kernels: blockIdx.y, threadIdx.x -> (level, cell of the tile, px)
+//   level 0: 64 CTAs, one 32x32-px cell each (16 x 16 quads)      level 3: 1 CTA, 64 cells of 2 x 2 quads
+//   level 1: 16 CTAs, 4 cells of 8 x 8 quads                      level 4 + 5: 1 CTA: 64 quads (one per cell) of level 4,
+//   level 2: 4 CTAs, 16 cells of 4 x 4 quads                                   64 single px (one per cell) of level 5
+// A thread owns a 2x2 quad (levels 0..4) or one px (level 5); all its px lie in ONE cell.
+// ---------------------------------------------------------------------------------------------------------
+struct CellMap { int l, n, cell, px, py, npx; bool valid; };
+
+__host__ __device__ inline int cellmap_ctas(int levels) {
+    const int per_level[6] = {64, 16, 4, 1, 1, 0};   // level 5 shares the CTA of level 4
+    int c = 0;
+    for (int l = 0; l < levels && l < 6; l++) c += per_level[l];
+    return c;
+}
+__device__ __forceinline__ CellMap cell_map(int by, int t, int levels) {
+    CellMap m;
+    m.valid = true; m.npx = 4;
+    int tt;
+    if (by < 64) { m.l = 0; m.cell = by; tt = t; }
+    else if (by < 80) { m.l = 1; m.cell = (by - 64) * 4 + (t >> 6); tt = t & 63; }
+    else if (by < 84) { m.l = 2; m.cell = (by - 80) * 16 + (t >> 4); tt = t & 15; }
+    else if (by == 84) { m.l = 3; m.cell = t >> 2; tt = t & 3; }
+    else {
+        if (t < 64) { m.l = 4; m.cell = t; tt = 0; }
+        else { m.l = 5; m.cell = t - 64; tt = 0; m.npx = 1; m.valid = t < 128 && levels > 5; }
+    }
+    m.n = kEle >> m.l;
+    const int side = m.n >> 3;                 // cell side in px: 32, 16, 8, 4, 2, 1
+    const int Q = max(side >> 1, 1);           // quads per cell side
+    const int qy = tt / Q, qx = tt - qy * Q;
+    m.px = (m.cell & 7) * side + 2 * qx;
+    m.py = (m.cell >> 3) * side + 2 * qy;
+    if (m.l >= levels) m.valid = false;
+    return m;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// 0. competitive cells.  One CTA per touched tile, one thread per (level, cell of the tile).  Pass 1: the best lower
+// bound L over the tile's entries and the tile state (cmin).  Pass 2: entry i is competitive iff hi_i >= L ('>=': ties
+// are decided by feed order, so an equal frame may still win; where everything is 0 -- the mosaic's outer rim -- every
+// covering frame stays in, because `0 >= 0` lets the last one overwrite).  A frame that is NOT competitive is strictly
+// below the frame (or state) that attains L at every px of the cell: it can never be the final winner there.
+// Outputs: the per-(tile, level, cell) bit mask over the tile's entries, the per-frame `comp` cell flags, and cmin reset
+// to +inf in every cell the decide stage will revisit (it re-establishes the exact minimum there).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(384) mbc_bounds_kernel(const __grid_constant__ GroupParams p, const __grid_constant__ TileLayout lay) {
+    const TileWork T = p.tiles[blockIdx.x];
+    const int l = threadIdx.x >> 6, cell = threadIdx.x & 63;
+    if (l >= p.levels) return;
+    const int ccx = cell & 7, ccy = cell >> 3;
+    float* cmin = reinterpret_cast<float*>(T.state + lay.cmin_off) + l * 64 + cell;
+    uint32_t* cm = p.cmask + (((size_t)blockIdx.x * p.levels + l) * 64 + cell) * p.mask_words;
+    float best_lo = -INFINITY;
+    if (p.cull) {
+        if (!T.fresh) best_lo = *cmin;
+        for (int i = 0; i < T.count; i++) {
+            const TileEntry E = p.entries[T.first + i];
+            const FrameJob& J = p.jobs[E.frame];
+            float lo, hi;
+            cell_weight_bounds(J.hinvf, J.nx, J.ny, p.sw, p.sh, p.weight_type, l, E.rtx * 8 + ccx, E.rty * 8 + ccy, &lo, &hi);
+            best_lo = fmaxf(best_lo, lo);
+        }
+    }
+    uint32_t any = 0u;
+    for (int w = 0; w < p.mask_words; w++) {
+        uint32_t bits = 0u;
+        const int i1 = min(T.count, (w + 1) * 32);
+        for (int i = w * 32; i < i1; i++) {
+            const TileEntry E = p.entries[T.first + i];
+            const FrameJob& J = p.jobs[E.frame];
+            bool in = true;
+            if (p.cull) {
+                float lo, hi;
+                cell_weight_bounds(J.hinvf, J.nx, J.ny, p.sw, p.sh, p.weight_type, l, E.rtx * 8 + ccx, E.rty * 8 + ccy, &lo, &hi);
+                in = hi >= best_lo;
+            }
+            if (in) {
+                bits |= 1u << (i & 31);
+                p.comp[cell_base(p, E.frame, l) + (size_t)((E.rty - J.wy) * 8 + ccy) * (J.wnx * 8) + ((E.rtx - J.wx) * 8 + ccx)] = 1;
+            }
+        }
+        cm[w] = bits;
+        any |= bits;
+    }
+    if (any) *cmin = INFINITY;
+}
+cudaError_t launch_mbc_bounds(const GroupParams& p, const TileLayout& lay, cudaStream_t stream) {
+    if (p.n_tiles == 0) return cudaSuccess;
+    mbc_bounds_kernel<<<p.n_tiles, 64 * min(p.levels, 6), 0, stream>>>(p, lay);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// 1./3. propagate: dst[k] = cells within reach of a src flag.  A flag of level m in cell c' makes level k necessary in
+// cells [c' - lo[m][k], c' + hi[m][k]] (both axes); the host derives the tables by interval arithmetic over the exact
+// taps (make_reach_table / make_weight_reach_table).  One thread per (frame, level, cell); needed cells are appended to
+// the level's work list (warp-aggregated atomics).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mbx_propagate_kernel(const __grid_constant__ GroupParams p, int image) {
+    const int f = blockIdx.y;
+    const FrameJob& J = p.jobs[f];
+    const int cw = J.wnx * 8, ch = J.wny * 8, nc = cw * ch, L = p.levels;   // nc is a multiple of 64: a warp never straddles levels
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const bool live = i < L * nc;
+    const int k = live ? i / nc : 0, c = live ? i - k * nc : 0, cy = c / cw, cx = c - cy * cw;
+    const uint8_t* src = image ? p.win : p.comp;
+    uint8_t* dst = image ? p.need : p.needw;
+    bool v = false;
+    if (live) {
+        for (int m = 0; m < L && !v; m++) {
+            const int rl = image ? p.reach_lo[m][k] : p.wreach_lo[m][k], rh = image ? p.reach_hi[m][k] : p.wreach_hi[m][k];
+            if (rl == 0xFF) continue;
+            const uint8_t* w = src + cell_base(p, f, m);   // a frame's flags are a few KB: L1/L2 resident
+            // c is required by a flag in c' iff c' - rl <= c <= c' + rh  <=>  c - rh <= c' <= c + rl
+            const int y0 = max(cy - rh, 0), y1 = min(cy + rl, ch - 1), x0 = max(cx - rh, 0), x1 = min(cx + rl, cw - 1);
+            for (int y = y0; y <= y1 && !v; y++)
+                for (int x = x0; x <= x1; x++) v |= w[y * cw + x] != 0;
+        }
+        dst[cell_base(p, f, k) + c] = v ? 1 : 0;
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, v);
+    if (ballot) {
+        const int lane = threadIdx.x & 31, leader = __ffs(ballot) - 1;
+        const int kk = __shfl_sync(0xffffffffu, k, leader);
+        unsigned base = 0;
+        if (lane == leader) base = atomicAdd(p.list_count + image * 6 + kk, (unsigned)__popc(ballot));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (v) p.lists[((size_t)image * L + k) * p.list_cap + base + __popc(ballot & ((1u << lane) - 1u))] = ((uint32_t)f << 16) | (uint32_t)c;
+    }
+    if (p.need_stats && ballot && (threadIdx.x & 31) == __ffs(ballot) - 1) {   // px of level k the frames have to compute (a cell is (32 >> k)^2 px)
+        const unsigned long long side = (unsigned long long)max(32 >> k, 1);
+        atomicAdd(p.need_stats + (image ? 20 : 26) + k, side * side * (unsigned long long)__popc(ballot));
+    }
+}
+cudaError_t launch_mbx_propagate(const GroupParams& p, int image, cudaStream_t stream) {
+    dim3 g((p.levels * p.cells_max + 255) / 256, p.n_frames);
+    mbx_propagate_kernel<<<g, 256, 0, stream>>>(p, image);
+    return cudaGetLastError();
+}
+
+// Reach table of the image side.  A win of level m occupying cell c (level-m px [c*B, (c+1)*B - 1], B = 32 >> m)
+// needs: its own px of G_m; if m is not the top level, G_{m+1} on [(lo >> 1) - 1, (hi >> 1) + 1] (the pyrUp taps of
+// lap_quad); and every G_{k+1} px u needs G_k on [2u - 2, 2u + 2] (pyrDown taps; borders reflect inwards only).
+// Cell of level-k px q = (q << k) >> 5.  The table is translation invariant (cells are aligned at every level).
+void make_reach_table(int levels, unsigned char lo_tab[6][6], unsigned char hi_tab[6][6]) {
+    for (int m = 0; m < 6; m++)
+        for (int k = 0; k < 6; k++) lo_tab[m][k] = hi_tab[m][k] = 0xFF;
+    const long long c = 1 << 12;
+    for (int m = 0; m < levels && m < 6; m++) {
+        const long long B = 32 >> m;
+        long long a = c * B, b = (c + 1) * B - 1;
+        int k = m;
+        auto put = [&](int lvl, long long x0, long long x1) {
+            long long c0 = (x0 << lvl) >> 5, c1 = (x1 << lvl) >> 5;
+            lo_tab[m][lvl] = (unsigned char)(c - c0);
+            hi_tab[m][lvl] = (unsigned char)(c1 - c);
+        };
+        if (m + 1 < levels) {
+            a = (a >> 1) - 1; b = (b >> 1) + 1;
+            k = m + 1;
+        }
+        put(k, a, b);
+        for (; k > 0; k--) {
+            a = 2 * a - 2; b = 2 * b + 2;
+            put(k - 1, a, b);
+        }
+    }
+}
+// Reach table of the weight side: a competitive cell c of level m needs W_m on its own px and, down the pyrDown chain,
+// W_{k} on [2u - 2, 2u + 2] for every needed px u of W_{k+1}.
+void make_weight_reach_table(int levels, unsigned char lo_tab[6][6], unsigned char hi_tab[6][6]) {
+    for (int m = 0; m < 6; m++)
+        for (int k = 0; k < 6; k++) lo_tab[m][k] = hi_tab[m][k] = 0xFF;
+    const long long c = 1 << 12;
+    for (int m = 0; m < levels && m < 6; m++) {
+        const long long B = 32 >> m;
+        long long a = c * B, b = (c + 1) * B - 1;
+        for (int k = m; k >= 0; k--) {
+            long long c0 = (a << k) >> 5, c1 = (b << k) >> 5;
+            lo_tab[m][k] = (unsigned char)(c - c0);
+            hi_tab[m][k] = (unsigned char)(c1 - c);
+            a = 2 * a - 2; b = 2 * b + 2;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// persistent per-frame stages over the work lists: item = (frame << 16) | cell of the frame's window
+// ---------------------------------------------------------------------------------------------------------
+// 1a. level-0 weights (nearest, constant 0; FP32 coordinate with exact FP64 redo of ambiguous px, see mbw_weights4):
+// one CTA iteration = one 32 x 32 cell, one thread = 4 px
+__global__ void __launch_bounds__(256) mbw_warp_kernel(const __grid_constant__ GroupParams p) {
+    const unsigned n = p.list_count[0];
+    const uint32_t* list = p.lists;
+    for (unsigned it = blockIdx.x; it < n; it += gridDim.x) {
+        const uint32_t item = list[it];
+        const int f = (int)(item >> 16), c = (int)(item & 0xFFFFu);
+        const FrameJob& J = p.jobs[f];
+        const int cw = J.wnx * 8, cy = c / cw, cx = c - cy * cw, ww = J.wnx * kEle;
+        const int u = cx * 32 + (threadIdx.x & 7) * 4, v = cy * 32 + (threadIdx.x >> 3);
+        const float4 w = mbw_weights4(p, J, u + J.wx * kEle, v + J.wy * kEle);
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.scratch + J.w_off[0]) + (size_t)v * ww + u) = w;
+    }
+}
+cudaError_t launch_mbw_warp(const GroupParams& p, int ctas, cudaStream_t stream) {
+    mbw_warp_kernel<<<ctas, 256, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// 4a. level-0 Gaussian (u8x4, 1/32-px bilinear, BORDER_REFLECT) of the listed cells
+__global__ void __launch_bounds__(256) mbs_warp_kernel(const __grid_constant__ GroupParams p) {
+    const unsigned n = p.list_count[6];
+    const uint32_t* list = p.lists + (size_t)p.levels * p.list_cap;
+    for (unsigned it = blockIdx.x; it < n; it += gridDim.x) {
+        const uint32_t item = list[it];
+        const int f = (int)(item >> 16), c = (int)(item & 0xFFFFu);
+        const FrameJob& J = p.jobs[f];
+        const int cw = J.wnx * 8, cy = c / cw, cx = c - cy * cw, ww = J.wnx * kEle;
+        const int u = cx * 32 + (threadIdx.x & 7) * 4, v = cy * 32 + (threadIdx.x >> 3);
+        double M[9];
+#pragma unroll
+        for (int i = 0; i < 9; i++) M[i] = J.hinv[i];
+        const RawSrc R = make_raw_src(J.raw, J.raw_stride, nullptr, p.sw, p.sh);
+        uint32_t g[4];
+        mb_sample4<false>(p, R, M, u + J.wx * kEle, v + J.wy * kEle, g, nullptr);
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint32_t*>(p.scratch + J.g_off[0]) + (size_t)v * ww + u) = make_uint4(g[0], g[1], g[2], g[3]);
+    }
+}
+cudaError_t launch_mbs_warp(const GroupParams& p, int ctas, cudaStream_t stream) {
+    mbs_warp_kernel<<<ctas, 256, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+// 1b./4b. pyrDown l -> l+1 of the listed cells of level l+1 (a cell is S x S outputs, S = 32 >> (l+1)).
+// Separable [1 4 6 4 1], BORDER_REFLECT_101 in REGION coordinates.  One thread = 2 adjacent output columns x up to 4
+// output rows: the input rows stream through a 5-row register window, each fetched with 8-byte loads (7 input columns).
+// Image: packed 16-bit lanes (B,R in one register, G alone): row sums <= 4080, column sums <= 65280, (x+128)>>8.
+// Weight: f32 in OpenCV 2.4.9's association (rows s0*6 + (s-1 + s1)*4 + s-2 + s2 left to right; columns
+// ((r0+r4)+(r2+r2)) + ((r1+r3)+r2)*4, scaled by 1/256 -- PyrDownVec_32f).
+template <bool IMG>
+__global__ void __launch_bounds__(256) mbx_pyrdown_kernel(const __grid_constant__ GroupParams p, int l) {
+    const int S = 32 >> (l + 1);                     // 16, 8, 4, 2, 1
+    const int cpw = max(S >> 1, 1), rqs = max(S >> 2, 1), tpc = cpw * rqs;   // threads per cell: 32, 8, 2, 1, 1
+    const int ipc = 256 / tpc;                       // cells per CTA iteration
+    const int rows = min(S, 4), rlim = 2 * rows + 3; // output rows per thread, input rows it streams
+    const unsigned n = p.list_count[(IMG ? 6 : 0) + l + 1];
+    const uint32_t* list = p.lists + ((size_t)(IMG ? p.levels : 0) + l + 1) * p.list_cap;
+    const int sub = threadIdx.x / tpc, tt = threadIdx.x - sub * tpc;
+    const int cp = tt % cpw, rq = tt / cpw;
+    const int ns = kEle >> l, nd = kEle >> (l + 1);
+    for (unsigned base = blockIdx.x * ipc; base < n; base += gridDim.x * ipc) {
+        const unsigned it = base + sub;
+        if (it >= n) continue;
+        const uint32_t item = list[it];
+        const int f = (int)(item >> 16), c = (int)(item & 0xFFFFu);
+        const FrameJob& J = p.jobs[f];
+        const int cw = J.wnx * 8, cy = c / cw, cx = c - cy * cw;
+        const int sww = J.wnx * ns, swh = J.wny * ns, srw = J.nx * ns, srh = J.ny * ns, sox = J.wx * ns, soy = J.wy * ns;
+        const int dww = J.wnx * nd, dox = J.wx * nd, doy = J.wy * nd;
+        const int u = cx * S + 2 * cp, v0 = cy * S + 4 * rq;
+        const bool two = S >= 2;
+        const int U = u + dox, V0 = v0 + doy;
+        int xs[7];
+        const int c0 = 2 * U - 2 - sox;
+        const bool fast = (2 * U - 2 >= 0) && (2 * U + 4 < srw) && (c0 >= 0) && (c0 + 6 < sww);
+        if (fast) {
+#pragma unroll
+            for (int d = 0; d < 7; d++) xs[d] = c0 + d;
+        } else {
+#pragma unroll
+            for (int d = 0; d < 7; d++) xs[d] = clampi(reflect101_idx(2 * U + d - 2, srw) - sox, 0, sww - 1);
+        }
+        if constexpr (IMG) {
+            const uint32_t* SG = reinterpret_cast<const uint32_t*>(p.scratch + J.g_off[l]);
+            uint32_t* DG = reinterpret_cast<uint32_t*>(p.scratch + J.g_off[l + 1]);
+            uint32_t hb0[5], hg0[5], hb1[5], hg1[5];
+#pragma unroll
+            for (int r = 0; r < 11; r++) {
+                if (r < rlim) {
+                    const int ys = clampi(reflect101_idx(2 * V0 + r - 2, srh) - soy, 0, swh - 1);
+                    const uint32_t* gr = SG + (size_t)ys * sww;
+                    uint32_t e[7];
+                    if (fast) {
+                        const uint2* g2 = reinterpret_cast<const uint2*>(gr + xs[0]);
+                        const uint2 a = g2[0], b = g2[1], cc = g2[2];
+                        e[0] = a.x; e[1] = a.y; e[2] = b.x; e[3] = b.y; e[4] = cc.x; e[5] = cc.y; e[6] = gr[xs[0] + 6];
+                    } else {
+#pragma unroll
+                        for (int d = 0; d < 7; d++) e[d] = gr[xs[d]];
+                    }
+                    uint32_t br[7], g[7];
+#pragma unroll
+                    for (int d = 0; d < 7; d++) { br[d] = e[d] & kM2; g[d] = (e[d] >> 8) & 0xFFu; }
+                    hb0[r % 5] = br[2] * 6u + (br[1] + br[3]) * 4u + br[0] + br[4];
+                    hb1[r % 5] = br[4] * 6u + (br[3] + br[5]) * 4u + br[2] + br[6];
+                    hg0[r % 5] = g[2] * 6u + (g[1] + g[3]) * 4u + g[0] + g[4];
+                    hg1[r % 5] = g[4] * 6u + (g[3] + g[5]) * 4u + g[2] + g[6];
+                    if (r >= 4 && (r & 1) == 0) {
+                        const int k = (r - 4) >> 1, v = v0 + k;
+                        const int i0 = (r - 4) % 5, i1 = (r - 3) % 5, i2 = (r - 2) % 5, i3 = (r - 1) % 5, i4 = r % 5;
+                        const uint32_t vbr0 = hb0[i0] + hb0[i4] + (hb0[i1] + hb0[i3]) * 4u + hb0[i2] * 6u;
+                        const uint32_t vbr1 = hb1[i0] + hb1[i4] + (hb1[i1] + hb1[i3]) * 4u + hb1[i2] * 6u;
+                        const uint32_t vg0 = hg0[i0] + hg0[i4] + (hg0[i1] + hg0[i3]) * 4u + hg0[i2] * 6u;
+                        const uint32_t vg1 = hg1[i0] + hg1[i4] + (hg1[i1] + hg1[i3]) * 4u + hg1[i2] * 6u;
+                        const uint32_t o0 = (((vbr0 + 0x00800080u) >> 8) & kM2) | (((vg0 + 128u) >> 8) << 8);
+                        const uint32_t o1 = (((vbr1 + 0x00800080u) >> 8) & kM2) | (((vg1 + 128u) >> 8) << 8);
+                        const size_t o = (size_t)v * dww + u;
+                        if (two) *reinterpret_cast<uint2*>(DG + o) = make_uint2(o0, o1);   // u and dww are even when S >= 2
+                        else DG[o] = o0;
+                    }
+                }
+            }
+        } else {
+            const float* SW = reinterpret_cast<const float*>(p.scratch + J.w_off[l]);
+            float* DW = reinterpret_cast<float*>(p.scratch + J.w_off[l + 1]);
+            float h0[5], h1[5];
+#pragma unroll
+            for (int r = 0; r < 11; r++) {
+                if (r < rlim) {
+                    const int ys = clampi(reflect101_idx(2 * V0 + r - 2, srh) - soy, 0, swh - 1);
+                    const float* wr = SW + (size_t)ys * sww;
+                    float fv[7];
+                    if (fast) {
+                        const float2* w2 = reinterpret_cast<const float2*>(wr + xs[0]);
+                        const float2 fa = w2[0], fb = w2[1], fc = w2[2];
+                        fv[0] = fa.x; fv[1] = fa.y; fv[2] = fb.x; fv[3] = fb.y; fv[4] = fc.x; fv[5] = fc.y; fv[6] = wr[xs[0] + 6];
+                    } else {
+#pragma unroll
+                        for (int d = 0; d < 7; d++) fv[d] = wr[xs[d]];
+                    }
+                    h0[r % 5] = fv[2] * 6.f + (fv[1] + fv[3]) * 4.f + fv[0] + fv[4];
+                    h1[r % 5] = fv[4] * 6.f + (fv[3] + fv[5]) * 4.f + fv[2] + fv[6];
+                    if (r >= 4 && (r & 1) == 0) {
+                        const int k = (r - 4) >> 1, v = v0 + k;
+                        const int i0 = (r - 4) % 5, i1 = (r - 3) % 5, i2 = (r - 2) % 5, i3 = (r - 1) % 5, i4 = r % 5;
+                        const float t00 = (h0[i0] + h0[i4]) + (h0[i2] + h0[i2]), t10 = (h0[i1] + h0[i3]) + h0[i2];
+                        const float t01 = (h1[i0] + h1[i4]) + (h1[i2] + h1[i2]), t11 = (h1[i1] + h1[i3]) + h1[i2];
+                        const float ow0 = (t00 + t10 * 4.f) * (1.f / 256.f), ow1 = (t01 + t11 * 4.f) * (1.f / 256.f);
+                        const size_t o = (size_t)v * dww + u;
+                        if (two) *reinterpret_cast<float2*>(DW + o) = make_float2(ow0, ow1);
+                        else DW[o] = ow0;
+                    }
+                }
+            }
+        }
+    }
+}
+cudaError_t launch_mbx_pyrdown(const GroupParams& p, int image, int level, int ctas, cudaStream_t stream) {
+    if (image) mbx_pyrdown_kernel<true><<<ctas, 256, 0, stream>>>(p, level);
+    else mbx_pyrdown_kernel<false><<<ctas, 256, 0, stream>>>(p, level);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// 2. decide, tile-centric and cell-aligned: per px of the tile, scan the COMPETITIVE entries of its cell in feed order
+// and keep the last one whose weight is >= everything before it (state included; a fresh tile starts at -inf so the
+// first entry copies unconditionally, MultiBandMap2DCPU.cpp:498-504) -- exactly what the sequential `if (srcW >= dstW)`
+// updates leave behind (:539-547; 0 >= 0 ties overwrite).  Winners go to the tile's weight plane, the winner map
+// (entry index per pyramid px, 0xFFFF = the state stands) and the frames' `win` cell flags; cmin gets the exact new
+// minimum of every revisited cell.  Cells without a competitive entry are skipped without a load.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mbs_decide_kernel(const __grid_constant__ GroupParams p, const __grid_constant__ TileLayout lay) {
+    const TileWork T = p.tiles[blockIdx.x];
+    const CellMap m = cell_map(blockIdx.y, threadIdx.x, p.levels);
+    if (!m.valid) return;
+    const int l = m.l, n = m.n, px = m.px, py = m.py;
+    const bool quad = m.npx == 4;
+    const uint32_t* cm = p.cmask + (((size_t)blockIdx.x * p.levels + l) * 64 + m.cell) * p.mask_words;
+    uint32_t any = 0u;
+    for (int w = 0; w < p.mask_words; w++) any |= cm[w];
+    if (!any) return;
+    const size_t to = (size_t)py * n + px;
+    float* tw = reinterpret_cast<float*>(T.state + lay.wgt_off[l]) + to;
+    float bw[4];
+    if (T.fresh) { bw[0] = bw[1] = bw[2] = bw[3] = -INFINITY; }
+    else if (quad) {
+        const float2 t0 = *reinterpret_cast<const float2*>(tw), t1 = *reinterpret_cast<const float2*>(tw + n);
+        bw[0] = t0.x; bw[1] = t0.y; bw[2] = t1.x; bw[3] = t1.y;
+    } else { bw[0] = tw[0]; bw[1] = bw[2] = bw[3] = INFINITY; }
+    int best[4] = {-1, -1, -1, -1};
+    unsigned wins = 0;
+    for (int w = 0; w < p.mask_words; w++) {
+        uint32_t bits = cm[w];
+        while (bits) {
+            const int i = w * 32 + __ffs(bits) - 1;
+            bits &= bits - 1;
+            const TileEntry E = p.entries[T.first + i];
+            const FrameJob& J = p.jobs[E.frame];
+            const int st = J.wnx * n;
+            const float* qp = reinterpret_cast<const float*>(p.scratch + J.w_off[l]) + (size_t)((E.rty - J.wy) * n + py) * st + (size_t)((E.rtx - J.wx) * n + px);
+            const unsigned cw = !(T.fresh && i == 0);
+            if (quad) {
+                const float2 t0 = *reinterpret_cast<const float2*>(qp), t1 = *reinterpret_cast<const float2*>(qp + st);
+                const float s[4] = {t0.x, t0.y, t1.x, t1.y};
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (s[k] >= bw[k]) { bw[k] = s[k]; best[k] = i; wins += cw; }   // '>=' : MultiBandMap2DCPU.cpp:542
+            } else {
+                const float s = qp[0];
+                if (s >= bw[0]) { bw[0] = s; best[0] = i; wins += cw; }
+            }
+        }
+    }
+    if (p.stats && wins) atomicAdd(p.stats + l, (unsigned long long)wins);
+    // winner map + tile weights
+    uint16_t* wm = p.wmap + (size_t)blockIdx.x * p.wmap_stride + lay.px_off[l] + to;
+    if (!quad) {
+        wm[0] = (uint16_t)(best[0] < 0 ? 0xFFFF : best[0]);
+        if (best[0] >= 0) tw[0] = bw[0];
+    } else {
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            const int k0 = 2 * r, k1 = 2 * r + 1;
+            *reinterpret_cast<ushort2*>(wm + (size_t)r * n) =
+                make_ushort2((unsigned short)(best[k0] < 0 ? 0xFFFF : best[k0]), (unsigned short)(best[k1] < 0 ? 0xFFFF : best[k1]));
+            float* wr = tw + (size_t)r * n;
+            if (best[k0] >= 0 && best[k1] >= 0) *reinterpret_cast<float2*>(wr) = make_float2(bw[k0], bw[k1]);
+            else if (best[k0] >= 0) wr[0] = bw[k0];
+            else if (best[k1] >= 0) wr[1] = bw[k1];
+        }
+    }
+    // exact minimum of the revisited cell (weights are >= 0, so the int order of the bit patterns is the float order)
+    const float mn = fminf(fminf(bw[0], bw[1]), fminf(bw[2], bw[3]));
+    atomicMin(reinterpret_cast<int*>(T.state + lay.cmin_off) + l * 64 + m.cell, __float_as_int(fmaxf(mn, 0.f)));
+    // `win` cell flags of the winning frames (all px of a thread lie in one cell of the tile)
+    const int ccx = m.cell & 7, ccy = m.cell >> 3;
+    int seen[4] = {-1, -1, -1, -1};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (best[k] < 0) continue;
+        bool dup = false;
+#pragma unroll
+        for (int k2 = 0; k2 < k; k2++) dup |= seen[k2] == best[k];
+        seen[k] = best[k];
+        if (dup) continue;
+        const TileEntry E = p.entries[T.first + best[k]];
+        const FrameJob& J = p.jobs[E.frame];
+        uint8_t* wf = p.win + cell_base(p, E.frame, l) + (size_t)((E.rty - J.wy) * 8 + ccy) * (J.wnx * 8) + ((E.rtx - J.wx) * 8 + ccx);
+        if (!*wf) *wf = 1;
+    }
+}
+cudaError_t launch_mbs_decide(const GroupParams& p, const TileLayout& lay, cudaStream_t stream) {
+    if (p.n_tiles == 0) return cudaSuccess;
+    dim3 g(p.n_tiles, cellmap_ctas(p.levels));
+    mbs_decide_kernel<<<g, 256, 0, stream>>>(p, lay);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// 5. Laplacian of the winners (read from the winner map) into the tile state; same mapping as decide, cells without a
+// competitive entry (no winner map written) are skipped
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 4) mbs_lap_kernel(const __grid_constant__ GroupParams p, const __grid_constant__ TileLayout lay) {
+    const TileWork T = p.tiles[blockIdx.x];
+    const CellMap m = cell_map(blockIdx.y, threadIdx.x, p.levels);
+    if (!m.valid) return;
+    const int l = m.l, n = m.n, px = m.px, py = m.py;
+    const bool quad = m.npx == 4;
+    const uint32_t* cm = p.cmask + (((size_t)blockIdx.x * p.levels + l) * 64 + m.cell) * p.mask_words;
+    uint32_t any = 0u;
+    for (int w = 0; w < p.mask_words; w++) any |= cm[w];
+    if (!any) return;
+    const size_t to = (size_t)py * n + px;
+    const uint16_t* wm = p.wmap + (size_t)blockIdx.x * p.wmap_stride + lay.px_off[l] + to;
+    int best[4] = {-1, -1, -1, -1};
+    if (quad) {
+        const ushort2 a = *reinterpret_cast<const ushort2*>(wm), b = *reinterpret_cast<const ushort2*>(wm + n);
+        best[0] = a.x == 0xFFFF ? -1 : a.x; best[1] = a.y == 0xFFFF ? -1 : a.y;
+        best[2] = b.x == 0xFFFF ? -1 : b.x; best[3] = b.y == 0xFFFF ? -1 : b.y;
+    } else best[0] = wm[0] == 0xFFFF ? -1 : wm[0];
+    if (best[0] < 0 && best[1] < 0 && best[2] < 0 && best[3] < 0) return;
+    int lap[4][3];
+    bool done[4] = {best[0] < 0, best[1] < 0, best[2] < 0, best[3] < 0};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (done[k]) continue;
+        const int f = best[k];
+        const TileEntry E = p.entries[T.first + f];
+        int tmp[4][3];
+        lap_quad(p, p.jobs[E.frame], l, E.rtx * n + px, E.rty * n + py, quad, tmp);
+#pragma unroll
+        for (int k2 = k; k2 < 4; k2++)
+            if (!done[k2] && best[k2] == f) { lap[k2][0] = tmp[k2][0]; lap[k2][1] = tmp[k2][1]; lap[k2][2] = tmp[k2][2]; done[k2] = true; }
+    }
+    const size_t plane = (size_t)n * n;
+    int16_t* tl = reinterpret_cast<int16_t*>(T.state + lay.lap_off[l]) + to;
+    if (!quad) {
+        tl[0] = (int16_t)lap[0][0]; tl[plane] = (int16_t)lap[0][1]; tl[2 * plane] = (int16_t)lap[0][2];
+        return;
+    }
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const int k0 = 2 * r, k1 = 2 * r + 1;
+        int16_t* tr = tl + (size_t)r * n;
+        if (best[k0] >= 0 && best[k1] >= 0) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) *reinterpret_cast<short2*>(tr + c * plane) = make_short2((short)lap[k0][c], (short)lap[k1][c]);
+        } else if (best[k0] >= 0) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) tr[c * plane] = (int16_t)lap[k0][c];
+        } else if (best[k1] >= 0) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) tr[c * plane + 1] = (int16_t)lap[k1][c];
+        }
+    }
+}
+cudaError_t launch_mbs_lap(const GroupParams& p, const TileLayout& lay, cudaStream_t stream) {
+    if (p.n_tiles == 0) return cudaSuccess;
+    dim3 g(p.n_tiles, cellmap_ctas(p.levels));
+    mbs_lap_kernel<<<g, 256, 0, stream>>>(p, lay);
+    return cudaGetLastError();
+}
+
+}  // namespace m2d

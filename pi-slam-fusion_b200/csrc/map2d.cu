@@ -23,6 +23,7 @@
 #include "../../include/map2d_b200.h"
 #include "geom.h"
 #include "kernels.cuh"
+#include "bounds.h"
 
 int m2d_write_png(const char* path, const uint8_t* bgr_or_bgra, int w, int h, int channels);  // png.cpp
 
@@ -141,17 +142,18 @@ struct m2d_map {
     size_t collapse_cap = 0;
 
     static constexpr int kMaxCtx = 8;
+    static constexpr int kMaxGroup = 1024;   // frames per group (the winner map holds 16-bit entry indices per tile)
     int kCtx = 4;                   // group contexts in flight (M2D_CTX env overrides, for tuning)
     bool weights_first = true;      // multi-band decides winners from the weight pyramids first, then warps and filters the
                                     // image only where a winner needs it (kernels.cu "WEIGHTS-FIRST variant"); M2D_SPARSE=0
                                     // selects the dense pipeline (every frame fully warped and filtered) for A/B runs
-    cudaStream_t decide_stream = nullptr;  // chain of the groups' decide stages (tile weights), ahead of the Laplacian chain
+    cudaStream_t decide_stream = nullptr;  // chain of the groups' bounds + decide stages (tile weights, cmin), ahead of the Laplacian chain
     cudaEvent_t dense_done = nullptr;      // last dense-pipeline select on the handle's stream (small groups), see run_group
     bool dense_pending = false;
-    bool decide_cull = false;       // M2D_DCULL=1 (EXPERIMENTAL, never run on a GPU): best-first decide stage with bound-based culling
-    bool lean_weights = false;      // M2D_WLEAN=1 (EXPERIMENTAL, never run on a GPU): shorter FP32 pass of the weight warp
-    bool fused_weight_pyr = false;  // M2D_WFUSED=1 (EXPERIMENTAL, unmeasured): weights-first pipeline with weight warp + first weight pyrDown fused
-    bool fused_warp_pyr = false;    // M2D_FUSED=1: warp + first pyrDown in one shared-memory kernel (measured 7 % slower, kept for A/B)
+    bool weight_cull = true;        // bound-based culling of (frame, cell) pairs before any weight is computed (bounds.h);
+                                    // M2D_WCULL=0 treats every covering frame as competitive (A/B runs, parity sweeps)
+    double scratch_budget = 12e9;   // bytes of group scratch per context that the default group size aims at (M2D_SCRATCH_GB)
+    int sm_count = 148;
     GroupCtx ctx[kMaxCtx];
     int ctx_next = 0;
 
@@ -211,11 +213,10 @@ int m2d_map::init() {
     CU(cudaMalloc(&d_stats, 32 * sizeof(unsigned long long)));
     CU(cudaMemsetAsync(d_stats, 0, 32 * sizeof(unsigned long long), stream));
     if (const char* e = getenv("M2D_CTX")) kCtx = std::max(2, std::min(atoi(e), (int)kMaxCtx));
-    if (const char* e = getenv("M2D_FUSED")) fused_warp_pyr = atoi(e) != 0;
     if (const char* e = getenv("M2D_SPARSE")) weights_first = atoi(e) != 0;
-    if (const char* e = getenv("M2D_WFUSED")) fused_weight_pyr = atoi(e) != 0;
-    if (const char* e = getenv("M2D_WLEAN")) lean_weights = atoi(e) != 0;
-    if (const char* e = getenv("M2D_DCULL")) decide_cull = atoi(e) != 0;
+    if (const char* e = getenv("M2D_WCULL")) weight_cull = atoi(e) != 0;
+    if (const char* e = getenv("M2D_SCRATCH_GB")) scratch_budget = std::max(0.25, atof(e)) * 1e9;
+    CU(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, cfg.device));
     CU(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&decide_stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&dense_done, cudaEventDisableTiming));
@@ -421,16 +422,23 @@ int m2d_map::grow(void** p, size_t* cap, size_t need, bool pinned) {
 }
 
 int m2d_map::group_size(int w, int h, bool on_device) const {
-    if (cfg.batch_frames > 0) return std::min(cfg.batch_frames, 512);
+    if (cfg.batch_frames > 0) return std::min(cfg.batch_frames, kMaxGroup);
     // Weighted mode keeps no per-frame scratch, and its best-first culling gets sharper the more frames a group holds:
-    // device-resident batches are fused in groups of 192 frames (larger single launches stop overlapping host preparation) (host batches stay small so that the H2D
-    // staging of one group overlaps the fusion of the previous one).
+    // device-resident batches are fused in groups of 192 frames (larger single launches stop overlapping host
+    // preparation); host batches stay small so that the H2D staging of one group overlaps the fusion of the previous one.
     if (type != M2D_TYPE_MULTIBAND && on_device) return 192;
-    double mpx = (double)w * h / 1e6;
-    // weights-first multi-band: the more frames compete inside a group, the smaller each frame's share of winners and
-    // with it the image work (measured: 32 / 64 / 128 frames of 720p -> 7.8 / 7.4 / 6.8 ms per 500 frames)
-    // (host batches keep the smaller groups: the H2D staging of the first group is not overlapped by anything)
-    if (type == M2D_TYPE_MULTIBAND && weights_first && !fused_warp_pyr && on_device) return std::max(1, std::min((int)(200.0 / std::max(mpx, 0.25)), 128));
+    const double mpx = (double)w * h / 1e6;
+    if (type == M2D_TYPE_MULTIBAND && weights_first) {
+        // weights-first multi-band: the more frames compete inside a group, the smaller each frame's share of competitive
+        // cells and winners, and with it the weight AND image work -> as many frames as the scratch budget holds (a frame's
+        // scratch pyramid is ~11 B per px of its tile-aligned region).  Host batches keep 64-frame groups: they are bound
+        // by the PCIe copy, which the next group's copy must overlap.
+        if (!on_device) return std::max(4, std::min((int)(100.0 / std::max(mpx, 0.25)), 64));
+        const double s = (cfg.resolution > 0 || cfg.scale <= 0) ? 1.0 : cfg.scale;
+        const double tiles = (std::ceil(w * s / kEle) + 2) * (std::ceil(h * s / kEle) + 2);
+        const double per_frame = tiles * kEle * kEle * 11.0;
+        return std::max(4, std::min((int)(scratch_budget / per_frame), kMaxGroup));
+    }
     int k = (int)(100.0 / std::max(mpx, 0.25));  // ~100 Mpx of source per group (measured: larger groups amortise better)
     return std::max(1, std::min(k, 64));
 }
@@ -484,6 +492,7 @@ int m2d_map::feed_frames(int n, const uint8_t* base, size_t frame_stride, int w,
     CU(cudaSetDevice(cfg.device));
     { int rc = ensure_weight_images(w, h); if (rc != M2D_OK) return rc; }
     int K = group_size(w, h, on_device);
+    if (n > K) K = (n + (n + K - 1) / K - 1) / ((n + K - 1) / K);   // equal-sized groups: 500 frames at K = 480 -> 250 + 250
     int worst = M2D_OK;
     for (int i = 0; i < n; i += K) {
         int m = std::min(K, n - i);
@@ -630,17 +639,25 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
     { size_t cap = c.blob_cap; int rc = grow((void**)&c.h_blob, &cap, blob, true); if (rc != M2D_OK) return rc;
       rc = grow((void**)&c.d_blob, &c.blob_cap, blob, false); if (rc != M2D_OK) return rc; }
     if (!on_device) { int rc = grow((void**)&c.d_raw, &c.raw_cap, (size_t)nj * npx * 3 + 256, false); if (rc != M2D_OK) return rc; }
-    // weights-first multi-band: cell flags (win | need) and the winner map live behind the pyramids
+    // weights-first multi-band: cell flags, competitive masks, work lists and the winner map live behind the pyramids
     // (groups of a few frames -- streaming feed() calls -- take the dense pipeline: a lone frame wins most of what it
-    // covers, so there is little to skip, and the dense pipeline needs 6 launches instead of 14)
-    const bool sparse = weights_first && type == M2D_TYPE_MULTIBAND && levels <= 6 && !fused_warp_pyr && !tiles.empty() && nj >= 4;
+    // covers, so there is little to skip, and the dense pipeline needs 6 launches instead of ~20)
+    const bool sparse = weights_first && type == M2D_TYPE_MULTIBAND && levels <= 6 && !tiles.empty() && nj >= 4;
     const int cells_max = max_wnx * 8 * max_wny * 8;
     const int wmap_stride = (lay.px_off[levels] + 7) & ~7;
-    size_t off_win = 0, off_need = 0, off_wmap = 0, flag_bytes = 0;
+    size_t off_flags = 0, off_cmask = 0, off_lists = 0, off_counts = 0, off_wmap = 0, flag_bytes = 0;
+    int mask_words = 1;
     if (sparse) {
+        if (cells_max > 65535 || nj > 65535) { err = "frame region too large for the weights-first work lists"; return M2D_ERR_UNSUPPORTED; }
+        size_t max_count = 1;
+        for (size_t t = 0; t < tiles.size(); t++) max_count = std::max(max_count, per_tile[t].size());
+        mask_words = (int)((max_count + 31) / 32);
         flag_bytes = ((size_t)nj * levels * cells_max + 255) & ~(size_t)255;
-        off_win = scratch; scratch += flag_bytes;
-        off_need = scratch; scratch += flag_bytes;
+        off_flags = scratch; scratch += 2 * flag_bytes;                                   // comp | win   (zeroed per group ...
+        off_counts = scratch; scratch += 256;                                             // ... together with the 12 list lengths)
+        scratch += 2 * flag_bytes;                                                        // needw | need (fully written by propagate)
+        off_cmask = scratch; scratch += ((size_t)tiles.size() * levels * 64 * mask_words * sizeof(uint32_t) + 255) & ~(size_t)255;
+        off_lists = scratch; scratch += ((size_t)2 * levels * nj * cells_max * sizeof(uint32_t) + 255) & ~(size_t)255;
         off_wmap = scratch; scratch += ((size_t)tiles.size() * wmap_stride * sizeof(uint16_t) + 255) & ~(size_t)255;
     }
     if (scratch) { int rc = grow((void**)&c.d_scratch, &c.scratch_cap, scratch, false); if (rc != M2D_OK) return rc; }
@@ -666,7 +683,7 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
     }
     if (!on_device) {
         CU(cudaEventRecord(c.copied, copy_stream));
-        CU(cudaStreamWaitEvent(c.stage, c.copied, 0));
+        if (!sparse) CU(cudaStreamWaitEvent(c.stage, c.copied, 0));   // weights-first: only the image stage waits for the pixels
     }
     // ---- work lists
     memcpy(c.h_blob, jobs.data(), (size_t)nj * sizeof(FrameJob));
@@ -675,9 +692,8 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
     // Weighted mode visits a tile's frames best-first (closest footprint centre first): the result is order-free
     // ("largest alpha, earliest frame on ties", tracked per px by the kernel) and almost every later frame is then
     // rejected by the alpha upper bound before any sampling.  With collect_stats the sequential order is kept.
-    // (multi-band: only the experimental best-first decide stage wants it, M2D_DCULL=1; its rule "largest weight, latest
-    // frame on ties" is order-free as well)
-    const bool best_first = ((type != M2D_TYPE_MULTIBAND) || (sparse && decide_cull)) && !cfg.collect_stats;
+    // (multi-band keeps feed order: its tie rule -- the LAST of equal weights wins -- is resolved by scanning in order)
+    const bool best_first = (type != M2D_TYPE_MULTIBAND) && !cfg.collect_stats;
     for (size_t t = 0; t < tiles.size(); t++) {
         if (best_first && per_tile[t].size() > 1) {
             float cx = (float)tile_abs[t].first + 0.5f, cy = (float)tile_abs[t].second + 0.5f;
@@ -703,11 +719,19 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
     p.sw = w; p.sh = h; p.levels = levels; p.weight_type = cfg.weight_type;
     p.alpha = d_alpha; p.wimg = d_wimg; p.scratch = c.d_scratch;
     p.stats = cfg.collect_stats ? d_stats : nullptr;
+    p.need_stats = (cfg.collect_stats || profiling) ? d_stats : nullptr;
     p.max_wnx = max_wnx; p.max_wny = max_wny;
     if (sparse) {
-        p.win = c.d_scratch + off_win; p.need = c.d_scratch + off_need; p.cells_max = cells_max;
+        p.comp = c.d_scratch + off_flags; p.win = p.comp + flag_bytes;
+        p.needw = c.d_scratch + off_counts + 256; p.need = p.needw + flag_bytes;
+        p.cells_max = cells_max;
+        p.cmask = reinterpret_cast<uint32_t*>(c.d_scratch + off_cmask); p.mask_words = mask_words;
+        p.lists = reinterpret_cast<uint32_t*>(c.d_scratch + off_lists); p.list_cap = nj * cells_max;
+        p.list_count = reinterpret_cast<unsigned*>(c.d_scratch + off_counts);
         p.wmap = reinterpret_cast<uint16_t*>(c.d_scratch + off_wmap); p.wmap_stride = wmap_stride;
         make_reach_table(levels, p.reach_lo, p.reach_hi);
+        make_weight_reach_table(levels, p.wreach_lo, p.wreach_hi);
+        p.cull = (weight_cull && !cfg.collect_stats) ? 1 : 0;   // the win counters follow the sequential semantics: no culling then
     }
 
     // Order-independent stages run on the context's own stream (they overlap the previous group's select); the
@@ -719,37 +743,35 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
         CU(cudaStreamWaitEvent(c.stage, c.staged, 0));
     }
     if (sparse) {
-        // (a level goes to the tail only when its output is small: <= 16 K px per frame)
-        auto small_level = [&](int lv) { long long nd = kEle >> (lv + 1); return (long long)max_wnx * nd * max_wny * nd <= 16384; };
-        int l_tail = 0;
-        for (; l_tail + 1 < levels && (!small_level(l_tail) || levels - 1 - l_tail < 2); l_tail++) {}
-        // 1. weights only, dense, on the context's stream
-        CU(cudaMemsetAsync(p.win, 0, flag_bytes, c.stage));
-        int l_w = 0;   // first level the stand-alone weight pyrDown still has to produce from
-        if (fused_weight_pyr && levels >= 2) {
-            LAUNCHKS(M2D_K_MBW_WARP, c.stage, launch_mbw_warp_pyr(p, c.stage, lean_weights));   // levels 0 and 1 in one pass
-            l_w = 1;
-        } else LAUNCHKS(M2D_K_MBW_WARP, c.stage, launch_mbw_warp(p, c.stage, lean_weights));
-        for (int l = l_w; l < l_tail; l++) LAUNCHKS(M2D_K_MBW_PYR, c.stage, launch_mbw_pyrdown(p, l, c.stage));
-        if (l_tail + 1 < levels) LAUNCHKS(M2D_K_MBW_PYR, c.stage, launch_mbw_pyrtail(p, l_tail, c.stage));
-        CU(cudaEventRecord(c.staged, c.stage));
-        // 2.+3. winners and need flags: the decide chain serialises groups in feed order (tile weights only), and runs
-        // ahead of the Laplacian chain on the handle's stream (which writes the Laplacian planes only)
+        const int ctas = sm_count * 8;   // persistent list kernels: every resident CTA slot of the GPU, grid-stride over the items
+        // 0.+1. competitive cells (closed-form bounds against the other frames and the tile state), then the weights in the
+        // cells that matter.  bounds reads/reset cmin, which the previous group's decide wrote: it runs on the decide chain.
         cudaStream_t ds = profiling ? stream : decide_stream;
+        CU(cudaEventRecord(c.staged, c.stage));                      // the blob upload
         CU(cudaStreamWaitEvent(ds, c.staged, 0));
         if (dense_pending) {   // a dense group's select (handle stream) wrote tile weights: the decide chain must see them
             CU(cudaStreamWaitEvent(ds, dense_done, 0));
             dense_pending = false;
         }
-        if (decide_cull && !cfg.collect_stats) LAUNCHKS(M2D_K_MBS_DECIDE, ds, launch_mbs_decide_bf(p, lay, ds));
-        else LAUNCHKS(M2D_K_MBS_DECIDE, ds, launch_mbs_decide(p, lay, ds));
-        LAUNCHKS(M2D_K_MBS_PROPAGATE, ds, launch_mbs_propagate(p, ds));
+        CU(cudaMemsetAsync(p.comp, 0, 2 * flag_bytes + 256, ds));    // comp | win flags ... and the list lengths (off_counts follows the flags)
+        LAUNCHKS(M2D_K_MBC_BOUNDS, ds, launch_mbc_bounds(p, lay, ds));
+        LAUNCHKS(M2D_K_MBS_PROPAGATE, ds, launch_mbx_propagate(p, 0, ds));
         CU(cudaEventRecord(c.decided, ds));
-        // 4. image work in the needed cells, back on the context's stream
         CU(cudaStreamWaitEvent(c.stage, c.decided, 0));
-        LAUNCHKS(M2D_K_MBS_WARP, c.stage, launch_mbs_warp(p, c.stage));
-        for (int l = 0; l < l_tail; l++) LAUNCHKS(M2D_K_MBS_PYR, c.stage, launch_mbs_pyrdown(p, l, c.stage));
-        if (l_tail + 1 < levels) LAUNCHKS(M2D_K_MBS_PYR, c.stage, launch_mbs_pyrtail(p, l_tail, c.stage));
+        LAUNCHKS(M2D_K_MBW_WARP, c.stage, launch_mbw_warp(p, ctas, c.stage));
+        for (int l = 0; l + 1 < levels; l++) LAUNCHKS(M2D_K_MBW_PYR, c.stage, launch_mbx_pyrdown(p, 0, l, ctas, c.stage));
+        CU(cudaEventRecord(c.staged, c.stage));
+        // 2.+3. winners and need flags: the decide chain serialises groups in feed order (tile weights only), and runs
+        // ahead of the Laplacian chain on the handle's stream (which writes the Laplacian planes only)
+        CU(cudaStreamWaitEvent(ds, c.staged, 0));
+        LAUNCHKS(M2D_K_MBS_DECIDE, ds, launch_mbs_decide(p, lay, ds));
+        LAUNCHKS(M2D_K_MBS_PROPAGATE, ds, launch_mbx_propagate(p, 1, ds));
+        CU(cudaEventRecord(c.decided, ds));
+        // 4. image work in the needed cells, back on the context's stream (only here are the frames' pixels needed)
+        CU(cudaStreamWaitEvent(c.stage, c.decided, 0));
+        if (!on_device) CU(cudaStreamWaitEvent(c.stage, c.copied, 0));
+        LAUNCHKS(M2D_K_MBS_WARP, c.stage, launch_mbs_warp(p, ctas, c.stage));
+        for (int l = 0; l + 1 < levels; l++) LAUNCHKS(M2D_K_MBS_PYR, c.stage, launch_mbx_pyrdown(p, 1, l, ctas, c.stage));
         CU(cudaEventRecord(c.staged, c.stage));
         // 5. winners' Laplacians into the tiles, in feed order on the handle's stream
         CU(cudaStreamWaitEvent(stream, c.staged, 0));
@@ -757,12 +779,7 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
     } else if (type == M2D_TYPE_MULTIBAND) {
         // full-grid pyrDown while a level is big enough; the small deep levels go through one tail launch
         int l = 0;
-        if (fused_warp_pyr && levels >= 2) {
-            LAUNCHKS(M2D_K_MB_WARP, c.stage, launch_mb_warp_pyr(p, c.stage));  // level 0 and level 1 in one pass
-            l = 1;
-        } else {
-            LAUNCHKS(M2D_K_MB_WARP, c.stage, launch_mb_warp(p, c.stage));
-        }
+        LAUNCHKS(M2D_K_MB_WARP, c.stage, launch_mb_warp(p, c.stage));
         // (a level goes to the tail only when its output is small: <= 16 K px per frame, i.e. one 1024-thread CTA's worth)
         auto small_level = [&](int lv) { long long nd = kEle >> (lv + 1); return (long long)max_wnx * nd * max_wny * nd <= 16384; };
         for (; l + 1 < levels && (!small_level(l) || levels - 1 - l < 2); l++) LAUNCHKS(M2D_K_MB_PYRDOWN, c.stage, launch_mb_pyrdown(p, l, c.stage));
@@ -1290,6 +1307,10 @@ int m2d_save(m2d_handle h, const char* filename) {
 }
 
 size_t m2d_tile_bytes(m2d_handle h) { return h ? h->tile_bytes : 0; }
+size_t m2d_tile_state_bytes(m2d_handle h) {
+    if (!h) return 0;
+    return h->type == M2D_TYPE_MULTIBAND ? h->lay.cmin_off : h->tile_bytes;
+}
 int m2d_tile_count(m2d_handle h) { API_LOCK(h); return h ? (int)h->tiles_in_use : 0; }
 
 int m2d_export_tiles(m2d_handle h, int max_tiles, int* abs_xy, uint8_t* dst, int dst_on_device, int* n_out) {
@@ -1531,7 +1552,12 @@ int m2d_get_stats(m2d_handle h, m2d_stats* out) {
     CU(cudaMemcpyAsync(d, m.d_stats, sizeof d, cudaMemcpyDeviceToHost, m.stream));
     CU(cudaStreamSynchronize(m.stream));
     *out = m.stats;
-    if (m.type == M2D_TYPE_MULTIBAND) for (int l = 0; l < M2D_MAX_LEVELS; l++) { out->win_px[l] = d[l]; out->need_px[l] = 20 + l < 32 ? d[20 + l] : 0; }
+    if (m.type == M2D_TYPE_MULTIBAND)
+        for (int l = 0; l < M2D_MAX_LEVELS; l++) {
+            out->win_px[l] = d[l];
+            out->need_px[l] = l < 6 ? d[20 + l] : 0;
+            out->needw_px[l] = l < 6 ? d[26 + l] : 0;
+        }
     else { out->win_px[0] = d[17]; out->footprint_px = d[16]; }
     return M2D_OK;
 }
@@ -1586,6 +1612,24 @@ int m2d_tile_gps_corners(const double* plane7, double grid_min_x, double grid_mi
         out[i][1] = wy / lat_unit + lat1;
         out[i][2] = 0.0;
     }
+    return M2D_OK;
+}
+
+int m2d_cell_weight_bounds(const double* hinv, int nx, int ny, int sw, int sh, int weight_type, int level, int cx, int cy,
+                           float* lo, float* hi) {
+    if (!hinv || !lo || !hi || level < 0 || level > 5 || nx < 1 || ny < 1 || cx < 0 || cy < 0 || cx >= nx * 8 || cy >= ny * 8) return M2D_ERR_ARG;
+    float m[9];
+    for (int i = 0; i < 9; i++) m[i] = (float)hinv[i];   // FrameJob::hinvf
+    cell_weight_bounds(m, nx, ny, sw, sh, weight_type, level, cx, cy, lo, hi);
+    return M2D_OK;
+}
+
+int m2d_weight_reach_table(int levels, unsigned char* lo, unsigned char* hi) {
+    if (!lo || !hi || levels < 1 || levels > 6) return M2D_ERR_ARG;
+    unsigned char l[6][6], h[6][6];
+    make_weight_reach_table(levels, l, h);
+    memcpy(lo, l, 36);
+    memcpy(hi, h, 36);
     return M2D_OK;
 }
 

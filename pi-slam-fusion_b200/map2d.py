@@ -35,20 +35,21 @@ class Stats(C.Structure):
     """m2d_stats"""
     _fields_ = [("frames_fed", C.c_uint64), ("frames_fused", C.c_uint64), ("input_px", C.c_uint64),
                 ("region_px", C.c_uint64 * MAX_LEVELS), ("fresh_px", C.c_uint64 * MAX_LEVELS),
-                ("win_px", C.c_uint64 * MAX_LEVELS), ("footprint_px", C.c_uint64), ("need_px", C.c_uint64 * MAX_LEVELS)]
+                ("win_px", C.c_uint64 * MAX_LEVELS), ("footprint_px", C.c_uint64), ("need_px", C.c_uint64 * MAX_LEVELS),
+                ("needw_px", C.c_uint64 * MAX_LEVELS)]
 
     def as_dict(self):
         return {"frames_fed": self.frames_fed, "frames_fused": self.frames_fused, "input_px": self.input_px,
                 "region_px": list(self.region_px), "fresh_px": list(self.fresh_px), "win_px": list(self.win_px),
-                "footprint_px": self.footprint_px, "need_px": list(self.need_px)}
+                "footprint_px": self.footprint_px, "need_px": list(self.need_px), "needw_px": list(self.needw_px)}
 
 
 EXPORTS = ["m2d_config_default", "m2d_create", "m2d_destroy", "m2d_prepare", "m2d_feed", "m2d_feed_device",
            "m2d_feed_batch", "m2d_feed_poses", "m2d_plan_rects", "m2d_set_shard", "m2d_sync", "m2d_queue_size", "m2d_set_stream", "m2d_reset", "m2d_get_grid",
-           "m2d_last_rect", "m2d_get_tile", "m2d_get_image", "m2d_save", "m2d_tile_bytes", "m2d_tile_count",
+           "m2d_last_rect", "m2d_get_tile", "m2d_get_image", "m2d_save", "m2d_tile_bytes", "m2d_tile_state_bytes", "m2d_tile_count",
            "m2d_export_tiles", "m2d_import_tiles", "m2d_poll_changed", "m2d_get_tile_image", "m2d_save_state", "m2d_load_state", "m2d_get_stats", "m2d_last_error",
            "m2d_launch_count", "m2d_profile", "m2d_get_kernel_times", "m2d_alloc_host", "m2d_free_host", "m2d_compute_bounds",
-           "m2d_tile_gps_corners", "m2d_reach_table", "m2d_ingest_open", "m2d_ingest_open_seeded", "m2d_ingest_abort", "m2d_ingest_push", "m2d_ingest_pause", "m2d_ingest_drain", "m2d_ingest_close", "m2d_ingest_stats"]
+           "m2d_tile_gps_corners", "m2d_reach_table", "m2d_weight_reach_table", "m2d_cell_weight_bounds", "m2d_ingest_open", "m2d_ingest_open_seeded", "m2d_ingest_abort", "m2d_ingest_push", "m2d_ingest_pause", "m2d_ingest_drain", "m2d_ingest_close", "m2d_ingest_stats"]
 
 _lib = None
 
@@ -76,6 +77,9 @@ def lib():
     L.m2d_plan_rects.argtypes = [vp, C.c_int, dp, ip]
     L.m2d_tile_gps_corners.argtypes = [dp, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, dp, dp, dp]
     L.m2d_reach_table.argtypes = [C.c_int, C.POINTER(C.c_ubyte), C.POINTER(C.c_ubyte)]
+    L.m2d_weight_reach_table.argtypes = [C.c_int, C.POINTER(C.c_ubyte), C.POINTER(C.c_ubyte)]
+    L.m2d_cell_weight_bounds.argtypes = [dp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.m2d_ingest_open.argtypes = [vp, C.c_int, C.c_int]
     L.m2d_ingest_open_seeded.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.m2d_ingest_abort.argtypes = [vp]
@@ -97,6 +101,8 @@ def lib():
     L.m2d_save.argtypes = [vp, C.c_char_p]
     L.m2d_tile_bytes.argtypes = [vp]
     L.m2d_tile_bytes.restype = C.c_size_t
+    L.m2d_tile_state_bytes.argtypes = [vp]
+    L.m2d_tile_state_bytes.restype = C.c_size_t
     L.m2d_tile_count.argtypes = [vp]
     L.m2d_export_tiles.argtypes = [vp, C.c_int, ip, vp, C.c_int, ip]
     L.m2d_import_tiles.argtypes = [vp, C.c_int, ip, vp, C.c_int]
@@ -151,6 +157,25 @@ def reach_table(levels):
     if rc != OK:
         raise ValueError("m2d_reach_table(%d) failed: %d" % (levels, rc))
     return lo.reshape(6, 6), hi.reshape(6, 6)
+
+
+def weight_reach_table(levels):
+    """(lo, hi) 6x6 uint8 arrays of m2d_weight_reach_table: cells of weight level k a competitive cell of level m depends on."""
+    lo, hi = np.zeros(36, np.uint8), np.zeros(36, np.uint8)
+    rc = lib().m2d_weight_reach_table(levels, lo.ctypes.data_as(C.POINTER(C.c_ubyte)), hi.ctypes.data_as(C.POINTER(C.c_ubyte)))
+    if rc != OK:
+        raise ValueError("m2d_weight_reach_table(%d) failed: %d" % (levels, rc))
+    return lo.reshape(6, 6), hi.reshape(6, 6)
+
+
+def cell_weight_bounds(hinv, nx, ny, sw, sh, weight_type, level, cx, cy):
+    """(lo, hi) of m2d_cell_weight_bounds: closed-form bounds of a frame's level-`level` weight over one 32-px cell."""
+    hinv = np.ascontiguousarray(hinv, np.float64).reshape(9)
+    lo, hi = C.c_float(), C.c_float()
+    rc = lib().m2d_cell_weight_bounds(_dptr(hinv), nx, ny, sw, sh, weight_type, level, cx, cy, C.byref(lo), C.byref(hi))
+    if rc != OK:
+        raise ValueError("m2d_cell_weight_bounds failed: %d" % rc)
+    return lo.value, hi.value
 
 
 def map2d_update_command(plane, grid, tx, ty, gps_origin, image_name="LastTexMat"):
@@ -396,6 +421,10 @@ class Map2D:
     def tile_bytes(self):
         return int(lib().m2d_tile_bytes(self._h))
 
+    def tile_state_bytes(self):
+        """Leading bytes of a tile record that are reference state (the rest is library-private), see m2d_tile_state_bytes."""
+        return int(lib().m2d_tile_state_bytes(self._h))
+
     def tile_count(self):
         return int(lib().m2d_tile_count(self._h))
 
@@ -455,7 +484,7 @@ class Map2D:
         return int(lib().m2d_launch_count(self._h))
 
     KERNEL_CLASSES = ("weighted_fuse", "mb_warp", "mb_pyrdown", "mb_select", "collapse", "misc", "mb_pyrtail",
-                      "mbw_warp", "mbw_pyramid", "mbs_decide", "mbs_propagate", "mbs_warp", "mbs_pyramid", "mbs_lap", "k14", "k15")
+                      "mbw_warp", "mbw_pyramid", "mbs_decide", "mbs_propagate", "mbs_warp", "mbs_pyramid", "mbs_lap", "mbc_bounds", "k15")
 
     def profile(self, enable):
         return self._check(lib().m2d_profile(self._h, int(enable)))

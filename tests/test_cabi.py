@@ -49,7 +49,7 @@ def test_config_struct_layout_matches():
     assert c.weight_type == 0 and c.force_float == 0 and c.collect_stats == 0 and c.batch_frames == 0
     # header struct: 2 doubles + 12 ints
     assert C.sizeof(m2d.Config) == 2 * 8 + 12 * 4
-    assert C.sizeof(m2d.Stats) == 8 * (3 + 3 * m2d.MAX_LEVELS + 1 + m2d.MAX_LEVELS)  # ... + need_px[MAX_LEVELS]
+    assert C.sizeof(m2d.Stats) == 8 * (3 + 3 * m2d.MAX_LEVELS + 1 + 2 * m2d.MAX_LEVELS)  # ... + need_px, needw_px[MAX_LEVELS]
 
 
 def test_unsupported_types_and_arguments():

@@ -336,33 +336,16 @@ def test_tile_shards_on_one_gpu_equal_unsharded(typ, axis, span, count):
         m.close()
 
 
-def test_fused_warp_pyramid_variant_is_bit_exact(monkeypatch):
-    """M2D_FUSED=1 selects the shared-memory kernel that warps a block plus halo and emits level 1 directly (an A/B
-    alternative to the two-pass path).  Same bits, including sharded windows and 8 bands."""
-    import torch
-    monkeypatch.setenv("M2D_FUSED", "1")
-    seq = synth.Sequence(12, 320, 180, seed=23, jitter=True, noise=True, fpl=4, prepare_frames=4)
-    dev = torch.from_numpy(seq.frames()).cuda()
-    for kw in ({}, {"band_number": 8}, {"band_number": 1}, {"shard_rank": 1, "shard_count": 2, "shard_axis": 0, "shard_span": 1}):
-        g = m2d.Map2D.create(3, thread=False, batch_frames=5, **kw)
-        o = O.OracleMap2D.create(3, **kw)
-        assert g.prepare(seq.plane, seq.camera, seq.prepare_poses) and o.prepare(seq.plane, seq.camera, seq.prepare_poses)
-        res = g.feed_batch(dev.data_ptr(), seq.n, seq.w * seq.h * 3, seq.w, seq.h, seq.w * 3, seq.poses, True)
-        for k in range(seq.n):
-            assert (res[k] == 0) == o.feed(seq.frame(k), seq.poses[k])
-        g.sync()
-        compare_state(g, o, 3)
-        g.close()
-
-
-@pytest.mark.parametrize("sparse", ["1", "0"])
-def test_weights_first_and_dense_pipelines_are_bit_exact(monkeypatch, sparse):
-    """Multi-band has two pipelines: weights-first (default; winners decided from the weight pyramids, image
-    warp/pyrDown only in the cells a winner's Laplacian needs) and dense (M2D_SPARSE=0).  Same bits as
-    the oracle from both: jittered and noisy frames, several groups, 1/3/5 bands, a sharded window, stats, and the
-    dense fallback the weights-first pipeline takes for 8 bands."""
+@pytest.mark.parametrize("sparse,cull", [("1", "1"), ("1", "0"), ("0", "1")])
+def test_weights_first_and_dense_pipelines_are_bit_exact(monkeypatch, sparse, cull):
+    """Multi-band has two pipelines: weights-first (default; competitive cells from closed-form weight bounds, winners
+    decided from the weight pyramids, image warp/pyrDown only in the cells a winner's Laplacian needs, DESIGN.md §3;
+    M2D_WCULL=0 switches the bound-based culling off) and dense (M2D_SPARSE=0).  Same bits as the oracle from all:
+    jittered and noisy frames, several groups, 1/3/5 bands, a sharded window, stats, and the dense fallback the
+    weights-first pipeline takes for 8 bands."""
     import torch
     monkeypatch.setenv("M2D_SPARSE", sparse)
+    monkeypatch.setenv("M2D_WCULL", cull)
     seq = synth.Sequence(14, 320, 180, seed=29, jitter=True, noise=True, fpl=4, prepare_frames=4)
     dev = torch.from_numpy(seq.frames()).cuda()
     for kw in ({}, {"band_number": 3}, {"band_number": 1}, {"band_number": 8}, {"collect_stats": 1},
@@ -392,43 +375,103 @@ def test_weights_first_and_dense_pipelines_are_bit_exact(monkeypatch, sparse):
     g.close()
 
 
-@pytest.mark.skipif(os.environ.get("M2D_TEST_EXPERIMENTAL") != "1",
-                    reason="experimental kernel variants are parity-checked on demand (M2D_TEST_EXPERIMENTAL=1)")
-@pytest.mark.parametrize("variant", [{"M2D_WFUSED": "1"}, {"M2D_WLEAN": "1"}, {"M2D_WFUSED": "1", "M2D_WLEAN": "1"}, {"M2D_DCULL": "1"},
-                                     {"M2D_WFUSED": "1", "M2D_WLEAN": "1", "M2D_DCULL": "1"}])
-def test_experimental_weight_kernels_are_bit_exact(monkeypatch, variant):
-    """Opt-in variants of the weights-first pipeline's weight stage.  M2D_WFUSED=1 (weight warp + first weight pyrDown
-    fused) passed this test on the B200 at the end of round 1 but was never timed; M2D_WLEAN=1 (shorter FP32 pass:
-    explicit FMAs, Newton-carried reciprocal, magic-number rounding) has only been checked by the numpy emulation in
-    tests/test_weights_first_host.py; M2D_DCULL=1 (best-first decide stage that skips frames whose weight upper bound
-    cannot win) has its bound and its order-free rule checked on the CPU only.  All stay opt-in, and this test on
-    demand, until they have run and been measured on a GPU."""
+def raw_state(m):
+    """Every tile this handle holds as (sorted absolute coordinates, [n, state_bytes] uint8 CUDA tensor of reference state)."""
     import torch
-    for k, v in variant.items():
-        monkeypatch.setenv(k, v)
-    seq = synth.Sequence(14, 320, 180, seed=29, jitter=True, noise=True, fpl=4, prepare_frames=4)
-    dev = torch.from_numpy(seq.frames()).cuda()
-    for kw in ({}, {"band_number": 3}, {"band_number": 1}, {"shard_rank": 1, "shard_count": 2, "shard_axis": 0, "shard_span": 1}):
-        g = m2d.Map2D.create(3, thread=False, batch_frames=5, **kw)
-        o = O.OracleMap2D.create(3, **kw)
+    n, tb, sb = m.tile_count(), m.tile_bytes(), m.tile_state_bytes()
+    buf = torch.empty(max(n, 1) * tb, dtype=torch.uint8, device="cuda")
+    xy = m.export_tiles(buf.data_ptr(), n, True)
+    order = np.lexsort((xy[:, 0], xy[:, 1]))
+    st = buf.view(max(n, 1), tb)[:n, :sb][torch.from_numpy(order).cuda()]
+    return xy[order], st
+
+
+@pytest.mark.parametrize("typ,n,seed", [(1, 100, 1), (3, 500, 2)])
+def test_benchmarked_configs_are_bit_exact(typ, n, seed):
+    """EXACTLY what bench.py's step_device runs -- BASELINE configs[0] (cfg1: 100 x 1280x720, seed 1, weighted) and
+    configs[1] (cfg2: 500 x 1280x720, seed 2, multi-band), frames resident in HBM, ONE m2d_feed_batch call with the
+    library's default group size, collect_stats off (best-first order + alpha-bound culling for weighted; competitive-cell
+    culling + weights-first for multi-band) -- against the oracle fed frame by frame: every tile of every level and the
+    collapsed mosaic, byte for byte.  (Map2DCPU.cpp:324-329, MultiBandMap2DCPU.cpp:539-547)"""
+    import torch
+    seq = synth.Sequence(n, 1280, 720, seed=seed)
+    frames = seq.frames()
+    dev = torch.from_numpy(frames).cuda()
+    g = m2d.Map2D.create(typ, thread=False)
+    o = O.OracleMap2D.create(typ)
+    O.set_threads(os.cpu_count() or 1)
+    try:
         assert g.prepare(seq.plane, seq.camera, seq.prepare_poses) and o.prepare(seq.plane, seq.camera, seq.prepare_poses)
-        res = g.feed_batch(dev.data_ptr(), seq.n, seq.w * seq.h * 3, seq.w, seq.h, seq.w * 3, seq.poses, True)
-        for k in range(seq.n):
-            assert (res[k] == 0) == o.feed(seq.frame(k), seq.poses[k])
+        for rep in range(2):   # the bench resets and feeds again: the second pass runs on recycled pool tiles
+            g.reset()
+            res = g.feed_batch(dev.data_ptr(), n, 1280 * 720 * 3, 1280, 720, 1280 * 3, seq.poses, True)
+        exp = np.array([0 if o.feed(frames[k], seq.poses[k]) else 1 for k in range(n)])
+        assert np.array_equal(res, exp)
         g.sync()
-        compare_state(g, o, 3)
-        g.close()
-    seq = synth.Sequence(24, 1280, 720, seed=2, fpl=6, prepare_frames=6)
-    dev = torch.from_numpy(seq.frames()).cuda()
-    g = m2d.Map2D.create(3, thread=False, batch_frames=16)
-    o = O.OracleMap2D.create(3)
-    assert g.prepare(seq.plane, seq.camera, seq.prepare_poses) and o.prepare(seq.plane, seq.camera, seq.prepare_poses)
-    g.feed_batch(dev.data_ptr(), seq.n, seq.w * seq.h * 3, seq.w, seq.h, seq.w * 3, seq.poses, True)
-    for k in range(seq.n):
-        assert o.feed(seq.frame(k), seq.poses[k])
-    g.sync()
-    compare_state(g, o, 3)
+        assert compare_state(g, o, typ) > 150
+    finally:
+        O.set_threads(1)
     g.close()
+
+
+SWEEP = [  # (w, h, frames, tilt rad, scale, weight_type): >= 1e9 input px in total
+    (1280, 720, 300, 0.0, 1.0, 0), (1280, 720, 160, 0.45, 1.0, 1), (1920, 1080, 120, 0.3, 0.5, 0), (1920, 1080, 60, 0.1, 2.0, 0),
+    (4000, 3000, 24, 0.2, 1.0, 0), (4000, 3000, 12, 0.48, 0.7, 1)]
+
+
+@pytest.mark.parametrize("typ", [1, 3])
+def test_culling_never_changes_results(monkeypatch, typ):
+    """The shortcuts the benchmarked numbers rest on, against the same library with the shortcuts off, over > 1e9 input px
+    of randomly tilted (up to 28 deg), yawed, jittered frames at 720p / 1080p / 12 MP and map scales 0.5 - 2:
+      weighted   best-first order + alpha upper bounds (collect_stats=0)  ==  sequential, unculled (collect_stats=1)
+      multi-band competitive-cell culling (bounds.h) + weights-first     ==  M2D_WCULL=0  ==  dense pipeline (M2D_SPARSE=0)
+    Raw tile state (every level, weights included) and the grid must be identical."""
+    import torch
+    total = 0
+    for (w, h, n, tilt, scale, wt) in SWEEP:
+        seq = synth.Sequence(n, w, h, seed=31 + n, jitter=True)
+        rng = np.random.default_rng(n)
+        poses = seq.poses.copy()
+        for k in range(n):
+            q = synth._qmul(synth._qmul(synth._qaxis((0, 0, 1), rng.uniform(-3.1, 3.1)),
+                                        synth._qmul(synth._qaxis((0, 1, 0), rng.uniform(-tilt, tilt)), synth._qaxis((1, 0, 0), rng.uniform(-tilt, tilt)))),
+                            np.array([1.0, 0, 0, 0]))
+            poses[k, 3:] = q / np.linalg.norm(q)
+        tex = torch.from_numpy(seq.texture).cuda()
+        dev = torch.empty((n, h, w, 3), dtype=torch.uint8, device="cuda")
+        for k in range(n):   # the same crops Sequence.frame() makes, gathered on the GPU
+            r0, c0 = seq.frame_origin(k)
+            rows = torch.from_numpy((r0 - np.arange(h)) % tex.shape[0]).cuda()
+            cols = torch.from_numpy((c0 + np.arange(w)) % tex.shape[1]).cuda()
+            dev[k] = tex[rows[:, None], cols[None, :]]
+        if typ == 1:
+            variants = [({"collect_stats": 0}, {}), ({"collect_stats": 1}, {})]
+        else:
+            variants = [({}, {"M2D_WCULL": "1", "M2D_SPARSE": "1"}), ({}, {"M2D_WCULL": "0", "M2D_SPARSE": "1"}), ({}, {"M2D_WCULL": "1", "M2D_SPARSE": "0"})]
+        ref = None
+        for kw, env in variants:
+            for k_, v_ in env.items():
+                monkeypatch.setenv(k_, v_)
+            m = m2d.Map2D.create(typ, thread=False, scale=scale, weight_type=wt, **kw)
+            assert m.prepare(seq.plane, seq.camera, poses[:20])
+            res = m.feed_batch(dev.data_ptr(), n, w * h * 3, w, h, w * 3, poses, True)
+            m.sync()
+            xy, st = raw_state(m)
+            gr = m.grid()
+            if ref is None:
+                ref = (res, xy, st, gr)
+                assert (res == 0).sum() > n // 2
+            else:
+                assert np.array_equal(res, ref[0]) and np.array_equal(xy, ref[1]) and (gr["w"], gr["h"]) == (ref[3]["w"], ref[3]["h"])
+                same = torch.equal(st, ref[2])
+                assert same, "%dx%d tilt %.2f scale %.1f: %d tile bytes differ with %s %s" % (
+                    w, h, tilt, scale, int((st != ref[2]).sum()), kw, env)
+            m.close()
+            del m
+        total += int((ref[0] == 0).sum()) * w * h
+        del dev, ref
+        torch.cuda.empty_cache()
+    assert total >= 1_000_000_000, total
 
 
 def test_ties_keep_reference_order():

@@ -1,8 +1,11 @@
-"""Host-side proofs behind the weights-first multi-band pipeline (kernels.cu "WEIGHTS-FIRST variant"), on the CPU:
-  * the reach table (which cells of which Gaussian level a winner depends on) against a brute-force walk of the actual
-    pyrUp / pyrDown taps, borders included;
+"""Host-side proofs behind the weights-first multi-band pipeline (csrc/kernels_wf.cu), on the CPU:
+  * the reach tables (which cells of which Gaussian / weight level a winner / a competitive cell depends on) against a
+    brute-force walk of the actual pyrUp / pyrDown taps, borders included;
   * the FP32 weight-coordinate fast path of mbw_warp_kernel: wherever it does NOT flag a px as ambiguous, its rounded
-    source coordinate equals the exact FP64 one OpenCV computes."""
+    source coordinate equals the exact FP64 one OpenCV computes;
+  * the closed-form cell bounds the pipeline culls with (csrc/bounds.h, called through m2d_cell_weight_bounds -- the very
+    code the bounds kernel runs) against real weight pyramids built by the oracle;
+  * the order-free form of the reference's sequential `>=` rule."""
 import numpy as np
 import pytest
 
@@ -76,55 +79,8 @@ def fast_path(M, xs, ys, sw, sh):
     return rx, ry, amb
 
 
-def fma32(a, b, c):
-    """__fmaf_rn for float32 arrays: the product of two floats is exact in float64, one rounding to float32 at the end
-    (the intermediate float64 sum rounds first; a double rounding can differ from the true FMA by 1 ulp in ~1e-9 of cases,
-    far inside the 48-ulp band this test is about)."""
-    return (np.asarray(a, np.float64) * np.asarray(b, np.float64) + np.asarray(c, np.float64)).astype(np.float32)
-
-
-def lean_path(M, xs, ys, sw, sh):
-    """numpy restatement of the EXPERIMENTAL mbw_weights4_lean FP32 pass: explicit FMAs, one reciprocal per 4-px run carried
-    by Newton steps, rounding by the 1.5*2^23 trick."""
-    f = np.float32
-    mf = M.astype(np.float32)
-    xf, yf = xs.astype(np.float32), ys.astype(np.float32)
-    x4 = (np.floor(xs / 4) * 4).astype(np.float32)
-    jj = (xs - np.floor(xs / 4) * 4).astype(int)
-    den0, nx0, ny0 = fma32(mf[7], yf, mf[8]), fma32(mf[1], yf, mf[2]), fma32(mf[4], yf, mf[5])
-    wa, wb = fma32(mf[6], x4, den0), fma32(mf[6], x4 + f(3), den0)
-    wmin = np.minimum(wa, wb)
-    ok = wmin > f(1e-3)
-    newton = abs(mf[6]) * f(3) < f(1e-4) * wmin
-    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
-        r = f(1) / wa
-        r3 = r.copy()
-        for j in range(1, 4):
-            den = fma32(mf[6], x4 + f(j), den0)
-            step = np.where(newton, fma32(r3, fma32(-den, r3, f(1)), r3), f(1) / den).astype(np.float32)
-            r3 = step
-            r = np.where(jj >= j, step, r).astype(np.float32)     # the reciprocal this px ends up with
-        fx, fy = fma32(mf[0], xf, nx0) * r, fma32(mf[3], xf, ny0) * r
-        rmax = np.maximum(f(1) / wa, r3)
-        magx = fma32(abs(mf[0]), x4 + f(3), fma32(abs(mf[1]), yf, abs(mf[2]))) * rmax
-        magy = fma32(abs(mf[3]), x4 + f(3), fma32(abs(mf[4]), yf, abs(mf[5]))) * rmax
-        thr_x, thr_y = fma32(f(48) * f(5.97e-8), magx, f(1e-6)), fma32(f(48) * f(5.97e-8), magy, f(1e-6))
-        magic = f(12582912.0)
-        tx, ty = (fx + magic).astype(np.float32), (fy + magic).astype(np.float32)
-        rx, ry = tx - magic, ty - magic
-        ix = tx.view(np.int32) - 0x4B400000
-        iy = ty.view(np.int32) - 0x4B400000
-        sane = (abs(fx) < f(2097152)) & (abs(fy) < f(2097152))
-        slack_x, slack_y = f(4) * f(5.97e-8) * magx, f(4) * f(5.97e-8) * magy     # __fdividef vs IEEE division
-        amb = ~ok | (sane & ((f(0.5) - abs(fx - rx) < thr_x - slack_x) | (f(0.5) - abs(fy - ry) < thr_y - slack_y)))
-    assert np.array_equal(ix[sane & ok].astype(np.float32), rx[sane & ok]), "bits(t) - 0x4B400000 must be the rounded value"
-    far = ok & ~sane      # millions of px away: the kernel writes weight 0 without asking the exact path
-    return np.where(far, f(-1e9), rx), np.where(far, f(-1e9), ry), amb, far
-
-
-@pytest.mark.parametrize("variant", ["default", "lean"])
 @pytest.mark.parametrize("w,h,n,tilt", [(1280, 720, 120, False), (4000, 3000, 40, False), (1920, 1080, 60, True), (320, 180, 40, True)])
-def test_fp32_weight_coordinates_agree_with_fp64_when_not_ambiguous(w, h, n, tilt, variant):
+def test_fp32_weight_coordinates_agree_with_fp64_when_not_ambiguous(w, h, n, tilt):
     seq = synth.Sequence(n, w, h, seed=11, jitter=True)
     poses = seq.poses.copy()
     if tilt:   # strong roll/pitch (still accepted by the ray.down >= 0.4 test): large perspective terms
@@ -151,14 +107,8 @@ def test_fp32_weight_coordinates_agree_with_fp64_when_not_ambiguous(w, h, n, til
         W = 1.0 / (M[6] * xb + M[7] * ys + M[8] + M[6] * x1)
         ex = np.rint((M[0] * xb + M[1] * ys + M[2] + M[0] * x1) * W)
         ey = np.rint((M[3] * xb + M[4] * ys + M[5] + M[3] * x1) * W)
-        if variant == "lean":
-            rx, ry, amb, far = lean_path(M, xs, ys, w, h)
-            inside = (ex >= 0) & (ex < w) & (ey >= 0) & (ey < h)
-            assert not (far & inside).any(), "a px declared 'far outside' must really be outside the frame"
-            sure = ~amb & ~far
-        else:
-            rx, ry, amb = fast_path(M, xs, ys, w, h)
-            sure = ~amb
+        rx, ry, amb = fast_path(M, xs, ys, w, h)
+        sure = ~amb
         assert np.array_equal(rx[sure], ex[sure]) and np.array_equal(ry[sure], ey[sure]), "frame %d" % k
         checked += int(sure.sum())
         ambiguous += int(amb.sum())
@@ -166,71 +116,77 @@ def test_fp32_weight_coordinates_agree_with_fp64_when_not_ambiguous(w, h, n, til
     assert ambiguous < 0.25 * (checked + ambiguous), "the fast path must decide the great majority of px"
 
 
-def level_weight_upper_bound(mf, x0, y0, x1, y1, sw, sh, weight_type):
-    """Upper bound of a frame's level-l weight over a set of level-l px, given the level-0 rect [x0,x1] x [y0,y1]
-    (region px, inclusive) that contains the supports of those px.  FP32 throughout, as a kernel would evaluate it:
-    the image of the rect under the inverse homography is the convex hull of its 4 mapped corners (denominators
-    positive), its bounding box grown by 1 px covers every rounded sampling position, and the weight image decreases
-    with the distance to the frame centre — so the weight at the box's point nearest to the centre bounds them all.
-    PyrDown is a convex combination (borders reflect inwards), so coarser levels inherit the bound; (1 + 3e-5) covers
-    the float rounding of up to five filter passes.  A plan for round 2 (cull entries in the decide stage without
-    loading them); validated here against real weight pyramids."""
-    f = np.float32
-    xs = np.array([x0, x1, x0, x1], np.float32)
-    ys = np.array([y0, y0, y1, y1], np.float32)
-    den = mf[6] * xs + mf[7] * ys + mf[8]
-    if (den <= f(1e-3)).any():
-        return np.inf
-    sx, sy = (mf[0] * xs + mf[1] * ys + mf[2]) / den, (mf[3] * xs + mf[4] * ys + mf[5]) / den
-    bx0, bx1, by0, by1 = sx.min() - f(1), sx.max() + f(1), sy.min() - f(1), sy.max() + f(1)
-    if bx1 < f(-0.5) or bx0 > f(sw) - f(0.5) or by1 < f(-0.5) or by0 > f(sh) - f(0.5):
-        return 0.0   # the whole set samples outside the frame
-    xc, yc = f(sw // 2), f(sh // 2)
-    dx = max(f(0), bx0 - xc, xc - bx1)
-    dy = max(f(0), by0 - yc, yc - by1)
-    dis = f(1) - min(np.sqrt(dx * dx + dy * dy) / np.sqrt(xc * xc + yc * yc), f(1))
-    v = dis if weight_type == 0 else dis * dis
-    return float(max(v, f(1e-5)) * f(1 + 3e-5) + f(1e-7))
+@pytest.mark.parametrize("levels", [1, 2, 3, 4, 5, 6])
+def test_weight_reach_table_covers_every_tap(levels):
+    lo, hi = (t.astype(int) for t in m2d.weight_reach_table(levels))
+    tiles = 3
+    size = [tiles * (256 >> l) for l in range(levels)]
+    worst = np.zeros((6, 6, 2), int)
+    for m in range(levels):
+        for p in range(size[m]):                  # every px of weight level m that a competitive cell may contain
+            need = {m: {p}}
+            for k in range(m, 0, -1):             # pyrDown taps, BORDER_REFLECT_101
+                need[k - 1] = {reflect101(2 * u + d - 2, size[k - 1]) for u in need[k] for d in range(5)}
+            c = (p << m) >> 5
+            for k, pts in need.items():
+                assert lo[m][k] != 255
+                cells = [(q << k) >> 5 for q in pts]
+                assert min(cells) >= c - lo[m][k] and max(cells) <= c + hi[m][k], (levels, m, p, k)
+                worst[m][k] = np.maximum(worst[m][k], [c - min(cells), max(cells) - c])
+    for m in range(levels):
+        for k in range(6):
+            if k <= m:
+                assert (worst[m][k] == [lo[m][k], hi[m][k]]).all(), (levels, m, k, worst[m][k], lo[m][k], hi[m][k])
+            else:
+                assert lo[m][k] == 255 and hi[m][k] == 255
 
 
-@pytest.mark.parametrize("w,h,weight_type,tilt", [(320, 180, 0, False), (320, 180, 1, True), (1280, 720, 0, True)])
-def test_level_weight_upper_bound_is_conservative(w, h, weight_type, tilt):
-    seq = synth.Sequence(12, w, h, seed=17, jitter=True)
+def tilted_poses(seq, seed, yaw=3.0, tilt=0.4):
+    rng = np.random.default_rng(seed)
     poses = seq.poses.copy()
-    if tilt:
-        rng = np.random.default_rng(2)
-        for k in range(seq.n):
-            q = synth._qmul(synth._qmul(synth._qaxis((0, 0, 1), rng.uniform(-3, 3)),
-                                        synth._qmul(synth._qaxis((0, 1, 0), rng.uniform(-0.4, 0.4)), synth._qaxis((1, 0, 0), rng.uniform(-0.4, 0.4)))),
-                            np.array([1.0, 0, 0, 0]))
-            poses[k, 3:] = q / np.linalg.norm(q)
-    m = O.OracleMap2D.create(3, weight_type=weight_type)
+    for k in range(seq.n):
+        q = synth._qmul(synth._qmul(synth._qaxis((0, 0, 1), rng.uniform(-yaw, yaw)),
+                                    synth._qmul(synth._qaxis((0, 1, 0), rng.uniform(-tilt, tilt)), synth._qaxis((1, 0, 0), rng.uniform(-tilt, tilt)))),
+                        np.array([1.0, 0, 0, 0]))
+        poses[k, 3:] = q / np.linalg.norm(q)
+    return poses
+
+
+@pytest.mark.parametrize("w,h,weight_type,tilt,scale", [(320, 180, 0, False, 1.0), (320, 180, 1, True, 1.0), (1280, 720, 0, True, 1.0),
+                                                     (1280, 720, 0, False, 1.0), (640, 360, 1, False, 1.7), (640, 360, 0, True, 0.6)])
+def test_cell_weight_bounds_are_conservative(w, h, weight_type, tilt, scale):
+    """lo <= W_l(u) <= hi for EVERY px of EVERY cell of every level of real weight pyramids (oracle primitives: nearest
+    warp of the weight image, five f32 pyrDowns with the region's reflect-101 border), nadir / jittered / strongly tilted
+    frames, both weight types, map scales below and above 1.  Also: the bounds are tight enough to be useful."""
+    seq = synth.Sequence(12, w, h, seed=17, jitter=True)
+    poses = tilted_poses(seq, 2) if tilt else seq.poses
+    m = O.OracleMap2D.create(3, weight_type=weight_type, scale=scale)
     assert m.prepare(seq.plane, seq.camera, poses[:6])
     rects, hinv = m.compute_bounds(poses)
     wimg = O.weight_image_f32(w, h, weight_type)
-    rng = np.random.default_rng(3)
-    levels, checked, useful = 6, 0, 0
-    for k in range(0, seq.n, 3 if w > 1000 else 1):
+    levels, cells, tight, gap = 6, 0, 0, []
+    for k in range(0, seq.n, 4 if w > 1000 else 2):
         if rects[k, 2] <= rects[k, 0]:
             continue
-        nx, ny = (rects[k, 2] - rects[k, 0]) * 256, (rects[k, 3] - rects[k, 1]) * 256
-        pyr = [O.warp_f32_nearest(wimg, np.linalg.inv(hinv[k]), (nx, ny))]
+        nx, ny = int(rects[k, 2] - rects[k, 0]), int(rects[k, 3] - rects[k, 1])
+        pyr = [O.warp_f32_nearest(wimg, np.linalg.inv(hinv[k]), (nx * 256, ny * 256))]
         for _ in range(levels - 1):
             pyr.append(O.pyrdown_f32(pyr[-1]))
-        mf = hinv[k].reshape(9).astype(np.float32)
         for l in range(levels):
-            R = 0 if l == 0 else (2 << l) - 2          # level-0 half-support of a level-l px: 2^(l+1) - 2
-            H, Wd = pyr[l].shape
-            for _ in range(150):
-                cw, chh = min(64, Wd), min(max(2, 2 * (32 * 2 // max(min(64, Wd), 1))), H)   # a warp's px set: 64 x 2, or full rows
-                X0, Y0 = int(rng.integers(0, Wd - cw + 1)), int(rng.integers(0, H - chh + 1)) & ~1
-                actual = float(pyr[l][Y0:Y0 + chh, X0:X0 + cw].max())
-                ub = level_weight_upper_bound(mf, (X0 << l) - R, (Y0 << l) - R, ((X0 + cw - 1) << l) + R, ((Y0 + chh - 1) << l) + R,
-                                              w, h, weight_type)
-                assert ub >= actual, (k, l, X0, Y0, ub, actual)
-                checked += 1
-                useful += ub < 0.5
-    assert checked > 1000 and useful > 0.1 * checked, "the bound must also be tight enough to reject far-away frames"
+            B = max(32 >> l, 1)
+            blk = pyr[l].reshape(ny * 8, B, nx * 8, B)
+            mn, mx = blk.min(axis=(1, 3)), blk.max(axis=(1, 3))
+            for cy in range(ny * 8):
+                for cx in range(nx * 8):
+                    lo, hi = m2d.cell_weight_bounds(hinv[k], nx, ny, w, h, weight_type, l, cx, cy)
+                    assert lo <= mn[cy, cx] and mx[cy, cx] <= hi, (k, l, cx, cy, lo, float(mn[cy, cx]), float(mx[cy, cx]), hi)
+                    cells += 1
+                    if lo > 0:
+                        tight += 1
+                        gap.append(hi - lo)
+    print("cells %d tight %.3f mean gap %.3f" % (cells, tight / cells, float(np.mean(gap))))
+    assert cells > 5000 and tight > (0.04 if w * scale < 600 else 0.15) * cells, (cells, tight)   # a 320x180 frame is 10 x 5.6 cells in a 24 x 16-cell region
+    assert np.mean(gap) < (0.45 if w * scale < 600 else 0.1), "interior cells: a band of a few percent of the weight range (a cell's 32 px are a large part of a small frame)"
 
 
 def test_latest_maximum_rule_equals_the_sequential_scan():
