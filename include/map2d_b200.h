@@ -179,6 +179,25 @@ size_t m2d_tile_state_bytes(m2d_handle h);
 int m2d_tile_count(m2d_handle h);
 int m2d_export_tiles(m2d_handle h, int max_tiles, int* abs_xy, uint8_t* dst, int dst_on_device, int* n_out);
 int m2d_import_tiles(m2d_handle h, int n, const int* abs_xy, const uint8_t* src, int src_on_device);
+/* The same for the tiles inside rect_abs = {x0,y0,x1,y1} (absolute tile coordinates, half open; NULL = all).
+ * max_tiles == 0 only counts (*n_out), nothing is copied. */
+int m2d_export_tiles_rect(m2d_handle h, const int* rect_abs, int max_tiles, int* abs_xy, uint8_t* dst, int dst_on_device,
+                          int* n_out);
+/* Give the tiles inside rect_abs back to the pool (a shard discards the halo tiles it imported for a sharded save). */
+int m2d_drop_tiles_rect(m2d_handle h, const int* rect_abs, int* n_dropped);
+
+/* Sharded save (SURVEY.md §8e "collapse sharded"; MultiBandMap2DCPU.cpp:779-847 assembles and restores ONE mosaic over the
+ * bbox of all touched tiles).  m2d_tile_bbox: bbox of the tiles this handle holds, absolute tile coordinates (M2D_REJECTED if
+ * none).  m2d_get_image_rect: the collapse of save() over an explicit WINDOW of tiles -- tiles the handle does not hold
+ * count as the zeros the reference pastes for absent tiles -- of which only the CROP (inside the window) is written to `out`
+ * (host memory, or device memory if out_on_device), crop_w x crop_h x channels bytes; out == NULL only reports the size.
+ * A shard that owns tile rows [r0, r1) collapses window = global bbox columns x rows [r0 - k, r1 + k) (clipped to the
+ * global bbox; the k halo rows imported raw from its neighbours, k = ceil((2^levels - 2) / 256), 1 for <= 8 levels) and
+ * crops rows [r0, r1): the strips of all shards tile the reference's mosaic byte for byte, no shard ever holds the whole
+ * map, and only k tile rows per boundary cross the interconnect. */
+int m2d_tile_bbox(m2d_handle h, int bbox_abs[4]);
+int m2d_get_image_rect(m2d_handle h, uint8_t* out, int out_on_device, const int window_abs[4], const int crop_abs[4],
+                       int* w, int* h_px, int* channels);
 
 /* Display path without GL (Map2D::draw, Map2D.h:93): the reference marks tiles `Ischanged` in renderFrame and, on the GL
  * thread, re-blends each changed tile into a texture (MultiBandMap2DCPU.cpp:702-742 -> Ele::updateTexture -> Ele::blend

@@ -838,56 +838,98 @@ int orc_get_tile(orc_map* o, int tx, int ty, int level, void* out, float* weight
     }
     return M2D_OK;
 }
-// Map2DCPU::save (Map2DCPU.cpp:523-560) / MultiBandMap2DCPU::save (MultiBandMap2DCPU.cpp:779-841), in memory.
+// Map2DCPU::save (Map2DCPU.cpp:523-560) / MultiBandMap2DCPU::save (MultiBandMap2DCPU.cpp:779-841), in memory, over an explicit
+// window of tiles (grid coordinates; absent tiles are the zeros the reference pastes), of which `crop` is written to `out`.
+static int collapse_window(Map& m, uint8_t* out, const int win[4], const int crop[4], int* w, int* h, int* channels) {
+    const int x0 = win[0], y0 = win[1], x1 = win[2], y1 = win[3];
+    if (x1 <= x0 || y1 <= y0 || crop[0] < x0 || crop[1] < y0 || crop[2] > x1 || crop[3] > y1 || crop[2] <= crop[0] || crop[3] <= crop[1]) return M2D_ERR_ARG;
+    int tw = x1 - x0, th = y1 - y0;
+    int cn = m.type == M2D_TYPE_MULTIBAND ? 3 : 4;
+    const size_t CW = (size_t)(crop[2] - crop[0]) * M2D_ELE_PIXELS, CH = (size_t)(crop[3] - crop[1]) * M2D_ELE_PIXELS;
+    *w = (int)CW; *h = (int)CH; *channels = cn;
+    if (!out) return M2D_OK;
+    size_t W = (size_t)tw * M2D_ELE_PIXELS, H = (size_t)th * M2D_ELE_PIXELS;
+    auto tile_at = [&](int x, int y) -> const Tile* {
+        if (x < 0 || y < 0 || x >= m.w || y >= m.h) return nullptr;
+        return m.data[(size_t)x + (size_t)y * m.w].get();
+    };
+    std::vector<uint8_t> full(W * H * cn);
+    if (m.type != M2D_TYPE_MULTIBAND) {
+        memset(full.data(), 0, full.size());  // the reference leaves untouched tiles uninitialised; we define 0
+        for (int x = x0; x < x1; x++)
+            for (int y = y0; y < y1; y++) {
+                const Tile* e = tile_at(x, y);
+                if (!e || e->bgra.empty()) continue;
+                for (int ey = 0; ey < M2D_ELE_PIXELS; ey++)
+                    memcpy(full.data() + (((size_t)(y - y0) * M2D_ELE_PIXELS + ey) * W + (size_t)(x - x0) * M2D_ELE_PIXELS) * 4,
+                           &e->bgra[(size_t)ey * M2D_ELE_PIXELS * 4], (size_t)M2D_ELE_PIXELS * 4);
+            }
+    } else {
+        int L = m.band_num;
+        std::vector<Img16> pyr(L + 1);
+        std::vector<float> w0(W * H, 0.f);
+        for (int i = 0; i <= L; i++) {
+            int n = M2D_ELE_PIXELS >> i;
+            pyr[i].rows = th * n; pyr[i].cols = tw * n;
+            pyr[i].d.assign((size_t)pyr[i].rows * pyr[i].cols * 3, 0);
+        }
+        for (int x = x0; x < x1; x++)
+            for (int y = y0; y < y1; y++) {
+                const Tile* e = tile_at(x, y);
+                if (!e || e->lap.empty()) continue;
+                for (int i = 0; i <= L; i++) {
+                    int n = M2D_ELE_PIXELS >> i;
+                    for (int ey = 0; ey < n; ey++) {
+                        memcpy(&pyr[i].d[(((size_t)(y - y0) * n + ey) * pyr[i].cols + (size_t)(x - x0) * n) * 3], &e->lap[i][(size_t)ey * n * 3], (size_t)n * 3 * sizeof(int16_t));
+                        if (i == 0) memcpy(&w0[((size_t)(y - y0) * n + ey) * W + (size_t)(x - x0) * n], &e->wgt[0][(size_t)ey * n], (size_t)n * sizeof(float));
+                    }
+                }
+            }
+        restore_from_laplace_pyr(pyr);
+        uint8_t bg = sat_u8(m.cfg.background);
+        size_t npx = W * H;
+        for (size_t p = 0; p < npx; p++) {
+            if (w0[p] == 0) { full[3 * p] = full[3 * p + 1] = full[3 * p + 2] = bg; continue; }
+            full[3 * p] = sat_u8(pyr[0].d[3 * p]); full[3 * p + 1] = sat_u8(pyr[0].d[3 * p + 1]); full[3 * p + 2] = sat_u8(pyr[0].d[3 * p + 2]);
+        }
+    }
+    for (size_t r = 0; r < CH; r++)
+        memcpy(out + r * CW * cn, full.data() + (((size_t)(crop[1] - y0) * M2D_ELE_PIXELS + r) * W + (size_t)(crop[0] - x0) * M2D_ELE_PIXELS) * cn, CW * cn);
+    return M2D_OK;
+}
 int orc_get_image(orc_map* o, uint8_t* out, int* w, int* h, int* channels, int* tile_min_x, int* tile_min_y) {
     Map& m = o->m;
     if (!m.valid || m.w == 0 || m.h == 0) return M2D_REJECTED;
     int x0, y0, x1, y1;
     if (!m.tile_bbox(x0, y0, x1, y1)) return M2D_REJECTED;
-    int tw = x1 - x0, th = y1 - y0;
-    int cn = m.type == M2D_TYPE_MULTIBAND ? 3 : 4;
-    *w = tw * M2D_ELE_PIXELS; *h = th * M2D_ELE_PIXELS; *channels = cn; *tile_min_x = x0; *tile_min_y = y0;
-    if (!out) return M2D_OK;
-    size_t W = (size_t)*w;
-    if (m.type != M2D_TYPE_MULTIBAND) {
-        memset(out, 0, W * (size_t)*h * 4);  // the reference leaves untouched tiles uninitialised; we define 0
-        for (int x = x0; x < x1; x++)
-            for (int y = y0; y < y1; y++) {
-                const auto& e = m.data[(size_t)x + (size_t)y * m.w];
-                if (!e || e->bgra.empty()) continue;
-                for (int ey = 0; ey < M2D_ELE_PIXELS; ey++)
-                    memcpy(out + (((size_t)(y - y0) * M2D_ELE_PIXELS + ey) * W + (size_t)(x - x0) * M2D_ELE_PIXELS) * 4,
-                           &e->bgra[(size_t)ey * M2D_ELE_PIXELS * 4], (size_t)M2D_ELE_PIXELS * 4);
-            }
-        return M2D_OK;
-    }
-    int L = m.band_num;
-    std::vector<Img16> pyr(L + 1);
-    std::vector<float> w0(W * (size_t)*h, 0.f);
-    for (int i = 0; i <= L; i++) {
-        int n = M2D_ELE_PIXELS >> i;
-        pyr[i].rows = th * n; pyr[i].cols = tw * n;
-        pyr[i].d.assign((size_t)pyr[i].rows * pyr[i].cols * 3, 0);
-    }
-    for (int x = x0; x < x1; x++)
-        for (int y = y0; y < y1; y++) {
-            const auto& e = m.data[(size_t)x + (size_t)y * m.w];
-            if (!e || e->lap.empty()) continue;
-            for (int i = 0; i <= L; i++) {
-                int n = M2D_ELE_PIXELS >> i;
-                for (int ey = 0; ey < n; ey++) {
-                    memcpy(&pyr[i].d[(((size_t)(y - y0) * n + ey) * pyr[i].cols + (size_t)(x - x0) * n) * 3], &e->lap[i][(size_t)ey * n * 3], (size_t)n * 3 * sizeof(int16_t));
-                    if (i == 0) memcpy(&w0[((size_t)(y - y0) * n + ey) * W + (size_t)(x - x0) * n], &e->wgt[0][(size_t)ey * n], (size_t)n * sizeof(float));
-                }
-            }
+    *tile_min_x = x0; *tile_min_y = y0;
+    const int win[4] = {x0, y0, x1, y1};
+    return collapse_window(m, out, win, win, w, h, channels);
+}
+// stand-ins for m2d_tile_bbox / m2d_get_image_rect / m2d_export_tiles_rect / m2d_drop_tiles_rect (sharded save, host-logic tests)
+int orc_tile_bbox(orc_map* o, int* bbox_abs) {
+    Map& m = o->m;
+    int x0, y0, x1, y1;
+    if (!m.valid || !m.tile_bbox(x0, y0, x1, y1)) return M2D_REJECTED;
+    bbox_abs[0] = x0 + m.org_x; bbox_abs[1] = y0 + m.org_y; bbox_abs[2] = x1 + m.org_x; bbox_abs[3] = y1 + m.org_y;
+    return M2D_OK;
+}
+int orc_get_image_rect(orc_map* o, uint8_t* out, int, const int* window_abs, const int* crop_abs, int* w, int* h, int* channels) {
+    Map& m = o->m;
+    if (!m.valid) return M2D_ERR_STATE;
+    const int win[4] = {window_abs[0] - m.org_x, window_abs[1] - m.org_y, window_abs[2] - m.org_x, window_abs[3] - m.org_y};
+    const int crop[4] = {crop_abs[0] - m.org_x, crop_abs[1] - m.org_y, crop_abs[2] - m.org_x, crop_abs[3] - m.org_y};
+    return collapse_window(m, out, win, crop, w, h, channels);
+}
+int orc_drop_tiles_rect(orc_map* o, const int* rect_abs, int* n_dropped) {
+    Map& m = o->m;
+    int n = 0;
+    for (int y = std::max(rect_abs[1] - m.org_y, 0); y < std::min(rect_abs[3] - m.org_y, m.h); y++)
+        for (int x = std::max(rect_abs[0] - m.org_x, 0); x < std::min(rect_abs[2] - m.org_x, m.w); x++) {
+            auto& e = m.data[(size_t)y * m.w + x];
+            if (e) { e.reset(); n++; }
         }
-    restore_from_laplace_pyr(pyr);
-    uint8_t bg = sat_u8(m.cfg.background);
-    size_t npx = W * (size_t)*h;
-    for (size_t p = 0; p < npx; p++) {
-        if (w0[p] == 0) { out[3 * p] = out[3 * p + 1] = out[3 * p + 2] = bg; continue; }
-        out[3 * p] = sat_u8(pyr[0].d[3 * p]); out[3 * p + 1] = sat_u8(pyr[0].d[3 * p + 1]); out[3 * p + 2] = sat_u8(pyr[0].d[3 * p + 2]);
-    }
+    if (n_dropped) *n_dropped = n;
     return M2D_OK;
 }
 size_t orc_tile_bytes(orc_map* o) { return o->m.tile_bytes(); }
@@ -896,14 +938,24 @@ int orc_tile_count(orc_map* o) {
     for (auto& e : o->m.data) if (e && !(o->m.type == M2D_TYPE_MULTIBAND ? e->lap.empty() : e->bgra.empty())) n++;
     return n;
 }
+int orc_export_tiles_rect(orc_map* o, const int* rect_abs, int max_tiles, int* abs_xy, uint8_t* dst, int, int* n_out);
 int orc_export_tiles(orc_map* o, int max_tiles, int* abs_xy, uint8_t* dst, int, int* n_out) {
+    return orc_export_tiles_rect(o, nullptr, max_tiles, abs_xy, dst, 0, n_out);
+}
+int orc_export_tiles_rect(orc_map* o, const int* rect_abs, int max_tiles, int* abs_xy, uint8_t* dst, int, int* n_out) {
     Map& m = o->m;
     int n = 0;
     size_t tb = m.tile_bytes();
-    for (int y = 0; y < m.h; y++)
-        for (int x = 0; x < m.w; x++) {
+    int ry0 = 0, ry1 = m.h, rx0 = 0, rx1 = m.w;
+    if (rect_abs) {
+        rx0 = std::max(rect_abs[0] - m.org_x, 0); ry0 = std::max(rect_abs[1] - m.org_y, 0);
+        rx1 = std::min(rect_abs[2] - m.org_x, m.w); ry1 = std::min(rect_abs[3] - m.org_y, m.h);
+    }
+    for (int y = ry0; y < ry1; y++)
+        for (int x = rx0; x < rx1; x++) {
             const auto& e = m.data[(size_t)y * m.w + x];
             if (!e || (m.type == M2D_TYPE_MULTIBAND ? e->lap.empty() : e->bgra.empty())) continue;
+            if (max_tiles == 0) { n++; continue; }   // count only
             if (n >= max_tiles) return M2D_ERR_ARG;
             abs_xy[2 * n] = x + m.org_x; abs_xy[2 * n + 1] = y + m.org_y;
             uint8_t* d = dst + (size_t)n * tb;

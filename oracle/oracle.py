@@ -84,6 +84,10 @@ def lib():
         L.orc_tile_count.argtypes = [vp]
         L.orc_export_tiles.argtypes = [vp, C.c_int, ip, vp, C.c_int, ip]
         L.orc_import_tiles.argtypes = [vp, C.c_int, ip, vp, C.c_int]
+        L.orc_export_tiles_rect.argtypes = [vp, ip, C.c_int, ip, vp, C.c_int, ip]
+        L.orc_drop_tiles_rect.argtypes = [vp, ip, ip]
+        L.orc_tile_bbox.argtypes = [vp, ip]
+        L.orc_get_image_rect.argtypes = [vp, vp, C.c_int, ip, ip, ip, ip, ip]
         L.orc_compute_bounds.argtypes = [vp, C.c_int, dp, ip, dp]
         L.orc_set_threads.argtypes = [C.c_int]
         L.orc_set_threads.restype = None
@@ -287,6 +291,36 @@ class OracleMap2D:
         rc = lib().orc_export_tiles(self._h, max_tiles, xy.ctypes.data_as(C.POINTER(C.c_int)), dst_ptr, 0, C.byref(n))
         assert rc == 0
         return xy[:n.value].copy()
+
+    def export_tiles_rect(self, rect_abs, dst_ptr, max_tiles, on_device=False):
+        r = (C.c_int * 4)(*[int(v) for v in rect_abs])
+        xy = np.zeros((max(max_tiles, 1), 2), np.int32)
+        n = C.c_int()
+        rc = lib().orc_export_tiles_rect(self._h, r, max_tiles, xy.ctypes.data_as(C.POINTER(C.c_int)), dst_ptr, 0, C.byref(n))
+        assert rc == 0
+        return n.value if max_tiles == 0 else xy[:n.value].copy()
+
+    def drop_tiles_rect(self, rect_abs):
+        r = (C.c_int * 4)(*[int(v) for v in rect_abs])
+        n = C.c_int()
+        lib().orc_drop_tiles_rect(self._h, r, C.byref(n))
+        return n.value
+
+    def tile_bbox(self):
+        r = (C.c_int * 4)()
+        return tuple(r) if lib().orc_tile_bbox(self._h, r) == 0 else None
+
+    def get_image_rect(self, window_abs, crop_abs, out_ptr=None, on_device=False):
+        win = (C.c_int * 4)(*[int(v) for v in window_abs])
+        crop = (C.c_int * 4)(*[int(v) for v in crop_abs])
+        w, h, cn = C.c_int(), C.c_int(), C.c_int()
+        assert lib().orc_get_image_rect(self._h, None, 0, win, crop, C.byref(w), C.byref(h), C.byref(cn)) == 0
+        if out_ptr is not None:
+            assert lib().orc_get_image_rect(self._h, out_ptr, 0, win, crop, C.byref(w), C.byref(h), C.byref(cn)) == 0
+            return h.value, w.value, cn.value
+        out = np.empty((h.value, w.value, cn.value), np.uint8)
+        assert lib().orc_get_image_rect(self._h, out.ctypes.data, 0, win, crop, C.byref(w), C.byref(h), C.byref(cn)) == 0
+        return out
 
     def import_tiles(self, xy, src_ptr, on_device=False):
         xy = np.ascontiguousarray(xy, np.int32).reshape(-1, 2)

@@ -79,6 +79,8 @@ __global__ void __launch_bounds__(384) mbc_bounds_kernel(const __grid_constant__
     float* cmin = reinterpret_cast<float*>(T.state + lay.cmin_off) + l * 64 + cell;
     uint32_t* cm = p.cmask + (((size_t)blockIdx.x * p.levels + l) * 64 + cell) * p.mask_words;
     float best_lo = -INFINITY;
+    constexpr int kCache = 48;     // upper bounds of the first entries are kept (thread-local memory) instead of recomputed
+    float hic[kCache];
     if (p.cull) {
         if (!T.fresh) best_lo = *cmin;
         for (int i = 0; i < T.count; i++) {
@@ -87,6 +89,7 @@ __global__ void __launch_bounds__(384) mbc_bounds_kernel(const __grid_constant__
             float lo, hi;
             cell_weight_bounds(J.hinvf, J.nx, J.ny, p.sw, p.sh, p.weight_type, l, E.rtx * 8 + ccx, E.rty * 8 + ccy, &lo, &hi);
             best_lo = fmaxf(best_lo, lo);
+            if (i < kCache) hic[i] = hi;
         }
     }
     uint32_t any = 0u;
@@ -99,7 +102,8 @@ __global__ void __launch_bounds__(384) mbc_bounds_kernel(const __grid_constant__
             bool in = true;
             if (p.cull) {
                 float lo, hi;
-                cell_weight_bounds(J.hinvf, J.nx, J.ny, p.sw, p.sh, p.weight_type, l, E.rtx * 8 + ccx, E.rty * 8 + ccy, &lo, &hi);
+                if (i < kCache) hi = hic[i];
+                else cell_weight_bounds(J.hinvf, J.nx, J.ny, p.sw, p.sh, p.weight_type, l, E.rtx * 8 + ccx, E.rty * 8 + ccy, &lo, &hi);
                 in = hi >= best_lo;
             }
             if (in) {
@@ -119,50 +123,109 @@ cudaError_t launch_mbc_bounds(const GroupParams& p, const TileLayout& lay, cudaS
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// 1./3. propagate: dst[k] = cells within reach of a src flag.  A flag of level m in cell c' makes level k necessary in
-// cells [c' - lo[m][k], c' + hi[m][k]] (both axes); the host derives the tables by interval arithmetic over the exact
-// taps (make_reach_table / make_weight_reach_table).  One thread per (frame, level, cell); needed cells are appended to
-// the level's work list (warp-aggregated atomics).
+// 1./3. propagate: level k is needed in the cells within reach of a src flag.  A flag of level m in cell c' makes level k
+// necessary in cells [c' - lo[m][k], c' + hi[m][k]] (both axes); the host derives the tables by interval arithmetic over
+// the exact taps (make_reach_table / make_weight_reach_table).  One CTA per frame: the frame's src flags of all levels
+// are packed into row bit masks in shared memory, a (level, row, 32-cell word) of the result is then a handful of
+// shifts and ORs (a 2-D dilation), and its set bits are appended to the level's work list -- one global atomic per
+// (CTA, level), items of a frame contiguous and in row-major order.
 // ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t shifted_word(const uint32_t* row, int w, int ww, int d) {   // bit x of the result = bit (32 w + x + d) of the row
+    const uint32_t cur = row[w];
+    if (d == 0) return cur;
+    if (d > 0) return (cur >> d) | ((w + 1 < ww ? row[w + 1] : 0u) << (32 - d));
+    return (cur << (-d)) | ((w > 0 ? row[w - 1] : 0u) >> (32 + d));
+}
+
 __global__ void __launch_bounds__(256) mbx_propagate_kernel(const __grid_constant__ GroupParams p, int image) {
-    const int f = blockIdx.y;
+    extern __shared__ uint32_t sbits[];   // [L][ch][ww]
+    __shared__ unsigned s_count[6], s_base[6];
+    const int f = blockIdx.x;
     const FrameJob& J = p.jobs[f];
-    const int cw = J.wnx * 8, ch = J.wny * 8, nc = cw * ch, L = p.levels;   // nc is a multiple of 64: a warp never straddles levels
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    const bool live = i < L * nc;
-    const int k = live ? i / nc : 0, c = live ? i - k * nc : 0, cy = c / cw, cx = c - cy * cw;
+    const int cw = J.wnx * 8, ch = J.wny * 8, ww = (cw + 31) >> 5, L = p.levels;
     const uint8_t* src = image ? p.win : p.comp;
-    uint8_t* dst = image ? p.need : p.needw;
-    bool v = false;
-    if (live) {
-        for (int m = 0; m < L && !v; m++) {
-            const int rl = image ? p.reach_lo[m][k] : p.wreach_lo[m][k], rh = image ? p.reach_hi[m][k] : p.wreach_hi[m][k];
-            if (rl == 0xFF) continue;
-            const uint8_t* w = src + cell_base(p, f, m);   // a frame's flags are a few KB: L1/L2 resident
-            // c is required by a flag in c' iff c' - rl <= c <= c' + rh  <=>  c - rh <= c' <= c + rl
-            const int y0 = max(cy - rh, 0), y1 = min(cy + rl, ch - 1), x0 = max(cx - rh, 0), x1 = min(cx + rl, cw - 1);
-            for (int y = y0; y <= y1 && !v; y++)
-                for (int x = x0; x <= x1; x++) v |= w[y * cw + x] != 0;
+    if (threadIdx.x < 6) s_count[threadIdx.x] = 0;
+    const int nwords = L * ch * ww;
+    for (int i = threadIdx.x; i < nwords; i += 256) {
+        const int w = i % ww, y = (i / ww) % ch, m = i / (ww * ch);
+        const uint8_t* q = src + cell_base(p, f, m) + (size_t)y * cw + w * 32;   // cell_base and cw are multiples of 8
+        const int nb = min(32, cw - w * 32);
+        uint32_t bits = 0u;
+        for (int b8 = 0; b8 < nb; b8 += 8) {
+            const uint2 v = *reinterpret_cast<const uint2*>(q + b8);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                bits |= (((v.x >> (8 * j)) & 0xFFu) ? 1u : 0u) << (b8 + j);
+                bits |= (((v.y >> (8 * j)) & 0xFFu) ? 1u : 0u) << (b8 + 4 + j);
+            }
         }
-        dst[cell_base(p, f, k) + c] = v ? 1 : 0;
+        sbits[i] = bits;
     }
-    const unsigned ballot = __ballot_sync(0xffffffffu, v);
-    if (ballot) {
-        const int lane = threadIdx.x & 31, leader = __ffs(ballot) - 1;
-        const int kk = __shfl_sync(0xffffffffu, k, leader);
-        unsigned base = 0;
-        if (lane == leader) base = atomicAdd(p.list_count + image * 6 + kk, (unsigned)__popc(ballot));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (v) p.lists[((size_t)image * L + k) * p.list_cap + base + __popc(ballot & ((1u << lane) - 1u))] = ((uint32_t)f << 16) | (uint32_t)c;
-    }
-    if (p.need_stats && ballot && (threadIdx.x & 31) == __ffs(ballot) - 1) {   // px of level k the frames have to compute (a cell is (32 >> k)^2 px)
-        const unsigned long long side = (unsigned long long)max(32 >> k, 1);
-        atomicAdd(p.need_stats + (image ? 20 : 26) + k, side * side * (unsigned long long)__popc(ballot));
+    __syncthreads();
+    // pass A: result words + their slot inside the CTA's share of the list
+    constexpr int kMaxPerThread = 8;      // ceil(6 levels * 256 rows * 8 words / 256 threads) would be 48; regions that large take more rounds
+    for (int i0 = 0; i0 < nwords; i0 += 256 * kMaxPerThread) {
+        uint32_t acc[kMaxPerThread];
+        unsigned off[kMaxPerThread];
+#pragma unroll
+        for (int r = 0; r < kMaxPerThread; r++) {
+            const int i = i0 + r * 256 + threadIdx.x;
+            acc[r] = 0u; off[r] = 0u;
+            if (i >= nwords) continue;
+            const int w = i % ww, y = (i / ww) % ch, k = i / (ww * ch);
+            uint32_t a = 0u;
+            for (int m = 0; m < L; m++) {
+                const int rl = image ? p.reach_lo[m][k] : p.wreach_lo[m][k], rh = image ? p.reach_hi[m][k] : p.wreach_hi[m][k];
+                if (rl == 0xFF) continue;
+                // cell c is required by a flag in c' iff c' - rl <= c <= c' + rh  <=>  c - rh <= c' <= c + rl
+                const int y0 = max(y - rh, 0), y1 = min(y + rl, ch - 1);
+                for (int yy = y0; yy <= y1; yy++) {
+                    const uint32_t* row = sbits + ((size_t)m * ch + yy) * ww;
+                    for (int d = -rh; d <= rl; d++) a |= shifted_word(row, w, ww, d);
+                }
+            }
+            const int nb = min(32, cw - w * 32);
+            if (nb < 32) a &= (1u << nb) - 1u;
+            acc[r] = a;
+            if (a) off[r] = atomicAdd(&s_count[k], (unsigned)__popc(a));
+        }
+        __syncthreads();
+        if (threadIdx.x < L && s_count[threadIdx.x]) {
+            s_base[threadIdx.x] = atomicAdd(p.list_count + image * 6 + threadIdx.x, s_count[threadIdx.x]);
+            if (p.need_stats) {   // px of level k the frames have to compute (a cell is (32 >> k)^2 px)
+                const unsigned long long side = (unsigned long long)max(32 >> threadIdx.x, 1);
+                atomicAdd(p.need_stats + (image ? 20 : 26) + threadIdx.x, side * side * (unsigned long long)s_count[threadIdx.x]);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < kMaxPerThread; r++) {
+            uint32_t a = acc[r];
+            if (!a) continue;
+            const int i = i0 + r * 256 + threadIdx.x;
+            const int w = i % ww, y = (i / ww) % ch, k = i / (ww * ch);
+            uint32_t* dst = p.lists + ((size_t)image * L + k) * p.list_cap + s_base[k] + off[r];
+            const uint32_t item0 = ((uint32_t)f << 16) | (uint32_t)(y * cw + w * 32);
+            while (a) {
+                const int b = __ffs(a) - 1;
+                a &= a - 1;
+                *dst++ = item0 + (uint32_t)b;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < 6) s_count[threadIdx.x] = 0;
+        __syncthreads();
     }
 }
 cudaError_t launch_mbx_propagate(const GroupParams& p, int image, cudaStream_t stream) {
-    dim3 g((p.levels * p.cells_max + 255) / 256, p.n_frames);
-    mbx_propagate_kernel<<<g, 256, 0, stream>>>(p, image);
+    const int ww = (p.max_wnx * 8 + 31) / 32;
+    const size_t smem = (size_t)p.levels * (p.max_wny * 8) * ww * sizeof(uint32_t);
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;   // a frame region beyond ~250 x 250 tiles
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(mbx_propagate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    mbx_propagate_kernel<<<p.n_frames, 256, smem, stream>>>(p, image);
     return cudaGetLastError();
 }
 

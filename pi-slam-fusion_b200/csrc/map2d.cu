@@ -184,6 +184,7 @@ struct m2d_map {
     bool owns(int tx, int ty) const;
     bool tile_bbox(int& x0, int& y0, int& x1, int& y1) const;
     int get_image(uint8_t* out, int* w, int* h, int* channels, int* tmx, int* tmy);
+    int collapse_window(uint8_t* out, bool out_on_device, const int win[4], const int crop[4], int* w, int* h, int* channels);
     int queue_size();
     int sync();
     int reset();
@@ -816,18 +817,39 @@ int m2d_map::get_image(uint8_t* out, int* w, int* h, int* channels, int* tmx, in
     if (!valid || g.w == 0 || g.h == 0) return M2D_REJECTED;
     int x0, y0, x1, y1;
     if (!tile_bbox(x0, y0, x1, y1)) return M2D_REJECTED;
+    *tmx = x0; *tmy = y0;
+    const int win[4] = {x0, y0, x1, y1};
+    return collapse_window(out, false, win, win, w, h, channels);
+}
+
+// The collapse of save() over an explicit WINDOW of tiles (grid coordinates; tiles the table does not hold count as the
+// zeros the reference pastes for absent tiles), of which the CROP rows/columns are written to `out` (host or device).
+// The whole-map save is window = crop = bbox of the touched tiles.  A sharded save collapses, on every shard, the global
+// bbox's columns x (its own tile rows + halo rows) and crops its own rows: a px of restored level l-1 depends on
+// restored level l within 1 coarse px, so what a window edge that is NOT the mosaic's edge gets wrong reaches
+// 2^levels - 2 level-0 px into the window (62 px for 6 levels) -- one halo tile row keeps the crop exact.
+int m2d_map::collapse_window(uint8_t* out, bool out_on_device, const int win[4], const int crop[4], int* w, int* h, int* channels) {
+    if (!valid) return M2D_REJECTED;
+    const int x0 = win[0], y0 = win[1], x1 = win[2], y1 = win[3];
+    if (x1 <= x0 || y1 <= y0 || crop[0] < x0 || crop[1] < y0 || crop[2] > x1 || crop[3] > y1 || crop[2] <= crop[0] || crop[3] <= crop[1]) return M2D_ERR_ARG;
     int tw = x1 - x0, th = y1 - y0;
     int cn = (type == M2D_TYPE_MULTIBAND) ? 3 : 4;
-    *w = tw * kEle; *h = th * kEle; *channels = cn; *tmx = x0; *tmy = y0;
+    const size_t CW = (size_t)(crop[2] - crop[0]) * kEle, CH = (size_t)(crop[3] - crop[1]) * kEle;
+    *w = (int)CW; *h = (int)CH; *channels = cn;
     if (!out) return M2D_OK;
     CU(cudaSetDevice(cfg.device));
-    size_t W = (size_t)*w, H = (size_t)*h;
+    size_t W = (size_t)tw * kEle, H = (size_t)th * kEle;
+    const cudaMemcpyKind kind = out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    const bool full = crop[0] == x0 && crop[1] == y0 && crop[2] == x1 && crop[3] == y1;
+    auto tile_at = [&](int x, int y) -> const uint8_t* {
+        return (x < 0 || y < 0 || x >= g.w || y >= g.h) ? nullptr : table[(size_t)y * g.w + x];
+    };
+    std::vector<PasteItem> items;
+    for (int y = y0; y < y1; y++)
+        for (int x = x0; x < x1; x++)
+            if (const uint8_t* t = tile_at(x, y)) items.push_back(PasteItem{t, x - x0, y - y0});
     if (type != M2D_TYPE_MULTIBAND) {
-        // assemble the BGRA mosaic in HBM (one paste launch), then ONE device->host copy
-        std::vector<PasteItem> items;
-        for (int y = y0; y < y1; y++)
-            for (int x = x0; x < x1; x++)
-                if (const uint8_t* t = table[(size_t)y * g.w + x]) items.push_back(PasteItem{t, x - x0, y - y0});
+        // assemble the BGRA mosaic in HBM (one paste launch), then ONE copy out
         size_t off_items = (W * H * 4 + 255) & ~(size_t)255;
         CU(cudaStreamSynchronize(stream));
         { int rc = grow((void**)&d_collapse, &collapse_cap, off_items + items.size() * sizeof(PasteItem) + 256, false); if (rc != M2D_OK) return rc; }
@@ -835,16 +857,13 @@ int m2d_map::get_image(uint8_t* out, int* w, int* h, int* channels, int* tmx, in
         CU(cudaMemsetAsync(d_collapse, 0, W * H * 4, stream));  // untouched tiles: the reference leaves them undefined, we define 0
         CU(cudaMemcpyAsync(d_items, items.data(), items.size() * sizeof(PasteItem), cudaMemcpyHostToDevice, stream));
         LAUNCHK(M2D_K_COLLAPSE, launch_bgra_paste(d_items, (int)items.size(), reinterpret_cast<uint32_t*>(d_collapse), (int)W, stream));
-        CU(cudaMemcpyAsync(out, d_collapse, W * H * 4, cudaMemcpyDeviceToHost, stream));
+        if (full) CU(cudaMemcpyAsync(out, d_collapse, W * H * 4, kind, stream));
+        else CU(cudaMemcpy2DAsync(out, CW * 4, d_collapse + ((size_t)(crop[1] - y0) * kEle * W + (size_t)(crop[0] - x0) * kEle) * 4, W * 4, CW * 4, CH, kind, stream));
         CU(cudaStreamSynchronize(stream));
         return M2D_OK;
     }
     // multi-band: collapse on the GPU.  Buffers are cached in the handle (grow-only): cudaMalloc/cudaFree of ~1 GB
     // per call costs far more than the collapse itself.
-    std::vector<PasteItem> items;
-    for (int y = y0; y < y1; y++)
-        for (int x = x0; x < x1; x++)
-            if (const uint8_t* t = table[(size_t)y * g.w + x]) items.push_back(PasteItem{t, x - x0, y - y0});
     MosaicSet ms{};
     size_t off = 0, offs[M2D_MAX_LEVELS][3];
     for (int l = 0; l < levels; l++) {
@@ -869,7 +888,8 @@ int m2d_map::get_image(uint8_t* out, int* w, int* h, int* channels, int* tmx, in
     LAUNCHK(M2D_K_COLLAPSE, launch_mosaic_paste(d_items, (int)items.size(), lay, ms, stream));
     for (int l = levels - 1; l > 0; l--) LAUNCHK(M2D_K_COLLAPSE, launch_mosaic_upadd(ms.lv[l], ms.lv[l - 1], stream));
     LAUNCHK(M2D_K_COLLAPSE, launch_mosaic_final(ms.lv[0], ms.w0, cfg.background, d_out, stream));
-    CU(cudaMemcpyAsync(out, d_out, W * H * 3, cudaMemcpyDeviceToHost, stream));
+    if (full) CU(cudaMemcpyAsync(out, d_out, W * H * 3, kind, stream));
+    else CU(cudaMemcpy2DAsync(out, CW * 3, d_out + ((size_t)(crop[1] - y0) * kEle * W + (size_t)(crop[0] - x0) * kEle) * 3, W * 3, CW * 3, CH, kind, stream));
     CU(cudaStreamSynchronize(stream));
     return M2D_OK;
 }
@@ -1290,6 +1310,43 @@ int m2d_get_image(m2d_handle h, uint8_t* out, int* w, int* hpx, int* channels, i
     return h->get_image(out, w, hpx, channels, tmx, tmy);
 }
 
+int m2d_tile_bbox(m2d_handle h, int* bbox_abs) {
+    API_LOCK(h);
+    if (!h || !bbox_abs) return M2D_ERR_ARG;
+    if (!h->valid) return M2D_ERR_STATE;
+    int x0, y0, x1, y1;
+    if (!h->tile_bbox(x0, y0, x1, y1)) return M2D_REJECTED;
+    bbox_abs[0] = x0 + h->org_x; bbox_abs[1] = y0 + h->org_y; bbox_abs[2] = x1 + h->org_x; bbox_abs[3] = y1 + h->org_y;
+    return M2D_OK;
+}
+
+int m2d_get_image_rect(m2d_handle h, uint8_t* out, int out_on_device, const int* window_abs, const int* crop_abs, int* w, int* hpx,
+                       int* channels) {
+    API_LOCK(h);
+    if (!h || !window_abs || !crop_abs || !w || !hpx || !channels) return M2D_ERR_ARG;
+    if (!h->valid) return M2D_ERR_STATE;
+    const int ox = h->org_x, oy = h->org_y;
+    const int win[4] = {window_abs[0] - ox, window_abs[1] - oy, window_abs[2] - ox, window_abs[3] - oy};
+    const int crop[4] = {crop_abs[0] - ox, crop_abs[1] - oy, crop_abs[2] - ox, crop_abs[3] - oy};
+    return h->collapse_window(out, out_on_device != 0, win, crop, w, hpx, channels);
+}
+
+int m2d_drop_tiles_rect(m2d_handle h, const int* rect_abs, int* n_dropped) {
+    API_LOCK(h);
+    if (!h || !rect_abs) return M2D_ERR_ARG;
+    m2d_map& m = *h;
+    if (!m.valid) return M2D_ERR_STATE;
+    if (cudaSetDevice(m.cfg.device) != cudaSuccess || cudaStreamSynchronize(m.stream) != cudaSuccess) return M2D_ERR_CUDA;
+    int n = 0;
+    for (int y = std::max(rect_abs[1] - m.org_y, 0); y < std::min(rect_abs[3] - m.org_y, m.g.h); y++)
+        for (int x = std::max(rect_abs[0] - m.org_x, 0); x < std::min(rect_abs[2] - m.org_x, m.g.w); x++) {
+            uint8_t*& t = m.table[(size_t)y * m.g.w + x];
+            if (t) { m.free_tiles.push_back(t); t = nullptr; m.tiles_in_use--; n++; }
+        }
+    if (n_dropped) *n_dropped = n;
+    return M2D_OK;
+}
+
 int m2d_save(m2d_handle h, const char* filename) {
     API_LOCK(h);
     if (!h || !filename) return M2D_ERR_ARG;
@@ -1314,8 +1371,12 @@ size_t m2d_tile_state_bytes(m2d_handle h) {
 int m2d_tile_count(m2d_handle h) { API_LOCK(h); return h ? (int)h->tiles_in_use : 0; }
 
 int m2d_export_tiles(m2d_handle h, int max_tiles, int* abs_xy, uint8_t* dst, int dst_on_device, int* n_out) {
+    return m2d_export_tiles_rect(h, nullptr, max_tiles, abs_xy, dst, dst_on_device, n_out);
+}
+
+int m2d_export_tiles_rect(m2d_handle h, const int* rect_abs, int max_tiles, int* abs_xy, uint8_t* dst, int dst_on_device, int* n_out) {
     API_LOCK(h);
-    if (!h || !abs_xy || !dst || !n_out) return M2D_ERR_ARG;
+    if (!h || !abs_xy || !n_out || (!dst && max_tiles > 0)) return M2D_ERR_ARG;
     m2d_map& m = *h;
     std::string& err = m.err;
     uint64_t& launches = m.launches;
@@ -1325,17 +1386,22 @@ int m2d_export_tiles(m2d_handle h, int max_tiles, int* abs_xy, uint8_t* dst, int
     if (!m.valid) return M2D_ERR_STATE;
     CU(cudaSetDevice(m.cfg.device));
     std::vector<uint8_t*> ptrs;
-    for (int y = 0; y < m.g.h; y++)
-        for (int x = 0; x < m.g.w; x++) {
+    int ry0 = 0, ry1 = m.g.h, rx0 = 0, rx1 = m.g.w;
+    if (rect_abs) {
+        rx0 = std::max(rect_abs[0] - m.org_x, 0); ry0 = std::max(rect_abs[1] - m.org_y, 0);
+        rx1 = std::min(rect_abs[2] - m.org_x, m.g.w); ry1 = std::min(rect_abs[3] - m.org_y, m.g.h);
+    }
+    for (int y = ry0; y < ry1; y++)
+        for (int x = rx0; x < rx1; x++) {
             uint8_t* t = m.table[(size_t)y * m.g.w + x];
             if (!t) continue;
-            if ((int)ptrs.size() >= max_tiles) return M2D_ERR_ARG;
+            if ((int)ptrs.size() >= max_tiles) { if (max_tiles == 0) { ptrs.push_back(t); continue; } return M2D_ERR_ARG; }
             abs_xy[2 * ptrs.size()] = x + m.org_x; abs_xy[2 * ptrs.size() + 1] = y + m.org_y;
             ptrs.push_back(t);
         }
     int n = (int)ptrs.size();
     *n_out = n;
-    if (n == 0) return M2D_OK;
+    if (n == 0 || max_tiles == 0) return M2D_OK;   // max_tiles == 0: count only
     if (dst_on_device && (m.tile_bytes % 16) == 0 && (reinterpret_cast<uintptr_t>(dst) % 16) == 0) {
         // one gather kernel instead of n small copies
         CU(cudaStreamSynchronize(stream));

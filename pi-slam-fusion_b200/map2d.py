@@ -47,7 +47,7 @@ class Stats(C.Structure):
 EXPORTS = ["m2d_config_default", "m2d_create", "m2d_destroy", "m2d_prepare", "m2d_feed", "m2d_feed_device",
            "m2d_feed_batch", "m2d_feed_poses", "m2d_plan_rects", "m2d_set_shard", "m2d_sync", "m2d_queue_size", "m2d_set_stream", "m2d_reset", "m2d_get_grid",
            "m2d_last_rect", "m2d_get_tile", "m2d_get_image", "m2d_save", "m2d_tile_bytes", "m2d_tile_state_bytes", "m2d_tile_count",
-           "m2d_export_tiles", "m2d_import_tiles", "m2d_poll_changed", "m2d_get_tile_image", "m2d_save_state", "m2d_load_state", "m2d_get_stats", "m2d_last_error",
+           "m2d_export_tiles", "m2d_import_tiles", "m2d_export_tiles_rect", "m2d_drop_tiles_rect", "m2d_tile_bbox", "m2d_get_image_rect", "m2d_poll_changed", "m2d_get_tile_image", "m2d_save_state", "m2d_load_state", "m2d_get_stats", "m2d_last_error",
            "m2d_launch_count", "m2d_profile", "m2d_get_kernel_times", "m2d_alloc_host", "m2d_free_host", "m2d_compute_bounds",
            "m2d_tile_gps_corners", "m2d_reach_table", "m2d_weight_reach_table", "m2d_cell_weight_bounds", "m2d_ingest_open", "m2d_ingest_open_seeded", "m2d_ingest_abort", "m2d_ingest_push", "m2d_ingest_pause", "m2d_ingest_drain", "m2d_ingest_close", "m2d_ingest_stats"]
 
@@ -106,6 +106,10 @@ def lib():
     L.m2d_tile_count.argtypes = [vp]
     L.m2d_export_tiles.argtypes = [vp, C.c_int, ip, vp, C.c_int, ip]
     L.m2d_import_tiles.argtypes = [vp, C.c_int, ip, vp, C.c_int]
+    L.m2d_export_tiles_rect.argtypes = [vp, ip, C.c_int, ip, vp, C.c_int, ip]
+    L.m2d_drop_tiles_rect.argtypes = [vp, ip, ip]
+    L.m2d_tile_bbox.argtypes = [vp, ip]
+    L.m2d_get_image_rect.argtypes = [vp, vp, C.c_int, ip, ip, ip, ip, ip]
     L.m2d_poll_changed.argtypes = [vp, C.c_int, ip, ip]
     L.m2d_get_tile_image.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, ip]
     L.m2d_save_state.argtypes = [vp, C.c_char_p]
@@ -434,6 +438,41 @@ class Map2D:
         n = C.c_int()
         self._check(lib().m2d_export_tiles(self._h, max_tiles, xy.ctypes.data_as(C.POINTER(C.c_int)), dst_ptr, int(on_device), C.byref(n)))
         return xy[:n.value].copy()
+
+    def export_tiles_rect(self, rect_abs, dst_ptr, max_tiles, on_device):
+        """export_tiles for the tiles inside rect_abs = (x0, y0, x1, y1), absolute tile coordinates; max_tiles = 0 counts only
+        (returns the count)."""
+        r = (C.c_int * 4)(*[int(v) for v in rect_abs])
+        xy = np.zeros((max(max_tiles, 1), 2), np.int32)
+        n = C.c_int()
+        self._check(lib().m2d_export_tiles_rect(self._h, r, max_tiles, xy.ctypes.data_as(C.POINTER(C.c_int)), dst_ptr, int(on_device), C.byref(n)))
+        return n.value if max_tiles == 0 else xy[:n.value].copy()
+
+    def drop_tiles_rect(self, rect_abs):
+        r = (C.c_int * 4)(*[int(v) for v in rect_abs])
+        n = C.c_int()
+        self._check(lib().m2d_drop_tiles_rect(self._h, r, C.byref(n)))
+        return n.value
+
+    def tile_bbox(self):
+        """(x0, y0, x1, y1) of the tiles this handle holds, absolute tile coordinates; None if it holds none."""
+        r = (C.c_int * 4)()
+        rc = lib().m2d_tile_bbox(self._h, r)
+        return tuple(r) if self._check(rc) else None
+
+    def get_image_rect(self, window_abs, crop_abs, out_ptr=None, on_device=False):
+        """The collapse of save() over an explicit window of tiles, cropped (m2d_get_image_rect).  Without out_ptr: a
+        new numpy array [h, w, channels]; with out_ptr (host or device memory): (h, w, channels)."""
+        win = (C.c_int * 4)(*[int(v) for v in window_abs])
+        crop = (C.c_int * 4)(*[int(v) for v in crop_abs])
+        w, h, cn = C.c_int(), C.c_int(), C.c_int()
+        self._check(lib().m2d_get_image_rect(self._h, None, 0, win, crop, C.byref(w), C.byref(h), C.byref(cn)))
+        if out_ptr is not None:
+            self._check(lib().m2d_get_image_rect(self._h, out_ptr, int(on_device), win, crop, C.byref(w), C.byref(h), C.byref(cn)))
+            return h.value, w.value, cn.value
+        out = np.empty((h.value, w.value, cn.value), np.uint8)
+        self._check(lib().m2d_get_image_rect(self._h, out.ctypes.data, 0, win, crop, C.byref(w), C.byref(h), C.byref(cn)))
+        return out
 
     def import_tiles(self, xy, src_ptr, on_device):
         xy = np.ascontiguousarray(xy, np.int32).reshape(-1, 2)

@@ -286,6 +286,123 @@ class ShardedMap2D:
         self.map.sync()
         return res
 
+    # ---- sharded save: every rank collapses its own strip (+ halo rows from its neighbours); nobody holds the whole map ----
+    def save_sharded(self, axis, span, origin, levels=None, out=None, gather=False):
+        """The sharded half of Map2D::save (MultiBandMap2DCPU.cpp:779-847 / Map2DCPU.cpp:523-564) for the contiguous
+        strips align_strips() installs (rank r owns absolute tile coordinates [origin + r*span, origin + (r+1)*span)
+        along `axis`).  Collective.  Steps: all ranks agree on the global bbox of touched tiles (one tiny all_gather);
+        neighbours swap the k tile rows next to their common boundary, raw (k = ceil((2^levels - 2) / 256): what a
+        window edge that is not the mosaic's edge gets wrong reaches 2^levels - 2 level-0 px into the window); every
+        rank collapses window = its strip + halo (m2d_get_image_rect) and keeps the crop = its strip.
+        Returns (strip, rect_abs): strip = uint8 tensor [h, w, channels] on the rank's device (CUDA) or CPU (gloo), or None
+        if the rank owns no row of the bbox, written into `out` (a flat uint8 tensor, grown as needed) if given;
+        rect_abs = the strip's absolute tile rect.  gather=True additionally assembles the whole mosaic on rank 0
+        (returned there instead of the strip; only sensible when it fits one device)."""
+        dev = torch.device("cuda", self.device) if self.cuda else torch.device("cpu")
+        levels = levels or getattr(self.map, "levels", 1)
+        k = max(1, -(-((1 << levels) - 2) // 256)) if self.type == 3 else 0
+        bb = self.map.tile_bbox()
+        mine = torch.tensor(list(bb) + [1] if bb else [0, 0, 0, 0, 0], dtype=torch.int64, device=dev)
+        allbb = [torch.zeros(5, dtype=torch.int64, device=dev) for _ in range(self.world)]
+        if self.world > 1:
+            dist.all_gather(allbb, mine)
+        else:
+            allbb = [mine]
+        allbb = np.array([t.cpu().numpy() for t in allbb])
+        have = allbb[allbb[:, 4] == 1]
+        if len(have) == 0:
+            return None, None
+        G = [int(have[:, 0].min()), int(have[:, 1].min()), int(have[:, 2].max()), int(have[:, 3].max())]
+        g0, g1 = (G[0], G[2]) if axis == 0 else (G[1], G[3])
+        if g0 < origin or g1 > origin + span * self.world or (self.world > 1 and span < k):
+            raise RuntimeError("save_sharded needs the contiguous strips of align_strips(); use gather_to_root() for other layouts")
+
+        def interval(r):
+            return max(origin + r * span, g0), min(origin + (r + 1) * span, g1)
+
+        def rect(a, b):   # tile rect of rows/columns [a, b) along the shard axis, full extent across
+            return (a, G[1], b, G[3]) if axis == 0 else (G[0], a, G[2], b)
+
+        lo, hi = interval(self.rank)
+        tb = self.map.tile_bytes()
+        halos = []
+        if k and self.world > 1:
+            # what I send: my first k rows to the rank below, my last k rows to the rank above (if they own anything)
+            sends, recvs = [], []
+            for nb, (a, b) in ((self.rank - 1, (lo, min(lo + k, hi))), (self.rank + 1, (max(hi - k, lo), hi))):
+                if nb < 0 or nb >= self.world or hi <= lo:
+                    continue
+                nlo, nhi = interval(nb)
+                if nhi <= nlo:
+                    continue   # NOTE: an empty neighbour strip in the middle of the bbox is not handled (align_strips never makes one)
+                n = self.map.export_tiles_rect(rect(a, b), 0, 0, self.cuda) if b > a else 0
+                buf = torch.empty(max(n, 1) * tb, dtype=torch.uint8, device=dev)
+                xy = self.map.export_tiles_rect(rect(a, b), buf.data_ptr(), n, self.cuda) if n else np.zeros((0, 2), np.int32)
+                sends.append((nb, n, torch.from_numpy(np.ascontiguousarray(xy.reshape(-1))).to(dev), buf))
+            # counts first (neighbours only), then the tiles
+            cnt_out = {nb: torch.tensor([n], dtype=torch.int64, device=dev) for nb, n, _, _ in sends}
+            cnt_in = {nb: torch.zeros(1, dtype=torch.int64, device=dev) for nb, _, _, _ in sends}
+            ops = [dist.P2POp(dist.isend, cnt_out[nb], nb) for nb in cnt_out] + [dist.P2POp(dist.irecv, cnt_in[nb], nb) for nb in cnt_in]
+            if ops:
+                for req in dist.batch_isend_irecv(ops):
+                    req.wait()
+            ops = []
+            for nb, n, xy_t, buf in sends:
+                if n:
+                    ops += [dist.P2POp(dist.isend, xy_t, nb), dist.P2POp(dist.isend, buf[:n * tb], nb)]
+                m = int(cnt_in[nb].item())
+                if m:
+                    xy_r = torch.empty(m * 2, dtype=torch.int32, device=dev)
+                    buf_r = torch.empty(m * tb, dtype=torch.uint8, device=dev)
+                    recvs.append((xy_r, buf_r))
+                    ops += [dist.P2POp(dist.irecv, xy_r, nb), dist.P2POp(dist.irecv, buf_r, nb)]
+            if ops:
+                for req in dist.batch_isend_irecv(ops):
+                    req.wait()
+                if self.cuda:
+                    torch.cuda.current_stream().synchronize()
+            for xy_r, buf_r in recvs:
+                self.map.import_tiles(xy_r.cpu().numpy().reshape(-1, 2), buf_r.data_ptr(), self.cuda)
+            halos = [rect(max(lo - k, g0), lo), rect(hi, min(hi + k, g1))]
+        strip, srect = None, None
+        if hi > lo:
+            win, srect = rect(max(lo - k, g0), min(hi + k, g1)), rect(lo, hi)
+            cn = 3 if self.type == 3 else 4
+            hpx, wpx = (srect[3] - srect[1]) * 256, (srect[2] - srect[0]) * 256
+            need = hpx * wpx * cn
+            if out is None or out.numel() < need:
+                out = torch.empty(need, dtype=torch.uint8, device=dev)
+            self.map.get_image_rect(win, srect, out.data_ptr(), self.cuda)
+            strip = out[:need].view(hpx, wpx, cn)
+        for r_ in halos:
+            if r_[2] > r_[0] and r_[3] > r_[1]:
+                self.map.drop_tiles_rect(r_)
+        if not gather:
+            return strip, srect
+        # optional: the whole mosaic on rank 0 (192 KiB per tile instead of 874 KB of raw state, already collapsed)
+        shape = torch.tensor(list(strip.shape) if strip is not None else [0, 0, 0], dtype=torch.int64, device=dev)
+        shapes = [torch.zeros(3, dtype=torch.int64, device=dev) for _ in range(self.world)]
+        if self.world > 1:
+            dist.all_gather(shapes, shape)
+        else:
+            shapes = [shape]
+        shapes = [tuple(int(v) for v in t.tolist()) for t in shapes]
+        if self.rank != 0:
+            if strip is not None:
+                dist.send(strip.contiguous().view(-1), 0)
+            return None, G
+        parts = []
+        for r in range(self.world):
+            if shapes[r][0] == 0:
+                continue
+            if r == 0:
+                parts.append(strip)
+            else:
+                t = torch.empty(shapes[r], dtype=torch.uint8, device=dev)
+                dist.recv(t.view(-1), r)
+                parts.append(t)
+        return torch.cat(parts, dim=1 if axis == 0 else 0), G
+
     def gather_to_root(self):
         """Raw owned tiles -> rank 0 (which imports them).  Returns the number of tiles received by the root."""
         tb = self.map.tile_bytes()
@@ -334,28 +451,20 @@ def bench_main(args, rank, world, local_rank):
     return bench_weak(args, rank, world, local_rank)
 
 
-def bench_weak(args, rank, world, local_rank):
-    """N x the BASELINE survey (same flight-line length, N x the lines), cut into N strips of tiles.  Every rank holds
-    the frames of its own flight lines in HBM (args.frames each); per step the halo frames cross NVLink by P2P
-    (inside the timed region), every rank sees every pose and fuses the tiles it owns.  The final tile gather is
-    timed separately (it is the sharded half of save(), which the 1-GPU `value` does not contain either)."""
-    import json
-    import pi_slam_fusion_b200.map2d as m2d
-    import pi_slam_fusion_b200.synth as synth
-    import bench as B
+def _sha(t):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(t.cpu().numpy() if hasattr(t, "cpu") else t).tobytes()).hexdigest()[:16]
 
-    saved_stdout = os.dup(1)   # NCCL prints its banner to stdout; the contract is ONE JSON line there
-    os.dup2(2, 1)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    if args.size:   # `bench` imported here is a second copy of the module bench.py runs as __main__
-        B.W, B.H = (int(v) for v in args.size.lower().split("x"))
-    W, H = B.W, B.H
-    mode = args.mode
+
+def _strip_run(args, rank, world, local_rank, mode, seq, label, steps, warm, check_unsharded, want_e2e, B, m2d, want_sha=False):
+    """One tile-sharded job on `world` GPUs: contiguous strips of tiles (align_strips), frames resident in the HBM of the GPU
+    whose flight lines produced them, halo frames by NCCL P2P inside the timed region, poses to all ranks.  Timed: a step =
+    reset + exchange + fuse (max over ranks, device events and wall clock); then the sharded save on its own (halo tile
+    rows between neighbours, per-rank collapse of its own strip, D2H of the strip into pinned host memory).
+    Returns the result dict on rank 0 (None elsewhere)."""
+    BB = B
+    W, H, n = seq.w, seq.h, seq.n
     typ = 3 if mode == "multiband" else 1
-    per_gpu = args.frames
-    n = per_gpu * world
-    fpl = synth.frames_per_line(per_gpu, W, H)
-    seq = synth.Sequence(n, W, H, seed=B.SEED, fpl=fpl)
     dev = torch.device("cuda", local_rank)
     sm = ShardedMap2D(lambda t, **kw: m2d.Map2D.create(t, thread=False, **kw), typ, rank, world, device=local_rank,
                       shard_axis=0, shard_span=4, batch_frames=args.batch)
@@ -364,18 +473,13 @@ def bench_weak(args, rank, world, local_rank):
     plan = DeliveryPlan(rects, axis, span, world, even_split(n, world), origin)
     buf, mine = sm.alloc_owned_buffer(plan, W, H)
     lo, hi = plan.resident[rank]
-    host_t = torch.empty((hi - lo, H, W, 3), dtype=torch.uint8, pin_memory=True)
-    host = host_t.numpy()
-    for k in range(lo, hi):
-        host[k - lo] = seq.frame(k)
-    mine.copy_(host_t)            # inputs resident in HBM before the timed region, on the GPU that "captured" them
+    mine.copy_(BB.device_frames(torch, seq, lo, hi, dev))   # inputs resident in HBM before the timed region, on the GPU that "captured" them
     torch.cuda.synchronize()
 
     def step():
         sm.map.reset()
         return sm.feed_all_owned(plan, buf, seq.poses, W, H)
 
-    warm = max(args.warmup, 3)
     for _ in range(warm):
         res = step()
     sampler = B.ClockSampler(local_rank)
@@ -386,45 +490,48 @@ def bench_weak(args, rank, world, local_rank):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         res = step()           # ends with m2d_sync: the library's streams have drained
     ev1.record()
     torch.cuda.synchronize()
-    wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    wall_ms = (time.perf_counter() - t0) * 1e3 / steps
     dist.barrier()
     torch.cuda.synchronize()
-    ms = max(ev0.elapsed_time(ev1) / args.steps, wall_ms)
-    launches = float(sm.map.launch_count() - l0) / args.steps
+    ms = max(ev0.elapsed_time(ev1) / steps, wall_ms)
+    launches = float(sm.map.launch_count() - l0) / steps
     clocks = sampler.result()
 
-    # final tile gather to the root, timed on its own; the first call pays NCCL's lazy connection set-up between
-    # the root and the ranks it has not exchanged halos with, and the root's tile-pool growth: warm once, then time
-    sm.gather_to_root()
+    # ---- sharded save: warm once (NCCL connections, collapse buffers), then time
+    strip, srect = sm.save_sharded(axis, span, origin)
+    nbytes = int(strip.numel()) if strip is not None else 0
+    host = torch.empty(max(nbytes, 1), dtype=torch.uint8, pin_memory=True)
+    out_dev = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
+
+    def save():
+        st, _ = sm.save_sharded(axis, span, origin, out=out_dev)
+        if st is not None:
+            host[:nbytes].copy_(st.view(-1), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
     dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    sm.gather_to_root()
+    save()
     torch.cuda.synchronize()
-    gather_ms = (time.perf_counter() - t0) * 1e3
+    save_ms = (time.perf_counter() - t0) * 1e3
 
-    # e2e: host buffers -> H2D of the rank's own frames, halo exchange, fuse, tile gather, mosaic D2H on the root
-    e2e_ms = out_bytes = None
-    if not args.no_e2e:
-        out_pinned = None
-        if rank == 0:
-            img, _ = sm.map.get_image()
-            out_bytes = img.nbytes
-            del img
-            out_pinned = torch.empty(out_bytes, dtype=torch.uint8, pin_memory=True).numpy()
+    # ---- e2e: host buffers -> H2D of the rank's own frames, halo exchange, fuse, sharded save, strip D2H on every rank
+    e2e_ms = None
+    if want_e2e:
+        host_in = torch.empty((hi - lo, H, W, 3), dtype=torch.uint8, pin_memory=True)
+        host_in.copy_(mine)
 
         def step_e2e():
             sm.map.reset()
-            mine.copy_(host_t, non_blocking=True)
+            mine.copy_(host_in, non_blocking=True)
             torch.cuda.current_stream().synchronize()
             sm.feed_all_owned(plan, buf, seq.poses, W, H)
-            sm.gather_to_root()
-            if rank == 0:
-                sm.map.get_image(out=out_pinned)
+            save()
 
         step_e2e()
         dist.barrier()
@@ -436,36 +543,121 @@ def bench_weak(args, rank, world, local_rank):
         torch.cuda.synchronize()
         dist.barrier()
         e2e_ms = (time.perf_counter() - t0) * 1e3 / reps
+        del host_in
 
-    t = torch.tensor([ms, gather_ms, e2e_ms or 0.0, launches], device=dev, dtype=torch.float64)
+    # ---- correctness inside the run: the strips, assembled on rank 0, against an UNSHARDED run of the same survey on rank 0
+    parity = None
+    if check_unsharded:
+        step()
+        mosaic, gbox = sm.save_sharded(axis, span, origin, gather=True)
+        if rank == 0:
+            ref = m2d.Map2D.create(typ, thread=False, device=local_rank, batch_frames=args.batch)
+            assert ref.prepare(seq.plane, seq.camera, seq.prepare_poses)
+            chunk = max(1, min(n, int(6e9 // (W * H * 3))))
+            for c0 in range(0, n, chunk):
+                fr = BB.device_frames(torch, seq, c0, min(c0 + chunk, n), dev)
+                ref.feed_batch(fr.data_ptr(), fr.shape[0], W * H * 3, W, H, W * 3, seq.poses[c0:c0 + fr.shape[0]], True)
+                ref.sync()
+                del fr
+            img, org = ref.get_image()
+            same = bool(tuple(img.shape) == tuple(mosaic.shape) and np.array_equal(img, mosaic.cpu().numpy()))
+            parity = {"checked": "mosaic of the sharded save (strips of all ranks) vs an unsharded run of the same %d frames on rank 0" % n,
+                      "identical": same, "sha256_sharded": _sha(mosaic), "sha256_unsharded": _sha(img), "mosaic_px": int(img.shape[0] * img.shape[1])}
+            ref.close()
+            del img
+        del mosaic
+    mosaic_sha = None
+    if want_sha and not check_unsharded:   # the assembled mosaic's digest, comparable across runs with different N
+        mosaic, gbox = sm.save_sharded(axis, span, origin, gather=True)
+        if rank == 0:
+            mosaic_sha = _sha(mosaic)
+        del mosaic
+    t = torch.tensor([ms, save_ms, e2e_ms or 0.0, launches], device=dev, dtype=torch.float64)
     tmax = t.clone()
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
-    hull = torch.tensor([plan.hull[rank][1] - plan.hull[rank][0]], device=dev, dtype=torch.float64)
-    dist.all_reduce(hull, op=dist.ReduceOp.MAX)
+    hull = torch.tensor([plan.hull[rank][1] - plan.hull[rank][0], float(nbytes)], device=dev, dtype=torch.float64)
+    hmax = hull.clone()
+    dist.all_reduce(hmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(hull, op=dist.ReduceOp.SUM)
     fused = int((res == 0).sum())
+    tiles = torch.tensor([float(sm.map.tile_count())], device=dev, dtype=torch.float64)
+    dist.all_reduce(tiles, op=dist.ReduceOp.SUM)
+    out = None
     if rank == 0:
-        ms_step = float(tmax[0])
+        ms_step, sv = float(tmax[0]), float(tmax[1])
         px = fused * W * H
-        e2e = None
+        out = {"label": label, "mode": mode, "value": px / (ms_step * 1e-3) / 1e6, "unit": B.UNIT, "ms_per_step": ms_step, "frames": n, "frames_fused": fused,
+               "gpu_launches": int(float(t[3])), "clocks": clocks, "tiles": int(tiles.item()),
+               "parallelism": "%d contiguous strips of %d tiles along axis %d (tile ownership); frames resident on the GPU of their own flight lines, "
+                              "%d halo frames exchanged by NCCL P2P per step (inside the timed region), poses to all ranks; largest rank feeds %d of %d frames"
+                              % (world, span, axis, plan.frames_moved(), int(hmax[0].item()), n),
+               "save": {"what": "sharded save: neighbours swap one raw tile row per boundary, every rank collapses ITS strip and copies it to pinned host memory; no rank holds the whole map",
+                        "ms": sv, "mosaic_bytes": int(hull[1].item()), "value_incl_save": px / ((ms_step + sv) * 1e-3) / 1e6},
+               "parity": parity}
+        if mosaic_sha:
+            out["mosaic_sha256"] = mosaic_sha
         if e2e_ms is not None:
-            e2e = {"value": px / (float(tmax[2]) * 1e-3) / 1e6, "unit": B.UNIT, "h2d_bytes_per_step": n * W * H * 3,
-                   "d2h_bytes_per_step": out_bytes, "ms_per_step": float(tmax[2]),
-                   "what": "per rank: H2D of its own pinned host frames, halo exchange, m2d_feed_batch; then tile gather to rank 0 and m2d_get_image (collapse + D2H of the whole mosaic)"}
-        line = {"metric": B.METRIC, "value": px / (ms_step * 1e-3) / 1e6, "unit": B.UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "s16" if mode == "multiband" else "u8", "data": "synthetic",
-                "config": {"workload": B.workload_name(mode, per_gpu) + " x %d GPUs: %d frames, %d flight lines of %d" % (world, n, -(-n // fpl), fpl),
-                           "mode": mode, "frames": n, "frames_per_gpu": per_gpu, "frames_fused": fused,
-                           "parallelism": "%d strips of %d tiles along axis %d (tile ownership); frames resident on the GPU of their own flight lines, "
-                                          "%d halo frames exchanged by NCCL P2P per step (inside the timed region), poses to all ranks; "
-                                          "largest rank feeds %d frames" % (world, span, axis, plan.frames_moved(), int(hull.item())),
-                           "final_tile_gather": "not in `value` (like save() at 1 GPU); %.2f ms to rank 0, see breakdown_ms" % float(tmax[1]),
-                           "l2": "inputs %.2f GB per GPU per step > 126 MB L2" % (per_gpu * W * H * 3 / 1e9)},
-                "clocks": clocks, "gpu_launches": int(float(t[3])),
-                "breakdown_ms": {"exchange_plus_fuse": ms_step, "tile_gather_to_root": float(tmax[1]),
-                                 "value_incl_gather": px / ((ms_step + float(tmax[1])) * 1e-3) / 1e6},
-                "e2e": e2e, "roofline": None, "cpu_baseline": None}
+            out["e2e"] = {"value": px / (float(tmax[2]) * 1e-3) / 1e6, "unit": B.UNIT, "h2d_bytes_per_step": n * W * H * 3,
+                          "d2h_bytes_per_step": int(hull[1].item()), "ms_per_step": float(tmax[2]),
+                          "what": "per rank: H2D of its own pinned host frames, halo exchange, m2d_feed_batch, sharded save (m2d_get_image_rect of its strip) + D2H of the strip"}
+    sm.map.close()
+    del buf, mine, out_dev, host
+    torch.cuda.empty_cache()
+    return out
+
+
+def bench_weak(args, rank, world, local_rank):
+    """Headline: N x the BASELINE cfg2 survey (same flight-line length, N x the lines), cut into N strips of tiles -- per-GPU
+    work is fixed (weak scaling).  The same line carries the weighted mode on the same survey, and cfg3 (BASELINE configs[2]:
+    the 1000-frame 4000x3000 multi-band survey) as ONE fixed job cut into N strips (strong scaling)."""
+    import json
+    import pi_slam_fusion_b200.map2d as m2d
+    import pi_slam_fusion_b200.synth as synth
+    import bench as B
+
+    saved_stdout = os.dup(1)   # NCCL prints its banner to stdout; the contract is ONE JSON line there
+    os.dup2(2, 1)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    head_cfg = B.CFG2 if args.mode == "multiband" else B.CFG1
+    other_mode = "weighted" if args.mode == "multiband" else "multiband"
+    mode, per_gpu, W, H, seed, _ = head_cfg
+    per_gpu = args.frames or B.CFG2[1]          # the weak-scaled survey is cfg2-shaped in both modes (500 frames per GPU)
+    W, H, seed = B.CFG2[2], B.CFG2[3], B.CFG2[4]
+    if args.size:
+        W, H = (int(v) for v in args.size.lower().split("x"))
+    n = per_gpu * world
+    fpl = synth.frames_per_line(per_gpu, W, H)
+    seq = synth.Sequence(n, W, H, seed=seed, fpl=fpl)
+    warm = max(args.warmup, 3)
+    head = _strip_run(args, rank, world, local_rank, mode, seq, "headline", args.steps, warm, True, not args.no_e2e, B, m2d)
+    other = cfg3 = None
+    if not args.only:
+        other = _strip_run(args, rank, world, local_rank, other_mode, seq, other_mode, max(3, args.steps // 2), 3, True, not args.no_e2e, B, m2d)
+        if args.cfg3_frames > 0:
+            _, n3, w3, h3, s3, _ = B.CFG3
+            n3 = args.cfg3_frames
+            seq3 = synth.Sequence(n3, w3, h3, seed=s3)
+            cfg3 = _strip_run(args, rank, world, local_rank, "multiband", seq3, "cfg3", max(2, min(args.steps, 5)), 2, False, False, B, m2d, want_sha=True)
+    if rank == 0:
+        cfg = B.config_of(mode, n, W, H, seed, world)
+        cfg["frames_per_gpu"] = per_gpu
+        cfg["workload"] += " x %d GPUs: %d frames, %d flight lines of %d" % (world, n, -(-n // fpl), fpl)
+        line = {"metric": B.METRIC, "value": head["value"], "unit": B.UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": warm, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "s16" if mode == "multiband" else "u8", "data": "synthetic", "config": cfg,
+                "run": {"frames_fused": head["frames_fused"], "parallelism": head["parallelism"], "tiles": head["tiles"]},
+                "clocks": head["clocks"], "gpu_launches": head["gpu_launches"],
+                "breakdown_ms": {"exchange_plus_fuse": head["ms_per_step"], "sharded_save": head["save"]["ms"],
+                                 "value_incl_save": head["save"]["value_incl_save"]},
+                "save": head["save"], "e2e": head.get("e2e"), "parity": head["parity"], "roofline": None, "cpu_baseline": None}
+        if other:
+            line[other_mode] = other
+        if cfg3:
+            cfg3["workload"] = B.workload_name("multiband", seq3.n, seq3.w, seq3.h, B.CFG3[4])
+            cfg3["scaling"] = "strong"
+            cfg3["n_gpus"] = world
+            line["cfg3"] = cfg3
         os.write(saved_stdout, (json.dumps(line) + "\n").encode())
     dist.destroy_process_group()
 

@@ -61,6 +61,15 @@ def _worker(rank, world, port, typ, distributed_input, q, backend="gloo"):
             mine.copy_(torch.from_numpy(seq.frames(range(lo, hi))))
             res = sm.feed_all_owned(plan, buf, poses, seq.w, seq.h)
             extra = {"hull": plan.hull, "moved": plan.frames_moved(), "n": seq.n}
+            # sharded save BEFORE any gather: every rank collapses its own strip (+ one halo tile row from its neighbours)
+            before = sm.map.tile_count()
+            mosaic, gbox = sm.save_sharded(axis, span, origin, gather=True)
+            assert sm.map.tile_count() == before, "halo tiles must be dropped again"
+            strip, srect = sm.save_sharded(axis, span, origin)      # and without the final gather: just my strip
+            extra["strip"] = None if strip is None else (tuple(strip.shape), tuple(srect))
+            if rank == 0:
+                extra["sharded_mosaic"] = mosaic.cpu().numpy()
+                extra["gbox"] = tuple(gbox)
         elif distributed_input:
             ids = ShardedMap2D.local_frame_ids(seq.n, rank, world, block=3)
             local = torch.from_numpy(seq.frames(ids)).to(tdev)
@@ -99,6 +108,10 @@ def _worker(rank, world, port, typ, distributed_input, q, backend="gloo"):
             ia, ib = ref.get_image(), sm.map.get_image()
             out.update(exp=exp, same_grid=bool(same_grid), ntiles=ntiles, bad=bad,
                        image_equal=bool(ia[1] == ib[1] and np.array_equal(ia[0], ib[0])))
+            if "sharded_mosaic" in out:   # the strips of the sharded save tile the reference's mosaic byte for byte
+                sh = out.pop("sharded_mosaic")
+                out["sharded_save_equal"] = bool(sh.shape == ia[0].shape and np.array_equal(sh, ia[0]))
+                out["sharded_save_bbox_ok"] = bool(ref.tile_bbox() == out["gbox"])
         q.put(out)
     finally:
         dist.destroy_process_group()
@@ -129,6 +142,9 @@ def test_two_rank_sharded_equals_unsharded(typ, distributed_input, world):
     if distributed_input == "owned":
         # the plan really kept pixels away from ranks that do not need them, and really moved the halo frames
         assert any(tuple(h) != (0, root["n"]) for h in root["hull"]) and 0 < root["moved"] < root["n"]
+        assert root["sharded_save_equal"] and root["sharded_save_bbox_ok"]
+        strips = [o["strip"] for o in sorted(outs, key=lambda o: o["rank"]) if o["strip"] is not None]
+        assert len(strips) >= 2, "at least two ranks must hold a strip of the mosaic"
 
 
 def test_delivery_plan_properties():
