@@ -9,6 +9,7 @@ ONE JSON line.  Headline (`value`, `e2e`, `roofline`, `cpu_baseline`) = BASELINE
   stream_latency  configs[4] (cfg5: 2000 synchronous feed() calls, 1920x1080, pose jitter, H2D included): p50 / p99 ms
   cfg3            configs[2] (MultiBandMap2DCPU on 4000x3000 frames, 1000-frame survey): value on this many GPUs (the SAME
                   job at every N: strong scaling, tile-sharded for N > 1)
+  cfg4            configs[3] (weighted fusion of a 5000-frame 4000x3000 survey, ~120 GB of map state): at 8 GPUs only
   parity          the mosaic of the fed prefix, bit for bit against the CPU oracle (sha256 of both)
 Per measured mode:
   value     whole-job Mpix/s with the frames already resident in HBM (one m2d_feed_batch on device pointers per step)
@@ -42,6 +43,7 @@ UNIT = "Mpix/s"
 CFG1 = ("weighted", 100, 1280, 720, 1, False)
 CFG2 = ("multiband", 500, 1280, 720, 2, False)
 CFG3 = ("multiband", 1000, 4000, 3000, 3, False)
+CFG4 = ("weighted", 5000, 4000, 3000, 4, False)
 CFG5 = (None, 2000, 1920, 1080, 5, True)
 
 
@@ -474,6 +476,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="m2d_config.batch_frames (0 = library default)")
     ap.add_argument("--stream-latency", type=int, default=CFG5[1], help="frames of the cfg5 latency run (0 = skip)")
     ap.add_argument("--cfg3-frames", type=int, default=CFG3[1], help="frames of the cfg3 run (0 = skip)")
+    ap.add_argument("--cfg4-frames", type=int, default=-1, help="frames of the cfg4 run (N>1 only; default: 5000 at 8 GPUs, else skipped; 0 = skip)")
     ap.add_argument("--only", action="store_true", help="headline mode only: no second mode, no cfg3, no cfg5")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1 headline. weak: N x the survey, --frames per GPU, strips of tiles, halo frames by P2P; strong: the same frames cut into N shards")

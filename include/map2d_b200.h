@@ -145,6 +145,10 @@ int m2d_sync(m2d_handle h);
 int m2d_queue_size(m2d_handle h);                 /* frames enqueued and not yet finished on the GPU */
 int m2d_set_stream(m2d_handle h, void* cuda_stream /* cudaStream_t, NULL = library-owned */);
 int m2d_reset(m2d_handle h);                      /* drop all tiles, keep the prepared grid */
+/* Device-resident frames that are still being produced on another stream (a decoder, an NCCL receive of halo frames): the
+ * NEXT m2d_feed_device / m2d_feed_batch call makes every kernel that reads frame pixels wait for `cuda_event`
+ * (cudaEvent_t) first; bounds, weights and winners -- which need poses only -- start at once.  One feed call consumes it. */
+int m2d_set_input_event(m2d_handle h, void* cuda_event);
 
 /* Grid as laid out by prepare()/spreadMap (Map2DCPUData: _w,_h,_min,_max,_lengthPixel). */
 int m2d_get_grid(m2d_handle h, int* w, int* h_tiles, double min_xyz[3], double max_xyz[3],

@@ -70,6 +70,7 @@ struct GroupParams {
     int wmap_stride;           // >= TileLayout::px_off[levels], even
     unsigned char reach_lo[6][6], reach_hi[6][6];    // image: [win level m][Gaussian level k] in cells, 0xFF = none (make_reach_table)
     unsigned char wreach_lo[6][6], wreach_hi[6][6];  // weights: [competitive level m][weight level k]   (make_weight_reach_table)
+    int use_tma;               // pyrDown 0 -> 1 through TMA-staged shared-memory patches (M2D_TMA=0: register-window kernel)
     int cull;                  // 0: every entry of a tile is treated as competitive (collect_stats, M2D_WCULL=0)
 };
 

@@ -436,7 +436,223 @@ __global__ void __launch_bounds__(256) mbx_pyrdown_kernel(const __grid_constant_
         }
     }
 }
+// ---- bulk-copy (TMA engine) helpers: 1-D cp.async.bulk global -> shared, completion counted on an mbarrier ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {   // 16-byte aligned src, dst, size
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// 1b'./4b'. pyrDown 0 -> 1 of the listed cells with the input patch STAGED IN SHARED MEMORY BY THE TMA ENGINE.  The
+// register-window kernel above is latency-bound (ncu: 31 % issue slots, 25-37 % DRAM, 33-49 % occupancy at 64-76
+// registers): every thread waits on its own 44 global loads.  Here a warp owns a cell (16 x 16 outputs <- 35 x 35 input
+// px): lane r issues ONE bulk copy per patch row (cp.async.bulk, 160 B = 40 px from the 16-byte aligned column
+// 32 cx - 4) into the warp's stage buffer, completion is counted on the stage's mbarrier (expect_tx = 35 x 160 B), and
+// the patch of the warp's NEXT cell is in flight while the current one is filtered out of shared memory (2 stages per
+// warp, no CTA-wide barrier anywhere).  Same arithmetic, same association, same thread -> output mapping as the
+// register-window kernel.  Cells on the rim of the frame's window (reflected or clamped taps, ~10 %) take the
+// register-window path inside the same kernel.
+constexpr int kPW = 40, kPH = 35, kPStages = 2;
+constexpr int kPatchWords = kPW * kPH;                                   // 1400 words = 5600 B per stage
+constexpr size_t kPyrTmaSmem = (size_t)8 * kPStages * kPatchWords * 4 + 8 * kPStages * 8;
+
+template <bool IMG>
+__global__ void __launch_bounds__(256) mbx_pyrdown0_tma_kernel(const __grid_constant__ GroupParams p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t* buf = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)warp * kPStages * kPatchWords;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)8 * kPStages * kPatchWords * 4) + warp * kPStages;
+    if (lane == 0) {
+        for (int s = 0; s < kPStages; s++) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const unsigned n = p.list_count[(IMG ? 6 : 0) + 1];
+    const uint32_t* list = p.lists + ((size_t)(IMG ? p.levels : 0) + 1) * p.list_cap;
+    const unsigned gw = blockIdx.x * 8 + warp, stride = gridDim.x * 8;
+    const int cp = lane & 7, rq = lane >> 3;
+    const int ns = kEle, nd = kEle >> 1;
+    unsigned parity = 0;   // bit s: the phase parity the next wait on stage s expects
+
+    // issue the patch of item `it` into stage s (all lanes call; rim cells issue nothing and return false)
+    auto prefetch = [&](unsigned it, int s) -> bool {
+        const uint32_t item = list[it];
+        const int f = (int)(item >> 16), c = (int)(item & 0xFFFFu);
+        const FrameJob& J = p.jobs[f];
+        const int cw = J.wnx * 8, ch = J.wny * 8, cy = c / cw, cx = c - cy * cw;
+        if (cx < 1 || cx > cw - 2 || cy < 1 || cy > ch - 2) return false;
+        const int sww = J.wnx * ns;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(p.scratch + (IMG ? J.g_off[0] : J.w_off[0])) + (size_t)(32 * cy - 2) * sww + (32 * cx - 4);
+        uint32_t* dst = buf + (size_t)s * kPatchWords;
+        if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the stage was read through the generic proxy two items ago
+            mbar_arrive_expect_tx(&bars[s], kPH * kPW * 4);
+        }
+        __syncwarp();
+        bulk_g2s(dst + lane * kPW, src + (size_t)lane * sww, kPW * 4, &bars[s]);
+        if (lane < kPH - 32) bulk_g2s(dst + (32 + lane) * kPW, src + (size_t)(32 + lane) * sww, kPW * 4, &bars[s]);
+        return true;
+    };
+
+    unsigned it = gw;
+    bool staged = it < n ? prefetch(it, 0) : false;
+    int s = 0;
+    for (; it < n; it += stride, s ^= 1) {
+        const unsigned nxt = it + stride;
+        const bool staged_next = nxt < n ? prefetch(nxt, s ^ 1) : false;
+        const uint32_t item = list[it];
+        const int f = (int)(item >> 16), c = (int)(item & 0xFFFFu);
+        const FrameJob& J = p.jobs[f];
+        const int cw = J.wnx * 8, cy = c / cw, cx = c - cy * cw;
+        const int dww = J.wnx * nd;
+        const int u = cx * 16 + 2 * cp, v0 = cy * 16 + 4 * rq;
+        if (staged) {
+            mbar_wait(&bars[s], (parity >> s) & 1u);
+            parity ^= 1u << s;
+            const uint32_t* patch = buf + (size_t)s * kPatchWords + (size_t)(8 * rq) * kPW + 4 * cp + 2;   // the thread's 7 x 11 window
+            if constexpr (IMG) {
+                uint32_t* DG = reinterpret_cast<uint32_t*>(p.scratch + J.g_off[1]);
+                uint32_t hb0[5], hg0[5], hb1[5], hg1[5];
+#pragma unroll
+                for (int r = 0; r < 11; r++) {
+                    const uint32_t* gr = patch + r * kPW;
+                    const uint2 a = *reinterpret_cast<const uint2*>(gr), b = *reinterpret_cast<const uint2*>(gr + 2), cc = *reinterpret_cast<const uint2*>(gr + 4);
+                    const uint32_t e[7] = {a.x, a.y, b.x, b.y, cc.x, cc.y, gr[6]};
+                    uint32_t br[7], g[7];
+#pragma unroll
+                    for (int d = 0; d < 7; d++) { br[d] = e[d] & kM2; g[d] = (e[d] >> 8) & 0xFFu; }
+                    hb0[r % 5] = br[2] * 6u + (br[1] + br[3]) * 4u + br[0] + br[4];
+                    hb1[r % 5] = br[4] * 6u + (br[3] + br[5]) * 4u + br[2] + br[6];
+                    hg0[r % 5] = g[2] * 6u + (g[1] + g[3]) * 4u + g[0] + g[4];
+                    hg1[r % 5] = g[4] * 6u + (g[3] + g[5]) * 4u + g[2] + g[6];
+                    if (r >= 4 && (r & 1) == 0) {
+                        const int k = (r - 4) >> 1, v = v0 + k;
+                        const int i0 = (r - 4) % 5, i1 = (r - 3) % 5, i2 = (r - 2) % 5, i3 = (r - 1) % 5, i4 = r % 5;
+                        const uint32_t vbr0 = hb0[i0] + hb0[i4] + (hb0[i1] + hb0[i3]) * 4u + hb0[i2] * 6u;
+                        const uint32_t vbr1 = hb1[i0] + hb1[i4] + (hb1[i1] + hb1[i3]) * 4u + hb1[i2] * 6u;
+                        const uint32_t vg0 = hg0[i0] + hg0[i4] + (hg0[i1] + hg0[i3]) * 4u + hg0[i2] * 6u;
+                        const uint32_t vg1 = hg1[i0] + hg1[i4] + (hg1[i1] + hg1[i3]) * 4u + hg1[i2] * 6u;
+                        const uint32_t o0 = (((vbr0 + 0x00800080u) >> 8) & kM2) | (((vg0 + 128u) >> 8) << 8);
+                        const uint32_t o1 = (((vbr1 + 0x00800080u) >> 8) & kM2) | (((vg1 + 128u) >> 8) << 8);
+                        *reinterpret_cast<uint2*>(DG + (size_t)v * dww + u) = make_uint2(o0, o1);
+                    }
+                }
+            } else {
+                float* DW = reinterpret_cast<float*>(p.scratch + J.w_off[1]);
+                const float* fpatch = reinterpret_cast<const float*>(patch);
+                float h0[5], h1[5];
+#pragma unroll
+                for (int r = 0; r < 11; r++) {
+                    const float* wr = fpatch + r * kPW;
+                    const float2 fa = *reinterpret_cast<const float2*>(wr), fb = *reinterpret_cast<const float2*>(wr + 2), fc = *reinterpret_cast<const float2*>(wr + 4);
+                    const float fv[7] = {fa.x, fa.y, fb.x, fb.y, fc.x, fc.y, wr[6]};
+                    h0[r % 5] = fv[2] * 6.f + (fv[1] + fv[3]) * 4.f + fv[0] + fv[4];
+                    h1[r % 5] = fv[4] * 6.f + (fv[3] + fv[5]) * 4.f + fv[2] + fv[6];
+                    if (r >= 4 && (r & 1) == 0) {
+                        const int k = (r - 4) >> 1, v = v0 + k;
+                        const int i0 = (r - 4) % 5, i1 = (r - 3) % 5, i2 = (r - 2) % 5, i3 = (r - 1) % 5, i4 = r % 5;
+                        const float t00 = (h0[i0] + h0[i4]) + (h0[i2] + h0[i2]), t10 = (h0[i1] + h0[i3]) + h0[i2];
+                        const float t01 = (h1[i0] + h1[i4]) + (h1[i2] + h1[i2]), t11 = (h1[i1] + h1[i3]) + h1[i2];
+                        *reinterpret_cast<float2*>(DW + (size_t)v * dww + u) = make_float2((t00 + t10 * 4.f) * (1.f / 256.f), (t01 + t11 * 4.f) * (1.f / 256.f));
+                    }
+                }
+            }
+            __syncwarp();   // every lane is done with the stage before it is refilled
+        } else {
+            // rim cell: reflected / clamped taps straight from global memory (register-window path)
+            const int sww = J.wnx * ns, swh = J.wny * ns, srw = J.nx * ns, srh = J.ny * ns, sox = J.wx * ns, soy = J.wy * ns;
+            const int U = u + J.wx * nd, V0 = v0 + J.wy * nd;
+            int xs[7];
+#pragma unroll
+            for (int d = 0; d < 7; d++) xs[d] = clampi(reflect101_idx(2 * U + d - 2, srw) - sox, 0, sww - 1);
+            if constexpr (IMG) {
+                const uint32_t* SG = reinterpret_cast<const uint32_t*>(p.scratch + J.g_off[0]);
+                uint32_t* DG = reinterpret_cast<uint32_t*>(p.scratch + J.g_off[1]);
+                uint32_t hb0[5], hg0[5], hb1[5], hg1[5];
+#pragma unroll
+                for (int r = 0; r < 11; r++) {
+                    const int ys = clampi(reflect101_idx(2 * V0 + r - 2, srh) - soy, 0, swh - 1);
+                    const uint32_t* gr = SG + (size_t)ys * sww;
+                    uint32_t br[7], g[7];
+#pragma unroll
+                    for (int d = 0; d < 7; d++) { const uint32_t e = gr[xs[d]]; br[d] = e & kM2; g[d] = (e >> 8) & 0xFFu; }
+                    hb0[r % 5] = br[2] * 6u + (br[1] + br[3]) * 4u + br[0] + br[4];
+                    hb1[r % 5] = br[4] * 6u + (br[3] + br[5]) * 4u + br[2] + br[6];
+                    hg0[r % 5] = g[2] * 6u + (g[1] + g[3]) * 4u + g[0] + g[4];
+                    hg1[r % 5] = g[4] * 6u + (g[3] + g[5]) * 4u + g[2] + g[6];
+                    if (r >= 4 && (r & 1) == 0) {
+                        const int k = (r - 4) >> 1, v = v0 + k;
+                        const int i0 = (r - 4) % 5, i1 = (r - 3) % 5, i2 = (r - 2) % 5, i3 = (r - 1) % 5, i4 = r % 5;
+                        const uint32_t vbr0 = hb0[i0] + hb0[i4] + (hb0[i1] + hb0[i3]) * 4u + hb0[i2] * 6u;
+                        const uint32_t vbr1 = hb1[i0] + hb1[i4] + (hb1[i1] + hb1[i3]) * 4u + hb1[i2] * 6u;
+                        const uint32_t vg0 = hg0[i0] + hg0[i4] + (hg0[i1] + hg0[i3]) * 4u + hg0[i2] * 6u;
+                        const uint32_t vg1 = hg1[i0] + hg1[i4] + (hg1[i1] + hg1[i3]) * 4u + hg1[i2] * 6u;
+                        const uint32_t o0 = (((vbr0 + 0x00800080u) >> 8) & kM2) | (((vg0 + 128u) >> 8) << 8);
+                        const uint32_t o1 = (((vbr1 + 0x00800080u) >> 8) & kM2) | (((vg1 + 128u) >> 8) << 8);
+                        *reinterpret_cast<uint2*>(DG + (size_t)v * dww + u) = make_uint2(o0, o1);
+                    }
+                }
+            } else {
+                const float* SW = reinterpret_cast<const float*>(p.scratch + J.w_off[0]);
+                float* DW = reinterpret_cast<float*>(p.scratch + J.w_off[1]);
+                float h0[5], h1[5];
+#pragma unroll
+                for (int r = 0; r < 11; r++) {
+                    const int ys = clampi(reflect101_idx(2 * V0 + r - 2, srh) - soy, 0, swh - 1);
+                    const float* wr = SW + (size_t)ys * sww;
+                    float fv[7];
+#pragma unroll
+                    for (int d = 0; d < 7; d++) fv[d] = wr[xs[d]];
+                    h0[r % 5] = fv[2] * 6.f + (fv[1] + fv[3]) * 4.f + fv[0] + fv[4];
+                    h1[r % 5] = fv[4] * 6.f + (fv[3] + fv[5]) * 4.f + fv[2] + fv[6];
+                    if (r >= 4 && (r & 1) == 0) {
+                        const int k = (r - 4) >> 1, v = v0 + k;
+                        const int i0 = (r - 4) % 5, i1 = (r - 3) % 5, i2 = (r - 2) % 5, i3 = (r - 1) % 5, i4 = r % 5;
+                        const float t00 = (h0[i0] + h0[i4]) + (h0[i2] + h0[i2]), t10 = (h0[i1] + h0[i3]) + h0[i2];
+                        const float t01 = (h1[i0] + h1[i4]) + (h1[i2] + h1[i2]), t11 = (h1[i1] + h1[i3]) + h1[i2];
+                        *reinterpret_cast<float2*>(DW + (size_t)v * dww + u) = make_float2((t00 + t10 * 4.f) * (1.f / 256.f), (t01 + t11 * 4.f) * (1.f / 256.f));
+                    }
+                }
+            }
+        }
+        staged = staged_next;
+    }
+}
+
 cudaError_t launch_mbx_pyrdown(const GroupParams& p, int image, int level, int ctas, cudaStream_t stream) {
+    if (level == 0 && p.use_tma) {
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaError_t e = cudaFuncSetAttribute(mbx_pyrdown0_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPyrTmaSmem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(mbx_pyrdown0_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPyrTmaSmem);
+            if (e != cudaSuccess) return e;
+            attr_done = true;
+        }
+        const int tma_ctas = max(1, ctas / 4);   // 2 resident CTAs per SM (90 KB of stage buffers each)
+        if (image) mbx_pyrdown0_tma_kernel<true><<<tma_ctas, 256, kPyrTmaSmem, stream>>>(p);
+        else mbx_pyrdown0_tma_kernel<false><<<tma_ctas, 256, kPyrTmaSmem, stream>>>(p);
+        return cudaGetLastError();
+    }
     if (image) mbx_pyrdown_kernel<true><<<ctas, 256, 0, stream>>>(p, level);
     else mbx_pyrdown_kernel<false><<<ctas, 256, 0, stream>>>(p, level);
     return cudaGetLastError();

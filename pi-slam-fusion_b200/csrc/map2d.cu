@@ -132,6 +132,13 @@ struct m2d_map {
     std::vector<void*> chunks;
     std::vector<uint8_t*> free_tiles;
     size_t tiles_in_use = 0;
+    // pool filler: a helper thread keeps at least `pool_low` tiles free by allocating the next slab AHEAD of need, so
+    // that a streaming feed() never waits for a cudaMalloc (5-7 ms for a 128 MiB slab: it was the whole p99 of cfg5)
+    std::mutex pool_mu;
+    std::condition_variable pool_cv;
+    std::thread pool_thread;
+    bool pool_stop = false, pool_failed = false;
+    size_t pool_low = 0;
 
     // per-size weight images
     int wimg_w = 0, wimg_h = 0;
@@ -152,6 +159,8 @@ struct m2d_map {
     bool dense_pending = false;
     bool weight_cull = true;        // bound-based culling of (frame, cell) pairs before any weight is computed (bounds.h);
                                     // M2D_WCULL=0 treats every covering frame as competitive (A/B runs, parity sweeps)
+    cudaEvent_t input_event = nullptr;   // m2d_set_input_event: the frames of the next feed call are valid once it fires
+    bool use_tma = true;            // M2D_TMA=0: pyrDown 0 -> 1 with the register-window kernel instead of TMA-staged patches (A/B)
     double scratch_budget = 12e9;   // bytes of group scratch per context that the default group size aims at (M2D_SCRATCH_GB)
     int sm_count = 148;
     GroupCtx ctx[kMaxCtx];
@@ -179,6 +188,7 @@ struct m2d_map {
     int ensure_weight_images(int w, int h);
     int alloc_tile(uint8_t** out);
     int reserve_tiles(size_t n);
+    void pool_filler();
     int grow(void** p, size_t* cap, size_t need, bool pinned);
     int group_size(int w, int h, bool on_device) const;
     bool owns(int tx, int ty) const;
@@ -216,6 +226,7 @@ int m2d_map::init() {
     if (const char* e = getenv("M2D_CTX")) kCtx = std::max(2, std::min(atoi(e), (int)kMaxCtx));
     if (const char* e = getenv("M2D_SPARSE")) weights_first = atoi(e) != 0;
     if (const char* e = getenv("M2D_WCULL")) weight_cull = atoi(e) != 0;
+    if (const char* e = getenv("M2D_TMA")) use_tma = atoi(e) != 0;
     if (const char* e = getenv("M2D_SCRATCH_GB")) scratch_budget = std::max(0.25, atof(e)) * 1e9;
     CU(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, cfg.device));
     CU(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
@@ -240,6 +251,11 @@ int m2d_map::init() {
 
 void m2d_map::release() {
     cudaSetDevice(cfg.device);
+    if (pool_thread.joinable()) {
+        { std::lock_guard<std::mutex> lk(pool_mu); pool_stop = true; }
+        pool_cv.notify_all();
+        pool_thread.join();
+    }
     if (stream) cudaStreamSynchronize(stream);
     for (void* c : chunks) cudaFree(c);
     chunks.clear();
@@ -328,6 +344,11 @@ int m2d_map::prepare(const double* plane7, const double* cam, int n, const doubl
     // so ~1/4 of the grid is what the prepare-frames actually cover), capped at 2 GiB; failure here is not fatal.
     size_t want = std::min<size_t>(((size_t)w * h + 3) / 4, ((size_t)2 << 30) / tile_bytes);
     if (reserve_tiles(want) != M2D_OK) err.clear();
+    if (!pool_thread.joinable()) {
+        // keep the tiles of about two frames free at all times (a frame region is (W/256 + 2) x (H/256 + 2) tiles at scale 1)
+        pool_low = std::max<size_t>(32, 2 * (size_t)(cam[0] / kEle + 2) * (size_t)(cam[1] / kEle + 2));
+        pool_thread = std::thread([this] { pool_filler(); });
+    }
     return M2D_OK;
 }
 
@@ -385,7 +406,8 @@ int m2d_map::ensure_weight_images(int w, int h) {
 // Grow the pool until at least n tiles are free (128 MiB slabs).  Called from prepare() for the prepared grid, so
 // that streaming feed() calls do not hit a cudaMalloc (a multi-millisecond stall) in steady state.
 int m2d_map::reserve_tiles(size_t n) {
-    while (free_tiles.size() < n) {
+    for (;;) {
+        { std::lock_guard<std::mutex> lk(pool_mu); if (free_tiles.size() >= n) return M2D_OK; }
         size_t per_chunk = std::max<size_t>(16, ((size_t)128 << 20) / tile_bytes);
         void* c = nullptr;
         cudaError_t e = cudaMalloc(&c, per_chunk * tile_bytes);
@@ -394,17 +416,45 @@ int m2d_map::reserve_tiles(size_t n) {
             cudaGetLastError();
             return M2D_ERR_NOMEM;
         }
+        std::lock_guard<std::mutex> lk(pool_mu);
         chunks.push_back(c);
         for (size_t i = per_chunk; i-- > 0;) free_tiles.push_back((uint8_t*)c + i * tile_bytes);
     }
-    return M2D_OK;
+}
+
+void m2d_map::pool_filler() {
+    cudaSetDevice(cfg.device);
+    std::unique_lock<std::mutex> lk(pool_mu);
+    for (;;) {
+        pool_cv.wait(lk, [&] { return pool_stop || (!pool_failed && free_tiles.size() < pool_low); });
+        if (pool_stop) return;
+        // a cudaMalloc stalls concurrent launches of the feed thread for a millisecond or two whatever its size: once the map
+        // has grown past the first slabs, grow in 512 MiB steps so that fewer than 1 % of streamed frames ever meet one
+        const size_t per_chunk = std::max<size_t>(16, ((size_t)(chunks.size() >= 8 ? 512 : 128) << 20) / tile_bytes);
+        lk.unlock();
+        void* c = nullptr;
+        cudaError_t e = cudaMalloc(&c, per_chunk * tile_bytes);   // the slow part, off the feed path
+        lk.lock();
+        if (e != cudaSuccess) { cudaGetLastError(); pool_failed = true; continue; }   // the feed path will report NOMEM if it runs dry
+        chunks.push_back(c);
+        for (size_t i = per_chunk; i-- > 0;) free_tiles.push_back((uint8_t*)c + i * tile_bytes);
+    }
 }
 
 int m2d_map::alloc_tile(uint8_t** out) {
-    if (free_tiles.empty()) {
-        int rc = reserve_tiles(1);
-        if (rc != M2D_OK) return rc;
+    {
+        std::lock_guard<std::mutex> lk(pool_mu);
+        if (!free_tiles.empty()) {
+            *out = free_tiles.back();
+            free_tiles.pop_back();
+            tiles_in_use++;
+            if (free_tiles.size() < pool_low) pool_cv.notify_one();
+            return M2D_OK;
+        }
     }
+    int rc = reserve_tiles(1);   // the filler fell behind (a large batch): allocate here
+    if (rc != M2D_OK) return rc;
+    std::lock_guard<std::mutex> lk(pool_mu);
     *out = free_tiles.back();
     free_tiles.pop_back();
     tiles_in_use++;
@@ -464,10 +514,21 @@ int m2d_map::sync() {
 
 int m2d_map::reset() {
     CU(cudaSetDevice(cfg.device));
-    CU(cudaStreamSynchronize(stream));
-    for (int i = 0; i < kCtx; i++) ctx[i].busy = false;
-    for (uint8_t*& t : table)
-        if (t) { free_tiles.push_back(t); t = nullptr; tiles_in_use--; }
+    // No device synchronisation: the tiles go back to the pool while the kernels that last touched them may still be in
+    // flight, and that is safe because whoever gets a recycled tile (a later group, as a FRESH tile) only ever touches it
+    // from kernels that are stream-ordered behind those (decide chain -> image chain -> Laplacian chain of the handle;
+    // weight planes and Laplacian planes are disjoint byte ranges of a tile).  So a reset()+feed_batch() sequence keeps
+    // the GPU busy across the reset: the host prepares the next group while the previous one is still being fused.
+    // With counters or per-kernel timing on, the device counters are cleared here, so everything must have landed.
+    if (cfg.collect_stats || profiling) {
+        CU(cudaStreamSynchronize(stream));
+        for (int i = 0; i < kCtx; i++) ctx[i].busy = false;
+    }
+    {
+        std::lock_guard<std::mutex> lk(pool_mu);
+        for (uint8_t*& t : table)
+            if (t) { free_tiles.push_back(t); t = nullptr; tiles_in_use--; }
+    }
     std::fill(changed.begin(), changed.end(), 0);
     CU(cudaMemsetAsync(d_stats, 0, 32 * sizeof(unsigned long long), stream));
     memset(&stats, 0, sizeof stats);
@@ -492,6 +553,7 @@ int m2d_map::feed_frames(int n, const uint8_t* base, size_t frame_stride, int w,
     if (stride < (size_t)w * 3) return M2D_ERR_ARG;
     CU(cudaSetDevice(cfg.device));
     { int rc = ensure_weight_images(w, h); if (rc != M2D_OK) return rc; }
+    struct EventScope { cudaEvent_t& e; ~EventScope() { e = nullptr; } } event_scope{input_event};   // one feed call consumes the event
     int K = group_size(w, h, on_device);
     if (n > K) K = (n + (n + K - 1) / K - 1) / ((n + K - 1) / K);   // equal-sized groups: 500 frames at K = 480 -> 250 + 250
     int worst = M2D_OK;
@@ -518,6 +580,7 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
         m2d_map* m; std::vector<std::pair<int, int>> abs; bool armed = true;
         ~FreshGuard() {
             if (!armed) return;
+            std::lock_guard<std::mutex> lk(m->pool_mu);
             for (auto& a : abs) {
                 int x = a.first - m->org_x, y = a.second - m->org_y;
                 if (x < 0 || y < 0 || x >= m->g.w || y >= m->g.h) continue;
@@ -732,6 +795,7 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
         p.wmap = reinterpret_cast<uint16_t*>(c.d_scratch + off_wmap); p.wmap_stride = wmap_stride;
         make_reach_table(levels, p.reach_lo, p.reach_hi);
         make_weight_reach_table(levels, p.wreach_lo, p.wreach_hi);
+        p.use_tma = use_tma ? 1 : 0;
         p.cull = (weight_cull && !cfg.collect_stats) ? 1 : 0;   // the win counters follow the sequential semantics: no culling then
     }
 
@@ -771,6 +835,7 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
         // 4. image work in the needed cells, back on the context's stream (only here are the frames' pixels needed)
         CU(cudaStreamWaitEvent(c.stage, c.decided, 0));
         if (!on_device) CU(cudaStreamWaitEvent(c.stage, c.copied, 0));
+        if (input_event) CU(cudaStreamWaitEvent(c.stage, input_event, 0));   // frames still travelling (e.g. NCCL halo exchange)
         LAUNCHKS(M2D_K_MBS_WARP, c.stage, launch_mbs_warp(p, ctas, c.stage));
         for (int l = 0; l + 1 < levels; l++) LAUNCHKS(M2D_K_MBS_PYR, c.stage, launch_mbx_pyrdown(p, 1, l, ctas, c.stage));
         CU(cudaEventRecord(c.staged, c.stage));
@@ -780,6 +845,7 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
     } else if (type == M2D_TYPE_MULTIBAND) {
         // full-grid pyrDown while a level is big enough; the small deep levels go through one tail launch
         int l = 0;
+        if (input_event) CU(cudaStreamWaitEvent(c.stage, input_event, 0));
         LAUNCHKS(M2D_K_MB_WARP, c.stage, launch_mb_warp(p, c.stage));
         // (a level goes to the tail only when its output is small: <= 16 K px per frame, i.e. one 1024-thread CTA's worth)
         auto small_level = [&](int lv) { long long nd = kEle >> (lv + 1); return (long long)max_wnx * nd * max_wny * nd <= 16384; };
@@ -791,6 +857,7 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
         if (weights_first) { CU(cudaEventRecord(dense_done, stream)); dense_pending = true; }
     } else {
         // weighted mode samples the caller's BGR8 frames in place (plus the alpha plane): no packed copy
+        if (input_event) CU(cudaStreamWaitEvent(c.stage, input_event, 0));
         CU(cudaEventRecord(c.staged, c.stage));
         CU(cudaStreamWaitEvent(stream, c.staged, 0));
         LAUNCHK(M2D_K_WEIGHTED, launch_weighted_group(p, stream));
@@ -1250,6 +1317,12 @@ int m2d_set_stream(m2d_handle h, void* s) {
     return M2D_OK;
 }
 int m2d_reset(m2d_handle h) { API_LOCK(h); return h ? h->reset() : M2D_ERR_ARG; }
+int m2d_set_input_event(m2d_handle h, void* cuda_event) {
+    API_LOCK(h);
+    if (!h) return M2D_ERR_ARG;
+    h->input_event = (cudaEvent_t)cuda_event;
+    return M2D_OK;
+}
 
 int m2d_get_grid(m2d_handle h, int* w, int* ht, double* mn, double* mx, double* lp) {
     API_LOCK(h);
@@ -1338,6 +1411,7 @@ int m2d_drop_tiles_rect(m2d_handle h, const int* rect_abs, int* n_dropped) {
     if (!m.valid) return M2D_ERR_STATE;
     if (cudaSetDevice(m.cfg.device) != cudaSuccess || cudaStreamSynchronize(m.stream) != cudaSuccess) return M2D_ERR_CUDA;
     int n = 0;
+    std::lock_guard<std::mutex> lk(m.pool_mu);
     for (int y = std::max(rect_abs[1] - m.org_y, 0); y < std::min(rect_abs[3] - m.org_y, m.g.h); y++)
         for (int x = std::max(rect_abs[0] - m.org_x, 0); x < std::min(rect_abs[2] - m.org_x, m.g.w); x++) {
             uint8_t*& t = m.table[(size_t)y * m.g.w + x];

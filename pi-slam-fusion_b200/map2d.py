@@ -45,7 +45,7 @@ class Stats(C.Structure):
 
 
 EXPORTS = ["m2d_config_default", "m2d_create", "m2d_destroy", "m2d_prepare", "m2d_feed", "m2d_feed_device",
-           "m2d_feed_batch", "m2d_feed_poses", "m2d_plan_rects", "m2d_set_shard", "m2d_sync", "m2d_queue_size", "m2d_set_stream", "m2d_reset", "m2d_get_grid",
+           "m2d_feed_batch", "m2d_feed_poses", "m2d_plan_rects", "m2d_set_shard", "m2d_sync", "m2d_queue_size", "m2d_set_stream", "m2d_reset", "m2d_set_input_event", "m2d_get_grid",
            "m2d_last_rect", "m2d_get_tile", "m2d_get_image", "m2d_save", "m2d_tile_bytes", "m2d_tile_state_bytes", "m2d_tile_count",
            "m2d_export_tiles", "m2d_import_tiles", "m2d_export_tiles_rect", "m2d_drop_tiles_rect", "m2d_tile_bbox", "m2d_get_image_rect", "m2d_poll_changed", "m2d_get_tile_image", "m2d_save_state", "m2d_load_state", "m2d_get_stats", "m2d_last_error",
            "m2d_launch_count", "m2d_profile", "m2d_get_kernel_times", "m2d_alloc_host", "m2d_free_host", "m2d_compute_bounds",
@@ -94,6 +94,7 @@ def lib():
     L.m2d_queue_size.argtypes = [vp]
     L.m2d_set_stream.argtypes = [vp, vp]
     L.m2d_reset.argtypes = [vp]
+    L.m2d_set_input_event.argtypes = [vp, vp]
     L.m2d_get_grid.argtypes = [vp, ip, ip, dp, dp, dp]
     L.m2d_last_rect.argtypes = [vp, ip]
     L.m2d_get_tile.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp]
@@ -375,6 +376,10 @@ class Map2D:
 
     def reset(self):
         return self._check(lib().m2d_reset(self._h))
+
+    def set_input_event(self, cuda_event):
+        """The next feed call's pixel-reading kernels wait for this cudaEvent_t (e.g. torch.cuda.Event().cuda_event)."""
+        return self._check(lib().m2d_set_input_event(self._h, cuda_event))
 
     def set_stream(self, cuda_stream):
         return self._check(lib().m2d_set_stream(self._h, cuda_stream))

@@ -242,11 +242,11 @@ class ShardedMap2D:
         return buf, buf[lo - b0:hi - b0]
 
     def feed_all_owned(self, plan, buf, poses, w, h):
-        """One pass over the whole sequence.  Halo frames come by P2P from the ranks they are resident on, in two
-        batched isend/irecv groups posted up front: first the transfers that fill receivers' LOWER halos (frames
-        that precede the receiver's own ones in feed order), then the UPPER halos.  The rank feeds in global order —
-        poses only outside its hull, pixels inside — and waits for the upper halos only after it has enqueued its
-        lower halo and its own frames, so that transfer overlaps the fusion."""
+        """One pass over the whole sequence.  Halo frames come by P2P from the ranks they are resident on (batched
+        isend/irecv groups posted up front).  The rank feeds in global order -- poses only outside its hull, pixels
+        inside, the whole hull in ONE m2d_feed_batch (large groups cull best) -- and the library's pixel-reading kernels
+        wait on the device for the transfer (m2d_set_input_event), so it overlaps the bounds / weight / decide stages,
+        which need poses only."""
         poses = np.ascontiguousarray(poses, np.float64).reshape(-1, 7)
         n = len(poses)
         assert n == plan.n
@@ -263,31 +263,33 @@ class ShardedMap2D:
                     ops.append(dist.P2POp(dist.irecv, buf[lo - b0:hi - b0], src))
             return dist.batch_isend_irecv(ops) if ops else []
 
-        def wait(reqs):
-            for req in reqs:
-                req.wait()
-            if reqs and self.cuda:
-                torch.cuda.current_stream().synchronize()  # the library consumes buf on its own stream
-
         first, second = post(True), post(False)
         a, b = plan.hull[self.rank]
-        split = min(max(plan.resident[self.rank][1], a), b)   # [a,split): lower halo + own frames, [split,b): upper halo
         res = np.zeros(n, np.int32)
         if a > 0:
             res[:a] = self.map.feed_poses(poses[:a])
-        wait(first)
-        if split > a:
-            res[a:split] = self.map.feed_batch(buf[a - b0:].data_ptr(), split - a, w * h * 3, w, h, w * 3, poses[a:split], self.cuda)
-        wait(second)
-        if b > split:
-            res[split:b] = self.map.feed_batch(buf[split - b0:].data_ptr(), b - split, w * h * 3, w, h, w * 3, poses[split:b], self.cuda)
+        reqs = list(first) + list(second)
+        for req in reqs:
+            req.wait()               # NCCL: the CURRENT STREAM waits for the transfer, the host does not
+        ev = None
+        if reqs and self.cuda:
+            if hasattr(self.map, "set_input_event"):
+                # the library reads pixels on its own streams: its image kernels wait for this event, while bounds, weights
+                # and winners (poses only) run at once -- the halo transfer hides behind them
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream())
+                self.map.set_input_event(ev.cuda_event)
+            else:
+                torch.cuda.current_stream().synchronize()
+        if b > a:
+            res[a:b] = self.map.feed_batch(buf[a - b0:].data_ptr(), b - a, w * h * 3, w, h, w * 3, poses[a:b], self.cuda)
         if b < n:
             res[b:] = self.map.feed_poses(poses[b:])
         self.map.sync()
         return res
 
     # ---- sharded save: every rank collapses its own strip (+ halo rows from its neighbours); nobody holds the whole map ----
-    def save_sharded(self, axis, span, origin, levels=None, out=None, gather=False):
+    def save_sharded(self, axis, span, origin, levels=None, out=None, gather=False, chunk=None, sink=None):
         """The sharded half of Map2D::save (MultiBandMap2DCPU.cpp:779-847 / Map2DCPU.cpp:523-564) for the contiguous
         strips align_strips() installs (rank r owns absolute tile coordinates [origin + r*span, origin + (r+1)*span)
         along `axis`).  Collective.  Steps: all ranks agree on the global bbox of touched tiles (one tiny all_gather);
@@ -297,7 +299,9 @@ class ShardedMap2D:
         Returns (strip, rect_abs): strip = uint8 tensor [h, w, channels] on the rank's device (CUDA) or CPU (gloo), or None
         if the rank owns no row of the bbox, written into `out` (a flat uint8 tensor, grown as needed) if given;
         rect_abs = the strip's absolute tile rect.  gather=True additionally assembles the whole mosaic on rank 0
-        (returned there instead of the strip; only sensible when it fits one device)."""
+        (returned there instead of the strip; only sensible when it fits one device).  chunk=c collapses the strip c tile
+        rows (columns) at a time and hands every piece to sink(tensor, rect_abs) -- a strip larger than the device's free
+        memory (cfg4: 15 GB of BGRA per rank) is streamed to the host through one reusable buffer."""
         dev = torch.device("cuda", self.device) if self.cuda else torch.device("cpu")
         levels = levels or getattr(self.map, "levels", 1)
         k = max(1, -(-((1 << levels) - 2) // 256)) if self.type == 3 else 0
@@ -366,14 +370,24 @@ class ShardedMap2D:
             halos = [rect(max(lo - k, g0), lo), rect(hi, min(hi + k, g1))]
         strip, srect = None, None
         if hi > lo:
-            win, srect = rect(max(lo - k, g0), min(hi + k, g1)), rect(lo, hi)
+            srect = rect(lo, hi)
             cn = 3 if self.type == 3 else 4
-            hpx, wpx = (srect[3] - srect[1]) * 256, (srect[2] - srect[0]) * 256
-            need = hpx * wpx * cn
-            if out is None or out.numel() < need:
-                out = torch.empty(need, dtype=torch.uint8, device=dev)
-            self.map.get_image_rect(win, srect, out.data_ptr(), self.cuda)
-            strip = out[:need].view(hpx, wpx, cn)
+            step = chunk if (chunk and sink) else (hi - lo)
+            for c0 in range(lo, hi, step):
+                c1 = min(c0 + step, hi)
+                win, crop = rect(max(c0 - k, g0), min(c1 + k, g1)), rect(c0, c1)
+                hpx, wpx = (crop[3] - crop[1]) * 256, (crop[2] - crop[0]) * 256
+                need = hpx * wpx * cn
+                if out is None:
+                    out = getattr(self, "_save_buf", None)
+                if out is None or out.numel() < need:
+                    out = self._save_buf = torch.empty(need, dtype=torch.uint8, device=dev)   # cached: cudaMalloc of GBs is slow
+                self.map.get_image_rect(win, crop, out.data_ptr(), self.cuda)
+                strip = out[:need].view(hpx, wpx, cn)
+                if sink:
+                    sink(strip, crop)
+            if chunk and sink:
+                strip = None
         for r_ in halos:
             if r_[2] > r_[0] and r_[3] > r_[1]:
                 self.map.drop_tiles_rect(r_)
@@ -473,7 +487,9 @@ def _strip_run(args, rank, world, local_rank, mode, seq, label, steps, warm, che
     plan = DeliveryPlan(rects, axis, span, world, even_split(n, world), origin)
     buf, mine = sm.alloc_owned_buffer(plan, W, H)
     lo, hi = plan.resident[rank]
-    mine.copy_(BB.device_frames(torch, seq, lo, hi, dev))   # inputs resident in HBM before the timed region, on the GPU that "captured" them
+    for c0 in range(lo, hi, 64):   # inputs resident in HBM before the timed region, on the GPU that "captured" them
+        c1 = min(c0 + 64, hi)
+        mine[c0 - lo:c1 - lo].copy_(BB.device_frames(torch, seq, c0, c1, dev))
     torch.cuda.synchronize()
 
     def step():
@@ -501,17 +517,24 @@ def _strip_run(args, rank, world, local_rank, mode, seq, label, steps, warm, che
     launches = float(sm.map.launch_count() - l0) / steps
     clocks = sampler.result()
 
-    # ---- sharded save: warm once (NCCL connections, collapse buffers), then time
-    strip, srect = sm.save_sharded(axis, span, origin)
-    nbytes = int(strip.numel()) if strip is not None else 0
-    host = torch.empty(max(nbytes, 1), dtype=torch.uint8, pin_memory=True)
-    out_dev = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
+    # ---- sharded save: warm once (NCCL connections, collapse buffers), then time.  The strip is collapsed 16 tile rows
+    # at a time and streamed to the host through one reusable pinned buffer (a rank's strip may exceed its free HBM: cfg4)
+    sink_state = {"host": None, "bytes": 0}
+
+    def sink(t, rect_abs):
+        nb = int(t.numel())
+        if sink_state["host"] is None or sink_state["host"].numel() < nb:
+            sink_state["host"] = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
+        sink_state["host"][:nb].copy_(t.reshape(-1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the device buffer is reused by the next piece
+        sink_state["bytes"] += nb
 
     def save():
-        st, _ = sm.save_sharded(axis, span, origin, out=out_dev)
-        if st is not None:
-            host[:nbytes].copy_(st.view(-1), non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+        sink_state["bytes"] = 0
+        sm.save_sharded(axis, span, origin, chunk=16, sink=sink)
+
+    save()
+    nbytes = sink_state["bytes"]
 
     dist.barrier()
     torch.cuda.synchronize()
@@ -602,7 +625,8 @@ def _strip_run(args, rank, world, local_rank, mode, seq, label, steps, warm, che
                           "d2h_bytes_per_step": int(hull[1].item()), "ms_per_step": float(tmax[2]),
                           "what": "per rank: H2D of its own pinned host frames, halo exchange, m2d_feed_batch, sharded save (m2d_get_image_rect of its strip) + D2H of the strip"}
     sm.map.close()
-    del buf, mine, out_dev, host
+    del buf, mine, sink_state
+    sm._save_buf = None
     torch.cuda.empty_cache()
     return out
 
@@ -631,7 +655,7 @@ def bench_weak(args, rank, world, local_rank):
     seq = synth.Sequence(n, W, H, seed=seed, fpl=fpl)
     warm = max(args.warmup, 3)
     head = _strip_run(args, rank, world, local_rank, mode, seq, "headline", args.steps, warm, True, not args.no_e2e, B, m2d)
-    other = cfg3 = None
+    other = cfg3 = cfg4 = None
     if not args.only:
         other = _strip_run(args, rank, world, local_rank, other_mode, seq, other_mode, max(3, args.steps // 2), 3, True, not args.no_e2e, B, m2d)
         if args.cfg3_frames > 0:
@@ -639,6 +663,13 @@ def bench_weak(args, rank, world, local_rank):
             n3 = args.cfg3_frames
             seq3 = synth.Sequence(n3, w3, h3, seed=s3)
             cfg3 = _strip_run(args, rank, world, local_rank, "multiband", seq3, "cfg3", max(2, min(args.steps, 5)), 2, False, False, B, m2d, want_sha=True)
+        n4 = args.cfg4_frames if args.cfg4_frames >= 0 else (B.CFG4[1] if world >= 8 else 0)
+        if n4 > 0:
+            # BASELINE configs[3]: weighted fusion of a 5000-frame 4000x3000 survey with 30 % / 30 % overlap: ~470k tiles =
+            # ~120 GB of BGRA map state, more than one GPU's tile budget; sharded, saved strip by strip, never gathered
+            _, _, w4, h4, s4, _ = B.CFG4
+            seq4 = synth.Sequence(n4, w4, h4, seed=s4, along=0.7, cross=0.7)
+            cfg4 = _strip_run(args, rank, world, local_rank, "weighted", seq4, "cfg4", 3, 2, False, False, B, m2d)
     if rank == 0:
         cfg = B.config_of(mode, n, W, H, seed, world)
         cfg["frames_per_gpu"] = per_gpu
@@ -658,6 +689,12 @@ def bench_weak(args, rank, world, local_rank):
             cfg3["scaling"] = "strong"
             cfg3["n_gpus"] = world
             line["cfg3"] = cfg3
+        if cfg4:
+            cfg4["workload"] = "cfg4: Map2DCPU weighted fusion, %d synthetic %dx%d frames, 30 %%/30 %% overlap (seed %d): map state %.1f GB across %d GPUs" % (
+                seq4.n, seq4.w, seq4.h, B.CFG4[4], cfg4["tiles"] * 262144 / 1e9, world)
+            cfg4["scaling"] = "strong"
+            cfg4["n_gpus"] = world
+            line["cfg4"] = cfg4
         os.write(saved_stdout, (json.dumps(line) + "\n").encode())
     dist.destroy_process_group()
 
