@@ -37,6 +37,15 @@ public:
     /* type: Map2D::TypeCPU / TypeGPU (weighted) or TypeMultiBandCPU.  The svar keys the CPU classes read
      * (Map2DCPU.cpp:75,246; MultiBandMap2DCPU.cpp:228,235,260,444,840) are copied into the config once. */
     explicit Map2DB200(int type, bool thread = true, int device = 0) : _h(NULL), _thread(thread) {
+        std::vector<int> devices(1, device);
+        init(type, thread, devices);
+    }
+    /* Several GPUs behind the same object (one host process, tiles sharded over the devices): m2d_create_multi. */
+    Map2DB200(int type, bool thread, const std::vector<int>& devices) : _h(NULL), _thread(thread) { init(type, thread, devices); }
+    virtual ~Map2DB200() { m2d_destroy(_h); }
+
+private:
+    void init(int type, bool thread, const std::vector<int>& devices) {
         m2d_config cfg;
         m2d_config_default(&cfg);
         cfg.scale = svar.GetDouble("Map2D.Scale", 1);
@@ -46,11 +55,12 @@ public:
         cfg.force_float = svar.GetInt("MultiBandMap2DCPU.ForceFloat", 0);
         cfg.background = svar.GetInt("Result.BackGroundColor");
         cfg.thread = thread ? 1 : 0;
-        cfg.device = device;
-        int rc = m2d_create(type, &cfg, &_h);
+        cfg.device = devices.empty() ? 0 : devices[0];
+        int rc = devices.size() > 1 ? m2d_create_multi(type, &cfg, (int)devices.size(), &devices[0], &_h) : m2d_create(type, &cfg, &_h);
         if (rc != M2D_OK) std::cerr << "Map2DB200: m2d_create failed (" << rc << "); no CPU fallback is taken.\n";
     }
-    virtual ~Map2DB200() { m2d_destroy(_h); }
+
+public:
 
     virtual bool prepare(const pi::SE3d& plane, const PinHoleParameters& camera,
                          const std::deque<std::pair<cv::Mat, pi::SE3d> >& frames) {

@@ -99,6 +99,16 @@ void m2d_config_default(m2d_config* cfg);
 
 /* Map2D::create — Map2D.cpp:51-66. type NONE/RENDER -> M2D_ERR_UNSUPPORTED and *out = NULL. */
 int m2d_create(int type, const m2d_config* cfg, m2d_handle* out);
+/* Multi-GPU behind the boundary: ONE host process (the reference's host is one process: Map2D::create, Map2D.cpp:51-66), one
+ * sub-map per device, tiles sharded by spatial ownership (block-cyclic strips of cfg->shard_span tiles along
+ * cfg->shard_axis, on absolute tile coordinates).  The returned handle takes the same calls as a single-device one:
+ * m2d_prepare / m2d_feed* (every device sees every pose and copies -- or, for device-resident frames, reads in place over
+ * NVLink peer access -- only the frames under which it owns tiles; the devices fuse concurrently) / m2d_sync /
+ * m2d_queue_size / m2d_reset / m2d_get_grid / m2d_last_rect / m2d_get_tile / m2d_poll_changed / m2d_get_image / m2d_save
+ * (raw tiles are read to the first device over NVLink and collapsed there) / m2d_ingest_* / m2d_destroy.  Calls that only
+ * make sense on one shard (set_shard, export/import, get_image_rect, state files, ...) return M2D_ERR_UNSUPPORTED.
+ * n_devices == 1 is m2d_create on that device.  Requires peer access between the devices. */
+int m2d_create_multi(int type, const m2d_config* cfg, int n_devices, const int* devices, m2d_handle* out);
 void m2d_destroy(m2d_handle h);
 
 /* Map2D::prepare — only the poses of the prepare-frames are used to lay out the tile grid

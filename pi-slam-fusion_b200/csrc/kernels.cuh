@@ -39,6 +39,12 @@ struct TileEntry {
     short rtx, rty;            // tile position inside that frame's region
 };
 
+struct EntryRef {                // per (tile entry, level): where the frame's weight plane starts under the tile (kernels_wf.cu)
+    unsigned long long base;     // address of the weight of the tile's px (0, 0) at that level
+    int stride;                  // row pitch of the plane in px (window width in tiles * tile side)
+    int cell0;                   // index into the per-frame cell flag arrays of the tile's cell (0, 0) at that level
+};
+
 struct GroupParams {
     const FrameJob* jobs;
     const TileWork* tiles;
@@ -70,6 +76,7 @@ struct GroupParams {
     int wmap_stride;           // >= TileLayout::px_off[levels], even
     unsigned char reach_lo[6][6], reach_hi[6][6];    // image: [win level m][Gaussian level k] in cells, 0xFF = none (make_reach_table)
     unsigned char wreach_lo[6][6], wreach_hi[6][6];  // weights: [competitive level m][weight level k]   (make_weight_reach_table)
+    EntryRef* etable;          // [n_entries][levels]
     int use_tma;               // pyrDown 0 -> 1 through TMA-staged shared-memory patches (M2D_TMA=0: register-window kernel)
     int cull;                  // 0: every entry of a tile is treated as competitive (collect_stats, M2D_WCULL=0)
 };
@@ -113,6 +120,7 @@ cudaError_t launch_mb_pyrtail(const GroupParams& p, int l_first, cudaStream_t st
 cudaError_t launch_mb_select(const GroupParams& p, const TileLayout& lay, cudaStream_t stream);
 // weights-first multi-band pipeline (kernels_wf.cu)
 cudaError_t launch_mbc_bounds(const GroupParams& p, const TileLayout& lay, cudaStream_t stream);          // competitive cells
+cudaError_t launch_mbc_entry_table(const GroupParams& p, int n_entries, cudaStream_t stream);
 cudaError_t launch_mbx_propagate(const GroupParams& p, int image, cudaStream_t stream);                   // need flags + work lists
 cudaError_t launch_mbw_warp(const GroupParams& p, int ctas, cudaStream_t stream);                         // level-0 weights, listed cells
 cudaError_t launch_mbx_pyrdown(const GroupParams& p, int image, int level, int ctas, cudaStream_t stream); // l -> l+1, listed cells

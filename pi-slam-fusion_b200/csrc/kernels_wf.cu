@@ -659,6 +659,30 @@ cudaError_t launch_mbx_pyrdown(const GroupParams& p, int image, int level, int c
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// 1c. entry table: for every (tile entry, level) the address of the frame's weight plane at the tile's origin and its row
+// pitch, so that the decide stage reaches a candidate's weights with ONE dependent load (mask -> table -> weights) instead
+// of three (mask -> entry -> frame job -> weights)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mbc_entry_table_kernel(const __grid_constant__ GroupParams p, int n_entries) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n_entries * p.levels) return;
+    const int e = i / p.levels, l = i - e * p.levels, n = kEle >> l;
+    const TileEntry E = p.entries[e];
+    const FrameJob& J = p.jobs[E.frame];
+    const int st = J.wnx * n;
+    EntryRef r;
+    r.base = reinterpret_cast<unsigned long long>(p.scratch + J.w_off[l]) + 4ull * ((size_t)((E.rty - J.wy) * n) * st + (size_t)((E.rtx - J.wx) * n));
+    r.stride = st;
+    r.cell0 = (int)(((size_t)E.frame * p.levels + l) * p.cells_max + (size_t)((E.rty - J.wy) * 8) * (J.wnx * 8) + (E.rtx - J.wx) * 8);   // flag index of the tile's cell (0,0)
+    p.etable[i] = r;
+}
+cudaError_t launch_mbc_entry_table(const GroupParams& p, int n_entries, cudaStream_t stream) {
+    if (n_entries == 0) return cudaSuccess;
+    mbc_entry_table_kernel<<<(n_entries * p.levels + 255) / 256, 256, 0, stream>>>(p, n_entries);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // 2. decide, tile-centric and cell-aligned: per px of the tile, scan the COMPETITIVE entries of its cell in feed order
 // and keep the last one whose weight is >= everything before it (state included; a fresh tile starts at -inf so the
 // first entry copies unconditionally, MultiBandMap2DCPU.cpp:498-504) -- exactly what the sequential `if (srcW >= dstW)`
@@ -691,10 +715,9 @@ __global__ void __launch_bounds__(256) mbs_decide_kernel(const __grid_constant__
         while (bits) {
             const int i = w * 32 + __ffs(bits) - 1;
             bits &= bits - 1;
-            const TileEntry E = p.entries[T.first + i];
-            const FrameJob& J = p.jobs[E.frame];
-            const int st = J.wnx * n;
-            const float* qp = reinterpret_cast<const float*>(p.scratch + J.w_off[l]) + (size_t)((E.rty - J.wy) * n + py) * st + (size_t)((E.rtx - J.wx) * n + px);
+            const EntryRef R = p.etable[(size_t)(T.first + i) * p.levels + l];
+            const int st = R.stride;
+            const float* qp = reinterpret_cast<const float*>(R.base) + (size_t)py * st + px;
             const unsigned cw = !(T.fresh && i == 0);
             if (quad) {
                 const float2 t0 = *reinterpret_cast<const float2*>(qp), t1 = *reinterpret_cast<const float2*>(qp + st);
@@ -740,9 +763,8 @@ __global__ void __launch_bounds__(256) mbs_decide_kernel(const __grid_constant__
         for (int k2 = 0; k2 < k; k2++) dup |= seen[k2] == best[k];
         seen[k] = best[k];
         if (dup) continue;
-        const TileEntry E = p.entries[T.first + best[k]];
-        const FrameJob& J = p.jobs[E.frame];
-        uint8_t* wf = p.win + cell_base(p, E.frame, l) + (size_t)((E.rty - J.wy) * 8 + ccy) * (J.wnx * 8) + ((E.rtx - J.wx) * 8 + ccx);
+        const EntryRef R = p.etable[(size_t)(T.first + best[k]) * p.levels + l];
+        uint8_t* wf = p.win + (size_t)(unsigned)R.cell0 + (size_t)ccy * (R.stride / n * 8) + ccx;   // stride / n = window width in tiles
         if (!*wf) *wf = 1;
     }
 }

@@ -103,6 +103,14 @@ constexpr int kIngestBatch = 16;       // frames the worker hands to feed() at o
 constexpr int kIngestSpare = 4;        // slots for producers that are mid-copy
 
 struct m2d_map {
+    // Multi-device handle (m2d_create_multi): ONE host process, one sub-handle per GPU, tiles sharded by spatial ownership
+    // (block-cyclic strips, m2d_config.shard_axis / shard_span).  The top handle owns no CUDA resources; prepare / feed /
+    // sync / reset / save / getters are routed to the sub-handles.  Peer access is enabled between the devices, so a
+    // device-resident frame is sampled in place over NVLink by every GPU that owns tiles under it, and the save gathers raw
+    // tiles to the first device with plain peer loads.
+    std::vector<m2d_map*> subs;
+    void mirror() { if (!subs.empty()) { g = subs[0]->g; valid = subs[0]->valid; min_z = subs[0]->min_z; max_z = subs[0]->max_z; length_pixel = subs[0]->length_pixel;
+                                          org_x = subs[0]->org_x; org_y = subs[0]->org_y; stats = subs[0]->stats; memcpy(last_rect, subs[0]->last_rect, sizeof last_rect); } }
     int type = 0;
     m2d_config cfg{};
     int band_num = 5, levels = 6;
@@ -195,6 +203,7 @@ struct m2d_map {
     bool tile_bbox(int& x0, int& y0, int& x1, int& y1) const;
     int get_image(uint8_t* out, int* w, int* h, int* channels, int* tmx, int* tmy);
     int collapse_window(uint8_t* out, bool out_on_device, const int win[4], const int crop[4], int* w, int* h, int* channels);
+    int multi_get_image(uint8_t* out, int* w, int* h, int* channels, int* tmx, int* tmy);
     int queue_size();
     int sync();
     int reset();
@@ -250,6 +259,11 @@ int m2d_map::init() {
 }
 
 void m2d_map::release() {
+    if (!subs.empty()) {
+        for (m2d_map* sub : subs) { sub->release(); delete sub; }
+        subs.clear();
+        return;
+    }
     cudaSetDevice(cfg.device);
     if (pool_thread.joinable()) {
         { std::lock_guard<std::mutex> lk(pool_mu); pool_stop = true; }
@@ -285,6 +299,12 @@ void m2d_map::release() {
 
 // Map2DPrepare::prepare (Map2D.cpp:32-49) + Map2DCPUData::prepare (Map2DCPU.cpp:44-92 / MultiBandMap2DCPU.cpp:199-255)
 int m2d_map::prepare(const double* plane7, const double* cam, int n, const double* poses) {
+    if (!subs.empty()) {
+        int rc = M2D_OK;
+        for (m2d_map* sub : subs) { int r = sub->prepare(plane7, cam, n, poses); if (r != M2D_OK) { rc = r; err = sub->err; } }
+        mirror();
+        return rc;
+    }
     if (n <= 0 || !poses || cam[0] <= 0 || cam[1] <= 0 || cam[2] == 0 || cam[3] == 0) return M2D_REJECTED;
     // cv::remap keeps source coordinates in 16-bit maps (saturate_cast<short>); the kernels rely on sw, sh <= 32767
     if (cam[0] > 32767 || cam[1] > 32767) { err = "camera larger than 32767 px: unsupported (OpenCV's remap maps are 16-bit)"; return M2D_ERR_UNSUPPORTED; }
@@ -495,6 +515,7 @@ int m2d_map::group_size(int w, int h, bool on_device) const {
 }
 
 int m2d_map::queue_size() {
+    if (!subs.empty()) { int q = 0; for (m2d_map* sub : subs) q = std::max(q, sub->queue_size()); return q; }
     int q = 0;
     for (int i = 0; i < kCtx; i++) {
         GroupCtx& c = ctx[i];
@@ -506,6 +527,7 @@ int m2d_map::queue_size() {
 }
 
 int m2d_map::sync() {
+    if (!subs.empty()) { int rc = M2D_OK; for (m2d_map* sub : subs) { int r = sub->sync(); if (r != M2D_OK) { rc = r; err = sub->err; } } return rc; }
     CU(cudaSetDevice(cfg.device));
     CU(cudaStreamSynchronize(stream));
     for (int i = 0; i < kCtx; i++) ctx[i].busy = false;
@@ -513,6 +535,7 @@ int m2d_map::sync() {
 }
 
 int m2d_map::reset() {
+    if (!subs.empty()) { int rc = M2D_OK; for (m2d_map* sub : subs) { int r = sub->reset(); if (r != M2D_OK) { rc = r; err = sub->err; } } mirror(); return rc; }
     CU(cudaSetDevice(cfg.device));
     // No device synchronisation: the tiles go back to the pool while the kernels that last touched them may still be in
     // flight, and that is safe because whoever gets a recycled tile (a later group, as a FRESH tile) only ever touches it
@@ -538,6 +561,20 @@ int m2d_map::reset() {
 
 int m2d_map::feed_frames(int n, const uint8_t* base, size_t frame_stride, int w, int h, size_t stride, const double* poses,
                          bool on_device, int* result, const uint8_t* const* ptrs) {
+    if (!subs.empty()) {
+        // every sub-handle sees every frame: it takes the same accept / spreadMap decisions as an unsharded map, copies (or
+        // reads over NVLink) only the frames under which it owns tiles, and returns once its work is enqueued -- the
+        // devices then fuse concurrently
+        std::vector<int> scratch_res((size_t)std::max(n, 1));
+        int rc0 = M2D_OK;
+        for (size_t i = 0; i < subs.size(); i++) {
+            int r = subs[i]->feed_frames(n, base, frame_stride, w, h, stride, poses, on_device, i == 0 ? result : scratch_res.data(), ptrs);
+            if (r < 0) { err = subs[i]->err; return r; }
+            if (i == 0) rc0 = r;
+        }
+        mirror();
+        return rc0;
+    }
     if (!valid) {                                         // Map2DCPU.cpp:129
         stats.frames_fed += n;
         for (int i = 0; i < n && result; i++) result[i] = M2D_REJECTED;
@@ -709,7 +746,7 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
     const bool sparse = weights_first && type == M2D_TYPE_MULTIBAND && levels <= 6 && !tiles.empty() && nj >= 4;
     const int cells_max = max_wnx * 8 * max_wny * 8;
     const int wmap_stride = (lay.px_off[levels] + 7) & ~7;
-    size_t off_flags = 0, off_cmask = 0, off_lists = 0, off_counts = 0, off_wmap = 0, flag_bytes = 0;
+    size_t off_flags = 0, off_cmask = 0, off_lists = 0, off_counts = 0, off_wmap = 0, off_etable = 0, flag_bytes = 0;
     int mask_words = 1;
     if (sparse) {
         if (cells_max > 65535 || nj > 65535) { err = "frame region too large for the weights-first work lists"; return M2D_ERR_UNSUPPORTED; }
@@ -723,6 +760,8 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
         off_cmask = scratch; scratch += ((size_t)tiles.size() * levels * 64 * mask_words * sizeof(uint32_t) + 255) & ~(size_t)255;
         off_lists = scratch; scratch += ((size_t)2 * levels * nj * cells_max * sizeof(uint32_t) + 255) & ~(size_t)255;
         off_wmap = scratch; scratch += ((size_t)tiles.size() * wmap_stride * sizeof(uint16_t) + 255) & ~(size_t)255;
+        off_etable = scratch; scratch += (n_entries * levels * sizeof(EntryRef) + 255) & ~(size_t)255;
+        if ((size_t)nj * levels * cells_max > 0x7fffffffull) { err = "group too large for 32-bit cell flag indices"; return M2D_ERR_UNSUPPORTED; }
     }
     if (scratch) { int rc = grow((void**)&c.d_scratch, &c.scratch_cap, scratch, false); if (rc != M2D_OK) return rc; }
 
@@ -793,6 +832,7 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
         p.lists = reinterpret_cast<uint32_t*>(c.d_scratch + off_lists); p.list_cap = nj * cells_max;
         p.list_count = reinterpret_cast<unsigned*>(c.d_scratch + off_counts);
         p.wmap = reinterpret_cast<uint16_t*>(c.d_scratch + off_wmap); p.wmap_stride = wmap_stride;
+        p.etable = reinterpret_cast<EntryRef*>(c.d_scratch + off_etable);
         make_reach_table(levels, p.reach_lo, p.reach_hi);
         make_weight_reach_table(levels, p.wreach_lo, p.wreach_hi);
         p.use_tma = use_tma ? 1 : 0;
@@ -820,6 +860,7 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
         }
         CU(cudaMemsetAsync(p.comp, 0, 2 * flag_bytes + 256, ds));    // comp | win flags ... and the list lengths (off_counts follows the flags)
         LAUNCHKS(M2D_K_MBC_BOUNDS, ds, launch_mbc_bounds(p, lay, ds));
+        LAUNCHKS(M2D_K_MBC_BOUNDS, ds, launch_mbc_entry_table(p, (int)n_entries, ds));
         LAUNCHKS(M2D_K_MBS_PROPAGATE, ds, launch_mbx_propagate(p, 0, ds));
         CU(cudaEventRecord(c.decided, ds));
         CU(cudaStreamWaitEvent(c.stage, c.decided, 0));
@@ -881,6 +922,7 @@ bool m2d_map::tile_bbox(int& x0, int& y0, int& x1, int& y1) const {
 
 // save() in memory — Map2DCPU.cpp:523-560 / MultiBandMap2DCPU.cpp:779-841
 int m2d_map::get_image(uint8_t* out, int* w, int* h, int* channels, int* tmx, int* tmy) {
+    if (!subs.empty()) return multi_get_image(out, w, h, channels, tmx, tmy);
     if (!valid || g.w == 0 || g.h == 0) return M2D_REJECTED;
     int x0, y0, x1, y1;
     if (!tile_bbox(x0, y0, x1, y1)) return M2D_REJECTED;
@@ -961,6 +1003,55 @@ int m2d_map::collapse_window(uint8_t* out, bool out_on_device, const int win[4],
     return M2D_OK;
 }
 
+// Multi-device save: the raw tiles of the other devices are read into the first device's pool over NVLink (peer loads from
+// the import kernel), collapsed there like a single-GPU map, and the copies are given back.  (The strip-wise sharded save
+// that never holds the whole map on one GPU is the multi-process path: pi-slam-fusion_b200/sharded.py save_sharded.)
+int m2d_map::multi_get_image(uint8_t* out, int* w, int* h, int* channels, int* tmx, int* tmy) {
+    int X0 = INT32_MAX, Y0 = INT32_MAX, X1 = INT32_MIN, Y1 = INT32_MIN;
+    for (m2d_map* sub : subs) {
+        int x0, y0, x1, y1;
+        if (!sub->valid || !sub->tile_bbox(x0, y0, x1, y1)) continue;
+        X0 = std::min(X0, x0); Y0 = std::min(Y0, y0); X1 = std::max(X1, x1); Y1 = std::max(Y1, y1);
+    }
+    if (X1 <= X0) return M2D_REJECTED;
+    *w = (X1 - X0) * kEle; *h = (Y1 - Y0) * kEle; *channels = (type == M2D_TYPE_MULTIBAND) ? 3 : 4; *tmx = X0; *tmy = Y0;
+    if (!out) return M2D_OK;
+    m2d_map* root = subs[0];
+    std::vector<int> foreign;   // absolute coordinates of the imported copies
+    int rc = M2D_OK;
+    for (size_t i = 1; i < subs.size() && rc == M2D_OK; i++) {
+        m2d_map* sub = subs[i];
+        const int n = (int)sub->tiles_in_use;
+        if (!n) continue;
+        CU(cudaSetDevice(sub->cfg.device));
+        uint8_t* buf = nullptr;
+        if (cudaMalloc(&buf, (size_t)n * sub->tile_bytes) != cudaSuccess) { cudaGetLastError(); err = "multi-device save: staging allocation failed"; return M2D_ERR_NOMEM; }
+        std::vector<int> xy((size_t)n * 2);
+        int got = 0;
+        rc = m2d_export_tiles(sub, n, xy.data(), buf, 1, &got);
+        if (rc == M2D_OK) rc = m2d_import_tiles(root, got, xy.data(), buf, 1);   // runs on the root device, reads `buf` through peer access
+        if (rc != M2D_OK) err = rc == M2D_OK ? err : (root->err.empty() ? sub->err : root->err);
+        cudaSetDevice(sub->cfg.device);
+        cudaFree(buf);
+        foreign.insert(foreign.end(), xy.begin(), xy.begin() + 2 * (size_t)got);
+    }
+    if (rc == M2D_OK) { rc = root->get_image(out, w, h, channels, tmx, tmy); if (rc != M2D_OK) err = root->err; }
+    {   // the root keeps only what it owns
+        cudaSetDevice(root->cfg.device);
+        cudaStreamSynchronize(root->stream);
+        std::lock_guard<std::mutex> lk(root->pool_mu);
+        for (size_t k = 0; k + 1 < foreign.size(); k += 2) {
+            const int x = foreign[k] - root->org_x, y = foreign[k + 1] - root->org_y;
+            if (x < 0 || y < 0 || x >= root->g.w || y >= root->g.h) continue;
+            uint8_t*& t = root->table[(size_t)y * root->g.w + x];
+            if (t) { root->free_tiles.push_back(t); t = nullptr; root->tiles_in_use--; }
+        }
+    }
+    return rc;
+}
+
+#define MULTI_UNSUPPORTED(h) do { if ((h) && !(h)->subs.empty()) { (h)->err = std::string(__func__) + ": not available on a multi-device handle"; return M2D_ERR_UNSUPPORTED; } } while (0)
+
 // ---------------------------------------------------------------------------------------------------------------
 // extern "C"
 // ---------------------------------------------------------------------------------------------------------------
@@ -995,6 +1086,44 @@ int m2d_create(int type, const m2d_config* cfg, m2d_handle* out) {
         return rc;
     }
     *out = m;
+    return M2D_OK;
+}
+
+int m2d_create_multi(int type, const m2d_config* cfg, int n_devices, const int* devices, m2d_handle* out) {
+    if (!out) return M2D_ERR_ARG;
+    *out = nullptr;
+    if (n_devices < 1 || n_devices > 64 || !devices) return M2D_ERR_ARG;
+    m2d_config c;
+    if (cfg) c = *cfg; else m2d_config_default(&c);
+    if (n_devices == 1) { c.device = devices[0]; return m2d_create(type, &c, out); }
+    if (c.shard_count > 1) return M2D_ERR_ARG;   // the multi-device handle shards by itself
+    if (c.shard_axis != 0 && c.shard_axis != 1) c.shard_axis = 1;
+    if (c.shard_span < 1) c.shard_span = 4;
+    m2d_map* top = new m2d_map();
+    top->cfg = c;
+    top->cfg.device = devices[0];
+    for (int i = 0; i < n_devices; i++) {
+        m2d_config ci = c;
+        ci.device = devices[i]; ci.shard_rank = i; ci.shard_count = n_devices;
+        m2d_handle sub = nullptr;
+        int rc = m2d_create(type, &ci, &sub);
+        if (rc != M2D_OK) { top->release(); delete top; return rc; }
+        top->subs.push_back(sub);
+    }
+    top->type = top->subs[0]->type; top->band_num = top->subs[0]->band_num; top->levels = top->subs[0]->levels;
+    top->lay = top->subs[0]->lay; top->tile_bytes = top->subs[0]->tile_bytes;
+    for (int a = 0; a < n_devices; a++)      // peer access both ways: frames and tiles are read in place over NVLink
+        for (int b = 0; b < n_devices; b++) {
+            if (a == b || devices[a] == devices[b]) continue;
+            int can = 0;
+            if (cudaSetDevice(devices[a]) == cudaSuccess && cudaDeviceCanAccessPeer(&can, devices[a], devices[b]) == cudaSuccess && can) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(devices[b], 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); can = 0; }
+                cudaGetLastError();
+            }
+            if (!can) { fprintf(stderr, "m2d_create_multi: no peer access between devices %d and %d\n", devices[a], devices[b]); top->release(); delete top; return M2D_ERR_UNSUPPORTED; }
+        }
+    *out = top;
     return M2D_OK;
 }
 
@@ -1037,6 +1166,7 @@ int m2d_feed_batch(m2d_handle h, int n, const uint8_t* base, size_t frame_stride
 
 int m2d_feed_poses(m2d_handle h, int n, const double* poses, int* result) {
     API_LOCK(h);
+    MULTI_UNSUPPORTED(h);
     if (!h || n < 0) return M2D_ERR_ARG;
     if (n == 0) return M2D_OK;
     if (!poses) return M2D_ERR_ARG;
@@ -1074,6 +1204,7 @@ int m2d_feed_poses(m2d_handle h, int n, const double* poses, int* result) {
 
 int m2d_plan_rects(m2d_handle h, int n, const double* poses, int* rects) {
     API_LOCK(h);
+    if (h && !h->subs.empty()) return m2d_plan_rects(h->subs[0], n, poses, rects);
     if (!h || n < 0 || (n && (!poses || !rects))) return M2D_ERR_ARG;
     if (!h->valid) return M2D_ERR_STATE;
     GridGeom g = h->g;   // dry run on a copy: the map itself is not touched
@@ -1099,6 +1230,7 @@ int m2d_plan_rects(m2d_handle h, int n, const double* poses, int* rects) {
 
 int m2d_set_shard(m2d_handle h, int rank, int count, int axis, int span, int origin) {
     API_LOCK(h);
+    MULTI_UNSUPPORTED(h);
     if (!h || count < 1 || rank < 0 || rank >= count || (axis != 0 && axis != 1) || span < 1) return M2D_ERR_ARG;
     if (h->tiles_in_use != 0) { h->err = "m2d_set_shard: the map already holds tiles"; return M2D_ERR_STATE; }
     h->cfg.shard_rank = rank; h->cfg.shard_count = count; h->cfg.shard_axis = axis; h->cfg.shard_span = span;
@@ -1303,6 +1435,7 @@ int m2d_queue_size(m2d_handle h) {
 }
 int m2d_set_stream(m2d_handle h, void* s) {
     API_LOCK(h);
+    MULTI_UNSUPPORTED(h);
     if (!h) return M2D_ERR_ARG;
     cudaSetDevice(h->cfg.device);
     cudaStreamSynchronize(h->stream);
@@ -1319,6 +1452,7 @@ int m2d_set_stream(m2d_handle h, void* s) {
 int m2d_reset(m2d_handle h) { API_LOCK(h); return h ? h->reset() : M2D_ERR_ARG; }
 int m2d_set_input_event(m2d_handle h, void* cuda_event) {
     API_LOCK(h);
+    if (h && !h->subs.empty()) { for (m2d_map* sub : h->subs) sub->input_event = (cudaEvent_t)cuda_event; return M2D_OK; }
     if (!h) return M2D_ERR_ARG;
     h->input_event = (cudaEvent_t)cuda_event;
     return M2D_OK;
@@ -1344,6 +1478,10 @@ int m2d_last_rect(m2d_handle h, int* rect) {
 
 int m2d_get_tile(m2d_handle h, int tx, int ty, int level, void* data, float* weight) {
     API_LOCK(h);
+    if (h && !h->subs.empty()) {   // the tile lives on the device that owns it
+        for (m2d_map* sub : h->subs) { int rc = m2d_get_tile(sub, tx, ty, level, data, weight); if (rc != M2D_REJECTED) { if (rc < 0) h->err = sub->err; return rc; } }
+        return M2D_REJECTED;
+    }
     if (!h || !data) return M2D_ERR_ARG;
     m2d_map& m = *h;
     std::string& err = m.err;
@@ -1385,6 +1523,7 @@ int m2d_get_image(m2d_handle h, uint8_t* out, int* w, int* hpx, int* channels, i
 
 int m2d_tile_bbox(m2d_handle h, int* bbox_abs) {
     API_LOCK(h);
+    MULTI_UNSUPPORTED(h);
     if (!h || !bbox_abs) return M2D_ERR_ARG;
     if (!h->valid) return M2D_ERR_STATE;
     int x0, y0, x1, y1;
@@ -1396,6 +1535,7 @@ int m2d_tile_bbox(m2d_handle h, int* bbox_abs) {
 int m2d_get_image_rect(m2d_handle h, uint8_t* out, int out_on_device, const int* window_abs, const int* crop_abs, int* w, int* hpx,
                        int* channels) {
     API_LOCK(h);
+    MULTI_UNSUPPORTED(h);
     if (!h || !window_abs || !crop_abs || !w || !hpx || !channels) return M2D_ERR_ARG;
     if (!h->valid) return M2D_ERR_STATE;
     const int ox = h->org_x, oy = h->org_y;
@@ -1406,6 +1546,7 @@ int m2d_get_image_rect(m2d_handle h, uint8_t* out, int out_on_device, const int*
 
 int m2d_drop_tiles_rect(m2d_handle h, const int* rect_abs, int* n_dropped) {
     API_LOCK(h);
+    MULTI_UNSUPPORTED(h);
     if (!h || !rect_abs) return M2D_ERR_ARG;
     m2d_map& m = *h;
     if (!m.valid) return M2D_ERR_STATE;
@@ -1442,7 +1583,12 @@ size_t m2d_tile_state_bytes(m2d_handle h) {
     if (!h) return 0;
     return h->type == M2D_TYPE_MULTIBAND ? h->lay.cmin_off : h->tile_bytes;
 }
-int m2d_tile_count(m2d_handle h) { API_LOCK(h); return h ? (int)h->tiles_in_use : 0; }
+int m2d_tile_count(m2d_handle h) {
+    API_LOCK(h);
+    if (!h) return 0;
+    if (!h->subs.empty()) { int n = 0; for (m2d_map* sub : h->subs) n += (int)sub->tiles_in_use; return n; }
+    return (int)h->tiles_in_use;
+}
 
 int m2d_export_tiles(m2d_handle h, int max_tiles, int* abs_xy, uint8_t* dst, int dst_on_device, int* n_out) {
     return m2d_export_tiles_rect(h, nullptr, max_tiles, abs_xy, dst, dst_on_device, n_out);
@@ -1450,6 +1596,7 @@ int m2d_export_tiles(m2d_handle h, int max_tiles, int* abs_xy, uint8_t* dst, int
 
 int m2d_export_tiles_rect(m2d_handle h, const int* rect_abs, int max_tiles, int* abs_xy, uint8_t* dst, int dst_on_device, int* n_out) {
     API_LOCK(h);
+    MULTI_UNSUPPORTED(h);
     if (!h || !abs_xy || !n_out || (!dst && max_tiles > 0)) return M2D_ERR_ARG;
     m2d_map& m = *h;
     std::string& err = m.err;
@@ -1493,6 +1640,7 @@ int m2d_export_tiles_rect(m2d_handle h, const int* rect_abs, int max_tiles, int*
 
 int m2d_import_tiles(m2d_handle h, int n, const int* abs_xy, const uint8_t* src, int src_on_device) {
     API_LOCK(h);
+    MULTI_UNSUPPORTED(h);
     if (!h || n < 0 || (n && (!abs_xy || !src))) return M2D_ERR_ARG;
     m2d_map& m = *h;
     std::string& err = m.err;
@@ -1527,6 +1675,13 @@ int m2d_import_tiles(m2d_handle h, int n, const int* abs_xy, const uint8_t* src,
 
 int m2d_poll_changed(m2d_handle h, int max_tiles, int* xy, int* n_out) {
     API_LOCK(h);
+    if (h && !h->subs.empty()) {   // every device tracks the tiles it owns
+        if (!xy || !n_out || max_tiles < 0) return M2D_ERR_ARG;
+        int n = 0;
+        for (m2d_map* sub : h->subs) { int k = 0; int rc = m2d_poll_changed(sub, max_tiles - n, xy + 2 * n, &k); if (rc != M2D_OK) return rc; n += k; }
+        *n_out = n;
+        return M2D_OK;
+    }
     if (!h || !xy || !n_out || max_tiles < 0) return M2D_ERR_ARG;
     m2d_map& m = *h;
     if (!m.valid) return M2D_ERR_STATE;
@@ -1542,6 +1697,7 @@ int m2d_poll_changed(m2d_handle h, int max_tiles, int* xy, int* n_out) {
 
 int m2d_get_tile_image(m2d_handle h, int tx, int ty, int high_quality, uint8_t* out, int* channels) {
     API_LOCK(h);
+    MULTI_UNSUPPORTED(h);
     if (!h || !out || !channels) return M2D_ERR_ARG;
     m2d_map& m = *h;
     std::string& err = m.err;
@@ -1622,6 +1778,7 @@ struct StateHeader {
 
 int m2d_save_state(m2d_handle h, const char* filename) {
     API_LOCK(h);
+    MULTI_UNSUPPORTED(h);
     if (!h || !filename) return M2D_ERR_ARG;
     m2d_map& m = *h;
     if (!m.valid) return M2D_ERR_STATE;
@@ -1648,6 +1805,7 @@ int m2d_save_state(m2d_handle h, const char* filename) {
 
 int m2d_load_state(m2d_handle h, const char* filename) {
     API_LOCK(h);
+    MULTI_UNSUPPORTED(h);
     if (!h || !filename) return M2D_ERR_ARG;
     m2d_map& m = *h;
     std::string& err = m.err;
@@ -1684,6 +1842,7 @@ int m2d_load_state(m2d_handle h, const char* filename) {
 
 int m2d_get_stats(m2d_handle h, m2d_stats* out) {
     API_LOCK(h);
+    if (h && !h->subs.empty()) return m2d_get_stats(h->subs[0], out);   // frame counters are identical on every device; px counters are the first device's share
     if (!h || !out) return M2D_ERR_ARG;
     m2d_map& m = *h;
     std::string& err = m.err;
@@ -1704,12 +1863,14 @@ int m2d_get_stats(m2d_handle h, m2d_stats* out) {
 
 int m2d_profile(m2d_handle h, int enable) {
     API_LOCK(h);
+    if (h && !h->subs.empty()) { for (m2d_map* sub : h->subs) sub->profiling = enable != 0; return M2D_OK; }
     if (!h) return M2D_ERR_ARG;
     h->profiling = enable != 0;
     return M2D_OK;
 }
 int m2d_get_kernel_times(m2d_handle h, double* ms, uint64_t* count) {
     API_LOCK(h);
+    MULTI_UNSUPPORTED(h);
     if (!h || !ms || !count) return M2D_ERR_ARG;
     m2d_map& m = *h;
     std::string& err = m.err;
@@ -1727,7 +1888,12 @@ int m2d_get_kernel_times(m2d_handle h, double* ms, uint64_t* count) {
 }
 
 const char* m2d_last_error(m2d_handle h) { return h ? h->err.c_str() : "null handle"; }
-uint64_t m2d_launch_count(m2d_handle h) { return h ? h->launches : 0; }
+uint64_t m2d_launch_count(m2d_handle h) {
+    if (!h) return 0;
+    uint64_t n = h->launches;
+    for (m2d_map* sub : h->subs) n += sub->launches;
+    return n;
+}
 
 int m2d_tile_gps_corners(const double* plane7, double grid_min_x, double grid_min_y, double ele_size, int tx, int ty,
                          const double* gps_origin, double* tl, double* br) {
@@ -1791,6 +1957,7 @@ void m2d_free_host(void* p) { if (p) cudaFreeHost(p); }
 
 int m2d_compute_bounds(m2d_handle h, int n, const double* poses, int* rects, double* hinv) {
     API_LOCK(h);
+    if (h && !h->subs.empty()) return m2d_compute_bounds(h->subs[0], n, poses, rects, hinv);
     if (!h || n < 0 || !poses || !rects || !hinv) return M2D_ERR_ARG;
     m2d_map& m = *h;
     std::string& err = m.err;

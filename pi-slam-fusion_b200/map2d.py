@@ -44,7 +44,7 @@ class Stats(C.Structure):
                 "footprint_px": self.footprint_px, "need_px": list(self.need_px), "needw_px": list(self.needw_px)}
 
 
-EXPORTS = ["m2d_config_default", "m2d_create", "m2d_destroy", "m2d_prepare", "m2d_feed", "m2d_feed_device",
+EXPORTS = ["m2d_config_default", "m2d_create", "m2d_create_multi", "m2d_destroy", "m2d_prepare", "m2d_feed", "m2d_feed_device",
            "m2d_feed_batch", "m2d_feed_poses", "m2d_plan_rects", "m2d_set_shard", "m2d_sync", "m2d_queue_size", "m2d_set_stream", "m2d_reset", "m2d_set_input_event", "m2d_get_grid",
            "m2d_last_rect", "m2d_get_tile", "m2d_get_image", "m2d_save", "m2d_tile_bytes", "m2d_tile_state_bytes", "m2d_tile_count",
            "m2d_export_tiles", "m2d_import_tiles", "m2d_export_tiles_rect", "m2d_drop_tiles_rect", "m2d_tile_bbox", "m2d_get_image_rect", "m2d_poll_changed", "m2d_get_tile_image", "m2d_save_state", "m2d_load_state", "m2d_get_stats", "m2d_last_error",
@@ -67,6 +67,7 @@ def lib():
     L.m2d_config_default.argtypes = [C.POINTER(Config)]
     L.m2d_config_default.restype = None
     L.m2d_create.argtypes = [C.c_int, C.POINTER(Config), C.POINTER(vp)]
+    L.m2d_create_multi.argtypes = [C.c_int, C.POINTER(Config), C.c_int, C.POINTER(C.c_int), C.POINTER(vp)]
     L.m2d_destroy.argtypes = [vp]
     L.m2d_destroy.restype = None
     L.m2d_prepare.argtypes = [vp, dp, dp, C.c_int, dp]
@@ -223,11 +224,17 @@ class Map2D:
     """Reference-shaped object; see module docstring."""
     NoType, TypeCPU, TypeGPU, TypeMultiBandCPU, TypeRender = 0, 1, 2, 3, 4  # Map2D.h:83
 
-    def __init__(self, type_, cfg):
+    def __init__(self, type_, cfg, devices=None):
         self.cfg = cfg
         self.type = self.TypeCPU if type_ == self.TypeGPU else type_
         self._h = C.c_void_p()
-        rc = lib().m2d_create(type_, C.byref(cfg), C.byref(self._h))
+        if devices is not None and len(devices) > 1:   # one process, several GPUs (m2d_create_multi)
+            arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+            rc = lib().m2d_create_multi(type_, C.byref(cfg), len(devices), arr, C.byref(self._h))
+        else:
+            if devices:
+                cfg.device = int(devices[0])
+            rc = lib().m2d_create(type_, C.byref(cfg), C.byref(self._h))
         if rc != OK:
             raise RuntimeError("m2d_create(type=%d) failed with status %d (no CUDA device? unsupported type?)" % (type_, rc))
         self.levels = (min(cfg.band_number if cfg.band_number > 0 else 5, 8) + 1) if self.type == self.TypeMultiBandCPU else 1
@@ -237,8 +244,9 @@ class Map2D:
         """Map2D::create(type, thread) — returns None for NoType like the reference's null SPtr."""
         if type_ == cls.NoType:
             return None
+        devices = kw.pop("devices", None)
         cfg = kw.pop("cfg", None) or default_config(thread=int(bool(thread)), **kw)
-        return cls(type_, cfg)
+        return cls(type_, cfg, devices)
 
     def close(self):
         if getattr(self, "_h", None):

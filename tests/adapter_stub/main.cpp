@@ -10,8 +10,11 @@ int main(int argc, char** argv) {
     const bool threaded = argc > 3 && atoi(argv[3]) != 0;   // Map2D::create(type, thread)
     const int n_feed = argc > 4 ? atoi(argv[4]) : 4;        // frames handed to feed() ...
     const int first_feed = argc > 5 ? atoi(argv[5]) : 0;    // ... starting at this one (frames 0..3 are the prepare set)
+    const int n_dev = argc > 6 ? atoi(argv[6]) : 1;         // > 1: one process, several GPUs (m2d_create_multi)
     const int W = 320, H = 180;
-    Map2DB200 map(type, threaded);
+    std::vector<int> devices;
+    for (int d = 0; d < n_dev; d++) devices.push_back(d);
+    Map2DB200 map(type, threaded, devices);
     std::deque<std::pair<cv::Mat, pi::SE3d> > frames, all;
     for (int k = 0; k < 8; k++) {
         cv::Mat img(H, W, CV_8UC3);

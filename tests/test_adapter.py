@@ -69,3 +69,21 @@ def test_adapter_thread_mode_uses_the_ingest_queue(tmp_path, typ):
     assert r2["saved"] == "1" and open(c, "rb").read() == open(d, "rb").read()
     r4 = run(exe, str(typ), str(tmp_path / "sync_none.png"), "0", "0", "0")   # thread=false never renders the prepare set
     assert r4["prepared"] == "1" and r4["saved"] == "0" and r4["image"] == "0x0"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("typ", [1, 3])
+@pytest.mark.parametrize("threaded", ["0", "1"])
+def test_adapter_drives_two_gpus_in_one_process(tmp_path, typ, threaded):
+    """Multi-GPU behind the boundary: the unmodified host loop, ONE process, `Map2DB200(type, thread, {0, 1})` ->
+    m2d_create_multi.  Tiles are sharded over the two devices, every device sees every frame, save() gathers over NVLink.
+    The PNG must equal the single-GPU one byte for byte."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    exe = build(tmp_path)
+    a, b = str(tmp_path / "one.png"), str(tmp_path / "two.png")
+    r1 = run(exe, str(typ), a, threaded, "8", "0", "1")
+    r2 = run(exe, str(typ), b, threaded, "8", "0", "2")
+    assert r2["handle"] == "1" and r2["prepared"] == "1" and r2["fed"] == "8" and r2["saved"] == "1" and r2["image"] == r1["image"]
+    assert open(a, "rb").read() == open(b, "rb").read()
