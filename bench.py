@@ -62,6 +62,16 @@ def config_of(mode, n, w, h, seed, n_gpus=1):
             "l2": "inputs %.2f GB per step > 126 MB L2 (no flush needed)" % (n * w * h * 3 / 1e9)}
 
 
+def config_weak(mode, per_gpu, w, h, seed, world):
+    """`config` of the N > 1 line (both arms): the weak-scaled survey = N x the cfg2-shaped survey, same flight-line length."""
+    n = per_gpu * world
+    fpl = synth.frames_per_line(per_gpu, w, h)
+    cfg = config_of(mode, n, w, h, seed, world)
+    cfg["frames_per_gpu"] = per_gpu
+    cfg["workload"] += " x %d GPUs: %d frames, %d flight lines of %d" % (world, n, -(-n // fpl), fpl)
+    return cfg
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -190,13 +200,15 @@ def run_reference(args, rank, world):
         return
     from oracle import oracle as O
     mode, n, w, h, seed, _ = (CFG2 if args.mode == "multiband" else CFG1)
+    if world > 1:                                  # N > 1: the weak-scaled survey of the product arm (cfg2-shaped in both modes)
+        n, w, h, seed = CFG2[1:5]
     n = args.frames or n
     if args.size:
         w, h = (int(v) for v in args.size.lower().split("x"))
     typ = 3 if mode == "multiband" else 1
     threads = os.cpu_count() or 1
     O.set_threads(threads)
-    n_job = n * world if world > 1 else n          # N > 1: the weak-scaled survey of the product arm
+    n_job = n * world if world > 1 else n
     fpl = synth.frames_per_line(n, w, h) if world > 1 else None
     seq = synth.Sequence(n_job, w, h, seed=seed, fpl=fpl)
     sample = min(n_job, args.ref_frames if args.ref_frames > 0 else max(4, int(500 * 1280 * 720 / (w * h))))
@@ -218,7 +230,7 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "s16" if mode == "multiband" else "u8", "data": "synthetic",
-            "config": config_of(mode, n_job, w, h, seed, world),
+            "config": config_weak(mode, n, w, h, seed, world) if world > 1 else config_of(mode, n_job, w, h, seed, 1),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": "first %d frames of the %d-frame workload per step (oracle/map2d_oracle.cpp, OpenMP, %d threads)" % (sample, n_job, threads)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

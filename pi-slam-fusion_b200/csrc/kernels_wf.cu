@@ -641,12 +641,14 @@ __global__ void __launch_bounds__(256) mbx_pyrdown0_tma_kernel(const __grid_cons
 
 cudaError_t launch_mbx_pyrdown(const GroupParams& p, int image, int level, int ctas, cudaStream_t stream) {
     if (level == 0 && p.use_tma) {
-        static bool attr_done = false;
-        if (!attr_done) {
+        static bool attr_done[64] = {};   // the attribute is per device (a multi-device handle launches on several)
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64 || !attr_done[dev]) {
             cudaError_t e = cudaFuncSetAttribute(mbx_pyrdown0_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPyrTmaSmem);
             if (e == cudaSuccess) e = cudaFuncSetAttribute(mbx_pyrdown0_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPyrTmaSmem);
             if (e != cudaSuccess) return e;
-            attr_done = true;
+            if (dev >= 0 && dev < 64) attr_done[dev] = true;
         }
         const int tma_ctas = max(1, ctas / 4);   // 2 resident CTAs per SM (90 KB of stage buffers each)
         if (image) mbx_pyrdown0_tma_kernel<true><<<tma_ctas, 256, kPyrTmaSmem, stream>>>(p);

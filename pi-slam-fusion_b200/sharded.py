@@ -671,9 +671,7 @@ def bench_weak(args, rank, world, local_rank):
             seq4 = synth.Sequence(n4, w4, h4, seed=s4, along=0.7, cross=0.7)
             cfg4 = _strip_run(args, rank, world, local_rank, "weighted", seq4, "cfg4", 3, 2, False, False, B, m2d)
     if rank == 0:
-        cfg = B.config_of(mode, n, W, H, seed, world)
-        cfg["frames_per_gpu"] = per_gpu
-        cfg["workload"] += " x %d GPUs: %d frames, %d flight lines of %d" % (world, n, -(-n // fpl), fpl)
+        cfg = B.config_weak(mode, per_gpu, W, H, seed, world)
         line = {"metric": B.METRIC, "value": head["value"], "unit": B.UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": warm, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "s16" if mode == "multiband" else "u8", "data": "synthetic", "config": cfg,
