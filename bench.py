@@ -340,6 +340,15 @@ def measure_mode(args, m2d, torch, mode, n, w, h, seed, local_rank, stream, want
             me.feed_batch(host_ptr, n, frame_bytes, w, h, w * 3, seq.poses, False)
             return me.get_image(out=out_pinned)
 
+        def step_e2e_split():   # the same, with a sync between the two halves: where the time goes (not the reported number)
+            me.reset()
+            t0 = time.perf_counter()
+            me.feed_batch(host_ptr, n, frame_bytes, w, h, w * 3, seq.poses, False)
+            me.sync()
+            t1 = time.perf_counter()
+            me.get_image(out=out_pinned)
+            return (t1 - t0) * 1e3, (time.perf_counter() - t1) * 1e3
+
         for _ in range(2):
             step_e2e()
         torch.cuda.synchronize()
@@ -354,8 +363,11 @@ def measure_mode(args, m2d, torch, mode, n, w, h, seed, local_rank, stream, want
         torch.cuda.synchronize()
         wall = (time.perf_counter() - t0) / reps
         ms_e2e = max(e0.elapsed_time(e1) / reps, wall * 1e3)
+        feed_ms, save_ms = step_e2e_split()
         e2e = {"value": fused * w * h / (ms_e2e * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": n * frame_bytes,
                "d2h_bytes_per_step": out_bytes, "ms_per_step": ms_e2e,
+               "breakdown_ms": {"feed_batch_from_host": feed_ms, "collapse_and_d2h": save_ms,
+                                "h2d_gbs": n * frame_bytes / (feed_ms * 1e-3) / 1e9},
                "what": "m2d_feed_batch(host pinned frames) + m2d_get_image (collapse + D2H of the mosaic)"}
         me.close()
         m2d.free_pinned(out_ptr)

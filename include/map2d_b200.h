@@ -74,6 +74,10 @@ typedef struct m2d_config {
     int shard_rank, shard_count, shard_axis, shard_span;
     int collect_stats;   /* non-zero: kernels also count winners (for algorithmic-byte accounting) */
     int batch_frames;    /* frames fused per launch group in m2d_feed_batch (0 = library default) */
+    int f32_mode;        /* float association of cv::pyrDown(CV_32F) on the weight pyramid: 0 = OpenCV 2.4.9 (the
+                            reference's OpenCV: scalar rows, SSE columns; default), 1 = OpenCV 4.x (universal intrinsics:
+                            what the cv2 4.13 in this image executes) -- only there to diff the GPU path against REAL
+                            OpenCV end to end (tests/test_golden.py); differences are <= 2 ulp of a weight */
 } m2d_config;
 
 /* Algorithmic-traffic counters, SURVEY.md §8(d). Filled by the oracle always and by the CUDA library when

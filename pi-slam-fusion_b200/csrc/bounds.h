@@ -25,6 +25,12 @@
 //    | W_l(u) - w(phi(r)) | <= Lip / dmax * (hd + sqrt(2) sigma_l) + (0.7072 / dmax + float slack), r = rect centre,
 //    where 0.7072 covers the nearest-neighbour rounding of the sample position.  Squaring (WeightType 1) and the 1e-5
 //    clamp are monotone, so they are applied to the two ends.
+//  * TIGHTER UPPER bound for WeightType 0 (same precondition): s -> 1 - |s - c| / dmax is CONCAVE, so by Jensen
+//    sum_i k_i w(phi(q_i)) <= w(sum_i k_i phi(q_i)); the tap set is symmetric about q (no tap is folded: S lies inside
+//    the frame, hence inside the region), so the mean of the mapped taps differs from phi(q) only by the curvature of
+//    the projective map: |sum_i k_i phi(q_i) - phi(q)| <= 1/2 M2 E|x - q|^2 = M2 sigma_l^2 with
+//    M2 = 2 sqrt(2) Lip |d'| / min d >= |d^2 phi| (phi d = N is affine, so d^2 phi = -(d phi (x) d' + d' (x) d phi) / d).
+//    The sqrt(2) sigma_l term of the Lipschitz bound -- 26 px at level 5 -- shrinks to a fraction of a px.
 #pragma once
 #include <math.h>
 
@@ -92,6 +98,12 @@ M2D_HD void cell_weight_bounds(const float* m, int nx, int ny, int sw, int sh, i
     if (weight_type != 0) {
         w_hi = fmaxf(w_hi, 0.f); w_hi = w_hi * w_hi;
         w_lo = fmaxf(w_lo, 0.f); w_lo = w_lo * w_lo;
+    } else {
+        // concavity: the kernel spread only enters through the curvature of the projective map
+        const float sig2 = 0.5f * kSqrt2Sigma[l] * kSqrt2Sigma[l];
+        const float m2 = 2.8285f * lip * sqrtf(m[6] * m[6] + m[7] * m[7]) / dmin;
+        const float spread_j = (lip * hd + m2 * sig2 + 0.7072f) / dmax + 1e-5f;
+        w_hi = fminf(w_hi, base + spread_j);
     }
     const float hi = fmaxf(w_hi, 1e-5f) * (1.f + 3e-5f) + 2e-6f;
     const float lo = fmaxf(fmaxf(w_lo, 1e-5f) * (1.f - 3e-5f) - 2e-6f, 0.f);

@@ -275,6 +275,31 @@ __device__ __forceinline__ void lap_quad(const GroupParams& p, const FrameJob& J
     }
 }
 
+// f32 pyrDown association (oracle: pyr_down_f32).  mode 0 = OpenCV 2.4.9: rows s0*6 + (s-1 + s1)*4 + s-2 + s2 left to right,
+// columns ((r0+r4)+(r2+r2)) + ((r1+r3)+r2)*4, scaled by 1/256 (PyrDownVec_32f).  mode 1 = OpenCV 4.x, whose SIMD bodies
+// cover output columns [1, hvec_end) horizontally -- s0*6 + ((s-1+s1)*4 + (s-2+s2)) -- and [0, vvec_end) vertically (same
+// expression as 2.4.9), the remaining columns using the scalar expressions.  U = output column in REGION coordinates.
+struct F32Assoc { int mode, hvec_end, vvec_end; };
+__device__ __forceinline__ F32Assoc f32_assoc(int mode, int src_cols) {
+    F32Assoc a;
+    a.mode = mode;
+    const int ocols = (src_cols + 1) / 2, width0 = min((src_cols - 3) / 2 + 1, ocols);
+    a.hvec_end = (mode == 1 && width0 > 1) ? 1 + ((width0 - 1) / 4) * 4 : 0;
+    a.vvec_end = (mode == 1) ? (ocols / 4) * 4 : ocols;
+    return a;
+}
+__device__ __forceinline__ float pyr_h(const F32Assoc& a, int U, float sm2, float sm1, float s0, float sp1, float sp2) {
+    if (a.mode == 1 && U >= 1 && U < a.hvec_end) return s0 * 6.f + ((sm1 + sp1) * 4.f + (sm2 + sp2));
+    return s0 * 6.f + (sm1 + sp1) * 4.f + sm2 + sp2;
+}
+__device__ __forceinline__ float pyr_v(const F32Assoc& a, int U, float r0, float r1, float r2, float r3, float r4) {
+    if (U < a.vvec_end) {
+        const float t0 = (r0 + r4) + (r2 + r2), t1 = (r1 + r3) + r2;
+        return (t0 + t1 * 4.f) * (1.f / 256.f);
+    }
+    return (r2 * 6.f + (r1 + r3) * 4.f + r0 + r4) * (1.f / 256.f);
+}
+
 __device__ __forceinline__ size_t cell_base(const GroupParams& p, int frame, int l) { return ((size_t)frame * p.levels + l) * p.cells_max; }
 
 // ---- 1a. weight warp (nearest, constant 0): one thread = 4 px ----

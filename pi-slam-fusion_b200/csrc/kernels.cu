@@ -228,7 +228,7 @@ cudaError_t launch_mb_warp(const GroupParams& p, cudaStream_t stream) {
 // ---------------------------------------------------------------------------------------------------------
 struct HRow { uint32_t br0, g0, br1, g1; float w0, w1; };  // horizontal sums for output columns u and u+1
 
-__device__ __forceinline__ HRow pyr_hrow(const uint32_t* __restrict__ gr, const float* __restrict__ wr, const int* xs, bool fast) {
+__device__ __forceinline__ HRow pyr_hrow(const uint32_t* __restrict__ gr, const float* __restrict__ wr, const int* xs, bool fast, const F32Assoc& fa, int U) {
     uint32_t e[7];
     float f[7];
     if (fast) {  // xs[0] is even and the 7 columns are consecutive: 8-byte vector loads
@@ -251,8 +251,8 @@ __device__ __forceinline__ HRow pyr_hrow(const uint32_t* __restrict__ gr, const 
     h.g0 = g[2] * 6u + (g[1] + g[3]) * 4u + g[0] + g[4];
     h.g1 = g[4] * 6u + (g[3] + g[5]) * 4u + g[2] + g[6];
     // f32, OpenCV 2.4.9 association: s0*6 + (s-1 + s1)*4 + s-2 + s2, left to right
-    h.w0 = f[2] * 6.f + (f[1] + f[3]) * 4.f + f[0] + f[4];
-    h.w1 = f[4] * 6.f + (f[3] + f[5]) * 4.f + f[2] + f[6];
+    h.w0 = pyr_h(fa, U, f[0], f[1], f[2], f[3], f[4]);
+    h.w1 = pyr_h(fa, U + 1, f[2], f[3], f[4], f[5], f[6]);
     return h;
 }
 
@@ -282,11 +282,12 @@ __global__ void __launch_bounds__(256, 4) mb_pyrdown_kernel(const __grid_constan
         for (int d = 0; d < 7; d++) xs[d] = clampi(reflect101_idx(2 * U + d - 2, srw) - sox, 0, sww - 1);
     }
     int V0 = v0 + doy;
+    const F32Assoc fa = f32_assoc(p.f32_mode, srw);
     HRow h[5];
 #pragma unroll
     for (int r = 0; r < 11; r++) {
         int ys = clampi(reflect101_idx(2 * V0 + r - 2, srh) - soy, 0, swh - 1);
-        h[r % 5] = pyr_hrow(SG + (size_t)ys * sww, SW + (size_t)ys * sww, xs, fast);
+        h[r % 5] = pyr_hrow(SG + (size_t)ys * sww, SW + (size_t)ys * sww, xs, fast, fa, U);
         if (r >= 4 && (r & 1) == 0) {
             int k = (r - 4) >> 1, v = v0 + k;
             if (v < dwh) {
@@ -298,9 +299,7 @@ __global__ void __launch_bounds__(256, 4) mb_pyrdown_kernel(const __grid_constan
                 uint32_t o0 = (((vbr0 + 0x00800080u) >> 8) & kM2) | (((vg0 + 128u) >> 8) << 8);
                 uint32_t o1 = (((vbr1 + 0x00800080u) >> 8) & kM2) | (((vg1 + 128u) >> 8) << 8);
                 // columns ((r0+r4)+(r2+r2)) + ((r1+r3)+r2)*4, scaled by 1/256 (PyrDownVec_32f of OpenCV 2.4.9)
-                float t00 = (r0.w0 + r4.w0) + (r2.w0 + r2.w0), t10 = (r1.w0 + r3.w0) + r2.w0;
-                float t01 = (r0.w1 + r4.w1) + (r2.w1 + r2.w1), t11 = (r1.w1 + r3.w1) + r2.w1;
-                float ow0 = (t00 + t10 * 4.f) * (1.f / 256.f), ow1 = (t01 + t11 * 4.f) * (1.f / 256.f);
+                float ow0 = pyr_v(fa, U, r0.w0, r1.w0, r2.w0, r3.w0, r4.w0), ow1 = pyr_v(fa, U + 1, r0.w1, r1.w1, r2.w1, r3.w1, r4.w1);
                 size_t o = (size_t)v * dww + u;
                 if (two && !(dww & 1)) {  // 8-byte stores need an even row pitch (odd only at 1-px tile levels)
                     *reinterpret_cast<uint2*>(DG + o) = make_uint2(o0, o1);
@@ -336,6 +335,7 @@ __global__ void __launch_bounds__(1024) mb_pyrtail_kernel(const __grid_constant_
         const float* SW = reinterpret_cast<const float*>(p.scratch + J.w_off[l]);
         uint32_t* DG = reinterpret_cast<uint32_t*>(p.scratch + J.g_off[l + 1]);
         float* DW = reinterpret_cast<float*>(p.scratch + J.w_off[l + 1]);
+        const F32Assoc fa = f32_assoc(p.f32_mode, srw);
         for (int o = threadIdx.x; o < dww * dwh; o += blockDim.x) {
             int v = o / dww, u = o - v * dww;
             int U = u + dox, V = v + doy;
@@ -354,14 +354,12 @@ __global__ void __launch_bounds__(1024) mb_pyrtail_kernel(const __grid_constant_
                 uint32_t a = gr[xs[0]], b = gr[xs[1]], c = gr[xs[2]], d = gr[xs[3]], e = gr[xs[4]];
                 hbr[r] = (c & kM2) * 6u + ((b & kM2) + (d & kM2)) * 4u + (a & kM2) + (e & kM2);
                 hg[r] = ((c >> 8) & 0xFFu) * 6u + (((b >> 8) & 0xFFu) + ((d >> 8) & 0xFFu)) * 4u + ((a >> 8) & 0xFFu) + ((e >> 8) & 0xFFu);
-                hw[r] = wr[xs[2]] * 6.f + (wr[xs[1]] + wr[xs[3]]) * 4.f + wr[xs[0]] + wr[xs[4]];
+                hw[r] = pyr_h(fa, U, wr[xs[0]], wr[xs[1]], wr[xs[2]], wr[xs[3]], wr[xs[4]]);
             }
             uint32_t vbr = hbr[0] + hbr[4] + (hbr[1] + hbr[3]) * 4u + hbr[2] * 6u;
             uint32_t vg = hg[0] + hg[4] + (hg[1] + hg[3]) * 4u + hg[2] * 6u;
-            float t0 = (hw[0] + hw[4]) + (hw[2] + hw[2]);
-            float t1 = (hw[1] + hw[3]) + hw[2];
             DG[o] = (((vbr + 0x00800080u) >> 8) & kM2) | (((vg + 128u) >> 8) << 8);
-            DW[o] = (t0 + t1 * 4.f) * (1.f / 256.f);
+            DW[o] = pyr_v(fa, U, hw[0], hw[1], hw[2], hw[3], hw[4]);
         }
         __syncthreads();
     }

@@ -53,6 +53,7 @@ struct GroupParams {
     int sw, sh;                // source frame size
     int levels;                // multi-band: band_num + 1
     int weight_type;           // Map2D.WeightType (alpha = dis or dis^2)
+    int f32_mode;              // m2d_config.f32_mode: float association of the weight pyrDown (0 = OpenCV 2.4.9, 1 = 4.x)
     const uint8_t* alpha;      // weighted: sw*sh alpha image (Map2DCPU.cpp:236-258)
     const float* wimg;         // multi-band: sw*sh float weight image (MultiBandMap2DCPU.cpp:396-418)
     uint8_t* scratch;          // multi-band: group scratch pyramid

@@ -404,6 +404,7 @@ __global__ void __launch_bounds__(256) mbx_pyrdown_kernel(const __grid_constant_
         } else {
             const float* SW = reinterpret_cast<const float*>(p.scratch + J.w_off[l]);
             float* DW = reinterpret_cast<float*>(p.scratch + J.w_off[l + 1]);
+            const F32Assoc assoc = f32_assoc(p.f32_mode, srw);
             float h0[5], h1[5];
 #pragma unroll
             for (int r = 0; r < 11; r++) {
@@ -419,14 +420,12 @@ __global__ void __launch_bounds__(256) mbx_pyrdown_kernel(const __grid_constant_
 #pragma unroll
                         for (int d = 0; d < 7; d++) fv[d] = wr[xs[d]];
                     }
-                    h0[r % 5] = fv[2] * 6.f + (fv[1] + fv[3]) * 4.f + fv[0] + fv[4];
-                    h1[r % 5] = fv[4] * 6.f + (fv[3] + fv[5]) * 4.f + fv[2] + fv[6];
+                    h0[r % 5] = pyr_h(assoc, U, fv[0], fv[1], fv[2], fv[3], fv[4]);
+                    h1[r % 5] = pyr_h(assoc, U + 1, fv[2], fv[3], fv[4], fv[5], fv[6]);
                     if (r >= 4 && (r & 1) == 0) {
                         const int k = (r - 4) >> 1, v = v0 + k;
                         const int i0 = (r - 4) % 5, i1 = (r - 3) % 5, i2 = (r - 2) % 5, i3 = (r - 1) % 5, i4 = r % 5;
-                        const float t00 = (h0[i0] + h0[i4]) + (h0[i2] + h0[i2]), t10 = (h0[i1] + h0[i3]) + h0[i2];
-                        const float t01 = (h1[i0] + h1[i4]) + (h1[i2] + h1[i2]), t11 = (h1[i1] + h1[i3]) + h1[i2];
-                        const float ow0 = (t00 + t10 * 4.f) * (1.f / 256.f), ow1 = (t01 + t11 * 4.f) * (1.f / 256.f);
+                        const float ow0 = pyr_v(assoc, U, h0[i0], h0[i1], h0[i2], h0[i3], h0[i4]), ow1 = pyr_v(assoc, U + 1, h1[i0], h1[i1], h1[i2], h1[i3], h1[i4]);
                         const size_t o = (size_t)v * dww + u;
                         if (two) *reinterpret_cast<float2*>(DW + o) = make_float2(ow0, ow1);
                         else DW[o] = ow0;
@@ -526,6 +525,8 @@ __global__ void __launch_bounds__(256) mbx_pyrdown0_tma_kernel(const __grid_cons
         const int cw = J.wnx * 8, cy = c / cw, cx = c - cy * cw;
         const int dww = J.wnx * nd;
         const int u = cx * 16 + 2 * cp, v0 = cy * 16 + 4 * rq;
+        const int UR = u + J.wx * nd;                              // output column in region coordinates
+        const F32Assoc assoc = f32_assoc(p.f32_mode, J.nx * ns);
         if (staged) {
             mbar_wait(&bars[s], (parity >> s) & 1u);
             parity ^= 1u << s;
@@ -560,20 +561,26 @@ __global__ void __launch_bounds__(256) mbx_pyrdown0_tma_kernel(const __grid_cons
             } else {
                 float* DW = reinterpret_cast<float*>(p.scratch + J.w_off[1]);
                 const float* fpatch = reinterpret_cast<const float*>(patch);
+                const bool odd = (rq & 1) != 0;
                 float h0[5], h1[5];
 #pragma unroll
                 for (int r = 0; r < 11; r++) {
                     const float* wr = fpatch + r * kPW;
-                    const float2 fa = *reinterpret_cast<const float2*>(wr), fb = *reinterpret_cast<const float2*>(wr + 2), fc = *reinterpret_cast<const float2*>(wr + 4);
-                    const float fv[7] = {fa.x, fa.y, fb.x, fb.y, fc.x, fc.y, wr[6]};
-                    h0[r % 5] = fv[2] * 6.f + (fv[1] + fv[3]) * 4.f + fv[0] + fv[4];
-                    h1[r % 5] = fv[4] * 6.f + (fv[3] + fv[5]) * 4.f + fv[2] + fv[6];
+                    // The four row groups (rq) of a warp sit 8 * 40 words = a multiple of 32 banks apart, and every lane's first
+                    // pair starts at a word = 2 (mod 4): loaded in the same order, the groups would collide 4-way.  Odd groups
+                    // swap the order of each two pairs, so that at every LDS half of the lanes is on words 2,3 (mod 4) and the
+                    // other half on words 0,1 -- 2-way instead of 4-way conflicts.  (The 4th pair's second word is never used.)
+                    const float2 l0 = *reinterpret_cast<const float2*>(wr + (odd ? 2 : 0)), l1 = *reinterpret_cast<const float2*>(wr + (odd ? 0 : 2));
+                    const float2 l2 = *reinterpret_cast<const float2*>(wr + (odd ? 6 : 4)), l3 = *reinterpret_cast<const float2*>(wr + (odd ? 4 : 6));
+                    const float2 fa = odd ? l1 : l0, fb = odd ? l0 : l1, fc = odd ? l3 : l2;
+                    const float fv[7] = {fa.x, fa.y, fb.x, fb.y, fc.x, fc.y, odd ? l2.x : l3.x};
+                    h0[r % 5] = pyr_h(assoc, UR, fv[0], fv[1], fv[2], fv[3], fv[4]);
+                    h1[r % 5] = pyr_h(assoc, UR + 1, fv[2], fv[3], fv[4], fv[5], fv[6]);
                     if (r >= 4 && (r & 1) == 0) {
                         const int k = (r - 4) >> 1, v = v0 + k;
                         const int i0 = (r - 4) % 5, i1 = (r - 3) % 5, i2 = (r - 2) % 5, i3 = (r - 1) % 5, i4 = r % 5;
-                        const float t00 = (h0[i0] + h0[i4]) + (h0[i2] + h0[i2]), t10 = (h0[i1] + h0[i3]) + h0[i2];
-                        const float t01 = (h1[i0] + h1[i4]) + (h1[i2] + h1[i2]), t11 = (h1[i1] + h1[i3]) + h1[i2];
-                        *reinterpret_cast<float2*>(DW + (size_t)v * dww + u) = make_float2((t00 + t10 * 4.f) * (1.f / 256.f), (t01 + t11 * 4.f) * (1.f / 256.f));
+                        *reinterpret_cast<float2*>(DW + (size_t)v * dww + u) =
+                            make_float2(pyr_v(assoc, UR, h0[i0], h0[i1], h0[i2], h0[i3], h0[i4]), pyr_v(assoc, UR + 1, h1[i0], h1[i1], h1[i2], h1[i3], h1[i4]));
                     }
                 }
             }
@@ -623,14 +630,13 @@ __global__ void __launch_bounds__(256) mbx_pyrdown0_tma_kernel(const __grid_cons
                     float fv[7];
 #pragma unroll
                     for (int d = 0; d < 7; d++) fv[d] = wr[xs[d]];
-                    h0[r % 5] = fv[2] * 6.f + (fv[1] + fv[3]) * 4.f + fv[0] + fv[4];
-                    h1[r % 5] = fv[4] * 6.f + (fv[3] + fv[5]) * 4.f + fv[2] + fv[6];
+                    h0[r % 5] = pyr_h(assoc, UR, fv[0], fv[1], fv[2], fv[3], fv[4]);
+                    h1[r % 5] = pyr_h(assoc, UR + 1, fv[2], fv[3], fv[4], fv[5], fv[6]);
                     if (r >= 4 && (r & 1) == 0) {
                         const int k = (r - 4) >> 1, v = v0 + k;
                         const int i0 = (r - 4) % 5, i1 = (r - 3) % 5, i2 = (r - 2) % 5, i3 = (r - 1) % 5, i4 = r % 5;
-                        const float t00 = (h0[i0] + h0[i4]) + (h0[i2] + h0[i2]), t10 = (h0[i1] + h0[i3]) + h0[i2];
-                        const float t01 = (h1[i0] + h1[i4]) + (h1[i2] + h1[i2]), t11 = (h1[i1] + h1[i3]) + h1[i2];
-                        *reinterpret_cast<float2*>(DW + (size_t)v * dww + u) = make_float2((t00 + t10 * 4.f) * (1.f / 256.f), (t01 + t11 * 4.f) * (1.f / 256.f));
+                        *reinterpret_cast<float2*>(DW + (size_t)v * dww + u) =
+                            make_float2(pyr_v(assoc, UR, h0[i0], h0[i1], h0[i2], h0[i3], h0[i4]), pyr_v(assoc, UR + 1, h1[i0], h1[i1], h1[i2], h1[i3], h1[i4]));
                     }
                 }
             }

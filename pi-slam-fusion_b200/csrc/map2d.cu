@@ -819,7 +819,7 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
     p.tiles = reinterpret_cast<const TileWork*>(c.d_blob + off_tiles);
     p.entries = reinterpret_cast<const TileEntry*>(c.d_blob + off_entries);
     p.n_frames = nj; p.n_tiles = (int)tiles.size();
-    p.sw = w; p.sh = h; p.levels = levels; p.weight_type = cfg.weight_type;
+    p.sw = w; p.sh = h; p.levels = levels; p.weight_type = cfg.weight_type; p.f32_mode = cfg.f32_mode;
     p.alpha = d_alpha; p.wimg = d_wimg; p.scratch = c.d_scratch;
     p.stats = cfg.collect_stats ? d_stats : nullptr;
     p.need_stats = (cfg.collect_stats || profiling) ? d_stats : nullptr;
@@ -1070,6 +1070,7 @@ int m2d_create(int type, const m2d_config* cfg, m2d_handle* out) {
     m2d_config c;
     if (cfg) c = *cfg; else m2d_config_default(&c);
     if (c.force_float) return M2D_ERR_UNSUPPORTED;
+    if (c.f32_mode != 0 && c.f32_mode != 1) return M2D_ERR_ARG;
     if (c.scale == 0) c.scale = 1.0;
     if (c.shard_count < 1) c.shard_count = 1;
     if (c.shard_rank < 0 || c.shard_rank >= c.shard_count) return M2D_ERR_ARG;

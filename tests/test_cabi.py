@@ -47,8 +47,8 @@ def test_config_struct_layout_matches():
     m2d.lib().m2d_config_default(C.byref(c))
     assert c.scale == 1.0 and c.band_number == 5 and c.shard_count == 1 and c.resolution == 0.0
     assert c.weight_type == 0 and c.force_float == 0 and c.collect_stats == 0 and c.batch_frames == 0
-    # header struct: 2 doubles + 12 ints
-    assert C.sizeof(m2d.Config) == 2 * 8 + 12 * 4
+    # header struct: 2 doubles + 13 ints (+ padding to 8)
+    assert C.sizeof(m2d.Config) == 2 * 8 + 14 * 4
     assert C.sizeof(m2d.Stats) == 8 * (3 + 3 * m2d.MAX_LEVELS + 1 + 2 * m2d.MAX_LEVELS)  # ... + need_px, needw_px[MAX_LEVELS]
 
 

@@ -126,3 +126,47 @@ def test_cuda_path_reproduces_goldens(name, typ):
     for k in ("frames_fused", "input_px", "region_px", "fresh_px", "win_px"):
         assert s[k] == gold["stats"][k], k
     g.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pipeline", ["weights_first", "dense", "streaming"])
+@pytest.mark.parametrize("jitter", [False, True])
+def test_gpu_multiband_equals_real_opencv_end_to_end(monkeypatch, pipeline, jitter):
+    """The CUDA multi-band path against REAL OpenCV, with nothing of ours in between: tests/cv2_reference.py builds the whole
+    feed()/save() recipe from cv2 4.13 primitives (getPerspectiveTransform, warpPerspective 16SC3 BORDER_REFLECT, pyrDown f32 and
+    16S, detail.createLaplacePyr / restoreImageFromLaplacePyr; only the nearest weight warp is restated, because cv2 >= 4.12
+    changed its border rule).  With m2d_config.f32_mode = 1 (cv2 4.x's float association of the weight pyrDown instead of
+    2.4.9's) the GPU must reproduce its grid, every tile of every level -- int16 Laplacians AND float weights -- and the
+    saved mosaic byte for byte, through the weights-first pipeline (culling, work lists, TMA pyrDown), the dense pipeline
+    and frame-by-frame streaming."""
+    import torch
+    import pi_slam_fusion_b200.map2d as m2d
+    pytest.importorskip("cv2")
+    from tests.cv2_reference import Cv2Map2D
+    if pipeline == "dense":
+        monkeypatch.setenv("M2D_SPARSE", "0")
+    seq = synth.Sequence(14, 320, 180, seed=7, jitter=jitter, noise=jitter, fpl=4, prepare_frames=6)
+    frames = seq.frames()
+    c = Cv2Map2D(3)
+    g = m2d.Map2D.create(3, thread=False, f32_mode=1, batch_frames=0 if pipeline == "weights_first" else 5)
+    assert c.prepare(seq.plane, seq.camera, seq.prepare_poses) and g.prepare(seq.plane, seq.camera, seq.prepare_poses)
+    exp = [c.feed(frames[k], seq.poses[k]) for k in range(seq.n)]
+    if pipeline == "streaming":
+        got = [g.feed(frames[k], seq.poses[k]) for k in range(seq.n)]
+    else:
+        dev = torch.from_numpy(frames).cuda()
+        got = [r == 0 for r in g.feed_batch(dev.data_ptr(), seq.n, seq.w * seq.h * 3, seq.w, seq.h, seq.w * 3, seq.poses, True)]
+    assert got == exp
+    g.sync()
+    gr = g.grid()
+    assert (gr["w"], gr["h"]) == (c.w, c.h) and gr["length_pixel"] == c.lp and list(gr["min"]) == c.min
+    assert len(c.tiles) > 0 and g.tile_count() == len(c.tiles)
+    for (tx, ty) in c.tiles:
+        for l in range(6):
+            gl, gw = g.get_tile(tx, ty, l)
+            cl, cw = c.get_tile(tx, ty, l)
+            assert np.array_equal(gw, cw), "tile (%d,%d) L%d weights differ from cv2" % (tx, ty, l)
+            assert np.array_equal(gl, cl), "tile (%d,%d) L%d Laplacian differs from cv2" % (tx, ty, l)
+    (ig, og), (ic, oc) = g.get_image(), c.get_image()
+    assert og == oc and np.array_equal(ig, ic)
+    g.close()
