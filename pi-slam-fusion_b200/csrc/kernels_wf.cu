@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(384) mbc_bounds_kernel(const __grid_constant__
                 float lo, hi;
                 if (i < kCache) hi = hic[i];
                 else cell_weight_bounds(J.hinvf, J.nx, J.ny, p.sw, p.sh, p.weight_type, l, E.rtx * 8 + ccx, E.rty * 8 + ccy, &lo, &hi);
-                in = hi >= best_lo;
+                in = !(hi < best_lo);   // NaN-safe: a bound that could not be evaluated never culls
             }
             if (in) {
                 bits |= 1u << (i & 31);

@@ -375,6 +375,40 @@ def test_weights_first_and_dense_pipelines_are_bit_exact(monkeypatch, sparse, cu
     g.close()
 
 
+@pytest.mark.parametrize("bands", [7, 8])
+def test_sharded_window_ring_follows_the_level_count(bands):
+    """The pyramid window of a shard = owned tiles + a ring that must cover the level-0 support of the deepest Laplacian
+    tap: 3 * 2^(L-1) - 2 px = 94 for the default 6 levels (1 tile), 382 for 8 levels (2 tiles), 766 for 9 levels (3 tiles).
+    Frames wide enough (5 x 4 tiles) for a one-tile ring to be too small: every shard's tiles must still equal the oracle's
+    unsharded run."""
+    import torch
+    seq = synth.Sequence(6, 1100, 800, seed=33, jitter=True, fpl=3, prepare_frames=3, cross=0.5, along=0.4)
+    frames = seq.frames()
+    dev = torch.from_numpy(frames).cuda()
+    o = O.OracleMap2D.create(3, band_number=bands)
+    O.set_threads(os.cpu_count() or 1)
+    try:
+        assert o.prepare(seq.plane, seq.camera, seq.prepare_poses)
+        for k in range(seq.n):
+            assert o.feed(frames[k], seq.poses[k])
+    finally:
+        O.set_threads(1)
+    count = 3
+    shards = [m2d.Map2D.create(3, thread=False, band_number=bands, shard_rank=r, shard_count=count, shard_axis=0, shard_span=1) for r in range(count)]
+    for m in shards:
+        assert m.prepare(seq.plane, seq.camera, seq.prepare_poses)
+        assert (m.feed_batch(dev.data_ptr(), seq.n, seq.w * seq.h * 3, seq.w, seq.h, seq.w * 3, seq.poses, True) == 0).all()
+        m.sync()
+    tb = shards[0].tile_bytes()
+    for m in shards[1:]:
+        n = m.tile_count()
+        buf = torch.empty(max(n, 1) * tb, dtype=torch.uint8, device="cuda")
+        assert shards[0].import_tiles(m.export_tiles(buf.data_ptr(), n, True), buf.data_ptr(), True)
+    compare_state(shards[0], o, 3)
+    for m in shards:
+        m.close()
+
+
 def raw_state(m):
     """Every tile this handle holds as (sorted absolute coordinates, [n, state_bytes] uint8 CUDA tensor of reference state)."""
     import torch
