@@ -1030,7 +1030,7 @@ int m2d_map::multi_get_image(uint8_t* out, int* w, int* h, int* channels, int* t
         int got = 0;
         rc = m2d_export_tiles(sub, n, xy.data(), buf, 1, &got);
         if (rc == M2D_OK) rc = m2d_import_tiles(root, got, xy.data(), buf, 1);   // runs on the root device, reads `buf` through peer access
-        if (rc != M2D_OK) err = rc == M2D_OK ? err : (root->err.empty() ? sub->err : root->err);
+        if (rc != M2D_OK) err = root->err.empty() ? sub->err : root->err;
         cudaSetDevice(sub->cfg.device);
         cudaFree(buf);
         foreign.insert(foreign.end(), xy.begin(), xy.begin() + 2 * (size_t)got);

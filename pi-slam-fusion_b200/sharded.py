@@ -226,7 +226,14 @@ class ShardedMap2D:
             raise ValueError("no frame of the sequence is accepted")
         ext = [(int(ok[:, 0].min()), int(ok[:, 2].max())), (int(ok[:, 1].min()), int(ok[:, 3].max()))]
         if axis is None:
-            axis = 0 if ext[0][1] - ext[0][0] >= ext[1][1] - ext[1][0] else 1
+            # cut ACROSS the flight lines: along the axis on which consecutive frames move least (the cross-track axis), so
+            # that a strip holds whole flight lines, its frames are contiguous in feed order and only the lines next to a
+            # boundary are halo frames.  (Cutting along the track would make every rank need a piece of every line.)
+            cx, cy = 0.5 * (ok[:, 0] + ok[:, 2]), 0.5 * (ok[:, 1] + ok[:, 3])
+            if len(ok) > 1:
+                axis = 0 if np.abs(np.diff(cx)).mean() <= np.abs(np.diff(cy)).mean() else 1
+            else:
+                axis = 0 if ext[0][1] - ext[0][0] >= ext[1][1] - ext[1][0] else 1
         lo, hi = ext[axis]
         span = max(1, -(-(hi - lo) // self.world))
         self.map.set_shard(self.rank, self.world, axis, span, lo)
@@ -662,14 +669,22 @@ def bench_weak(args, rank, world, local_rank):
             _, n3, w3, h3, s3, _ = B.CFG3
             n3 = args.cfg3_frames
             seq3 = synth.Sequence(n3, w3, h3, seed=s3)
-            cfg3 = _strip_run(args, rank, world, local_rank, "multiband", seq3, "cfg3", max(2, min(args.steps, 5)), 2, False, False, B, m2d, want_sha=True)
+            try:
+                cfg3 = _strip_run(args, rank, world, local_rank, "multiband", seq3, "cfg3", max(2, min(args.steps, 5)), 2, False, False, B, m2d, want_sha=True)
+            except Exception as e:   # (an error that hits every rank alike, e.g. out of memory: the rest of the line is still worth printing)
+                cfg3 = {"error": "%s: %s" % (type(e).__name__, e)}
+                torch.cuda.empty_cache()
         n4 = args.cfg4_frames if args.cfg4_frames >= 0 else (B.CFG4[1] if world >= 8 else 0)
         if n4 > 0:
             # BASELINE configs[3]: weighted fusion of a 5000-frame 4000x3000 survey with 30 % / 30 % overlap: ~470k tiles =
             # ~120 GB of BGRA map state, more than one GPU's tile budget; sharded, saved strip by strip, never gathered
             _, _, w4, h4, s4, _ = B.CFG4
             seq4 = synth.Sequence(n4, w4, h4, seed=s4, along=0.7, cross=0.7)
-            cfg4 = _strip_run(args, rank, world, local_rank, "weighted", seq4, "cfg4", 3, 2, False, False, B, m2d)
+            try:
+                cfg4 = _strip_run(args, rank, world, local_rank, "weighted", seq4, "cfg4", 3, 2, False, False, B, m2d)
+            except Exception as e:
+                cfg4 = {"error": "%s: %s" % (type(e).__name__, e)}
+                torch.cuda.empty_cache()
     if rank == 0:
         cfg = B.config_weak(mode, per_gpu, W, H, seed, world)
         line = {"metric": B.METRIC, "value": head["value"], "unit": B.UNIT, "n_gpus": world, "steps": args.steps,
@@ -682,12 +697,16 @@ def bench_weak(args, rank, world, local_rank):
                 "save": head["save"], "e2e": head.get("e2e"), "parity": head["parity"], "roofline": None, "cpu_baseline": None}
         if other:
             line[other_mode] = other
-        if cfg3:
+        if cfg3 and "error" in cfg3:
+            line["cfg3"] = cfg3
+        elif cfg3:
             cfg3["workload"] = B.workload_name("multiband", seq3.n, seq3.w, seq3.h, B.CFG3[4])
             cfg3["scaling"] = "strong"
             cfg3["n_gpus"] = world
             line["cfg3"] = cfg3
-        if cfg4:
+        if cfg4 and "error" in cfg4:
+            line["cfg4"] = cfg4
+        elif cfg4:
             cfg4["workload"] = "cfg4: Map2DCPU weighted fusion, %d synthetic %dx%d frames, 30 %%/30 %% overlap (seed %d): map state %.1f GB across %d GPUs" % (
                 seq4.n, seq4.w, seq4.h, B.CFG4[4], cfg4["tiles"] * 262144 / 1e9, world)
             cfg4["scaling"] = "strong"
