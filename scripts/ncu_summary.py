@@ -28,9 +28,10 @@ if len(sys.argv) > 2 and sys.argv[2] == "--traffic":
     import json, os
     names = {"mb_warp_kernel": "mb_warp", "mb_pyrdown_kernel": "mb_pyrdown", "mb_select_kernel": "mb_select", "pack_kernel": "pack",
              "weighted_group_kernel": "weighted_fuse", "mb_pyrtail_kernel": "mb_pyrtail",
-             "mbw_warp_kernel": "mbw_warp", "mbw_pyrdown_kernel": "mbw_pyramid", "mbs_decide_kernel": "mbs_decide",
-             "mbs_propagate_kernel": "mbs_propagate", "mbs_warp_kernel": "mbs_warp", "mbs_pyrdown_kernel": "mbs_pyramid",
-             "mbs_lap_kernel": "mbs_lap"}
+             "mbw_warp_kernel": "mbw_warp", "mbs_decide_kernel": "mbs_decide", "mbx_propagate_kernel": "mbs_propagate",
+             "mbs_warp_kernel": "mbs_warp", "mbs_lap_kernel": "mbs_lap", "mbc_bounds_kernel": "mbc_bounds",
+             "void mbx_pyrdown_kernel<0>": "mbw_pyramid", "void mbx_pyrdown0_tma_kernel<0>": "mbw_pyramid",
+             "void mbx_pyrdown_kernel<1>": "mbs_pyramid", "void mbx_pyrdown0_tma_kernel<1>": "mbs_pyramid"}
     path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_traffic.json")
     t = json.load(open(path)) if os.path.exists(path) else {}
     ik, ir, iw, it = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("gpu__time_duration.sum")
