@@ -509,6 +509,8 @@ def main():
     ap.add_argument("--only", action="store_true", help="headline mode only: no second mode, no cfg3, no cfg5")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1 headline. weak: N x the survey, --frames per GPU, strips of tiles, halo frames by P2P; strong: the same frames cut into N shards")
+    ap.add_argument("--halo", default="peer", choices=["peer", "copy"],
+                    help="N>1: how halo frames reach a rank. peer: sampled in place from the neighbour's HBM over NVLink (CUDA IPC); copy: NCCL P2P copies every step")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

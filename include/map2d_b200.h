@@ -136,6 +136,11 @@ int m2d_feed_device(m2d_handle h, const uint8_t* d_bgr, int w, int h_px, size_t 
 int m2d_feed_batch(m2d_handle h, int n, const uint8_t* base, size_t frame_stride, int w, int h_px,
                    size_t stride, const double* poses /* n x 7 */, int on_device, int* result);
 
+/* The same with one pointer per frame (frames that do not lie at a fixed stride: e.g. some in this GPU's memory, some mapped
+ * from a neighbouring GPU's with m2d_ipc_open and sampled in place over NVLink). */
+int m2d_feed_batch_ptrs(m2d_handle h, int n, const uint8_t* const* frames, int w, int h_px, size_t stride,
+                        const double* poses /* n x 7 */, int on_device, int* result);
+
 /* Sharded runs: the frames a shard does NOT need pixels for.  Applies exactly what feed() does to
  * the grid for each pose (bounds, reject test, spreadMap — Map2DCPU.cpp:163-233) and nothing else, so that every
  * shard takes the same grid decisions as an unsharded run while frame pixels travel only to the shards that own
@@ -301,6 +306,17 @@ int m2d_weight_reach_table(int levels, unsigned char lo[36], unsigned char hi[36
  * pyramid (MultiBandMap2DCPU.cpp:449-474).  Pure host arithmetic, no handle. */
 int m2d_cell_weight_bounds(const double hinv[9], int nx, int ny, int sw, int sh, int weight_type, int level, int cx,
                            int cy, float* lo, float* hi);
+
+/* Frame buffers that the other PROCESSES of a multi-GPU job can map (CUDA IPC).  One process per GPU keeps the frames its own
+ * flight lines produced in a buffer from m2d_device_alloc, exports it once (m2d_ipc_export -> 64 opaque bytes, sent to the
+ * neighbours by any means), and a neighbour that owns tiles under some of those frames maps the buffer (m2d_ipc_open, peer
+ * access over NVLink/NVSwitch is enabled on the way) and passes the mapped addresses to m2d_feed_batch_ptrs: its kernels
+ * sample the remote frames in place, so only the px that are really needed cross the link and no halo copy is ever made. */
+void* m2d_device_alloc(int device, size_t bytes);
+void m2d_device_free(int device, void* p);
+int m2d_ipc_export(void* dptr, unsigned char handle[64]);
+int m2d_ipc_open(int device, const unsigned char handle[64], void** dptr);
+int m2d_ipc_close(int device, void* dptr);
 
 /* Pinned host staging helpers for callers that want truly asynchronous m2d_feed(). */
 void* m2d_alloc_host(size_t bytes);

@@ -1165,6 +1165,16 @@ int m2d_feed_batch(m2d_handle h, int n, const uint8_t* base, size_t frame_stride
     return rc < 0 ? rc : M2D_OK;
 }
 
+int m2d_feed_batch_ptrs(m2d_handle h, int n, const uint8_t* const* frames, int w, int hpx, size_t stride, const double* poses,
+                        int on_device, int* result) {
+    API_LOCK(h);
+    if (!h || n < 0) return M2D_ERR_ARG;
+    if (n == 0) return M2D_OK;
+    if (!frames || !poses) return M2D_ERR_ARG;
+    int rc = h->feed_frames(n, nullptr, 0, w, hpx, stride, poses, on_device != 0, result, frames);
+    return rc < 0 ? rc : M2D_OK;
+}
+
 int m2d_feed_poses(m2d_handle h, int n, const double* poses, int* result) {
     API_LOCK(h);
     MULTI_UNSUPPORTED(h);
@@ -1946,6 +1956,39 @@ int m2d_reach_table(int levels, unsigned char* lo, unsigned char* hi) {
     make_reach_table(levels, l, h);
     memcpy(lo, l, 36);
     memcpy(hi, h, 36);
+    return M2D_OK;
+}
+
+// ---- device buffers that other PROCESSES on the node can map (CUDA IPC): frames stay where they were captured and the
+// kernels of a neighbouring rank sample them in place over NVLink -- no halo copies, only the px that are really needed move
+void* m2d_device_alloc(int device, size_t bytes) {
+    void* p = nullptr;
+    if (cudaSetDevice(device) != cudaSuccess || cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void m2d_device_free(int device, void* p) {
+    if (!p) return;
+    cudaSetDevice(device);
+    cudaFree(p);
+}
+int m2d_ipc_export(void* dptr, unsigned char* handle64) {
+    if (!dptr || !handle64) return M2D_ERR_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t hd;
+    if (cudaIpcGetMemHandle(&hd, dptr) != cudaSuccess) { cudaGetLastError(); return M2D_ERR_CUDA; }
+    memcpy(handle64, &hd, 64);
+    return M2D_OK;
+}
+int m2d_ipc_open(int device, const unsigned char* handle64, void** dptr) {
+    if (!handle64 || !dptr) return M2D_ERR_ARG;
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handle64, 64);
+    if (cudaSetDevice(device) != cudaSuccess || cudaIpcOpenMemHandle(dptr, hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return M2D_ERR_CUDA; }
+    return M2D_OK;
+}
+int m2d_ipc_close(int device, void* dptr) {
+    if (!dptr) return M2D_OK;
+    if (cudaSetDevice(device) != cudaSuccess || cudaIpcCloseMemHandle(dptr) != cudaSuccess) { cudaGetLastError(); return M2D_ERR_CUDA; }
     return M2D_OK;
 }
 

@@ -45,7 +45,7 @@ class Stats(C.Structure):
 
 
 EXPORTS = ["m2d_config_default", "m2d_create", "m2d_create_multi", "m2d_destroy", "m2d_prepare", "m2d_feed", "m2d_feed_device",
-           "m2d_feed_batch", "m2d_feed_poses", "m2d_plan_rects", "m2d_set_shard", "m2d_sync", "m2d_queue_size", "m2d_set_stream", "m2d_reset", "m2d_set_input_event", "m2d_get_grid",
+           "m2d_feed_batch", "m2d_feed_batch_ptrs", "m2d_device_alloc", "m2d_device_free", "m2d_ipc_export", "m2d_ipc_open", "m2d_ipc_close", "m2d_feed_poses", "m2d_plan_rects", "m2d_set_shard", "m2d_sync", "m2d_queue_size", "m2d_set_stream", "m2d_reset", "m2d_set_input_event", "m2d_get_grid",
            "m2d_last_rect", "m2d_get_tile", "m2d_get_image", "m2d_save", "m2d_tile_bytes", "m2d_tile_state_bytes", "m2d_tile_count",
            "m2d_export_tiles", "m2d_import_tiles", "m2d_export_tiles_rect", "m2d_drop_tiles_rect", "m2d_tile_bbox", "m2d_get_image_rect", "m2d_poll_changed", "m2d_get_tile_image", "m2d_save_state", "m2d_load_state", "m2d_get_stats", "m2d_last_error",
            "m2d_launch_count", "m2d_profile", "m2d_get_kernel_times", "m2d_alloc_host", "m2d_free_host", "m2d_compute_bounds",
@@ -74,6 +74,14 @@ def lib():
     L.m2d_feed.argtypes = [vp, vp, C.c_int, C.c_int, C.c_size_t, dp]
     L.m2d_feed_device.argtypes = [vp, vp, C.c_int, C.c_int, C.c_size_t, dp]
     L.m2d_feed_batch.argtypes = [vp, C.c_int, vp, C.c_size_t, C.c_int, C.c_int, C.c_size_t, dp, C.c_int, ip]
+    L.m2d_feed_batch_ptrs.argtypes = [vp, C.c_int, C.POINTER(vp), C.c_int, C.c_int, C.c_size_t, dp, C.c_int, ip]
+    L.m2d_device_alloc.argtypes = [C.c_int, C.c_size_t]
+    L.m2d_device_alloc.restype = vp
+    L.m2d_device_free.argtypes = [C.c_int, vp]
+    L.m2d_device_free.restype = None
+    L.m2d_ipc_export.argtypes = [vp, C.c_char_p]
+    L.m2d_ipc_open.argtypes = [C.c_int, C.c_char_p, C.POINTER(vp)]
+    L.m2d_ipc_close.argtypes = [C.c_int, vp]
     L.m2d_feed_poses.argtypes = [vp, C.c_int, dp, ip]
     L.m2d_plan_rects.argtypes = [vp, C.c_int, dp, ip]
     L.m2d_tile_gps_corners.argtypes = [dp, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int, dp, dp, dp]
@@ -205,6 +213,45 @@ def tile_overlay(map2d, tx, ty, high_quality=True):
     return np.ascontiguousarray(img[::-1, :, 2::-1])
 
 
+class DeviceBuffer:
+    """A cudaMalloc'ed buffer that other processes on the node can map (m2d_device_alloc / m2d_ipc_*).  `.tensor()` wraps it
+    as a torch uint8 tensor (no copy, via __cuda_array_interface__) so that it can be filled like any other tensor."""
+
+    def __init__(self, device, nbytes):
+        self.device, self.nbytes = int(device), int(nbytes)
+        self.ptr = lib().m2d_device_alloc(self.device, max(self.nbytes, 16))
+        if not self.ptr:
+            raise MemoryError("m2d_device_alloc(%d bytes) failed on device %d" % (nbytes, device))
+        self.__cuda_array_interface__ = {"shape": (max(self.nbytes, 16),), "typestr": "|u1", "data": (self.ptr, False), "version": 2}
+
+    def tensor(self):
+        import torch
+        return torch.as_tensor(self, device=torch.device("cuda", self.device))[:self.nbytes]
+
+    def export(self):
+        h = C.create_string_buffer(64)
+        if lib().m2d_ipc_export(self.ptr, h) != OK:
+            raise RuntimeError("m2d_ipc_export failed")
+        return h.raw
+
+    def free(self):
+        if self.ptr:
+            lib().m2d_device_free(self.device, self.ptr)
+            self.ptr = None
+
+
+def ipc_open(device, handle):
+    """Map a buffer another process exported with DeviceBuffer.export(); returns its address in this process."""
+    p = C.c_void_p()
+    if lib().m2d_ipc_open(int(device), handle, C.byref(p)) != OK:
+        raise RuntimeError("m2d_ipc_open failed (CUDA IPC / peer access not available between these GPUs?)")
+    return p.value
+
+
+def ipc_close(device, ptr):
+    lib().m2d_ipc_close(int(device), ptr)
+
+
 def pinned_empty(shape, dtype=np.uint8):
     """numpy array backed by page-locked host memory from m2d_alloc_host (truly asynchronous feeds)."""
     n = int(np.prod(shape)) * np.dtype(dtype).itemsize
@@ -314,6 +361,15 @@ class Map2D:
         rc = lib().m2d_feed_batch(self._h, n, base_ptr, frame_stride, w, h, stride, _dptr(poses), int(on_device),
                                   res.ctypes.data_as(C.POINTER(C.c_int)))
         self._check(rc)
+        return res
+
+    def feed_batch_ptrs(self, ptrs, w, h, stride, poses, on_device=True):
+        """feed_batch with one address per frame (e.g. some frames mapped from a neighbouring GPU's memory)."""
+        poses = np.ascontiguousarray(poses, np.float64).reshape(-1, 7)
+        n = len(ptrs)
+        arr = (C.c_void_p * max(n, 1))(*[int(p) for p in ptrs])
+        res = np.zeros(n, np.int32)
+        self._check(lib().m2d_feed_batch_ptrs(self._h, n, arr, w, h, stride, _dptr(poses), int(on_device), res.ctypes.data_as(C.POINTER(C.c_int))))
         return res
 
     def feed_poses(self, poses):

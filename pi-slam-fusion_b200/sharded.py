@@ -295,6 +295,65 @@ class ShardedMap2D:
         self.map.sync()
         return res
 
+    # ---- zero-copy frame delivery: frames stay where they were captured, neighbours sample them in place over NVLink ----
+    def share_frames(self, plan, w, h):
+        """CUDA only.  Put this rank's resident frames into a buffer the other processes can map (CUDA IPC), map the
+        buffers of the ranks that hold frames of this rank's hull, and return (mine, ptrs): `mine` = uint8 tensor
+        [resident frames, h, w, 3] to be filled by the caller, `ptrs` = one device address per frame of the sequence (0 where
+        the rank needs no pixels).  The kernels of m2d_feed_batch_ptrs then read halo frames straight from the neighbour's HBM
+        (P2P loads over NVLink/NVSwitch): no halo copy is made and only the px that are really sampled cross the link."""
+        import pi_slam_fusion_b200.map2d as m2d
+        fb = w * h * 3
+        lo, hi = plan.resident[self.rank]
+        self._frames = m2d.DeviceBuffer(self.device, max(hi - lo, 1) * fb)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, self._frames.export())
+        a, b = plan.hull[self.rank]
+        ptrs = np.zeros(plan.n, np.uint64)
+        self._mapped = []
+        for r in range(self.world):
+            rlo, rhi = plan.resident[r]
+            k0, k1 = max(a, rlo), min(b, rhi)
+            if r == self.rank:
+                k0, k1 = rlo, rhi
+                base = self._frames.ptr
+            elif k1 > k0:
+                base = m2d.ipc_open(self.device, handles[r])
+                self._mapped.append(base)
+            else:
+                continue
+            for k in range(k0, k1):
+                ptrs[k] = base + (k - rlo) * fb
+        mine = self._frames.tensor()[:(hi - lo) * fb].view(hi - lo, h, w, 3)
+        return mine, ptrs
+
+    def unshare_frames(self):
+        import pi_slam_fusion_b200.map2d as m2d
+        dist.barrier()   # nobody reads my frames any more
+        for p in getattr(self, "_mapped", []):
+            m2d.ipc_close(self.device, p)
+        self._mapped = []
+        if getattr(self, "_frames", None) is not None:
+            self._frames.free()
+            self._frames = None
+
+    def feed_all_peer(self, plan, ptrs, poses, w, h):
+        """One pass over the whole sequence with share_frames() delivery: poses only outside the rank's hull, ONE
+        m2d_feed_batch_ptrs inside it (own frames by local address, halo frames by their mapped peer address).  No
+        collective, no copy: the only inter-GPU traffic are the kernels' own loads."""
+        poses = np.ascontiguousarray(poses, np.float64).reshape(-1, 7)
+        n = len(poses)
+        a, b = plan.hull[self.rank]
+        res = np.zeros(n, np.int32)
+        if a > 0:
+            res[:a] = self.map.feed_poses(poses[:a])
+        if b > a:
+            res[a:b] = self.map.feed_batch_ptrs(ptrs[a:b], w, h, w * 3, poses[a:b], True)
+        if b < n:
+            res[b:] = self.map.feed_poses(poses[b:])
+        self.map.sync()
+        return res
+
     # ---- sharded save: every rank collapses its own strip (+ halo rows from its neighbours); nobody holds the whole map ----
     def save_sharded(self, axis, span, origin, levels=None, out=None, gather=False, chunk=None, sink=None):
         """The sharded half of Map2D::save (MultiBandMap2DCPU.cpp:779-847 / Map2DCPU.cpp:523-564) for the contiguous
@@ -492,15 +551,23 @@ def _strip_run(args, rank, world, local_rank, mode, seq, label, steps, warm, che
     assert sm.prepare(seq.plane, seq.camera, seq.prepare_poses)
     rects, axis, span, origin = sm.align_strips(seq.poses)
     plan = DeliveryPlan(rects, axis, span, world, even_split(n, world), origin)
-    buf, mine = sm.alloc_owned_buffer(plan, W, H)
+    peer = getattr(args, "halo", "peer") == "peer"
+    if peer:   # frames stay on the GPU that "captured" them; neighbours sample halo frames in place over NVLink (CUDA IPC)
+        buf = None
+        mine, ptrs = sm.share_frames(plan, W, H)
+    else:      # halo frames are copied by NCCL P2P inside every step
+        buf, mine = sm.alloc_owned_buffer(plan, W, H)
     lo, hi = plan.resident[rank]
-    for c0 in range(lo, hi, 64):   # inputs resident in HBM before the timed region, on the GPU that "captured" them
+    for c0 in range(lo, hi, 64):   # inputs resident in HBM before the timed region
         c1 = min(c0 + 64, hi)
         mine[c0 - lo:c1 - lo].copy_(BB.device_frames(torch, seq, c0, c1, dev))
     torch.cuda.synchronize()
+    dist.barrier()
 
     def step():
         sm.map.reset()
+        if peer:
+            return sm.feed_all_peer(plan, ptrs, seq.poses, W, H)
         return sm.feed_all_owned(plan, buf, seq.poses, W, H)
 
     for _ in range(warm):
@@ -560,7 +627,12 @@ def _strip_run(args, rank, world, local_rank, mode, seq, label, steps, warm, che
             sm.map.reset()
             mine.copy_(host_in, non_blocking=True)
             torch.cuda.current_stream().synchronize()
-            sm.feed_all_owned(plan, buf, seq.poses, W, H)
+            if peer:
+                dist.barrier()        # the neighbours' frames have landed too before anybody samples them ...
+                sm.feed_all_peer(plan, ptrs, seq.poses, W, H)
+                dist.barrier()        # ... and nobody re-uploads while a neighbour still reads
+            else:
+                sm.feed_all_owned(plan, buf, seq.poses, W, H)
             save()
 
         step_e2e()
@@ -620,8 +692,10 @@ def _strip_run(args, rank, world, local_rank, mode, seq, label, steps, warm, che
         out = {"label": label, "mode": mode, "value": px / (ms_step * 1e-3) / 1e6, "unit": B.UNIT, "ms_per_step": ms_step, "frames": n, "frames_fused": fused,
                "gpu_launches": int(float(t[3])), "clocks": clocks, "tiles": int(tiles.item()),
                "parallelism": "%d contiguous strips of %d tiles along axis %d (tile ownership); frames resident on the GPU of their own flight lines, "
-                              "%d halo frames exchanged by NCCL P2P per step (inside the timed region), poses to all ranks; largest rank feeds %d of %d frames"
-                              % (world, span, axis, plan.frames_moved(), int(hmax[0].item()), n),
+                              "%d halo frames %s, poses to all ranks; largest rank feeds %d of %d frames"
+                              % (world, span, axis, plan.frames_moved(),
+                                 "sampled IN PLACE from the neighbour's HBM over NVLink (CUDA IPC peer loads inside the fusion kernels, no copies)" if peer
+                                 else "exchanged by NCCL P2P per step (inside the timed region)", int(hmax[0].item()), n),
                "save": {"what": "sharded save: neighbours swap one raw tile row per boundary, every rank collapses ITS strip and copies it to pinned host memory; no rank holds the whole map",
                         "ms": sv, "mosaic_bytes": int(hull[1].item()), "value_incl_save": px / ((ms_step + sv) * 1e-3) / 1e6},
                "parity": parity}
@@ -633,6 +707,8 @@ def _strip_run(args, rank, world, local_rank, mode, seq, label, steps, warm, che
                           "what": "per rank: H2D of its own pinned host frames, halo exchange, m2d_feed_batch, sharded save (m2d_get_image_rect of its strip) + D2H of the strip"}
     sm.map.close()
     del buf, mine, sink_state
+    if peer:
+        sm.unshare_frames()
     sm._save_buf = None
     torch.cuda.empty_cache()
     return out

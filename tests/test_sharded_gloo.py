@@ -42,7 +42,7 @@ def _worker(rank, world, port, typ, distributed_input, q, backend="gloo"):
         else:
             factory, device, tdev = (lambda t, **kw: O.OracleMap2D.create(t, **kw)), None, torch.device("cpu")
         from pi_slam_fusion_b200.sharded import DeliveryPlan, even_split
-        if distributed_input == "owned":   # a longer strip survey, so that some frames are needed by one rank only
+        if distributed_input in ("owned", "peer"):   # a longer strip survey, so that some frames are needed by one rank only
             seq = synth.Sequence(30, 320, 180, seed=23, jitter=True, fpl=3, prepare_frames=3, cross=0.9, along=0.6)
         else:
             seq = synth.Sequence(14, 320, 180, seed=21, jitter=True, fpl=4, prepare_frames=3, cross=0.9, along=0.6)
@@ -52,14 +52,21 @@ def _worker(rank, world, port, typ, distributed_input, q, backend="gloo"):
         poses = seq.poses.copy()
         poses[6, 3:] = [0.5, 0.5, 0.5, 0.5]  # rejected on every rank alike
         extra = {}
-        if distributed_input == "owned":
+        if distributed_input in ("owned", "peer"):
             rects, axis, span, origin = sm.align_strips(poses)
             plan = DeliveryPlan(rects, axis, span, world, even_split(seq.n, world), origin)
-            buf, mine = sm.alloc_owned_buffer(plan, seq.w, seq.h)
-            buf.fill_(7)  # halo slots start as garbage: they must be overwritten by the exchange
             lo, hi = plan.resident[rank]
-            mine.copy_(torch.from_numpy(seq.frames(range(lo, hi))))
-            res = sm.feed_all_owned(plan, buf, poses, seq.w, seq.h)
+            if distributed_input == "peer":   # CUDA only: halo frames are sampled in place from the neighbour's HBM (CUDA IPC)
+                mine, ptrs = sm.share_frames(plan, seq.w, seq.h)
+                mine.copy_(torch.from_numpy(seq.frames(range(lo, hi))).to(tdev))
+                torch.cuda.synchronize()
+                dist.barrier()
+                res = sm.feed_all_peer(plan, ptrs, poses, seq.w, seq.h)
+            else:
+                buf, mine = sm.alloc_owned_buffer(plan, seq.w, seq.h)
+                buf.fill_(7)  # halo slots start as garbage: they must be overwritten by the exchange
+                mine.copy_(torch.from_numpy(seq.frames(range(lo, hi))))
+                res = sm.feed_all_owned(plan, buf, poses, seq.w, seq.h)
             extra = {"hull": plan.hull, "moved": plan.frames_moved(), "n": seq.n}
             # sharded save BEFORE any gather: every rank collapses its own strip (+ one halo tile row from its neighbours)
             before = sm.map.tile_count()
@@ -112,6 +119,8 @@ def _worker(rank, world, port, typ, distributed_input, q, backend="gloo"):
                 sh = out.pop("sharded_mosaic")
                 out["sharded_save_equal"] = bool(sh.shape == ia[0].shape and np.array_equal(sh, ia[0]))
                 out["sharded_save_bbox_ok"] = bool(ref.tile_bbox() == out["gbox"])
+        if distributed_input == "peer":
+            sm.unshare_frames()
         q.put(out)
     finally:
         dist.destroy_process_group()

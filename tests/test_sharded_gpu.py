@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("typ", [1, 3])
-@pytest.mark.parametrize("delivery", [False, True, "owned"])
+@pytest.mark.parametrize("delivery", [False, True, "owned", "peer"])
 def test_two_gpu_sharded_equals_oracle(typ, delivery):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
