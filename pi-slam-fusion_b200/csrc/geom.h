@@ -133,8 +133,9 @@ M2D_HD bool invert3x3(const double* s, double* t) {
 
 // renderFrame part 1: corner rays, obliqueness test, ground hits, bbox, tile range, homography.
 // Tile indices are computed against `g` as it is; the caller applies spreadMap (host) when the bbox leaves it
-// and then calls again.
-M2D_HD void frame_bounds(const GridGeom& g, const double* pose7, FrameBounds* out) {
+// and then calls again.  with_homography = false stops after the tile range (ok, x0..y1, gx0..gy1 are final, hinv stays 0):
+// all a pose-only feed or a dry run needs, at a third of the cost.
+M2D_HD void frame_bounds(const GridGeom& g, const double* pose7, FrameBounds* out, bool with_homography = true) {
     out->ok = 0;
     out->x0 = out->y0 = out->x1 = out->y1 = -1;
     for (int i = 0; i < 9; i++) out->hinv[i] = 0;
@@ -161,16 +162,26 @@ M2D_HD void frame_bounds(const GridGeom& g, const double* pose7, FrameBounds* ou
     out->gx0 = xmin; out->gy0 = ymin; out->gx1 = xmax; out->gy1 = ymax;
     int xi0 = (int)floor((xmin - g.min_x) * g.ele_size_inv), yi0 = (int)floor((ymin - g.min_y) * g.ele_size_inv);
     int xi1 = (int)ceil((xmax - g.min_x) * g.ele_size_inv), yi1 = (int)ceil((ymax - g.min_y) * g.ele_size_inv);
-    double ox = g.min_x + g.ele_size * xi0, oy = g.min_y + g.ele_size * yi0;
-    float srcp[8], dstp[8];
-    for (int i = 0; i < 4; i++) {
-        srcp[2 * i] = (float)ipx[i]; srcp[2 * i + 1] = (float)ipy[i];
-        dstp[2 * i] = (float)((px[i] - ox) * g.length_pixel_inv);
-        dstp[2 * i + 1] = (float)((py[i] - oy) * g.length_pixel_inv);
+    if (!with_homography) {
+        // The full path also rejects a frame whose homography cannot be solved (LU pivot below 100 eps), which only happens
+        // when the four ground hits are (nearly) collinear, e.g. a camera centre ON the plane.  Every shard must take the
+        // same decision, so a quad that is anywhere near degenerate goes through the full path after all.
+        const double area2 = fabs((px[3] - px[0]) * (py[2] - py[1]) - (px[2] - px[1]) * (py[3] - py[0]));   // 2 * area, from the diagonals
+        const double ext = (xmax - xmin) * (xmax - xmin) + (ymax - ymin) * (ymax - ymin);
+        if (!(area2 > 1e-6 * ext)) with_homography = true;
     }
-    double M[9];
-    if (!perspective_from_points(srcp, dstp, M)) return;
-    if (!invert3x3(M, out->hinv)) return;
+    if (with_homography) {
+        double ox = g.min_x + g.ele_size * xi0, oy = g.min_y + g.ele_size * yi0;
+        float srcp[8], dstp[8];
+        for (int i = 0; i < 4; i++) {
+            srcp[2 * i] = (float)ipx[i]; srcp[2 * i + 1] = (float)ipy[i];
+            dstp[2 * i] = (float)((px[i] - ox) * g.length_pixel_inv);
+            dstp[2 * i + 1] = (float)((py[i] - oy) * g.length_pixel_inv);
+        }
+        double M[9];
+        if (!perspective_from_points(srcp, dstp, M)) return;
+        if (!invert3x3(M, out->hinv)) return;
+    }
     out->x0 = xi0; out->y0 = yi0; out->x1 = xi1; out->y1 = yi1;
     out->ok = 1;
 }

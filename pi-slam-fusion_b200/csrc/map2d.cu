@@ -1190,11 +1190,11 @@ int m2d_feed_poses(m2d_handle h, int n, const double* poses, int* result) {
             if (!m.valid) break;
             FrameBounds fb;
             const double* pose = poses + 7 * (size_t)i;
-            frame_bounds(m.g, pose, &fb);
+            frame_bounds(m.g, pose, &fb, false);   // no pixels: the homography is not needed
             if (!fb.ok) break;
             if (fb.gx0 < m.g.min_x || fb.gx1 > m.g.max_x || fb.gy0 < m.g.min_y || fb.gy1 > m.g.max_y) {
                 if (m.spread(fb.gx0, fb.gy0, fb.gx1, fb.gy1) != M2D_OK) break;
-                frame_bounds(m.g, pose, &fb);
+                frame_bounds(m.g, pose, &fb, false);   // no pixels: the homography is not needed
                 if (!fb.ok) break;
             }
             if (fb.x0 < 0 || fb.y0 < 0 || fb.x1 > m.g.w || fb.y1 > m.g.h || fb.x0 >= fb.x1 || fb.y0 >= fb.y1) break;
@@ -1225,12 +1225,12 @@ int m2d_plan_rects(m2d_handle h, int n, const double* poses, int* rects) {
         r[0] = r[1] = r[2] = r[3] = -1;
         FrameBounds fb;
         const double* pose = poses + 7 * (size_t)i;
-        frame_bounds(g, pose, &fb);
+        frame_bounds(g, pose, &fb, false);
         if (!fb.ok) continue;
         if (fb.gx0 < g.min_x || fb.gx1 > g.max_x || fb.gy0 < g.min_y || fb.gy1 > g.max_y) {
             int dx, dy;
             if (grow_geom(g, org_x, org_y, fb.gx0, fb.gy0, fb.gx1, fb.gy1, &dx, &dy) != M2D_OK) continue;
-            frame_bounds(g, pose, &fb);
+            frame_bounds(g, pose, &fb, false);
             if (!fb.ok) continue;
         }
         if (fb.x0 < 0 || fb.y0 < 0 || fb.x1 > g.w || fb.y1 > g.h || fb.x0 >= fb.x1 || fb.y0 >= fb.y1) continue;
