@@ -337,7 +337,7 @@ class ShardedMap2D:
             self._frames.free()
             self._frames = None
 
-    def feed_all_peer(self, plan, ptrs, poses, w, h):
+    def feed_all_peer(self, plan, ptrs, poses, w, h, sync=True):
         """One pass over the whole sequence with share_frames() delivery: poses only outside the rank's hull, ONE
         m2d_feed_batch_ptrs inside it (own frames by local address, halo frames by their mapped peer address).  No
         collective, no copy: the only inter-GPU traffic are the kernels' own loads."""
@@ -351,7 +351,8 @@ class ShardedMap2D:
             res[a:b] = self.map.feed_batch_ptrs(ptrs[a:b], w, h, w * 3, poses[a:b], True)
         if b < n:
             res[b:] = self.map.feed_poses(poses[b:])
-        self.map.sync()
+        if sync:   # (the frames are static inputs: back-to-back passes need no sync in between, the host may run ahead)
+            self.map.sync()
         return res
 
     # ---- sharded save: every rank collapses its own strip (+ halo rows from its neighbours); nobody holds the whole map ----
@@ -564,14 +565,15 @@ def _strip_run(args, rank, world, local_rank, mode, seq, label, steps, warm, che
     torch.cuda.synchronize()
     dist.barrier()
 
-    def step():
+    def step(sync=True):
         sm.map.reset()
         if peer:
-            return sm.feed_all_peer(plan, ptrs, seq.poses, W, H)
+            return sm.feed_all_peer(plan, ptrs, seq.poses, W, H, sync=sync)
         return sm.feed_all_owned(plan, buf, seq.poses, W, H)
 
     for _ in range(warm):
         res = step()
+    sm.map.sync()
     sampler = B.ClockSampler(local_rank)
     sampler.start()
     l0 = sm.map.launch_count()
@@ -581,7 +583,8 @@ def _strip_run(args, rank, world, local_rank, mode, seq, label, steps, warm, che
     ev0.record()
     t0 = time.perf_counter()
     for _ in range(steps):
-        res = step()           # ends with m2d_sync: the library's streams have drained
+        res = step(sync=False)   # like the 1-GPU bench: passes back to back, the host prepares pass i+1 while pass i is being fused
+    sm.map.sync()                # the library's streams have drained
     ev1.record()
     torch.cuda.synchronize()
     wall_ms = (time.perf_counter() - t0) * 1e3 / steps
