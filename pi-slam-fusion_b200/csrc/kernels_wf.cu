@@ -698,7 +698,8 @@ cudaError_t launch_mbc_entry_table(const GroupParams& p, int n_entries, cudaStre
 // (entry index per pyramid px, 0xFFFF = the state stands) and the frames' `win` cell flags; cmin gets the exact new
 // minimum of every revisited cell.  Cells without a competitive entry are skipped without a load.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) mbs_decide_kernel(const __grid_constant__ GroupParams p, const __grid_constant__ TileLayout lay) {
+constexpr int kDecideChunk = 3;
+__global__ void __launch_bounds__(256, 5) mbs_decide_kernel(const __grid_constant__ GroupParams p, const __grid_constant__ TileLayout lay) {
     const TileWork T = p.tiles[blockIdx.x];
     const CellMap m = cell_map(blockIdx.y, threadIdx.x, p.levels);
     if (!m.valid) return;
@@ -718,24 +719,52 @@ __global__ void __launch_bounds__(256) mbs_decide_kernel(const __grid_constant__
     } else { bw[0] = tw[0]; bw[1] = bw[2] = bw[3] = INFINITY; }
     int best[4] = {-1, -1, -1, -1};
     unsigned wins = 0;
+    // Candidates are taken kDecideChunk at a time: first their table entries, then their weights, only then the comparisons (in feed
+    // order).  A cell rarely has more than three or four competitive frames, so all loads of a thread are in flight together instead
+    // of one dependent chain (mask -> table -> weights) per candidate.
     for (int w = 0; w < p.mask_words; w++) {
         uint32_t bits = cm[w];
         while (bits) {
-            const int i = w * 32 + __ffs(bits) - 1;
-            bits &= bits - 1;
-            const EntryRef R = p.etable[(size_t)(T.first + i) * p.levels + l];
-            const int st = R.stride;
-            const float* qp = reinterpret_cast<const float*>(R.base) + (size_t)py * st + px;
-            const unsigned cw = !(T.fresh && i == 0);
-            if (quad) {
-                const float2 t0 = *reinterpret_cast<const float2*>(qp), t1 = *reinterpret_cast<const float2*>(qp + st);
-                const float s[4] = {t0.x, t0.y, t1.x, t1.y};
+            int idx[kDecideChunk];
 #pragma unroll
-                for (int k = 0; k < 4; k++)
-                    if (s[k] >= bw[k]) { bw[k] = s[k]; best[k] = i; wins += cw; }   // '>=' : MultiBandMap2DCPU.cpp:542
-            } else {
-                const float s = qp[0];
-                if (s >= bw[0]) { bw[0] = s; best[0] = i; wins += cw; }
+            for (int j = 0; j < kDecideChunk; j++) {
+                idx[j] = -1;
+                if (bits) { idx[j] = w * 32 + __ffs(bits) - 1; bits &= bits - 1; }
+            }
+            const float* qp[kDecideChunk];
+            int st[kDecideChunk];
+#pragma unroll
+            for (int j = 0; j < kDecideChunk; j++) {
+                qp[j] = nullptr; st[j] = 0;
+                if (idx[j] >= 0) {
+                    const EntryRef R = p.etable[(size_t)(T.first + idx[j]) * p.levels + l];
+                    st[j] = R.stride;
+                    qp[j] = reinterpret_cast<const float*>(R.base) + (size_t)py * R.stride + px;
+                }
+            }
+            float2 t0[kDecideChunk], t1[kDecideChunk];
+#pragma unroll
+            for (int j = 0; j < kDecideChunk; j++) {
+                t0[j] = make_float2(-INFINITY, -INFINITY); t1[j] = t0[j];
+                if (idx[j] >= 0) {
+                    if (quad) { t0[j] = *reinterpret_cast<const float2*>(qp[j]); t1[j] = *reinterpret_cast<const float2*>(qp[j] + st[j]); }
+                    else t0[j].x = qp[j][0];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kDecideChunk; j++) {
+                if (idx[j] < 0) continue;
+                const int i = idx[j];
+                const unsigned cw = !(T.fresh && i == 0);
+                if (quad) {
+                    const float s[4] = {t0[j].x, t0[j].y, t1[j].x, t1[j].y};
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        if (s[k] >= bw[k]) { bw[k] = s[k]; best[k] = i; wins += cw; }   // '>=' : MultiBandMap2DCPU.cpp:542
+                } else {
+                    const float s = t0[j].x;
+                    if (s >= bw[0]) { bw[0] = s; best[0] = i; wins += cw; }
+                }
             }
         }
     }
