@@ -78,6 +78,12 @@ typedef struct m2d_config {
                             reference's OpenCV: scalar rows, SSE columns; default), 1 = OpenCV 4.x (universal intrinsics:
                             what the cv2 4.13 in this image executes) -- only there to diff the GPU path against REAL
                             OpenCV end to end (tests/test_golden.py); differences are <= 2 ulp of a weight */
+    /* TypeRender only (Map2DRender.cpp:52-310, the inline MultiBandBlender): */
+    int render_blend;    /* 0 = what the reference executes: CV_32F weights, per level `if (w >= dst_w) take src` (:206-213; default);
+                            1 = the disabled `#else` branch == stock OpenCV with CV_32F weights: dst += short(src * w), normalise
+                            (:214-220, 264-267); 2 = the CV_16S branch == stock OpenCV with CV_16S weights: dst += short((src * w)
+                            >> 8), dst_w += w, normalise (:227-249).  1 and 2 equal cv::detail::MultiBandBlender bit for bit */
+    int render_bands;    /* 0 = the reference's rule: ceil(log2(sqrt(canvas area) * 5 / 100)) - 1 (:707-715); > 0 overrides */
 } m2d_config;
 
 /* Algorithmic-traffic counters, SURVEY.md §8(d). Filled by the oracle always and by the CUDA library when

@@ -278,7 +278,9 @@ void pyr_down_s16(const int16_t* src, int rows, int cols, int cn, int16_t* dst) 
 // cv::pyrDown for CV_32F, OpenCV 2.4.9 association (x86-64 always has SSE):
 //   horizontal (scalar code):  row = s[2x]*6 + (s[2x-1] + s[2x+1])*4 + s[2x-2] + s[2x+2]      (left to right)
 //   vertical (PyrDownVec_32f): ((r0 + r4) + (r2 + r2)) + ((r1 + r3) + r2)*4,  then * (1/256)
-// (every level width in this application is a multiple of 8, so the SSE body covers whole rows.)
+// (the SSE body takes 8 columns per iteration; the remaining ocols % 8 columns use the scalar expression
+//  r2*6 + (r1 + r3)*4 + r0 + r4.  Tile-path levels of <= 5 bands are multiples of 8 wide; deeper levels and
+//  Map2DRender's sub-images are not.)
 void pyr_down_f32(const float* src, int rows, int cols, float* dst) {
     int orows = (rows + 1) / 2, ocols = (cols + 1) / 2;
     // OpenCV 4.x (g_f32_mode 1): columns [1, 1+4k) with 1+4k <= width0 go through PyrDownVecH (4 lanes):
@@ -286,7 +288,7 @@ void pyr_down_f32(const float* src, int rows, int cols, float* dst) {
     //   first (ocols/4)*4 columns use the vector form below, the tail the scalar form.
     int width0 = std::min((cols - 3) / 2 + 1, ocols);
     int hvec_end = (g_f32_mode == 1 && width0 > 1) ? 1 + ((width0 - 1) / 4) * 4 : 0;  // vector cols: [1, hvec_end)
-    int vvec_end = (g_f32_mode == 1) ? (ocols / 4) * 4 : ocols;
+    int vvec_end = (g_f32_mode == 1) ? (ocols / 4) * 4 : (ocols / 8) * 8;  // 2.4.9: PyrDownVec_32f takes 8 columns per step
 #pragma omp parallel for num_threads(g_threads) schedule(static)
     for (int y = 0; y < orows; y++) {
         std::vector<float> h((size_t)5 * ocols);
@@ -724,6 +726,10 @@ bool Map::tile_bbox(int& minx, int& miny, int& maxx, int& maxy) const {
 
 }  // namespace
 
+#define RENDER_ORACLE_PART 1
+#include "render_oracle.inl"  // Map2DRender (type 4): warps, blender, renderFrames
+#undef RENDER_ORACLE_PART
+
 // ---------------------------------------------------------------------------------------------------
 // extern "C" surface (mirrors include/map2d_b200.h with the orc_ prefix, plus the primitives)
 // ---------------------------------------------------------------------------------------------------
@@ -754,12 +760,12 @@ void orc_pyrup_s16(const int16_t* src, int rows, int cols, int cn, int16_t* dst)
 void orc_weight_image_u8(int w, int h, int weight_type, uint8_t* out) { weight_image_u8(w, h, weight_type, out); }
 void orc_weight_image_f32(int w, int h, int weight_type, float* out) { weight_image_f32(w, h, weight_type, out); }
 
-struct orc_map { Map m; };
+struct orc_map { Map m; RenderState rs; };
 
 int orc_create(int type, const m2d_config* cfg, orc_map** out) {
     *out = nullptr;
     if (type == M2D_TYPE_GPU) type = M2D_TYPE_CPU;  // Map2D.cpp:57-65
-    if (type != M2D_TYPE_CPU && type != M2D_TYPE_MULTIBAND) return M2D_ERR_UNSUPPORTED;
+    if (type != M2D_TYPE_CPU && type != M2D_TYPE_MULTIBAND && type != M2D_TYPE_RENDER) return M2D_ERR_UNSUPPORTED;
     if (cfg && cfg->force_float) return M2D_ERR_UNSUPPORTED;
     orc_map* o = new orc_map();
     o->m.type = type;
@@ -779,6 +785,7 @@ int orc_prepare(orc_map* o, const double* plane, const double* cam, int n, const
     return M2D_OK;
 }
 int orc_feed(orc_map* o, const uint8_t* bgr, int w, int h, size_t stride, const double* pose) {
+    if (o->m.type == M2D_TYPE_RENDER) return M2D_REJECTED;  // Map2DRender::renderFrame is `return false` (Map2DRender.cpp:464-467)
     return o->m.feed(bgr, w, h, stride, pose) ? M2D_OK : M2D_REJECTED;
 }
 int orc_plan_rects(orc_map* o, int n, const double* poses, int* rects) {  // stand-in for m2d_plan_rects
@@ -1092,5 +1099,9 @@ int orc_compute_bounds(orc_map* o, int n, const double* poses, int* rects, doubl
     }
     return M2D_OK;
 }
+
+#define RENDER_ORACLE_PART 2
+#include "render_oracle.inl"  // orc_render_*: stand-ins for m2d_render_*
+#undef RENDER_ORACLE_PART
 
 }  // extern "C"

@@ -21,7 +21,8 @@ class Config(C.Structure):
                 ("band_number", C.c_int), ("force_float", C.c_int), ("background", C.c_int),
                 ("thread", C.c_int), ("device", C.c_int), ("shard_rank", C.c_int), ("shard_count", C.c_int),
                 ("shard_axis", C.c_int), ("shard_span", C.c_int), ("collect_stats", C.c_int),
-                ("batch_frames", C.c_int), ("f32_mode", C.c_int)]
+                ("batch_frames", C.c_int), ("f32_mode", C.c_int), ("render_blend", C.c_int),
+                ("render_bands", C.c_int)]
 
 
 class Stats(C.Structure):
@@ -48,8 +49,9 @@ def default_config(**kw):
 def build(force=False):
     src = os.path.join(_HERE, "map2d_oracle.cpp")
     hdr = os.path.join(_HERE, "..", "include", "map2d_b200.h")
+    inl = os.path.join(_HERE, "render_oracle.inl")
     if (not force and os.path.exists(_LIB_PATH)
-            and os.path.getmtime(_LIB_PATH) >= max(os.path.getmtime(src), os.path.getmtime(hdr))):
+            and os.path.getmtime(_LIB_PATH) >= max(os.path.getmtime(src), os.path.getmtime(hdr), os.path.getmtime(inl))):
         return _LIB_PATH
     subprocess.check_call(["make", "-C", _HERE, "-B", "libmap2d_oracle.so"], stdout=subprocess.DEVNULL)
     return _LIB_PATH
@@ -107,6 +109,13 @@ def lib():
         L.orc_weight_image_u8.restype = None
         L.orc_weight_image_f32.argtypes = [C.c_int, C.c_int, C.c_int, vp]
         L.orc_weight_image_f32.restype = None
+        for n in ("orc_warp_u8c3_reflect", "orc_warp_u8c1_nearest"):
+            getattr(L, n).argtypes = [vp, C.c_int, C.c_int, dp, vp, C.c_int, C.c_int]
+        L.orc_render_weight_image.argtypes = [C.c_int, C.c_int, vp]
+        L.orc_render_weight_image.restype = None
+        L.orc_render_frames.argtypes = [vp, C.c_int, vp, C.c_size_t, C.c_int, C.c_int, C.c_size_t, dp, ip]
+        L.orc_render_get.argtypes = [vp, vp, vp, ip, ip, ip, ip, ip]
+        L.orc_render_warped.argtypes = [vp, C.c_int, vp, vp, ip, ip, ip, ip]
         _lib = L
     return _lib
 
@@ -191,6 +200,23 @@ def pyrup_s16(a):
     return out
 
 
+def warp_u8c3_reflect(src, M, dsize):
+    """cv2.warpPerspective(8UC3, INTER_LINEAR, BORDER_REFLECT) -- Map2DRender.cpp:586"""
+    return _warp(lib().orc_warp_u8c3_reflect, src, M, dsize, np.uint8, 3)
+
+
+def warp_u8c1_nearest(src, M, dsize):
+    """cv2.warpPerspective(8UC1, INTER_NEAREST, BORDER_CONSTANT 0) -- Map2DRender.cpp:587"""
+    return _warp(lib().orc_warp_u8c1_nearest, src, M, dsize, np.uint8, 1)
+
+
+def render_weight_image(w, h):
+    """The 8-bit weight image of Map2DRender::renderFrames (Map2DRender.cpp:507-529)."""
+    out = np.zeros((h, w), np.uint8)
+    lib().orc_render_weight_image(w, h, out.ctypes.data)
+    return out
+
+
 def weight_image_u8(w, h, weight_type=0):
     out = np.zeros((h, w), np.uint8)
     lib().orc_weight_image_u8(w, h, weight_type, out.ctypes.data)
@@ -204,7 +230,7 @@ def weight_image_f32(w, h, weight_type=0):
 
 
 # ---------------------------------------------------------------- the Map2D object
-TYPE_CPU, TYPE_GPU, TYPE_MULTIBAND = 1, 2, 3
+TYPE_CPU, TYPE_GPU, TYPE_MULTIBAND, TYPE_RENDER = 1, 2, 3, 4
 
 
 class OracleMap2D:
@@ -239,6 +265,37 @@ class OracleMap2D:
         assert img.dtype == np.uint8 and img.ndim == 3 and img.shape[2] == 3 and img.strides[2] == 1 and img.strides[1] == 3
         pose = np.ascontiguousarray(pose, np.float64).reshape(7)
         return lib().orc_feed(self._h, img.ctypes.data, img.shape[1], img.shape[0], img.strides[0], _dptr(pose)) == 0
+
+    # ---- Map2DRender (type 4): one batch -> one blended canvas (Map2DRender.cpp:479-760)
+    def render_frames(self, frames, poses):
+        frames = np.ascontiguousarray(frames, np.uint8)
+        assert frames.ndim == 4 and frames.shape[3] == 3
+        poses = np.ascontiguousarray(poses, np.float64).reshape(-1, 7)
+        n, h, w = frames.shape[:3]
+        res = np.zeros(max(n, 1), np.int32)
+        rc = lib().orc_render_frames(self._h, n, frames.ctypes.data, w * h * 3, w, h, w * 3, _dptr(poses),
+                                     res.ctypes.data_as(C.POINTER(C.c_int)))
+        return rc, res[:n]
+
+    def render_get(self):
+        """(result int16 HxWx3, mask u8 HxW, num_bands, (tile_x0, tile_y0)) of the last render_frames, or None."""
+        w, h, nb, tx, ty = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        if lib().orc_render_get(self._h, None, None, C.byref(w), C.byref(h), C.byref(nb), C.byref(tx), C.byref(ty)) != 0:
+            return None
+        res = np.zeros((h.value, w.value, 3), np.int16)
+        mask = np.zeros((h.value, w.value), np.uint8)
+        lib().orc_render_get(self._h, res.ctypes.data, mask.ctypes.data, None, None, None, None, None)
+        return res, mask, nb.value, (tx.value, ty.value)
+
+    def render_warped(self, i):
+        """(img u8 hxwx3, mask u8 hxw, (cx, cy)) handed to the blender for frame i, or None if the frame was skipped."""
+        iw, ih, cx, cy = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        if lib().orc_render_warped(self._h, i, None, None, C.byref(iw), C.byref(ih), C.byref(cx), C.byref(cy)) != 0:
+            return None
+        img = np.zeros((ih.value, iw.value, 3), np.uint8)
+        mask = np.zeros((ih.value, iw.value), np.uint8)
+        lib().orc_render_warped(self._h, i, img.ctypes.data, mask.ctypes.data, C.byref(iw), C.byref(ih), C.byref(cx), C.byref(cy))
+        return img, mask, (cx.value, cy.value)
 
     def grid(self):
         w, h, lp = C.c_int(), C.c_int(), C.c_double()

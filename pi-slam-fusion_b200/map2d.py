@@ -28,7 +28,8 @@ class Config(C.Structure):
                 ("band_number", C.c_int), ("force_float", C.c_int), ("background", C.c_int),
                 ("thread", C.c_int), ("device", C.c_int), ("shard_rank", C.c_int), ("shard_count", C.c_int),
                 ("shard_axis", C.c_int), ("shard_span", C.c_int), ("collect_stats", C.c_int),
-                ("batch_frames", C.c_int), ("f32_mode", C.c_int)]
+                ("batch_frames", C.c_int), ("f32_mode", C.c_int), ("render_blend", C.c_int),
+                ("render_bands", C.c_int)]
 
 
 class Stats(C.Structure):
