@@ -491,6 +491,73 @@ def measure_cfg3(args, m2d, torch, local_rank, stream):
     return out
 
 
+def measure_render(args, m2d, torch, local_rank, stream, n=20):
+    """Map2DRender (type 4), ONE batch of n 1280x720 frames (the reference renders its prepare-frames, 10-20 of
+    them, as one batch) through m2d_render_frames: warp into per-frame boxes, sub-image pyramids, canvas blend, restore."""
+    _, _, w, h, seed, _ = CFG2
+    seq = synth.Sequence(n, w, h, seed=seed, jitter=True)
+    host, host_ptr = m2d.pinned_empty((n, h, w, 3))
+    for k in range(n):
+        host[k] = seq.frame(k)
+    dev = torch.from_numpy(host).cuda()
+    out = {"workload": "Map2DRender batch: %d synthetic %dx%d frames, pose jitter, selection blend (what the reference executes), auto band count" % (n, w, h),
+           "unit": UNIT}
+    m = m2d.Map2D.create(m2d.Map2D.TypeRender, thread=False, device=local_rank)
+    m.set_stream(stream.cuda_stream)
+    assert m.prepare(seq.plane, seq.camera, seq.prepare_poses)
+
+    def step():
+        return m.render_frames(dev.data_ptr(), seq.poses, on_device=True, w=w, h=h)
+
+    for _ in range(3):
+        rc, res = step()
+    m.sync()
+    l0 = m.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    reps = max(3, min(args.steps, 10))
+    ev0.record(stream)
+    for _ in range(reps):
+        step()
+    ev1.record(stream)
+    m.sync()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / reps
+    fused = int((res == 0).sum())
+    r16, mask, nb, org = m.render_get()
+    out.update({"value": fused * w * h / (ms * 1e-3) / 1e6, "ms_per_step": ms, "steps": reps, "frames_blended": fused, "bands": nb,
+                "canvas": [int(r16.shape[1]), int(r16.shape[0])], "gpu_launches": int((m.launch_count() - l0) // reps)})
+    # e2e: host frames in, 8-bit canvas out
+    t0 = time.perf_counter()
+    for _ in range(3):
+        m.render_frames(host, seq.poses)
+        img, _ = m.get_image()
+    e2e_ms = (time.perf_counter() - t0) / 3 * 1e3
+    out["e2e"] = {"value": fused * w * h / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(host.nbytes),
+                  "d2h_bytes_per_step": int(img.nbytes)}
+    if not args.no_cpu:
+        from oracle import oracle as O
+        threads = os.cpu_count() or 1
+        O.set_threads(threads)
+        o = O.OracleMap2D(O.TYPE_RENDER)
+        assert o.prepare(seq.plane, seq.camera, seq.prepare_poses)
+        t0 = time.perf_counter()
+        o.render_frames(host, seq.poses)
+        dt = time.perf_counter() - t0
+        O.set_threads(1)
+        ref16, refmask, refnb, reforg = o.render_get()
+        same = bool(refnb == nb and reforg == org and np.array_equal(ref16, r16) and np.array_equal(refmask, mask))
+        out["cpu_baseline"] = {"value": fused * w * h / dt / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
+                               "sample": "the whole batch, oracle/render_oracle.inl (warps and pyramids OpenMP, blend loop serial; %.1f s)" % dt}
+        out["parity"] = {"checked": "the blender's CV_16SC3 result + mask of the whole batch vs the CPU oracle", "identical": same,
+                         "sha256_gpu": sha(r16), "sha256_oracle": sha(ref16)}
+    m.close()
+    del dev
+    m2d.free_pinned(host_ptr)
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -558,6 +625,10 @@ def main():
             line["stream_latency"] = sl
         if args.cfg3_frames > 0:
             line["cfg3"] = measure_cfg3(args, m2d, torch, local_rank, stream)
+        try:
+            line["render"] = measure_render(args, m2d, torch, local_rank, stream)
+        except Exception as e:   # a sub-run must not cost the headline line
+            line["render"] = {"error": "%s: %s" % (type(e).__name__, e)}
     print(json.dumps(line))
 
 

@@ -16,6 +16,10 @@
  *   starts out holding the prepare-frames, Map2D.cpp:42, which the worker therefore renders first)
  *                                            -> m2d_ingest_open_seeded(20, n) + m2d_ingest_push of every prepare-frame
  *                                               at prepare(); feed() = m2d_ingest_push
+ *   Map2D::TypeRender (Map2DRender.cpp)      -> prepare(thread=true) hands the prepare-frames to m2d_render_frames as the ONE batch
+ *                                               the reference's worker renders before it stops (:419-420, 758, 812-829) and
+ *                                               writes "result.png" (reference: "result.jpg", :748); feed() only queues
+ *                                               (thread=true, :446-452) or returns false (thread=false, :464-467)
  *   Map2D::draw()                            -> no-op (GL is out of scope); its data path is m2d_poll_changed +
  *                                               m2d_get_tile_image (changed tiles, blended textures) and
  *                                               m2d_tile_gps_corners (the Map2DUpdate overlay corners)
@@ -23,6 +27,7 @@
 #ifndef MAP2D_B200_ADAPTER_H
 #define MAP2D_B200_ADAPTER_H
 
+#include <algorithm>
 #include <deque>
 #include <iostream>
 #include <string>
@@ -34,14 +39,14 @@
 
 class Map2DB200 : public Map2D {
 public:
-    /* type: Map2D::TypeCPU / TypeGPU (weighted) or TypeMultiBandCPU.  The svar keys the CPU classes read
+    /* type: Map2D::TypeCPU / TypeGPU (weighted), TypeMultiBandCPU or TypeRender.  The svar keys the CPU classes read
      * (Map2DCPU.cpp:75,246; MultiBandMap2DCPU.cpp:228,235,260,444,840) are copied into the config once. */
-    explicit Map2DB200(int type, bool thread = true, int device = 0) : _h(NULL), _thread(thread) {
+    explicit Map2DB200(int type, bool thread = true, int device = 0) : _h(NULL), _thread(thread), _type(type) {
         std::vector<int> devices(1, device);
         init(type, thread, devices);
     }
     /* Several GPUs behind the same object (one host process, tiles sharded over the devices): m2d_create_multi. */
-    Map2DB200(int type, bool thread, const std::vector<int>& devices) : _h(NULL), _thread(thread) { init(type, thread, devices); }
+    Map2DB200(int type, bool thread, const std::vector<int>& devices) : _h(NULL), _thread(thread), _type(type) { init(type, thread, devices); }
     virtual ~Map2DB200() { m2d_destroy(_h); }
 
 private:
@@ -73,8 +78,9 @@ public:
             pose7(it->second, &poses[7 * i]);
         /* A second prepare() swaps in a new Prepare object with its own frame deque (Map2DCPU.cpp:105-125): whatever
          * was still queued for the old map is never rendered.  So: discard the old queue BEFORE the grid is replaced. */
-        if (_thread) m2d_ingest_abort(_h);
+        if (_thread && _type != M2D_TYPE_RENDER) m2d_ingest_abort(_h);
         if (m2d_prepare(_h, p, cam, (int)frames.size(), poses.empty() ? NULL : &poses[0]) != M2D_OK) return false;
+        if (_type == M2D_TYPE_RENDER) return _thread ? renderBatch(frames) : true;
         if (!_thread) return true;   /* thread=false: the prepare-frames are never rendered (only feed() renders) */
         /* thread=true: the reference starts its worker here (Map2DCPU.cpp:119-120).  Map2DPrepare::_frames is both the
          * prepare set and the worker's queue (Map2D.cpp:42-47), so the worker renders the prepare-frames first, in
@@ -101,6 +107,7 @@ public:
         }
         double p[7];
         pose7(pose, p);
+        if (_type == M2D_TYPE_RENDER && _thread) return true;   /* queued, never rendered: the worker stopped after its first batch */
         if (_thread) return m2d_ingest_push(_h, img.data, img.cols, img.rows, img.step, 3, p) == M2D_OK;  /* enqueue only */
         return m2d_feed(_h, img.data, img.cols, img.rows, img.step, p) == M2D_OK;
     }
@@ -110,8 +117,8 @@ public:
     /* thread=true: frames still queued are fused first (the reference would save without them). */
     virtual bool save(const std::string& filename) {
         if (!_h) return false;
-        if (_thread) m2d_ingest_drain(_h);
-        return m2d_save(_h, filename.c_str()) == M2D_OK;
+        if (_thread && _type != M2D_TYPE_RENDER) m2d_ingest_drain(_h);
+        return m2d_save(_h, filename.c_str()) == M2D_OK;   /* (Map2DRender::save returns false; here the last canvas is written) */
     }
 
     virtual uint queueSize() { return _h ? (uint)m2d_queue_size(_h) : 0; }
@@ -119,7 +126,7 @@ public:
     /* Addition over the reference: the saved image in memory, BGRA (weighted) or BGR. */
     cv::Mat getImage(int* tile_min_x = NULL, int* tile_min_y = NULL) {
         int w, h, cn, tx, ty;
-        if (_h && _thread) m2d_ingest_drain(_h);
+        if (_h && _thread && _type != M2D_TYPE_RENDER) m2d_ingest_drain(_h);
         if (!_h || m2d_get_image(_h, NULL, &w, &h, &cn, &tx, &ty) != M2D_OK) return cv::Mat();
         cv::Mat out(h, w, cn == 4 ? CV_8UC4 : CV_8UC3);
         if (m2d_get_image(_h, out.data, &w, &h, &cn, &tx, &ty) != M2D_OK) return cv::Mat();
@@ -131,6 +138,27 @@ public:
     m2d_handle handle() const { return _h; }
 
 private:
+    /* Map2DRender::run -> renderFrames(frames): everything queued -- at prepare() time, the prepare-frames -- is one batch. */
+    bool renderBatch(const std::deque<std::pair<cv::Mat, pi::SE3d> >& frames) {
+        if (frames.empty()) return true;
+        const cv::Mat& f0 = frames.front().first;
+        const size_t frame_bytes = (size_t)f0.cols * f0.rows * 3;
+        std::vector<unsigned char> pix(frame_bytes * frames.size());
+        std::vector<double> poses(frames.size() * 7);
+        int n = 0;
+        for (std::deque<std::pair<cv::Mat, pi::SE3d> >::const_iterator it = frames.begin(); it != frames.end(); ++it) {
+            const cv::Mat& img = it->first;
+            if (img.type() != CV_8UC3 || !img.data || img.cols != f0.cols || img.rows != f0.rows) continue;
+            for (int y = 0; y < img.rows; y++)
+                std::copy(img.data + (size_t)y * img.step, img.data + (size_t)y * img.step + (size_t)img.cols * 3,
+                          pix.begin() + frame_bytes * n + (size_t)y * img.cols * 3);
+            pose7(it->second, &poses[7 * (size_t)n]);
+            n++;
+        }
+        if (!n || m2d_render_frames(_h, n, &pix[0], frame_bytes, f0.cols, f0.rows, (size_t)f0.cols * 3, &poses[0], 0, NULL) != M2D_OK) return false;
+        m2d_save(_h, "result.png");   /* cv::imwrite("result.jpg", result), Map2DRender.cpp:748 */
+        return true;
+    }
     static void pose7(const pi::SE3d& s, double* o) { /* stream order x y z qx qy qz qw, SE3.h:105-117 */
         const pi::Point3d& t = s.get_translation();
         const pi::SO3d& r = s.get_rotation();
@@ -138,6 +166,7 @@ private:
     }
     m2d_handle _h;
     bool _thread;
+    int _type;
     Map2DB200(const Map2DB200&);
     Map2DB200& operator=(const Map2DB200&);
 };

@@ -42,7 +42,7 @@ extern "C" {
 #define M2D_MAX_LEVELS 9   /* BandNumber is clamped to ceil(log2(256)) = 8 -> 9 stored levels */
 
 /* Map2D::Map2DType, Map2D.h:83. TypeGPU(2) behaves like TypeCPU(1): the reference build has no CUDA and
- * create(TypeGPU) hands back a Map2DCPU (Map2D.cpp:57-65). TypeRender(4) is out of scope. */
+ * create(TypeGPU) hands back a Map2DCPU (Map2D.cpp:57-65). TypeRender(4) is the batch blender of Map2DRender.cpp: it takes m2d_render_frames, not m2d_feed*. */
 enum { M2D_TYPE_NONE = 0, M2D_TYPE_CPU = 1, M2D_TYPE_GPU = 2, M2D_TYPE_MULTIBAND = 3, M2D_TYPE_RENDER = 4 };
 
 #define M2D_OK 0
@@ -107,7 +107,7 @@ typedef struct m2d_map* m2d_handle;
 
 void m2d_config_default(m2d_config* cfg);
 
-/* Map2D::create — Map2D.cpp:51-66. type NONE/RENDER -> M2D_ERR_UNSUPPORTED and *out = NULL. */
+/* Map2D::create — Map2D.cpp:51-66. type NONE -> M2D_ERR_UNSUPPORTED and *out = NULL. */
 int m2d_create(int type, const m2d_config* cfg, m2d_handle* out);
 /* Multi-GPU behind the boundary: ONE host process (the reference's host is one process: Map2D::create, Map2D.cpp:51-66), one
  * sub-map per device, tiles sharded by spatial ownership (block-cyclic strips of cfg->shard_span tiles along
@@ -237,6 +237,23 @@ int m2d_get_image_rect(m2d_handle h, uint8_t* out, int out_on_device, const int 
 int m2d_poll_changed(m2d_handle h, int max_tiles, int* xy /* 2 ints per tile */, int* n_out);
 int m2d_get_tile_image(m2d_handle h, int tx, int ty, int high_quality, uint8_t* out, int* channels);
 
+/* Map2DRender (Map2D::TypeRender = 4) -- Map2DFusion/Map2DRender.cpp.  The reference's feed() only queues (thread = true) or
+ * returns false (thread = false, renderFrame :464-467); its worker takes EVERYTHING queued -- the prepare-frames first -- as one
+ * batch through renderFrames (:479-760): every frame is warped into its own bounding box (8UC3 bilinear BORDER_REFLECT + the
+ * 8-bit weight image, nearest), the map is spread, and an inline copy of cv::detail::MultiBandBlender (:52-310) blends the
+ * batch onto a canvas of whole tiles with ceil(log2(sqrt(area) * 0.05)) - 1 bands (m2d_config.render_bands overrides); the
+ * result goes to "result.jpg" and the thread stops.  m2d_render_frames is that batch call: frame i at base + i * frame_stride
+ * (host or device memory), poses camera-to-world.  result[i] = M2D_OK, or M2D_REJECTED for a frame the reference skips
+ * (oblique view).  Not built: the GUI (cv::imshow / waitKey of every pyramid level, Map2DRender.ShowPyrLaplace) and the seam
+ * finder (Map2DRender.EnableSeam, cv::detail::DpSeamFinder: a sequential dynamic program) -- i.e. EnableSeam = 0.
+ * The blended canvas stays in the handle: m2d_get_image returns it as 8-bit BGR (what cv::imwrite stores), m2d_save writes a
+ * PNG instead of a JPEG, m2d_render_get returns the blender's raw outputs: the CV_16SC3 result (w*h*3 int16, masked px 0), its
+ * mask (w*h, 255 where the level-0 weight exceeds WEIGHT_EPS), the band count and the ABSOLUTE tile coordinate of the canvas
+ * origin.  m2d_feed* on a TypeRender handle return M2D_REJECTED like the reference. */
+int m2d_render_frames(m2d_handle h, int n, const uint8_t* base, size_t frame_stride, int w, int h_px, size_t stride,
+                      const double* poses /* n x 7 */, int on_device, int* result);
+int m2d_render_get(m2d_handle h, int16_t* result16, uint8_t* mask, int* w, int* h_px, int* num_bands, int* tile_x0, int* tile_y0);
+
 /* Checkpoint / resume of the mosaic (the reference can only save the final PNG; its SLAM map has
  * MapHash::save/load, GSLAM-DIYSLAM/src/zhaoyong/MapHash.cpp:376,458).  save_state writes the prepared grid
  * (camera, plane, extents, origin) and the raw state of every tile held by this handle; load_state restores them
@@ -258,7 +275,8 @@ enum { M2D_K_WEIGHTED = 0, M2D_K_MB_WARP = 1, M2D_K_MB_PYRDOWN = 2, M2D_K_MB_SEL
        /* weights-first multi-band pipeline (default): weight warp / weight pyramid / decide / propagate (weight + image side) /
         * sparse image warp / sparse image pyramid / winners' Laplacian / competitive-cell bounds */
        M2D_K_MBW_WARP = 7, M2D_K_MBW_PYR = 8, M2D_K_MBS_DECIDE = 9, M2D_K_MBS_PROPAGATE = 10, M2D_K_MBS_WARP = 11, M2D_K_MBS_PYR = 12,
-       M2D_K_MBS_LAP = 13, M2D_K_MBC_BOUNDS = 14 };
+       M2D_K_MBS_LAP = 13, M2D_K_MBC_BOUNDS = 14,
+       M2D_K_RENDER = 15 /* TypeRender: warp / pyramid / blend / normalise / final of m2d_render_frames */ };
 int m2d_profile(m2d_handle h, int enable);
 int m2d_get_kernel_times(m2d_handle h, double* ms /* M2D_KERNEL_CLASSES */, uint64_t* count /* M2D_KERNEL_CLASSES */);
 

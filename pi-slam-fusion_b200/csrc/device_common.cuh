@@ -43,20 +43,29 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 // shared sampling helpers
 // ---------------------------------------------------------------------------------------------------------
 // Row base of cv::warpPerspectiveInvoker for the 64-px block containing x: X0 = M0*xb + M1*y + M2, etc.
-struct RowBase { double X0, Y0, W0; };
+// When M6 == 0 (an affine or row-affine homography: every exactly nadir frame) the denominator W0 + M6*x1 is W0 itself for
+// every px of the row, bit for bit, so its reciprocal is taken ONCE per row segment instead of once per px.
+struct RowBase { double X0, Y0, W0, Winv; bool const_w; };
 __device__ __forceinline__ RowBase row_base(const double* M, int x, int y) {
     int xb = x & ~63;
     RowBase r;
     r.X0 = M[0] * xb + M[1] * y + M[2];
     r.Y0 = M[3] * xb + M[4] * y + M[5];
     r.W0 = M[6] * xb + M[7] * y + M[8];
+    r.const_w = M[6] == 0.0;
+    r.Winv = 0.0;
+    if (r.const_w) r.Winv = (r.W0 != 0.0) ? 1.0 / r.W0 : 0.0;
     return r;
 }
 // Un-quantised source coordinate of the px at offset x1 (as a double, exactly the int->double value OpenCV
 // multiplies by) inside the block.  INTER_LINEAR rounds 32*f, INTER_NEAREST rounds f (32/W == 32*(1/W) exactly).
 __device__ __forceinline__ void px_coord(const double* M, const RowBase& r, double x1, double& fx, double& fy) {
-    double W = r.W0 + M[6] * x1;
-    W = (W != 0.0) ? 1.0 / W : 0.0;
+    double W;
+    if (r.const_w) W = r.Winv;
+    else {
+        W = r.W0 + M[6] * x1;
+        W = (W != 0.0) ? 1.0 / W : 0.0;
+    }
     fx = (r.X0 + M[0] * x1) * W;
     fy = (r.Y0 + M[3] * x1) * W;
 }
@@ -276,7 +285,9 @@ __device__ __forceinline__ void lap_quad(const GroupParams& p, const FrameJob& J
 }
 
 // f32 pyrDown association (oracle: pyr_down_f32).  mode 0 = OpenCV 2.4.9: rows s0*6 + (s-1 + s1)*4 + s-2 + s2 left to right,
-// columns ((r0+r4)+(r2+r2)) + ((r1+r3)+r2)*4, scaled by 1/256 (PyrDownVec_32f).  mode 1 = OpenCV 4.x, whose SIMD bodies
+// columns ((r0+r4)+(r2+r2)) + ((r1+r3)+r2)*4, scaled by 1/256 (PyrDownVec_32f: 8 columns per step, the remaining ocols % 8
+// columns use the scalar r2*6 + (r1+r3)*4 + r0 + r4 -- only levels narrower than 8 px per tile and Map2DRender's sub-images
+// have such a tail).  mode 1 = OpenCV 4.x, whose SIMD bodies
 // cover output columns [1, hvec_end) horizontally -- s0*6 + ((s-1+s1)*4 + (s-2+s2)) -- and [0, vvec_end) vertically (same
 // expression as 2.4.9), the remaining columns using the scalar expressions.  U = output column in REGION coordinates.
 struct F32Assoc { int mode, hvec_end, vvec_end; };
@@ -285,7 +296,7 @@ __device__ __forceinline__ F32Assoc f32_assoc(int mode, int src_cols) {
     a.mode = mode;
     const int ocols = (src_cols + 1) / 2, width0 = min((src_cols - 3) / 2 + 1, ocols);
     a.hvec_end = (mode == 1 && width0 > 1) ? 1 + ((width0 - 1) / 4) * 4 : 0;
-    a.vvec_end = (mode == 1) ? (ocols / 4) * 4 : ocols;
+    a.vvec_end = (mode == 1) ? (ocols / 4) * 4 : (ocols / 8) * 8;   // 2.4.9's PyrDownVec_32f takes 8 columns per step, scalar tail
     return a;
 }
 __device__ __forceinline__ float pyr_h(const F32Assoc& a, int U, float sm2, float sm1, float s0, float sp1, float sp2) {

@@ -111,6 +111,34 @@ struct PasteItem {
     int tx, ty;                // tile position inside the mosaic
 };
 
+// ---- Map2DRender (type 4): the batch blender, Map2DRender.cpp:52-310 + 479-760 (kernels_render.cu) ----
+constexpr int kRenderMaxLevels = 16;
+struct RenderJob {               // one frame of a render batch
+    double hinv[9];              // px of the frame's own warped image -> source px (Map2DRender.cpp:579-586)
+    const uint8_t* raw;          // BGR8 source, sampled in place
+    int raw_stride;
+    int iw, ih;                  // size of the warped image (sizes[idx], :572)
+    int left, top;               // where it sits inside the bordered sub-image (copyMakeBorder, :147-151)
+    int x_tl, y_tl;              // the sub-image on the canvas, level 0 (multiples of 1 << num_bands, :118-139)
+    int sw, sh;                  // sub-image size, level 0 (multiples of 1 << num_bands)
+    unsigned long long g_off[kRenderMaxLevels];  // byte offsets in the batch scratch: packed u8x4 Gaussian of level l ...
+    unsigned long long w_off[kRenderMaxLevels];  // ... and its weight plane (f32, or s16 for render_blend 2)
+};
+struct RenderCanvas {            // dst_pyr_laplace_ / dst_band_weights_ (:87-100)
+    int levels;                  // num_bands + 1
+    int w[kRenderMaxLevels], h[kRenderMaxLevels];
+    int16_t* lap[kRenderMaxLevels][3];   // planar B, G, R
+    void* wgt[kRenderMaxLevels];         // f32, or s16 for render_blend 2
+};
+cudaError_t launch_rnd_weight_image(int sw, int sh, uint8_t* out, cudaStream_t stream);
+cudaError_t launch_rnd_warp(const RenderJob* d_jobs, int n_frames, int max_px, uint8_t* scratch, const uint8_t* wimg, int src_w, int src_h,
+                            int s16_weights, cudaStream_t stream);
+cudaError_t launch_rnd_pyrdown(const RenderJob* d_jobs, int n_frames, int max_px_l0, uint8_t* scratch, int level, int f32_mode, int s16_weights,
+                               cudaStream_t stream);
+cudaError_t launch_rnd_blend(const RenderJob* d_jobs, int n_frames, const uint8_t* scratch, const RenderCanvas& C, int blend, cudaStream_t stream);
+cudaError_t launch_rnd_normalize(const RenderCanvas& C, int blend, cudaStream_t stream);
+cudaError_t launch_rnd_final(const RenderCanvas& C, int s16_weights, int wf, int hf, int16_t* out16, uint8_t* out8, uint8_t* mask, cudaStream_t stream);
+
 // launchers (asynchronous on `stream`; return the launch error)
 cudaError_t launch_weight_images(int sw, int sh, int weight_type, uint8_t* alpha, float* wimg, cudaStream_t stream);
 cudaError_t launch_bounds(const GridGeom& g, int n, const double* d_poses, FrameBounds* d_out, cudaStream_t stream);

@@ -184,6 +184,23 @@ struct m2d_map {
     unsigned long long* d_stats = nullptr;  // [0..8] level wins, [16] footprint, [17] weighted wins
     m2d_stats stats{};
 
+    // Map2DRender (type 4): one batch -> one blended canvas.  Grow-only device buffers, the last result stays in HBM.
+    uint8_t* rnd_wimg = nullptr;            // 8-bit weight image of the camera size (Map2DRender.cpp:507-529)
+    int rnd_wimg_w = 0, rnd_wimg_h = 0;
+    uint8_t* rnd_canvas = nullptr;          // canvas pyramids (planar int16 Laplacians + weights) and the outputs
+    size_t rnd_canvas_cap = 0;
+    uint8_t* rnd_scratch = nullptr;         // sub-image pyramids of the frames of one chunk
+    size_t rnd_scratch_cap = 0;
+    uint8_t* rnd_raw = nullptr;             // staging of host frames (one chunk)
+    size_t rnd_raw_cap = 0;
+    uint8_t* rnd_jobs = nullptr;            // RenderJob array of one chunk
+    size_t rnd_jobs_cap = 0;
+    bool rnd_have = false;
+    int rnd_w = 0, rnd_h = 0, rnd_bands = 0, rnd_tx0 = 0, rnd_ty0 = 0;   // tx0, ty0: ABSOLUTE tile coordinate of the canvas origin
+    size_t rnd_off16 = 0, rnd_off8 = 0, rnd_offmask = 0;
+    int render_frames(int n, const uint8_t* base, size_t frame_stride, int w, int h, size_t stride, const double* poses, bool on_device,
+                      int* result);
+
     int init();
     void release();
     int prepare(const double* plane, const double* cam, int n, const double* poses);
@@ -253,7 +270,7 @@ int m2d_map::init() {
         lay = make_tile_layout(levels);
         tile_bytes = lay.bytes;
     } else {
-        tile_bytes = (size_t)kEle * kEle * 4;
+        tile_bytes = (size_t)kEle * kEle * 4;   // (TypeRender keeps no tiles: its state is the canvas of the last batch)
     }
     return M2D_OK;
 }
@@ -290,6 +307,11 @@ void m2d_map::release() {
     }
     if (d_stats) cudaFree(d_stats);
     if (d_collapse) cudaFree(d_collapse);
+    if (rnd_wimg) cudaFree(rnd_wimg);
+    if (rnd_canvas) cudaFree(rnd_canvas);
+    if (rnd_scratch) cudaFree(rnd_scratch);
+    if (rnd_raw) cudaFree(rnd_raw);
+    if (rnd_jobs) cudaFree(rnd_jobs);
     for (ProfRec& r : prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
     if (copy_stream) { cudaStreamSynchronize(copy_stream); cudaStreamDestroy(copy_stream); }
     if (decide_stream) { cudaStreamSynchronize(decide_stream); cudaStreamDestroy(decide_stream); }
@@ -360,6 +382,8 @@ int m2d_map::prepare(const double* plane7, const double* cam, int n, const doubl
     changed.assign((size_t)w * h, 0);
     last_rect[0] = last_rect[1] = last_rect[2] = last_rect[3] = -1;
     valid = true;
+    rnd_have = false;
+    if (type == M2D_TYPE_RENDER) return M2D_OK;   // no tiles: Map2DRenderData::_data is never filled (Map2DRender.cpp:479-760)
     // Pre-reserve pool slabs for a quarter of the prepared grid (prepare() doubles the pose bbox about its centre,
     // so ~1/4 of the grid is what the prepare-frames actually cover), capped at 2 GiB; failure here is not fatal.
     size_t want = std::min<size_t>(((size_t)w * h + 3) / 4, ((size_t)2 << 30) / tile_bytes);
@@ -556,6 +580,7 @@ int m2d_map::reset() {
     CU(cudaMemsetAsync(d_stats, 0, 32 * sizeof(unsigned long long), stream));
     memset(&stats, 0, sizeof stats);
     last_rect[0] = last_rect[1] = last_rect[2] = last_rect[3] = -1;
+    rnd_have = false;
     return M2D_OK;
 }
 
@@ -575,7 +600,7 @@ int m2d_map::feed_frames(int n, const uint8_t* base, size_t frame_stride, int w,
         mirror();
         return rc0;
     }
-    if (!valid) {                                         // Map2DCPU.cpp:129
+    if (!valid || type == M2D_TYPE_RENDER) {              // Map2DCPU.cpp:129; Map2DRender::renderFrame is `return false` (:464-467)
         stats.frames_fed += n;
         for (int i = 0; i < n && result; i++) result[i] = M2D_REJECTED;
         return M2D_REJECTED;
@@ -924,6 +949,15 @@ bool m2d_map::tile_bbox(int& x0, int& y0, int& x1, int& y1) const {
 int m2d_map::get_image(uint8_t* out, int* w, int* h, int* channels, int* tmx, int* tmy) {
     if (!subs.empty()) return multi_get_image(out, w, h, channels, tmx, tmy);
     if (!valid || g.w == 0 || g.h == 0) return M2D_REJECTED;
+    if (type == M2D_TYPE_RENDER) {   // the blended canvas of the last m2d_render_frames, 16S -> 8U like cv::imwrite / convertTo (:748-749)
+        if (!rnd_have) return M2D_REJECTED;
+        *w = rnd_w; *h = rnd_h; *channels = 3; *tmx = rnd_tx0 - org_x; *tmy = rnd_ty0 - org_y;
+        if (!out) return M2D_OK;
+        CU(cudaSetDevice(cfg.device));
+        CU(cudaMemcpyAsync(out, rnd_canvas + rnd_off8, (size_t)rnd_w * rnd_h * 3, cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
+        return M2D_OK;
+    }
     int x0, y0, x1, y1;
     if (!tile_bbox(x0, y0, x1, y1)) return M2D_REJECTED;
     *tmx = x0; *tmy = y0;
@@ -1066,10 +1100,11 @@ int m2d_create(int type, const m2d_config* cfg, m2d_handle* out) {
     if (!out) return M2D_ERR_ARG;
     *out = nullptr;
     if (type == M2D_TYPE_GPU) type = M2D_TYPE_CPU;  // Map2D.cpp:57-65: TypeGPU yields the Map2DCPU semantics
-    if (type != M2D_TYPE_CPU && type != M2D_TYPE_MULTIBAND) return M2D_ERR_UNSUPPORTED;
+    if (type != M2D_TYPE_CPU && type != M2D_TYPE_MULTIBAND && type != M2D_TYPE_RENDER) return M2D_ERR_UNSUPPORTED;
     m2d_config c;
     if (cfg) c = *cfg; else m2d_config_default(&c);
     if (c.force_float) return M2D_ERR_UNSUPPORTED;
+    if (type == M2D_TYPE_RENDER && (c.render_blend < 0 || c.render_blend > 2 || c.render_bands < 0 || c.shard_count > 1)) return M2D_ERR_ARG;
     if (c.f32_mode != 0 && c.f32_mode != 1) return M2D_ERR_ARG;
     if (c.scale == 0) c.scale = 1.0;
     if (c.shard_count < 1) c.shard_count = 1;
@@ -1097,6 +1132,7 @@ int m2d_create_multi(int type, const m2d_config* cfg, int n_devices, const int* 
     m2d_config c;
     if (cfg) c = *cfg; else m2d_config_default(&c);
     if (n_devices == 1) { c.device = devices[0]; return m2d_create(type, &c, out); }
+    if (type == M2D_TYPE_RENDER) return M2D_ERR_UNSUPPORTED;   // one batch, one canvas: a single device
     if (c.shard_count > 1) return M2D_ERR_ARG;   // the multi-device handle shards by itself
     if (c.shard_axis != 0 && c.shard_axis != 1) c.shard_axis = 1;
     if (c.shard_span < 1) c.shard_span = 4;
@@ -1305,6 +1341,7 @@ int m2d_ingest_open(m2d_handle h, int capacity, int start_paused) { return m2d_i
 int m2d_ingest_open_seeded(m2d_handle h, int capacity, int seed_frames, int start_paused) {
     if (!h || capacity < 1 || capacity > 4096 || seed_frames < 0 || seed_frames > 4096) return M2D_ERR_ARG;
     if (h->ingest) return M2D_ERR_STATE;
+    if (h->type == M2D_TYPE_RENDER) { h->err = "m2d_ingest_open: TypeRender renders ONE batch (m2d_render_frames), it has no streaming queue"; return M2D_ERR_UNSUPPORTED; }
     if (!h->valid) { h->err = "m2d_ingest_open: prepare() first (the frame size comes from the camera)"; return M2D_ERR_STATE; }
     if (cudaSetDevice(h->cfg.device) != cudaSuccess) return M2D_ERR_CUDA;
     Ingest* I = new Ingest();
@@ -1530,6 +1567,235 @@ int m2d_get_image(m2d_handle h, uint8_t* out, int* w, int* hpx, int* channels, i
         if ((long long)qw * qh * qc > cap) { h->err = "m2d_get_image: the mosaic grew since the size query; query again"; return M2D_ERR_STATE; }
     }
     return h->get_image(out, w, hpx, channels, tmx, tmy);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Map2DRender (TypeRender = 4) -- Map2DRender.cpp:479-760 renderFrames + the inline MultiBandBlender (:52-310), without the
+// GUI (imshow / waitKey) and the seam finder (Map2DRender.EnableSeam = 0).  Host part: the per-frame geometry in FP64 (the
+// same operations in the same order as the reference, so that sizes, corners and homographies are its bits), spreadMap, the
+// blender's sub-image bookkeeping (:103-139); device part: kernels_render.cu.
+// ---------------------------------------------------------------------------------------------------------
+int m2d_map::render_frames(int n, const uint8_t* base, size_t frame_stride, int w, int h, size_t stride, const double* poses, bool on_device,
+                           int* result) {
+    if (type != M2D_TYPE_RENDER || !subs.empty()) return M2D_ERR_STATE;
+    for (int i = 0; i < n && result; i++) result[i] = M2D_REJECTED;
+    stats.frames_fed += n;
+    if (!valid) return M2D_REJECTED;
+    if (!base || !poses || n <= 0) return M2D_ERR_ARG;
+    if (w != g.cam_w || h != g.cam_h) return M2D_REJECTED;
+    if (stride < (size_t)w * 3) return M2D_ERR_ARG;
+    CU(cudaSetDevice(cfg.device));
+    rnd_have = false;
+    if (rnd_wimg_w != w || rnd_wimg_h != h) {
+        CU(cudaStreamSynchronize(stream));
+        if (rnd_wimg) { CU(cudaFree(rnd_wimg)); rnd_wimg = nullptr; }
+        CU(cudaMalloc(&rnd_wimg, (size_t)w * h + 16));
+        LAUNCHK(M2D_K_RENDER, launch_rnd_weight_image(w, h, rnd_wimg, stream));
+        rnd_wimg_w = w; rnd_wimg_h = h;
+    }
+    // 1. per frame: ground quad, own bounding box, size, homography into the box (:536-603)
+    struct Geo { bool ok; int iw, ih; float cwx, cwy; double hinv[9]; };
+    std::vector<Geo> geo((size_t)n);
+    double gminx = 0, gminy = 0, gmaxx = 0, gmaxy = 0;   // pi::Point2d min,max start at (0,0) (:532)
+    const double lpi = g.length_pixel_inv;
+    for (int idx = 0; idx < n; idx++) {
+        Geo& F = geo[idx];
+        F.ok = false;
+        Pose f = pose_mul(g.plane_inv, pose_from7(poses + 7 * (size_t)idx));
+        const double ipx[4] = {0, g.cam_w, 0, g.cam_w}, ipy[4] = {0, 0, g.cam_h, g.cam_h};
+        double px[4], py[4];
+        const double down_z = (f.t.z < 0) ? 1.0 : -1.0;
+        bool ok = true;
+        for (int j = 0; j < 4; j++) {
+            Vec3 u; u.x = (ipx[j] - g.cx) * g.fxinv; u.y = (ipy[j] - g.cy) * g.fyinv; u.z = 1.;
+            Vec3 axis = qrot(f.r, u);
+            if (axis.x * 0.0 + axis.y * 0.0 + axis.z * down_z < 0.4) { ok = false; break; }
+            double s = f.t.z / axis.z;
+            px[j] = f.t.x - axis.x * s; py[j] = f.t.y - axis.y * s;
+        }
+        if (!ok) continue;
+        double cminx = 1e6, cminy = 1e6, cmaxx = -1e6, cmaxy = -1e6;
+        for (int i = 0; i < 4; i++) {
+            if (px[i] < cminx) cminx = px[i];
+            if (py[i] < cminy) cminy = py[i];
+            if (px[i] > cmaxx) cmaxx = px[i];
+            if (py[i] > cmaxy) cmaxy = py[i];
+        }
+        if (cminx < gminx) gminx = cminx;
+        if (cminy < gminy) gminy = cminy;
+        if (cmaxx > gmaxx) gmaxx = cmaxx;
+        if (cmaxy > gmaxy) gmaxy = cmaxy;
+        F.cwx = (float)cminx; F.cwy = (float)cminy;
+        F.iw = (int)((cmaxx - cminx) * lpi);
+        F.ih = (int)((cmaxy - cminy) * lpi);
+        if (F.iw <= 0 || F.ih <= 0) continue;
+        // cv::warpPerspective walks its destination in 64-px column blocks once it is >= 64 x 16 px (BLOCK_SZ 32: bh0 = min(16, h),
+        // bw0 = min(1024 / bh0, w)); the kernels assume that block base.  A warped frame smaller than that is not a survey frame.
+        if (F.iw < 64 || F.ih < 16) { err = "m2d_render_frames: a frame's footprint is below 64 x 16 px at this map scale"; if (result) result[idx] = M2D_ERR_UNSUPPORTED; continue; }
+        float srcp[8], dstp[8];
+        for (int i = 0; i < 4; i++) {
+            srcp[2 * i] = (float)ipx[i]; srcp[2 * i + 1] = (float)ipy[i];
+            dstp[2 * i] = (float)((px[i] - cminx) * lpi);
+            dstp[2 * i + 1] = (float)((py[i] - cminy) * lpi);
+        }
+        double M[9];
+        if (!perspective_from_points(srcp, dstp, M) || !invert3x3(M, F.hinv)) continue;
+        F.ok = true;
+        if (result) result[idx] = M2D_OK;
+    }
+    // 2. spreadMap + whole tiles (:606-639)
+    if (gminx < g.min_x || gminy < g.min_y || gmaxx > g.max_x || gmaxy > g.max_y) {
+        int rc = spread(gminx, gminy, gmaxx, gmaxy);
+        if (rc != M2D_OK) return rc;
+    }
+    const int xminInt = (int)floor((gminx - g.min_x) * g.ele_size_inv), yminInt = (int)floor((gminy - g.min_y) * g.ele_size_inv);
+    const int xmaxInt = (int)ceil((gmaxx - g.min_x) * g.ele_size_inv), ymaxInt = (int)ceil((gmaxy - g.min_y) * g.ele_size_inv);
+    if (xminInt < 0 || yminInt < 0 || xmaxInt > g.w || ymaxInt > g.h || xminInt >= xmaxInt || yminInt >= ymaxInt) return M2D_REJECTED;
+    const double minx = g.min_x + g.ele_size * xminInt, miny = g.min_y + g.ele_size * yminInt;
+    if ((long long)(xmaxInt - xminInt) * (ymaxInt - yminInt) > (1ll << 14)) { err = "m2d_render_frames: canvas larger than 16384 tiles"; return M2D_ERR_UNSUPPORTED; }
+    const int Wf = (xmaxInt - xminInt) * kEle, Hf = (ymaxInt - yminInt) * kEle;
+    // 3. the blender: band count (:707-715), prepare (:73-101)
+    int nb;
+    {
+        double blend_strength = 5;
+        float blend_width = std::sqrt(static_cast<float>(Wf * Hf)) * blend_strength / 100.f;
+        nb = static_cast<int>(std::ceil(std::log(blend_width) / std::log(2.)) - 1.);
+        if (cfg.render_bands > 0) nb = cfg.render_bands;
+        double max_len = (double)std::max(Wf, Hf);
+        nb = std::min(nb, (int)std::ceil(std::log(max_len) / std::log(2.0)));
+    }
+    if (nb < 1 || nb + 1 > kRenderMaxLevels) { err = "m2d_render_frames: band count outside [1, 15]"; return M2D_ERR_UNSUPPORTED; }
+    const int step = 1 << nb;
+    const int W = Wf + (step - Wf % step) % step, H = Hf + (step - Hf % step) % step;
+    const int s16w = cfg.render_blend == 2;
+    const size_t wbytes = s16w ? 2 : 4;
+    RenderCanvas C{};
+    C.levels = nb + 1;
+    size_t off = 0, lap_off[kRenderMaxLevels][3], wgt_off[kRenderMaxLevels];
+    for (int l = 0, cw = W, ch = H; l <= nb; l++) {
+        if (l) { cw = (cw + 1) / 2; ch = (ch + 1) / 2; }
+        C.w[l] = cw; C.h[l] = ch;
+        const size_t px = (size_t)cw * ch;
+        for (int c = 0; c < 3; c++) { lap_off[l][c] = off; off += (px * 2 + 255) & ~(size_t)255; }
+        wgt_off[l] = off; off += (px * wbytes + 255) & ~(size_t)255;
+    }
+    const size_t zero_bytes = off;
+    rnd_off16 = off; off += ((size_t)Wf * Hf * 6 + 255) & ~(size_t)255;
+    rnd_off8 = off; off += ((size_t)Wf * Hf * 3 + 255) & ~(size_t)255;
+    rnd_offmask = off; off += ((size_t)Wf * Hf + 255) & ~(size_t)255;
+    CU(cudaStreamSynchronize(stream));
+    { int rc = grow((void**)&rnd_canvas, &rnd_canvas_cap, off, false); if (rc != M2D_OK) return rc; }
+    for (int l = 0; l <= nb; l++) {
+        for (int c = 0; c < 3; c++) C.lap[l][c] = reinterpret_cast<int16_t*>(rnd_canvas + lap_off[l][c]);
+        C.wgt[l] = rnd_canvas + wgt_off[l];
+    }
+    CU(cudaMemsetAsync(rnd_canvas, 0, zero_bytes, stream));
+    // the sub-image of every frame (:103-139) and its scratch pyramid
+    std::vector<RenderJob> jobs;
+    std::vector<int> job_frame;
+    std::vector<size_t> job_bytes;
+    for (int idx = 0; idx < n; idx++) {
+        const Geo& F = geo[idx];
+        if (!F.ok) continue;
+        const int tlx = (int)((F.cwx - minx) * lpi), tly = (int)((F.cwy - miny) * lpi);   // cornersImages (:648-649)
+        const int gap = 3 * step;
+        int tnx = std::max(0, tlx - gap), tny = std::max(0, tly - gap);
+        int bnx = std::min(W, tlx + F.iw + gap), bny = std::min(H, tly + F.ih + gap);
+        tnx = (tnx >> nb) << nb; tny = (tny >> nb) << nb;
+        int width = bnx - tnx, height = bny - tny;
+        width += (step - width % step) % step;
+        height += (step - height % step) % step;
+        bnx = tnx + width; bny = tny + height;
+        const int dy = std::max(bny - H, 0), dx = std::max(bnx - W, 0);
+        tnx -= dx; bnx -= dx; tny -= dy; bny -= dy;
+        if (tlx < 0 || tly < 0 || tnx < 0 || tny < 0 || tlx < tnx || tly < tny) { err = "m2d_render_frames: frame corner outside the canvas"; return M2D_ERR_STATE; }
+        RenderJob J{};
+        memcpy(J.hinv, F.hinv, sizeof J.hinv);
+        J.iw = F.iw; J.ih = F.ih; J.left = tlx - tnx; J.top = tly - tny; J.x_tl = tnx; J.y_tl = tny; J.sw = width; J.sh = height;
+        size_t b = 0;
+        for (int l = 0; l <= nb; l++) {
+            const size_t px = (size_t)(width >> l) * (height >> l);
+            J.g_off[l] = b; b += (px * 4 + 255) & ~(size_t)255;
+            J.w_off[l] = b; b += (px * wbytes + 255) & ~(size_t)255;
+        }
+        jobs.push_back(J); job_frame.push_back(idx); job_bytes.push_back(b);
+    }
+    // 4. chunks of frames that fit the scratch budget, each blended into the canvas in feed order
+    const size_t frame_bytes = (size_t)h * stride;
+    size_t j0 = 0;
+    while (j0 < jobs.size()) {
+        size_t j1 = j0, bytes = 0;
+        int max_px = 0;
+        while (j1 < jobs.size() && j1 - j0 < 1024 && (j1 == j0 || bytes + job_bytes[j1] <= (size_t)scratch_budget)) {
+            for (int l = 0; l <= nb; l++) { jobs[j1].g_off[l] += bytes; jobs[j1].w_off[l] += bytes; }
+            bytes += job_bytes[j1];
+            max_px = std::max(max_px, jobs[j1].sw * jobs[j1].sh);
+            j1++;
+        }
+        const int m = (int)(j1 - j0);
+        CU(cudaStreamSynchronize(stream));   // the previous chunk still reads the buffers that may move below
+        { int rc = grow((void**)&rnd_scratch, &rnd_scratch_cap, bytes, false); if (rc != M2D_OK) return rc; }
+        { int rc = grow((void**)&rnd_jobs, &rnd_jobs_cap, (size_t)m * sizeof(RenderJob), false); if (rc != M2D_OK) return rc; }
+        if (!on_device) { int rc = grow((void**)&rnd_raw, &rnd_raw_cap, (size_t)m * frame_bytes + 16, false); if (rc != M2D_OK) return rc; }
+        for (int k = 0; k < m; k++) {
+            RenderJob& J = jobs[j0 + k];
+            const uint8_t* src = base + (size_t)job_frame[j0 + k] * frame_stride;
+            J.raw_stride = (int)stride;
+            if (on_device) J.raw = src;
+            else {
+                J.raw = rnd_raw + (size_t)k * frame_bytes;
+                CU(cudaMemcpyAsync(rnd_raw + (size_t)k * frame_bytes, src, frame_bytes, cudaMemcpyHostToDevice, stream));
+            }
+        }
+        CU(cudaMemcpyAsync(rnd_jobs, jobs.data() + j0, (size_t)m * sizeof(RenderJob), cudaMemcpyHostToDevice, stream));
+        const RenderJob* dj = reinterpret_cast<const RenderJob*>(rnd_jobs);
+        LAUNCHK(M2D_K_RENDER, launch_rnd_warp(dj, m, max_px, rnd_scratch, rnd_wimg, w, h, s16w, stream));
+        for (int l = 0; l < nb; l++) LAUNCHK(M2D_K_RENDER, launch_rnd_pyrdown(dj, m, max_px, rnd_scratch, l, cfg.f32_mode, s16w, stream));
+        LAUNCHK(M2D_K_RENDER, launch_rnd_blend(dj, m, rnd_scratch, C, cfg.render_blend, stream));
+        stats.frames_fused += (uint64_t)m;
+        stats.input_px += (uint64_t)m * (uint64_t)w * h;
+        j0 = j1;
+    }
+    // 5. blend(): normalise (weighted sums), restore, mask, crop (:256-300)
+    if (cfg.render_blend != 0) LAUNCHK(M2D_K_RENDER, launch_rnd_normalize(C, cfg.render_blend, stream));
+    for (int l = nb; l > 0; l--) {
+        MosaicLevel cl{{C.lap[l][0], C.lap[l][1], C.lap[l][2]}, C.w[l], C.h[l]}, fl{{C.lap[l - 1][0], C.lap[l - 1][1], C.lap[l - 1][2]}, C.w[l - 1], C.h[l - 1]};
+        LAUNCHK(M2D_K_COLLAPSE, launch_mosaic_upadd(cl, fl, stream));
+    }
+    LAUNCHK(M2D_K_RENDER, launch_rnd_final(C, s16w, Wf, Hf, reinterpret_cast<int16_t*>(rnd_canvas + rnd_off16), rnd_canvas + rnd_off8,
+                                            rnd_canvas + rnd_offmask, stream));
+    rnd_w = Wf; rnd_h = Hf; rnd_bands = nb; rnd_tx0 = xminInt + org_x; rnd_ty0 = yminInt + org_y;
+    rnd_have = true;
+    last_rect[0] = xminInt; last_rect[1] = yminInt; last_rect[2] = xmaxInt; last_rect[3] = ymaxInt;
+    if (!on_device) CU(cudaStreamSynchronize(stream));   // the caller's (pageable or pinned) frames are free again
+    return M2D_OK;
+}
+
+int m2d_render_frames(m2d_handle h, int n, const uint8_t* base, size_t frame_stride, int w, int hpx, size_t stride, const double* poses,
+                      int on_device, int* result) {
+    API_LOCK(h);
+    if (!h) return M2D_ERR_ARG;
+    return h->render_frames(n, base, frame_stride, w, hpx, stride, poses, on_device != 0, result);
+}
+
+int m2d_render_get(m2d_handle h, int16_t* result16, uint8_t* mask, int* w, int* hpx, int* num_bands, int* tile_x0, int* tile_y0) {
+    API_LOCK(h);
+    if (!h || h->type != M2D_TYPE_RENDER) return M2D_ERR_ARG;
+    m2d_map& m = *h;
+    std::string& err = m.err;
+    if (!m.rnd_have) return M2D_REJECTED;
+    if (w) *w = m.rnd_w;
+    if (hpx) *hpx = m.rnd_h;
+    if (num_bands) *num_bands = m.rnd_bands;
+    if (tile_x0) *tile_x0 = m.rnd_tx0;
+    if (tile_y0) *tile_y0 = m.rnd_ty0;
+    if (!result16 && !mask) return M2D_OK;
+    CU(cudaSetDevice(m.cfg.device));
+    const size_t px = (size_t)m.rnd_w * m.rnd_h;
+    if (result16) CU(cudaMemcpyAsync(result16, m.rnd_canvas + m.rnd_off16, px * 6, cudaMemcpyDeviceToHost, m.stream));
+    if (mask) CU(cudaMemcpyAsync(mask, m.rnd_canvas + m.rnd_offmask, px, cudaMemcpyDeviceToHost, m.stream));
+    CU(cudaStreamSynchronize(m.stream));
+    return M2D_OK;
 }
 
 int m2d_tile_bbox(m2d_handle h, int* bbox_abs) {

@@ -50,7 +50,8 @@ EXPORTS = ["m2d_config_default", "m2d_create", "m2d_create_multi", "m2d_destroy"
            "m2d_last_rect", "m2d_get_tile", "m2d_get_image", "m2d_save", "m2d_tile_bytes", "m2d_tile_state_bytes", "m2d_tile_count",
            "m2d_export_tiles", "m2d_import_tiles", "m2d_export_tiles_rect", "m2d_drop_tiles_rect", "m2d_tile_bbox", "m2d_get_image_rect", "m2d_poll_changed", "m2d_get_tile_image", "m2d_save_state", "m2d_load_state", "m2d_get_stats", "m2d_last_error",
            "m2d_launch_count", "m2d_profile", "m2d_get_kernel_times", "m2d_alloc_host", "m2d_free_host", "m2d_compute_bounds",
-           "m2d_tile_gps_corners", "m2d_reach_table", "m2d_weight_reach_table", "m2d_cell_weight_bounds", "m2d_ingest_open", "m2d_ingest_open_seeded", "m2d_ingest_abort", "m2d_ingest_push", "m2d_ingest_pause", "m2d_ingest_drain", "m2d_ingest_close", "m2d_ingest_stats"]
+           "m2d_tile_gps_corners", "m2d_reach_table", "m2d_weight_reach_table", "m2d_cell_weight_bounds", "m2d_ingest_open", "m2d_ingest_open_seeded", "m2d_ingest_abort", "m2d_ingest_push", "m2d_ingest_pause", "m2d_ingest_drain", "m2d_ingest_close", "m2d_ingest_stats",
+           "m2d_render_frames", "m2d_render_get"]
 
 _lib = None
 
@@ -137,6 +138,8 @@ def lib():
     L.m2d_free_host.argtypes = [vp]
     L.m2d_free_host.restype = None
     L.m2d_compute_bounds.argtypes = [vp, C.c_int, dp, ip, dp]
+    L.m2d_render_frames.argtypes = [vp, C.c_int, vp, C.c_size_t, C.c_int, C.c_int, C.c_size_t, dp, C.c_int, ip]
+    L.m2d_render_get.argtypes = [vp, vp, vp, ip, ip, ip, ip, ip]
     _lib = L
     return L
 
@@ -329,6 +332,13 @@ class Map2D:
             lib().m2d_ingest_abort(self._h)
         if not self._check(lib().m2d_prepare(self._h, _dptr(plane), _dptr(camera), len(poses), _dptr(poses))):
             return False
+        if self.type == self.TypeRender:
+            # Map2DRender: the worker started by prepare() takes everything queued -- the prepare-frames -- as ONE batch through
+            # renderFrames and stops (Map2DRender.cpp:419-420, 469-478, 758, 812-829); thread=False never renders (:464-467)
+            imgs = [np.asarray(f[0]) for f in pairs]
+            if threaded and imgs:
+                self.render_frames(np.stack(imgs), np.asarray([f[1] for f in pairs], np.float64))
+            return True
         if not threaded:
             return True
         self._check(lib().m2d_ingest_open_seeded(self._h, 20, len(pairs), 1))
@@ -344,6 +354,8 @@ class Map2D:
             print("Map2DB200::feed: image must be CV_8UC3")  # reference: type()!=CV_8UC3 -> false
             return False
         pose = np.ascontiguousarray(pose, np.float64).reshape(7)
+        if self.type == self.TypeRender and self.cfg.thread:
+            return True   # Map2DRender::feed only queues (Map2DRender.cpp:446-452); its worker has stopped after the first batch
         if self.cfg.thread and self._ingest_open():
             return self._check(lib().m2d_ingest_push(self._h, img.ctypes.data, img.shape[1], img.shape[0], img.strides[0], 3, _dptr(pose)))
         return self._check(lib().m2d_feed(self._h, img.ctypes.data, img.shape[1], img.shape[0], img.strides[0], _dptr(pose)))
@@ -372,6 +384,34 @@ class Map2D:
         res = np.zeros(n, np.int32)
         self._check(lib().m2d_feed_batch_ptrs(self._h, n, arr, w, h, stride, _dptr(poses), int(on_device), res.ctypes.data_as(C.POINTER(C.c_int))))
         return res
+
+    # --- Map2DRender (type 4): one batch -> one blended canvas (Map2DRender.cpp:479-760) ---------------------
+    def render_frames(self, frames, poses, on_device=False, w=None, h=None):
+        """frames: n x H x W x 3 uint8 array (host), or a device address of n packed frames with on_device=True (+ w, h).
+        Returns the per-frame status array (0 = blended, 1 = skipped like the reference: oblique view)."""
+        poses = np.ascontiguousarray(poses, np.float64).reshape(-1, 7)
+        n = len(poses)
+        if on_device:
+            ptr = int(frames)
+        else:
+            frames = np.ascontiguousarray(frames, np.uint8)
+            assert frames.ndim == 4 and frames.shape[0] == n and frames.shape[3] == 3
+            h, w = frames.shape[1:3]
+            ptr = frames.ctypes.data
+        res = np.zeros(max(n, 1), np.int32)
+        rc = lib().m2d_render_frames(self._h, n, ptr, w * h * 3, w, h, w * 3, _dptr(poses), int(on_device), res.ctypes.data_as(C.POINTER(C.c_int)))
+        self._check(rc)
+        return rc, res[:n]
+
+    def render_get(self):
+        """(result int16 HxWx3, mask uint8 HxW, num_bands, (tile_x0, tile_y0)) of the last render_frames, or None."""
+        w, h, nb, tx, ty = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        if lib().m2d_render_get(self._h, None, None, C.byref(w), C.byref(h), C.byref(nb), C.byref(tx), C.byref(ty)) != OK:
+            return None
+        res = np.zeros((h.value, w.value, 3), np.int16)
+        mask = np.zeros((h.value, w.value), np.uint8)
+        self._check(lib().m2d_render_get(self._h, res.ctypes.data, mask.ctypes.data, None, None, None, None, None))
+        return res, mask, nb.value, (tx.value, ty.value)
 
     def feed_poses(self, poses):
         """Sharded runs: frames whose pixels this shard does not need (grid growth only), see m2d_feed_poses."""

@@ -72,6 +72,26 @@ def test_adapter_thread_mode_uses_the_ingest_queue(tmp_path, typ):
 
 
 @pytest.mark.gpu
+def test_adapter_type_render(tmp_path):
+    """Map2D::create(TypeRender, thread): thread=true renders the prepare-frames as ONE batch at prepare() (the reference's
+    worker takes the whole queue through renderFrames and stops, Map2DRender.cpp:812-829, 758) and writes result.png next to
+    the process (reference: result.jpg); feed() only queues.  thread=false: feed() is false, nothing is ever rendered."""
+    exe = build(tmp_path)
+    cwd = os.getcwd()
+    os.chdir(str(tmp_path))
+    try:
+        r = run(exe, "4", str(tmp_path / "render.png"), "1", "4", "4")
+        assert r["handle"] == "1" and r["prepared"] == "1" and r["fed"] == "4" and r["oblique_accepted"] == "1" and r["saved"] == "1"
+        w, h = map(int, re.match(r"(\d+)x(\d+)", r["image"]).groups())
+        assert w > 0 and w % 256 == 0 and h % 256 == 0
+        assert open(str(tmp_path / "render.png"), "rb").read() == open(str(tmp_path / "result.png"), "rb").read()
+        r = run(exe, "4", str(tmp_path / "none.png"), "0", "4", "0")
+        assert r["prepared"] == "1" and r["fed"] == "0" and r["saved"] == "0" and r["image"] == "0x0"
+    finally:
+        os.chdir(cwd)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("typ", [1, 3])
 @pytest.mark.parametrize("threaded", ["0", "1"])
 def test_adapter_drives_two_gpus_in_one_process(tmp_path, typ, threaded):

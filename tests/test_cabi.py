@@ -47,8 +47,9 @@ def test_config_struct_layout_matches():
     m2d.lib().m2d_config_default(C.byref(c))
     assert c.scale == 1.0 and c.band_number == 5 and c.shard_count == 1 and c.resolution == 0.0
     assert c.weight_type == 0 and c.force_float == 0 and c.collect_stats == 0 and c.batch_frames == 0
-    # header struct: 2 doubles + 13 ints (+ padding to 8)
-    assert C.sizeof(m2d.Config) == 2 * 8 + 14 * 4
+    # header struct: 2 doubles + 15 ints (+ padding to 8)
+    assert C.sizeof(m2d.Config) == 2 * 8 + 16 * 4
+    assert c.render_blend == 0 and c.render_bands == 0 and c.f32_mode == 0
     assert C.sizeof(m2d.Stats) == 8 * (3 + 3 * m2d.MAX_LEVELS + 1 + 2 * m2d.MAX_LEVELS)  # ... + need_px, needw_px[MAX_LEVELS]
 
 
@@ -57,7 +58,9 @@ def test_unsupported_types_and_arguments():
     h = C.c_void_p()
     cfg = m2d.default_config()
     assert L.m2d_create(0, C.byref(cfg), C.byref(h)) == -5 and not h.value      # NoType
-    assert L.m2d_create(4, C.byref(cfg), C.byref(h)) == -5 and not h.value      # TypeRender: out of scope
+    bad = m2d.default_config(render_blend=3)
+    assert L.m2d_create(4, C.byref(bad), C.byref(h)) == -1 and not h.value      # TypeRender: unknown blend
+    assert L.m2d_create(5, C.byref(cfg), C.byref(h)) == -5 and not h.value      # no such Map2DType
     ff = m2d.default_config(force_float=1)
     assert L.m2d_create(3, C.byref(ff), C.byref(h)) == -5 and not h.value       # ForceFloat unsupported
     assert m2d.Map2D.create(0) is None                                           # null SPtr in the reference
