@@ -335,15 +335,17 @@ def measure_mode(args, m2d, torch, mode, n, w, h, seed, local_rank, stream, want
         del img
         out_pinned, out_ptr = m2d.pinned_empty((out_bytes,))
 
+        zc = bool(getattr(args, "zero_copy", False))   # experiment: the kernels sample the pinned host frames in place over PCIe
+
         def step_e2e():
             me.reset()
-            me.feed_batch(host_ptr, n, frame_bytes, w, h, w * 3, seq.poses, False)
+            me.feed_batch(host_ptr, n, frame_bytes, w, h, w * 3, seq.poses, zc)
             return me.get_image(out=out_pinned)
 
         def step_e2e_split():   # the same, with a sync between the two halves: where the time goes (not the reported number)
             me.reset()
             t0 = time.perf_counter()
-            me.feed_batch(host_ptr, n, frame_bytes, w, h, w * 3, seq.poses, False)
+            me.feed_batch(host_ptr, n, frame_bytes, w, h, w * 3, seq.poses, zc)
             me.sync()
             t1 = time.perf_counter()
             me.get_image(out=out_pinned)
@@ -364,7 +366,8 @@ def measure_mode(args, m2d, torch, mode, n, w, h, seed, local_rank, stream, want
         wall = (time.perf_counter() - t0) / reps
         ms_e2e = max(e0.elapsed_time(e1) / reps, wall * 1e3)
         feed_ms, save_ms = step_e2e_split()
-        e2e = {"value": fused * w * h / (ms_e2e * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": n * frame_bytes,
+        e2e_sha = sha(out_pinned[:out_bytes])
+        e2e = {"mosaic_sha256": e2e_sha, "zero_copy": zc,"value": fused * w * h / (ms_e2e * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": n * frame_bytes,
                "d2h_bytes_per_step": out_bytes, "ms_per_step": ms_e2e,
                "breakdown_ms": {"feed_batch_from_host": feed_ms, "collapse_and_d2h": save_ms,
                                 "h2d_gbs": n * frame_bytes / (feed_ms * 1e-3) / 1e9},
@@ -579,6 +582,7 @@ def main():
     ap.add_argument("--halo", default="peer", choices=["peer", "copy"],
                     help="N>1: how halo frames reach a rank. peer: sampled in place from the neighbour's HBM over NVLink (CUDA IPC); copy: NCCL P2P copies every step")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--zero-copy", action="store_true", help="e2e experiment: pass the pinned host frames as device pointers (sampled in place over PCIe)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

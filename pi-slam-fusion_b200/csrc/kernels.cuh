@@ -26,6 +26,9 @@ struct FrameJob {
     int wx, wy, wnx, wny;      // pyramid window inside the region (tiles, relative to the region origin)
     unsigned long long g_off[M2D_MAX_LEVELS];  // byte offset in the group scratch of level l's u8x4 Gaussian
     unsigned long long w_off[M2D_MAX_LEVELS];  // ... of level l's f32 weight plane
+    const uint8_t* pull_src;   // pull mode (pinned host frames, weights-first pipeline): device-visible address of the caller's
+                               // frame in HOST memory; `raw` is then a staging slot in HBM that mbs_pull fills with the needed
+                               // 256-byte chunks only (NULL otherwise)
 };
 
 // Tile-centric work list of a group.
@@ -80,6 +83,10 @@ struct GroupParams {
     EntryRef* etable;          // [n_entries][levels]
     int use_tma;               // pyrDown 0 -> 1 through TMA-staged shared-memory patches (M2D_TMA=0: register-window kernel)
     int cull;                  // 0: every entry of a tile is treated as competitive (collect_stats, M2D_WCULL=0)
+    // pull mode: which 256-byte chunks of every frame the image stage will read (bit per chunk, src_words words per frame)
+    uint32_t* src_bits;
+    int src_words;
+    unsigned long long frame_bytes;
 };
 
 // Tile state layout in HBM (multi-band): for each level l (side n = 256>>l): B,G,R int16 planes then f32 weight.
@@ -156,6 +163,8 @@ cudaError_t launch_mbx_pyrdown(const GroupParams& p, int image, int level, int c
 cudaError_t launch_mbs_decide(const GroupParams& p, const TileLayout& lay, cudaStream_t stream);
 cudaError_t launch_mbs_warp(const GroupParams& p, int ctas, cudaStream_t stream);                         // level-0 Gaussian, listed cells
 cudaError_t launch_mbs_lap(const GroupParams& p, const TileLayout& lay, cudaStream_t stream);
+cudaError_t launch_mbs_mark(const GroupParams& p, int ctas, cudaStream_t stream);   // pull mode: chunks of the source frames the listed cells sample
+cudaError_t launch_mbs_pull(const GroupParams& p, int ctas, cudaStream_t stream);   // ... copied from pinned host memory into the staging slots
 void make_reach_table(int levels, unsigned char lo_tab[6][6], unsigned char hi_tab[6][6]);
 void make_weight_reach_table(int levels, unsigned char lo_tab[6][6], unsigned char hi_tab[6][6]);
 cudaError_t launch_tile_copy(uint8_t* const* d_tiles, int n, uint8_t* buf, size_t tile_bytes, int to_buf, cudaStream_t stream);

@@ -209,7 +209,12 @@ struct m2d_map {
     int feed_frames(int n, const uint8_t* base, size_t frame_stride, int w, int h, size_t stride, const double* poses,
                     bool on_device, int* result, const uint8_t* const* ptrs = nullptr);
     int run_group(int n, const uint8_t* base, size_t frame_stride, int w, int h, size_t stride, const double* poses,
-                  bool on_device, int* result, const uint8_t* const* ptrs);
+                  bool on_device, int* result, const uint8_t* const* ptrs, const uint8_t* pull_base = nullptr);
+    // Pinned host frames (m2d_alloc_host / cudaHostAlloc: device-visible under UVA) are not staged whole: weighted mode samples
+    // them in place over PCIe, the weights-first multi-band pipeline pulls only the chunks its winners need (kernels_wf.cu
+    // mbs_mark / mbs_pull).  M2D_ZEROCOPY=0 keeps the cudaMemcpyAsync staging of every frame (A/B runs).
+    bool zero_copy = true;
+    bool pull_poison = false;       // M2D_PULL_POISON=1 (tests): fill the staging slots with 0xA5 before every pull
     int ensure_weight_images(int w, int h);
     int alloc_tile(uint8_t** out);
     int reserve_tiles(size_t n);
@@ -253,6 +258,8 @@ int m2d_map::init() {
     if (const char* e = getenv("M2D_SPARSE")) weights_first = atoi(e) != 0;
     if (const char* e = getenv("M2D_WCULL")) weight_cull = atoi(e) != 0;
     if (const char* e = getenv("M2D_TMA")) use_tma = atoi(e) != 0;
+    if (const char* e = getenv("M2D_ZEROCOPY")) zero_copy = atoi(e) != 0;
+    if (const char* e = getenv("M2D_PULL_POISON")) pull_poison = atoi(e) != 0;
     if (const char* e = getenv("M2D_SCRATCH_GB")) scratch_budget = std::max(0.25, atof(e)) * 1e9;
     CU(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, cfg.device));
     CU(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
@@ -616,13 +623,26 @@ int m2d_map::feed_frames(int n, const uint8_t* base, size_t frame_stride, int w,
     CU(cudaSetDevice(cfg.device));
     { int rc = ensure_weight_images(w, h); if (rc != M2D_OK) return rc; }
     struct EventScope { cudaEvent_t& e; ~EventScope() { e = nullptr; } } event_scope{input_event};   // one feed call consumes the event
-    int K = group_size(w, h, on_device);
+    // Pinned (page-locked, device-visible) host frames in batches: no whole-frame staging copies.
+    const uint8_t* pull_base = nullptr;
+    if (!on_device && zero_copy && !ptrs && n >= 8) {
+        cudaPointerAttributes a0{}, a1{};
+        const uint8_t* last = base + (size_t)(n - 1) * frame_stride + (size_t)(h - 1) * stride + (size_t)w * 3 - 1;
+        if (cudaPointerGetAttributes(&a0, base) == cudaSuccess && cudaPointerGetAttributes(&a1, last) == cudaSuccess &&
+            a0.type == cudaMemoryTypeHost && a1.type == cudaMemoryTypeHost && a0.devicePointer && a1.devicePointer &&
+            (const uint8_t*)a1.devicePointer - (const uint8_t*)a0.devicePointer == last - base)
+            pull_base = (const uint8_t*)a0.devicePointer;
+        else cudaGetLastError();
+        if (pull_base && type != M2D_TYPE_MULTIBAND) { base = pull_base; on_device = true; pull_base = nullptr; }   // weighted: sampled in place
+    }
+    int K = group_size(w, h, on_device || pull_base != nullptr);
     if (n > K) K = (n + (n + K - 1) / K - 1) / ((n + K - 1) / K);   // equal-sized groups: 500 frames at K = 480 -> 250 + 250
     int worst = M2D_OK;
     for (int i = 0; i < n; i += K) {
         int m = std::min(K, n - i);
         int rc = run_group(m, ptrs ? nullptr : base + (size_t)i * frame_stride, frame_stride, w, h, stride, poses + 7 * (size_t)i,
-                           on_device, result ? result + i : nullptr, ptrs ? ptrs + i : nullptr);
+                           on_device, result ? result + i : nullptr, ptrs ? ptrs + i : nullptr,
+                           pull_base ? pull_base + (size_t)i * frame_stride : nullptr);
         if (rc < 0) return rc;
         if (rc != M2D_OK) worst = rc;
     }
@@ -631,7 +651,7 @@ int m2d_map::feed_frames(int n, const uint8_t* base, size_t frame_stride, int w,
 
 // One group: feed() semantics for frames [0,n) in order (Map2DCPU.cpp:127-336 / MultiBandMap2DCPU.cpp:288-558).
 int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, int h, size_t stride, const double* poses,
-                       bool on_device, int* result, const uint8_t* const* ptrs) {
+                       bool on_device, int* result, const uint8_t* const* ptrs, const uint8_t* pull_base) {
     GroupCtx& c = ctx[ctx_next];
     ctx_next = (ctx_next + 1) % kCtx;
     if (c.busy) { CU(cudaEventSynchronize(c.done)); c.busy = false; }
@@ -764,15 +784,20 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
     size_t blob = off_entries + n_entries * sizeof(TileEntry) + 256;
     { size_t cap = c.blob_cap; int rc = grow((void**)&c.h_blob, &cap, blob, true); if (rc != M2D_OK) return rc;
       rc = grow((void**)&c.d_blob, &c.blob_cap, blob, false); if (rc != M2D_OK) return rc; }
-    if (!on_device) { int rc = grow((void**)&c.d_raw, &c.raw_cap, (size_t)nj * npx * 3 + 256, false); if (rc != M2D_OK) return rc; }
+    const size_t slot_bytes = (npx * 3 + 255) & ~(size_t)255;   // staging slot of one host frame (256-byte aligned: pull mode copies 256-byte chunks)
+    if (!on_device) { int rc = grow((void**)&c.d_raw, &c.raw_cap, (size_t)nj * slot_bytes + 256, false); if (rc != M2D_OK) return rc; }
     // weights-first multi-band: cell flags, competitive masks, work lists and the winner map live behind the pyramids
     // (groups of a few frames -- streaming feed() calls -- take the dense pipeline: a lone frame wins most of what it
     // covers, so there is little to skip, and the dense pipeline needs 6 launches instead of ~20)
     const bool sparse = weights_first && type == M2D_TYPE_MULTIBAND && levels <= 6 && !tiles.empty() && nj >= 4;
     const int cells_max = max_wnx * 8 * max_wny * 8;
     const int wmap_stride = (lay.px_off[levels] + 7) & ~7;
-    size_t off_flags = 0, off_cmask = 0, off_lists = 0, off_counts = 0, off_wmap = 0, off_etable = 0, flag_bytes = 0;
+    size_t off_flags = 0, off_cmask = 0, off_lists = 0, off_counts = 0, off_wmap = 0, off_etable = 0, flag_bytes = 0, off_srcbits = 0;
     int mask_words = 1;
+    // pull mode: pinned host frames, tightly packed, 16-byte aligned -> the image stage pulls the chunks it needs itself
+    const bool pull = sparse && !on_device && pull_base && !ptrs && stride == (size_t)w * 3 &&
+                      ((uintptr_t)pull_base % 16 == 0) && (frame_stride % 16 == 0);
+    const int src_words = (int)(((npx * 3 + 255) / 256 + 31) / 32);
     if (sparse) {
         if (cells_max > 65535 || nj > 65535) { err = "frame region too large for the weights-first work lists"; return M2D_ERR_UNSUPPORTED; }
         size_t max_count = 1;
@@ -786,6 +811,7 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
         off_lists = scratch; scratch += ((size_t)2 * levels * nj * cells_max * sizeof(uint32_t) + 255) & ~(size_t)255;
         off_wmap = scratch; scratch += ((size_t)tiles.size() * wmap_stride * sizeof(uint16_t) + 255) & ~(size_t)255;
         off_etable = scratch; scratch += (n_entries * levels * sizeof(EntryRef) + 255) & ~(size_t)255;
+        if (pull) { off_srcbits = scratch; scratch += ((size_t)nj * src_words * sizeof(uint32_t) + 255) & ~(size_t)255; }
         if ((size_t)nj * levels * cells_max > 0x7fffffffull) { err = "group too large for 32-bit cell flag indices"; return M2D_ERR_UNSUPPORTED; }
     }
     if (scratch) { int rc = grow((void**)&c.d_scratch, &c.scratch_cap, scratch, false); if (rc != M2D_OK) return rc; }
@@ -796,9 +822,12 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
     for (int j = 0; j < nj; j++) {
         const uint8_t* src = ptrs ? ptrs[src_index[j]] : base + (size_t)src_index[j] * frame_stride;
         if (on_device) { jobs[j].raw = src; jobs[j].raw_stride = (int)stride; }
-        else {
-            uint8_t* dst = c.d_raw + (size_t)j * npx * 3;
-            if (tight) {
+        else if (pull) {
+            jobs[j].raw = c.d_raw + (size_t)j * slot_bytes; jobs[j].raw_stride = w * 3;
+            jobs[j].pull_src = pull_base + (size_t)src_index[j] * frame_stride;
+        } else {
+            uint8_t* dst = c.d_raw + (size_t)j * slot_bytes;
+            if (tight && slot_bytes == npx * 3) {
                 if (j == 0 || src_index[j] != src_index[j - 1] + 1) {  // start of a run of consecutive accepted frames
                     int e = j;
                     while (e + 1 < nj && src_index[e + 1] == src_index[e] + 1) e++;
@@ -862,6 +891,7 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
         make_weight_reach_table(levels, p.wreach_lo, p.wreach_hi);
         p.use_tma = use_tma ? 1 : 0;
         p.cull = (weight_cull && !cfg.collect_stats) ? 1 : 0;   // the win counters follow the sequential semantics: no culling then
+        if (pull) { p.src_bits = reinterpret_cast<uint32_t*>(c.d_scratch + off_srcbits); p.src_words = src_words; p.frame_bytes = npx * 3; }
     }
 
     // Order-independent stages run on the context's own stream (they overlap the previous group's select); the
@@ -900,8 +930,14 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
         CU(cudaEventRecord(c.decided, ds));
         // 4. image work in the needed cells, back on the context's stream (only here are the frames' pixels needed)
         CU(cudaStreamWaitEvent(c.stage, c.decided, 0));
-        if (!on_device) CU(cudaStreamWaitEvent(c.stage, c.copied, 0));
+        if (!on_device && !pull) CU(cudaStreamWaitEvent(c.stage, c.copied, 0));
         if (input_event) CU(cudaStreamWaitEvent(c.stage, input_event, 0));   // frames still travelling (e.g. NCCL halo exchange)
+        if (pull) {   // the GPU fetches the chunks of the pinned host frames that the listed cells sample -- nothing else crosses PCIe
+            CU(cudaMemsetAsync(p.src_bits, 0, (size_t)nj * src_words * sizeof(uint32_t), c.stage));
+            if (pull_poison) CU(cudaMemsetAsync(c.d_raw, 0xA5, (size_t)nj * slot_bytes, c.stage));
+            LAUNCHKS(M2D_K_MISC, c.stage, launch_mbs_mark(p, ctas, c.stage));
+            LAUNCHKS(M2D_K_MISC, c.stage, launch_mbs_pull(p, ctas, c.stage));
+        }
         LAUNCHKS(M2D_K_MBS_WARP, c.stage, launch_mbs_warp(p, ctas, c.stage));
         for (int l = 0; l + 1 < levels; l++) LAUNCHKS(M2D_K_MBS_PYR, c.stage, launch_mbx_pyrdown(p, 1, l, ctas, c.stage));
         CU(cudaEventRecord(c.staged, c.stage));
