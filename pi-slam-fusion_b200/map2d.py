@@ -633,7 +633,7 @@ class Map2D:
         return int(lib().m2d_launch_count(self._h))
 
     KERNEL_CLASSES = ("weighted_fuse", "mb_warp", "mb_pyrdown", "mb_select", "collapse", "misc", "mb_pyrtail",
-                      "mbw_warp", "mbw_pyramid", "mbs_decide", "mbs_propagate", "mbs_warp", "mbs_pyramid", "mbs_lap", "mbc_bounds", "k15")
+                      "mbw_warp", "mbw_pyramid", "mbs_decide", "mbs_propagate", "mbs_warp", "mbs_pyramid", "mbs_lap", "mbc_bounds", "render")
 
     def profile(self, enable):
         return self._check(lib().m2d_profile(self._h, int(enable)))
