@@ -569,13 +569,40 @@ cudaError_t launch_bgra_paste(const PasteItem* d_items, int n_items, uint32_t* m
     return cudaGetLastError();
 }
 
-// One launch pastes every touched tile (all levels) into the zero-initialised per-level mosaics.
-__global__ void __launch_bounds__(256) mosaic_paste_kernel(const PasteItem* __restrict__ items, const __grid_constant__ TileLayout lay,
-                                                           const __grid_constant__ MosaicSet ms) {
+// One launch pastes every touched tile into the zero-initialised per-level mosaics: levels whose tile side is >= 8 px move 8 px
+// (16 bytes per plane) per thread -- int16 planes moved two bytes per thread use a sixth of what a warp's load / store path can
+// carry -- and the few px of deeper levels go through a one-warp tail kernel.
+__global__ void __launch_bounds__(256) mosaic_paste8_kernel(const PasteItem* __restrict__ items, const __grid_constant__ TileLayout lay,
+                                                            const __grid_constant__ MosaicSet ms, int vec_levels) {
     const PasteItem it = items[blockIdx.x];
-    int i = blockIdx.y * 256 + threadIdx.x;
-    if (i >= lay.px_off[lay.levels]) return;
+    int u = blockIdx.y * 256 + threadIdx.x;      // 8-px unit index over the vector levels
     int l = 0;
+    for (; l < vec_levels; l++) {
+        const int cnt = (lay.px_off[l + 1] - lay.px_off[l]) >> 3;
+        if (u < cnt) break;
+        u -= cnt;
+    }
+    if (l >= vec_levels) return;
+    const int n = kEle >> l, upr = n >> 3;
+    const int y = u / upr, x = (u - y * upr) * 8;
+    const int16_t* tl = reinterpret_cast<const int16_t*>(it.tile + lay.lap_off[l]);
+    const MosaicLevel& m = ms.lv[l];
+    const size_t s = (size_t)y * n + x, plane = (size_t)n * n;
+    const size_t o = (size_t)(it.ty * n + y) * m.w + (size_t)it.tx * n + x;
+#pragma unroll
+    for (int c = 0; c < 3; c++) *reinterpret_cast<uint4*>(m.g[c] + o) = *reinterpret_cast<const uint4*>(tl + c * plane + s);
+    if (l == 0) {
+        const float4* w = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(it.tile + lay.wgt_off[0]) + s);
+        float4* d = reinterpret_cast<float4*>(ms.w0 + o);
+        d[0] = w[0]; d[1] = w[1];
+    }
+}
+__global__ void __launch_bounds__(256) mosaic_paste_tail_kernel(const PasteItem* __restrict__ items, const __grid_constant__ TileLayout lay,
+                                                                const __grid_constant__ MosaicSet ms, int first_level) {
+    const PasteItem it = items[blockIdx.x];
+    int i = lay.px_off[first_level] + threadIdx.x;   // the levels below 8 px a side hold at most 16 + 4 + 1 px
+    if (i >= lay.px_off[lay.levels]) return;
+    int l = first_level;
     while (i >= lay.px_off[l + 1]) l++;
     i -= lay.px_off[l];
     const int n = kEle >> l;
@@ -585,12 +612,16 @@ __global__ void __launch_bounds__(256) mosaic_paste_kernel(const PasteItem* __re
     size_t o = (size_t)(it.ty * n + y) * m.w + (size_t)it.tx * n + x;
     size_t plane = (size_t)n * n;
     m.g[0][o] = tl[i]; m.g[1][o] = tl[plane + i]; m.g[2][o] = tl[2 * plane + i];
-    if (l == 0) ms.w0[o] = reinterpret_cast<const float*>(it.tile + lay.wgt_off[0])[i];
 }
 cudaError_t launch_mosaic_paste(const PasteItem* d_items, int n_items, const TileLayout& lay, const MosaicSet& ms, cudaStream_t stream) {
     if (n_items == 0) return cudaSuccess;
-    dim3 g(n_items, (lay.px_off[lay.levels] + 255) / 256);
-    mosaic_paste_kernel<<<g, 256, 0, stream>>>(d_items, lay, ms);
+    int vec_levels = 0;
+    while (vec_levels < lay.levels && (kEle >> vec_levels) >= 8) vec_levels++;
+    if (vec_levels > 0) {
+        dim3 g(n_items, ((lay.px_off[vec_levels] >> 3) + 255) / 256);
+        mosaic_paste8_kernel<<<g, 256, 0, stream>>>(d_items, lay, ms, vec_levels);
+    }
+    if (vec_levels < lay.levels) mosaic_paste_tail_kernel<<<n_items, 32, 0, stream>>>(d_items, lay, ms, vec_levels);
     return cudaGetLastError();
 }
 // Display-time collapse of ONE tile (MultiBandMap2DCPUEle::blend, MultiBandMap2DCPU.cpp:77-146): paste sub-rectangles of
@@ -650,9 +681,53 @@ __global__ void __launch_bounds__(256) mosaic_upadd_kernel(MosaicLevel C, Mosaic
         F.g[c][o] = (int16_t)sat16((int)F.g[c][o] + up);
     }
 }
+// The same, 8 consecutive fine px (16 bytes per plane) per thread: needs F.w % 8 == 0 (then C.w == F.w / 2 is a multiple of 4 and
+// every row of both levels starts 8-byte aligned).  The 8 px use coarse columns i0-1 .. i0+4 (i0 = x0 / 2) of rows r0, j, r2.
+__global__ void __launch_bounds__(256) mosaic_upadd8_kernel(MosaicLevel C, MosaicLevel F) {
+    const int x0 = (blockIdx.x * 32 + threadIdx.x) * 8, y = blockIdx.y * 8 + threadIdx.y;
+    if (x0 >= F.w || y >= F.h) return;
+    const int i0 = x0 >> 1, j = y >> 1;
+    const int cl = pyrup_axis_lo(i0 - 1, C.w), cr = pyrup_axis_hi(i0 + 4, C.w);
+    const int r0 = pyrup_axis_lo(j - 1, C.h), r2 = pyrup_axis_hi(j + 1, C.h);
+    const bool yodd = y & 1;
+    const size_t o = (size_t)y * F.w + x0;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const int16_t* G = C.g[c];
+        int h[3][8];
+        const int rr[3] = {r0, j, r2};
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            if (k == 0 && yodd) continue;        // odd rows use rows j and r2 only
+            const int16_t* q = G + (size_t)rr[k] * C.w;
+            const short4 mid = *reinterpret_cast<const short4*>(q + i0);
+            const int v[6] = {(int)q[cl], (int)mid.x, (int)mid.y, (int)mid.z, (int)mid.w, (int)q[cr]};
+#pragma unroll
+            for (int m = 0; m < 4; m++) {
+                h[k][2 * m] = v[m] + v[m + 1] * 6 + v[m + 2];
+                h[k][2 * m + 1] = (v[m + 1] + v[m + 2]) * 4;
+            }
+        }
+        int16_t* fp = F.g[c] + o;
+        uint4 fv = *reinterpret_cast<const uint4*>(fp);
+        int16_t* f = reinterpret_cast<int16_t*>(&fv);
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const int v = yodd ? (h[1][e] + h[2][e]) * 4 : (h[0][e] + h[1][e] * 6 + h[2][e]);
+            f[e] = (int16_t)sat16((int)f[e] + sat16((v + 32) >> 6));
+        }
+        *reinterpret_cast<uint4*>(fp) = fv;
+    }
+}
 cudaError_t launch_mosaic_upadd(MosaicLevel coarse, MosaicLevel fine, cudaStream_t stream) {
-    dim3 b(32, 8), g((fine.w + 31) / 32, (fine.h + 7) / 8);
-    mosaic_upadd_kernel<<<g, b, 0, stream>>>(coarse, fine);
+    dim3 b(32, 8);
+    if (fine.w % 8 == 0 && coarse.w * 2 == fine.w) {
+        dim3 g((fine.w / 8 + 31) / 32, (fine.h + 7) / 8);
+        mosaic_upadd8_kernel<<<g, b, 0, stream>>>(coarse, fine);
+    } else {
+        dim3 g((fine.w + 31) / 32, (fine.h + 7) / 8);
+        mosaic_upadd_kernel<<<g, b, 0, stream>>>(coarse, fine);
+    }
     return cudaGetLastError();
 }
 __global__ void mosaic_final_kernel(MosaicLevel m, const float* __restrict__ w0, int background, uint8_t* __restrict__ out) {
@@ -667,9 +742,33 @@ __global__ void mosaic_final_kernel(MosaicLevel m, const float* __restrict__ w0,
         out[3 * i + 2] = (uint8_t)min(max((int)m.g[2][i], 0), 255);
     }
 }
+// 4 px per thread (the mosaic is whole tiles wide): 8-byte loads per plane, one 16-byte weight load, three 4-byte stores.
+__global__ void __launch_bounds__(256) mosaic_final4_kernel(MosaicLevel m, const float* __restrict__ w0, int background, uint8_t* __restrict__ out) {
+    const size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x, n4 = ((size_t)m.w * m.h) >> 2;
+    if (q >= n4) return;
+    const size_t i = q * 4;
+    const float4 w = *reinterpret_cast<const float4*>(w0 + i);
+    const short4 b = *reinterpret_cast<const short4*>(m.g[0] + i), g = *reinterpret_cast<const short4*>(m.g[1] + i), r = *reinterpret_cast<const short4*>(m.g[2] + i);
+    const uint32_t bg = (uint32_t)min(max(background, 0), 255);
+    const float ws[4] = {w.x, w.y, w.z, w.w};
+    const int bs[4] = {b.x, b.y, b.z, b.w}, gs[4] = {g.x, g.y, g.z, g.w}, rs[4] = {r.x, r.y, r.z, r.w};
+    uint32_t px[12];
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        const bool off = ws[e] == 0.f;
+        px[3 * e] = off ? bg : (uint32_t)min(max(bs[e], 0), 255);
+        px[3 * e + 1] = off ? bg : (uint32_t)min(max(gs[e], 0), 255);
+        px[3 * e + 2] = off ? bg : (uint32_t)min(max(rs[e], 0), 255);
+    }
+    uint32_t* o = reinterpret_cast<uint32_t*>(out + 3 * i);
+    o[0] = px[0] | (px[1] << 8) | (px[2] << 16) | (px[3] << 24);
+    o[1] = px[4] | (px[5] << 8) | (px[6] << 16) | (px[7] << 24);
+    o[2] = px[8] | (px[9] << 8) | (px[10] << 16) | (px[11] << 24);
+}
 cudaError_t launch_mosaic_final(MosaicLevel m0, const float* w0, int background, uint8_t* out_bgr, cudaStream_t stream) {
     size_t n = (size_t)m0.w * m0.h;
-    mosaic_final_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(m0, w0, background, out_bgr);
+    if (n % 4 == 0 && (reinterpret_cast<uintptr_t>(out_bgr) & 3) == 0) mosaic_final4_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, stream>>>(m0, w0, background, out_bgr);
+    else mosaic_final_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(m0, w0, background, out_bgr);
     return cudaGetLastError();
 }
 
