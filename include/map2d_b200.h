@@ -336,6 +336,12 @@ int m2d_weight_reach_table(int levels, unsigned char lo[36], unsigned char hi[36
 int m2d_cell_weight_bounds(const double hinv[9], int nx, int ny, int sw, int sh, int weight_type, int level, int cx,
                            int cy, float* lo, float* hi);
 
+/* Introspection for tests: the source rectangle pull mode fetches for one 32 x 32 level-0 cell of a frame's region (csrc/bounds.h
+ * pull_cell_rect, the very code mbs_mark runs).  (X0, Y0) = region px of the cell's corner, hinv as m2d_compute_bounds returns
+ * it; rect = {lox, hix, loy, hiy}, inclusive source px, containing every tap the image warp of the cell can read (bilinear,
+ * 1/32-px rounding, BORDER_REFLECT).  M2D_REJECTED: degenerate geometry, rect is the whole frame.  Pure host arithmetic. */
+int m2d_pull_cell_rect(const double hinv[9], int X0, int Y0, int sw, int sh, int rect[4]);
+
 /* Frame buffers that the other PROCESSES of a multi-GPU job can map (CUDA IPC).  One process per GPU keeps the frames its own
  * flight lines produced in a buffer from m2d_device_alloc, exports it once (m2d_ipc_export -> 64 opaque bytes, sent to the
  * neighbours by any means), and a neighbour that owns tiles under some of those frames maps the buffer (m2d_ipc_open, peer

@@ -111,4 +111,37 @@ M2D_HD void cell_weight_bounds(const float* m, int nx, int ny, int sw, int sh, i
     *hi_out = fminf(hi, hi_loose);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Pull mode (kernels_wf.cu mbs_mark / mbs_pull): which source px the image warp of one 32 x 32 level-0 cell can read.
+// The cell's region px (X0..X0+31, Y0..Y0+31) map through the inverse homography to a convex quad (positive
+// denominators); mb_sample4 reads, for every px, the taps floor(f) and floor(f)+1 per axis of a coordinate rounded to
+// 1/32 px, folded back into the frame by BORDER_REFLECT (index -k reads k-1, index n-1+k reads n-k).  Returns the
+// inclusive source rectangle [lox, hix] x [loy, hiy] that contains every such tap: the quad's bounding box, -2 / +3 px,
+// with whatever sticks out of the frame reflected back in (the whole axis if it sticks out by more than the frame).
+// false: the denominator is not positive somewhere on the cell (or a coordinate is absurd) -> the caller takes the
+// whole frame.  Only conservativeness matters; tests/test_weights_first_host.py checks this very code (through
+// m2d_pull_cell_rect) against a brute-force walk of the taps.
+M2D_HD bool pull_cell_rect(const double* hinv, int X0, int Y0, int sw, int sh, int* lox, int* hix, int* loy, int* hiy) {
+    double x0 = 1e300, x1 = -1e300, y0 = 1e300, y1 = -1e300;
+    bool bad = false;
+    for (int k = 0; k < 4; k++) {
+        const double X = (double)(X0 + ((k & 1) ? 31 : 0)), Y = (double)(Y0 + ((k & 2) ? 31 : 0));
+        const double W = hinv[6] * X + hinv[7] * Y + hinv[8];
+        const double fx = (hinv[0] * X + hinv[1] * Y + hinv[2]) / W, fy = (hinv[3] * X + hinv[4] * Y + hinv[5]) / W;
+        if (!(W > 0.0) || !(fabs(fx) < 1e8) || !(fabs(fy) < 1e8)) bad = true;
+        x0 = fmin(x0, fx); x1 = fmax(x1, fx); y0 = fmin(y0, fy); y1 = fmax(y1, fy);
+    }
+    if (bad) { *lox = 0; *hix = sw - 1; *loy = 0; *hiy = sh - 1; return false; }
+    const int sx0 = (int)floor(x0) - 2, sx1 = (int)floor(x1) + 3, sy0 = (int)floor(y0) - 2, sy1 = (int)floor(y1) + 3;
+    int lx = sx0 > 0 ? sx0 : 0, hx = sx1 < sw - 1 ? sx1 : sw - 1, ly = sy0 > 0 ? sy0 : 0, hy = sy1 < sh - 1 ? sy1 : sh - 1;
+    if (sx0 < 0) { lx = 0; const int r = -sx0 - 1 < sw - 1 ? -sx0 - 1 : sw - 1; hx = hx > r ? hx : r; }
+    if (sx1 >= sw) { hx = sw - 1; int r = 2 * sw - 1 - sx1; r = r > 0 ? r : 0; lx = lx < r ? lx : r; }
+    if (sy0 < 0) { ly = 0; const int r = -sy0 - 1 < sh - 1 ? -sy0 - 1 : sh - 1; hy = hy > r ? hy : r; }
+    if (sy1 >= sh) { hy = sh - 1; int r = 2 * sh - 1 - sy1; r = r > 0 ? r : 0; ly = ly < r ? ly : r; }
+    if (sx0 < -sw || sx1 >= 2 * sw || lx > hx) { lx = 0; hx = sw - 1; }
+    if (sy0 < -sh || sy1 >= 2 * sh || ly > hy) { ly = 0; hy = sh - 1; }
+    *lox = lx; *hix = hx; *loy = ly; *hiy = hy;
+    return true;
+}
+
 }  // namespace m2d

@@ -329,8 +329,9 @@ cudaError_t launch_mbs_warp(const GroupParams& p, int ctas, cudaStream_t stream)
 // the (row-major, tightly packed) frame that its bilinear taps can touch; mbs_pull copies the marked chunks from the caller's
 // pinned host memory (device-visible under UVA) into the frame's staging slot in HBM with 16-byte lanes, 256 contiguous bytes
 // per half-warp -- every needed byte crosses PCIe exactly once, in full-size read requests -- and mbs_warp then samples the
-// slot as if the whole frame were there.  Conservative by construction: +-2 px around the projected cell, reflection folded in,
-// +-16 bytes for the aligned 3-word tap fetches; a cell with a non-positive denominator marks the whole frame.
+// slot as if the whole frame were there.  Conservative by construction (bounds.h pull_cell_rect: -2 / +3 px around the projected
+// cell, reflection folded in, whole frame for a non-positive denominator; proven on the CPU against a brute-force walk of the
+// taps), +-16 bytes for the aligned 3-word tap fetches.
 __global__ void __launch_bounds__(256) mbs_mark_kernel(const __grid_constant__ GroupParams p) {
     const unsigned n = p.list_count[6];
     const uint32_t* list = p.lists + (size_t)p.levels * p.list_cap;
@@ -341,33 +342,8 @@ __global__ void __launch_bounds__(256) mbs_mark_kernel(const __grid_constant__ G
         const int f = (int)(item >> 16), c = (int)(item & 0xFFFFu);
         const FrameJob& J = p.jobs[f];
         const int cw = J.wnx * 8, cy = c / cw, cx = c - cy * cw;
-        const double X = (double)(cx * 32 + J.wx * kEle + ((lane & 1) ? 31 : 0)), Y = (double)(cy * 32 + J.wy * kEle + ((lane & 2) ? 31 : 0));
-        const double W = J.hinv[6] * X + J.hinv[7] * Y + J.hinv[8];
-        double fx = (J.hinv[0] * X + J.hinv[1] * Y + J.hinv[2]) / W, fy = (J.hinv[3] * X + J.hinv[4] * Y + J.hinv[5]) / W;
-        bool bad = !(W > 0.0) || !(fabs(fx) < 1e8) || !(fabs(fy) < 1e8);
-        bad = __any_sync(0xffffffffu, bad);
-        double x0 = fx, x1 = fx, y0 = fy, y1 = fy;
-#pragma unroll
-        for (int o = 1; o <= 2; o <<= 1) {   // lanes 4k..4k+3 hold the four corners
-            x0 = fmin(x0, __shfl_xor_sync(0xffffffffu, x0, o)); x1 = fmax(x1, __shfl_xor_sync(0xffffffffu, x1, o));
-            y0 = fmin(y0, __shfl_xor_sync(0xffffffffu, y0, o)); y1 = fmax(y1, __shfl_xor_sync(0xffffffffu, y1, o));
-        }
         int lox, hix, loy, hiy;
-        if (bad) { lox = 0; hix = p.sw - 1; loy = 0; hiy = p.sh - 1; }
-        else {
-            const int sx0 = (int)floor(x0) - 2, sx1 = (int)floor(x1) + 3, sy0 = (int)floor(y0) - 2, sy1 = (int)floor(y1) + 3;
-            // BORDER_REFLECT: index -k reads k-1, index n-1+k reads n-k.  Fold what sticks out back in (whole axis if it sticks out
-            // by more than the axis).
-            lox = max(sx0, 0); hix = min(sx1, p.sw - 1); loy = max(sy0, 0); hiy = min(sy1, p.sh - 1);
-            if (sx0 < 0) { lox = 0; hix = max(hix, min(-sx0 - 1, p.sw - 1)); }
-            if (sx1 >= p.sw) { hix = p.sw - 1; lox = min(lox, max(2 * p.sw - 1 - sx1, 0)); }
-            if (sy0 < 0) { loy = 0; hiy = max(hiy, min(-sy0 - 1, p.sh - 1)); }
-            if (sy1 >= p.sh) { hiy = p.sh - 1; loy = min(loy, max(2 * p.sh - 1 - sy1, 0)); }
-            if (sx0 < -p.sw || sx1 >= 2 * p.sw) { lox = 0; hix = p.sw - 1; }
-            if (sy0 < -p.sh || sy1 >= 2 * p.sh) { loy = 0; hiy = p.sh - 1; }
-            if (lox > hix) { lox = 0; hix = p.sw - 1; }
-            if (loy > hiy) { loy = 0; hiy = p.sh - 1; }
-        }
+        pull_cell_rect(J.hinv, cx * 32 + J.wx * kEle, cy * 32 + J.wy * kEle, p.sw, p.sh, &lox, &hix, &loy, &hiy);   // bounds.h
         uint32_t* bits = p.src_bits + (size_t)f * p.src_words;
         for (int y = loy + lane; y <= hiy; y += 32) {
             long long b0 = (long long)y * J.raw_stride + 3 * lox - 16, b1 = (long long)y * J.raw_stride + 3 * hix + 2 + 16;

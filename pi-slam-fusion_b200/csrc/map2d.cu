@@ -2243,6 +2243,11 @@ int m2d_cell_weight_bounds(const double* hinv, int nx, int ny, int sw, int sh, i
     return M2D_OK;
 }
 
+int m2d_pull_cell_rect(const double* hinv, int X0, int Y0, int sw, int sh, int* rect) {
+    if (!hinv || !rect || sw < 1 || sh < 1) return M2D_ERR_ARG;
+    return pull_cell_rect(hinv, X0, Y0, sw, sh, &rect[0], &rect[1], &rect[2], &rect[3]) ? M2D_OK : M2D_REJECTED;
+}
+
 int m2d_weight_reach_table(int levels, unsigned char* lo, unsigned char* hi) {
     if (!lo || !hi || levels < 1 || levels > 6) return M2D_ERR_ARG;
     unsigned char l[6][6], h[6][6];

@@ -51,7 +51,7 @@ EXPORTS = ["m2d_config_default", "m2d_create", "m2d_create_multi", "m2d_destroy"
            "m2d_export_tiles", "m2d_import_tiles", "m2d_export_tiles_rect", "m2d_drop_tiles_rect", "m2d_tile_bbox", "m2d_get_image_rect", "m2d_poll_changed", "m2d_get_tile_image", "m2d_save_state", "m2d_load_state", "m2d_get_stats", "m2d_last_error",
            "m2d_launch_count", "m2d_profile", "m2d_get_kernel_times", "m2d_alloc_host", "m2d_free_host", "m2d_compute_bounds",
            "m2d_tile_gps_corners", "m2d_reach_table", "m2d_weight_reach_table", "m2d_cell_weight_bounds", "m2d_ingest_open", "m2d_ingest_open_seeded", "m2d_ingest_abort", "m2d_ingest_push", "m2d_ingest_pause", "m2d_ingest_drain", "m2d_ingest_close", "m2d_ingest_stats",
-           "m2d_render_frames", "m2d_render_get"]
+           "m2d_render_frames", "m2d_render_get", "m2d_pull_cell_rect"]
 
 _lib = None
 
@@ -140,6 +140,7 @@ def lib():
     L.m2d_compute_bounds.argtypes = [vp, C.c_int, dp, ip, dp]
     L.m2d_render_frames.argtypes = [vp, C.c_int, vp, C.c_size_t, C.c_int, C.c_int, C.c_size_t, dp, C.c_int, ip]
     L.m2d_render_get.argtypes = [vp, vp, vp, ip, ip, ip, ip, ip]
+    L.m2d_pull_cell_rect.argtypes = [dp, C.c_int, C.c_int, C.c_int, C.c_int, ip]
     _lib = L
     return L
 
@@ -194,6 +195,16 @@ def cell_weight_bounds(hinv, nx, ny, sw, sh, weight_type, level, cx, cy):
     if rc != OK:
         raise ValueError("m2d_cell_weight_bounds failed: %d" % rc)
     return lo.value, hi.value
+
+
+def pull_cell_rect(hinv, X0, Y0, sw, sh):
+    """(ok, (lox, hix, loy, hiy)) of m2d_pull_cell_rect: the source px pull mode fetches for the cell at region px (X0, Y0)."""
+    hinv = np.ascontiguousarray(hinv, np.float64).reshape(9)
+    r = (C.c_int * 4)()
+    rc = lib().m2d_pull_cell_rect(_dptr(hinv), int(X0), int(Y0), int(sw), int(sh), r)
+    if rc < 0:
+        raise ValueError("m2d_pull_cell_rect failed: %d" % rc)
+    return rc == OK, tuple(r)
 
 
 def map2d_update_command(plane, grid, tx, ty, gps_origin, image_name="LastTexMat"):

@@ -210,3 +210,69 @@ def test_latest_maximum_rule_equals_the_sequential_scan():
             if s > bw2 or (s == bw2 and k > best2):
                 bw2, best2 = s, int(k)
         assert (bw, best) == (bw2, best2)
+
+
+def _warp_coords(Mi, width, height):
+    """The 1/32-px integer coordinates cv::warpPerspectiveInvoker computes for a width x height destination (the oracle's
+    warp_row_coords: 64-px column blocks, X0 = M0*xb + M1*y + M2 advanced by M0*x1), vectorised in float64."""
+    x = np.arange(width)
+    xb = ((x // 64) * 64).astype(np.float64)[None, :]
+    x1 = (x % 64).astype(np.float64)[None, :]
+    y = np.arange(height, dtype=np.float64)[:, None]
+    X0 = (Mi[0, 0] * xb + Mi[0, 1] * y) + Mi[0, 2]
+    Y0 = (Mi[1, 0] * xb + Mi[1, 1] * y) + Mi[1, 2]
+    W0 = (Mi[2, 0] * xb + Mi[2, 1] * y) + Mi[2, 2]
+    W = W0 + Mi[2, 0] * x1
+    with np.errstate(divide="ignore", invalid="ignore"):
+        W = np.where(W != 0, 32.0 / W, 0.0)
+    fX = np.clip((X0 + Mi[0, 0] * x1) * W, -2147483648.0, 2147483647.0)
+    fY = np.clip((Y0 + Mi[1, 0] * x1) * W, -2147483648.0, 2147483647.0)
+    return np.rint(fX).astype(np.int64), np.rint(fY).astype(np.int64)
+
+
+def _reflect(p, n):
+    """cv::borderInterpolate(BORDER_REFLECT), vectorised (any number of folds)."""
+    p = np.mod(p, 2 * n)
+    return np.where(p >= n, 2 * n - 1 - p, p)
+
+
+@pytest.mark.parametrize("w,h,tilt,scale", [(640, 360, False, 1.0), (640, 360, True, 1.0), (1280, 720, True, 1.0), (320, 180, True, 0.5),
+                                            (640, 360, True, 2.2), (96, 64, True, 1.0)])
+def test_pull_rect_contains_every_tap(w, h, tilt, scale):
+    """Pull mode (kernels_wf.cu mbs_mark / mbs_pull) copies, for every needed 32 x 32 cell, the source rectangle
+    m2d_pull_cell_rect returns.  Walk the bilinear taps of EVERY px of EVERY cell of the frames' regions exactly as the warp
+    computes them (1/32-px rounding, saturate_cast<short>, BORDER_REFLECT) and check that none falls outside -- nadir, jittered
+    and strongly tilted frames, map scales 0.5 - 2.2, a frame smaller than its reflection margin.  Also: the rectangle is not
+    wastefully large (what is fetched stays close to what is read)."""
+    seq = synth.Sequence(10, w, h, seed=23, jitter=True)
+    poses = tilted_poses(seq, 2) if tilt else seq.poses
+    m = O.OracleMap2D.create(3, scale=scale)
+    assert m.prepare(seq.plane, seq.camera, poses[:5])
+    rects, hinv = m.compute_bounds(poses)
+    cells = waste_num = waste_den = 0
+    for k in range(seq.n):
+        if rects[k, 2] <= rects[k, 0]:
+            continue
+        nx, ny = int(rects[k, 2] - rects[k, 0]), int(rects[k, 3] - rects[k, 1])
+        X, Y = _warp_coords(hinv[k], nx * 256, ny * 256)
+        sx, sy = np.clip(X >> 5, -32768, 32767), np.clip(Y >> 5, -32768, 32767)
+        tx0, tx1, ty0, ty1 = _reflect(sx, w), _reflect(sx + 1, w), _reflect(sy, h), _reflect(sy + 1, h)
+        txlo, txhi = np.minimum(tx0, tx1), np.maximum(tx0, tx1)
+        tylo, tyhi = np.minimum(ty0, ty1), np.maximum(ty0, ty1)
+        blk = lambda a, f: f(f(a.reshape(ny * 8, 32, nx * 8, 32), axis=3), axis=1)   # noqa: E731
+        cxlo, cxhi, cylo, cyhi = blk(txlo, np.min), blk(txhi, np.max), blk(tylo, np.min), blk(tyhi, np.max)
+        for cy in range(ny * 8):
+            for cx in range(nx * 8):
+                ok, (lox, hix, loy, hiy) = m2d.pull_cell_rect(hinv[k], cx * 32, cy * 32, w, h)
+                assert 0 <= lox <= hix < w and 0 <= loy <= hiy < h
+                assert lox <= cxlo[cy, cx] and cxhi[cy, cx] <= hix and loy <= cylo[cy, cx] and cyhi[cy, cx] <= hiy, \
+                    (k, cx, cy, (lox, hix, loy, hiy), (int(cxlo[cy, cx]), int(cxhi[cy, cx]), int(cylo[cy, cx]), int(cyhi[cy, cx])))
+                cells += 1
+                inside = (sx[cy * 32:cy * 32 + 32, cx * 32:cx * 32 + 32] >= 0).all() and (sx[cy * 32:cy * 32 + 32, cx * 32:cx * 32 + 32] < w - 1).all() and \
+                    (sy[cy * 32:cy * 32 + 32, cx * 32:cx * 32 + 32] >= 0).all() and (sy[cy * 32:cy * 32 + 32, cx * 32:cx * 32 + 32] < h - 1).all()
+                if ok and inside:   # interior cells: fetched area vs the taps' own bounding box
+                    waste_num += (hix - lox + 1) * (hiy - loy + 1)
+                    waste_den += (cxhi[cy, cx] - cxlo[cy, cx] + 1) * (cyhi[cy, cx] - cylo[cy, cx] + 1)
+    assert cells > 500
+    if waste_den:
+        assert waste_num / waste_den < (1.6 if scale <= 1.0 else 2.6), waste_num / waste_den   # 5 px of margin per axis on a 32/scale-px box
