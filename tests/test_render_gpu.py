@@ -148,3 +148,23 @@ def test_render_boundary_semantics():
     rc, _ = t.render_frames(bad, seq.poses[:2])
     assert rc == 1                                  # frame size != camera size: refused like renderFrame
     t.close()
+
+
+def test_render_edge_cases():
+    """A batch of oblique frames only: the reference blends nothing onto the one tile around the origin and returns true (an
+    all-masked canvas); an empty batch is an argument error."""
+    seq = synth.Sequence(4, 320, 180, seed=3, jitter=True, fpl=3, prepare_frames=4)
+    frames = seq.frames()
+    g, o, _ = run_pair(seq)
+    poses = seq.poses.copy()
+    for k in range(seq.n):
+        poses[k, 3:] = synth._qmul(synth._qaxis((0, 1, 0), np.radians(75.0)), np.array([1.0, 0.0, 0.0, 0.0]))
+    rc_g, res_g = g.render_frames(frames, poses)
+    rc_o, res_o = o.render_frames(frames, poses)
+    assert rc_g == rc_o == 0 and np.array_equal(res_g, res_o) and (res_g == 1).all()
+    a, b = g.render_get(), o.render_get()
+    assert a[2] == b[2] and a[3] == b[3] and a[0].shape == b[0].shape == (256, 256, 3)
+    assert not a[0].any() and not a[1].any() and not b[0].any() and not b[1].any()
+    with pytest.raises(RuntimeError):
+        g.render_frames(frames[:0], poses[:0])
+    g.close()

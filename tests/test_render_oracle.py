@@ -219,3 +219,18 @@ def test_render_is_rejected_through_feed_and_needs_prepare():
     assert o.prepare(seq.plane, seq.camera, seq.prepare_poses)
     assert not o.feed(seq.frame(0), seq.poses[0])   # Map2DRender::renderFrame returns false (thread = false)
     assert o.render_get() is None
+
+
+def test_render_batch_of_oblique_frames_only_gives_a_blank_canvas():
+    """Every frame fails the 0.4 test (Map2DRender.cpp:548-557) -> min/max stay at the origin (:532) -> the one tile around the
+    origin is 'blended' from nothing: renderFrames still returns true, with an all-masked canvas."""
+    seq = _seq(n=4)
+    poses = seq.poses.copy()
+    for k in range(seq.n):
+        poses[k, 3:] = synth._qmul(synth._qaxis((0, 1, 0), np.radians(75.0)), np.array([1.0, 0.0, 0.0, 0.0]))
+    o = O.OracleMap2D(O.TYPE_RENDER)
+    assert o.prepare(seq.plane, seq.camera, seq.prepare_poses)
+    rc, res = o.render_frames(seq.frames(), poses)
+    assert rc == 0 and (res == 1).all()
+    r16, mask, nb, _ = o.render_get()
+    assert r16.shape == (256, 256, 3) and not r16.any() and not mask.any() and nb == 3
