@@ -633,7 +633,6 @@ int m2d_map::feed_frames(int n, const uint8_t* base, size_t frame_stride, int w,
             (const uint8_t*)a1.devicePointer - (const uint8_t*)a0.devicePointer == last - base)
             pull_base = (const uint8_t*)a0.devicePointer;
         else cudaGetLastError();
-        if (pull_base && type != M2D_TYPE_MULTIBAND) { base = pull_base; on_device = true; pull_base = nullptr; }   // weighted: sampled in place
     }
     int K = group_size(w, h, on_device || pull_base != nullptr);
     if (n > K) K = (n + (n + K - 1) / K - 1) / ((n + K - 1) / K);   // equal-sized groups: 500 frames at K = 480 -> 250 + 250
@@ -785,7 +784,15 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
     { size_t cap = c.blob_cap; int rc = grow((void**)&c.h_blob, &cap, blob, true); if (rc != M2D_OK) return rc;
       rc = grow((void**)&c.d_blob, &c.blob_cap, blob, false); if (rc != M2D_OK) return rc; }
     const size_t slot_bytes = (npx * 3 + 255) & ~(size_t)255;   // staging slot of one host frame (256-byte aligned: pull mode copies 256-byte chunks)
-    if (!on_device) { int rc = grow((void**)&c.d_raw, &c.raw_cap, (size_t)nj * slot_bytes + 256, false); if (rc != M2D_OK) return rc; }
+    // Pinned host frames (pull_base = their device-visible address): not staged whole where frames overlap.  A px that a single
+    // frame covers is read once either way, and SM-initiated PCIe reads are slower (38 GB/s measured) than the copy engine
+    // (48-52 GB/s), so the zero-copy paths are taken only when a touched tile is covered by >= 2.5 frames on average.
+    size_t region_tiles = 0;
+    for (const FrameJob& J : jobs) region_tiles += (size_t)J.wnx * J.wny;
+    const bool overlapping = !tiles.empty() && 2 * region_tiles >= 5 * tiles.size();
+    // weighted mode: best-first culling touches every map px once or twice -> the kernel samples the host frames in place
+    const bool inplace = !on_device && pull_base && !ptrs && overlapping && type != M2D_TYPE_MULTIBAND;
+    if (!on_device && !inplace) { int rc = grow((void**)&c.d_raw, &c.raw_cap, (size_t)nj * slot_bytes + 256, false); if (rc != M2D_OK) return rc; }
     // weights-first multi-band: cell flags, competitive masks, work lists and the winner map live behind the pyramids
     // (groups of a few frames -- streaming feed() calls -- take the dense pipeline: a lone frame wins most of what it
     // covers, so there is little to skip, and the dense pipeline needs 6 launches instead of ~20)
@@ -795,7 +802,7 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
     size_t off_flags = 0, off_cmask = 0, off_lists = 0, off_counts = 0, off_wmap = 0, off_etable = 0, flag_bytes = 0, off_srcbits = 0;
     int mask_words = 1;
     // pull mode: pinned host frames, tightly packed, 16-byte aligned -> the image stage pulls the chunks it needs itself
-    const bool pull = sparse && !on_device && pull_base && !ptrs && stride == (size_t)w * 3 &&
+    const bool pull = sparse && !on_device && pull_base && !ptrs && overlapping && stride == (size_t)w * 3 &&
                       ((uintptr_t)pull_base % 16 == 0) && (frame_stride % 16 == 0);
     const int src_words = (int)(((npx * 3 + 255) / 256 + 31) / 32);
     if (sparse) {
@@ -822,6 +829,7 @@ int m2d_map::run_group(int n, const uint8_t* base, size_t frame_stride, int w, i
     for (int j = 0; j < nj; j++) {
         const uint8_t* src = ptrs ? ptrs[src_index[j]] : base + (size_t)src_index[j] * frame_stride;
         if (on_device) { jobs[j].raw = src; jobs[j].raw_stride = (int)stride; }
+        else if (inplace) { jobs[j].raw = pull_base + (size_t)src_index[j] * frame_stride; jobs[j].raw_stride = (int)stride; }
         else if (pull) {
             jobs[j].raw = c.d_raw + (size_t)j * slot_bytes; jobs[j].raw_stride = w * 3;
             jobs[j].pull_src = pull_base + (size_t)src_index[j] * frame_stride;

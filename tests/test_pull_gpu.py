@@ -109,3 +109,25 @@ def test_pageable_frames_and_small_batches_are_staged():
         g.close()
     finally:
         m2d.free_pinned(ptr)
+
+
+@pytest.mark.parametrize("typ", [1, 3])
+def test_sparse_surveys_keep_the_staging_copies(monkeypatch, typ):
+    """Frames that barely overlap (5 % side lap: < 2.5 frames per touched tile) are read about once either way, and the copy
+    engine moves whole frames faster than the SMs can pull them: such groups stay on the staging path.  Same results."""
+    seq = synth.Sequence(12, 640, 360, seed=3, jitter=True, noise=True, along=0.95, cross=0.95, fpl=4, prepare_frames=4)
+    host, ptr = pinned_frames(seq)
+    try:
+        g, res = feed_pinned(typ, seq, host, ptr)
+        o, acc = oracle_of(typ, seq, host)
+        assert [r == 0 for r in res] == acc
+        compare_state(g, o, typ)
+        a = g.launch_count()
+        g.close()
+        monkeypatch.setenv("M2D_ZEROCOPY", "0")
+        g2, _ = feed_pinned(typ, seq, host, ptr)
+        compare_state(g2, o, typ)
+        assert a == g2.launch_count()        # no mark / pull launches were added
+        g2.close()
+    finally:
+        m2d.free_pinned(ptr)
