@@ -158,6 +158,22 @@ def _select_blend_cv2(imgs, masks, corners, W, H, nb):
     return res, mask, nb
 
 
+@pytest.mark.parametrize("blend,wt", [(1, cv2.CV_32F), (2, cv2.CV_16S)])
+def test_weighted_sum_blends_on_noise_and_exactly_nadir_frames(blend, wt):
+    """i.i.d. noise content (every rounding counts) on exactly nadir poses (affine homographies), larger frames: still the
+    real cv2.detail_MultiBandBlender bit for bit."""
+    seq = synth.Sequence(9, 320, 180, seed=11, jitter=False, noise=True, fpl=3, prepare_frames=5)
+    o = _render(blend, seq, 0, f32_mode=1)
+    res, mask, nb, _ = o.render_get()
+    b = cv2.detail_MultiBandBlender(0, nb, wt)
+    b.prepare((0, 0, res.shape[1], res.shape[0]))
+    for i in range(seq.n):
+        img, m, c = o.render_warped(i)
+        b.feed(img, m, c)
+    ref, ref_mask = b.blend(None, None)
+    assert np.array_equal(ref_mask, mask) and np.array_equal(ref, res) and mask.any()
+
+
 @pytest.mark.parametrize("bands", [0, 3])
 def test_selection_blend_equals_cv2_primitives(bands):
     seq = _seq(n=8, seed=5)
