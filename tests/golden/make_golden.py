@@ -113,6 +113,34 @@ def main():
             img2, org2 = o.get_image()
             out["oracle249"]["%s/type%d" % (name, typ)] = {"tiles": state_record(o, typ, 6), "mosaic": sha(img2),
                                                            "mosaic_origin": list(org2), "stats": o.stats()}
+    # ---- Map2DRender (type 4): the batch blender.  "render/cv2": the oracle with cv2 4.x's float association, recorded only
+    # after its weighted-sum blends (1, 2) have been found equal to the REAL cv2.detail_MultiBandBlender fed with the same warped
+    # frames, right here; "render/oracle249": the oracle's default (2.4.9) association, what the CUDA path defaults to.
+    out["render"] = {}
+    for name, kw in SEQS.items():
+        seq = synth.Sequence(**kw)
+        frames = seq.frames()
+        for blend in (0, 1, 2):
+            for mode, fam in ((1, "cv2"), (0, "oracle249")):
+                O.set_f32_mode(mode)
+                o = O.OracleMap2D(O.TYPE_RENDER, render_blend=blend)
+                assert o.prepare(seq.plane, seq.camera, seq.prepare_poses)
+                rc, res = o.render_frames(frames, seq.poses)
+                assert rc == 0
+                r16, mask, nb, org = o.render_get()
+                if mode == 1 and blend in (1, 2):
+                    b = cv2.detail_MultiBandBlender(0, nb, cv2.CV_32F if blend == 1 else cv2.CV_16S)
+                    b.prepare((0, 0, r16.shape[1], r16.shape[0]))
+                    for i in range(seq.n):
+                        w = o.render_warped(i)
+                        if w is not None:
+                            b.feed(w[0], w[1], w[2])
+                    ref, ref_mask = b.blend(None, None)
+                    assert np.array_equal(ref, r16) and np.array_equal(ref_mask, mask), "render oracle != cv2 blender (%s blend %d)" % (name, blend)
+                out["render"]["%s/blend%d/%s" % (name, blend, fam)] = {
+                    "accepted": [int(v) for v in res], "bands": nb, "origin": list(org), "shape": list(r16.shape),
+                    "result": sha(r16), "mask": sha(mask), "image8": sha(np.clip(r16, 0, 255).astype(np.uint8))}
+    O.set_f32_mode(0)
     with open(os.path.join(HERE, "golden.json"), "w") as f:
         json.dump(out, f, indent=1, sort_keys=True)
     np.savez_compressed(os.path.join(HERE, "kat.npz"), **kat)

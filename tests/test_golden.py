@@ -170,3 +170,45 @@ def test_gpu_multiband_equals_real_opencv_end_to_end(monkeypatch, pipeline, jitt
     (ig, og), (ic, oc) = g.get_image(), c.get_image()
     assert og == oc and np.array_equal(ig, ic)
     g.close()
+
+
+# ---- Map2DRender (type 4) ---------------------------------------------------------------------------------------------
+RENDER_KEYS = sorted(GOLD.get("render", {}))
+
+
+def _render_record(m, res):
+    r16, mask, nb, org = m.render_get()
+    return {"accepted": [int(v) for v in res], "bands": nb, "origin": list(org), "shape": list(r16.shape), "result": sha(r16),
+            "mask": sha(mask), "image8": sha(np.clip(r16, 0, 255).astype(np.uint8))}
+
+
+@pytest.mark.parametrize("key", RENDER_KEYS)
+def test_render_oracle_reproduces_goldens(key):
+    """tests/golden/make_golden.py recorded these only after the weighted-sum blends had been found equal to the real
+    cv2.detail_MultiBandBlender; no cv2 needed here."""
+    name, blend, fam = key.split("/")
+    seq = synth.Sequence(**GOLD["sequences"][name])
+    O.set_f32_mode(1 if fam == "cv2" else 0)
+    o = O.OracleMap2D(O.TYPE_RENDER, render_blend=int(blend[-1]))
+    assert o.prepare(seq.plane, seq.camera, seq.prepare_poses)
+    rc, res = o.render_frames(seq.frames(), seq.poses)
+    assert rc == 0 and _render_record(o, res) == GOLD["render"][key]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", RENDER_KEYS)
+def test_render_cuda_path_reproduces_goldens(key):
+    """m2d_render_frames through the C-ABI against the committed fixtures, in both float associations (f32_mode 1 = the
+    fixtures that equal the real OpenCV blender; 0 = the 2.4.9 association the library defaults to)."""
+    import pi_slam_fusion_b200.map2d as m2d
+    name, blend, fam = key.split("/")
+    seq = synth.Sequence(**GOLD["sequences"][name])
+    g = m2d.Map2D.create(m2d.Map2D.TypeRender, thread=False, render_blend=int(blend[-1]), f32_mode=1 if fam == "cv2" else 0)
+    assert g.prepare(seq.plane, seq.camera, seq.prepare_poses)
+    rc, res = g.render_frames(seq.frames(), seq.poses)
+    assert rc == 0
+    rec = _render_record(g, res)
+    assert rec == GOLD["render"][key]
+    img, _ = g.get_image()
+    assert sha(img) == rec["image8"]
+    g.close()
